@@ -1,0 +1,228 @@
+"""ctypes binding of oracle/_ref/libflipref_{golden,fast}.so (the unmodified reference engine
+driven through oracle/ref_shim.cpp).  TEST INFRASTRUCTURE ONLY: imported by tests/, by
+__graft_entry__.smoke() and by bench.py's cpu_baseline / --impl reference legs, never by the
+product package."""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+STAGES = dict(obstacles=0, liquid_sdf=1, p2g=2, extrapolate_a=3, save=4, body_force=5, pressure=6,
+              extrapolate_b=7, constrain=8, g2p=9, advance=10, tail=11)
+ARRAYS = dict(U=0, V=1, W=2, validU=3, validV=4, validW=5, liquid_phi=6, solid_phi=7,
+              weightU=8, weightV=9, weightW=10, weightC=11, savedU=12, savedV=13, savedW=14, near_solid=15)
+
+
+def lib_path(kind="golden"):
+    return os.path.join(_HERE, "_ref", f"libflipref_{kind}.so")
+
+
+def available(kind="golden"):
+    return os.path.exists(lib_path(kind))
+
+
+_libs = {}
+
+
+def _load(kind):
+    if kind in _libs:
+        return _libs[kind]
+    L = C.CDLL(lib_path(kind))
+    L.ref_create.restype = C.c_void_p
+    L.ref_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double]
+    L.ref_destroy.argtypes = [C.c_void_p]
+    L.ref_last_error.restype = C.c_char_p
+    L.ref_last_error.argtypes = [C.c_void_p]
+    L.ref_set_threads.argtypes = [C.c_int]
+    L.ref_get_threads.restype = C.c_int
+    L.ref_add_body_force.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double]
+    L.ref_set_pressure_tolerance.argtypes = [C.c_void_p, C.c_double]
+    L.ref_load_particles.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.ref_initialize.argtypes = [C.c_void_p]
+    L.ref_update.argtypes = [C.c_void_p, C.c_double]
+    for f in ("ref_num_particles", "ref_current_frame", "ref_last_substeps", "ref_pcg_iterations", "ref_num_fluid_cells"):
+        getattr(L, f).argtypes = [C.c_void_p]
+        getattr(L, f).restype = C.c_int
+    L.ref_pcg_error.argtypes = [C.c_void_p]
+    L.ref_pcg_error.restype = C.c_double
+    L.ref_liquid_sdf_radius.argtypes = [C.c_void_p]
+    L.ref_liquid_sdf_radius.restype = C.c_double
+    L.ref_get_particles.argtypes = [C.c_void_p, C.c_void_p]
+    L.ref_set_particles.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.ref_begin_frame.argtypes = [C.c_void_p, C.c_double]
+    L.ref_begin_substep.argtypes = [C.c_void_p]
+    L.ref_begin_substep.restype = C.c_double
+    L.ref_end_substep.argtypes = [C.c_void_p]
+    L.ref_end_substep.restype = C.c_int
+    L.ref_end_frame.argtypes = [C.c_void_p]
+    L.ref_stage.argtypes = [C.c_void_p, C.c_int, C.c_double]
+    L.ref_stage_time.argtypes = [C.c_void_p, C.c_int]
+    L.ref_stage_time.restype = C.c_double
+    L.ref_array_bytes.argtypes = [C.c_void_p, C.c_int]
+    L.ref_array_bytes.restype = C.c_long
+    L.ref_get_array.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.ref_set_array.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.ref_near_solid_dims.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 3
+    L.ref_update_weight_grid.argtypes = [C.c_void_p]
+    L.ref_sample_velocity.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.ref_sample_solid_phi.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    _libs[kind] = L
+    return L
+
+
+class RefEngine:
+    """One reference FluidSimulation, created headless with particles injected before initialize()."""
+
+    def __init__(self, dims, dx, pos, vel, gravity=(0.0, -25.0, 0.0), kind="golden", threads=None, tol=None):
+        self.L = _load(kind)
+        self.dims = tuple(int(d) for d in dims)
+        self.dx = float(dx)
+        if threads is not None:
+            self.L.ref_set_threads(int(threads))
+        self.h = self.L.ref_create(self.dims[0], self.dims[1], self.dims[2], self.dx)
+        self.L.ref_add_body_force(self.h, *[float(g) for g in gravity])
+        if tol is not None:
+            self.L.ref_set_pressure_tolerance(self.h, float(tol))
+        pos = np.ascontiguousarray(pos, dtype=np.float32)
+        vel = np.ascontiguousarray(vel, dtype=np.float32)
+        if pos.shape[0] > 0:
+            self._check(self.L.ref_load_particles(self.h, pos.shape[0], pos.ctypes.data, vel.ctypes.data))
+        self._check(self.L.ref_initialize(self.h))
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError(self.L.ref_last_error(self.h).decode())
+
+    def close(self):
+        if self.h:
+            self.L.ref_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- whole frames through the public API
+    def update(self, dt):
+        self._check(self.L.ref_update(self.h, float(dt)))
+
+    @property
+    def num_particles(self):
+        return self.L.ref_num_particles(self.h)
+
+    def particles(self):
+        a = np.empty((self.num_particles, 6), dtype=np.float32)
+        self.L.ref_get_particles(self.h, a.ctypes.data)
+        return a
+
+    def set_particles(self, aos):
+        aos = np.ascontiguousarray(aos, dtype=np.float32)
+        assert self.L.ref_set_particles(self.h, aos.shape[0], aos.ctypes.data) == 0
+
+    @property
+    def pcg_iterations(self):
+        return self.L.ref_pcg_iterations(self.h)
+
+    @property
+    def pcg_error(self):
+        return self.L.ref_pcg_error(self.h)
+
+    @property
+    def num_fluid_cells(self):
+        return self.L.ref_num_fluid_cells(self.h)
+
+    @property
+    def radius(self):
+        return self.L.ref_liquid_sdf_radius(self.h)
+
+    @property
+    def substeps(self):
+        return self.L.ref_last_substeps(self.h)
+
+    # ---- stage-wise stepping
+    def begin_frame(self, dt):
+        self.L.ref_begin_frame(self.h, float(dt))
+
+    def begin_substep(self):
+        return self.L.ref_begin_substep(self.h)
+
+    def end_substep(self):
+        return bool(self.L.ref_end_substep(self.h))
+
+    def end_frame(self):
+        self.L.ref_end_frame(self.h)
+
+    def stage(self, name, dt):
+        self._check(self.L.ref_stage(self.h, STAGES[name], float(dt)))
+        return self.L.ref_stage_time(self.h, STAGES[name])
+
+    def shape_of(self, name):
+        I, J, K = self.dims
+        if name in ("U", "validU", "weightU", "savedU"):
+            return (K, J, I + 1)
+        if name in ("V", "validV", "weightV", "savedV"):
+            return (K, J + 1, I)
+        if name in ("W", "validW", "weightW", "savedW"):
+            return (K + 1, J, I)
+        if name in ("liquid_phi", "weightC"):
+            return (K, J, I)
+        if name == "solid_phi":
+            return (K + 1, J + 1, I + 1)
+        if name == "near_solid":
+            gi, gj, gk = C.c_int(), C.c_int(), C.c_int()
+            self.L.ref_near_solid_dims(self.h, C.byref(gi), C.byref(gj), C.byref(gk))
+            return (gk.value, gj.value, gi.value)
+        raise KeyError(name)
+
+    def array(self, name):
+        """Arrays come back shaped (k, j, i) — i fastest, as in Array3d (array3d.h:425-428)."""
+        which = ARRAYS[name]
+        dt = np.uint8 if name.startswith("valid") or name == "near_solid" else np.float32
+        shape = self.shape_of(name)
+        a = np.empty(shape, dtype=dt)
+        assert self.L.ref_array_bytes(self.h, which) == a.nbytes, (name, self.L.ref_array_bytes(self.h, which), a.nbytes)
+        assert self.L.ref_get_array(self.h, which, a.ctypes.data) == 0
+        return a
+
+    def set_array(self, name, a):
+        which = ARRAYS[name]
+        dt = np.uint8 if name.startswith("valid") or name == "near_solid" else np.float32
+        a = np.ascontiguousarray(a, dtype=dt)
+        assert self.L.ref_array_bytes(self.h, which) == a.nbytes
+        assert self.L.ref_set_array(self.h, which, a.ctypes.data) == 0
+
+    def update_weight_grid(self):
+        self.L.ref_update_weight_grid(self.h)
+
+    def sample_velocity(self, pos):
+        pos = np.ascontiguousarray(pos, dtype=np.float32)
+        out = np.empty_like(pos)
+        self.L.ref_sample_velocity(self.h, pos.shape[0], pos.ctypes.data, out.ctypes.data)
+        return out
+
+    def sample_solid_phi(self, pos):
+        pos = np.ascontiguousarray(pos, dtype=np.float32)
+        out = np.empty(pos.shape[0], dtype=np.float32)
+        self.L.ref_sample_solid_phi(self.h, pos.shape[0], pos.ctypes.data, out.ctypes.data)
+        return out
+
+    def step_stagewise(self, dt_frame, on_stage=None):
+        """One frame, stage by stage, equivalent to update(dt_frame). on_stage(name, dt_sub, self)
+        is called after every stage. Returns the list of substep lengths."""
+        self.begin_frame(dt_frame)
+        dts = []
+        more = True
+        while more:
+            dt = self.begin_substep()
+            dts.append(dt)
+            for name in ("obstacles", "liquid_sdf", "p2g", "extrapolate_a", "save", "body_force", "pressure",
+                         "extrapolate_b", "constrain", "g2p", "advance", "tail"):
+                self.stage(name, dt)
+                if on_stage is not None:
+                    on_stage(name, dt, self)
+            more = self.end_substep()
+        self.end_frame()
+        return dts
