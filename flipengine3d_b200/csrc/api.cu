@@ -1,0 +1,547 @@
+// C-ABI of libflip_b200.so (include/flip_b200.h): context lifetime, configuration, the frame /
+// substep loop of FluidSimulation::update and the stage dispatcher.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <new>
+#include "flip_internal.h"
+
+using namespace flip;
+
+namespace flip {
+void pressure_to_float(flip_ctx *c, float *devOut);
+}
+
+static thread_local std::string g_createError;
+
+template <class F>
+static int guarded(flip_ctx *c, F &&f) {
+    try {
+        if (c) cudaSetDevice(c->device);
+        f();
+        return FLIP_OK;
+    } catch (const CudaError &e) {
+        if (c) c->lastError = e.msg; else g_createError = e.msg;
+        return FLIP_ERR_CUDA;
+    } catch (const ApiError &e) {
+        if (c) c->lastError = e.msg; else g_createError = e.msg;
+        return e.code;
+    } catch (const std::bad_alloc &) {
+        if (c) c->lastError = "host allocation failed"; else g_createError = "host allocation failed";
+        return FLIP_ERR_RUNTIME;
+    }
+}
+
+template <class T>
+static void dev_alloc(T *&p, size_t n, bool zero = true) {
+    FLIP_CUDA_CHECK(cudaMalloc(&p, sizeof(T) * (n + 64)));
+    if (zero) FLIP_CUDA_CHECK(cudaMemset(p, 0, sizeof(T) * (n + 64)));
+}
+
+static void free_all(flip_ctx *c) {
+    cudaSetDevice(c->device);
+    particles_free(c);
+    pressure_free(c);
+    cudaFree(c->cellCount); cudaFree(c->cellStart); cudaFree(c->cellStartA); cudaFree(c->scanTemp);
+    cudaFree(c->U); cudaFree(c->V); cudaFree(c->W); cudaFree(c->sU); cudaFree(c->sV); cudaFree(c->sW);
+    cudaFree(c->validU); cudaFree(c->validV); cudaFree(c->validW); cudaFree(c->status);
+    cudaFree(c->frontier[0]); cudaFree(c->frontier[1]);
+    cudaFree(c->phiL); cudaFree(c->phiS); cudaFree(c->wU); cudaFree(c->wV); cudaFree(c->wW);
+    cudaFree(c->nearSolid); cudaFree(c->pressure);
+    cudaFree(c->dS);
+    if (c->hS) cudaFreeHost(c->hS);
+    if (c->eventsCreated) for (auto &e : c->evStage) cudaEventDestroy(e);
+    if (c->stream) cudaStreamDestroy(c->stream);
+}
+
+extern "C" {
+
+const char *flip_create_error(void) { return g_createError.c_str(); }
+
+int flip_create(flip_ctx **out, int isize, int jsize, int ksize, double dx, int device) {
+    if (!out) return FLIP_ERR_RUNTIME;
+    *out = nullptr;
+    // FluidSimulation::FluidSimulation: dims and dx must be positive (fluidsimulation.cpp:44-56)
+    if (isize <= 0 || jsize <= 0 || ksize <= 0 || !(dx > 0.0)) {
+        g_createError = "Error: dimensions and cell size must be greater than 0.";
+        return FLIP_ERR_DOMAIN;
+    }
+    if ((long long)(isize + 1) * (jsize + 1) * (long long)(ksize + 1) > 2000000000ll) {
+        g_createError = "grid too large for 32-bit cell indices";
+        return FLIP_ERR_DOMAIN;
+    }
+    flip_ctx *c = new (std::nothrow) flip_ctx();
+    if (!c) return FLIP_ERR_RUNTIME;
+    c->device = device;
+    int rc = guarded(nullptr, [&] {
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0)
+            throw CudaError(std::string("no CUDA device available (") + cudaGetErrorString(e) +
+                            "): libflip_b200 has no CPU fallback");
+        if (device < 0 || device >= ndev) throw ApiError(FLIP_ERR_OUT_OF_RANGE, "bad CUDA device ordinal");
+        FLIP_CUDA_CHECK(cudaSetDevice(device));
+        Dims &d = c->d;
+        d.I = isize; d.J = jsize; d.K = ksize; d.dx = dx;
+        d.nU = (isize + 1) * jsize * ksize;
+        d.nV = isize * (jsize + 1) * ksize;
+        d.nW = isize * jsize * (ksize + 1);
+        d.nC = isize * jsize * ksize;
+        d.nN = (isize + 1) * (jsize + 1) * (ksize + 1);
+        c->liquidRadius = 0.5 * 1.0 * dx * sqrt(3.0);   // _initializeParticleRadii fluidsimulation.cpp:2649
+        FLIP_CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        for (auto &e2 : c->evStage) FLIP_CUDA_CHECK(cudaEventCreate(&e2));
+        c->eventsCreated = true;
+        dev_alloc(c->U, d.nU); dev_alloc(c->V, d.nV); dev_alloc(c->W, d.nW);
+        dev_alloc(c->sU, d.nU); dev_alloc(c->sV, d.nV); dev_alloc(c->sW, d.nW);
+        dev_alloc(c->validU, d.nU); dev_alloc(c->validV, d.nV); dev_alloc(c->validW, d.nW);
+        size_t nmax = std::max(d.nU, std::max(d.nV, d.nW));
+        dev_alloc(c->status, nmax);
+        dev_alloc(c->frontier[0], nmax); dev_alloc(c->frontier[1], nmax);
+        dev_alloc(c->phiL, d.nC); dev_alloc(c->phiS, d.nN);
+        dev_alloc(c->wU, d.nU); dev_alloc(c->wV, d.nV); dev_alloc(c->wW, d.nW);
+        dev_alloc(c->cellCount, (size_t)d.nC + 1); dev_alloc(c->cellStart, (size_t)d.nC + 1);
+        dev_alloc(c->cellStartA, (size_t)d.nC + 1);
+        dev_alloc(c->dS, 1);
+        FLIP_CUDA_CHECK(cudaMallocHost(&c->hS, sizeof(DeviceScalars)));
+        memset(c->hS, 0, sizeof(DeviceScalars));
+        pressure_alloc(c);
+        // phi_liquid starts at the "no particles" value 3dx (particlelevelset.cpp:295-301)
+        std::vector<float> init((size_t)d.nC, (float)(3.0 * dx));
+        FLIP_CUDA_CHECK(cudaMemcpy(c->phiL, init.data(), sizeof(float) * d.nC, cudaMemcpyHostToDevice));
+    });
+    if (rc != FLIP_OK) {
+        free_all(c);
+        delete c;
+        return rc;
+    }
+    *out = c;
+    return FLIP_OK;
+}
+
+void flip_destroy(flip_ctx *c) {
+    if (!c) return;
+    free_all(c);
+    delete c;
+}
+
+const char *flip_last_error(const flip_ctx *c) { return c ? c->lastError.c_str() : "null context"; }
+
+int flip_add_body_force(flip_ctx *c, double fx, double fy, double fz) {
+    // _constantBodyForces is summed by _getConstantBodyForce (fluidsimulation.cpp:3436-3444), in vec3 floats
+    return guarded(c, [&] {
+        c->gravity[0] = (double)((float)c->gravity[0] + (float)fx);
+        c->gravity[1] = (double)((float)c->gravity[1] + (float)fy);
+        c->gravity[2] = (double)((float)c->gravity[2] + (float)fz);
+    });
+}
+
+int flip_set_pic_flip_ratio(flip_ctx *c, double r) {
+    return guarded(c, [&] {
+        if (r < 0.0 || r > 1.0) throw ApiError(FLIP_ERR_DOMAIN, "Error: PICFLIP ratio must be in range [0.0, 1.0].");
+        c->ratioPICFLIP = r;
+    });
+}
+int flip_set_cfl(flip_ctx *c, double cfl) {
+    return guarded(c, [&] {
+        if (cfl < 1.0) throw ApiError(FLIP_ERR_DOMAIN, "Error: CFL must be greater than or equal to 1.");
+        c->CFL = cfl;
+        c->extrapolationLayers = (int)ceil(cfl) + 2;
+    });
+}
+int flip_set_substep_limits(flip_ctx *c, int mn, int mx) {
+    return guarded(c, [&] {
+        if (mn < 1 || mx < mn || mx > 8) throw ApiError(FLIP_ERR_DOMAIN, "Error: bad time steps per frame range.");
+        c->minSubsteps = mn; c->maxSubsteps = mx;
+    });
+}
+int flip_set_pressure_solver(flip_ctx *c, double tol, double acc, int maxIter) {
+    return guarded(c, [&] {
+        if (!(tol > 0) || maxIter < 1) throw ApiError(FLIP_ERR_DOMAIN, "Error: bad pressure solver parameters.");
+        c->pressureTol = tol; c->pressureAcceptableTol = acc; c->pressureMaxIter = maxIter;
+    });
+}
+int flip_set_preconditioner(flip_ctx *c, int kind) {
+    return guarded(c, [&] {
+        if (kind < 0 || kind > 1) throw ApiError(FLIP_ERR_OUT_OF_RANGE, "unknown preconditioner");
+        c->preconditioner = kind;
+    });
+}
+
+int flip_load_particles(flip_ctx *c, int n, const float *pos, const float *vel) {
+    return guarded(c, [&] {
+        if (n < 0) throw ApiError(FLIP_ERR_OUT_OF_RANGE, "negative particle count");
+        if (n == 0) return;
+        c->loadQueuePos.insert(c->loadQueuePos.end(), pos, pos + 3ll * n);
+        c->loadQueueVel.insert(c->loadQueueVel.end(), vel, vel + 3ll * n);
+    });
+}
+
+int flip_add_fluid_box(flip_ctx *c, const double lo[3], const double hi[3], const double vel[3]) {
+    return guarded(c, [&] {
+        flip_ctx::FluidBox b;
+        for (int a = 0; a < 3; a++) { b.lo[a] = lo[a]; b.hi[a] = hi[a]; b.vel[a] = vel ? vel[a] : 0.0; }
+        c->fluidBoxes.push_back(b);
+    });
+}
+
+int flip_add_marker_particle(flip_ctx *c, const float p[3], const float v[3]) {
+    return guarded(c, [&] {
+        // before initialize the particle joins the load queue; afterwards it is appended to the store
+        if (!c->initialized) {
+            c->loadQueuePos.insert(c->loadQueuePos.end(), p, p + 3);
+            c->loadQueueVel.insert(c->loadQueueVel.end(), v, v + 3);
+            return;
+        }
+        int n = c->np;
+        std::vector<float> aos((size_t)6 * (n + 1));
+        particles_download_aos(c, aos.data());
+        float *a = aos.data() + 6ll * n;
+        a[0] = p[0]; a[1] = p[1]; a[2] = p[2]; a[3] = v[0]; a[4] = v[1]; a[5] = v[2];
+        particles_upload_aos(c, aos.data(), n + 1);
+    });
+}
+
+int flip_set_solid_sdf(flip_ctx *c, const float *phi) {
+    return guarded(c, [&] {
+        c->hostSolidPhi.assign(phi, phi + c->d.nN);
+        c->userSolidPhi = true;
+        if (c->initialized) {
+            // re-derive the static inputs
+            const Dims &d = c->d;
+            std::vector<float> wU, wV, wW, wC;
+            build_weights(d, c->hostSolidPhi, wU, wV, wW, wC);
+            std::vector<unsigned char> ns;
+            build_near_solid(d, c->hostSolidPhi, c->nearSolidFactor, c->solidExactBand, c->CFL, ns, c->nsI, c->nsJ, c->nsK);
+            FLIP_CUDA_CHECK(cudaMemcpy(c->phiS, c->hostSolidPhi.data(), sizeof(float) * d.nN, cudaMemcpyHostToDevice));
+            FLIP_CUDA_CHECK(cudaMemcpy(c->wU, wU.data(), sizeof(float) * d.nU, cudaMemcpyHostToDevice));
+            FLIP_CUDA_CHECK(cudaMemcpy(c->wV, wV.data(), sizeof(float) * d.nV, cudaMemcpyHostToDevice));
+            FLIP_CUDA_CHECK(cudaMemcpy(c->wW, wW.data(), sizeof(float) * d.nW, cudaMemcpyHostToDevice));
+            cudaFree(c->nearSolid); c->nearSolid = nullptr;
+            dev_alloc(c->nearSolid, ns.size());
+            FLIP_CUDA_CHECK(cudaMemcpy(c->nearSolid, ns.data(), ns.size(), cudaMemcpyHostToDevice));
+        }
+    });
+}
+
+// Seeds the queued fluid boxes: 8 particles per cell whose centre lies in the box, at (+-dx/4)^3
+// around the cell centre (FluidSimulation::_addNewFluidCells, fluidsimulation.cpp:4528-4559, with
+// jitter factor 0 the jitter amplitude is 0.25*(0-1e-3)*dx: omitted).
+static void seed_boxes(flip_ctx *c, std::vector<float> &pos, std::vector<float> &vel) {
+    const Dims &d = c->d;
+    double q = 0.25 * d.dx;
+    for (auto &b : c->fluidBoxes) {
+        for (int k = 0; k < d.K; k++) for (int j = 0; j < d.J; j++) for (int i = 0; i < d.I; i++) {
+            double cx = (i + 0.5) * d.dx, cy = (j + 0.5) * d.dx, cz = (k + 0.5) * d.dx;
+            if (cx < b.lo[0] || cx >= b.hi[0] || cy < b.lo[1] || cy >= b.hi[1] || cz < b.lo[2] || cz >= b.hi[2]) continue;
+            for (int s = 0; s < 8; s++) {
+                pos.push_back((float)(cx + ((s & 1) ? q : -q)));
+                pos.push_back((float)(cy + ((s & 2) ? q : -q)));
+                pos.push_back((float)(cz + ((s & 4) ? q : -q)));
+                vel.push_back((float)b.vel[0]); vel.push_back((float)b.vel[1]); vel.push_back((float)b.vel[2]);
+            }
+        }
+    }
+    c->fluidBoxes.clear();
+}
+
+int flip_initialize(flip_ctx *c) {
+    return guarded(c, [&] {
+        if (c->initialized) throw ApiError(FLIP_ERR_RUNTIME, "Error: FluidSimulation is already initialized.");
+        const Dims &d = c->d;
+        if (!c->userSolidPhi) build_box_solid_sdf(d, c->hostSolidPhi);
+        std::vector<float> wU, wV, wW, wC;
+        build_weights(d, c->hostSolidPhi, wU, wV, wW, wC);
+        std::vector<unsigned char> ns;
+        build_near_solid(d, c->hostSolidPhi, c->nearSolidFactor, c->solidExactBand, c->CFL, ns, c->nsI, c->nsJ, c->nsK);
+        FLIP_CUDA_CHECK(cudaMemcpy(c->phiS, c->hostSolidPhi.data(), sizeof(float) * d.nN, cudaMemcpyHostToDevice));
+        FLIP_CUDA_CHECK(cudaMemcpy(c->wU, wU.data(), sizeof(float) * d.nU, cudaMemcpyHostToDevice));
+        FLIP_CUDA_CHECK(cudaMemcpy(c->wV, wV.data(), sizeof(float) * d.nV, cudaMemcpyHostToDevice));
+        FLIP_CUDA_CHECK(cudaMemcpy(c->wW, wW.data(), sizeof(float) * d.nW, cudaMemcpyHostToDevice));
+        dev_alloc(c->nearSolid, ns.size());
+        FLIP_CUDA_CHECK(cudaMemcpy(c->nearSolid, ns.data(), ns.size(), cudaMemcpyHostToDevice));
+        // _loadParticles (fluidsimulation.cpp:2791) + queued fluid boxes
+        seed_boxes(c, c->loadQueuePos, c->loadQueueVel);
+        int n = (int)(c->loadQueuePos.size() / 3);
+        particles_upload_split(c, c->loadQueuePos.data(), c->loadQueueVel.data(), n);
+        c->loadQueuePos.clear(); c->loadQueuePos.shrink_to_fit();
+        c->loadQueueVel.clear(); c->loadQueueVel.shrink_to_fit();
+        c->initialized = true;
+    });
+}
+
+// ---- frame / substep bookkeeping (fluidsimulation.cpp:5768-5824) -------------------------------
+
+static double max_particle_speed(flip_ctx *c) {
+    // _getMaximumMarkerParticleSpeed (:5553-5565): sqrt(max dot(v,v)); the max over survivors is
+    // maintained by the sort's gather kernel
+    unsigned int bits = c->hS->maxSpeedSqBits;
+    float f;
+    memcpy(&f, &bits, sizeof(float));
+    return sqrt((double)f);
+}
+
+static double next_time_step(flip_ctx *c, double dt) {
+    // _calculateNextTimeStep (:5593-5613)
+    double maxu;
+    if (c->currentFrame == 0 && c->substepNumber == 0) {
+        // _predictMaximumMarkerParticleSpeed (:5529-5551): queued objects are already seeded here, so
+        // only the body-force term remains: |g| * dt, with |g| the float vec3 length
+        float gx = (float)c->gravity[0], gy = (float)c->gravity[1], gz = (float)c->gravity[2];
+        float len = sqrtf(gx * gx + gy * gy + gz * gz);
+        maxu = (double)len * dt;
+    } else {
+        maxu = max_particle_speed(c);
+    }
+    double eps = 1e-6;
+    return c->CFL * c->d.dx / (maxu + eps);
+}
+
+int flip_begin_frame(flip_ctx *c, double dt) {
+    return guarded(c, [&] {
+        if (!c->initialized) throw ApiError(FLIP_ERR_RUNTIME, "Error: FluidSimulation must be initialized before update.");
+        if (dt < 0.0) throw ApiError(FLIP_ERR_DOMAIN, "Error: delta time must be greater than or equal to 0.");
+        double epsdt = 1e-6;
+        dt = std::max(dt, epsdt);
+        c->frameDt = dt;
+        c->frameRemaining = dt;
+        c->substepNumber = 0;
+        c->stats.clear();
+    });
+}
+
+int flip_begin_substep(flip_ctx *c, double *out) {
+    return guarded(c, [&] {
+        double substepTime = c->frameDt / (double)c->minSubsteps;
+        double step = fmin(next_time_step(c, c->frameDt), c->frameRemaining);
+        double timeCompleted = c->frameDt - c->frameRemaining;
+        double stepLimit = (c->substepNumber + 1) * substepTime;
+        if (timeCompleted + step > stepLimit) step = fmin(substepTime, c->frameRemaining);
+        if (c->substepNumber == c->maxSubsteps - 1) step = c->frameRemaining;
+        c->frameRemaining -= step;
+        c->substepDt = step;
+        memset(&c->cur, 0, sizeof(c->cur));
+        c->cur.dt = step;
+        c->cur.pcg_converged = 1;
+        if (out) *out = step;
+    });
+}
+
+static void run_stage(flip_ctx *c, int stage, double dt) {
+    FLIP_CUDA_CHECK(cudaEventRecord(c->evStage[stage], c->stream));
+    switch (stage) {
+        case FLIP_STAGE_OBSTACLES: break;                    // static scene
+        case FLIP_STAGE_LIQUID_SDF: stage_liquid_sdf(c); break;
+        case FLIP_STAGE_P2G: stage_p2g(c); break;
+        case FLIP_STAGE_EXTRAPOLATE_A: if (c->np > 0) stage_extrapolate(c); break;   // :3262 guards on !empty()
+        case FLIP_STAGE_SAVE: stage_save(c); break;
+        case FLIP_STAGE_BODY_FORCE: stage_body_force(c, dt); break;
+        case FLIP_STAGE_PRESSURE: stage_pressure(c, dt); break;
+        case FLIP_STAGE_EXTRAPOLATE_B: stage_extrapolate(c); break;
+        case FLIP_STAGE_CONSTRAIN: stage_constrain(c); break;
+        case FLIP_STAGE_G2P: stage_g2p(c); break;
+        case FLIP_STAGE_ADVANCE: stage_advance(c, dt); break;
+        case FLIP_STAGE_TAIL: break;
+        default: throw ApiError(FLIP_ERR_OUT_OF_RANGE, "bad stage id");
+    }
+    FLIP_CUDA_CHECK(cudaEventRecord(c->evStage[stage + 1], c->stream));
+}
+
+int flip_run_stage(flip_ctx *c, int stage, double dt) {
+    return guarded(c, [&] {
+        if (!c->initialized) throw ApiError(FLIP_ERR_RUNTIME, "Error: FluidSimulation must be initialized before update.");
+        if (stage < 0 || stage >= FLIP_NUM_STAGES) throw ApiError(FLIP_ERR_OUT_OF_RANGE, "bad stage id");
+        run_stage(c, stage, dt);
+        FLIP_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, c->evStage[stage], c->evStage[stage + 1]);
+        c->stageMs[stage] = ms;
+    });
+}
+
+int flip_end_substep(flip_ctx *c, int *more) {
+    return guarded(c, [&] {
+        c->cur.particles = c->np;
+        c->cur.removed_solid = c->hS->removedSolid;
+        c->cur.removed_crowded = c->hS->removedCrowded;
+        c->cur.removed_fast = c->hS->removedFast;
+        c->stats.push_back(c->cur);
+        c->substepNumber++;
+        if (more) *more = c->frameRemaining > 1e-9 ? 1 : 0;
+    });
+}
+
+int flip_end_frame(flip_ctx *c) {
+    return guarded(c, [&] { c->currentFrame++; });
+}
+
+int flip_update(flip_ctx *c, double dt) {
+    int rc = flip_begin_frame(c, dt);
+    if (rc) return rc;
+    return guarded(c, [&] {
+        int more = 1;
+        while (more) {
+            double step = 0;
+            int r2 = flip_begin_substep(c, &step);
+            if (r2) throw ApiError(r2, c->lastError);
+            // all stages are enqueued back to back; the only host syncs are the scalar read-backs
+            // inside the pressure stage and at the end of the advance stage
+            for (int s = 0; s < FLIP_NUM_STAGES; s++) run_stage(c, s, step);
+            FLIP_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+            for (int s = 0; s < FLIP_NUM_STAGES; s++) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, c->evStage[s], c->evStage[s + 1]);
+                c->stageMs[s] = ms;
+            }
+            r2 = flip_end_substep(c, &more);
+            if (r2) throw ApiError(r2, c->lastError);
+        }
+        c->currentFrame++;
+    });
+}
+
+int flip_get_current_frame(const flip_ctx *c, int *f) { if (!c || !f) return FLIP_ERR_RUNTIME; *f = c->currentFrame; return FLIP_OK; }
+int flip_get_num_substeps(const flip_ctx *c, int *n) { if (!c || !n) return FLIP_ERR_RUNTIME; *n = (int)c->stats.size(); return FLIP_OK; }
+int flip_get_step_stats(const flip_ctx *c, int s, flip_step_stats *out) {
+    if (!c || !out) return FLIP_ERR_RUNTIME;
+    if (s < 0 || s >= (int)c->stats.size()) return FLIP_ERR_OUT_OF_RANGE;
+    *out = c->stats[s];
+    return FLIP_OK;
+}
+int flip_get_num_particles(const flip_ctx *c, int *n) { if (!c || !n) return FLIP_ERR_RUNTIME; *n = c->np; return FLIP_OK; }
+
+int flip_get_particles(flip_ctx *c, float *aos, int capacity) {
+    return guarded(c, [&] {
+        if (capacity < c->np) throw ApiError(FLIP_ERR_OUT_OF_RANGE, "Error: particle buffer too small.");
+        particles_download_aos(c, aos);
+    });
+}
+int flip_set_particles(flip_ctx *c, int n, const float *aos) {
+    return guarded(c, [&] {
+        if (!c->initialized) throw ApiError(FLIP_ERR_RUNTIME, "Error: FluidSimulation must be initialized first.");
+        if (n < 0) throw ApiError(FLIP_ERR_OUT_OF_RANGE, "negative particle count");
+        particles_upload_aos(c, aos, n);
+    });
+}
+int flip_get_particle_positions(flip_ctx *c, float *xyz, int capacity) {
+    return guarded(c, [&] {
+        if (capacity < c->np) throw ApiError(FLIP_ERR_OUT_OF_RANGE, "Error: particle buffer too small.");
+        particles_download_component(c, xyz, 0);
+    });
+}
+int flip_get_particle_velocities(flip_ctx *c, float *xyz, int capacity) {
+    return guarded(c, [&] {
+        if (capacity < c->np) throw ApiError(FLIP_ERR_OUT_OF_RANGE, "Error: particle buffer too small.");
+        particles_download_component(c, xyz, 1);
+    });
+}
+
+int flip_enable_particle_ids(flip_ctx *c, int on) {
+    return guarded(c, [&] { c->trackIds = on != 0; });
+}
+int flip_get_particle_ids(flip_ctx *c, int32_t *ids, int capacity) {
+    return guarded(c, [&] {
+        if (!c->trackIds) throw ApiError(FLIP_ERR_RUNTIME, "particle ids are not enabled");
+        if (capacity < c->np) throw ApiError(FLIP_ERR_OUT_OF_RANGE, "Error: particle buffer too small.");
+        particles_download_ids(c, (int *)ids);
+    });
+}
+
+int flip_get_velocity_field(flip_ctx *c, float *U, float *V, float *W) {
+    return guarded(c, [&] {
+        const Dims &d = c->d;
+        FLIP_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        if (U) FLIP_CUDA_CHECK(cudaMemcpy(U, c->U, sizeof(float) * d.nU, cudaMemcpyDeviceToHost));
+        if (V) FLIP_CUDA_CHECK(cudaMemcpy(V, c->V, sizeof(float) * d.nV, cudaMemcpyDeviceToHost));
+        if (W) FLIP_CUDA_CHECK(cudaMemcpy(W, c->W, sizeof(float) * d.nW, cudaMemcpyDeviceToHost));
+    });
+}
+
+static void *array_ptr(const flip_ctx *c, int which, int64_t *bytes) {
+    const Dims &d = c->d;
+    switch (which) {
+        case FLIP_ARRAY_U: *bytes = 4ll * d.nU; return c->U;
+        case FLIP_ARRAY_V: *bytes = 4ll * d.nV; return c->V;
+        case FLIP_ARRAY_W: *bytes = 4ll * d.nW; return c->W;
+        case FLIP_ARRAY_VALID_U: *bytes = d.nU; return c->validU;
+        case FLIP_ARRAY_VALID_V: *bytes = d.nV; return c->validV;
+        case FLIP_ARRAY_VALID_W: *bytes = d.nW; return c->validW;
+        case FLIP_ARRAY_LIQUID_PHI: *bytes = 4ll * d.nC; return c->phiL;
+        case FLIP_ARRAY_SOLID_PHI: *bytes = 4ll * d.nN; return c->phiS;
+        case FLIP_ARRAY_WEIGHT_U: *bytes = 4ll * d.nU; return c->wU;
+        case FLIP_ARRAY_WEIGHT_V: *bytes = 4ll * d.nV; return c->wV;
+        case FLIP_ARRAY_WEIGHT_W: *bytes = 4ll * d.nW; return c->wW;
+        case FLIP_ARRAY_SAVED_U: *bytes = 4ll * d.nU; return c->sU;
+        case FLIP_ARRAY_SAVED_V: *bytes = 4ll * d.nV; return c->sV;
+        case FLIP_ARRAY_SAVED_W: *bytes = 4ll * d.nW; return c->sW;
+        case FLIP_ARRAY_NEAR_SOLID: *bytes = (int64_t)c->nsI * c->nsJ * c->nsK; return c->nearSolid;
+        case FLIP_ARRAY_PRESSURE: *bytes = 4ll * d.nC; return nullptr;
+    }
+    *bytes = -1;
+    return nullptr;
+}
+
+int flip_array_bytes(const flip_ctx *c, int which, int64_t *bytes) {
+    if (!c || !bytes) return FLIP_ERR_RUNTIME;
+    array_ptr(c, which, bytes);
+    if (*bytes < 0) return (which == FLIP_ARRAY_WEIGHT_C) ? FLIP_ERR_UNSUPPORTED : FLIP_ERR_OUT_OF_RANGE;
+    return FLIP_OK;
+}
+
+int flip_get_array(flip_ctx *c, int which, void *out) {
+    return guarded(c, [&] {
+        int64_t bytes = 0;
+        void *p = array_ptr(c, which, &bytes);
+        if (bytes < 0) {
+            if (which == FLIP_ARRAY_WEIGHT_C)
+                throw ApiError(FLIP_ERR_UNSUPPORTED, "the cell-centre weight only multiplies solid velocities, which are zero for static solids; it is not built");
+            throw ApiError(FLIP_ERR_OUT_OF_RANGE, "bad array id");
+        }
+        FLIP_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        if (which == FLIP_ARRAY_PRESSURE) {
+            float *tmp = nullptr;
+            FLIP_CUDA_CHECK(cudaMalloc(&tmp, bytes));
+            pressure_to_float(c, tmp);
+            FLIP_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+            FLIP_CUDA_CHECK(cudaMemcpy(out, tmp, bytes, cudaMemcpyDeviceToHost));
+            cudaFree(tmp);
+            return;
+        }
+        if (!p) throw ApiError(FLIP_ERR_RUNTIME, "array not allocated yet (call flip_initialize)");
+        FLIP_CUDA_CHECK(cudaMemcpy(out, p, bytes, cudaMemcpyDeviceToHost));
+    });
+}
+
+int flip_set_array(flip_ctx *c, int which, const void *in) {
+    return guarded(c, [&] {
+        int64_t bytes = 0;
+        void *p = array_ptr(c, which, &bytes);
+        if (bytes < 0 || !p || which == FLIP_ARRAY_PRESSURE) throw ApiError(FLIP_ERR_OUT_OF_RANGE, "array cannot be set");
+        FLIP_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        FLIP_CUDA_CHECK(cudaMemcpy(p, in, bytes, cudaMemcpyHostToDevice));
+    });
+}
+
+int flip_get_stage_times_ms(const flip_ctx *c, float ms[FLIP_NUM_STAGES]) {
+    if (!c || !ms) return FLIP_ERR_RUNTIME;
+    for (int s = 0; s < FLIP_NUM_STAGES; s++) ms[s] = c->stageMs[s];
+    return FLIP_OK;
+}
+int flip_get_kernel_launches(const flip_ctx *c, int64_t *n) { if (!c || !n) return FLIP_ERR_RUNTIME; *n = c->launches; return FLIP_OK; }
+int flip_get_stream(const flip_ctx *c, void **s) { if (!c || !s) return FLIP_ERR_RUNTIME; *s = (void *)c->stream; return FLIP_OK; }
+int flip_synchronize(flip_ctx *c) {
+    return guarded(c, [&] { FLIP_CUDA_CHECK(cudaStreamSynchronize(c->stream)); });
+}
+
+int flip_set_slab(flip_ctx *c, int rank, int nranks, const void *id, int idBytes) {
+    (void)id; (void)idBytes;
+    return guarded(c, [&] {
+        if (nranks != 1 || rank != 0) throw ApiError(FLIP_ERR_UNSUPPORTED, "z-slab decomposition is not built yet");
+    });
+}
+int flip_get_nccl_unique_id(void *out, int idBytes) {
+    (void)out; (void)idBytes;
+    return FLIP_ERR_UNSUPPORTED;
+}
+
+}  // extern "C"

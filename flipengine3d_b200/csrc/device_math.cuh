@@ -1,0 +1,179 @@
+// Device helpers that restate the reference's scalar arithmetic with explicit round-to-nearest
+// intrinsics, so that nvcc cannot contract mul+add into FMA: the parity oracle is built with
+// -ffp-contract=off.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace flip {
+
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
+
+// vmath::dot / lengthsq: x*x + y*y + z*z, left to right in float (vmath.h:76-88)
+__device__ __forceinline__ float lengthsq3(float x, float y, float z) {
+    return fadd(fadd(fmul(x, x), fmul(y, y)), fmul(z, z));
+}
+// vmath::length (vmath.h:90): sqrt of the float sum; (float)sqrt((double)s) == sqrtf(s) (53 >= 2*24+2)
+__device__ __forceinline__ float length3(float x, float y, float z) { return __fsqrt_rn(lengthsq3(x, y, z)); }
+
+// Grid3d::positionToGridIndex (grid3d.h:56-61): (int)floor(p * (1.0/dx)) in double
+__device__ __forceinline__ int pos2idx(float p, double invdx) { return (int)floor(dmul((double)p, invdx)); }
+__device__ __forceinline__ int pos2idx_d(double p, double invdx) { return (int)floor(dmul(p, invdx)); }
+
+// Interpolation::trilinearInterpolate(double p[8], x, y, z)  interpolation.cpp:61-70
+// vertex order {000,100,010,001,101,011,110,111}; products and sums left to right, no FMA.
+__device__ __forceinline__ double trilerp8(const double p[8], double x, double y, double z) {
+    double mx = dsub(1.0, x), my = dsub(1.0, y), mz = dsub(1.0, z);
+    double s = dmul(dmul(dmul(p[0], mx), my), mz);
+    s = dadd(s, dmul(dmul(dmul(p[1], x), my), mz));
+    s = dadd(s, dmul(dmul(dmul(p[2], mx), y), mz));
+    s = dadd(s, dmul(dmul(dmul(p[3], mx), my), z));
+    s = dadd(s, dmul(dmul(dmul(p[4], x), my), z));
+    s = dadd(s, dmul(dmul(dmul(p[5], mx), y), z));
+    s = dadd(s, dmul(dmul(dmul(p[6], x), y), mz));
+    s = dadd(s, dmul(dmul(dmul(p[7], x), y), z));
+    return s;
+}
+
+// One MAC component sampled as MACVelocityField::_interpolateLinearU/V/W do
+// (macvelocityfield.cpp:519-613): shift the two transverse axes by dx/2 in double, floor, 8
+// samples with out-of-range -> 0, weights in double.  (sx,sy,sz) = 1 where the half-cell shift applies.
+// gi,gj,gk = dimensions of this component's array.
+template <int SX, int SY, int SZ>
+__device__ __forceinline__ double sample_mac(const float *__restrict__ g, int gi, int gj, int gk, double x, double y,
+                                             double z, double dx, double invdx, double hdx) {
+    if (SX) x = dsub(x, hdx);
+    if (SY) y = dsub(y, hdx);
+    if (SZ) z = dsub(z, hdx);
+    int i = pos2idx_d(x, invdx), j = pos2idx_d(y, invdx), k = pos2idx_d(z, invdx);
+    double fx = dmul(dsub(x, dmul((double)i, dx)), invdx);
+    double fy = dmul(dsub(y, dmul((double)j, dx)), invdx);
+    double fz = dmul(dsub(z, dmul((double)k, dx)), invdx);
+    double p[8];
+    bool i0 = (i >= 0 && i < gi), i1 = (i + 1 >= 0 && i + 1 < gi);
+    bool j0 = (j >= 0 && j < gj), j1 = (j + 1 >= 0 && j + 1 < gj);
+    bool k0 = (k >= 0 && k < gk), k1 = (k + 1 >= 0 && k + 1 < gk);
+    long long base = (long long)i + (long long)gi * ((long long)j + (long long)gj * (long long)k);
+    long long sj = gi, sk = (long long)gi * gj;
+    p[0] = (i0 && j0 && k0) ? (double)__ldg(g + base) : 0.0;
+    p[1] = (i1 && j0 && k0) ? (double)__ldg(g + base + 1) : 0.0;
+    p[2] = (i0 && j1 && k0) ? (double)__ldg(g + base + sj) : 0.0;
+    p[3] = (i0 && j0 && k1) ? (double)__ldg(g + base + sk) : 0.0;
+    p[4] = (i1 && j0 && k1) ? (double)__ldg(g + base + sk + 1) : 0.0;
+    p[5] = (i0 && j1 && k1) ? (double)__ldg(g + base + sk + sj) : 0.0;
+    p[6] = (i1 && j1 && k0) ? (double)__ldg(g + base + sj + 1) : 0.0;
+    p[7] = (i1 && j1 && k1) ? (double)__ldg(g + base + sk + sj + 1) : 0.0;
+    return trilerp8(p, fx, fy, fz);
+}
+
+struct MacField {
+    const float *U, *V, *W;
+};
+
+// MACVelocityField::evaluateVelocityAtPositionLinear(vec3)  macvelocityfield.cpp:635-645
+__device__ __forceinline__ void sample_velocity(const MacField &f, int I, int J, int K, double dx, double invdx,
+                                                double hdx, float px, float py, float pz, float &ox, float &oy,
+                                                float &oz) {
+    double x = px, y = py, z = pz;
+    // Grid3d::isPositionInGrid (grid3d.h:135): x < dx*i in double
+    if (!(x >= 0 && y >= 0 && z >= 0 && x < dmul(dx, (double)I) && y < dmul(dx, (double)J) && z < dmul(dx, (double)K))) {
+        ox = oy = oz = 0.0f;
+        return;
+    }
+    ox = (float)sample_mac<0, 1, 1>(f.U, I + 1, J, K, x, y, z, dx, invdx, hdx);
+    oy = (float)sample_mac<1, 0, 1>(f.V, I, J + 1, K, x, y, z, dx, invdx, hdx);
+    oz = (float)sample_mac<1, 1, 0>(f.W, I, J, K + 1, x, y, z, dx, invdx, hdx);
+}
+
+// Interpolation::trilinearInterpolate(vec3 p, double dx, Array3d<float>&)  interpolation.cpp:72-110
+// (node position narrowed to float, fraction = (float - float) * inv_dx in double)
+struct ScalarSample {
+    int i, j, k;
+    double fx, fy, fz;
+    float v[8];  // order 000,100,010,001,101,011,110,111
+};
+
+__device__ __forceinline__ void fetch_scalar(const float *__restrict__ g, int gi, int gj, int gk, double dx,
+                                             double invdx, float px, float py, float pz, ScalarSample &s) {
+    s.i = pos2idx(px, invdx);
+    s.j = pos2idx(py, invdx);
+    s.k = pos2idx(pz, invdx);
+    float gx = (float)dmul((double)(float)s.i, dx);
+    float gy = (float)dmul((double)(float)s.j, dx);
+    float gz = (float)dmul((double)(float)s.k, dx);
+    s.fx = dmul((double)fsub(px, gx), invdx);
+    s.fy = dmul((double)fsub(py, gy), invdx);
+    s.fz = dmul((double)fsub(pz, gz), invdx);
+    int i = s.i, j = s.j, k = s.k;
+    bool i0 = (i >= 0 && i < gi), i1 = (i + 1 >= 0 && i + 1 < gi);
+    bool j0 = (j >= 0 && j < gj), j1 = (j + 1 >= 0 && j + 1 < gj);
+    bool k0 = (k >= 0 && k < gk), k1 = (k + 1 >= 0 && k + 1 < gk);
+    long long base = (long long)i + (long long)gi * ((long long)j + (long long)gj * (long long)k);
+    long long sj = gi, sk = (long long)gi * gj;
+    s.v[0] = (i0 && j0 && k0) ? __ldg(g + base) : 0.0f;
+    s.v[1] = (i1 && j0 && k0) ? __ldg(g + base + 1) : 0.0f;
+    s.v[2] = (i0 && j1 && k0) ? __ldg(g + base + sj) : 0.0f;
+    s.v[3] = (i0 && j0 && k1) ? __ldg(g + base + sk) : 0.0f;
+    s.v[4] = (i1 && j0 && k1) ? __ldg(g + base + sk + 1) : 0.0f;
+    s.v[5] = (i0 && j1 && k1) ? __ldg(g + base + sk + sj) : 0.0f;
+    s.v[6] = (i1 && j1 && k0) ? __ldg(g + base + sj + 1) : 0.0f;
+    s.v[7] = (i1 && j1 && k1) ? __ldg(g + base + sk + sj + 1) : 0.0f;
+}
+
+__device__ __forceinline__ float scalar_value(const ScalarSample &s) {
+    double p[8];
+#pragma unroll
+    for (int m = 0; m < 8; m++) p[m] = (double)s.v[m];
+    return (float)trilerp8(p, s.fx, s.fy, s.fz);
+}
+
+__device__ __forceinline__ float sample_scalar(const float *__restrict__ g, int gi, int gj, int gk, double dx,
+                                               double invdx, float px, float py, float pz) {
+    ScalarSample s;
+    fetch_scalar(g, gi, gj, gk, dx, invdx, px, py, pz, s);
+    return scalar_value(s);
+}
+
+// Interpolation::bilinearInterpolate  interpolation.cpp:188-194
+__device__ __forceinline__ double bilerp(double v00, double v10, double v01, double v11, double ix, double iy) {
+    double l1 = dadd(dmul(dsub(1.0, ix), v00), dmul(ix, v10));
+    double l2 = dadd(dmul(dsub(1.0, ix), v01), dmul(ix, v11));
+    return dadd(dmul(dsub(1.0, iy), l1), dmul(iy, l2));
+}
+
+// Interpolation::trilinearInterpolateGradient  interpolation.cpp:196-262
+__device__ __forceinline__ void scalar_gradient(const ScalarSample &s, float &gx, float &gy, float &gz) {
+    float v000 = s.v[0], v100 = s.v[1], v010 = s.v[2], v001 = s.v[3];
+    float v101 = s.v[4], v011 = s.v[5], v110 = s.v[6], v111 = s.v[7];
+    gx = (float)bilerp(fsub(v100, v000), fsub(v110, v010), fsub(v101, v001), fsub(v111, v011), s.fy, s.fz);
+    gy = (float)bilerp(fsub(v010, v000), fsub(v110, v100), fsub(v011, v001), fsub(v111, v101), s.fx, s.fz);
+    gz = (float)bilerp(fsub(v001, v000), fsub(v101, v100), fsub(v011, v010), fsub(v111, v110), s.fx, s.fy);
+}
+
+// warp reductions
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_maxd(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ int warp_sum_i(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace flip

@@ -1,0 +1,204 @@
+// Internal declarations shared by the translation units of libflip_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/flip_b200.h"
+
+#define FLIP_CUDA_CHECK(call)                                                                   \
+    do {                                                                                        \
+        cudaError_t e__ = (call);                                                               \
+        if (e__ != cudaSuccess) {                                                               \
+            throw flip::CudaError(std::string(#call) + ": " + cudaGetErrorString(e__) + " at " + \
+                                  __FILE__ + ":" + std::to_string(__LINE__));                   \
+        }                                                                                       \
+    } while (0)
+
+namespace flip {
+
+struct CudaError {
+    std::string msg;
+    explicit CudaError(const std::string &m) : msg(m) {}
+};
+struct ApiError {
+    int code;
+    std::string msg;
+    ApiError(int c, const std::string &m) : code(c), msg(m) {}
+};
+
+// Grid geometry handed to kernels by value.
+struct Dims {
+    int I, J, K;        // cells
+    int nU, nV, nW;     // face counts
+    int nC;             // cells
+    int nN;             // nodes (I+1)(J+1)(K+1)
+    double dx;
+};
+
+// Particle store: SoA, 6 float arrays (24 B/particle), double buffered for the per-step cell sort.
+struct ParticleSoA {
+    float *px = nullptr, *py = nullptr, *pz = nullptr;
+    float *vx = nullptr, *vy = nullptr, *vz = nullptr;
+};
+
+// Device scalars written by kernels and read by later kernels / the host (one pinned mirror).
+struct DeviceScalars {
+    // particle bookkeeping
+    int numParticles;          // survivors after the last sort/compaction
+    int removedSolid, removedCrowded, removedFast;
+    unsigned int maxSpeedSqBits; // max |v|^2 over survivors, float bits (non-negative => uint order)
+    int speedHist[8];          // _getMarkerParticleSpeedLimit bins
+    float maxSpeedLimit;       // result of the histogram walk
+    int anyCrowded;            // some cell holds more than maxParticlesPerCell candidates
+    // pressure
+    int numRows;               // n
+    int numFluidCells;         // phi<0 over [1,N-2]^3 (== numRows)
+    int numSegments;
+    unsigned long long rhsMaxBits;  // ||b||_inf as double bits
+    // PCG (slots rotate by iteration)
+    double dotSZ[3];
+    double rho[3];
+    unsigned long long rMaxBits[3];
+    int pcgIterations;
+    int pcgDone;               // 0 running, 1 converged, 3 breakdown
+    double pcgError;
+    double pcgTol;
+    // extrapolation frontier sizes
+    int frontierCount[2];
+    // multigrid coarse solve etc.
+    int pad[8];
+};
+
+}  // namespace flip
+
+struct flip_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    flip::Dims d;
+    std::string lastError;
+    int64_t launches = 0;
+
+    // ---- configuration (defaults: fluidsimulation.h:1518-1701)
+    double gravity[3] = {0, 0, 0};
+    double ratioPICFLIP = 0.05;
+    double CFL = 5.0;
+    int minSubsteps = 1, maxSubsteps = 6;
+    double pressureTol = 1e-9, pressureAcceptableTol = 1.0;
+    int pressureMaxIter = 1000;
+    int preconditioner = 1;
+    int maxParticlesPerCell = 250;
+    double solidBufferWidth = 0.1f;          // float in the reference (fluidsimulation.h:1685)
+    double maxExtremeVelocityRemovalPercent = 0.0005;
+    int maxExtremeVelocityRemovalAbsolute = 35;
+    float markerParticleStepDistanceFactor = 0.5f;
+    int nearSolidFactor = 3;
+    int solidExactBand = 3;
+    int extrapolationLayers = 7;             // ceil(CFL)+2  fluidsimulation.cpp:3777
+    double liquidRadius = 0.0;               // 0.5*dx*sqrt(3)  fluidsimulation.cpp:2649
+
+    // ---- state machine of update()
+    bool initialized = false;
+    int currentFrame = 0;
+    int substepNumber = 0;
+    double frameDt = 0, frameRemaining = 0, substepDt = 0;
+    bool firstStepEver = true;               // frame 0 / substep 0 uses the predicted speed (:5595)
+    std::vector<flip_step_stats> stats;      // per substep of the last frame
+    flip_step_stats cur;                     // being filled
+
+    // ---- host staging
+    std::vector<float> loadQueuePos, loadQueueVel;   // loadMarkerParticleData queue
+    struct FluidBox { double lo[3], hi[3], vel[3]; };
+    std::vector<FluidBox> fluidBoxes;
+    std::vector<float> hostSolidPhi;          // nodal
+    bool userSolidPhi = false;
+    std::vector<float> hU, hV, hW;            // host mirror handed out by getVelocityField
+
+    // ---- device memory
+    int capacity = 0;                         // particle capacity
+    int np = 0;                               // live particles (host copy)
+    flip::ParticleSoA P[2];                   // ping-pong
+    int cur_buf = 0;
+    int *cellOfParticle = nullptr;            // [capacity] destination cell or -1 (removed)
+    int *sortIdx = nullptr;                   // [capacity] particle indices grouped by cell
+    int *srcIdx = nullptr;                    // [capacity] final gather map
+    int *pid[2] = {nullptr, nullptr};         // optional particle ids carried through the sorts
+    bool trackIds = false;
+    unsigned char *fastFlag = nullptr;        // [capacity] extreme-velocity flag
+    int *cellCount = nullptr;                 // [nC+1]
+    int *cellStart = nullptr;                 // [nC+1] exclusive scan of kept counts (valid for current particles)
+    int *cellStartA = nullptr;                // [nC+1] scan of candidate counts
+    void *scanTemp = nullptr;
+    size_t scanTempBytes = 0;
+
+    float *U = nullptr, *V = nullptr, *W = nullptr;
+    float *sU = nullptr, *sV = nullptr, *sW = nullptr;    // saved field
+    unsigned char *validU = nullptr, *validV = nullptr, *validW = nullptr;
+    unsigned char *status = nullptr;          // extrapolation level grid, max(nU,nV,nW)
+    int *frontier[2] = {nullptr, nullptr};
+    float *phiL = nullptr;                    // liquid SDF
+    float *phiS = nullptr;                    // solid SDF, nodal
+    float *wU = nullptr, *wV = nullptr, *wW = nullptr, *wC = nullptr;
+    unsigned char *nearSolid = nullptr;
+    int nsI = 0, nsJ = 0, nsK = 0;
+    float *pressure = nullptr;                // (I,J,K) float, last solution
+
+    // pressure system, dense-indexed vectors over cells + active 32-cell segments
+    int *segCell = nullptr;                   // [maxSegments] first cell of the segment
+    unsigned int *segMask = nullptr;          // [maxSegments] liquid lanes
+    int maxSegments = 0;
+    double *Adiag = nullptr;                  // [nC]
+    float *AoffU = nullptr, *AoffV = nullptr, *AoffW = nullptr;  // [nC] masked upper-face weights
+    double *vx_ = nullptr, *vr = nullptr, *vs = nullptr, *vz = nullptr, *vb = nullptr;   // [nC]
+    void *mg = nullptr;                       // multigrid hierarchy (pressure.cu)
+
+    flip::DeviceScalars *dS = nullptr;        // device
+    flip::DeviceScalars *hS = nullptr;        // pinned host mirror
+
+    cudaEvent_t evStage[FLIP_NUM_STAGES + 1];
+    float stageMs[FLIP_NUM_STAGES] = {0};
+    bool eventsCreated = false;
+
+    // multi-GPU slab
+    int rank = 0, nranks = 1;
+};
+
+namespace flip {
+
+// static_host.cpp
+void build_box_solid_sdf(const Dims &d, std::vector<float> &phi);
+void build_weights(const Dims &d, const std::vector<float> &phi, std::vector<float> &wU, std::vector<float> &wV,
+                   std::vector<float> &wW, std::vector<float> &wC);
+void build_near_solid(const Dims &d, const std::vector<float> &phi, int factor, int band, double cfl,
+                      std::vector<unsigned char> &grid, int &gi, int &gj, int &gk);
+
+// particles.cu
+void particles_alloc(flip_ctx *c, int capacity);
+void particles_free(flip_ctx *c);
+void particles_upload_aos(flip_ctx *c, const float *aos6, int n);      // filter + sort
+void particles_upload_split(flip_ctx *c, const float *pos, const float *vel, int n);
+void particles_download_aos(flip_ctx *c, float *aos6);
+void particles_download_component(flip_ctx *c, float *xyz, int which);  // 0 pos, 1 vel
+void particles_download_ids(flip_ctx *c, int *ids);
+void particles_sort(flip_ctx *c, bool applyRemovalRules, double frameDt);
+void stage_liquid_sdf(flip_ctx *c);
+void stage_p2g(flip_ctx *c);
+void stage_g2p(flip_ctx *c);
+void stage_advance(flip_ctx *c, double dt);
+
+// grid.cu
+void stage_extrapolate(flip_ctx *c);
+void stage_save(flip_ctx *c);
+void stage_body_force(flip_ctx *c, double dt);
+void stage_constrain(flip_ctx *c);
+
+// pressure.cu
+void pressure_alloc(flip_ctx *c);
+void pressure_free(flip_ctx *c);
+void stage_pressure(flip_ctx *c, double dt);
+
+// helpers
+void scalars_to_host(flip_ctx *c);   // async copy + sync
+inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
+
+}  // namespace flip

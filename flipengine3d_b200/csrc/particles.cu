@@ -1,0 +1,838 @@
+// Particle-side kernels of the FLIP step: per-step cell sort (+ the reference's particle removal
+// rules), liquid SDF + particle-to-grid gather, PIC/FLIP grid-to-particle update and RK3 advection
+// with solid collision.  Each kernel cites the reference code whose results it reproduces.
+#include <cub/device/device_scan.cuh>
+#include <cstring>
+#include "device_math.cuh"
+#include "flip_internal.h"
+
+namespace flip {
+
+static constexpr int TPB = 256;
+
+// ------------------------------------------------------------------------------------------------
+// allocation
+// ------------------------------------------------------------------------------------------------
+static void soa_alloc(ParticleSoA &p, int cap) {
+    FLIP_CUDA_CHECK(cudaMalloc(&p.px, sizeof(float) * cap));
+    FLIP_CUDA_CHECK(cudaMalloc(&p.py, sizeof(float) * cap));
+    FLIP_CUDA_CHECK(cudaMalloc(&p.pz, sizeof(float) * cap));
+    FLIP_CUDA_CHECK(cudaMalloc(&p.vx, sizeof(float) * cap));
+    FLIP_CUDA_CHECK(cudaMalloc(&p.vy, sizeof(float) * cap));
+    FLIP_CUDA_CHECK(cudaMalloc(&p.vz, sizeof(float) * cap));
+}
+static void soa_free(ParticleSoA &p) {
+    cudaFree(p.px); cudaFree(p.py); cudaFree(p.pz); cudaFree(p.vx); cudaFree(p.vy); cudaFree(p.vz);
+    p = ParticleSoA();
+}
+
+void particles_free(flip_ctx *c) {
+    soa_free(c->P[0]);
+    soa_free(c->P[1]);
+    cudaFree(c->cellOfParticle); c->cellOfParticle = nullptr;
+    cudaFree(c->sortIdx); c->sortIdx = nullptr;
+    cudaFree(c->srcIdx); c->srcIdx = nullptr;
+    cudaFree(c->fastFlag); c->fastFlag = nullptr;
+    cudaFree(c->pid[0]); cudaFree(c->pid[1]); c->pid[0] = c->pid[1] = nullptr;
+    c->capacity = 0;
+}
+
+void particles_alloc(flip_ctx *c, int capacity) {
+    if (capacity <= c->capacity) return;
+    // keep live particles when growing
+    ParticleSoA old[2] = {c->P[0], c->P[1]};
+    int oldCap = c->capacity;
+    int cap = capacity + capacity / 16 + 1024;
+    ParticleSoA nw[2];
+    soa_alloc(nw[0], cap);
+    soa_alloc(nw[1], cap);
+    int *npid[2] = {nullptr, nullptr};
+    FLIP_CUDA_CHECK(cudaMalloc(&npid[0], sizeof(int) * cap));
+    FLIP_CUDA_CHECK(cudaMalloc(&npid[1], sizeof(int) * cap));
+    if (oldCap > 0 && c->np > 0)
+        FLIP_CUDA_CHECK(cudaMemcpyAsync(npid[c->cur_buf], c->pid[c->cur_buf], sizeof(int) * c->np, cudaMemcpyDeviceToDevice, c->stream));
+    if (oldCap > 0 && c->np > 0) {
+        const ParticleSoA &s = old[c->cur_buf];
+        ParticleSoA &t = nw[c->cur_buf];
+        size_t b = sizeof(float) * c->np;
+        FLIP_CUDA_CHECK(cudaMemcpyAsync(t.px, s.px, b, cudaMemcpyDeviceToDevice, c->stream));
+        FLIP_CUDA_CHECK(cudaMemcpyAsync(t.py, s.py, b, cudaMemcpyDeviceToDevice, c->stream));
+        FLIP_CUDA_CHECK(cudaMemcpyAsync(t.pz, s.pz, b, cudaMemcpyDeviceToDevice, c->stream));
+        FLIP_CUDA_CHECK(cudaMemcpyAsync(t.vx, s.vx, b, cudaMemcpyDeviceToDevice, c->stream));
+        FLIP_CUDA_CHECK(cudaMemcpyAsync(t.vy, s.vy, b, cudaMemcpyDeviceToDevice, c->stream));
+        FLIP_CUDA_CHECK(cudaMemcpyAsync(t.vz, s.vz, b, cudaMemcpyDeviceToDevice, c->stream));
+        FLIP_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    }
+    if (oldCap > 0) {
+        soa_free(old[0]);
+        soa_free(old[1]);
+        cudaFree(c->cellOfParticle); cudaFree(c->sortIdx); cudaFree(c->srcIdx); cudaFree(c->fastFlag);
+        cudaFree(c->pid[0]); cudaFree(c->pid[1]);
+    }
+    c->P[0] = nw[0];
+    c->P[1] = nw[1];
+    c->pid[0] = npid[0];
+    c->pid[1] = npid[1];
+    FLIP_CUDA_CHECK(cudaMalloc(&c->cellOfParticle, sizeof(int) * cap));
+    FLIP_CUDA_CHECK(cudaMalloc(&c->sortIdx, sizeof(int) * cap));
+    FLIP_CUDA_CHECK(cudaMalloc(&c->srcIdx, sizeof(int) * cap));
+    FLIP_CUDA_CHECK(cudaMalloc(&c->fastFlag, cap));
+    c->capacity = cap;
+}
+
+// ------------------------------------------------------------------------------------------------
+// AoS <-> SoA at the API boundary (MarkerParticle, markerparticle.h:30-42)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_aos_to_soa(const float *__restrict__ aos, int n, ParticleSoA p) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const float *a = aos + 6ll * t;
+    p.px[t] = a[0]; p.py[t] = a[1]; p.pz[t] = a[2];
+    p.vx[t] = a[3]; p.vy[t] = a[4]; p.vz[t] = a[5];
+}
+__global__ void k_split_to_soa(const float *__restrict__ pos, const float *__restrict__ vel, int n, ParticleSoA p) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    p.px[t] = pos[3ll * t]; p.py[t] = pos[3ll * t + 1]; p.pz[t] = pos[3ll * t + 2];
+    p.vx[t] = vel[3ll * t]; p.vy[t] = vel[3ll * t + 1]; p.vz[t] = vel[3ll * t + 2];
+}
+__global__ void k_soa_to_aos(ParticleSoA p, int n, float *__restrict__ aos) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    float *a = aos + 6ll * t;
+    a[0] = p.px[t]; a[1] = p.py[t]; a[2] = p.pz[t];
+    a[3] = p.vx[t]; a[4] = p.vy[t]; a[5] = p.vz[t];
+}
+__global__ void k_soa_to_xyz(const float *x, const float *y, const float *z, int n, float *__restrict__ out) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    out[3ll * t] = x[t]; out[3ll * t + 1] = y[t]; out[3ll * t + 2] = z[t];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Cell sort + removal rules.
+//
+// Reference semantics reproduced (fluidsimulation.cpp:4298-4353):
+//   * particles whose solid SDF sample is < 0 are deleted and never counted;
+//   * per cell, in particle-index order, the first maxMarkerParticlesPerCell are kept;
+//   * of those, particles faster than the histogram speed limit are deleted (but still counted).
+// The load-time filter is the in-domain test of _loadMarkerParticles / _addMarkerParticle
+// (:2773-2785, :2637-2642).  Order inside a cell = previous index order (stable), so the whole
+// pipeline is deterministic.
+// ------------------------------------------------------------------------------------------------
+struct SortParams {
+    int n;
+    int I, J, K;
+    double dx, invdx;
+    int applyRules;
+    int maxPerCell;
+};
+
+// _getMarkerParticleSpeedLimit, first loop (:4300-4305): histogram of |v| in CFL*dx/dt_frame bins.
+__global__ void k_speed_hist(ParticleSoA p, int n, double speedLimitStep, int nbins, DeviceScalars *S) {
+    __shared__ int sh[8];
+    if (threadIdx.x < 8) sh[threadIdx.x] = 0;
+    __syncthreads();
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) {
+        float len = length3(p.vx[t], p.vy[t], p.vz[t]);
+        double speed = (double)len;
+        double b = fmin(floor(speed / speedLimitStep), (double)(nbins - 1));
+        int bi = (int)b;
+        if (bi > 0) atomicAdd(&sh[bi], 1);   // bin 0 is never read by the walk below
+    }
+    __syncthreads();
+    if (threadIdx.x > 0 && threadIdx.x < 8 && sh[threadIdx.x]) atomicAdd(&S->speedHist[threadIdx.x], sh[threadIdx.x]);
+}
+
+// _getMarkerParticleSpeedLimit, second loop (:4307-4320)
+__global__ void k_speed_limit(int n, double speedLimitStep, int nbins, double maxpct, int maxabs, DeviceScalars *S) {
+    int maxRemovalCount = (int)fmin((double)(int)((double)n * maxpct), (double)maxabs);
+    double maxspeed = nbins * speedLimitStep;
+    int cur = 0;
+    for (int i = nbins - 1; i > 0; i--) {
+        if (cur + S->speedHist[i] > maxRemovalCount) break;
+        cur += S->speedHist[i];
+        maxspeed = i * speedLimitStep;
+    }
+    S->maxSpeedLimit = (float)maxspeed;
+    for (int i = 0; i < 8; i++) S->speedHist[i] = 0;
+}
+
+__global__ void k_classify(ParticleSoA p, SortParams sp, const float *__restrict__ phiS, int *__restrict__ cellOf,
+                           unsigned char *__restrict__ fast, int *__restrict__ cellCount, DeviceScalars *S) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= sp.n) return;
+    float x = p.px[t], y = p.py[t], z = p.pz[t];
+    int i = pos2idx(x, sp.invdx), j = pos2idx(y, sp.invdx), k = pos2idx(z, sp.invdx);
+    int cell = -1;
+    bool inRange = (i >= 0 && j >= 0 && k >= 0 && i < sp.I && j < sp.J && k < sp.K);
+    unsigned char f = 0;
+    if (inRange) {
+        cell = i + sp.I * (j + sp.J * k);
+        if (sp.applyRules) {
+            // MeshLevelSet::trilinearInterpolateSolidPoints  meshlevelset.h:325-332
+            float phi = sample_scalar(phiS, sp.I + 1, sp.J + 1, sp.K + 1, sp.dx, sp.invdx, x, y, z);
+            if (phi < 0.0f) {
+                cell = -1;
+                atomicAdd(&S->removedSolid, 1);
+            } else {
+                float vx = p.vx[t], vy = p.vy[t], vz = p.vz[t];
+                float ms = S->maxSpeedLimit;
+                double maxspeedsq = (double)fmul(ms, ms);   // float*float then widened (:4328)
+                if ((double)lengthsq3(vx, vy, vz) > maxspeedsq) f = 1;
+            }
+        }
+    } else if (sp.applyRules) {
+        // cannot happen after _resolveCollision (positions are clamped into the boundary box); counted as solid
+        atomicAdd(&S->removedSolid, 1);
+    }
+    cellOf[t] = cell;
+    fast[t] = f;
+    if (cell >= 0) atomicAdd(&cellCount[cell], 1);
+}
+
+__global__ void k_scatter_idx(int n, const int *__restrict__ cellOf, const int *__restrict__ startA,
+                              int *__restrict__ cursor, int *__restrict__ sortIdx) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    int cell = cellOf[t];
+    if (cell < 0) return;
+    int r = atomicAdd(&cursor[cell], 1);
+    sortIdx[startA[cell] + r] = t;
+}
+
+// One thread per cell: order the cell's candidates by previous index, apply the per-cell cap and
+// the speed rule, leave the kept ones at the front of the cell's range, publish the kept count.
+__global__ void k_cell_finalize(int nC, const int *__restrict__ startA, int *__restrict__ sortIdx,
+                                const unsigned char *__restrict__ fast, int *__restrict__ keptCount, int applyRules,
+                                int maxPerCell, DeviceScalars *S) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nC) return;
+    int b = startA[c], e = startA[c + 1];
+    int n = e - b;
+    if (n == 0) { keptCount[c] = 0; return; }
+    // insertion sort (cells hold ~8 particles; the cap is 250)
+    for (int a = b + 1; a < e; a++) {
+        int v = sortIdx[a];
+        int q = a - 1;
+        while (q >= b && sortIdx[q] > v) { sortIdx[q + 1] = sortIdx[q]; q--; }
+        sortIdx[q + 1] = v;
+    }
+    int kept = n;
+    if (applyRules) {
+        kept = 0;
+        int crowded = 0, fastc = 0;
+        for (int a = b; a < e; a++) {
+            int v = sortIdx[a];
+            if (a - b >= maxPerCell) { crowded++; continue; }
+            if (fast[v]) { fastc++; continue; }
+            sortIdx[b + kept] = v;
+            kept++;
+        }
+        if (crowded) atomicAdd(&S->removedCrowded, crowded);
+        if (fastc) atomicAdd(&S->removedFast, fastc);
+    }
+    keptCount[c] = kept;
+}
+
+__global__ void k_build_src(int nC, const int *__restrict__ startA, const int *__restrict__ start,
+                            const int *__restrict__ sortIdx, int *__restrict__ srcIdx, DeviceScalars *S) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nC) return;
+    int b = start[c], e = start[c + 1];
+    int a = startA[c];
+    for (int q = b; q < e; q++) srcIdx[q] = sortIdx[a + (q - b)];
+    if (c == nC - 1) S->numParticles = e;
+}
+
+__global__ void k_iota(int *p, int n) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) p[t] = t;
+}
+
+__global__ void k_gather(ParticleSoA src, ParticleSoA dst, const int *__restrict__ srcIdx, int nmax, DeviceScalars *S,
+                         const int *__restrict__ idSrc, int *__restrict__ idDst) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int n = S->numParticles;
+    float sp2 = 0.0f;
+    if (t < n && t < nmax) {
+        int s = srcIdx[t];
+        if (idSrc) idDst[t] = idSrc[s];
+        dst.px[t] = src.px[s]; dst.py[t] = src.py[s]; dst.pz[t] = src.pz[s];
+        float vx = src.vx[s], vy = src.vy[s], vz = src.vz[s];
+        dst.vx[t] = vx; dst.vy[t] = vy; dst.vz[t] = vz;
+        sp2 = lengthsq3(vx, vy, vz);   // vmath::dot(mp.velocity, mp.velocity)  :5558
+    }
+    sp2 = warp_max(sp2);
+    if ((threadIdx.x & 31) == 0 && sp2 > 0.0f) atomicMax(&S->maxSpeedSqBits, __float_as_uint(sp2));
+}
+
+__global__ void k_reset_sort_scalars(DeviceScalars *S) {
+    S->removedSolid = 0; S->removedCrowded = 0; S->removedFast = 0;
+    S->maxSpeedSqBits = 0u;
+    S->numParticles = 0;
+}
+
+static void ensure_scan_temp(flip_ctx *c, int n) {
+    size_t bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, bytes, (int *)nullptr, (int *)nullptr, n, c->stream);
+    if (bytes > c->scanTempBytes) {
+        cudaFree(c->scanTemp);
+        FLIP_CUDA_CHECK(cudaMalloc(&c->scanTemp, bytes));
+        c->scanTempBytes = bytes;
+    }
+}
+
+void scalars_to_host(flip_ctx *c) {
+    FLIP_CUDA_CHECK(cudaMemcpyAsync(c->hS, c->dS, sizeof(DeviceScalars), cudaMemcpyDeviceToHost, c->stream));
+    FLIP_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+}
+
+// Sorts P[cur] (c->np particles) into P[1-cur], grouped by cell, and rebuilds cellStart.
+void particles_sort(flip_ctx *c, bool applyRules, double frameDt) {
+    const Dims &d = c->d;
+    int n = c->np;
+    cudaStream_t st = c->stream;
+    ParticleSoA &src = c->P[c->cur_buf];
+    ParticleSoA &dst = c->P[1 - c->cur_buf];
+    int nC = d.nC;
+    k_reset_sort_scalars<<<1, 1, 0, st>>>(c->dS); c->launches++;
+    FLIP_CUDA_CHECK(cudaMemsetAsync(c->cellCount, 0, sizeof(int) * (nC + 1), st));
+    if (n > 0) {
+        if (applyRules) {
+            // _removeMarkerParticles(_currentFrameDeltaTime): bins are CFL*dx/dt_FRAME wide
+            double speedLimitStep = c->CFL * d.dx / frameDt;
+            k_speed_hist<<<cdiv(n, TPB), TPB, 0, st>>>(src, n, speedLimitStep, c->maxSubsteps, c->dS); c->launches++;
+            k_speed_limit<<<1, 1, 0, st>>>(n, speedLimitStep, c->maxSubsteps, c->maxExtremeVelocityRemovalPercent,
+                                           c->maxExtremeVelocityRemovalAbsolute, c->dS); c->launches++;
+        }
+        SortParams sp;
+        sp.n = n; sp.I = d.I; sp.J = d.J; sp.K = d.K; sp.dx = d.dx; sp.invdx = 1.0 / d.dx;
+        sp.applyRules = applyRules ? 1 : 0; sp.maxPerCell = c->maxParticlesPerCell;
+        k_classify<<<cdiv(n, TPB), TPB, 0, st>>>(src, sp, c->phiS, c->cellOfParticle, c->fastFlag, c->cellCount, c->dS);
+        c->launches++;
+    }
+    ensure_scan_temp(c, nC + 1);
+    cub::DeviceScan::ExclusiveSum(c->scanTemp, c->scanTempBytes, c->cellCount, c->cellStartA, nC + 1, st); c->launches++;
+    FLIP_CUDA_CHECK(cudaMemsetAsync(c->cellCount, 0, sizeof(int) * (nC + 1), st));
+    if (n > 0) {
+        k_scatter_idx<<<cdiv(n, TPB), TPB, 0, st>>>(n, c->cellOfParticle, c->cellStartA, c->cellCount, c->sortIdx);
+        c->launches++;
+    }
+    k_cell_finalize<<<cdiv(nC, TPB), TPB, 0, st>>>(nC, c->cellStartA, c->sortIdx, c->fastFlag, c->cellCount,
+                                                   applyRules ? 1 : 0, c->maxParticlesPerCell, c->dS);
+    c->launches++;
+    FLIP_CUDA_CHECK(cudaMemsetAsync(c->cellCount + nC, 0, sizeof(int), st));
+    cub::DeviceScan::ExclusiveSum(c->scanTemp, c->scanTempBytes, c->cellCount, c->cellStart, nC + 1, st); c->launches++;
+    k_build_src<<<cdiv(nC, TPB), TPB, 0, st>>>(nC, c->cellStartA, c->cellStart, c->sortIdx, c->srcIdx, c->dS);
+    c->launches++;
+    if (n > 0) {
+        k_gather<<<cdiv(n, TPB), TPB, 0, st>>>(src, dst, c->srcIdx, n, c->dS, c->trackIds ? c->pid[c->cur_buf] : nullptr,
+                                               c->pid[1 - c->cur_buf]); c->launches++;
+    }
+    scalars_to_host(c);
+    c->np = c->hS->numParticles;
+    c->cur_buf = 1 - c->cur_buf;
+}
+
+void particles_upload_aos(flip_ctx *c, const float *aos6, int n) {
+    particles_alloc(c, n);
+    c->np = n;
+    if (n > 0) {
+        float *tmp = nullptr;
+        FLIP_CUDA_CHECK(cudaMalloc(&tmp, sizeof(float) * 6ll * n));
+        FLIP_CUDA_CHECK(cudaMemcpyAsync(tmp, aos6, sizeof(float) * 6ll * n, cudaMemcpyHostToDevice, c->stream));
+        k_aos_to_soa<<<cdiv(n, TPB), TPB, 0, c->stream>>>(tmp, n, c->P[c->cur_buf]); c->launches++;
+        if (c->trackIds) { k_iota<<<cdiv(n, TPB), TPB, 0, c->stream>>>(c->pid[c->cur_buf], n); c->launches++; }
+        FLIP_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        cudaFree(tmp);
+    }
+    particles_sort(c, false, 0.0);
+}
+
+void particles_upload_split(flip_ctx *c, const float *pos, const float *vel, int n) {
+    particles_alloc(c, n);
+    c->np = n;
+    if (n > 0) {
+        float *tp = nullptr, *tv = nullptr;
+        FLIP_CUDA_CHECK(cudaMalloc(&tp, sizeof(float) * 3ll * n));
+        FLIP_CUDA_CHECK(cudaMalloc(&tv, sizeof(float) * 3ll * n));
+        FLIP_CUDA_CHECK(cudaMemcpyAsync(tp, pos, sizeof(float) * 3ll * n, cudaMemcpyHostToDevice, c->stream));
+        FLIP_CUDA_CHECK(cudaMemcpyAsync(tv, vel, sizeof(float) * 3ll * n, cudaMemcpyHostToDevice, c->stream));
+        k_split_to_soa<<<cdiv(n, TPB), TPB, 0, c->stream>>>(tp, tv, n, c->P[c->cur_buf]); c->launches++;
+        if (c->trackIds) { k_iota<<<cdiv(n, TPB), TPB, 0, c->stream>>>(c->pid[c->cur_buf], n); c->launches++; }
+        FLIP_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        cudaFree(tp); cudaFree(tv);
+    }
+    particles_sort(c, false, 0.0);
+}
+
+void particles_download_aos(flip_ctx *c, float *aos6) {
+    int n = c->np;
+    if (n == 0) return;
+    float *tmp = nullptr;
+    FLIP_CUDA_CHECK(cudaMalloc(&tmp, sizeof(float) * 6ll * n));
+    k_soa_to_aos<<<cdiv(n, TPB), TPB, 0, c->stream>>>(c->P[c->cur_buf], n, tmp); c->launches++;
+    FLIP_CUDA_CHECK(cudaMemcpyAsync(aos6, tmp, sizeof(float) * 6ll * n, cudaMemcpyDeviceToHost, c->stream));
+    FLIP_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    cudaFree(tmp);
+}
+
+void particles_download_ids(flip_ctx *c, int *ids) {
+    if (c->np == 0) return;
+    FLIP_CUDA_CHECK(cudaMemcpyAsync(ids, c->pid[c->cur_buf], sizeof(int) * c->np, cudaMemcpyDeviceToHost, c->stream));
+    FLIP_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+}
+
+void particles_download_component(flip_ctx *c, float *xyz, int which) {
+    int n = c->np;
+    if (n == 0) return;
+    float *tmp = nullptr;
+    FLIP_CUDA_CHECK(cudaMalloc(&tmp, sizeof(float) * 3ll * n));
+    const ParticleSoA &p = c->P[c->cur_buf];
+    if (which == 0) k_soa_to_xyz<<<cdiv(n, TPB), TPB, 0, c->stream>>>(p.px, p.py, p.pz, n, tmp);
+    else k_soa_to_xyz<<<cdiv(n, TPB), TPB, 0, c->stream>>>(p.vx, p.vy, p.vz, n, tmp);
+    c->launches++;
+    FLIP_CUDA_CHECK(cudaMemcpyAsync(xyz, tmp, sizeof(float) * 3ll * n, cudaMemcpyDeviceToHost, c->stream));
+    FLIP_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    cudaFree(tmp);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Liquid SDF + P2G gather over cell-sorted particles.
+//
+// One thread per point (i,j,k) of the extended index space (I+1)x(J+1)x(K+1).  The thread owns
+//   phi(i,j,k)                (if i<I, j<J, k<K)   ParticleLevelSet min-splat  particlelevelset.cpp:582-630
+//   U(i,j,k), V(i,j,k), W(i,j,k) (where in range)  VelocityAdvector radial splat velocityadvector.cpp:390-459
+// and visits the particles of the 3x3x3 cells around (i,j,k) (every particle that can reach the
+// three faces lies there because r = 0.866dx < dx); the SDF's 5x5x5 box is completed in a second
+// phase only when the nearest particle so far is farther than 1.5dx (then particles outside 3x3x3
+// could be nearer).  Summation order per face = cell order (k,j,i) then index order inside a cell:
+// fixed, hence deterministic (the reference sums in particle-index order inside a 10^3 block; the
+// difference is float summation order only, SURVEY §7 hard part 3).
+//
+// Arithmetic restated literally: the reference works in coordinates local to a
+// 10-cell block; `p - offset`, `- blockOrigin`, node position `(float)l*dx` are evaluated here in
+// the same order and precision, so results are bit-identical per term for any dx.
+// ------------------------------------------------------------------------------------------------
+struct GatherParams {
+    int I, J, K;
+    double dx, invdx;
+    float hw;             // (float)(0.5*dx): _getDirectionOffset, velocityadvector.cpp:153-164
+    double blockdxP2G;    // _chunkWidth * _dx (double)            velocityadvector.cpp:411
+    double blockdxSDF;    // _blockwidth * _dx (double)            particlelevelset.cpp:593
+    double invBlockdxSDF; // 1.0 / (double)(float)(_blockwidth*_dx) particlelevelset.cpp:483,487
+    float r, rsq, coef1, coef2, coef3, eps;   // velocityadvector.cpp:393-399
+    float rS, srS;        // SDF radius (float) and search radius 2r particlelevelset.cpp:592-594
+    float maxDist;        // 3dx  particlelevelset.cpp:295
+    float hwS;            // cell-centre half width as added in double (GridIndexToCellCenter grid3d.h:101)
+    float halfDxSolid;    // post-process thresholds
+};
+
+__device__ __forceinline__ float kernel_weight(float d2, const GatherParams &g) {
+    // 1.0f - coef1*d2*d2*d2 + coef2*d2*d2 - coef3*d2, left to right (velocityadvector.cpp:437)
+    float a = fmul(fmul(fmul(g.coef1, d2), d2), d2);
+    float b = fmul(fmul(g.coef2, d2), d2);
+    float cc = fmul(g.coef3, d2);
+    return fsub(fadd(fsub(1.0f, a), b), cc);
+}
+
+__global__ void __launch_bounds__(128) k_sdf_p2g(ParticleSoA p, const int *__restrict__ cellStart, GatherParams g,
+                                                 float *__restrict__ U, float *__restrict__ V, float *__restrict__ W,
+                                                 unsigned char *__restrict__ validU, unsigned char *__restrict__ validV,
+                                                 unsigned char *__restrict__ validW, float *__restrict__ phiL,
+                                                 const float *__restrict__ phiS) {
+    const int I = g.I, J = g.J, K = g.K;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int j = blockIdx.y, k = blockIdx.z;
+    if (i > I) return;
+    const bool hasU = (j < J && k < K);
+    const bool hasV = (i < I && k < K);
+    const bool hasW = (i < I && j < J);
+    const bool hasC = (i < I && j < J && k < K);
+
+    // block of this node per axis and local node coordinate (the three components and the cell
+    // share (i,j,k), blocks are 10 wide for both subsystems)
+    const int bi = i / 10, bj = j / 10, bk = k / 10;
+    const int li = i - bi * 10, lj = j - bj * 10, lk = k - bk * 10;
+    // block origins  (float)bi * blockdx  -> float  (grid3d.h:81-83)
+    const float oxP = (float)dmul((double)(float)bi, g.blockdxP2G);
+    const float oyP = (float)dmul((double)(float)bj, g.blockdxP2G);
+    const float ozP = (float)dmul((double)(float)bk, g.blockdxP2G);
+    // node position (float)l*dx -> float   (grid3d.h:81)
+    const float gx = (float)dmul((double)(float)li, g.dx);
+    const float gy = (float)dmul((double)(float)lj, g.dx);
+    const float gz = (float)dmul((double)(float)lk, g.dx);
+    // cell centre (float)l*dx + hw in double -> float  (grid3d.h:101-104)
+    const double hwd = 0.5 * g.dx;
+    const float cx = (float)dadd(dmul((double)(float)li, g.dx), hwd);
+    const float cy = (float)dadd(dmul((double)(float)lj, g.dx), hwd);
+    const float cz = (float)dadd(dmul((double)(float)lk, g.dx), hwd);
+
+    float su = 0.f, wu = 0.f, sv = 0.f, wv = 0.f, sw = 0.f, ww = 0.f;
+    float best2 = 3.0e38f;   // min squared distance cell centre <-> particle (block-local arithmetic)
+
+    const int jlo = max(j - 1, 0), jhi = min(j + 1, J - 1);
+    const int klo = max(k - 1, 0), khi = min(k + 1, K - 1);
+    const int ilo = max(i - 1, 0), ihi = min(i + 1, I - 1);
+    for (int ck = klo; ck <= khi; ck++) {
+        for (int cj = jlo; cj <= jhi; cj++) {
+            int rowBase = I * (cj + J * ck);
+            int qb = __ldg(cellStart + rowBase + ilo);
+            int qe = __ldg(cellStart + rowBase + ihi + 1);
+            for (int q = qb; q < qe; q++) {
+                float x = __ldg(p.px + q), y = __ldg(p.py + q), z = __ldg(p.pz + q);
+                // block-local particle coordinates for the P2G components: (p - offset) - origin
+                float xl = fsub(x, oxP), yl = fsub(y, oyP), zl = fsub(z, ozP);                 // offset 0 on that axis
+                float xh = fsub(fsub(x, g.hw), oxP), yh = fsub(fsub(y, g.hw), oyP), zh = fsub(fsub(z, g.hw), ozP);
+                // v = gpos - p
+                float ax = fsub(gx, xl), ay = fsub(gy, yl), az = fsub(gz, zl);
+                float bx = fsub(gx, xh), by = fsub(gy, yh), bz = fsub(gz, zh);
+                float ax2 = fmul(ax, ax), ay2 = fmul(ay, ay), az2 = fmul(az, az);
+                float bx2 = fmul(bx, bx), by2 = fmul(by, by), bz2 = fmul(bz, bz);
+                float d2u = fadd(fadd(ax2, by2), bz2);
+                float d2v = fadd(fadd(bx2, ay2), bz2);
+                float d2w = fadd(fadd(bx2, by2), az2);
+                if (d2u < g.rsq) { float w = kernel_weight(d2u, g); su = fadd(su, fmul(w, __ldg(p.vx + q))); wu = fadd(wu, w); }
+                if (d2v < g.rsq) { float w = kernel_weight(d2v, g); sv = fadd(sv, fmul(w, __ldg(p.vy + q))); wv = fadd(wv, w); }
+                if (d2w < g.rsq) { float w = kernel_weight(d2w, g); sw = fadd(sw, fmul(w, __ldg(p.vz + q))); ww = fadd(ww, w); }
+                // SDF: all particles of the 3x3x3 neighbourhood are inside the reference's search box
+                // (|c-p|_inf < 1.5dx < 2r+0.5dx); block origin is the same number for both subsystems
+                float ex = fsub(cx, xl), ey = fsub(cy, yl), ez = fsub(cz, zl);
+                float d2c = lengthsq3(ex, ey, ez);
+                best2 = fminf(best2, d2c);
+            }
+        }
+    }
+
+    if (hasU) {
+        long long idx = (long long)i + (long long)(I + 1) * (j + (long long)J * k);
+        bool ok = wu > g.eps;
+        U[idx] = ok ? __fdiv_rn(su, wu) : su;     // scalar /= weight only if weight > eps (:448-453)
+        validU[idx] = ok ? 1 : 0;
+    }
+    if (hasV) {
+        long long idx = (long long)i + (long long)I * (j + (long long)(J + 1) * k);
+        bool ok = wv > g.eps;
+        V[idx] = ok ? __fdiv_rn(sv, wv) : sv;
+        validV[idx] = ok ? 1 : 0;
+    }
+    if (hasW) {
+        long long idx = (long long)i + (long long)I * (j + (long long)J * k);
+        bool ok = ww > g.eps;
+        W[idx] = ok ? __fdiv_rn(sw, ww) : sw;
+        validW[idx] = ok ? 1 : 0;
+    }
+    if (!hasC) return;
+
+    // ---- SDF phase 2: particles outside the 3x3x3 neighbourhood can only matter if nothing nearer
+    // than 1.5dx was found (they are at least 1.5dx away along one axis).
+    float thr = fmul(fmul(1.45f, (float)g.dx), fmul(1.45f, (float)g.dx));
+    if (!(best2 < thr)) {
+        const float sr = g.srS;
+        const double invdx = g.invdx;
+        const int j2lo = max(j - 2, 0), j2hi = min(j + 2, J - 1);
+        const int k2lo = max(k - 2, 0), k2hi = min(k + 2, K - 1);
+        const int i2lo = max(i - 2, 0), i2hi = min(i + 2, I - 1);
+        for (int ck = k2lo; ck <= k2hi; ck++) {
+            for (int cj = j2lo; cj <= j2hi; cj++) {
+                bool innerRow = (ck >= klo && ck <= khi && cj >= jlo && cj <= jhi);
+                int rowBase = I * (cj + J * ck);
+                int qb = __ldg(cellStart + rowBase + i2lo);
+                int qe = __ldg(cellStart + rowBase + i2hi + 1);
+                int sb = 0, se = 0;   // range already visited in phase 1 (skip)
+                if (innerRow) { sb = __ldg(cellStart + rowBase + ilo); se = __ldg(cellStart + rowBase + ihi + 1); }
+                for (int q = qb; q < qe; q++) {
+                    if (innerRow && q >= sb && q < se) { q = se - 1; continue; }
+                    float x = __ldg(p.px + q), y = __ldg(p.py + q), z = __ldg(p.pz + q);
+                    // block membership of the particle (particlelevelset.cpp:476-513): the blocks
+                    // overlapped by [p-sr, p+sr] in global coordinates
+                    int bminx = pos2idx_d((double)fsub(x, sr), g.invBlockdxSDF), bmaxx = pos2idx_d((double)fadd(x, sr), g.invBlockdxSDF);
+                    int bminy = pos2idx_d((double)fsub(y, sr), g.invBlockdxSDF), bmaxy = pos2idx_d((double)fadd(y, sr), g.invBlockdxSDF);
+                    int bminz = pos2idx_d((double)fsub(z, sr), g.invBlockdxSDF), bmaxz = pos2idx_d((double)fadd(z, sr), g.invBlockdxSDF);
+                    if (bi < bminx || bi > bmaxx || bj < bminy || bj > bmaxy || bk < bminz || bk > bmaxz) continue;
+                    // block-local search box (particlelevelset.cpp:596-607)
+                    float xl = fsub(x, oxP), yl = fsub(y, oyP), zl = fsub(z, ozP);
+                    int gminx = pos2idx(fsub(xl, sr), invdx), gmaxx = pos2idx(fadd(xl, sr), invdx);
+                    int gminy = pos2idx(fsub(yl, sr), invdx), gmaxy = pos2idx(fadd(yl, sr), invdx);
+                    int gminz = pos2idx(fsub(zl, sr), invdx), gmaxz = pos2idx(fadd(zl, sr), invdx);
+                    if (li < gminx || li > gmaxx || lj < gminy || lj > gmaxy || lk < gminz || lk > gmaxz) continue;
+                    float ex = fsub(cx, xl), ey = fsub(cy, yl), ez = fsub(cz, zl);
+                    best2 = fminf(best2, lengthsq3(ex, ey, ez));
+                }
+            }
+        }
+    }
+    // dist = length(gpos - p) - r ; phi = min(3dx, dist)   (particlelevelset.cpp:615-621, :295)
+    float phi = g.maxDist;
+    if (best2 < 1.0e38f) {
+        float dist = fsub(__fsqrt_rn(best2), g.rS);
+        if (dist < phi) phi = dist;
+    }
+    // postProcessSignedDistanceField (particlelevelset.cpp:172-196)
+    {
+        double dxd = g.dx;
+        if ((double)phi < 0.5 * dxd) {
+            // MeshLevelSet::getDistanceAtCellCenter  meshlevelset.cpp:152-162
+            int ni = I + 1;
+            long long nj = (long long)(I + 1) * (J + 1);
+            long long n0 = (long long)i + (long long)ni * j + nj * k;
+            float s = __ldg(phiS + n0);
+            s = fadd(s, __ldg(phiS + n0 + 1));
+            s = fadd(s, __ldg(phiS + n0 + ni));
+            s = fadd(s, __ldg(phiS + n0 + ni + 1));
+            s = fadd(s, __ldg(phiS + n0 + nj));
+            s = fadd(s, __ldg(phiS + n0 + nj + 1));
+            s = fadd(s, __ldg(phiS + n0 + nj + ni));
+            s = fadd(s, __ldg(phiS + n0 + nj + ni + 1));
+            if (fmul(0.125f, s) < 0.0f) phi = (float)dmul((double)-0.5f, dxd);
+        }
+        float epsf = (float)(0.005 * dxd);
+        if (fabsf(phi) < epsf) phi = (phi > 0.0f) ? epsf : -epsf;
+    }
+    phiL[(long long)i + (long long)I * (j + (long long)J * k)] = phi;
+}
+
+static GatherParams make_gather_params(const flip_ctx *c) {
+    const Dims &d = c->d;
+    GatherParams g;
+    g.I = d.I; g.J = d.J; g.K = d.K;
+    g.dx = d.dx; g.invdx = 1.0 / d.dx;
+    g.hw = (float)(0.5 * d.dx);
+    g.blockdxP2G = 10 * d.dx;
+    g.blockdxSDF = 10 * d.dx;
+    float blockdxf = (float)(10 * d.dx);
+    g.invBlockdxSDF = 1.0 / (double)blockdxf;
+    float r = (float)c->liquidRadius;
+    g.r = r; g.rsq = r * r;
+    g.eps = 1e-6f;
+    g.coef1 = (4.0f / 9.0f) * (1.0f / (r * r * r * r * r * r));
+    g.coef2 = (17.0f / 9.0f) * (1.0f / (r * r * r * r));
+    g.coef3 = (22.0f / 9.0f) * (1.0f / (r * r));
+    g.rS = r;
+    g.srS = 2.0f * r;
+    g.maxDist = (float)(3.0 * d.dx);
+    g.hwS = (float)(0.5 * d.dx);
+    g.halfDxSolid = 0;
+    return g;
+}
+
+// The SDF and the P2G are produced by the same gather; the stage that runs first computes both.
+static void run_sdf_p2g(flip_ctx *c) {
+    const Dims &d = c->d;
+    GatherParams g = make_gather_params(c);
+    dim3 block(128, 1, 1);
+    dim3 grid(cdiv(d.I + 1, 128), d.J + 1, d.K + 1);
+    k_sdf_p2g<<<grid, block, 0, c->stream>>>(c->P[c->cur_buf], c->cellStart, g, c->U, c->V, c->W, c->validU, c->validV,
+                                             c->validW, c->phiL, c->phiS);
+    c->launches++;
+    FLIP_CUDA_CHECK(cudaGetLastError());
+}
+
+void stage_liquid_sdf(flip_ctx *c) { run_sdf_p2g(c); }
+
+// _advectVelocityField (fluidsimulation.cpp:3253-3278): valid.reset(); MAC.clear(); advect().
+// The fused gather of stage_liquid_sdf already produced U,V,W and the valid masks from the same
+// particle state, so this stage has nothing left to launch.  (When driven stage by stage the
+// arrays can be read back here and compared with VelocityAdvector::advect.)
+void stage_p2g(flip_ctx *c) { (void)c; }
+
+// ------------------------------------------------------------------------------------------------
+// G2P (PIC/FLIP) and RK3 advection + collision
+// ------------------------------------------------------------------------------------------------
+struct AdvectParams {
+    int n;
+    int I, J, K;
+    double dx, invdx, hdx;
+    float ratioPIC, ratioFLIP;     // (float)_ratioPICFLIP, (float)(1 - _ratioPICFLIP)   :4088
+    float c1, c2, c3;              // (float)(0.5*dt), (float)(0.75*dt), (float)(dt/9.0f) :4191-4196
+    // boundary box after expand(-3dx-1e-4) and expand(-solidBufferWidth*dx)  (:2834-2839, :4214-4215)
+    float bminx, bminy, bminz;     // AABB::position (vec3, float)
+    double bw, bh, bd;             // AABB::width/height/depth (double)
+    double nearCell, invNearCell;  // _nearSolidGridCellSize
+    int nsI, nsJ, nsK;
+    float stepDistance;            // _markerParticleStepDistanceFactor * (float)_dx
+    float maxResolvedDistance;     // _CFLConditionNumber * _dx
+    double pushOut;                // _solidBufferWidth * _dx (float*double -> double)
+};
+
+__global__ void k_g2p(ParticleSoA p, AdvectParams a, MacField fnew, MacField fold) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.n) return;
+    float x = p.px[t], y = p.py[t], z = p.pz[t];
+    float nx, ny, nz, ox, oy, oz;
+    sample_velocity(fnew, a.I, a.J, a.K, a.dx, a.invdx, a.hdx, x, y, z, nx, ny, nz);
+    sample_velocity(fold, a.I, a.J, a.K, a.dx, a.invdx, a.hdx, x, y, z, ox, oy, oz);
+    // vFLIP = v + vPIC - vOld ; v = ratio*vPIC + (1-ratio)*vFLIP   (fluidsimulation.cpp:4084-4090)
+    float fx = fsub(fadd(p.vx[t], nx), ox);
+    float fy = fsub(fadd(p.vy[t], ny), oy);
+    float fz = fsub(fadd(p.vz[t], nz), oz);
+    p.vx[t] = fadd(fmul(a.ratioPIC, nx), fmul(a.ratioFLIP, fx));
+    p.vy[t] = fadd(fmul(a.ratioPIC, ny), fmul(a.ratioFLIP, fy));
+    p.vz[t] = fadd(fmul(a.ratioPIC, nz), fmul(a.ratioFLIP, fz));
+}
+
+// AABB::isPointInside  aabb.cpp:130-133
+__device__ __forceinline__ bool box_inside(const AdvectParams &a, float x, float y, float z) {
+    return x >= a.bminx && y >= a.bminy && z >= a.bminz && (double)x < dadd((double)a.bminx, a.bw) &&
+           (double)y < dadd((double)a.bminy, a.bh) && (double)z < dadd((double)a.bminz, a.bd);
+}
+// AABB::getNearestPointInsideAABB(p, 1e-6)  aabb.cpp:497-518
+__device__ __forceinline__ void box_nearest(const AdvectParams &a, float &x, float &y, float &z) {
+    if (box_inside(a, x, y, z)) return;
+    float maxx = fadd(a.bminx, (float)a.bw), maxy = fadd(a.bminy, (float)a.bh), maxz = fadd(a.bminz, (float)a.bd);
+    const double eps = 1e-6;
+    x = fmaxf(x, a.bminx); y = fmaxf(y, a.bminy); z = fmaxf(z, a.bminz);
+    x = (float)fmin((double)x, dsub((double)maxx, eps));
+    y = (float)fmin((double)y, dsub((double)maxy, eps));
+    z = (float)fmin((double)z, dsub((double)maxz, eps));
+}
+
+__device__ __forceinline__ bool near_solid(const unsigned char *__restrict__ ns, const AdvectParams &a, float x, float y, float z) {
+    int i = pos2idx(x, a.invNearCell), j = pos2idx(y, a.invNearCell), k = pos2idx(z, a.invNearCell);
+    if (i < 0 || j < 0 || k < 0 || i >= a.nsI || j >= a.nsJ || k >= a.nsK) return false;
+    return __ldg(ns + i + a.nsI * (j + a.nsJ * k)) != 0;
+}
+
+// FluidSimulation::_resolveCollision  fluidsimulation.cpp:4221-4296
+__device__ void resolve_collision(const AdvectParams &a, const float *__restrict__ phiS,
+                                  const unsigned char *__restrict__ ns, float ox, float oy, float oz, float &nx,
+                                  float &ny, float &nz) {
+    const int gi = a.I + 1, gj = a.J + 1, gk = a.K + 1;
+    int ci = pos2idx(nx, a.invdx), cj = pos2idx(ny, a.invdx), ck = pos2idx(nz, a.invdx);
+    if (!(ci >= 0 && cj >= 0 && ck >= 0 && ci < a.I && cj < a.J && ck < a.K)) box_nearest(a, nx, ny, nz);
+    if (!near_solid(ns, a, ox, oy, oz) && !near_solid(ns, a, nx, ny, nz)) return;
+
+    const float eps = 1e-6f;
+    float dxv = fsub(nx, ox), dyv = fsub(ny, oy), dzv = fsub(nz, oz);
+    float travel = length3(dxv, dyv, dzv);
+    if (travel < eps) return;
+    int numSteps = (int)ceilf(__fdiv_rn(travel, a.stepDistance));
+    // (newp - oldp).normalize(): v * (float)(1.0/len)   vmath.cpp:100-103
+    float inv = (float)(1.0 / (double)travel);
+    float sx = fmul(dxv, inv), sy = fmul(dyv, inv), sz = fmul(dzv, inv);
+
+    float lx = ox, ly = oy, lz = oz;   // lastPosition
+    float cx = 0.f, cy = 0.f, cz = 0.f;
+    bool found = false;
+    float collisionPhi = 0.0f;
+    ScalarSample smp;
+    for (int s = 0; s < numSteps; s++) {
+        if (s == numSteps - 1) { cx = nx; cy = ny; cz = nz; }
+        else {
+            float f = fmul((float)(s + 1), a.stepDistance);
+            cx = fadd(ox, fmul(sx, f)); cy = fadd(oy, fmul(sy, f)); cz = fadd(oz, fmul(sz, f));
+        }
+        fetch_scalar(phiS, gi, gj, gk, a.dx, a.invdx, cx, cy, cz, smp);
+        float phi = scalar_value(smp);
+        if (phi < 0.0f || !box_inside(a, cx, cy, cz)) { collisionPhi = phi; found = true; break; }
+        lx = cx; ly = cy; lz = cz;
+    }
+    if (!found) return;
+
+    float rx, ry, rz;
+    float gx, gy, gz;
+    scalar_gradient(smp, gx, gy, gz);
+    if (length3(gx, gy, gz) > eps) {
+        float glen = length3(gx, gy, gz);
+        float ginv = (float)(1.0 / (double)glen);
+        gx = fmul(gx, ginv); gy = fmul(gy, ginv); gz = fmul(gz, ginv);
+        // currentPosition - (collisionPhi - _solidBufferWidth*_dx) * grad : the scalar is double, narrowed
+        // to float by operator*(float, vec3)
+        float sc = (float)dsub((double)collisionPhi, a.pushOut);
+        rx = fsub(cx, fmul(gx, sc)); ry = fsub(cy, fmul(gy, sc)); rz = fsub(cz, fmul(gz, sc));
+        float rphi = sample_scalar(phiS, gi, gj, gk, a.dx, a.invdx, rx, ry, rz);
+        float rdist = length3(fsub(rx, cx), fsub(ry, cy), fsub(rz, cz));
+        if (rphi < 0 || rdist > a.maxResolvedDistance) { rx = lx; ry = ly; rz = lz; }
+    } else {
+        rx = lx; ry = ly; rz = lz;
+    }
+    if (!box_inside(a, rx, ry, rz)) {
+        float qx = rx, qy = ry, qz = rz;
+        box_nearest(a, rx, ry, rz);
+        float rphi = sample_scalar(phiS, gi, gj, gk, a.dx, a.invdx, rx, ry, rz);
+        float rdist = length3(fsub(rx, qx), fsub(ry, qy), fsub(rz, qz));
+        if (rphi < 0.0f || rdist > a.maxResolvedDistance) { rx = lx; ry = ly; rz = lz; }
+    }
+    nx = rx; ny = ry; nz = rz;
+}
+
+__global__ void k_advance(ParticleSoA p, AdvectParams a, MacField f, const float *__restrict__ phiS,
+                          const unsigned char *__restrict__ ns) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.n) return;
+    float x = p.px[t], y = p.py[t], z = p.pz[t];
+    // _RK3  fluidsimulation.cpp:4191-4198
+    float k1x, k1y, k1z, k2x, k2y, k2z, k3x, k3y, k3z;
+    sample_velocity(f, a.I, a.J, a.K, a.dx, a.invdx, a.hdx, x, y, z, k1x, k1y, k1z);
+    sample_velocity(f, a.I, a.J, a.K, a.dx, a.invdx, a.hdx, fadd(x, fmul(k1x, a.c1)), fadd(y, fmul(k1y, a.c1)),
+                    fadd(z, fmul(k1z, a.c1)), k2x, k2y, k2z);
+    sample_velocity(f, a.I, a.J, a.K, a.dx, a.invdx, a.hdx, fadd(x, fmul(k2x, a.c2)), fadd(y, fmul(k2y, a.c2)),
+                    fadd(z, fmul(k2z, a.c2)), k3x, k3y, k3z);
+    float sx = fadd(fadd(fmul(k1x, 2.0f), fmul(k2x, 3.0f)), fmul(k3x, 4.0f));
+    float sy = fadd(fadd(fmul(k1y, 2.0f), fmul(k2y, 3.0f)), fmul(k3y, 4.0f));
+    float sz = fadd(fadd(fmul(k1z, 2.0f), fmul(k2z, 3.0f)), fmul(k3z, 4.0f));
+    float nx = fadd(x, fmul(sx, a.c3)), ny = fadd(y, fmul(sy, a.c3)), nz = fadd(z, fmul(sz, a.c3));
+    resolve_collision(a, phiS, ns, x, y, z, nx, ny, nz);
+    p.px[t] = nx; p.py[t] = ny; p.pz[t] = nz;
+}
+
+static AdvectParams make_advect_params(const flip_ctx *c, double dt) {
+    const Dims &d = c->d;
+    AdvectParams a;
+    a.n = c->np;
+    a.I = d.I; a.J = d.J; a.K = d.K;
+    a.dx = d.dx; a.invdx = 1.0 / d.dx; a.hdx = 0.5 * d.dx;
+    a.ratioPIC = (float)c->ratioPICFLIP;
+    a.ratioFLIP = (float)(1 - c->ratioPICFLIP);
+    a.c1 = (float)(0.5 * dt);
+    a.c2 = (float)(0.75 * dt);
+    a.c3 = (float)(dt / 9.0f);
+    // _getBoundaryAABB + expand(-_solidBufferWidth*_dx): AABB::expand (aabb.cpp:122-128) with vec3 float position
+    {
+        float px = 0.f, py = 0.f, pz = 0.f;
+        double w = d.I * d.dx, h = d.J * d.dx, dp = d.K * d.dx;
+        auto expand = [&](double v) {
+            double hh = 0.5 * v;
+            float hf = (float)hh;
+            px = px - hf; py = py - hf; pz = pz - hf;
+            w += v; h += v; dp += v;
+        };
+        double eps = 1e-4;
+        expand(-3 * d.dx - eps);
+        expand(-(double)(float)c->solidBufferWidth * d.dx);
+        a.bminx = px; a.bminy = py; a.bminz = pz;
+        a.bw = w; a.bh = h; a.bd = dp;
+    }
+    a.nearCell = c->nearSolidFactor * d.dx;
+    a.invNearCell = 1.0 / a.nearCell;
+    a.nsI = c->nsI; a.nsJ = c->nsJ; a.nsK = c->nsK;
+    a.stepDistance = c->markerParticleStepDistanceFactor * (float)d.dx;
+    a.maxResolvedDistance = (float)(c->CFL * d.dx);
+    a.pushOut = (double)(float)c->solidBufferWidth * d.dx;
+    return a;
+}
+
+void stage_g2p(flip_ctx *c) {
+    if (c->np == 0) return;
+    AdvectParams a = make_advect_params(c, 0.0);
+    MacField fn{c->U, c->V, c->W}, fo{c->sU, c->sV, c->sW};
+    k_g2p<<<cdiv(c->np, TPB), TPB, 0, c->stream>>>(c->P[c->cur_buf], a, fn, fo);
+    c->launches++;
+    FLIP_CUDA_CHECK(cudaGetLastError());
+}
+
+void stage_advance(flip_ctx *c, double dt) {
+    if (c->np > 0) {
+        AdvectParams a = make_advect_params(c, dt);
+        MacField fn{c->U, c->V, c->W};
+        k_advance<<<cdiv(c->np, TPB), TPB, 0, c->stream>>>(c->P[c->cur_buf], a, fn, c->phiS, c->nearSolid);
+        c->launches++;
+        FLIP_CUDA_CHECK(cudaGetLastError());
+    }
+    // _removeMarkerParticles(_currentFrameDeltaTime) + re-sort for the next step
+    particles_sort(c, true, c->frameDt);
+}
+
+}  // namespace flip

@@ -1,0 +1,568 @@
+// Variational pressure projection (PressureSolver::solve, pressuresolver.cpp:44-77) as a
+// matrix-free 7-point PCG on the GPU.
+//
+// Layout.  All solver vectors are dense over the cells of the grid and indexed by the flat cell id
+// c = i + I*(j + J*k), so the six neighbours of a row are at c+-1, c+-I, c+-I*J and no column
+// indices are stored.  Work is driven by the list of ACTIVE SEGMENTS: aligned runs of 32
+// consecutive cell ids that contain at least one pressure row, each with a 32-bit lane mask; one
+// warp processes one segment.  The matrix is kept as the diagonal (fp64) plus, per cell, the three
+// float face weights towards +i,+j,+k masked to zero where the neighbour is not a row; the
+// off-diagonal is -(double)w * dt/dx^2, formed on the fly exactly as the reference forms it
+// (pressuresolver.cpp:723-808).  Algorithmic traffic of one operator application: 36 B/row.
+//
+// The reference's preconditioner is a serial MIC(0) (pcgsolver.h:69-221); here it is replaced by a
+// GPU-parallel one (Jacobi, or an aggregation multigrid V-cycle in fp32).  The Krylov vectors,
+// the residual test (||r||_inf <= tol*||b||_inf, pcgsolver.h:262-288), the iteration cap and the
+// "acceptable" fallback (pressuresolver.cpp:810-840) are the reference's, in fp64.
+#include <cub/device/device_scan.cuh>
+#include <cstring>
+#include "device_math.cuh"
+#include "flip_internal.h"
+
+namespace flip {
+
+static constexpr int TPB = 256;
+static constexpr int WPB = TPB / 32;
+
+struct PGrid {
+    int I, J, K;
+    int sj, sk;   // strides I, I*J
+};
+
+__device__ __forceinline__ bool is_row(const float *__restrict__ phi, const PGrid &g, int c) {
+    int i = c % g.I;
+    int j = (c / g.I) % g.J;
+    int k = c / g.sk;
+    return i >= 1 && j >= 1 && k >= 1 && i < g.I - 1 && j < g.J - 1 && k < g.K - 1 && __ldg(phi + c) < 0.0f;
+}
+
+// ---- 1. rows -> segments (pressuresolver.cpp:101-114: cells with phi<0 in [1,N-2]^3, (k,j,i) order)
+__global__ void k_seg_flag(const float *__restrict__ phi, PGrid g, int nC, int nSeg, unsigned int *__restrict__ mask,
+                           int *__restrict__ flag, DeviceScalars *S) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (warp >= nSeg) return;
+    int c = warp * 32 + lane;
+    bool row = (c < nC) && is_row(phi, g, c);
+    unsigned int m = __ballot_sync(0xffffffffu, row);
+    if (lane == 0) {
+        mask[warp] = m;
+        flag[warp] = m ? 1 : 0;
+        if (m) atomicAdd(&S->numRows, __popc(m));
+    }
+}
+
+__global__ void k_seg_compact(int nSeg, const unsigned int *__restrict__ mask, const int *__restrict__ flag,
+                              const int *__restrict__ pos, int *__restrict__ segCell, unsigned int *__restrict__ segMask,
+                              DeviceScalars *S) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nSeg) return;
+    if (flag[s]) {
+        int o = pos[s];
+        segCell[o] = s * 32;
+        segMask[o] = mask[s];
+    }
+    if (s == nSeg - 1) S->numSegments = pos[s] + flag[s];
+}
+
+// ---- 2. right-hand side and matrix
+struct BuildParams {
+    PGrid g;
+    double invdx;     // 1.0/_dx                    pressuresolver.cpp:582
+    double factor;    // _deltaTime/(_dx*_dx)       pressuresolver.cpp:725
+};
+
+__global__ void k_build_system(const int *__restrict__ segCell, const unsigned int *__restrict__ segMask,
+                               BuildParams bp, const float *__restrict__ phi,
+                               const float *__restrict__ U, const float *__restrict__ V, const float *__restrict__ W,
+                               const float *__restrict__ wU, const float *__restrict__ wV, const float *__restrict__ wW,
+                               double *__restrict__ Adiag, float *__restrict__ AoffU, float *__restrict__ AoffV,
+                               float *__restrict__ AoffW, double *__restrict__ b, double *__restrict__ x,
+                               DeviceScalars *S) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (warp >= S->numSegments) return;
+    const PGrid &g = bp.g;
+    int c = segCell[warp] + lane;
+    bool row = (segMask[warp] >> lane) & 1u;
+    double babs = 0.0;
+    if (row) {
+        int i = c % g.I, j = (c / g.I) % g.J, k = c / g.sk;
+        long long fu = (long long)i + (long long)(g.I + 1) * (j + (long long)g.J * k);
+        long long fv = (long long)i + (long long)g.I * (j + (long long)(g.J + 1) * k);
+        long long fw = c;
+        double volRight = wU[fu + 1], volLeft = wU[fu];
+        double volTop = wV[fv + g.I], volBottom = wV[fv];
+        double volFront = wW[fw + g.sk], volBack = wW[fw];
+        // _calculateNegativeDivergenceVectorThread  pressuresolver.cpp:580-613 (static solids: the
+        // solid-velocity terms are +-0)
+        double f = bp.invdx;
+        double div = 0.0;
+        div = dadd(div, dmul(dmul(-f, volRight), (double)U[fu + 1]));
+        div = dadd(div, dmul(dmul(f, volLeft), (double)U[fu]));
+        div = dadd(div, dmul(dmul(-f, volTop), (double)V[fv + g.I]));
+        div = dadd(div, dmul(dmul(f, volBottom), (double)V[fv]));
+        div = dadd(div, dmul(dmul(-f, volFront), (double)W[fw + g.sk]));
+        div = dadd(div, dmul(dmul(f, volBack), (double)W[fw]));
+        b[c] = div;
+        x[c] = 0.0;
+        babs = fabs(div);
+
+        // _calculateMatrixCoefficientsThread  pressuresolver.cpp:723-808
+        const double eps = 1e-9, maxtheta = 25.0;
+        double factor = bp.factor;
+        double phiC = phi[c];
+        double diag = dmul(dadd(dadd(dadd(dadd(dadd(volRight, volLeft), volTop), volBottom), volFront), volBack), factor);
+        auto side = [&](int nb, double vol, bool &nbRow) {
+            double phin = phi[nb];
+            nbRow = false;
+            if (phin < 0.0) {
+                nbRow = is_row(phi, g, nb);
+            } else {
+                double theta = phin / dadd(phiC, eps);
+                theta = fmax(-maxtheta, fmin(theta, maxtheta));
+                diag = dsub(diag, dmul(dmul(vol, factor), theta));
+            }
+        };
+        bool rR, rL, rT, rB, rF, rK;
+        side(c + 1, volRight, rR);
+        side(c - 1, volLeft, rL);
+        side(c + g.sj, volTop, rT);
+        side(c - g.sj, volBottom, rB);
+        side(c + g.sk, volFront, rF);
+        side(c - g.sk, volBack, rK);
+        diag = fmax(diag, 0.0);
+        Adiag[c] = diag;
+        AoffU[c] = rR ? (float)volRight : 0.0f;
+        AoffV[c] = rT ? (float)volTop : 0.0f;
+        AoffW[c] = rF ? (float)volFront : 0.0f;
+        // entries this row reads that no row owns
+        if (!rL) AoffU[c - 1] = 0.0f;
+        if (!rB) AoffV[c - g.sj] = 0.0f;
+        if (!rK) AoffW[c - g.sk] = 0.0f;
+    }
+    babs = warp_maxd(babs);
+    if (lane == 0 && babs > 0.0) atomicMax(&S->rhsMaxBits, (unsigned long long)__double_as_longlong(babs));
+}
+
+// y = A v at a row (off-diagonals only where the stored weight is nonzero: non-row neighbours may
+// hold stale data)
+__device__ __forceinline__ double apply_row(const PGrid &g, int c, double factor, const double *__restrict__ Adiag,
+                                            const float *__restrict__ AoffU, const float *__restrict__ AoffV,
+                                            const float *__restrict__ AoffW, const double *__restrict__ v) {
+    double acc = Adiag[c] * v[c];
+    float a;
+    double off = 0.0;
+    a = AoffW[c - g.sk]; if (a != 0.0f) off += (double)a * v[c - g.sk];
+    a = AoffV[c - g.sj]; if (a != 0.0f) off += (double)a * v[c - g.sj];
+    a = AoffU[c - 1];    if (a != 0.0f) off += (double)a * v[c - 1];
+    a = AoffU[c];        if (a != 0.0f) off += (double)a * v[c + 1];
+    a = AoffV[c];        if (a != 0.0f) off += (double)a * v[c + g.sj];
+    a = AoffW[c];        if (a != 0.0f) off += (double)a * v[c + g.sk];
+    return acc - factor * off;
+}
+
+struct PcgParams {
+    PGrid g;
+    double factor;
+    double tolFactor;
+};
+
+__device__ __forceinline__ void block_add(double v, double *target) {
+    __shared__ double sh[WPB];
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    v = warp_sum(v);
+    if (lane == 0) sh[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        double t = (lane < WPB) ? sh[lane] : 0.0;
+        t = warp_sum(t);
+        if (lane == 0 && t != 0.0) atomicAdd(target, t);
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ void block_max(double v, unsigned long long *target) {
+    __shared__ double shm[WPB];
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    v = warp_maxd(v);
+    if (lane == 0) shm[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        double t = (lane < WPB) ? shm[lane] : 0.0;
+        t = warp_maxd(t);
+        if (lane == 0 && t > 0.0) atomicMax(target, (unsigned long long)__double_as_longlong(t));
+    }
+    __syncthreads();
+}
+
+// r = b; z = M^-1 r (Jacobi); s = z; rho = z.r     (pcgsolver.h:258-276)
+__global__ void k_pcg_init(const int *__restrict__ segCell, const unsigned int *__restrict__ segMask, PcgParams pp,
+                           const double *__restrict__ b, const double *__restrict__ Adiag, double *__restrict__ r,
+                           double *__restrict__ z, double *__restrict__ s, DeviceScalars *S, int jacobi) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    double part = 0.0;
+    if (warp < S->numSegments) {
+        int c = segCell[warp] + lane;
+        if ((segMask[warp] >> lane) & 1u) {
+            double rv = b[c];
+            r[c] = rv;
+            if (jacobi) {
+                double d = Adiag[c];
+                double zv = (d != 0.0) ? rv / d : 0.0;
+                z[c] = zv;
+                s[c] = zv;
+                part = zv * rv;
+            }
+        }
+    }
+    if (jacobi) block_add(part, &S->rho[0]);
+}
+
+__global__ void k_pcg_scalars_init(DeviceScalars *S, double tolFactor) {
+    double bmax = __longlong_as_double((long long)S->rhsMaxBits);
+    S->pcgTol = tolFactor * bmax;
+    S->pcgError = bmax;
+    S->pcgIterations = 0;
+    S->pcgDone = 0;
+    for (int q = 0; q < 3; q++) { S->dotSZ[q] = 0.0; S->rho[q] = 0.0; S->rMaxBits[q] = 0ull; }
+}
+
+// z = A s ; dotSZ += s.z
+__global__ void k_pcg_spmv(const int *__restrict__ segCell, const unsigned int *__restrict__ segMask, PcgParams pp,
+                           const double *__restrict__ Adiag, const float *__restrict__ AoffU,
+                           const float *__restrict__ AoffV, const float *__restrict__ AoffW,
+                           const double *__restrict__ s, double *__restrict__ z, DeviceScalars *S, int it) {
+    if (S->pcgDone) return;
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    double part = 0.0;
+    if (warp < S->numSegments) {
+        int c = segCell[warp] + lane;
+        if ((segMask[warp] >> lane) & 1u) {
+            double zv = apply_row(pp.g, c, pp.factor, Adiag, AoffU, AoffV, AoffW, s);
+            z[c] = zv;
+            part = s[c] * zv;
+        }
+    }
+    block_add(part, &S->dotSZ[it % 3]);
+}
+
+// alpha = rho/(s.z); x += alpha s; r -= alpha z; rmax = ||r||_inf; [Jacobi: z = r/diag; rhoNew += z.r]
+__global__ void k_pcg_update(const int *__restrict__ segCell, const unsigned int *__restrict__ segMask,
+                             const double *__restrict__ Adiag, const double *__restrict__ s, double *__restrict__ z,
+                             double *__restrict__ x, double *__restrict__ r, DeviceScalars *S, int it, int jacobi) {
+    if (S->pcgDone) return;
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    double alpha = S->rho[it % 3] / S->dotSZ[it % 3];
+    double part = 0.0, rabs = 0.0;
+    if (warp < S->numSegments) {
+        int c = segCell[warp] + lane;
+        if ((segMask[warp] >> lane) & 1u) {
+            x[c] += alpha * s[c];
+            double rv = r[c] - alpha * z[c];
+            r[c] = rv;
+            rabs = fabs(rv);
+            if (jacobi) {
+                double d = Adiag[c];
+                double zv = (d != 0.0) ? rv / d : 0.0;
+                z[c] = zv;
+                part = zv * rv;
+            }
+        }
+    }
+    block_max(rabs, &S->rMaxBits[it % 3]);
+    if (jacobi) block_add(part, &S->rho[(it + 1) % 3]);
+}
+
+// rhoNew = z.r for preconditioners that produce z in a separate pass
+__global__ void k_pcg_dot_zr(const int *__restrict__ segCell, const unsigned int *__restrict__ segMask,
+                             const double *__restrict__ z, const double *__restrict__ r, DeviceScalars *S, int slot) {
+    if (S->pcgDone) return;
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    double part = 0.0;
+    if (warp < S->numSegments) {
+        int c = segCell[warp] + lane;
+        if ((segMask[warp] >> lane) & 1u) part = z[c] * r[c];
+    }
+    block_add(part, &S->rho[slot]);
+}
+
+// convergence test, beta = rhoNew/rho, s = z + beta s   (pcgsolver.h:286-297)
+__global__ void k_pcg_direction(const int *__restrict__ segCell, const unsigned int *__restrict__ segMask,
+                                const double *__restrict__ z, double *__restrict__ s, DeviceScalars *S, int it) {
+    if (S->pcgDone) return;
+    double rmax = __longlong_as_double((long long)S->rMaxBits[it % 3]);
+    double rho = S->rho[it % 3], rhoNew = S->rho[(it + 1) % 3];
+    bool converged = rmax <= S->pcgTol;
+    bool breakdown = !converged && (rhoNew == 0.0 || rhoNew != rhoNew);
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (!converged && !breakdown && warp < S->numSegments) {
+        double beta = rhoNew / rho;
+        int c = segCell[warp] + lane;
+        if ((segMask[warp] >> lane) & 1u) s[c] = z[c] + beta * s[c];
+    }
+    // the last block to finish publishes the scalars (no other block reads them after this point in
+    // this launch: every block sampled them above, before any block can reach the ticket below only
+    // if all blocks have passed -> use a ticket counter)
+    __shared__ bool last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        int ticket = atomicAdd(&S->pad[0], 1);
+        last = (ticket == (int)gridDim.x - 1);
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        S->pad[0] = 0;
+        S->pcgIterations = it + 1;
+        S->pcgError = rmax;
+        if (converged) S->pcgDone = 1;
+        else if (breakdown) S->pcgDone = 3;
+        S->dotSZ[(it + 1) % 3] = 0.0;
+        S->rMaxBits[(it + 1) % 3] = 0ull;
+        S->rho[(it + 2) % 3] = 0.0;
+    }
+}
+
+// ---- 3. velocity update  (_applySolutionToVelocityField, pressuresolver.cpp:842-1047)
+struct ApplyParams {
+    PGrid g;
+    float factor;   // (float)(_deltaTime/_dx)
+};
+
+__device__ __forceinline__ float row_pressure(const float *__restrict__ phi, const double *__restrict__ x,
+                                              const PGrid &g, int c) {
+    // pressureGrid is 0 except at pressure cells, where it is (float)soln  (:843-847)
+    return is_row(phi, g, c) ? (float)x[c] : 0.0f;
+}
+
+template <int DIR>
+__global__ void k_apply_pressure(ApplyParams ap, const float *__restrict__ phi, const double *__restrict__ x,
+                                 const float *__restrict__ wgt, float *__restrict__ vel,
+                                 unsigned char *__restrict__ valid) {
+    const PGrid &g = ap.g;
+    int gi = g.I + (DIR == 0), gj = g.J + (DIR == 1), gk = g.K + (DIR == 2);
+    long long n = (long long)gi * gj * gk;
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    int i = (int)(t % gi), j = (int)((t / gi) % gj), k = (int)(t / ((long long)gi * gj));
+    int a = (DIR == 0) ? i : (DIR == 1 ? j : k);
+    int amax = (DIR == 0) ? g.I : (DIR == 1 ? g.J : g.K);
+    unsigned char vflag = 0;
+    if (!(a == 0 || a == amax - 1)) {
+        const int stride = (DIR == 0) ? 1 : (DIR == 1 ? g.sj : g.sk);
+        // cell "2" is (i,j,k), cell "1" is one step back along DIR (pi,pj,pk)
+        int c2 = i + g.I * (j + g.J * k);
+        int c1 = c2 - stride;
+        bool in2 = (a < amax);       // a == amax: the face past the last cell
+        // FluidMaterialGrid::isFaceBorderingMaterial{U,V,W}  fluidmaterialgrid.cpp:126-150
+        bool f1 = phi[c1] < 0.0f;
+        bool f2 = in2 ? (phi[c2] < 0.0f) : false;
+        float w = wgt[t];
+        if (w > 0.0f && (f1 || f2)) {
+            float p1 = 0.0f, p2 = 0.0f;
+            if (f1 && f2) {
+                p1 = row_pressure(phi, x, g, c1);
+                p2 = row_pressure(phi, x, g, c2);
+            } else {
+                const float eps = 1e-6f;
+                float phi1 = phi[c1];
+                float phi2 = in2 ? phi[c2] : 0.0f;   // (w>0 never occurs on the outermost face of a walled domain)
+                if (f1) {
+                    float theta = __fdiv_rn(phi2, fadd(phi1, eps));
+                    theta = (float)fmax(-25.0, fmin((double)theta, 25.0));
+                    p1 = row_pressure(phi, x, g, c1);
+                    p2 = fmul(theta, p1);
+                } else {
+                    float theta = __fdiv_rn(phi1, fadd(phi2, eps));
+                    theta = (float)fmax(-25.0, fmin((double)theta, 25.0));
+                    p2 = row_pressure(phi, x, g, c2);
+                    p1 = fmul(theta, p2);
+                }
+            }
+            vel[t] = fadd(vel[t], fmul(-ap.factor, fsub(p2, p1)));
+            vflag = 1;
+        } else {
+            vel[t] = 0.0f;
+        }
+    }
+    valid[t] = vflag;
+}
+
+__global__ void k_pressure_to_float(const float *__restrict__ phi, const double *__restrict__ x, PGrid g, int nC,
+                                    float *__restrict__ out) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nC) return;
+    out[c] = row_pressure(phi, x, g, c);
+}
+
+__global__ void k_reset_pressure_scalars(DeviceScalars *S) {
+    S->numRows = 0; S->numSegments = 0; S->rhsMaxBits = 0ull; S->pad[0] = 0;
+    S->pcgIterations = 0; S->pcgDone = 0; S->pcgError = 0.0;
+}
+
+// ------------------------------------------------------------------------------------------------
+struct PressureScratch {
+    unsigned int *maskAll = nullptr;
+    int *flagAll = nullptr;
+    int *posAll = nullptr;
+    int nSegAll = 0;
+};
+
+void pressure_alloc(flip_ctx *c) {
+    const Dims &d = c->d;
+    int nSeg = cdiv(d.nC, 32);
+    c->maxSegments = nSeg;
+    FLIP_CUDA_CHECK(cudaMalloc(&c->segCell, sizeof(int) * nSeg));
+    FLIP_CUDA_CHECK(cudaMalloc(&c->segMask, sizeof(unsigned int) * nSeg));
+    size_t pad = (size_t)d.nC + 64;
+    FLIP_CUDA_CHECK(cudaMalloc(&c->Adiag, sizeof(double) * pad));
+    FLIP_CUDA_CHECK(cudaMalloc(&c->AoffU, sizeof(float) * pad));
+    FLIP_CUDA_CHECK(cudaMalloc(&c->AoffV, sizeof(float) * pad));
+    FLIP_CUDA_CHECK(cudaMalloc(&c->AoffW, sizeof(float) * pad));
+    FLIP_CUDA_CHECK(cudaMalloc(&c->vx_, sizeof(double) * pad));
+    FLIP_CUDA_CHECK(cudaMalloc(&c->vr, sizeof(double) * pad));
+    FLIP_CUDA_CHECK(cudaMalloc(&c->vs, sizeof(double) * pad));
+    FLIP_CUDA_CHECK(cudaMalloc(&c->vz, sizeof(double) * pad));
+    FLIP_CUDA_CHECK(cudaMalloc(&c->vb, sizeof(double) * pad));
+    FLIP_CUDA_CHECK(cudaMemset(c->AoffU, 0, sizeof(float) * pad));
+    FLIP_CUDA_CHECK(cudaMemset(c->AoffV, 0, sizeof(float) * pad));
+    FLIP_CUDA_CHECK(cudaMemset(c->AoffW, 0, sizeof(float) * pad));
+    FLIP_CUDA_CHECK(cudaMemset(c->vx_, 0, sizeof(double) * pad));
+    FLIP_CUDA_CHECK(cudaMemset(c->vs, 0, sizeof(double) * pad));
+    FLIP_CUDA_CHECK(cudaMemset(c->vz, 0, sizeof(double) * pad));
+    FLIP_CUDA_CHECK(cudaMemset(c->vr, 0, sizeof(double) * pad));
+    PressureScratch *ps = new PressureScratch();
+    ps->nSegAll = nSeg;
+    FLIP_CUDA_CHECK(cudaMalloc(&ps->maskAll, sizeof(unsigned int) * nSeg));
+    FLIP_CUDA_CHECK(cudaMalloc(&ps->flagAll, sizeof(int) * (nSeg + 1)));
+    FLIP_CUDA_CHECK(cudaMalloc(&ps->posAll, sizeof(int) * (nSeg + 1)));
+    c->mg = ps;
+}
+
+void pressure_free(flip_ctx *c) {
+    cudaFree(c->segCell); cudaFree(c->segMask); cudaFree(c->Adiag);
+    cudaFree(c->AoffU); cudaFree(c->AoffV); cudaFree(c->AoffW);
+    cudaFree(c->vx_); cudaFree(c->vr); cudaFree(c->vs); cudaFree(c->vz); cudaFree(c->vb);
+    if (c->mg) {
+        PressureScratch *ps = (PressureScratch *)c->mg;
+        cudaFree(ps->maskAll); cudaFree(ps->flagAll); cudaFree(ps->posAll);
+        delete ps;
+        c->mg = nullptr;
+    }
+}
+
+void stage_pressure(flip_ctx *c, double dt) {
+    const Dims &d = c->d;
+    cudaStream_t st = c->stream;
+    PressureScratch *ps = (PressureScratch *)c->mg;
+    PGrid g{d.I, d.J, d.K, d.I, d.I * d.J};
+    int nSeg = ps->nSegAll;
+
+    k_reset_pressure_scalars<<<1, 1, 0, st>>>(c->dS); c->launches++;
+    k_seg_flag<<<cdiv((long long)nSeg * 32, TPB), TPB, 0, st>>>(c->phiL, g, d.nC, nSeg, ps->maskAll, ps->flagAll, c->dS);
+    c->launches++;
+    size_t bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, bytes, ps->flagAll, ps->posAll, nSeg, st);
+    if (bytes > c->scanTempBytes) {
+        cudaFree(c->scanTemp);
+        FLIP_CUDA_CHECK(cudaMalloc(&c->scanTemp, bytes));
+        c->scanTempBytes = bytes;
+    }
+    cub::DeviceScan::ExclusiveSum(c->scanTemp, c->scanTempBytes, ps->flagAll, ps->posAll, nSeg, st); c->launches++;
+    k_seg_compact<<<cdiv(nSeg, TPB), TPB, 0, st>>>(nSeg, ps->maskAll, ps->flagAll, ps->posAll, c->segCell, c->segMask, c->dS);
+    c->launches++;
+
+    // The number of active segments is only known on the device; launches are sized for the upper
+    // bound we can derive on the host without a sync: every particle's cell could be its own segment.
+    int segBound = nSeg;
+    {
+        long long byParticles = (long long)c->np * 27;   // a particle makes at most 27 cells liquid
+        if (byParticles < segBound) segBound = (int)byParticles;
+        if (segBound < 1) segBound = 1;
+    }
+    int segBlocks = cdiv((long long)segBound * 32, TPB);
+
+    BuildParams bp;
+    bp.g = g;
+    bp.invdx = 1.0 / d.dx;
+    bp.factor = dt / (d.dx * d.dx);
+    k_build_system<<<segBlocks, TPB, 0, st>>>(c->segCell, c->segMask, bp, c->phiL, c->U, c->V, c->W, c->wU, c->wV,
+                                             c->wW, c->Adiag, c->AoffU, c->AoffV, c->AoffW, c->vb, c->vx_, c->dS);
+    c->launches++;
+    scalars_to_host(c);
+    int n = c->hS->numRows;
+    int numSeg = c->hS->numSegments;
+    double bmax;
+    {
+        unsigned long long bits = c->hS->rhsMaxBits;
+        memcpy(&bmax, &bits, sizeof(double));
+    }
+    c->cur.pressure_rows = n;
+    c->cur.fluid_cells = n;
+    c->cur.rhs_max = bmax;
+    c->cur.pcg_iterations = 0;
+    c->cur.pcg_error = 0.0;
+    c->cur.pcg_converged = 1;
+    // early out (pressuresolver.cpp:52-62): velocities and the valid mask stay untouched
+    if (n == 0 || bmax < c->pressureTol) return;
+
+    segBlocks = cdiv((long long)numSeg * 32, TPB);
+    PcgParams pp;
+    pp.g = g;
+    pp.factor = bp.factor;
+    pp.tolFactor = fmax(c->pressureTol, 1e-30);
+    int jacobi = 1;
+    k_pcg_scalars_init<<<1, 1, 0, st>>>(c->dS, pp.tolFactor); c->launches++;
+    k_pcg_init<<<segBlocks, TPB, 0, st>>>(c->segCell, c->segMask, pp, c->vb, c->Adiag, c->vr, c->vz, c->vs, c->dS, jacobi);
+    c->launches++;
+
+    int it = 0;
+    const int batch = 16;
+    bool done = false;
+    while (!done && it < c->pressureMaxIter) {
+        int stop = it + batch;
+        if (stop > c->pressureMaxIter) stop = c->pressureMaxIter;
+        for (; it < stop; it++) {
+            k_pcg_spmv<<<segBlocks, TPB, 0, st>>>(c->segCell, c->segMask, pp, c->Adiag, c->AoffU, c->AoffV, c->AoffW,
+                                                  c->vs, c->vz, c->dS, it);
+            k_pcg_update<<<segBlocks, TPB, 0, st>>>(c->segCell, c->segMask, c->Adiag, c->vs, c->vz, c->vx_, c->vr,
+                                                    c->dS, it, jacobi);
+            k_pcg_direction<<<segBlocks, TPB, 0, st>>>(c->segCell, c->segMask, c->vz, c->vs, c->dS, it);
+            c->launches += 3;
+        }
+        scalars_to_host(c);
+        done = c->hS->pcgDone != 0;
+    }
+    FLIP_CUDA_CHECK(cudaGetLastError());
+    c->cur.pcg_iterations = c->hS->pcgIterations;
+    c->cur.pcg_error = c->hS->pcgError;
+    bool success = c->hS->pcgDone == 1;
+    if (success) c->cur.pcg_converged = 1;
+    else if (c->hS->pcgIterations == c->pressureMaxIter && c->hS->pcgError < c->pressureAcceptableTol) c->cur.pcg_converged = 2;
+    else c->cur.pcg_converged = 0;
+    // _solveLinearSystem failure: solve() returns before applying (pressuresolver.cpp:70-72)
+    if (c->cur.pcg_converged == 0) return;
+
+    ApplyParams ap;
+    ap.g = g;
+    ap.factor = (float)(dt / d.dx);
+    k_apply_pressure<0><<<cdiv(d.nU, TPB), TPB, 0, st>>>(ap, c->phiL, c->vx_, c->wU, c->U, c->validU);
+    k_apply_pressure<1><<<cdiv(d.nV, TPB), TPB, 0, st>>>(ap, c->phiL, c->vx_, c->wV, c->V, c->validV);
+    k_apply_pressure<2><<<cdiv(d.nW, TPB), TPB, 0, st>>>(ap, c->phiL, c->vx_, c->wW, c->W, c->validW);
+    c->launches += 3;
+    FLIP_CUDA_CHECK(cudaGetLastError());
+}
+
+void pressure_to_float(flip_ctx *c, float *devOut) {
+    const Dims &d = c->d;
+    PGrid g{d.I, d.J, d.K, d.I, d.I * d.J};
+    k_pressure_to_float<<<cdiv(d.nC, TPB), TPB, 0, c->stream>>>(c->phiL, c->vx_, g, d.nC, devOut);
+    c->launches++;
+}
+
+}  // namespace flip

@@ -1,0 +1,337 @@
+"""ctypes binding of libflip_b200.so and a Python mirror of the reference's FluidSimulation API.
+
+The product is the C-ABI library (include/flip_b200.h); this module is the thin host-side mirror
+used by tests/ and bench.py.  It never falls back to a CPU implementation: if the library is
+missing, or no CUDA device is present, construction raises.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libflip_b200.so")
+
+STAGES = ("obstacles", "liquid_sdf", "p2g", "extrapolate_a", "save", "body_force", "pressure",
+          "extrapolate_b", "constrain", "g2p", "advance", "tail")
+STAGE_ID = {n: i for i, n in enumerate(STAGES)}
+ARRAY_ID = dict(U=0, V=1, W=2, validU=3, validV=4, validW=5, liquid_phi=6, solid_phi=7,
+                weightU=8, weightV=9, weightW=10, weightC=11, savedU=12, savedV=13, savedW=14,
+                near_solid=15, pressure=16)
+
+FLIP_OK, FLIP_ERR_RUNTIME, FLIP_ERR_DOMAIN, FLIP_ERR_OUT_OF_RANGE, FLIP_ERR_CUDA, FLIP_ERR_UNSUPPORTED = range(6)
+
+
+class FlipCudaError(RuntimeError):
+    pass
+
+
+class FlipUnsupported(RuntimeError):
+    pass
+
+
+# the exception types FluidSimulation throws for the same misuse (SURVEY §8b "Errors")
+_EXC = {FLIP_ERR_RUNTIME: RuntimeError, FLIP_ERR_DOMAIN: ValueError, FLIP_ERR_OUT_OF_RANGE: IndexError,
+        FLIP_ERR_CUDA: FlipCudaError, FLIP_ERR_UNSUPPORTED: FlipUnsupported}
+
+
+class StepStats(C.Structure):
+    _fields_ = [("particles", C.c_int32), ("fluid_cells", C.c_int32), ("pressure_rows", C.c_int32),
+                ("pcg_iterations", C.c_int32), ("pcg_converged", C.c_int32), ("removed_solid", C.c_int32),
+                ("removed_crowded", C.c_int32), ("removed_fast", C.c_int32), ("pcg_error", C.c_double),
+                ("rhs_max", C.c_double), ("dt", C.c_double)]
+
+    def as_dict(self):
+        return {f: getattr(self, f) for f, _ in self._fields_}
+
+
+_lib = None
+
+
+def load_library():
+    """Loads libflip_b200.so; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FileNotFoundError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`")
+    L = C.CDLL(LIB_PATH)
+    vp, ci, cd = C.c_void_p, C.c_int, C.c_double
+    L.flip_create.argtypes = [C.POINTER(vp), ci, ci, ci, cd, ci]
+    L.flip_destroy.argtypes = [vp]
+    L.flip_destroy.restype = None
+    L.flip_last_error.argtypes = [vp]
+    L.flip_last_error.restype = C.c_char_p
+    L.flip_create_error.restype = C.c_char_p
+    L.flip_add_body_force.argtypes = [vp, cd, cd, cd]
+    L.flip_set_pic_flip_ratio.argtypes = [vp, cd]
+    L.flip_set_cfl.argtypes = [vp, cd]
+    L.flip_set_substep_limits.argtypes = [vp, ci, ci]
+    L.flip_set_pressure_solver.argtypes = [vp, cd, cd, ci]
+    L.flip_set_preconditioner.argtypes = [vp, ci]
+    L.flip_load_particles.argtypes = [vp, ci, vp, vp]
+    L.flip_add_fluid_box.argtypes = [vp, C.POINTER(cd), C.POINTER(cd), C.POINTER(cd)]
+    L.flip_add_marker_particle.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.flip_set_solid_sdf.argtypes = [vp, vp]
+    L.flip_initialize.argtypes = [vp]
+    L.flip_update.argtypes = [vp, cd]
+    L.flip_get_current_frame.argtypes = [vp, C.POINTER(ci)]
+    L.flip_get_num_substeps.argtypes = [vp, C.POINTER(ci)]
+    L.flip_get_step_stats.argtypes = [vp, ci, C.POINTER(StepStats)]
+    L.flip_get_num_particles.argtypes = [vp, C.POINTER(ci)]
+    L.flip_get_particles.argtypes = [vp, vp, ci]
+    L.flip_set_particles.argtypes = [vp, ci, vp]
+    L.flip_get_particle_positions.argtypes = [vp, vp, ci]
+    L.flip_get_particle_velocities.argtypes = [vp, vp, ci]
+    L.flip_get_velocity_field.argtypes = [vp, vp, vp, vp]
+    L.flip_enable_particle_ids.argtypes = [vp, ci]
+    L.flip_get_particle_ids.argtypes = [vp, vp, ci]
+    L.flip_begin_frame.argtypes = [vp, cd]
+    L.flip_begin_substep.argtypes = [vp, C.POINTER(cd)]
+    L.flip_run_stage.argtypes = [vp, ci, cd]
+    L.flip_end_substep.argtypes = [vp, C.POINTER(ci)]
+    L.flip_end_frame.argtypes = [vp]
+    L.flip_array_bytes.argtypes = [vp, ci, C.POINTER(C.c_int64)]
+    L.flip_get_array.argtypes = [vp, ci, vp]
+    L.flip_set_array.argtypes = [vp, ci, vp]
+    L.flip_get_stage_times_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    L.flip_get_kernel_launches.argtypes = [vp, C.POINTER(C.c_int64)]
+    L.flip_get_stream.argtypes = [vp, C.POINTER(vp)]
+    L.flip_synchronize.argtypes = [vp]
+    L.flip_set_slab.argtypes = [vp, ci, ci, vp, ci]
+    L.flip_get_nccl_unique_id.argtypes = [vp, ci]
+    _lib = L
+    return L
+
+
+class MarkerParticleData:
+    """FluidSimulationMarkerParticleData (fluidsimulation.h:102-106): float xyz triplets."""
+
+    def __init__(self, positions, velocities):
+        self.positions = np.ascontiguousarray(positions, dtype=np.float32).reshape(-1, 3)
+        self.velocities = np.ascontiguousarray(velocities, dtype=np.float32).reshape(-1, 3)
+        assert self.positions.shape == self.velocities.shape
+        self.size = self.positions.shape[0]
+
+
+class FluidSimulation:
+    """Mirror of the subset of the reference's FluidSimulation that FluidManager and the north star
+    call: constructor, addBodyForce, addMeshFluid (axis-aligned boxes),
+    loadMarkerParticleData, initialize, update, getCurrentFrame, getNumMarkerParticles,
+    getMarkerParticles, getMarkerParticlePositionData/VelocityData, getVelocityField."""
+
+    def __init__(self, isize, jsize, ksize, dx, device=0):
+        self.L = load_library()
+        self.h = C.c_void_p()
+        rc = self.L.flip_create(C.byref(self.h), int(isize), int(jsize), int(ksize), float(dx), int(device))
+        if rc != FLIP_OK:
+            raise _EXC.get(rc, RuntimeError)(self.L.flip_create_error().decode())
+        self.dims = (int(isize), int(jsize), int(ksize))
+        self.dx = float(dx)
+
+    # -- plumbing
+    def _check(self, rc):
+        if rc != FLIP_OK:
+            raise _EXC.get(rc, RuntimeError)(self.L.flip_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            self.L.flip_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- configuration
+    def addBodyForce(self, fx, fy, fz):
+        self._check(self.L.flip_add_body_force(self.h, fx, fy, fz))
+
+    def setPICFLIPRatio(self, r):
+        self._check(self.L.flip_set_pic_flip_ratio(self.h, r))
+
+    def setCFLConditionNumber(self, n):
+        self._check(self.L.flip_set_cfl(self.h, n))
+
+    def setTimeStepsPerFrame(self, mn, mx):
+        self._check(self.L.flip_set_substep_limits(self.h, mn, mx))
+
+    def setPressureSolver(self, tolerance=1e-9, acceptable=1.0, max_iterations=1000):
+        self._check(self.L.flip_set_pressure_solver(self.h, tolerance, acceptable, max_iterations))
+
+    def setPreconditioner(self, kind):
+        self._check(self.L.flip_set_preconditioner(self.h, {"jacobi": 0, "multigrid": 1}.get(kind, kind)))
+
+    def setSurfaceSubdivisionLevel(self, n):
+        """Accepted and ignored: surface reconstruction is outside the hot path."""
+
+    def getSimulationDimensions(self):
+        return tuple(d * self.dx for d in self.dims)
+
+    def getGridDimensions(self):
+        return self.dims
+
+    def getCellSize(self):
+        return self.dx
+
+    def addMeshFluidBox(self, lo, hi, velocity=(0.0, 0.0, 0.0)):
+        a = (C.c_double * 3)(*lo)
+        b = (C.c_double * 3)(*hi)
+        v = (C.c_double * 3)(*velocity)
+        self._check(self.L.flip_add_fluid_box(self.h, a, b, v))
+
+    def loadMarkerParticleData(self, data):
+        if data.size == 0:
+            return
+        self._check(self.L.flip_load_particles(self.h, data.size, data.positions.ctypes.data, data.velocities.ctypes.data))
+
+    def addMarkerParticle(self, p, v):
+        a = (C.c_float * 3)(*p)
+        b = (C.c_float * 3)(*v)
+        self._check(self.L.flip_add_marker_particle(self.h, a, b))
+
+    def setSolidSDF(self, phi_nodal):
+        I, J, K = self.dims
+        phi = np.ascontiguousarray(phi_nodal, dtype=np.float32)
+        assert phi.size == (I + 1) * (J + 1) * (K + 1)
+        self._check(self.L.flip_set_solid_sdf(self.h, phi.ctypes.data))
+
+    def initialize(self):
+        self._check(self.L.flip_initialize(self.h))
+
+    # -- the hot path
+    def update(self, dt):
+        self._check(self.L.flip_update(self.h, float(dt)))
+
+    def getCurrentFrame(self):
+        v = C.c_int()
+        self._check(self.L.flip_get_current_frame(self.h, C.byref(v)))
+        return v.value
+
+    def getNumMarkerParticles(self):
+        v = C.c_int()
+        self._check(self.L.flip_get_num_particles(self.h, C.byref(v)))
+        return v.value
+
+    def getMarkerParticles(self, out=None):
+        """(n,6) float32 {px,py,pz,vx,vy,vz}: std::vector<MarkerParticle> by value."""
+        n = self.getNumMarkerParticles()
+        a = out if out is not None else np.empty((n, 6), dtype=np.float32)
+        self._check(self.L.flip_get_particles(self.h, a.ctypes.data, a.shape[0]))
+        return a[:n]
+
+    def setMarkerParticles(self, aos):
+        aos = np.ascontiguousarray(aos, dtype=np.float32).reshape(-1, 6)
+        self._check(self.L.flip_set_particles(self.h, aos.shape[0], aos.ctypes.data))
+
+    def enableParticleIds(self, on=True):
+        self._check(self.L.flip_enable_particle_ids(self.h, 1 if on else 0))
+
+    def getParticleIds(self):
+        n = self.getNumMarkerParticles()
+        a = np.empty(n, dtype=np.int32)
+        self._check(self.L.flip_get_particle_ids(self.h, a.ctypes.data, n))
+        return a
+
+    def getMarkerParticlePositionData(self):
+        n = self.getNumMarkerParticles()
+        a = np.empty((n, 3), dtype=np.float32)
+        self._check(self.L.flip_get_particle_positions(self.h, a.ctypes.data, n))
+        return a
+
+    def getMarkerParticleVelocityData(self):
+        n = self.getNumMarkerParticles()
+        a = np.empty((n, 3), dtype=np.float32)
+        self._check(self.L.flip_get_particle_velocities(self.h, a.ctypes.data, n))
+        return a
+
+    def getVelocityField(self):
+        """(U, V, W) host copies shaped (k,j,i) with the MACVelocityField extents."""
+        U, V, W = (np.empty(self.shape_of(n), dtype=np.float32) for n in ("U", "V", "W"))
+        self._check(self.L.flip_get_velocity_field(self.h, U.ctypes.data, V.ctypes.data, W.ctypes.data))
+        return U, V, W
+
+    # -- stats
+    def substep_stats(self):
+        n = C.c_int()
+        self._check(self.L.flip_get_num_substeps(self.h, C.byref(n)))
+        out = []
+        for s in range(n.value):
+            st = StepStats()
+            self._check(self.L.flip_get_step_stats(self.h, s, C.byref(st)))
+            out.append(st.as_dict())
+        return out
+
+    def stage_times_ms(self):
+        a = (C.c_float * len(STAGES))()
+        self._check(self.L.flip_get_stage_times_ms(self.h, a))
+        return dict(zip(STAGES, list(a)))
+
+    def kernel_launches(self):
+        v = C.c_int64()
+        self._check(self.L.flip_get_kernel_launches(self.h, C.byref(v)))
+        return v.value
+
+    def stream(self):
+        v = C.c_void_p()
+        self._check(self.L.flip_get_stream(self.h, C.byref(v)))
+        return v.value
+
+    def synchronize(self):
+        self._check(self.L.flip_synchronize(self.h))
+
+    # -- stage-wise seams
+    def begin_frame(self, dt):
+        self._check(self.L.flip_begin_frame(self.h, float(dt)))
+
+    def begin_substep(self):
+        v = C.c_double()
+        self._check(self.L.flip_begin_substep(self.h, C.byref(v)))
+        return v.value
+
+    def stage(self, name, dt):
+        self._check(self.L.flip_run_stage(self.h, STAGE_ID[name], float(dt)))
+
+    def end_substep(self):
+        v = C.c_int()
+        self._check(self.L.flip_end_substep(self.h, C.byref(v)))
+        return bool(v.value)
+
+    def end_frame(self):
+        self._check(self.L.flip_end_frame(self.h))
+
+    def shape_of(self, name):
+        I, J, K = self.dims
+        if name in ("U", "validU", "weightU", "savedU"):
+            return (K, J, I + 1)
+        if name in ("V", "validV", "weightV", "savedV"):
+            return (K, J + 1, I)
+        if name in ("W", "validW", "weightW", "savedW"):
+            return (K + 1, J, I)
+        if name in ("liquid_phi", "pressure"):
+            return (K, J, I)
+        if name == "solid_phi":
+            return (K + 1, J + 1, I + 1)
+        if name == "near_solid":
+            b = C.c_int64()
+            self._check(self.L.flip_array_bytes(self.h, ARRAY_ID[name], C.byref(b)))
+            return (b.value,)
+        raise KeyError(name)
+
+    def array(self, name):
+        dt = np.uint8 if name.startswith("valid") or name == "near_solid" else np.float32
+        a = np.empty(self.shape_of(name), dtype=dt)
+        b = C.c_int64()
+        self._check(self.L.flip_array_bytes(self.h, ARRAY_ID[name], C.byref(b)))
+        assert b.value == a.nbytes, (name, b.value, a.nbytes)
+        self._check(self.L.flip_get_array(self.h, ARRAY_ID[name], a.ctypes.data))
+        return a
+
+    def set_array(self, name, a):
+        dt = np.uint8 if name.startswith("valid") or name == "near_solid" else np.float32
+        a = np.ascontiguousarray(a, dtype=dt)
+        b = C.c_int64()
+        self._check(self.L.flip_array_bytes(self.h, ARRAY_ID[name], C.byref(b)))
+        assert b.value == a.nbytes, (name, b.value, a.nbytes)
+        self._check(self.L.flip_set_array(self.h, ARRAY_ID[name], a.ctypes.data))

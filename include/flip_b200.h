@@ -1,0 +1,191 @@
+/*
+ * flip_b200.h — C-ABI of the B200-native FLIP time step (libflip_b200.so).
+ *
+ * This is the drop-in boundary for the per-timestep hot path of the engine bundled in
+ * jklae/FLIPEngine3D (src/engine, Blender-FLIP-Fluids 1.0.9).  Every entry point names the
+ * reference interface it replaces (file:line relative to the reference tree).  Plain pointers and
+ * sizes only; no C++/torch types.  All `float*`/`uint8_t*` arguments are HOST pointers unless the
+ * name ends in `_dev`.  Every function returns FLIP_OK (0) or a nonzero status; the message is in
+ * flip_last_error().  A context is single-caller, like FluidSimulation::update().
+ *
+ * Array layouts are the reference's (array3d.h:425-428, macvelocityfield.cpp:46-54):
+ *   flat index i + W*(j + H*k);  U is (I+1,J,K), V (I,J+1,K), W (I,J,K+1);
+ *   liquid phi (I,J,K) cell centred; solid phi (I+1,J+1,K+1) nodal; masks are 1 byte per entry.
+ * Particles cross the boundary as the reference's MarkerParticle AoS {px,py,pz,vx,vy,vz}
+ * (markerparticle.h:30-42) or as the two float-triplet blobs of loadMarkerParticleData
+ * (fluidsimulation.h:102-106).
+ */
+#ifndef FLIP_B200_H
+#define FLIP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct flip_ctx flip_ctx;
+
+enum {
+    FLIP_OK = 0,
+    FLIP_ERR_RUNTIME = 1,      /* std::runtime_error in the reference (e.g. update before initialize, fluidsimulation.cpp:5756) */
+    FLIP_ERR_DOMAIN = 2,       /* std::domain_error (dt < 0, fluidsimulation.cpp:5761; bad dims/dx, :44-56) */
+    FLIP_ERR_OUT_OF_RANGE = 3, /* std::out_of_range (bad index ranges, fluidsimulation.cpp:2059) */
+    FLIP_ERR_CUDA = 4,         /* a CUDA call failed; there is NO CPU fallback */
+    FLIP_ERR_UNSUPPORTED = 5   /* a feature outside the hot-path scope was requested */
+};
+
+/* Stage ids: the order of FluidSimulation::_stepFluid (fluidsimulation.cpp:5471-5508). */
+enum {
+    FLIP_STAGE_OBSTACLES = 0,     /* _updateObstacleObjects          :3196 (static scene: no-op)          */
+    FLIP_STAGE_LIQUID_SDF = 1,    /* _updateLiquidLevelSet + postProcessSignedDistanceField :3225,:3246   */
+    FLIP_STAGE_P2G = 2,           /* VelocityAdvector::advect         velocityadvector.cpp:38              */
+    FLIP_STAGE_EXTRAPOLATE_A = 3, /* _extrapolateFluidVelocities      :3775 -> gridutils.cpp:32            */
+    FLIP_STAGE_SAVE = 4,          /* _saveVelocityField               :3287                                */
+    FLIP_STAGE_BODY_FORCE = 5,    /* _applyConstantBodyForces         :3450                                */
+    FLIP_STAGE_PRESSURE = 6,      /* PressureSolver::solve            pressuresolver.cpp:44                */
+    FLIP_STAGE_EXTRAPOLATE_B = 7, /* _extrapolateFluidVelocities      :3763                                */
+    FLIP_STAGE_CONSTRAIN = 8,     /* _constrainVelocityFields         :3937                                */
+    FLIP_STAGE_G2P = 9,           /* _updatePICFLIPMarkerParticleVelocities :4094                          */
+    FLIP_STAGE_ADVANCE = 10,      /* _advanceMarkerParticles (+_removeMarkerParticles) :4355,:4324         */
+    FLIP_STAGE_TAIL = 11,         /* _updateFluidObjects :4794 (nothing queued after load: no-op)          */
+    FLIP_NUM_STAGES = 12
+};
+
+/* Array ids for flip_get_array / flip_set_array. */
+enum {
+    FLIP_ARRAY_U = 0, FLIP_ARRAY_V = 1, FLIP_ARRAY_W = 2,                 /* float */
+    FLIP_ARRAY_VALID_U = 3, FLIP_ARRAY_VALID_V = 4, FLIP_ARRAY_VALID_W = 5, /* uint8 */
+    FLIP_ARRAY_LIQUID_PHI = 6,  /* float (I,J,K)        ParticleLevelSet::_phi   particlelevelset.h:134 */
+    FLIP_ARRAY_SOLID_PHI = 7,   /* float (I+1,J+1,K+1)  MeshLevelSet::_phi       meshlevelset.h:354     */
+    FLIP_ARRAY_WEIGHT_U = 8, FLIP_ARRAY_WEIGHT_V = 9, FLIP_ARRAY_WEIGHT_W = 10, FLIP_ARRAY_WEIGHT_C = 11, /* WeightGrid pressuresolver.h:48 */
+    FLIP_ARRAY_SAVED_U = 12, FLIP_ARRAY_SAVED_V = 13, FLIP_ARRAY_SAVED_W = 14,
+    FLIP_ARRAY_NEAR_SOLID = 15, /* uint8 coarse grid, cell = 3dx  fluidsimulation.cpp:3094 */
+    FLIP_ARRAY_PRESSURE = 16,   /* float (I,J,K) pressure of the last solve (pressuresolver.cpp:843-847) */
+    FLIP_NUM_ARRAYS = 17
+};
+
+/* Per-substep bookkeeping: the integers the reference logs in _logStepInfo (fluidsimulation.cpp:5710-5745). */
+typedef struct flip_step_stats {
+    int32_t particles;        /* "Fluid Particles"  after removal                                   */
+    int32_t fluid_cells;      /* "Fluid Cells"      _getNumFluidCells :4761                        */
+    int32_t pressure_rows;    /* PressureSolver::_matSize  pressuresolver.cpp:112                    */
+    int32_t pcg_iterations;   /* "Pressure Solver Iterations"                                       */
+    int32_t pcg_converged;    /* 1: reached tol; 2: hit max iterations but below acceptable tol; 0: failed */
+    int32_t removed_solid;    /* particles deleted by _removeMarkerParticles, by reason             */
+    int32_t removed_crowded;
+    int32_t removed_fast;
+    double pcg_error;         /* "Estimated Error"  = ||r||_inf                                      */
+    double rhs_max;           /* ||b||_inf                                                           */
+    double dt;                /* substep length                                                      */
+} flip_step_stats;
+
+/* ---- lifetime ---------------------------------------------------------------------------- */
+
+/* FluidSimulation::FluidSimulation(int,int,int,double)  fluidsimulation.cpp:35-63.
+ * `device` is the CUDA ordinal the context lives on. */
+int flip_create(flip_ctx **out, int isize, int jsize, int ksize, double dx, int device);
+/* FluidSimulation::~FluidSimulation  fluidsimulation.cpp:66 */
+void flip_destroy(flip_ctx *ctx);
+const char *flip_last_error(const flip_ctx *ctx);
+/* status string of the last failed flip_create (ctx does not exist yet) */
+const char *flip_create_error(void);
+
+/* ---- configuration (before flip_initialize) ------------------------------------------------ */
+
+/* FluidSimulation::addBodyForce(double,double,double)  fluidsimulation.cpp:1563 */
+int flip_add_body_force(flip_ctx *ctx, double fx, double fy, double fz);
+/* FluidSimulation::setPICFLIPRatio :1440, setCFLConditionNumber :1100,
+ * setMin/MaxTimeStepsPerFrame :1086-1098, pressure-solver members fluidsimulation.h:1657-1659 */
+int flip_set_pic_flip_ratio(flip_ctx *ctx, double ratio);
+int flip_set_cfl(flip_ctx *ctx, double cfl);
+int flip_set_substep_limits(flip_ctx *ctx, int min_steps, int max_steps);
+int flip_set_pressure_solver(flip_ctx *ctx, double tolerance, double acceptable_tolerance, int max_iterations);
+/* ThreadUtils-free: the analogue of choosing the engine's parallel resources. 0 = Jacobi,
+ * 1 = multigrid V-cycle (default). Both are GPU-parallel replacements of the reference's serial
+ * MIC(0) (pcgsolver.h:69-221); the stopping rule is the reference's. */
+int flip_set_preconditioner(flip_ctx *ctx, int kind);
+
+/* FluidSimulation::loadMarkerParticleData  fluidsimulation.cpp:2488 — float xyz triplets; copied;
+ * applied (with the in-domain filter of _loadMarkerParticles :2773) at flip_initialize(). */
+int flip_load_particles(flip_ctx *ctx, int n, const float *positions_xyz, const float *velocities_xyz);
+/* FluidSimulation::addMeshFluid(MeshObject) :1573 for the axis-aligned boxes FluidManager uses
+ * (src/FluidManager.cpp:56-64): queues a box [lo,hi) of world coordinates seeded with 8 particles
+ * per cell at flip_initialize() (reference: end of first step, _updateFluidObjects :4794). */
+int flip_add_fluid_box(flip_ctx *ctx, const double lo[3], const double hi[3], const double velocity[3]);
+/* FluidSimulation::_addMarkerParticle  fluidsimulation.cpp:2637 (range-checked push). */
+int flip_add_marker_particle(flip_ctx *ctx, const float position[3], const float velocity[3]);
+
+/* Override the static solid inputs.  By default the context builds the reference's
+ * domain box (inset 1.5dx+5e-5, fluidsimulation.cpp:2834-2839) itself.  phi: (I+1)(J+1)(K+1) floats. */
+int flip_set_solid_sdf(flip_ctx *ctx, const float *phi_nodal);
+
+/* FluidSimulation::initialize  fluidsimulation.cpp:82 */
+int flip_initialize(flip_ctx *ctx);
+
+/* ---- the hot path -------------------------------------------------------------------------- */
+
+/* FluidSimulation::update(double dt)  fluidsimulation.cpp:5755 — one frame, CFL substeps inside. */
+int flip_update(flip_ctx *ctx, double dt);
+/* FluidSimulation::getCurrentFrame :94 */
+int flip_get_current_frame(const flip_ctx *ctx, int *frame);
+/* number of substeps the last flip_update took, and their stats (index 0..substeps-1) */
+int flip_get_num_substeps(const flip_ctx *ctx, int *substeps);
+int flip_get_step_stats(const flip_ctx *ctx, int substep, flip_step_stats *out);
+
+/* FluidSimulation::getNumMarkerParticles :2049 */
+int flip_get_num_particles(const flip_ctx *ctx, int *n);
+/* FluidSimulation::getMarkerParticles() :2053 — copies n*6 floats {p,v} to host. */
+int flip_get_particles(flip_ctx *ctx, float *aos6, int capacity);
+/* Replace the particle store in place (the reverse of flip_get_particles; lock-step tests and the
+ * end-to-end benchmark leg use it).  Applies the in-domain filter of _addMarkerParticle. */
+int flip_set_particles(flip_ctx *ctx, int n, const float *aos6);
+/* FluidSimulation::getMarkerParticlePositionData / VelocityData :2408-2420 (xyz triplets). */
+int flip_get_particle_positions(flip_ctx *ctx, float *xyz, int capacity);
+int flip_get_particle_velocities(flip_ctx *ctx, float *xyz, int capacity);
+
+/* Optional particle identity: when enabled (before particles are uploaded), every particle carries the
+ * index it had in the last flip_load_particles / flip_set_particles call through the per-step cell
+ * sort, so callers can match particles across steps although the store is reordered (the reference
+ * keeps insertion order, fragmentedvector.h; here order is by cell).  Costs 8 B/particle/step. */
+int flip_enable_particle_ids(flip_ctx *ctx, int on);
+int flip_get_particle_ids(flip_ctx *ctx, int32_t *ids, int capacity);
+
+/* FluidSimulation::getVelocityField :2242 + MACVelocityField::getRawArrayU/V/W macvelocityfield.cpp:100-110 */
+int flip_get_velocity_field(flip_ctx *ctx, float *U, float *V, float *W);
+
+/* ---- per-stage seams (the reference's *Parameters structs: velocityadvector.h:62-67,
+ *      pressuresolver.h:63-79) for isolated parity tests and profiling ------------------------ */
+
+/* Frame/substep bookkeeping of update() (fluidsimulation.cpp:5768-5824) exposed step by step. */
+int flip_begin_frame(flip_ctx *ctx, double dt);
+int flip_begin_substep(flip_ctx *ctx, double *dt_substep);
+int flip_run_stage(flip_ctx *ctx, int stage, double dt_substep);
+int flip_end_substep(flip_ctx *ctx, int *more);
+int flip_end_frame(flip_ctx *ctx);
+
+int flip_array_bytes(const flip_ctx *ctx, int which, int64_t *bytes);
+int flip_get_array(flip_ctx *ctx, int which, void *host_out);
+int flip_set_array(flip_ctx *ctx, int which, const void *host_in);
+
+/* Device time of each stage in the last substep, milliseconds (CUDA events on the context's stream) —
+ * the analogue of the reference's TimingData buckets (fluidsimulation.h:1172-1233). */
+int flip_get_stage_times_ms(const flip_ctx *ctx, float ms[FLIP_NUM_STAGES]);
+/* Number of kernels this library launched on the context since creation. */
+int flip_get_kernel_launches(const flip_ctx *ctx, int64_t *launches);
+/* Raw cudaStream_t of the context (for callers that time with their own events). */
+int flip_get_stream(const flip_ctx *ctx, void **stream);
+int flip_synchronize(flip_ctx *ctx);
+
+/* ---- multi-GPU z-slab decomposition ------------------------------------------- */
+
+/* Make this context one z-slab [k0,k1) of a global I x J x Kglobal domain shared by `nranks`
+ * processes of one box.  nccl_unique_id: the 128 bytes of an ncclUniqueId created by rank 0 and
+ * distributed by the caller (e.g. torch.distributed broadcast).  Must precede flip_initialize. */
+int flip_set_slab(flip_ctx *ctx, int rank, int nranks, const void *nccl_unique_id, int id_bytes);
+int flip_get_nccl_unique_id(void *out_id, int id_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLIP_B200_H */

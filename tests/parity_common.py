@@ -1,0 +1,218 @@
+"""Lock-step parity harness: drives the reference engine (oracle/_ref, through oracle/refengine.py)
+and the CUDA engine (libflip_b200.so through flipengine3d_b200.engine) stage by stage from identical
+state and reports per-stage differences.  Test infrastructure only."""
+import os
+import sys
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from flipengine3d_b200 import engine as fe  # noqa: E402
+from oracle import refengine  # noqa: E402
+
+GRID_STAGE_ARRAYS = ("U", "V", "W", "validU", "validV", "validW", "liquid_phi")
+ALL_STAGES = ("obstacles", "liquid_sdf", "p2g", "extrapolate_a", "save", "body_force", "pressure",
+              "extrapolate_b", "constrain", "g2p", "advance", "tail")
+
+
+def rel_l2(a, b):
+    a = np.asarray(a, dtype=np.float64).ravel()
+    b = np.asarray(b, dtype=np.float64).ravel()
+    den = np.linalg.norm(b)
+    if den == 0.0:
+        return float(np.linalg.norm(a))
+    return float(np.linalg.norm(a - b) / den)
+
+
+def max_abs(a, b):
+    if a.size == 0:
+        return 0.0
+    return float(np.max(np.abs(np.asarray(a, dtype=np.float64) - np.asarray(b, dtype=np.float64))))
+
+
+def make_pair(scene, tol=None, threads=None, gravity=(0.0, -25.0, 0.0), preconditioner=None):
+    """Returns (ref, gpu) engines initialised from the same scene; the GPU engine gets the oracle's
+    own static solid SDF and the oracle's LOGICAL particle list."""
+    ref = refengine.RefEngine(scene["dims"], scene["dx"], scene["pos"], scene["vel"], gravity=gravity, threads=threads, tol=tol)
+    ref.stage("obstacles", 1.0 / 30.0)   # builds the solid SDF / near-solid grid exactly as the first step would
+    I, J, K = scene["dims"]
+    gpu = fe.FluidSimulation(I, J, K, scene["dx"])
+    gpu.addBodyForce(*gravity)
+    if tol is not None:
+        gpu.setPressureSolver(tolerance=tol)
+    if preconditioner is not None:
+        gpu.setPreconditioner(preconditioner)
+    gpu.enableParticleIds(True)
+    gpu.setSolidSDF(ref.array("solid_phi"))
+    gpu.initialize()
+    gpu.setMarkerParticles(ref.particles())
+    return ref, gpu
+
+
+def particles_by_id(gpu):
+    """GPU particles re-ordered to the order of the last setMarkerParticles call; returns (aos, ids)."""
+    p = gpu.getMarkerParticles()
+    ids = gpu.getParticleIds()
+    return p, ids
+
+
+def lockstep_substep(ref, gpu, dt, isolate=True, report=None):
+    """Runs one substep of both engines stage by stage.  With isolate=True the GPU's grid state is
+    overwritten with the oracle's before every stage, so each stage is compared from identical
+    inputs.  Returns a dict of metrics."""
+    rep = report if report is not None else {}
+    P0 = ref.particles()
+    gpu.setMarkerParticles(P0)
+    n0 = P0.shape[0]
+
+    def sync_grids():
+        for name in GRID_STAGE_ARRAYS:
+            gpu.set_array(name, ref.array(name))
+
+    def sync_saved():
+        for name in ("savedU", "savedV", "savedW"):
+            gpu.set_array(name, ref.array(name))
+
+    def cmp_fields(tag, names=("U", "V", "W")):
+        for name in names:
+            a, b = gpu.array(name), ref.array(name)
+            rep[f"{tag}.{name}.rel_l2"] = rel_l2(a, b)
+            rep[f"{tag}.{name}.max_abs"] = max_abs(a, b)
+
+    def cmp_valid(tag):
+        for name in ("validU", "validV", "validW"):
+            a, b = gpu.array(name), ref.array(name)
+            rep[f"{tag}.{name}.hamming"] = int(np.count_nonzero((a != 0) != (b != 0)))
+            rep[f"{tag}.{name}.count"] = int(np.count_nonzero(b))
+
+    # S1/S2: liquid SDF (the GPU produces SDF and P2G in one gather)
+    ref.stage("obstacles", dt)
+    ref.stage("liquid_sdf", dt)
+    gpu.stage("liquid_sdf", dt)
+    a, b = gpu.array("liquid_phi"), ref.array("liquid_phi")
+    rep["sdf.mismatch_cells"] = int(np.count_nonzero(a != b))
+    rep["sdf.max_abs"] = max_abs(a, b)
+    rep["sdf.sign_flips"] = int(np.count_nonzero((a < 0) != (b < 0)))
+    rep["sdf.liquid_cells"] = int(np.count_nonzero(b < 0))
+
+    # S3a: P2G
+    ref.stage("p2g", dt)
+    gpu.stage("p2g", dt)
+    cmp_fields("p2g")
+    cmp_valid("p2g")
+    if isolate:
+        sync_grids()
+
+    # S3b: extrapolation
+    ref.stage("extrapolate_a", dt)
+    gpu.stage("extrapolate_a", dt)
+    cmp_fields("extrapolate_a")
+    for name in ("U", "V", "W"):
+        rep[f"extrapolate_a.{name}.mismatch"] = int(np.count_nonzero(gpu.array(name) != ref.array(name)))
+    if isolate:
+        sync_grids()
+
+    # S4, S5
+    ref.stage("save", dt)
+    gpu.stage("save", dt)
+    ref.stage("body_force", dt)
+    gpu.stage("body_force", dt)
+    cmp_fields("body_force")
+    if isolate:
+        sync_grids()
+        sync_saved()
+
+    # S7a: pressure
+    ref.stage("pressure", dt)
+    gpu.stage("pressure", dt)
+    cmp_fields("pressure")
+    cmp_valid("pressure")
+    rep["pressure.ref_iterations"] = ref.pcg_iterations
+    rep["pressure.ref_error"] = ref.pcg_error
+    if isolate:
+        sync_grids()
+
+    # S7b
+    ref.stage("extrapolate_b", dt)
+    gpu.stage("extrapolate_b", dt)
+    cmp_fields("extrapolate_b")
+    if isolate:
+        sync_grids()
+
+    # S8
+    ref.stage("constrain", dt)
+    gpu.stage("constrain", dt)
+    cmp_fields("constrain")
+    for name in ("savedU", "savedV", "savedW"):
+        rep[f"constrain.{name}.rel_l2"] = rel_l2(gpu.array(name), ref.array(name))
+    if isolate:
+        sync_grids()
+        sync_saved()
+
+    # S10: G2P
+    ref.stage("g2p", dt)
+    gpu.stage("g2p", dt)
+    pg, ids = particles_by_id(gpu)
+    pr = ref.particles()
+    rep["g2p.vel.rel_l2"] = rel_l2(pg[:, 3:], pr[ids, 3:])
+    rep["g2p.vel.max_abs"] = max_abs(pg[:, 3:], pr[ids, 3:])
+    rep["g2p.vel.mismatch"] = int(np.count_nonzero(pg[:, 3:] != pr[ids, 3:]))
+    if isolate:
+        # put the oracle's post-G2P velocities in (keeps ids = index in pr)
+        gpu.setMarkerParticles(pr)
+
+    # S12: advance (+ removal)
+    ref.stage("advance", dt)
+    gpu.stage("advance", dt)
+    ref.stage("tail", dt)
+    gpu.stage("tail", dt)
+    rep["advance.ref_particles"] = ref.num_particles
+    rep["advance.gpu_particles"] = gpu.getNumMarkerParticles()
+    rep["n0"] = n0
+    if ref.num_particles == n0 and gpu.getNumMarkerParticles() == n0:
+        pg, ids = particles_by_id(gpu)
+        pr2 = ref.particles()
+        rep["advance.pos.rel_l2"] = rel_l2(pg[:, :3], pr2[ids, :3])
+        rep["advance.pos.max_abs"] = max_abs(pg[:, :3], pr2[ids, :3])
+        rep["advance.pos.mismatch"] = int(np.count_nonzero(pg[:, :3] != pr2[ids, :3]))
+    return rep
+
+
+def lockstep_frames(scene, frames=1, isolate=True, tol=None, threads=None, preconditioner=None, verbose=False):
+    ref, gpu = make_pair(scene, tol=tol, threads=threads, preconditioner=preconditioner)
+    reports = []
+    for f in range(frames):
+        ref.begin_frame(1.0 / 30.0)
+        gpu.begin_frame(1.0 / 30.0)
+        more = True
+        while more:
+            dt = ref.begin_substep()
+            gpu.begin_substep()   # bookkeeping only; the oracle's dt is used for both
+            rep = {"frame": f, "dt": dt}
+            lockstep_substep(ref, gpu, dt, isolate=isolate, report=rep)
+            more = ref.end_substep()
+            gpu.end_substep()
+            st = gpu.substep_stats()[-1]
+            rep["gpu.pcg_iterations"] = st["pcg_iterations"]
+            rep["gpu.pcg_error"] = st["pcg_error"]
+            rep["gpu.pcg_converged"] = st["pcg_converged"]
+            rep["gpu.pressure_rows"] = st["pressure_rows"]
+            rep["gpu.rhs_max"] = st["rhs_max"]
+            rep["ref.fluid_cells"] = ref.num_fluid_cells
+            reports.append(rep)
+            if verbose:
+                print_report(rep)
+        ref.end_frame()
+        gpu.end_frame()
+    ref.close()
+    gpu.close()
+    return reports
+
+
+def print_report(rep):
+    for k in sorted(rep):
+        v = rep[k]
+        print(f"  {k:38s} {v:.6g}" if isinstance(v, float) else f"  {k:38s} {v}")
+    print(flush=True)
