@@ -14,6 +14,37 @@ void pressure_to_float(flip_ctx *c, float *devOut);
 
 static thread_local std::string g_createError;
 
+namespace flip {
+size_t kt_begin(flip_ctx *c) {
+    if (!c->ktEnabled) return 0;
+    if (c->ktUsed + 2 > c->ktPool.size()) {
+        size_t old = c->ktPool.size();
+        c->ktPool.resize(old + 256);
+        for (size_t q = old; q < c->ktPool.size(); q++) FLIP_CUDA_CHECK(cudaEventCreate(&c->ktPool[q]));
+    }
+    size_t slot = c->ktUsed;
+    c->ktUsed += 2;
+    FLIP_CUDA_CHECK(cudaEventRecord(c->ktPool[slot], c->stream));
+    return slot;
+}
+void kt_end(flip_ctx *c, int cls, size_t slot) {
+    if (!c->ktEnabled) return;
+    FLIP_CUDA_CHECK(cudaEventRecord(c->ktPool[slot + 1], c->stream));
+    c->ktPending.push_back({cls, slot, slot + 1});
+}
+void kt_collect(flip_ctx *c) {
+    for (auto &p : c->ktPending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, c->ktPool[p.a], c->ktPool[p.b]) == cudaSuccess) {
+            c->ktSumMs[p.cls] += ms;
+            c->ktCount[p.cls]++;
+        }
+    }
+    c->ktPending.clear();
+    c->ktUsed = 0;
+}
+}  // namespace flip
+
 template <class F>
 static int guarded(flip_ctx *c, F &&f) {
     try {
@@ -51,6 +82,7 @@ static void free_all(flip_ctx *c) {
     cudaFree(c->dS);
     if (c->hS) cudaFreeHost(c->hS);
     if (c->eventsCreated) for (auto &e : c->evStage) cudaEventDestroy(e);
+    for (auto &e : c->ktPool) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
 }
 
@@ -353,6 +385,7 @@ int flip_run_stage(flip_ctx *c, int stage, double dt) {
         if (stage < 0 || stage >= FLIP_NUM_STAGES) throw ApiError(FLIP_ERR_OUT_OF_RANGE, "bad stage id");
         run_stage(c, stage, dt);
         FLIP_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        kt_collect(c);
         float ms = 0.f;
         cudaEventElapsedTime(&ms, c->evStage[stage], c->evStage[stage + 1]);
         c->stageMs[stage] = ms;
@@ -388,6 +421,7 @@ int flip_update(flip_ctx *c, double dt) {
             // inside the pressure stage and at the end of the advance stage
             for (int s = 0; s < FLIP_NUM_STAGES; s++) run_stage(c, s, step);
             FLIP_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+            kt_collect(c);
             for (int s = 0; s < FLIP_NUM_STAGES; s++) {
                 float ms = 0.f;
                 cudaEventElapsedTime(&ms, c->evStage[s], c->evStage[s + 1]);
@@ -525,6 +559,22 @@ int flip_set_array(flip_ctx *c, int which, const void *in) {
 int flip_get_stage_times_ms(const flip_ctx *c, float ms[FLIP_NUM_STAGES]) {
     if (!c || !ms) return FLIP_ERR_RUNTIME;
     for (int s = 0; s < FLIP_NUM_STAGES; s++) ms[s] = c->stageMs[s];
+    return FLIP_OK;
+}
+int flip_enable_kernel_timing(flip_ctx *c, int on) {
+    return guarded(c, [&] { FLIP_CUDA_CHECK(cudaStreamSynchronize(c->stream)); kt_collect(c); c->ktEnabled = on != 0; });
+}
+int flip_reset_kernel_timing(flip_ctx *c) {
+    return guarded(c, [&] {
+        FLIP_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        kt_collect(c);
+        for (int q = 0; q < FLIP_NUM_KERNEL_CLASSES; q++) { c->ktSumMs[q] = 0; c->ktCount[q] = 0; }
+    });
+}
+int flip_get_kernel_timing(const flip_ctx *c, int cls, double *ms, int64_t *n) {
+    if (!c || cls < 0 || cls >= FLIP_NUM_KERNEL_CLASSES) return FLIP_ERR_OUT_OF_RANGE;
+    if (ms) *ms = c->ktSumMs[cls];
+    if (n) *n = c->ktCount[cls];
     return FLIP_OK;
 }
 int flip_get_kernel_launches(const flip_ctx *c, int64_t *n) { if (!c || !n) return FLIP_ERR_RUNTIME; *n = c->launches; return FLIP_OK; }

@@ -159,6 +159,15 @@ struct flip_ctx {
     float stageMs[FLIP_NUM_STAGES] = {0};
     bool eventsCreated = false;
 
+    // optional per-kernel-class device timing (CUDA events on the context's stream)
+    bool ktEnabled = false;
+    std::vector<cudaEvent_t> ktPool;
+    size_t ktUsed = 0;
+    struct KtPending { int cls; size_t a, b; };
+    std::vector<KtPending> ktPending;
+    double ktSumMs[FLIP_NUM_KERNEL_CLASSES] = {0};
+    int64_t ktCount[FLIP_NUM_KERNEL_CLASSES] = {0};
+
     // multi-GPU slab
     int rank = 0, nranks = 1;
 };
@@ -199,6 +208,9 @@ void stage_pressure(flip_ctx *c, double dt);
 
 // helpers
 void scalars_to_host(flip_ctx *c);   // async copy + sync
+size_t kt_begin(flip_ctx *c);                    // records a start event, returns its slot (or 0 when disabled)
+void kt_end(flip_ctx *c, int cls, size_t slot);  // records the stop event
+void kt_collect(flip_ctx *c);                    // after a stream sync: folds pending pairs into the sums
 inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
 
 }  // namespace flip

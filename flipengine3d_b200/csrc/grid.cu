@@ -138,9 +138,11 @@ static void extrapolate_component(flip_ctx *c, float *grid, const unsigned char 
 // MACVelocityField::extrapolateVelocityField  macvelocityfield.cpp:671-677
 void stage_extrapolate(flip_ctx *c) {
     const Dims &d = c->d;
+    size_t kt = kt_begin(c);
     extrapolate_component(c, c->U, c->validU, d.I + 1, d.J, d.K);
     extrapolate_component(c, c->V, c->validV, d.I, d.J + 1, d.K);
     extrapolate_component(c, c->W, c->validW, d.I, d.J, d.K + 1);
+    kt_end(c, FLIP_KERNEL_EXTRAPOLATE, kt);
 }
 
 // ------------------------------------------------------------------------------------------------

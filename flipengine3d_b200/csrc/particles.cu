@@ -297,6 +297,7 @@ void particles_sort(flip_ctx *c, bool applyRules, double frameDt) {
     ParticleSoA &src = c->P[c->cur_buf];
     ParticleSoA &dst = c->P[1 - c->cur_buf];
     int nC = d.nC;
+    size_t ktSort = kt_begin(c);
     k_reset_sort_scalars<<<1, 1, 0, st>>>(c->dS); c->launches++;
     FLIP_CUDA_CHECK(cudaMemsetAsync(c->cellCount, 0, sizeof(int) * (nC + 1), st));
     if (n > 0) {
@@ -331,6 +332,7 @@ void particles_sort(flip_ctx *c, bool applyRules, double frameDt) {
         k_gather<<<cdiv(n, TPB), TPB, 0, st>>>(src, dst, c->srcIdx, n, c->dS, c->trackIds ? c->pid[c->cur_buf] : nullptr,
                                                c->pid[1 - c->cur_buf]); c->launches++;
     }
+    kt_end(c, FLIP_KERNEL_SORT, ktSort);
     scalars_to_host(c);
     c->np = c->hS->numParticles;
     c->cur_buf = 1 - c->cur_buf;
@@ -624,8 +626,10 @@ static void run_sdf_p2g(flip_ctx *c) {
     GatherParams g = make_gather_params(c);
     dim3 block(128, 1, 1);
     dim3 grid(cdiv(d.I + 1, 128), d.J + 1, d.K + 1);
+    size_t kt = kt_begin(c);
     k_sdf_p2g<<<grid, block, 0, c->stream>>>(c->P[c->cur_buf], c->cellStart, g, c->U, c->V, c->W, c->validU, c->validV,
                                              c->validW, c->phiL, c->phiS);
+    kt_end(c, FLIP_KERNEL_SDF_P2G, kt);
     c->launches++;
     FLIP_CUDA_CHECK(cudaGetLastError());
 }
@@ -818,7 +822,9 @@ void stage_g2p(flip_ctx *c) {
     if (c->np == 0) return;
     AdvectParams a = make_advect_params(c, 0.0);
     MacField fn{c->U, c->V, c->W}, fo{c->sU, c->sV, c->sW};
+    size_t kt = kt_begin(c);
     k_g2p<<<cdiv(c->np, TPB), TPB, 0, c->stream>>>(c->P[c->cur_buf], a, fn, fo);
+    kt_end(c, FLIP_KERNEL_G2P, kt);
     c->launches++;
     FLIP_CUDA_CHECK(cudaGetLastError());
 }
@@ -827,7 +833,9 @@ void stage_advance(flip_ctx *c, double dt) {
     if (c->np > 0) {
         AdvectParams a = make_advect_params(c, dt);
         MacField fn{c->U, c->V, c->W};
+        size_t kt = kt_begin(c);
         k_advance<<<cdiv(c->np, TPB), TPB, 0, c->stream>>>(c->P[c->cur_buf], a, fn, c->phiS, c->nearSolid);
+        kt_end(c, FLIP_KERNEL_ADVANCE, kt);
         c->launches++;
         FLIP_CUDA_CHECK(cudaGetLastError());
     }

@@ -463,6 +463,7 @@ void stage_pressure(flip_ctx *c, double dt) {
     PGrid g{d.I, d.J, d.K, d.I, d.I * d.J};
     int nSeg = ps->nSegAll;
 
+    size_t ktBuild = kt_begin(c);
     k_reset_pressure_scalars<<<1, 1, 0, st>>>(c->dS); c->launches++;
     k_seg_flag<<<cdiv((long long)nSeg * 32, TPB), TPB, 0, st>>>(c->phiL, g, d.nC, nSeg, ps->maskAll, ps->flagAll, c->dS);
     c->launches++;
@@ -494,6 +495,7 @@ void stage_pressure(flip_ctx *c, double dt) {
     k_build_system<<<segBlocks, TPB, 0, st>>>(c->segCell, c->segMask, bp, c->phiL, c->U, c->V, c->W, c->wU, c->wV,
                                              c->wW, c->Adiag, c->AoffU, c->AoffV, c->AoffW, c->vb, c->vx_, c->dS);
     c->launches++;
+    kt_end(c, FLIP_KERNEL_PRESSURE_BUILD, ktBuild);
     scalars_to_host(c);
     int n = c->hS->numRows;
     int numSeg = c->hS->numSegments;
@@ -528,11 +530,15 @@ void stage_pressure(flip_ctx *c, double dt) {
         int stop = it + batch;
         if (stop > c->pressureMaxIter) stop = c->pressureMaxIter;
         for (; it < stop; it++) {
+            size_t ktIt = kt_begin(c);
+            size_t ktSp = kt_begin(c);
             k_pcg_spmv<<<segBlocks, TPB, 0, st>>>(c->segCell, c->segMask, pp, c->Adiag, c->AoffU, c->AoffV, c->AoffW,
                                                   c->vs, c->vz, c->dS, it);
+            kt_end(c, FLIP_KERNEL_PCG_SPMV, ktSp);
             k_pcg_update<<<segBlocks, TPB, 0, st>>>(c->segCell, c->segMask, c->Adiag, c->vs, c->vz, c->vx_, c->vr,
                                                     c->dS, it, jacobi);
             k_pcg_direction<<<segBlocks, TPB, 0, st>>>(c->segCell, c->segMask, c->vz, c->vs, c->dS, it);
+            kt_end(c, FLIP_KERNEL_PCG_ITER, ktIt);
             c->launches += 3;
         }
         scalars_to_host(c);
@@ -551,9 +557,11 @@ void stage_pressure(flip_ctx *c, double dt) {
     ApplyParams ap;
     ap.g = g;
     ap.factor = (float)(dt / d.dx);
+    size_t ktAp = kt_begin(c);
     k_apply_pressure<0><<<cdiv(d.nU, TPB), TPB, 0, st>>>(ap, c->phiL, c->vx_, c->wU, c->U, c->validU);
     k_apply_pressure<1><<<cdiv(d.nV, TPB), TPB, 0, st>>>(ap, c->phiL, c->vx_, c->wV, c->V, c->validV);
     k_apply_pressure<2><<<cdiv(d.nW, TPB), TPB, 0, st>>>(ap, c->phiL, c->vx_, c->wW, c->W, c->validW);
+    kt_end(c, FLIP_KERNEL_PRESSURE_APPLY, ktAp);
     c->launches += 3;
     FLIP_CUDA_CHECK(cudaGetLastError());
 }

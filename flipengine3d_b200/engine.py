@@ -18,6 +18,9 @@ ARRAY_ID = dict(U=0, V=1, W=2, validU=3, validV=4, validW=5, liquid_phi=6, solid
                 weightU=8, weightV=9, weightW=10, weightC=11, savedU=12, savedV=13, savedW=14,
                 near_solid=15, pressure=16)
 
+KERNEL_CLASSES = ("sdf_p2g", "g2p", "advance", "sort", "extrapolate", "pcg_spmv", "pcg_iter", "pressure_build",
+                  "pressure_apply")
+
 FLIP_OK, FLIP_ERR_RUNTIME, FLIP_ERR_DOMAIN, FLIP_ERR_OUT_OF_RANGE, FLIP_ERR_CUDA, FLIP_ERR_UNSUPPORTED = range(6)
 
 
@@ -95,6 +98,9 @@ def load_library():
     L.flip_set_array.argtypes = [vp, ci, vp]
     L.flip_get_stage_times_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.flip_get_kernel_launches.argtypes = [vp, C.POINTER(C.c_int64)]
+    L.flip_enable_kernel_timing.argtypes = [vp, ci]
+    L.flip_reset_kernel_timing.argtypes = [vp]
+    L.flip_get_kernel_timing.argtypes = [vp, ci, C.POINTER(cd), C.POINTER(C.c_int64)]
     L.flip_get_stream.argtypes = [vp, C.POINTER(vp)]
     L.flip_synchronize.argtypes = [vp]
     L.flip_set_slab.argtypes = [vp, ci, ci, vp, ci]
@@ -267,6 +273,21 @@ class FluidSimulation:
         a = (C.c_float * len(STAGES))()
         self._check(self.L.flip_get_stage_times_ms(self.h, a))
         return dict(zip(STAGES, list(a)))
+
+    def enable_kernel_timing(self, on=True):
+        self._check(self.L.flip_enable_kernel_timing(self.h, 1 if on else 0))
+
+    def reset_kernel_timing(self):
+        self._check(self.L.flip_reset_kernel_timing(self.h))
+
+    def kernel_timing(self):
+        """{class: (total_ms, launches)}"""
+        out = {}
+        for i, name in enumerate(KERNEL_CLASSES):
+            ms, n = C.c_double(), C.c_int64()
+            self._check(self.L.flip_get_kernel_timing(self.h, i, C.byref(ms), C.byref(n)))
+            out[name] = (ms.value, n.value)
+        return out
 
     def kernel_launches(self):
         v = C.c_int64()

@@ -171,6 +171,24 @@ int flip_set_array(flip_ctx *ctx, int which, const void *host_in);
 /* Device time of each stage in the last substep, milliseconds (CUDA events on the context's stream) —
  * the analogue of the reference's TimingData buckets (fluidsimulation.h:1172-1233). */
 int flip_get_stage_times_ms(const flip_ctx *ctx, float ms[FLIP_NUM_STAGES]);
+/* Per-kernel-class device time, measured with CUDA event pairs recorded on the context's stream
+ * around the launches of each class while enabled.  total_ms / launches = mean launch duration. */
+enum {
+    FLIP_KERNEL_SDF_P2G = 0,   /* fused liquid-SDF + P2G gather                         */
+    FLIP_KERNEL_G2P = 1,       /* PIC/FLIP grid-to-particle                             */
+    FLIP_KERNEL_ADVANCE = 2,   /* RK3 + collision                                       */
+    FLIP_KERNEL_SORT = 3,      /* whole cell sort + removal pipeline (several launches) */
+    FLIP_KERNEL_EXTRAPOLATE = 4, /* one extrapolateVelocityField call (3 components)    */
+    FLIP_KERNEL_PCG_SPMV = 5,  /* one operator application (+ fused dot)                */
+    FLIP_KERNEL_PCG_ITER = 6,  /* one whole PCG iteration                               */
+    FLIP_KERNEL_PRESSURE_BUILD = 7, /* row enumeration + rhs + matrix                   */
+    FLIP_KERNEL_PRESSURE_APPLY = 8, /* velocity update                                  */
+    FLIP_NUM_KERNEL_CLASSES = 9
+};
+int flip_enable_kernel_timing(flip_ctx *ctx, int on);
+int flip_reset_kernel_timing(flip_ctx *ctx);
+int flip_get_kernel_timing(const flip_ctx *ctx, int kernel_class, double *total_ms, int64_t *launches);
+
 /* Number of kernels this library launched on the context since creation. */
 int flip_get_kernel_launches(const flip_ctx *ctx, int64_t *launches);
 /* Raw cudaStream_t of the context (for callers that time with their own events). */

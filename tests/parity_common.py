@@ -216,3 +216,42 @@ def print_report(rep):
         v = rep[k]
         print(f"  {k:38s} {v:.6g}" if isinstance(v, float) else f"  {k:38s} {v}")
     print(flush=True)
+
+
+# Tolerances of the parity contract (SURVEY §8d "Parity report"; north_star: integer bookkeeping
+# bit-exact, float fields rel L2 <= 1e-4 per step).
+TOL_REL_L2 = 1e-4
+TOL_P2G_REL_L2 = 1e-5      # P2G differs from the reference by float summation order only
+TOL_POS_MAX_ABS_DX = 1e-3  # particle positions: max-abs <= 1e-3 dx
+
+
+def check_report(rep, dx=0.125, isolate=True):
+    """Asserts the parity contract on one lock-step substep report."""
+    # integer bookkeeping: exact
+    assert rep["sdf.sign_flips"] == 0, rep
+    assert rep["gpu.pressure_rows"] == rep["ref.fluid_cells"] or rep["ref.fluid_cells"] == 0, rep
+    assert rep["advance.gpu_particles"] == rep["advance.ref_particles"], rep
+    for comp in "UVW":
+        assert rep[f"p2g.valid{comp}.hamming"] == 0, rep
+        assert rep[f"pressure.valid{comp}.hamming"] == 0, rep
+    # order-independent stages: bit-exact from identical inputs
+    assert rep["sdf.mismatch_cells"] == 0, rep
+    if isolate:
+        for comp in "UVW":
+            assert rep[f"extrapolate_a.{comp}.mismatch"] == 0, rep
+            assert rep[f"extrapolate_b.{comp}.max_abs"] == 0.0, rep
+            assert rep[f"body_force.{comp}.max_abs"] == 0.0, rep
+            assert rep[f"constrain.{comp}.max_abs"] == 0.0, rep
+        assert rep["g2p.vel.mismatch"] == 0, rep
+        if "advance.pos.mismatch" in rep:
+            assert rep["advance.pos.mismatch"] == 0, rep
+    # float fields
+    for comp in "UVW":
+        assert rep[f"p2g.{comp}.rel_l2"] <= TOL_P2G_REL_L2, rep
+        assert rep[f"pressure.{comp}.rel_l2"] <= TOL_REL_L2, rep
+        assert rep[f"extrapolate_b.{comp}.rel_l2"] <= TOL_REL_L2, rep
+    assert rep["g2p.vel.rel_l2"] <= TOL_REL_L2, rep
+    if "advance.pos.rel_l2" in rep:
+        assert rep["advance.pos.rel_l2"] <= TOL_REL_L2, rep
+        assert rep["advance.pos.max_abs"] <= TOL_POS_MAX_ABS_DX * dx, rep
+    assert rep["gpu.pcg_converged"] == 1, rep
