@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""Benchmark of the FLIP time-step hot path (BASELINE.json metric: particle-steps/s and ms/frame).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one frame, FluidSimulation::update(1/30) (fluidsimulation.cpp:5755), i.e. all CFL
+substeps of the whole hot path (liquid SDF, P2G, extrapolation, body force, pressure projection,
+G2P, RK3 advection + collision + removal) over the synthetic sphere-drop scene of SURVEY §8d
+config 3 (256^3 grid, 16.1 M marker particles).  value = sum over timed substeps of live particles
+/ device time (CUDA events on the context's stream, max over ranks).
+
+Our arm keeps the state resident in HBM for `value`; the `e2e` leg repeats the same frames through
+the C-ABI with HOST buffers: flip_set_particles (pinned host AoS -> device), flip_update,
+flip_get_particles (device -> pinned host AoS), every step, inside the timed region.
+
+--impl reference times the UNMODIFIED reference engine (oracle/_ref/libflipref_fast.so, built by
+oracle/Makefile from /root/reference) on the host cores, all threads, on a bounded sample of the
+same workload.  This file and tests/ are the only places that may execute anything under oracle/.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FRAME_DT = 1.0 / 30.0
+METRIC = "particle_steps_per_s"
+UNIT = "particle-steps/s"
+FALLBACK_HBM_GBS = 6650.0   # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+# ------------------------------------------------------------------------------------------------
+def measured_hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            for k in ("hbm_gbs", "hbm_gb_s", "hbm_GBps"):
+                if k in d:
+                    return float(d[k]), "measured"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+class quiet_stdout:
+    """The reference engine prints a version banner and its log straight to fd 1; keep our stdout to
+    the single JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        self.null = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(self.null, 1)
+
+    def __exit__(self, *a):
+        os.dup2(self.saved, 1)
+        os.close(self.null)
+        os.close(self.saved)
+
+
+def workload(grid):
+    from flipengine3d_b200 import scenes
+    sc = scenes.sphere_drop(grid)
+    return sc
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the unmodified reference engine on the host cores
+# ------------------------------------------------------------------------------------------------
+def run_reference(grid, steps, warmup, threads=None):
+    """Returns (particle_steps_per_s, ms_per_step, info). One step = one update(1/30)."""
+    from oracle import refengine
+    kind = "fast" if refengine.available("fast") else "golden"
+    if not refengine.available(kind):
+        raise RuntimeError("oracle/_ref is not built (run __graft_entry__.build() where /root/reference exists)")
+    sc = workload(grid)
+    with quiet_stdout():
+        ref = refengine.RefEngine(sc["dims"], sc["dx"], sc["pos"], sc["vel"], kind=kind, threads=threads)
+        cores = ref.L.ref_get_threads()
+        for _ in range(warmup):
+            ref.update(FRAME_DT)
+        psteps, t0 = 0, time.perf_counter()
+        for _ in range(steps):
+            n_before = ref.num_particles
+            ref.update(FRAME_DT)
+            psteps += n_before * max(ref.substeps, 1)
+        el = time.perf_counter() - t0
+    info = dict(kind="reference", cores=int(cores), build=kind,
+                substeps_per_frame=int(ref.substeps), sample=f"spheredrop{grid} ({sc['pos'].shape[0]} particles, same seeding rule as the GPU workload), "
+                       f"{steps} frame(s) of update(1/30) after {warmup} warm-up frame(s), surface reconstruction off")
+    ref.close()
+    return psteps / el, 1e3 * el / max(steps, 1), info
+
+
+def reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    v, ms, info = run_reference(args.ref_grid, args.steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 fields / f64 PCG", "data": "synthetic",
+            "config": {"workload": f"spheredrop{args.grid}", "sample_grid": args.ref_grid, "dx": 0.125,
+                       "frame_dt": FRAME_DT, "step": "one frame = FluidSimulation::update(1/30)"},
+            "cpu_baseline": dict(info, value=v, unit=UNIT),
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def liquid_face_count(phi):
+    """Nf_liq of SURVEY §8d: faces adjacent to at least one liquid cell."""
+    liq = phi < 0
+    K, J, I = liq.shape
+    u = np.zeros((K, J, I + 1), dtype=bool); u[:, :, :-1] |= liq; u[:, :, 1:] |= liq
+    v = np.zeros((K, J + 1, I), dtype=bool); v[:, :-1, :] |= liq; v[:, 1:, :] |= liq
+    w = np.zeros((K + 1, J, I), dtype=bool); w[:-1, :, :] |= liq; w[1:, :, :] |= liq
+    return int(u.sum() + v.sum() + w.sum())
+
+
+def algorithmic_bytes(Np, dims, n_rows, nf_liq):
+    """SURVEY §8d 'Algorithmic bytes' per launch of each kernel class."""
+    I, J, K = dims
+    Nc = I * J * K
+    Nf = (I + 1) * J * K + I * (J + 1) * K + I * J * (K + 1)
+    return {
+        "sdf_p2g": 24 * Np + 5 * Nf + 4 * Nc,     # fused liquid SDF + P2G: particles read once
+        "g2p": 36 * Np + 8 * nf_liq,
+        "advance": 24 * Np + 4 * nf_liq,
+        "extrapolate": 9 * Nf,                     # one extrapolateVelocityField call (3 components)
+        "pcg_spmv": 36 * n_rows,
+        "pcg_iter": 124 * n_rows,                  # + P (preconditioner data) not credited
+    }
+
+
+def ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from flipengine3d_b200 import engine as fe
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: libflip_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    sc = workload(args.grid)
+    I, J, K = sc["dims"]
+    sim = fe.FluidSimulation(I, J, K, sc["dx"], device=local_rank)
+    sim.addBodyForce(0.0, -25.0, 0.0)
+    if args.preconditioner:
+        sim.setPreconditioner(args.preconditioner)
+    sim.loadMarkerParticleData(fe.MarkerParticleData(sc["pos"], sc["vel"]))
+    sim.initialize()
+    stream = torch.cuda.ExternalStream(sim.stream(), device=torch.device("cuda", local_rank))
+
+    def barrier():
+        sim.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    for _ in range(args.warmup):
+        sim.update(FRAME_DT)
+    barrier()
+
+    # ---- timed region: K frames, state resident in HBM
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    sim.enable_kernel_timing(True)
+    sim.reset_kernel_timing()
+    launches0 = sim.kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    psteps, substeps, pcg_iters, rows = 0, 0, 0, []
+    stage_ms = {}
+    for _ in range(args.steps):
+        sim.update(FRAME_DT)
+        n_in = None
+        for st in sim.substep_stats():
+            # particles that went through the substep = survivors + those removed at its end
+            n_in = st["particles"] + st["removed_solid"] + st["removed_crowded"] + st["removed_fast"]
+            psteps += n_in
+            substeps += 1
+            pcg_iters += st["pcg_iterations"]
+            rows.append(st["pressure_rows"])
+        for k, v in sim.stage_times_ms().items():
+            stage_ms[k] = stage_ms.get(k, 0.0) + v
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = sim.kernel_launches() - launches0
+    kt = sim.kernel_timing()
+    sim.enable_kernel_timing(False)
+    clocks = sampler.stop()
+
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(psteps), float(launches)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms_max = float(t.item())
+    value = float(tot[0].item()) / (ms_max * 1e-3)
+
+    # ---- e2e leg: the same frames through the C-ABI with host buffers
+    Np = sim.getNumMarkerParticles()
+    host = torch.empty((Np + 4096, 6), dtype=torch.float32).pin_memory().numpy()
+    sim.getMarkerParticles(out=host)
+    barrier()
+    e2e_psteps, h2d, d2h = 0, 0, 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        n = sim.getNumMarkerParticles()
+        sim.setMarkerParticles(host[:n])             # host -> device (pinned)
+        h2d += n * 24
+        sim.update(FRAME_DT)
+        for st in sim.substep_stats():
+            e2e_psteps += st["particles"] + st["removed_solid"] + st["removed_crowded"] + st["removed_fast"]
+        n = sim.getNumMarkerParticles()
+        sim.getMarkerParticles(out=host)             # device -> host (pinned)
+        d2h += n * 24
+    sim.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    tp = torch.tensor([float(e2e_psteps)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tp, op=dist.ReduceOp.SUM)
+    e2e_value = float(tp.item()) / float(te.item())
+
+    if rank == 0:
+        peak, peak_kind = measured_hbm_peak()
+        n_rows = int(np.mean(rows)) if rows else 0
+        nf_liq = liquid_face_count(sim.array("liquid_phi"))
+        ab = algorithmic_bytes(Np, (I, J, K), n_rows, nf_liq)
+        kernels = {}
+        for name, (tot_ms, n) in kt.items():
+            if n == 0:
+                continue
+            avg_ms = tot_ms / n
+            ent = {"launches": int(n), "avg_ms": avg_ms, "total_ms": tot_ms, "share_of_step": tot_ms / ms}
+            if name in ab:
+                gbs = ab[name] / (avg_ms * 1e-3) / 1e9
+                ent.update(algorithmic_bytes=int(ab[name]), achieved_gbs=gbs, frac=gbs / peak)
+            kernels[name] = ent
+        # the dominant kernel: largest share of the step among single-kernel classes
+        singles = [k for k in ("sdf_p2g", "g2p", "advance", "pcg_spmv") if k in kernels]
+        dom = max(singles, key=lambda k: kernels[k]["total_ms"])
+        roof = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["achieved_gbs"], "peak": peak,
+                "peak_kind": peak_kind, "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": None,
+                "algorithmic_bytes": kernels[dom]["algorithmic_bytes"], "avg_launch_ms": kernels[dom]["avg_ms"],
+                "share_of_step": kernels[dom]["share_of_step"]}
+        tp_file = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp_file):
+            try:
+                roof["traffic"] = json.load(open(tp_file)).get(dom)
+            except Exception:
+                pass
+        cpu = None
+        if world == 1 or True:
+            try:
+                v, cms, info = run_reference(args.ref_grid, args.cpu_steps, 1)
+                cpu = dict(info, value=v, unit=UNIT, ms_per_step=cms)
+            except Exception as e:   # the oracle always exists on the GPU box; report loudly if not
+                cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"FAILED: {e}"}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32 fields / f64 PCG vectors", "data": "synthetic",
+                "config": {"workload": f"spheredrop{args.grid}", "grid": [I, J, K], "dx": sc["dx"], "particles": int(Np),
+                           "frame_dt": FRAME_DT, "step": "one frame = flip_update(1/30), all CFL substeps",
+                           "substeps_timed": substeps, "pcg_iterations_timed": pcg_iters, "pressure_rows": n_rows,
+                           "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (z-slab decomposition not built yet)",
+                           "l2": "inputs larger than L2 (particles 386 MB, each MAC field 202 MB vs 126 MB L2)"},
+                "roofline": roof, "kernels": kernels, "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
+                "cpu_baseline": cpu,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // args.steps,
+                        "d2h_bytes_per_step": d2h // args.steps, "ms_per_step": 1e3 * float(te.item()) / args.steps},
+                "gpu_launches": int(tot[1].item()), "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    sim.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--grid", type=int, default=256, help="sphere-drop grid size (headline: 256)")
+    ap.add_argument("--ref-grid", type=int, default=128,
+                    help="grid of the bounded CPU sample of the same workload (reference arm / cpu_baseline)")
+    ap.add_argument("--cpu-steps", type=int, default=3, help="frames of the cpu_baseline sample in our arm")
+    ap.add_argument("--preconditioner", default=None)
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3   # timing rule: at least 3 warm-up steps
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+    else:
+        ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()
