@@ -328,6 +328,332 @@ __global__ void k_pcg_direction(const int *__restrict__ segCell, const unsigned 
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Multigrid preconditioner: z = M^-1 r as one symmetric V-cycle of an aggregation multigrid.
+//
+// Level 0 is the pressure system itself (rows = liquid cells, driven by the active-segment list).
+// Level l+1 aggregates 2x2x2 cells of level l; its operator is the Galerkin product P^T A P with the
+// piecewise-constant P, which for a 7-point operator is again a 7-point operator: the coarse
+// off-diagonal towards +i is the sum of the fine off-diagonals crossing that aggregate face, the
+// coarse diagonal is the sum of the children's diagonals minus twice the off-diagonals interior to
+// the aggregate.  Free surface (ghost-fluid diagonal terms) and solid walls (zero face weights) are
+// carried to every level by construction, so no geometric special-casing is needed.  Smoother:
+// damped Jacobi, nu sweeps before and after the coarse correction (first sweep from a zero guess,
+// first post sweep fused with the prolongation); the coarse correction is over-weighted by a
+// constant (piecewise-constant aggregation under-estimates smooth corrections by ~2x).  Everything
+// is a fixed symmetric linear operator, as CG requires.  Levels hold fp32; the Krylov vectors, the
+// residual and the stopping test stay fp64 and are the reference's (pcgsolver.h:248-302).
+// Levels with <= MG_SMALL cells are run by one CTA in a single launch.
+// ------------------------------------------------------------------------------------------------
+static constexpr int MG_MAX_LEVELS = 12;
+static constexpr int MG_SMALL = 4096;
+
+struct MgLevel {
+    int I, J, K, sj, sk, n;
+    float *diag, *invD, *oU, *oV, *oW, *x, *x2, *b;
+};
+
+struct MgParams {
+    float omega;      // Jacobi damping
+    float scale;      // coarse-correction weight
+    int nu;           // pre = post sweeps
+    int coarseSweeps;
+};
+
+// sum_nb off(c,nb) * x(nb) on a dense level (bounds-checked: coarse cells can sit on the grid border)
+__device__ __forceinline__ float mg_offsum(const MgLevel &L, const float *x, int c, int i, int j, int k) {
+    float s = 0.0f, a;
+    if (k > 0) { a = L.oW[c - L.sk]; if (a != 0.0f) s += a * x[c - L.sk]; }
+    if (j > 0) { a = L.oV[c - L.sj]; if (a != 0.0f) s += a * x[c - L.sj]; }
+    if (i > 0) { a = L.oU[c - 1];    if (a != 0.0f) s += a * x[c - 1]; }
+    a = L.oU[c]; if (a != 0.0f) s += a * x[c + 1];
+    a = L.oV[c]; if (a != 0.0f) s += a * x[c + L.sj];
+    a = L.oW[c]; if (a != 0.0f) s += a * x[c + L.sk];
+    return s;
+}
+
+// x + scale * (P e)(c) at a cell and at its six neighbours is what the fused prolongation+sweep reads
+__device__ __forceinline__ float mg_corrected(const MgLevel &L, const MgLevel &C, const float *x, const float *e,
+                                              float scale, int c, int i, int j, int k) {
+    return x[c] + scale * e[(i >> 1) + C.sj * (j >> 1) + C.sk * (k >> 1)];
+}
+
+__device__ __forceinline__ float mg_offsum_corrected(const MgLevel &L, const MgLevel &C, const float *x, const float *e,
+                                                     float scale, int c, int i, int j, int k) {
+    float s = 0.0f, a;
+    if (k > 0) { a = L.oW[c - L.sk]; if (a != 0.0f) s += a * mg_corrected(L, C, x, e, scale, c - L.sk, i, j, k - 1); }
+    if (j > 0) { a = L.oV[c - L.sj]; if (a != 0.0f) s += a * mg_corrected(L, C, x, e, scale, c - L.sj, i, j - 1, k); }
+    if (i > 0) { a = L.oU[c - 1];    if (a != 0.0f) s += a * mg_corrected(L, C, x, e, scale, c - 1, i - 1, j, k); }
+    a = L.oU[c]; if (a != 0.0f) s += a * mg_corrected(L, C, x, e, scale, c + 1, i + 1, j, k);
+    a = L.oV[c]; if (a != 0.0f) s += a * mg_corrected(L, C, x, e, scale, c + L.sj, i, j + 1, k);
+    a = L.oW[c]; if (a != 0.0f) s += a * mg_corrected(L, C, x, e, scale, c + L.sk, i, j, k + 1);
+    return s;
+}
+
+// one damped-Jacobi sweep at cell c of a dense level.  mode 0: from a zero guess; 1: regular;
+// 2: regular on (xin + scale * P e)
+__device__ __forceinline__ float mg_sweep_cell(const MgLevel &L, const MgLevel &C, const float *xin, const float *e,
+                                               float omega, float scale, int mode, int c, int i, int j, int k) {
+    float inv = L.invD[c];
+    if (inv == 0.0f) return 0.0f;
+    float b = L.b[c];
+    if (mode == 0) return omega * inv * b;
+    float xc, ns;
+    if (mode == 1) { xc = xin[c]; ns = mg_offsum(L, xin, c, i, j, k); }
+    else { xc = mg_corrected(L, C, xin, e, scale, c, i, j, k); ns = mg_offsum_corrected(L, C, xin, e, scale, c, i, j, k); }
+    return (1.0f - omega) * xc + omega * inv * (b + ns);
+}
+
+// residual b - A x at a cell of a dense level
+__device__ __forceinline__ float mg_residual_cell(const MgLevel &L, const float *x, int c, int i, int j, int k) {
+    if (L.invD[c] == 0.0f) return 0.0f;
+    return L.b[c] - (L.diag[c] * x[c] - mg_offsum(L, x, c, i, j, k));
+}
+
+// b_coarse(C) = sum over the 8 children of the fine residual
+__device__ __forceinline__ float mg_restrict_cell(const MgLevel &F, const float *x, int ci, int cj, int ck) {
+    float s = 0.0f;
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        int i = 2 * ci + (q & 1), j = 2 * cj + ((q >> 1) & 1), k = 2 * ck + (q >> 2);
+        if (i < F.I && j < F.J && k < F.K) s += mg_residual_cell(F, x, i + F.sj * j + F.sk * k, i, j, k);
+    }
+    return s;
+}
+
+__global__ void k_mg_sweep(MgLevel L, MgLevel C, const float *xin, const float *e, float *xout, float omega,
+                           float scale, int mode, const DeviceScalars *S) {
+    if (S->pcgDone) return;
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= L.n) return;
+    int i = c % L.I, j = (c / L.I) % L.J, k = c / L.sk;
+    xout[c] = mg_sweep_cell(L, C, xin, e, omega, scale, mode, c, i, j, k);
+}
+
+__global__ void k_mg_restrict(MgLevel F, MgLevel C, const float *x, const DeviceScalars *S) {
+    if (S->pcgDone) return;
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C.n) return;
+    if (C.invD[c] == 0.0f) { C.b[c] = 0.0f; return; }
+    int i = c % C.I, j = (c / C.I) % C.J, k = c / C.sk;
+    C.b[c] = mg_restrict_cell(F, x, i, j, k);
+}
+
+struct MgSmallArgs {
+    MgLevel lv[MG_MAX_LEVELS];
+    int first, last;   // levels first..last are run by this launch (b of `first` is already set)
+    MgParams p;
+};
+
+// the small levels of the V-cycle in one CTA: down, coarsest sweeps, up.  Leaves the result in lv[first].x.
+__global__ void __launch_bounds__(1024) k_mg_small(MgSmallArgs A, const DeviceScalars *S) {
+    if (S->pcgDone) return;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const float omega = A.p.omega, scale = A.p.scale;
+    for (int l = A.first; l <= A.last; l++) {
+        const MgLevel &L = A.lv[l];
+        int sweeps = (l == A.last) ? A.p.coarseSweeps : A.p.nu;
+        float *xa = L.x, *xb = L.x2;
+        for (int s = 0; s < sweeps; s++) {
+            for (int c = tid; c < L.n; c += nt) {
+                int i = c % L.I, j = (c / L.I) % L.J, k = c / L.sk;
+                xb[c] = mg_sweep_cell(L, L, xa, nullptr, omega, scale, s == 0 ? 0 : 1, c, i, j, k);
+            }
+            __syncthreads();
+            float *t = xa; xa = xb; xb = t;
+        }
+        // after an odd number of sweeps the result sits in x2: copy so that x always holds it
+        if (sweeps & 1) {
+            for (int c = tid; c < L.n; c += nt) L.x[c] = L.x2[c];
+            __syncthreads();
+        }
+        if (l < A.last) {
+            const MgLevel &C = A.lv[l + 1];
+            for (int c = tid; c < C.n; c += nt) {
+                int i = c % C.I, j = (c / C.I) % C.J, k = c / C.sk;
+                C.b[c] = (C.invD[c] == 0.0f) ? 0.0f : mg_restrict_cell(L, L.x, i, j, k);
+            }
+            __syncthreads();
+        }
+    }
+    for (int l = A.last - 1; l >= A.first; l--) {
+        const MgLevel &L = A.lv[l];
+        const MgLevel &C = A.lv[l + 1];
+        float *xa = L.x, *xb = L.x2;
+        for (int s = 0; s < A.p.nu; s++) {
+            for (int c = tid; c < L.n; c += nt) {
+                int i = c % L.I, j = (c / L.I) % L.J, k = c / L.sk;
+                xb[c] = mg_sweep_cell(L, C, xa, C.x, omega, scale, s == 0 ? 2 : 1, c, i, j, k);
+            }
+            __syncthreads();
+            float *t = xa; xa = xb; xb = t;
+        }
+        if (A.p.nu & 1) {
+            for (int c = tid; c < L.n; c += nt) L.x[c] = L.x2[c];
+            __syncthreads();
+        }
+    }
+}
+
+// ---- level 0: segment-driven, right-hand side = the fp64 PCG residual
+struct Mg0 {
+    PGrid g;
+    float fac;                      // (float)(dt/dx^2): level-0 off-diagonal magnitude = fac * weight
+    const double *Adiag;
+    const float *oU, *oV, *oW;      // masked face weights (AoffU/V/W)
+    const float *invD;
+    const unsigned int *rowBits;    // 1 bit per cell: is a pressure row
+};
+
+__device__ __forceinline__ float mg0_offsum(const Mg0 &M, const float *x, int c) {
+    float s = 0.0f, a;
+    a = M.oW[c - M.g.sk]; if (a != 0.0f) s += a * x[c - M.g.sk];
+    a = M.oV[c - M.g.sj]; if (a != 0.0f) s += a * x[c - M.g.sj];
+    a = M.oU[c - 1];      if (a != 0.0f) s += a * x[c - 1];
+    a = M.oU[c];          if (a != 0.0f) s += a * x[c + 1];
+    a = M.oV[c];          if (a != 0.0f) s += a * x[c + M.g.sj];
+    a = M.oW[c];          if (a != 0.0f) s += a * x[c + M.g.sk];
+    return M.fac * s;
+}
+
+__device__ __forceinline__ float mg0_corr(const Mg0 &M, const MgLevel &C, const float *x, const float *e, float scale, int c) {
+    int i = c % M.g.I, j = (c / M.g.I) % M.g.J, k = c / M.g.sk;
+    return x[c] + scale * e[(i >> 1) + C.sj * (j >> 1) + C.sk * (k >> 1)];
+}
+
+__device__ __forceinline__ float mg0_offsum_corr(const Mg0 &M, const MgLevel &C, const float *x, const float *e,
+                                                 float scale, int c) {
+    float s = 0.0f, a;
+    a = M.oW[c - M.g.sk]; if (a != 0.0f) s += a * mg0_corr(M, C, x, e, scale, c - M.g.sk);
+    a = M.oV[c - M.g.sj]; if (a != 0.0f) s += a * mg0_corr(M, C, x, e, scale, c - M.g.sj);
+    a = M.oU[c - 1];      if (a != 0.0f) s += a * mg0_corr(M, C, x, e, scale, c - 1);
+    a = M.oU[c];          if (a != 0.0f) s += a * mg0_corr(M, C, x, e, scale, c + 1);
+    a = M.oV[c];          if (a != 0.0f) s += a * mg0_corr(M, C, x, e, scale, c + M.g.sj);
+    a = M.oW[c];          if (a != 0.0f) s += a * mg0_corr(M, C, x, e, scale, c + M.g.sk);
+    return M.fac * s;
+}
+
+// mode as in mg_sweep_cell.  last != 0: also write z (fp64) and accumulate rho = z.r into slot `rhoSlot`.
+__global__ void k_mg0_sweep(const int *__restrict__ segCell, const unsigned int *__restrict__ segMask, Mg0 M, MgLevel C,
+                            const double *__restrict__ r, const float *xin, const float *e, float *xout, float omega,
+                            float scale, int mode, int last, double *zout, DeviceScalars *S, int rhoSlot) {
+    if (S->pcgDone) return;
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    double part = 0.0;
+    if (warp < S->numSegments) {
+        int c = segCell[warp] + lane;
+        if ((segMask[warp] >> lane) & 1u) {
+            float inv = M.invD[c];
+            double rd = r[c];
+            float b = (float)rd;
+            float xn;
+            if (inv == 0.0f) xn = 0.0f;
+            else if (mode == 0) xn = omega * inv * b;
+            else if (mode == 1) xn = (1.0f - omega) * xin[c] + omega * inv * (b + mg0_offsum(M, xin, c));
+            else xn = (1.0f - omega) * mg0_corr(M, C, xin, e, scale, c) + omega * inv * (b + mg0_offsum_corr(M, C, xin, e, scale, c));
+            xout[c] = xn;
+            if (last) {
+                zout[c] = (double)xn;
+                part = (double)xn * rd;
+            }
+        }
+    }
+    if (last) block_add(part, &S->rho[rhoSlot]);
+}
+
+// b_1(C) = sum over the row children of (r - A0 x0)
+__global__ void k_mg0_restrict(Mg0 M, MgLevel C, const double *__restrict__ r, const float *x, const DeviceScalars *S) {
+    if (S->pcgDone) return;
+    int cc = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cc >= C.n) return;
+    if (C.invD[cc] == 0.0f) { C.b[cc] = 0.0f; return; }
+    int ci = cc % C.I, cj = (cc / C.I) % C.J, ck = cc / C.sk;
+    float s = 0.0f;
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        int i = 2 * ci + (q & 1), j = 2 * cj + ((q >> 1) & 1), k = 2 * ck + (q >> 2);
+        if (i >= M.g.I || j >= M.g.J || k >= M.g.K) continue;
+        int c = i + M.g.sj * j + M.g.sk * k;
+        if (!((M.rowBits[c >> 5] >> (c & 31)) & 1u)) continue;
+        s += (float)r[c] - ((float)M.Adiag[c] * x[c] - mg0_offsum(M, x, c));
+    }
+    C.b[cc] = s;
+}
+
+// ---- hierarchy construction (every solve: the liquid region changes every substep)
+__global__ void k_mg0_build(const int *__restrict__ segCell, const unsigned int *__restrict__ segMask,
+                            const double *__restrict__ Adiag, float *__restrict__ invD, const DeviceScalars *S) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (warp >= S->numSegments) return;
+    if ((segMask[warp] >> lane) & 1u) {
+        int c = segCell[warp] + lane;
+        double d = Adiag[c];
+        invD[c] = (d > 0.0) ? (float)(1.0 / d) : 0.0f;
+    }
+}
+
+// level 1 from level 0
+__global__ void k_mg_coarsen0(Mg0 M, MgLevel C) {
+    int cc = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cc >= C.n) return;
+    int ci = cc % C.I, cj = (cc / C.I) % C.J, ck = cc / C.sk;
+    float d = 0.0f, u = 0.0f, v = 0.0f, w = 0.0f;
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        int qi = q & 1, qj = (q >> 1) & 1, qk = q >> 2;
+        int i = 2 * ci + qi, j = 2 * cj + qj, k = 2 * ck + qk;
+        if (i >= M.g.I || j >= M.g.J || k >= M.g.K) continue;
+        int c = i + M.g.sj * j + M.g.sk * k;
+        if (!((M.rowBits[c >> 5] >> (c & 31)) & 1u)) continue;
+        d += (float)M.Adiag[c];
+        float au = M.fac * M.oU[c], av = M.fac * M.oV[c], aw = M.fac * M.oW[c];
+        if (qi == 0) d -= 2.0f * au; else u += au;
+        if (qj == 0) d -= 2.0f * av; else v += av;
+        if (qk == 0) d -= 2.0f * aw; else w += aw;
+    }
+    C.diag[cc] = d;
+    C.invD[cc] = (d > 0.0f) ? 1.0f / d : 0.0f;
+    C.oU[cc] = u; C.oV[cc] = v; C.oW[cc] = w;
+}
+
+// level l+1 from level l (l >= 1)
+__global__ void k_mg_coarsen(MgLevel F, MgLevel C) {
+    int cc = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cc >= C.n) return;
+    int ci = cc % C.I, cj = (cc / C.I) % C.J, ck = cc / C.sk;
+    float d = 0.0f, u = 0.0f, v = 0.0f, w = 0.0f;
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        int qi = q & 1, qj = (q >> 1) & 1, qk = q >> 2;
+        int i = 2 * ci + qi, j = 2 * cj + qj, k = 2 * ck + qk;
+        if (i >= F.I || j >= F.J || k >= F.K) continue;
+        int c = i + F.sj * j + F.sk * k;
+        d += F.diag[c];
+        float au = F.oU[c], av = F.oV[c], aw = F.oW[c];
+        if (qi == 0) d -= 2.0f * au; else u += au;
+        if (qj == 0) d -= 2.0f * av; else v += av;
+        if (qk == 0) d -= 2.0f * aw; else w += aw;
+    }
+    C.diag[cc] = d;
+    C.invD[cc] = (d > 0.0f) ? 1.0f / d : 0.0f;
+    C.oU[cc] = u; C.oV[cc] = v; C.oW[cc] = w;
+}
+
+// s = z on rows (start of PCG with a preconditioner that produced z in separate passes)
+__global__ void k_pcg_copy_zs(const int *__restrict__ segCell, const unsigned int *__restrict__ segMask,
+                              const double *__restrict__ z, double *__restrict__ s, const DeviceScalars *S) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (warp >= S->numSegments) return;
+    if ((segMask[warp] >> lane) & 1u) {
+        int c = segCell[warp] + lane;
+        s[c] = z[c];
+    }
+}
+
 // ---- 3. velocity update  (_applySolutionToVelocityField, pressuresolver.cpp:842-1047)
 struct ApplyParams {
     PGrid g;
