@@ -200,6 +200,14 @@ int flip_set_preconditioner(flip_ctx *c, int kind) {
     });
 }
 
+int flip_set_multigrid(flip_ctx *c, int sweeps, double damping, double weight, int coarsest) {
+    return guarded(c, [&] {
+        if (sweeps < 1 || sweeps > 8 || !(damping > 0.0 && damping <= 1.0) || !(weight > 0.0) || coarsest < 1)
+            throw ApiError(FLIP_ERR_DOMAIN, "Error: bad multigrid parameters.");
+        c->mgNu = sweeps; c->mgOmega = damping; c->mgScale = weight; c->mgCoarseSweeps = coarsest;
+    });
+}
+
 int flip_load_particles(flip_ctx *c, int n, const float *pos, const float *vel) {
     return guarded(c, [&] {
         if (n < 0) throw ApiError(FLIP_ERR_OUT_OF_RANGE, "negative particle count");

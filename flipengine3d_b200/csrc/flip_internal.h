@@ -87,6 +87,8 @@ struct flip_ctx {
     double pressureTol = 1e-9, pressureAcceptableTol = 1.0;
     int pressureMaxIter = 1000;
     int preconditioner = 1;
+    int mgNu = 2, mgCoarseSweeps = 8;
+    double mgOmega = 0.9, mgScale = 1.8;
     int maxParticlesPerCell = 250;
     double solidBufferWidth = 0.1f;          // float in the reference (fluidsimulation.h:1685)
     double maxExtremeVelocityRemovalPercent = 0.0005;

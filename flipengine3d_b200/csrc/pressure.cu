@@ -16,6 +16,7 @@
 // "acceptable" fallback (pressuresolver.cpp:810-840) are the reference's, in fp64.
 #include <cub/device/device_scan.cuh>
 #include <cstring>
+#include <utility>
 #include "device_math.cuh"
 #include "flip_internal.h"
 
@@ -150,15 +151,18 @@ __global__ void k_build_system(const int *__restrict__ segCell, const unsigned i
 __device__ __forceinline__ double apply_row(const PGrid &g, int c, double factor, const double *__restrict__ Adiag,
                                             const float *__restrict__ AoffU, const float *__restrict__ AoffV,
                                             const float *__restrict__ AoffW, const double *__restrict__ v) {
+    // all 14 loads are issued before any is consumed (rows are interior cells, so every index is in
+    // range); a stale vector entry behind a zero weight is discarded by the select, never multiplied
+    float a0 = AoffW[c - g.sk], a1 = AoffV[c - g.sj], a2 = AoffU[c - 1], a3 = AoffU[c], a4 = AoffV[c], a5 = AoffW[c];
+    double v0 = v[c - g.sk], v1 = v[c - g.sj], v2 = v[c - 1], v3 = v[c + 1], v4 = v[c + g.sj], v5 = v[c + g.sk];
     double acc = Adiag[c] * v[c];
-    float a;
     double off = 0.0;
-    a = AoffW[c - g.sk]; if (a != 0.0f) off += (double)a * v[c - g.sk];
-    a = AoffV[c - g.sj]; if (a != 0.0f) off += (double)a * v[c - g.sj];
-    a = AoffU[c - 1];    if (a != 0.0f) off += (double)a * v[c - 1];
-    a = AoffU[c];        if (a != 0.0f) off += (double)a * v[c + 1];
-    a = AoffV[c];        if (a != 0.0f) off += (double)a * v[c + g.sj];
-    a = AoffW[c];        if (a != 0.0f) off += (double)a * v[c + g.sk];
+    off += (a0 != 0.0f) ? (double)a0 * v0 : 0.0;
+    off += (a1 != 0.0f) ? (double)a1 * v1 : 0.0;
+    off += (a2 != 0.0f) ? (double)a2 * v2 : 0.0;
+    off += (a3 != 0.0f) ? (double)a3 * v3 : 0.0;
+    off += (a4 != 0.0f) ? (double)a4 * v4 : 0.0;
+    off += (a5 != 0.0f) ? (double)a5 * v5 : 0.0;
     return acc - factor * off;
 }
 
@@ -507,13 +511,15 @@ struct Mg0 {
 };
 
 __device__ __forceinline__ float mg0_offsum(const Mg0 &M, const float *x, int c) {
-    float s = 0.0f, a;
-    a = M.oW[c - M.g.sk]; if (a != 0.0f) s += a * x[c - M.g.sk];
-    a = M.oV[c - M.g.sj]; if (a != 0.0f) s += a * x[c - M.g.sj];
-    a = M.oU[c - 1];      if (a != 0.0f) s += a * x[c - 1];
-    a = M.oU[c];          if (a != 0.0f) s += a * x[c + 1];
-    a = M.oV[c];          if (a != 0.0f) s += a * x[c + M.g.sj];
-    a = M.oW[c];          if (a != 0.0f) s += a * x[c + M.g.sk];
+    float a0 = M.oW[c - M.g.sk], a1 = M.oV[c - M.g.sj], a2 = M.oU[c - 1], a3 = M.oU[c], a4 = M.oV[c], a5 = M.oW[c];
+    float x0 = x[c - M.g.sk], x1 = x[c - M.g.sj], x2 = x[c - 1], x3 = x[c + 1], x4 = x[c + M.g.sj], x5 = x[c + M.g.sk];
+    float s = 0.0f;
+    s += (a0 != 0.0f) ? a0 * x0 : 0.0f;
+    s += (a1 != 0.0f) ? a1 * x1 : 0.0f;
+    s += (a2 != 0.0f) ? a2 * x2 : 0.0f;
+    s += (a3 != 0.0f) ? a3 * x3 : 0.0f;
+    s += (a4 != 0.0f) ? a4 * x4 : 0.0f;
+    s += (a5 != 0.0f) ? a5 * x5 : 0.0f;
     return M.fac * s;
 }
 
@@ -524,13 +530,20 @@ __device__ __forceinline__ float mg0_corr(const Mg0 &M, const MgLevel &C, const 
 
 __device__ __forceinline__ float mg0_offsum_corr(const Mg0 &M, const MgLevel &C, const float *x, const float *e,
                                                  float scale, int c) {
-    float s = 0.0f, a;
-    a = M.oW[c - M.g.sk]; if (a != 0.0f) s += a * mg0_corr(M, C, x, e, scale, c - M.g.sk);
-    a = M.oV[c - M.g.sj]; if (a != 0.0f) s += a * mg0_corr(M, C, x, e, scale, c - M.g.sj);
-    a = M.oU[c - 1];      if (a != 0.0f) s += a * mg0_corr(M, C, x, e, scale, c - 1);
-    a = M.oU[c];          if (a != 0.0f) s += a * mg0_corr(M, C, x, e, scale, c + 1);
-    a = M.oV[c];          if (a != 0.0f) s += a * mg0_corr(M, C, x, e, scale, c + M.g.sj);
-    a = M.oW[c];          if (a != 0.0f) s += a * mg0_corr(M, C, x, e, scale, c + M.g.sk);
+    int i = c % M.g.I, j = (c / M.g.I) % M.g.J, k = c / M.g.sk;
+    float a0 = M.oW[c - M.g.sk], a1 = M.oV[c - M.g.sj], a2 = M.oU[c - 1], a3 = M.oU[c], a4 = M.oV[c], a5 = M.oW[c];
+    float x0 = x[c - M.g.sk], x1 = x[c - M.g.sj], x2 = x[c - 1], x3 = x[c + 1], x4 = x[c + M.g.sj], x5 = x[c + M.g.sk];
+    // parents of the six neighbours (rows are interior: i,j,k >= 1 and +1 stays inside the grid)
+    int pi = i >> 1, pj = C.sj * (j >> 1), pk = C.sk * (k >> 1);
+    float e0 = e[pi + pj + C.sk * ((k - 1) >> 1)], e1 = e[pi + C.sj * ((j - 1) >> 1) + pk], e2 = e[((i - 1) >> 1) + pj + pk];
+    float e3 = e[((i + 1) >> 1) + pj + pk], e4 = e[pi + C.sj * ((j + 1) >> 1) + pk], e5 = e[pi + pj + C.sk * ((k + 1) >> 1)];
+    float s = 0.0f;
+    s += (a0 != 0.0f) ? a0 * (x0 + scale * e0) : 0.0f;
+    s += (a1 != 0.0f) ? a1 * (x1 + scale * e1) : 0.0f;
+    s += (a2 != 0.0f) ? a2 * (x2 + scale * e2) : 0.0f;
+    s += (a3 != 0.0f) ? a3 * (x3 + scale * e3) : 0.0f;
+    s += (a4 != 0.0f) ? a4 * (x4 + scale * e4) : 0.0f;
+    s += (a5 != 0.0f) ? a5 * (x5 + scale * e5) : 0.0f;
     return M.fac * s;
 }
 
@@ -737,6 +750,11 @@ struct PressureScratch {
     int *flagAll = nullptr;
     int *posAll = nullptr;
     int nSegAll = 0;
+    // multigrid hierarchy
+    int numLevels = 0;                 // including level 0
+    int firstSmall = 0;                // levels firstSmall..numLevels-1 run in one CTA (0: none)
+    MgLevel lv[MG_MAX_LEVELS];         // lv[0]: only invD, x, x2 are used (dense over cells)
+    float *pool = nullptr;             // one allocation behind all level arrays
 };
 
 void pressure_alloc(flip_ctx *c) {
@@ -768,6 +786,43 @@ void pressure_alloc(flip_ctx *c) {
     FLIP_CUDA_CHECK(cudaMalloc(&ps->flagAll, sizeof(int) * (nSeg + 1)));
     FLIP_CUDA_CHECK(cudaMalloc(&ps->posAll, sizeof(int) * (nSeg + 1)));
     c->mg = ps;
+
+    // multigrid levels: halve (round up) until the grid is at most 2 cells wide
+    {
+        int I = d.I, J = d.J, K = d.K;
+        int L = 0;
+        size_t total = 0;
+        while (L < MG_MAX_LEVELS) {
+            MgLevel &lv = ps->lv[L];
+            lv.I = I; lv.J = J; lv.K = K; lv.sj = I; lv.sk = I * J; lv.n = I * J * K;
+            size_t np = (size_t)lv.n + 64;
+            total += (L == 0) ? 3 * np : 8 * np;
+            L++;
+            if (I <= 2 && J <= 2 && K <= 2) break;
+            I = (I + 1) / 2; J = (J + 1) / 2; K = (K + 1) / 2;
+        }
+        ps->numLevels = L;
+        FLIP_CUDA_CHECK(cudaMalloc(&ps->pool, sizeof(float) * total));
+        FLIP_CUDA_CHECK(cudaMemset(ps->pool, 0, sizeof(float) * total));
+        float *q = ps->pool;
+        ps->firstSmall = 0;
+        for (int l = 0; l < L; l++) {
+            MgLevel &lv = ps->lv[l];
+            size_t np = (size_t)lv.n + 64;
+            lv.diag = lv.oU = lv.oV = lv.oW = lv.b = nullptr;
+            lv.invD = q; q += np;
+            lv.x = q; q += np;
+            lv.x2 = q; q += np;
+            if (l > 0) {
+                lv.diag = q; q += np;
+                lv.oU = q; q += np;
+                lv.oV = q; q += np;
+                lv.oW = q; q += np;
+                lv.b = q; q += np;
+                if (ps->firstSmall == 0 && lv.n <= MG_SMALL) ps->firstSmall = l;
+            }
+        }
+    }
 }
 
 void pressure_free(flip_ctx *c) {
@@ -776,7 +831,7 @@ void pressure_free(flip_ctx *c) {
     cudaFree(c->vx_); cudaFree(c->vr); cudaFree(c->vs); cudaFree(c->vz); cudaFree(c->vb);
     if (c->mg) {
         PressureScratch *ps = (PressureScratch *)c->mg;
-        cudaFree(ps->maskAll); cudaFree(ps->flagAll); cudaFree(ps->posAll);
+        cudaFree(ps->maskAll); cudaFree(ps->flagAll); cudaFree(ps->posAll); cudaFree(ps->pool);
         delete ps;
         c->mg = nullptr;
     }
@@ -844,13 +899,106 @@ void stage_pressure(flip_ctx *c, double dt) {
     pp.g = g;
     pp.factor = bp.factor;
     pp.tolFactor = fmax(c->pressureTol, 1e-30);
-    int jacobi = 1;
+    const bool useMg = (c->preconditioner == 1) && ps->numLevels >= 2;
+    int jacobi = useMg ? 0 : 1;
+    Mg0 m0;
+    MgParams mp;
+    mp.omega = (float)c->mgOmega; mp.scale = (float)c->mgScale; mp.nu = c->mgNu; mp.coarseSweeps = c->mgCoarseSweeps;
+    if (useMg) {
+        m0.g = g; m0.fac = (float)bp.factor; m0.Adiag = c->Adiag;
+        m0.oU = c->AoffU; m0.oV = c->AoffV; m0.oW = c->AoffW;
+        m0.invD = ps->lv[0].invD; m0.rowBits = ps->maskAll;
+        size_t ktB = kt_begin(c);
+        k_mg0_build<<<segBlocks, TPB, 0, st>>>(c->segCell, c->segMask, c->Adiag, ps->lv[0].invD, c->dS); c->launches++;
+        k_mg_coarsen0<<<cdiv(ps->lv[1].n, TPB), TPB, 0, st>>>(m0, ps->lv[1]); c->launches++;
+        for (int l = 1; l + 1 < ps->numLevels; l++) {
+            k_mg_coarsen<<<cdiv(ps->lv[l + 1].n, TPB), TPB, 0, st>>>(ps->lv[l], ps->lv[l + 1]); c->launches++;
+        }
+        kt_end(c, FLIP_KERNEL_PRESSURE_BUILD, ktB);
+    }
+    // one V-cycle: z = M^-1 r, rho[rhoSlot] += z.r
+    auto vcycle = [&](int rhoSlot) {
+        const int L = ps->numLevels;
+        const int fs = ps->firstSmall ? ps->firstSmall : L;      // first level run by the single-CTA kernel
+        const int nu = mp.nu;
+        size_t ktV = kt_begin(c);
+        // ---- down
+        {   // level 0 pre-smoothing, result in cur0
+            float *xa = ps->lv[0].x, *xb = ps->lv[0].x2;
+            for (int sw = 0; sw < nu; sw++) {
+                k_mg0_sweep<<<segBlocks, TPB, 0, st>>>(c->segCell, c->segMask, m0, ps->lv[1], c->vr, xa, nullptr, xb, mp.omega,
+                                                      mp.scale, sw == 0 ? 0 : 1, 0, nullptr, c->dS, 0);
+                c->launches++;
+                std::swap(xa, xb);
+            }
+            // xa holds the result
+            k_mg0_restrict<<<cdiv(ps->lv[1].n, TPB), TPB, 0, st>>>(m0, ps->lv[1], c->vr, xa, c->dS); c->launches++;
+            ps->lv[0].x = xa; ps->lv[0].x2 = xb;
+        }
+        for (int l = 1; l < fs && l < L - 1; l++) {
+            MgLevel &lv = ps->lv[l];
+            float *xa = lv.x, *xb = lv.x2;
+            for (int sw = 0; sw < nu; sw++) {
+                k_mg_sweep<<<cdiv(lv.n, TPB), TPB, 0, st>>>(lv, lv, xa, nullptr, xb, mp.omega, mp.scale, sw == 0 ? 0 : 1, c->dS);
+                c->launches++;
+                std::swap(xa, xb);
+            }
+            lv.x = xa; lv.x2 = xb;
+            k_mg_restrict<<<cdiv(ps->lv[l + 1].n, TPB), TPB, 0, st>>>(lv, ps->lv[l + 1], lv.x, c->dS); c->launches++;
+        }
+        // ---- bottom: small levels in one CTA, or coarsest-level sweeps
+        if (fs < L) {
+            MgSmallArgs A;
+            for (int l = 0; l < L; l++) A.lv[l] = ps->lv[l];
+            A.first = fs; A.last = L - 1; A.p = mp;
+            k_mg_small<<<1, 1024, 0, st>>>(A, c->dS); c->launches++;
+        } else {
+            MgLevel &lv = ps->lv[L - 1];
+            float *xa = lv.x, *xb = lv.x2;
+            for (int sw = 0; sw < mp.coarseSweeps; sw++) {
+                k_mg_sweep<<<cdiv(lv.n, TPB), TPB, 0, st>>>(lv, lv, xa, nullptr, xb, mp.omega, mp.scale, sw == 0 ? 0 : 1, c->dS);
+                c->launches++;
+                std::swap(xa, xb);
+            }
+            lv.x = xa; lv.x2 = xb;
+        }
+        // ---- up
+        int top = (fs < L ? fs : L - 1) - 1;     // highest-numbered level handled by per-level launches on the way up
+        for (int l = top; l >= 1; l--) {
+            MgLevel &lv = ps->lv[l];
+            float *xa = lv.x, *xb = lv.x2;
+            for (int sw = 0; sw < nu; sw++) {
+                k_mg_sweep<<<cdiv(lv.n, TPB), TPB, 0, st>>>(lv, ps->lv[l + 1], xa, ps->lv[l + 1].x, xb, mp.omega, mp.scale,
+                                                          sw == 0 ? 2 : 1, c->dS);
+                c->launches++;
+                std::swap(xa, xb);
+            }
+            lv.x = xa; lv.x2 = xb;
+        }
+        {
+            float *xa = ps->lv[0].x, *xb = ps->lv[0].x2;
+            for (int sw = 0; sw < nu; sw++) {
+                int last = (sw == nu - 1) ? 1 : 0;
+                k_mg0_sweep<<<segBlocks, TPB, 0, st>>>(c->segCell, c->segMask, m0, ps->lv[1], c->vr, xa, ps->lv[1].x, xb, mp.omega,
+                                                      mp.scale, sw == 0 ? 2 : 1, last, c->vz, c->dS, rhoSlot);
+                c->launches++;
+                std::swap(xa, xb);
+            }
+            ps->lv[0].x = xa; ps->lv[0].x2 = xb;
+        }
+        kt_end(c, FLIP_KERNEL_PRECOND, ktV);
+    };
+
     k_pcg_scalars_init<<<1, 1, 0, st>>>(c->dS, pp.tolFactor); c->launches++;
     k_pcg_init<<<segBlocks, TPB, 0, st>>>(c->segCell, c->segMask, pp, c->vb, c->Adiag, c->vr, c->vz, c->vs, c->dS, jacobi);
     c->launches++;
+    if (useMg) {
+        vcycle(0);
+        k_pcg_copy_zs<<<segBlocks, TPB, 0, st>>>(c->segCell, c->segMask, c->vz, c->vs, c->dS); c->launches++;
+    }
 
     int it = 0;
-    const int batch = 16;
+    const int batch = useMg ? 4 : 16;
     bool done = false;
     while (!done && it < c->pressureMaxIter) {
         int stop = it + batch;
@@ -863,9 +1011,11 @@ void stage_pressure(flip_ctx *c, double dt) {
             kt_end(c, FLIP_KERNEL_PCG_SPMV, ktSp);
             k_pcg_update<<<segBlocks, TPB, 0, st>>>(c->segCell, c->segMask, c->Adiag, c->vs, c->vz, c->vx_, c->vr,
                                                     c->dS, it, jacobi);
+            c->launches += 2;
+            if (useMg) vcycle((it + 1) % 3);
             k_pcg_direction<<<segBlocks, TPB, 0, st>>>(c->segCell, c->segMask, c->vz, c->vs, c->dS, it);
             kt_end(c, FLIP_KERNEL_PCG_ITER, ktIt);
-            c->launches += 3;
+            c->launches++;
         }
         scalars_to_host(c);
         done = c->hS->pcgDone != 0;

@@ -105,6 +105,9 @@ int flip_set_pressure_solver(flip_ctx *ctx, double tolerance, double acceptable_
  * 1 = multigrid V-cycle (default). Both are GPU-parallel replacements of the reference's serial
  * MIC(0) (pcgsolver.h:69-221); the stopping rule is the reference's. */
 int flip_set_preconditioner(flip_ctx *ctx, int kind);
+/* Tuning of the multigrid V-cycle: damped-Jacobi sweeps before/after the coarse correction,
+ * damping, weight of the coarse correction, sweeps on the coarsest level. */
+int flip_set_multigrid(flip_ctx *ctx, int sweeps, double damping, double coarse_weight, int coarsest_sweeps);
 
 /* FluidSimulation::loadMarkerParticleData  fluidsimulation.cpp:2488 — float xyz triplets; copied;
  * applied (with the in-domain filter of _loadMarkerParticles :2773) at flip_initialize(). */
@@ -183,7 +186,8 @@ enum {
     FLIP_KERNEL_PCG_ITER = 6,  /* one whole PCG iteration                               */
     FLIP_KERNEL_PRESSURE_BUILD = 7, /* row enumeration + rhs + matrix                   */
     FLIP_KERNEL_PRESSURE_APPLY = 8, /* velocity update                                  */
-    FLIP_NUM_KERNEL_CLASSES = 9
+    FLIP_KERNEL_PRECOND = 9,   /* one preconditioner application (multigrid V-cycle)    */
+    FLIP_NUM_KERNEL_CLASSES = 10
 };
 int flip_enable_kernel_timing(flip_ctx *ctx, int on);
 int flip_reset_kernel_timing(flip_ctx *ctx);
