@@ -13,16 +13,16 @@ static constexpr int TPB = 256;
 // ------------------------------------------------------------------------------------------------
 // allocation
 // ------------------------------------------------------------------------------------------------
+// One allocation per SoA set: six float arrays of `cap` entries back to back (24*cap bytes), so the
+// idle half of the ping-pong pair doubles as the AoS staging area of uploads and downloads.
 static void soa_alloc(ParticleSoA &p, int cap) {
-    FLIP_CUDA_CHECK(cudaMalloc(&p.px, sizeof(float) * cap));
-    FLIP_CUDA_CHECK(cudaMalloc(&p.py, sizeof(float) * cap));
-    FLIP_CUDA_CHECK(cudaMalloc(&p.pz, sizeof(float) * cap));
-    FLIP_CUDA_CHECK(cudaMalloc(&p.vx, sizeof(float) * cap));
-    FLIP_CUDA_CHECK(cudaMalloc(&p.vy, sizeof(float) * cap));
-    FLIP_CUDA_CHECK(cudaMalloc(&p.vz, sizeof(float) * cap));
+    float *blk = nullptr;
+    FLIP_CUDA_CHECK(cudaMalloc(&blk, sizeof(float) * 6ull * cap));
+    p.px = blk; p.py = blk + (size_t)cap; p.pz = blk + 2ull * cap;
+    p.vx = blk + 3ull * cap; p.vy = blk + 4ull * cap; p.vz = blk + 5ull * cap;
 }
 static void soa_free(ParticleSoA &p) {
-    cudaFree(p.px); cudaFree(p.py); cudaFree(p.pz); cudaFree(p.vx); cudaFree(p.vy); cudaFree(p.vz);
+    cudaFree(p.px);
     p = ParticleSoA();
 }
 
@@ -342,13 +342,11 @@ void particles_upload_aos(flip_ctx *c, const float *aos6, int n) {
     particles_alloc(c, n);
     c->np = n;
     if (n > 0) {
-        float *tmp = nullptr;
-        FLIP_CUDA_CHECK(cudaMalloc(&tmp, sizeof(float) * 6ll * n));
+        // host AoS -> idle SoA block (as raw AoS) -> transpose into the live block
+        float *tmp = c->P[1 - c->cur_buf].px;
         FLIP_CUDA_CHECK(cudaMemcpyAsync(tmp, aos6, sizeof(float) * 6ll * n, cudaMemcpyHostToDevice, c->stream));
         k_aos_to_soa<<<cdiv(n, TPB), TPB, 0, c->stream>>>(tmp, n, c->P[c->cur_buf]); c->launches++;
         if (c->trackIds) { k_iota<<<cdiv(n, TPB), TPB, 0, c->stream>>>(c->pid[c->cur_buf], n); c->launches++; }
-        FLIP_CUDA_CHECK(cudaStreamSynchronize(c->stream));
-        cudaFree(tmp);
     }
     particles_sort(c, false, 0.0);
 }
@@ -357,15 +355,12 @@ void particles_upload_split(flip_ctx *c, const float *pos, const float *vel, int
     particles_alloc(c, n);
     c->np = n;
     if (n > 0) {
-        float *tp = nullptr, *tv = nullptr;
-        FLIP_CUDA_CHECK(cudaMalloc(&tp, sizeof(float) * 3ll * n));
-        FLIP_CUDA_CHECK(cudaMalloc(&tv, sizeof(float) * 3ll * n));
+        float *tp = c->P[1 - c->cur_buf].px;
+        float *tv = tp + 3ull * n;
         FLIP_CUDA_CHECK(cudaMemcpyAsync(tp, pos, sizeof(float) * 3ll * n, cudaMemcpyHostToDevice, c->stream));
         FLIP_CUDA_CHECK(cudaMemcpyAsync(tv, vel, sizeof(float) * 3ll * n, cudaMemcpyHostToDevice, c->stream));
         k_split_to_soa<<<cdiv(n, TPB), TPB, 0, c->stream>>>(tp, tv, n, c->P[c->cur_buf]); c->launches++;
         if (c->trackIds) { k_iota<<<cdiv(n, TPB), TPB, 0, c->stream>>>(c->pid[c->cur_buf], n); c->launches++; }
-        FLIP_CUDA_CHECK(cudaStreamSynchronize(c->stream));
-        cudaFree(tp); cudaFree(tv);
     }
     particles_sort(c, false, 0.0);
 }
@@ -373,12 +368,10 @@ void particles_upload_split(flip_ctx *c, const float *pos, const float *vel, int
 void particles_download_aos(flip_ctx *c, float *aos6) {
     int n = c->np;
     if (n == 0) return;
-    float *tmp = nullptr;
-    FLIP_CUDA_CHECK(cudaMalloc(&tmp, sizeof(float) * 6ll * n));
+    float *tmp = c->P[1 - c->cur_buf].px;
     k_soa_to_aos<<<cdiv(n, TPB), TPB, 0, c->stream>>>(c->P[c->cur_buf], n, tmp); c->launches++;
     FLIP_CUDA_CHECK(cudaMemcpyAsync(aos6, tmp, sizeof(float) * 6ll * n, cudaMemcpyDeviceToHost, c->stream));
     FLIP_CUDA_CHECK(cudaStreamSynchronize(c->stream));
-    cudaFree(tmp);
 }
 
 void particles_download_ids(flip_ctx *c, int *ids) {
@@ -390,15 +383,13 @@ void particles_download_ids(flip_ctx *c, int *ids) {
 void particles_download_component(flip_ctx *c, float *xyz, int which) {
     int n = c->np;
     if (n == 0) return;
-    float *tmp = nullptr;
-    FLIP_CUDA_CHECK(cudaMalloc(&tmp, sizeof(float) * 3ll * n));
+    float *tmp = c->P[1 - c->cur_buf].px;
     const ParticleSoA &p = c->P[c->cur_buf];
     if (which == 0) k_soa_to_xyz<<<cdiv(n, TPB), TPB, 0, c->stream>>>(p.px, p.py, p.pz, n, tmp);
     else k_soa_to_xyz<<<cdiv(n, TPB), TPB, 0, c->stream>>>(p.vx, p.vy, p.vz, n, tmp);
     c->launches++;
     FLIP_CUDA_CHECK(cudaMemcpyAsync(xyz, tmp, sizeof(float) * 3ll * n, cudaMemcpyDeviceToHost, c->stream));
     FLIP_CUDA_CHECK(cudaStreamSynchronize(c->stream));
-    cudaFree(tmp);
 }
 
 // ------------------------------------------------------------------------------------------------
