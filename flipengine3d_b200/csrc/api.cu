@@ -208,6 +208,10 @@ int flip_set_multigrid(flip_ctx *c, int sweeps, double damping, double weight, i
     });
 }
 
+int flip_set_solver_mode(flip_ctx *c, int persistent) {
+    return guarded(c, [&] { c->pcgPersistent = persistent ? 1 : 0; });
+}
+
 int flip_load_particles(flip_ctx *c, int n, const float *pos, const float *vel) {
     return guarded(c, [&] {
         if (n < 0) throw ApiError(FLIP_ERR_OUT_OF_RANGE, "negative particle count");

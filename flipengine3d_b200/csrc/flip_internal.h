@@ -88,6 +88,7 @@ struct flip_ctx {
     int pressureMaxIter = 1000;
     int preconditioner = 1;
     int mgNu = 2, mgCoarseSweeps = 8;
+    int pcgPersistent = 0;   // measured slower than the multi-launch solver at 2 M rows (occupancy-limited), kept selectable
     double mgOmega = 0.9, mgScale = 1.8;
     int maxParticlesPerCell = 250;
     double solidBufferWidth = 0.1f;          // float in the reference (fluidsimulation.h:1685)

@@ -14,11 +14,14 @@
 // GPU-parallel one (Jacobi, or an aggregation multigrid V-cycle in fp32).  The Krylov vectors,
 // the residual test (||r||_inf <= tol*||b||_inf, pcgsolver.h:262-288), the iteration cap and the
 // "acceptable" fallback (pressuresolver.cpp:810-840) are the reference's, in fp64.
+#include <cooperative_groups.h>
 #include <cub/device/device_scan.cuh>
 #include <cstring>
 #include <utility>
 #include "device_math.cuh"
 #include "flip_internal.h"
+
+namespace cg = cooperative_groups;
 
 namespace flip {
 
@@ -667,6 +670,306 @@ __global__ void k_pcg_copy_zs(const int *__restrict__ segCell, const unsigned in
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// The whole PCG solve as ONE persistent cooperative kernel.
+//
+// At n ~ 2 M rows every pass of the solver is a 10-30 us kernel, so the multi-launch formulation
+// above is bound by launch gaps, cold L1 and host polling rather than by HBM.  Here one grid that
+// fills the machine (148 SMs x resident CTAs) walks the same phases with grid-wide barriers in
+// between: the iteration loop, alpha/beta, the convergence test (||r||_inf <= tol, tested right
+// after the residual update as pcgsolver.h:286-288 does, i.e. before the next preconditioner
+// application) and the multigrid V-cycle all live on the device; the host launches once and reads
+// the scalars back once.  Levels small enough for one CTA are run by block 0 between two barriers.
+// The arithmetic per row is the same as in the multi-launch kernels (same device functions).
+// ------------------------------------------------------------------------------------------------
+struct PcgDev {
+    const int *segCell;
+    const unsigned int *segMask;
+    PGrid g;
+    double factor;
+    const double *Adiag;
+    const float *oU, *oV, *oW;
+    const double *b;
+    double *x, *r, *s, *z;
+    Mg0 m0;
+    MgLevel lv[MG_MAX_LEVELS];
+    int numLevels, firstSmall;
+    MgParams mp;
+    int useMg, maxIter;
+    DeviceScalars *S;
+};
+
+__device__ __forceinline__ double ldcg_d(const double *p) { return __ldcg(p); }
+
+// dense-level sweep / restrict over a grid-stride range
+__device__ __forceinline__ void pg_sweep_level(const MgLevel &L, const MgLevel &C, const float *xin, const float *e,
+                                               float *xout, float omega, float scale, int mode, int gtid, int gthreads) {
+    for (int c = gtid; c < L.n; c += gthreads) {
+        int i = c % L.I, j = (c / L.I) % L.J, k = c / L.sk;
+        xout[c] = mg_sweep_cell(L, C, xin, e, omega, scale, mode, c, i, j, k);
+    }
+}
+__device__ __forceinline__ void pg_restrict_level(const MgLevel &F, const MgLevel &C, const float *x, int gtid, int gthreads) {
+    for (int c = gtid; c < C.n; c += gthreads) {
+        if (C.invD[c] == 0.0f) { C.b[c] = 0.0f; continue; }
+        int i = c % C.I, j = (c / C.I) % C.J, k = c / C.sk;
+        C.b[c] = mg_restrict_cell(F, x, i, j, k);
+    }
+}
+
+__global__ void __launch_bounds__(TPB) k_pcg_persistent(PcgDev P) {
+    cg::grid_group grid = cg::this_grid();
+    DeviceScalars *S = P.S;
+    const int lane = threadIdx.x & 31;
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int gthreads = gridDim.x * blockDim.x;
+    const int gwarp = gtid >> 5, nwarps = gthreads >> 5;
+    const int nseg = S->numSegments;
+    const float omega = P.mp.omega, scale = P.mp.scale;
+    const int nu = P.mp.nu;
+    const int L = P.numLevels;
+    const int fs = P.firstSmall ? P.firstSmall : L;
+    float *x0a = P.lv[0].x, *x0b = P.lv[0].x2;
+
+    // ---- one V-cycle on r; the level-0 pre-sweep from the zero guess has already been written to x0a.
+    // Leaves z and accumulates rho[rhoSlot].  Every path through here is grid-uniform.
+    auto vcycle_after_first_sweep = [&](int rhoSlot) {
+        float *xa = x0a, *xb = x0b;
+        for (int sw = 1; sw < nu; sw++) {
+            for (int seg = gwarp; seg < nseg; seg += nwarps) {
+                if ((P.segMask[seg] >> lane) & 1u) {
+                    int c = P.segCell[seg] + lane;
+                    float inv = P.m0.invD[c];
+                    float bb = (float)P.r[c];
+                    xb[c] = (inv == 0.0f) ? 0.0f : (1.0f - omega) * xa[c] + omega * inv * (bb + mg0_offsum(P.m0, xa, c));
+                }
+            }
+            grid.sync();
+            float *t = xa; xa = xb; xb = t;
+        }
+        // restrict level 0 -> 1
+        {
+            const MgLevel &C = P.lv[1];
+            for (int cc = gtid; cc < C.n; cc += gthreads) {
+                if (C.invD[cc] == 0.0f) { C.b[cc] = 0.0f; continue; }
+                int ci = cc % C.I, cj = (cc / C.I) % C.J, ck = cc / C.sk;
+                float acc = 0.0f;
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    int i = 2 * ci + (q & 1), j = 2 * cj + ((q >> 1) & 1), k = 2 * ck + (q >> 2);
+                    if (i >= P.g.I || j >= P.g.J || k >= P.g.K) continue;
+                    int c = i + P.g.sj * j + P.g.sk * k;
+                    if (!((P.m0.rowBits[c >> 5] >> (c & 31)) & 1u)) continue;
+                    acc += (float)P.r[c] - ((float)P.Adiag[c] * xa[c] - mg0_offsum(P.m0, xa, c));
+                }
+                C.b[cc] = acc;
+            }
+        }
+        grid.sync();
+        // down through the big coarse levels
+        float *lx[MG_MAX_LEVELS];
+        for (int l = 1; l < fs && l < L - 1; l++) {
+            const MgLevel &Lv = P.lv[l];
+            float *ya = Lv.x, *yb = Lv.x2;
+            for (int sw = 0; sw < nu; sw++) {
+                pg_sweep_level(Lv, Lv, ya, nullptr, yb, omega, scale, sw == 0 ? 0 : 1, gtid, gthreads);
+                grid.sync();
+                float *t = ya; ya = yb; yb = t;
+            }
+            lx[l] = ya;
+            pg_restrict_level(Lv, P.lv[l + 1], ya, gtid, gthreads);
+            grid.sync();
+        }
+        // small levels: block 0 alone, CTA barriers only
+        if (fs < L) {
+            if (blockIdx.x == 0) {
+                const int tid = threadIdx.x, nt = blockDim.x;
+                for (int l = fs; l <= L - 1; l++) {
+                    const MgLevel &Lv = P.lv[l];
+                    int sweeps = (l == L - 1) ? P.mp.coarseSweeps : nu;
+                    float *ya = Lv.x, *yb = Lv.x2;
+                    for (int sw = 0; sw < sweeps; sw++) {
+                        pg_sweep_level(Lv, Lv, ya, nullptr, yb, omega, scale, sw == 0 ? 0 : 1, tid, nt);
+                        __syncthreads();
+                        float *t = ya; ya = yb; yb = t;
+                    }
+                    lx[l] = ya;
+                    if (l < L - 1) {
+                        pg_restrict_level(Lv, P.lv[l + 1], ya, tid, nt);
+                        __syncthreads();
+                    }
+                }
+                for (int l = L - 2; l >= fs; l--) {
+                    const MgLevel &Lv = P.lv[l];
+                    float *ya = lx[l], *yb = (ya == Lv.x) ? Lv.x2 : Lv.x;
+                    for (int sw = 0; sw < nu; sw++) {
+                        pg_sweep_level(Lv, P.lv[l + 1], ya, lx[l + 1], yb, omega, scale, sw == 0 ? 2 : 1, tid, nt);
+                        __syncthreads();
+                        float *t = ya; ya = yb; yb = t;
+                    }
+                    lx[l] = ya;
+                }
+                // publish where the result of level fs sits: always copy into Lv.x so that every block agrees
+                const MgLevel &Lf = P.lv[fs];
+                if (lx[fs] != Lf.x) {
+                    for (int c = tid; c < Lf.n; c += nt) Lf.x[c] = lx[fs][c];
+                }
+            }
+            lx[fs] = P.lv[fs].x;
+            grid.sync();
+        } else {
+            const MgLevel &Lv = P.lv[L - 1];
+            float *ya = Lv.x, *yb = Lv.x2;
+            for (int sw = 0; sw < P.mp.coarseSweeps; sw++) {
+                pg_sweep_level(Lv, Lv, ya, nullptr, yb, omega, scale, sw == 0 ? 0 : 1, gtid, gthreads);
+                grid.sync();
+                float *t = ya; ya = yb; yb = t;
+            }
+            lx[L - 1] = ya;
+        }
+        // up through the big coarse levels
+        int top = (fs < L ? fs : L - 1) - 1;
+        for (int l = top; l >= 1; l--) {
+            const MgLevel &Lv = P.lv[l];
+            float *ya = lx[l], *yb = (ya == Lv.x) ? Lv.x2 : Lv.x;
+            for (int sw = 0; sw < nu; sw++) {
+                pg_sweep_level(Lv, P.lv[l + 1], ya, lx[l + 1], yb, omega, scale, sw == 0 ? 2 : 1, gtid, gthreads);
+                grid.sync();
+                float *t = ya; ya = yb; yb = t;
+            }
+            lx[l] = ya;
+        }
+        // level 0 post-smoothing; the last sweep writes z and accumulates rho
+        const MgLevel &C1 = P.lv[1];
+        const float *e1 = lx[1];
+        double part = 0.0;
+        for (int sw = 0; sw < nu; sw++) {
+            const bool last = (sw == nu - 1);
+            for (int seg = gwarp; seg < nseg; seg += nwarps) {
+                if ((P.segMask[seg] >> lane) & 1u) {
+                    int c = P.segCell[seg] + lane;
+                    float inv = P.m0.invD[c];
+                    double rd = P.r[c];
+                    float bb = (float)rd;
+                    float xn;
+                    if (inv == 0.0f) xn = 0.0f;
+                    else if (sw == 0) xn = (1.0f - omega) * mg0_corr(P.m0, C1, xa, e1, scale, c) + omega * inv * (bb + mg0_offsum_corr(P.m0, C1, xa, e1, scale, c));
+                    else xn = (1.0f - omega) * xa[c] + omega * inv * (bb + mg0_offsum(P.m0, xa, c));
+                    xb[c] = xn;
+                    if (last) { P.z[c] = (double)xn; part += (double)xn * rd; }
+                }
+            }
+            if (last) block_add(part, &S->rho[rhoSlot]);
+            grid.sync();
+            float *t = xa; xa = xb; xb = t;
+        }
+        x0a = xa; x0b = xb;
+    };
+
+    // ---- prologue: r = b, z = M^-1 r, s = z, rho[0] = z.r      (pcgsolver.h:258-276)
+    {
+        double part = 0.0;
+        for (int seg = gwarp; seg < nseg; seg += nwarps) {
+            if ((P.segMask[seg] >> lane) & 1u) {
+                int c = P.segCell[seg] + lane;
+                double rv = P.b[c];
+                P.r[c] = rv;
+                if (P.useMg) {
+                    x0a[c] = omega * P.m0.invD[c] * (float)rv;
+                } else {
+                    double d = P.Adiag[c];
+                    double zv = (d != 0.0) ? rv / d : 0.0;
+                    P.z[c] = zv;
+                    P.s[c] = zv;
+                    part += zv * rv;
+                }
+            }
+        }
+        if (!P.useMg) block_add(part, &S->rho[0]);
+        grid.sync();
+        if (P.useMg) {
+            vcycle_after_first_sweep(0);
+            for (int seg = gwarp; seg < nseg; seg += nwarps) {
+                if ((P.segMask[seg] >> lane) & 1u) {
+                    int c = P.segCell[seg] + lane;
+                    P.s[c] = P.z[c];
+                }
+            }
+            grid.sync();
+        }
+    }
+
+    const double tol = S->pcgTol;
+    int it = 0;
+    int done = 0;
+    double rmax = S->pcgError;
+    for (; it < P.maxIter; it++) {
+        const int sl = it % 3, sn = (it + 1) % 3, sp = (it + 2) % 3;
+        // ---- z = A s, dotSZ = s.z
+        {
+            double part = 0.0;
+            for (int seg = gwarp; seg < nseg; seg += nwarps) {
+                if ((P.segMask[seg] >> lane) & 1u) {
+                    int c = P.segCell[seg] + lane;
+                    double zv = apply_row(P.g, c, P.factor, P.Adiag, P.oU, P.oV, P.oW, P.s);
+                    P.z[c] = zv;
+                    part += P.s[c] * zv;
+                }
+            }
+            block_add(part, &S->dotSZ[sl]);
+        }
+        grid.sync();
+        // ---- x += alpha s, r -= alpha z, ||r||_inf; first pre-sweep of the V-cycle (or Jacobi z, rho)
+        {
+            const double alpha = ldcg_d(&S->rho[sl]) / ldcg_d(&S->dotSZ[sl]);
+            double rabs = 0.0, part = 0.0;
+            for (int seg = gwarp; seg < nseg; seg += nwarps) {
+                if ((P.segMask[seg] >> lane) & 1u) {
+                    int c = P.segCell[seg] + lane;
+                    P.x[c] += alpha * P.s[c];
+                    double rv = P.r[c] - alpha * P.z[c];
+                    P.r[c] = rv;
+                    rabs = fmax(rabs, fabs(rv));
+                    if (P.useMg) {
+                        x0a[c] = omega * P.m0.invD[c] * (float)rv;
+                    } else {
+                        double d = P.Adiag[c];
+                        double zv = (d != 0.0) ? rv / d : 0.0;
+                        P.z[c] = zv;
+                        part += zv * rv;
+                    }
+                }
+            }
+            block_max(rabs, &S->rMaxBits[sl]);
+            if (!P.useMg) block_add(part, &S->rho[sn]);
+        }
+        grid.sync();
+        rmax = __longlong_as_double((long long)__ldcg(&S->rMaxBits[sl]));
+        if (rmax <= tol) { done = 1; it++; break; }
+        if (P.useMg) vcycle_after_first_sweep(sn);
+        // ---- beta, s = z + beta s
+        {
+            const double rho = ldcg_d(&S->rho[sl]), rhoNew = ldcg_d(&S->rho[sn]);
+            if (rhoNew == 0.0 || rhoNew != rhoNew) { done = 3; it++; break; }
+            const double beta = rhoNew / rho;
+            for (int seg = gwarp; seg < nseg; seg += nwarps) {
+                if ((P.segMask[seg] >> lane) & 1u) {
+                    int c = P.segCell[seg] + lane;
+                    P.s[c] = P.z[c] + beta * P.s[c];
+                }
+            }
+            if (gtid == 0) { S->dotSZ[sn] = 0.0; S->rMaxBits[sn] = 0ull; S->rho[sp] = 0.0; }
+        }
+        grid.sync();
+    }
+    if (gtid == 0) {
+        S->pcgIterations = it;
+        S->pcgError = rmax;
+        S->pcgDone = done;
+    }
+}
+
 // ---- 3. velocity update  (_applySolutionToVelocityField, pressuresolver.cpp:842-1047)
 struct ApplyParams {
     PGrid g;
@@ -755,6 +1058,7 @@ struct PressureScratch {
     int firstSmall = 0;                // levels firstSmall..numLevels-1 run in one CTA (0: none)
     MgLevel lv[MG_MAX_LEVELS];         // lv[0]: only invD, x, x2 are used (dense over cells)
     float *pool = nullptr;             // one allocation behind all level arrays
+    int coopBlocks = 0;                // grid of the persistent solver (SMs x resident CTAs)
 };
 
 void pressure_alloc(flip_ctx *c) {
@@ -990,6 +1294,30 @@ void stage_pressure(flip_ctx *c, double dt) {
     };
 
     k_pcg_scalars_init<<<1, 1, 0, st>>>(c->dS, pp.tolFactor); c->launches++;
+    if (c->pcgPersistent) {
+        PcgDev P;
+        P.segCell = c->segCell; P.segMask = c->segMask; P.g = g; P.factor = pp.factor;
+        P.Adiag = c->Adiag; P.oU = c->AoffU; P.oV = c->AoffV; P.oW = c->AoffW;
+        P.b = c->vb; P.x = c->vx_; P.r = c->vr; P.s = c->vs; P.z = c->vz;
+        P.m0 = m0;
+        if (!useMg) { P.m0.g = g; P.m0.fac = 0.f; P.m0.Adiag = c->Adiag; P.m0.oU = c->AoffU; P.m0.oV = c->AoffV; P.m0.oW = c->AoffW; P.m0.invD = ps->lv[0].invD; P.m0.rowBits = ps->maskAll; }
+        for (int l = 0; l < MG_MAX_LEVELS; l++) P.lv[l] = ps->lv[l < ps->numLevels ? l : 0];
+        P.numLevels = ps->numLevels; P.firstSmall = ps->firstSmall; P.mp = mp;
+        P.useMg = useMg ? 1 : 0; P.maxIter = c->pressureMaxIter; P.S = c->dS;
+        if (ps->coopBlocks == 0) {
+            int perSm = 0, sms = 0;
+            FLIP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_pcg_persistent, TPB, 0));
+            FLIP_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+            if (perSm < 1) throw CudaError("k_pcg_persistent does not fit on an SM");
+            ps->coopBlocks = perSm * sms;
+        }
+        void *args[] = {&P};
+        size_t ktS = kt_begin(c);
+        FLIP_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)k_pcg_persistent, dim3(ps->coopBlocks), dim3(TPB), args, 0, st));
+        kt_end(c, FLIP_KERNEL_PCG_SOLVE, ktS);
+        c->launches++;
+        scalars_to_host(c);
+    } else {
     k_pcg_init<<<segBlocks, TPB, 0, st>>>(c->segCell, c->segMask, pp, c->vb, c->Adiag, c->vr, c->vz, c->vs, c->dS, jacobi);
     c->launches++;
     if (useMg) {
@@ -1020,6 +1348,7 @@ void stage_pressure(flip_ctx *c, double dt) {
         scalars_to_host(c);
         done = c->hS->pcgDone != 0;
     }
+    }   // multi-launch path
     FLIP_CUDA_CHECK(cudaGetLastError());
     c->cur.pcg_iterations = c->hS->pcgIterations;
     c->cur.pcg_error = c->hS->pcgError;

@@ -19,7 +19,7 @@ ARRAY_ID = dict(U=0, V=1, W=2, validU=3, validV=4, validW=5, liquid_phi=6, solid
                 near_solid=15, pressure=16)
 
 KERNEL_CLASSES = ("sdf_p2g", "g2p", "advance", "sort", "extrapolate", "pcg_spmv", "pcg_iter", "pressure_build",
-                  "pressure_apply", "precond")
+                  "pressure_apply", "precond", "pcg_solve")
 
 FLIP_OK, FLIP_ERR_RUNTIME, FLIP_ERR_DOMAIN, FLIP_ERR_OUT_OF_RANGE, FLIP_ERR_CUDA, FLIP_ERR_UNSUPPORTED = range(6)
 
@@ -72,6 +72,7 @@ def load_library():
     L.flip_set_pressure_solver.argtypes = [vp, cd, cd, ci]
     L.flip_set_preconditioner.argtypes = [vp, ci]
     L.flip_set_multigrid.argtypes = [vp, ci, cd, cd, ci]
+    L.flip_set_solver_mode.argtypes = [vp, ci]
     L.flip_load_particles.argtypes = [vp, ci, vp, vp]
     L.flip_add_fluid_box.argtypes = [vp, C.POINTER(cd), C.POINTER(cd), C.POINTER(cd)]
     L.flip_add_marker_particle.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
@@ -172,6 +173,9 @@ class FluidSimulation:
 
     def setMultigrid(self, sweeps=2, damping=0.8, coarse_weight=1.8, coarsest_sweeps=8):
         self._check(self.L.flip_set_multigrid(self.h, sweeps, damping, coarse_weight, coarsest_sweeps))
+
+    def setSolverMode(self, persistent=True):
+        self._check(self.L.flip_set_solver_mode(self.h, 1 if persistent else 0))
 
     def setSurfaceSubdivisionLevel(self, n):
         """Accepted and ignored: surface reconstruction is outside the hot path."""

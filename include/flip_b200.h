@@ -108,6 +108,9 @@ int flip_set_preconditioner(flip_ctx *ctx, int kind);
 /* Tuning of the multigrid V-cycle: damped-Jacobi sweeps before/after the coarse correction,
  * damping, weight of the coarse correction, sweeps on the coarsest level. */
 int flip_set_multigrid(flip_ctx *ctx, int sweeps, double damping, double coarse_weight, int coarsest_sweeps);
+/* 1: the PCG solve runs as one persistent cooperative kernel (device-side iteration loop,
+ * grid-wide barriers); 0 (default): one launch per solver pass, host polls the convergence flag. Same arithmetic. */
+int flip_set_solver_mode(flip_ctx *ctx, int persistent);
 
 /* FluidSimulation::loadMarkerParticleData  fluidsimulation.cpp:2488 — float xyz triplets; copied;
  * applied (with the in-domain filter of _loadMarkerParticles :2773) at flip_initialize(). */
@@ -186,8 +189,9 @@ enum {
     FLIP_KERNEL_PCG_ITER = 6,  /* one whole PCG iteration                               */
     FLIP_KERNEL_PRESSURE_BUILD = 7, /* row enumeration + rhs + matrix                   */
     FLIP_KERNEL_PRESSURE_APPLY = 8, /* velocity update                                  */
-    FLIP_KERNEL_PRECOND = 9,   /* one preconditioner application (multigrid V-cycle)    */
-    FLIP_NUM_KERNEL_CLASSES = 10
+    FLIP_KERNEL_PRECOND = 9,   /* one preconditioner application (multigrid V-cycle), multi-launch solver only */
+    FLIP_KERNEL_PCG_SOLVE = 10, /* the whole PCG solve as one persistent cooperative kernel */
+    FLIP_NUM_KERNEL_CLASSES = 11
 };
 int flip_enable_kernel_timing(flip_ctx *ctx, int on);
 int flip_reset_kernel_timing(flip_ctx *ctx);

@@ -240,6 +240,31 @@ def test_update_equals_stagewise():
     assert np.array_equal(pa, pb)
 
 
+@pytest.mark.parametrize("prec", ["jacobi", "multigrid"])
+def test_solver_modes_agree(prec):
+    """The persistent cooperative solver and the multi-launch solver are the same algorithm: same
+    iteration counts (up to the order of the fp64 atomics in the dot products) and the same answer."""
+    sc = scenes.dam_break(40)
+    res = []
+    for persistent in (True, False):
+        s = fe.FluidSimulation(40, 40, 40, sc["dx"])
+        s.addBodyForce(0, -25, 0)
+        s.setPreconditioner(prec)
+        s.setSolverMode(persistent)
+        s.loadMarkerParticleData(fe.MarkerParticleData(sc["pos"], sc["vel"]))
+        s.initialize()
+        for f in range(3):
+            s.update(1.0 / 30.0)
+        st = s.substep_stats()[-1]
+        assert st["pcg_converged"] == 1 and st["pcg_error"] <= 1e-9 * st["rhs_max"]
+        res.append((st, s.getVelocityField()))
+    (sa, fa), (sb, fb) = res
+    assert sa["pressure_rows"] == sb["pressure_rows"]
+    assert abs(sa["pcg_iterations"] - sb["pcg_iterations"]) <= 2
+    for a, b in zip(fa, fb):
+        assert pc.rel_l2(a, b) <= 1e-5
+
+
 def test_run_to_run_determinism():
     sc = scenes.dam_break(32)
     outs = []
