@@ -69,21 +69,88 @@ static void dev_alloc(T *&p, size_t n, bool zero = true) {
     if (zero) FLIP_CUDA_CHECK(cudaMemset(p, 0, sizeof(T) * (n + 64)));
 }
 
+static void free_grids(flip_ctx *c);
+
 static void free_all(flip_ctx *c) {
     cudaSetDevice(c->device);
     particles_free(c);
-    pressure_free(c);
-    cudaFree(c->cellCount); cudaFree(c->cellStart); cudaFree(c->cellStartA); cudaFree(c->scanTemp);
-    cudaFree(c->U); cudaFree(c->V); cudaFree(c->W); cudaFree(c->sU); cudaFree(c->sV); cudaFree(c->sW);
-    cudaFree(c->validU); cudaFree(c->validV); cudaFree(c->validW); cudaFree(c->status);
-    cudaFree(c->frontier[0]); cudaFree(c->frontier[1]);
-    cudaFree(c->phiL); cudaFree(c->phiS); cudaFree(c->wU); cudaFree(c->wV); cudaFree(c->wW);
+    free_grids(c);
+    cudaFree(c->scanTemp);
     cudaFree(c->nearSolid); cudaFree(c->pressure);
     cudaFree(c->dS);
+    cudaFree(c->sendBuf[0]); cudaFree(c->sendBuf[1]);
+    comm_destroy(c->comm); c->comm = nullptr;
     if (c->hS) cudaFreeHost(c->hS);
     if (c->eventsCreated) for (auto &e : c->evStage) cudaEventDestroy(e);
     for (auto &e : c->ktPool) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
+}
+
+// Local grid of this context: Klocal planes starting at global plane kOff, of which [kOwn0,kOwn1) are owned.
+static void set_geometry(flip_ctx *c, int I, int J, int Klocal, double dx, int kOff, int Kg, int kOwn0, int kOwn1) {
+    Dims &d = c->d;
+    d.I = I; d.J = J; d.K = Klocal; d.dx = dx;
+    d.kOff = kOff; d.Kg = Kg; d.kOwn0 = kOwn0; d.kOwn1 = kOwn1;
+    d.nU = (I + 1) * J * Klocal;
+    d.nV = I * (J + 1) * Klocal;
+    d.nW = I * J * (Klocal + 1);
+    d.nC = I * J * Klocal;
+    d.nN = (I + 1) * (J + 1) * (Klocal + 1);
+}
+
+static void free_grids(flip_ctx *c) {
+    pressure_free(c);
+    cudaFree(c->cellCount); cudaFree(c->cellStart); cudaFree(c->cellStartA);
+    cudaFree(c->U); cudaFree(c->V); cudaFree(c->W); cudaFree(c->sU); cudaFree(c->sV); cudaFree(c->sW);
+    cudaFree(c->validU); cudaFree(c->validV); cudaFree(c->validW); cudaFree(c->status);
+    cudaFree(c->frontier[0]); cudaFree(c->frontier[1]);
+    cudaFree(c->phiL); cudaFree(c->phiS); cudaFree(c->wU); cudaFree(c->wV); cudaFree(c->wW);
+    c->cellCount = c->cellStart = c->cellStartA = nullptr;
+    c->U = c->V = c->W = c->sU = c->sV = c->sW = nullptr;
+    c->validU = c->validV = c->validW = c->status = nullptr;
+    c->frontier[0] = c->frontier[1] = nullptr;
+    c->phiL = c->phiS = c->wU = c->wV = c->wW = nullptr;
+}
+
+static void allocate_grids(flip_ctx *c) {
+    const Dims &d = c->d;
+    dev_alloc(c->U, d.nU); dev_alloc(c->V, d.nV); dev_alloc(c->W, d.nW);
+    dev_alloc(c->sU, d.nU); dev_alloc(c->sV, d.nV); dev_alloc(c->sW, d.nW);
+    dev_alloc(c->validU, d.nU); dev_alloc(c->validV, d.nV); dev_alloc(c->validW, d.nW);
+    size_t nmax = std::max(d.nU, std::max(d.nV, d.nW));
+    dev_alloc(c->status, nmax);
+    dev_alloc(c->frontier[0], nmax); dev_alloc(c->frontier[1], nmax);
+    dev_alloc(c->phiL, d.nC); dev_alloc(c->phiS, d.nN);
+    dev_alloc(c->wU, d.nU); dev_alloc(c->wV, d.nV); dev_alloc(c->wW, d.nW);
+    dev_alloc(c->cellCount, (size_t)d.nC + 1); dev_alloc(c->cellStart, (size_t)d.nC + 1);
+    dev_alloc(c->cellStartA, (size_t)d.nC + 1);
+    pressure_alloc(c);
+    // phi_liquid starts at the "no particles" value 3dx (particlelevelset.cpp:295-301)
+    std::vector<float> init((size_t)d.nC, (float)(3.0 * d.dx));
+    FLIP_CUDA_CHECK(cudaMemcpy(c->phiL, init.data(), sizeof(float) * d.nC, cudaMemcpyHostToDevice));
+}
+
+// Static inputs.  The solid SDF handed in (or built) is GLOBAL; a z-slab keeps its planes only.
+static void upload_static_inputs(flip_ctx *c) {
+    const Dims &d = c->d;
+    Dims gd = d;   // global geometry
+    gd.K = d.Kg; gd.kOff = 0;
+    gd.nN = (d.I + 1) * (d.J + 1) * (d.Kg + 1);
+    gd.nC = d.I * d.J * d.Kg;
+    if (!c->userSolidPhi) build_box_solid_sdf(gd, c->hostSolidPhi);
+    std::vector<unsigned char> ns;
+    build_near_solid(gd, c->hostSolidPhi, c->nearSolidFactor, c->solidExactBand, c->CFL, ns, c->nsI, c->nsJ, c->nsK);
+    const size_t nodePlane = (size_t)(d.I + 1) * (d.J + 1);
+    std::vector<float> local(c->hostSolidPhi.begin() + nodePlane * d.kOff, c->hostSolidPhi.begin() + nodePlane * (d.kOff + d.K + 1));
+    std::vector<float> wU, wV, wW, wC;
+    build_weights(d, local, wU, wV, wW, wC);
+    FLIP_CUDA_CHECK(cudaMemcpy(c->phiS, local.data(), sizeof(float) * d.nN, cudaMemcpyHostToDevice));
+    FLIP_CUDA_CHECK(cudaMemcpy(c->wU, wU.data(), sizeof(float) * d.nU, cudaMemcpyHostToDevice));
+    FLIP_CUDA_CHECK(cudaMemcpy(c->wV, wV.data(), sizeof(float) * d.nV, cudaMemcpyHostToDevice));
+    FLIP_CUDA_CHECK(cudaMemcpy(c->wW, wW.data(), sizeof(float) * d.nW, cudaMemcpyHostToDevice));
+    cudaFree(c->nearSolid); c->nearSolid = nullptr;
+    dev_alloc(c->nearSolid, ns.size());
+    FLIP_CUDA_CHECK(cudaMemcpy(c->nearSolid, ns.data(), ns.size(), cudaMemcpyHostToDevice));
 }
 
 extern "C" {
@@ -113,34 +180,16 @@ int flip_create(flip_ctx **out, int isize, int jsize, int ksize, double dx, int 
                             "): libflip_b200 has no CPU fallback");
         if (device < 0 || device >= ndev) throw ApiError(FLIP_ERR_OUT_OF_RANGE, "bad CUDA device ordinal");
         FLIP_CUDA_CHECK(cudaSetDevice(device));
-        Dims &d = c->d;
-        d.I = isize; d.J = jsize; d.K = ksize; d.dx = dx;
-        d.nU = (isize + 1) * jsize * ksize;
-        d.nV = isize * (jsize + 1) * ksize;
-        d.nW = isize * jsize * (ksize + 1);
-        d.nC = isize * jsize * ksize;
-        d.nN = (isize + 1) * (jsize + 1) * (ksize + 1);
+        c->KgCfg = ksize;
+        set_geometry(c, isize, jsize, ksize, dx, 0, ksize, 0, ksize);
         c->liquidRadius = 0.5 * 1.0 * dx * sqrt(3.0);   // _initializeParticleRadii fluidsimulation.cpp:2649
         FLIP_CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         for (auto &e2 : c->evStage) FLIP_CUDA_CHECK(cudaEventCreate(&e2));
         c->eventsCreated = true;
-        dev_alloc(c->U, d.nU); dev_alloc(c->V, d.nV); dev_alloc(c->W, d.nW);
-        dev_alloc(c->sU, d.nU); dev_alloc(c->sV, d.nV); dev_alloc(c->sW, d.nW);
-        dev_alloc(c->validU, d.nU); dev_alloc(c->validV, d.nV); dev_alloc(c->validW, d.nW);
-        size_t nmax = std::max(d.nU, std::max(d.nV, d.nW));
-        dev_alloc(c->status, nmax);
-        dev_alloc(c->frontier[0], nmax); dev_alloc(c->frontier[1], nmax);
-        dev_alloc(c->phiL, d.nC); dev_alloc(c->phiS, d.nN);
-        dev_alloc(c->wU, d.nU); dev_alloc(c->wV, d.nV); dev_alloc(c->wW, d.nW);
-        dev_alloc(c->cellCount, (size_t)d.nC + 1); dev_alloc(c->cellStart, (size_t)d.nC + 1);
-        dev_alloc(c->cellStartA, (size_t)d.nC + 1);
         dev_alloc(c->dS, 1);
         FLIP_CUDA_CHECK(cudaMallocHost(&c->hS, sizeof(DeviceScalars)));
         memset(c->hS, 0, sizeof(DeviceScalars));
-        pressure_alloc(c);
-        // phi_liquid starts at the "no particles" value 3dx (particlelevelset.cpp:295-301)
-        std::vector<float> init((size_t)d.nC, (float)(3.0 * dx));
-        FLIP_CUDA_CHECK(cudaMemcpy(c->phiL, init.data(), sizeof(float) * d.nC, cudaMemcpyHostToDevice));
+        allocate_grids(c);
     });
     if (rc != FLIP_OK) {
         free_all(c);
@@ -248,23 +297,11 @@ int flip_add_marker_particle(flip_ctx *c, const float p[3], const float v[3]) {
 
 int flip_set_solid_sdf(flip_ctx *c, const float *phi) {
     return guarded(c, [&] {
-        c->hostSolidPhi.assign(phi, phi + c->d.nN);
+        // always the GLOBAL nodal array, (I+1)(J+1)(Kglobal+1) floats
+        size_t nGlobal = (size_t)(c->d.I + 1) * (c->d.J + 1) * (c->d.Kg + 1);
+        c->hostSolidPhi.assign(phi, phi + nGlobal);
         c->userSolidPhi = true;
-        if (c->initialized) {
-            // re-derive the static inputs
-            const Dims &d = c->d;
-            std::vector<float> wU, wV, wW, wC;
-            build_weights(d, c->hostSolidPhi, wU, wV, wW, wC);
-            std::vector<unsigned char> ns;
-            build_near_solid(d, c->hostSolidPhi, c->nearSolidFactor, c->solidExactBand, c->CFL, ns, c->nsI, c->nsJ, c->nsK);
-            FLIP_CUDA_CHECK(cudaMemcpy(c->phiS, c->hostSolidPhi.data(), sizeof(float) * d.nN, cudaMemcpyHostToDevice));
-            FLIP_CUDA_CHECK(cudaMemcpy(c->wU, wU.data(), sizeof(float) * d.nU, cudaMemcpyHostToDevice));
-            FLIP_CUDA_CHECK(cudaMemcpy(c->wV, wV.data(), sizeof(float) * d.nV, cudaMemcpyHostToDevice));
-            FLIP_CUDA_CHECK(cudaMemcpy(c->wW, wW.data(), sizeof(float) * d.nW, cudaMemcpyHostToDevice));
-            cudaFree(c->nearSolid); c->nearSolid = nullptr;
-            dev_alloc(c->nearSolid, ns.size());
-            FLIP_CUDA_CHECK(cudaMemcpy(c->nearSolid, ns.data(), ns.size(), cudaMemcpyHostToDevice));
-        }
+        if (c->initialized) upload_static_inputs(c);   // re-derive the static inputs
     });
 }
 
@@ -275,7 +312,7 @@ static void seed_boxes(flip_ctx *c, std::vector<float> &pos, std::vector<float> 
     const Dims &d = c->d;
     double q = 0.25 * d.dx;
     for (auto &b : c->fluidBoxes) {
-        for (int k = 0; k < d.K; k++) for (int j = 0; j < d.J; j++) for (int i = 0; i < d.I; i++) {
+        for (int k = d.kOff + d.kOwn0; k < d.kOff + d.kOwn1; k++) for (int j = 0; j < d.J; j++) for (int i = 0; i < d.I; i++) {
             double cx = (i + 0.5) * d.dx, cy = (j + 0.5) * d.dx, cz = (k + 0.5) * d.dx;
             if (cx < b.lo[0] || cx >= b.hi[0] || cy < b.lo[1] || cy >= b.hi[1] || cz < b.lo[2] || cz >= b.hi[2]) continue;
             for (int s = 0; s < 8; s++) {
@@ -292,21 +329,11 @@ static void seed_boxes(flip_ctx *c, std::vector<float> &pos, std::vector<float> 
 int flip_initialize(flip_ctx *c) {
     return guarded(c, [&] {
         if (c->initialized) throw ApiError(FLIP_ERR_RUNTIME, "Error: FluidSimulation is already initialized.");
-        const Dims &d = c->d;
-        if (!c->userSolidPhi) build_box_solid_sdf(d, c->hostSolidPhi);
-        std::vector<float> wU, wV, wW, wC;
-        build_weights(d, c->hostSolidPhi, wU, wV, wW, wC);
-        std::vector<unsigned char> ns;
-        build_near_solid(d, c->hostSolidPhi, c->nearSolidFactor, c->solidExactBand, c->CFL, ns, c->nsI, c->nsJ, c->nsK);
-        FLIP_CUDA_CHECK(cudaMemcpy(c->phiS, c->hostSolidPhi.data(), sizeof(float) * d.nN, cudaMemcpyHostToDevice));
-        FLIP_CUDA_CHECK(cudaMemcpy(c->wU, wU.data(), sizeof(float) * d.nU, cudaMemcpyHostToDevice));
-        FLIP_CUDA_CHECK(cudaMemcpy(c->wV, wV.data(), sizeof(float) * d.nV, cudaMemcpyHostToDevice));
-        FLIP_CUDA_CHECK(cudaMemcpy(c->wW, wW.data(), sizeof(float) * d.nW, cudaMemcpyHostToDevice));
-        dev_alloc(c->nearSolid, ns.size());
-        FLIP_CUDA_CHECK(cudaMemcpy(c->nearSolid, ns.data(), ns.size(), cudaMemcpyHostToDevice));
+        upload_static_inputs(c);
         // _loadParticles (fluidsimulation.cpp:2791) + queued fluid boxes
         seed_boxes(c, c->loadQueuePos, c->loadQueueVel);
         int n = (int)(c->loadQueuePos.size() / 3);
+        // (a z-slab keeps the particles of its own planes only; every rank may be handed the whole scene)
         particles_upload_split(c, c->loadQueuePos.data(), c->loadQueueVel.data(), n);
         c->loadQueuePos.clear(); c->loadQueuePos.shrink_to_fit();
         c->loadQueueVel.clear(); c->loadQueueVel.shrink_to_fit();
@@ -377,10 +404,22 @@ static void run_stage(flip_ctx *c, int stage, double dt) {
         case FLIP_STAGE_OBSTACLES: break;                    // static scene
         case FLIP_STAGE_LIQUID_SDF: stage_liquid_sdf(c); break;
         case FLIP_STAGE_P2G: stage_p2g(c); break;
-        case FLIP_STAGE_EXTRAPOLATE_A: if (c->np > 0) stage_extrapolate(c); break;   // :3262 guards on !empty()
+        case FLIP_STAGE_EXTRAPOLATE_A: if (c->np_global > 0 || c->npStore > 0) stage_extrapolate(c); break;   // :3262 guards on !empty()
         case FLIP_STAGE_SAVE: stage_save(c); break;
         case FLIP_STAGE_BODY_FORCE: stage_body_force(c, dt); break;
-        case FLIP_STAGE_PRESSURE: stage_pressure(c, dt); break;
+        case FLIP_STAGE_PRESSURE:
+            stage_pressure(c, dt);
+            if (slab_on(c)) {
+                // projected velocities and masks of the halo planes come from the slabs that own them
+                const Dims &d = c->d;
+                slab_exchange_planes(c, c->U, (d.I + 1) * d.J, 0);
+                slab_exchange_planes(c, c->V, d.I * (d.J + 1), 0);
+                slab_exchange_planes(c, c->W, d.I * d.J, 1);
+                slab_exchange_planes_u8(c, c->validU, (d.I + 1) * d.J, 0);
+                slab_exchange_planes_u8(c, c->validV, d.I * (d.J + 1), 0);
+                slab_exchange_planes_u8(c, c->validW, d.I * d.J, 1);
+            }
+            break;
         case FLIP_STAGE_EXTRAPOLATE_B: stage_extrapolate(c); break;
         case FLIP_STAGE_CONSTRAIN: stage_constrain(c); break;
         case FLIP_STAGE_G2P: stage_g2p(c); break;
@@ -406,7 +445,7 @@ int flip_run_stage(flip_ctx *c, int stage, double dt) {
 
 int flip_end_substep(flip_ctx *c, int *more) {
     return guarded(c, [&] {
-        c->cur.particles = c->np;
+        c->cur.particles = slab_on(c) ? c->np_global : c->np;
         c->cur.removed_solid = c->hS->removedSolid;
         c->cur.removed_crowded = c->hS->removedCrowded;
         c->cur.removed_fast = c->hS->removedFast;
@@ -596,14 +635,49 @@ int flip_synchronize(flip_ctx *c) {
 }
 
 int flip_set_slab(flip_ctx *c, int rank, int nranks, const void *id, int idBytes) {
-    (void)id; (void)idBytes;
     return guarded(c, [&] {
-        if (nranks != 1 || rank != 0) throw ApiError(FLIP_ERR_UNSUPPORTED, "z-slab decomposition is not built yet");
+        if (c->initialized) throw ApiError(FLIP_ERR_RUNTIME, "flip_set_slab must precede flip_initialize");
+        if (nranks < 1 || rank < 0 || rank >= nranks) throw ApiError(FLIP_ERR_OUT_OF_RANGE, "bad rank / nranks");
+        if (nranks == 1) return;
+        const int Kg = c->KgCfg, H = c->halo;
+        int k0 = 0, k1 = 0;
+        flip_slab_range(Kg, nranks, rank, &k0, &k1);
+        if ((Kg / nranks) < H) throw ApiError(FLIP_ERR_DOMAIN, "z-slabs thinner than the halo width");
+        const int lo = rank > 0 ? H : 0, hi = rank < nranks - 1 ? H : 0;
+        c->comm = comm_create(rank, nranks, id, idBytes);
+        c->rank = rank; c->nranks = nranks;
+        free_grids(c);
+        set_geometry(c, c->d.I, c->d.J, (k1 - k0) + lo + hi, c->d.dx, k0 - lo, Kg, lo, lo + (k1 - k0));
+        allocate_grids(c);
     });
 }
 int flip_get_nccl_unique_id(void *out, int idBytes) {
-    (void)out; (void)idBytes;
-    return FLIP_ERR_UNSUPPORTED;
+    try {
+        comm_unique_id(out, idBytes);
+        return FLIP_OK;
+    } catch (const CudaError &e) { g_createError = e.msg; return FLIP_ERR_CUDA; }
+    catch (const ApiError &e) { g_createError = e.msg; return e.code; }
+}
+/* owned global planes of rank `rank`: a balanced split of K */
+int flip_slab_range(int K, int nranks, int rank, int *k0, int *k1) {
+    if (nranks < 1 || rank < 0 || rank >= nranks || !k0 || !k1) return FLIP_ERR_OUT_OF_RANGE;
+    *k0 = (int)((long long)K * rank / nranks);
+    *k1 = (int)((long long)K * (rank + 1) / nranks);
+    return FLIP_OK;
+}
+int flip_get_slab_info(const flip_ctx *c, int *kOff, int *Klocal, int *kOwn0, int *kOwn1) {
+    if (!c) return FLIP_ERR_RUNTIME;
+    if (kOff) *kOff = c->d.kOff;
+    if (Klocal) *Klocal = c->d.K;
+    if (kOwn0) *kOwn0 = c->d.kOwn0;
+    if (kOwn1) *kOwn1 = c->d.kOwn1;
+    return FLIP_OK;
+}
+int flip_set_halo(flip_ctx *c, int planes) {
+    return guarded(c, [&] {
+        if (planes < 16) throw ApiError(FLIP_ERR_DOMAIN, "the halo must cover the RK3 reach plus the extrapolation depth (>= 16 planes)");
+        c->halo = planes;
+    });
 }
 
 }  // extern "C"

@@ -45,7 +45,7 @@ __device__ __forceinline__ double trilerp8(const double p[8], double x, double y
 // gi,gj,gk = dimensions of this component's array.
 template <int SX, int SY, int SZ>
 __device__ __forceinline__ double sample_mac(const float *__restrict__ g, int gi, int gj, int gk, double x, double y,
-                                             double z, double dx, double invdx, double hdx) {
+                                             double z, double dx, double invdx, double hdx, int kOff) {
     if (SX) x = dsub(x, hdx);
     if (SY) y = dsub(y, hdx);
     if (SZ) z = dsub(z, hdx);
@@ -56,8 +56,10 @@ __device__ __forceinline__ double sample_mac(const float *__restrict__ g, int gi
     double p[8];
     bool i0 = (i >= 0 && i < gi), i1 = (i + 1 >= 0 && i + 1 < gi);
     bool j0 = (j >= 0 && j < gj), j1 = (j + 1 >= 0 && j + 1 < gj);
-    bool k0 = (k >= 0 && k < gk), k1 = (k + 1 >= 0 && k + 1 < gk);
-    long long base = (long long)i + (long long)gi * ((long long)j + (long long)gj * (long long)k);
+    // arrays hold the local planes of a z-slab: plane k (global) is stored at k - kOff
+    int kl = k - kOff;
+    bool k0 = (kl >= 0 && kl < gk), k1 = (kl + 1 >= 0 && kl + 1 < gk);
+    long long base = (long long)i + (long long)gi * ((long long)j + (long long)gj * (long long)kl);
     long long sj = gi, sk = (long long)gi * gj;
     p[0] = (i0 && j0 && k0) ? (double)__ldg(g + base) : 0.0;
     p[1] = (i1 && j0 && k0) ? (double)__ldg(g + base + 1) : 0.0;
@@ -74,19 +76,25 @@ struct MacField {
     const float *U, *V, *W;
 };
 
+// grid geometry seen by the particle kernels: I,J,K = local array extents, Kg = global K, kOff = global
+// index of local plane 0 (single GPU: K == Kg, kOff == 0)
+struct GridGeom {
+    int I, J, K, Kg, kOff;
+};
+
 // MACVelocityField::evaluateVelocityAtPositionLinear(vec3)  macvelocityfield.cpp:635-645
-__device__ __forceinline__ void sample_velocity(const MacField &f, int I, int J, int K, double dx, double invdx,
+__device__ __forceinline__ void sample_velocity(const MacField &f, const GridGeom &G, double dx, double invdx,
                                                 double hdx, float px, float py, float pz, float &ox, float &oy,
                                                 float &oz) {
     double x = px, y = py, z = pz;
     // Grid3d::isPositionInGrid (grid3d.h:135): x < dx*i in double
-    if (!(x >= 0 && y >= 0 && z >= 0 && x < dmul(dx, (double)I) && y < dmul(dx, (double)J) && z < dmul(dx, (double)K))) {
+    if (!(x >= 0 && y >= 0 && z >= 0 && x < dmul(dx, (double)G.I) && y < dmul(dx, (double)G.J) && z < dmul(dx, (double)G.Kg))) {
         ox = oy = oz = 0.0f;
         return;
     }
-    ox = (float)sample_mac<0, 1, 1>(f.U, I + 1, J, K, x, y, z, dx, invdx, hdx);
-    oy = (float)sample_mac<1, 0, 1>(f.V, I, J + 1, K, x, y, z, dx, invdx, hdx);
-    oz = (float)sample_mac<1, 1, 0>(f.W, I, J, K + 1, x, y, z, dx, invdx, hdx);
+    ox = (float)sample_mac<0, 1, 1>(f.U, G.I + 1, G.J, G.K, x, y, z, dx, invdx, hdx, G.kOff);
+    oy = (float)sample_mac<1, 0, 1>(f.V, G.I, G.J + 1, G.K, x, y, z, dx, invdx, hdx, G.kOff);
+    oz = (float)sample_mac<1, 1, 0>(f.W, G.I, G.J, G.K + 1, x, y, z, dx, invdx, hdx, G.kOff);
 }
 
 // Interpolation::trilinearInterpolate(vec3 p, double dx, Array3d<float>&)  interpolation.cpp:72-110
@@ -98,7 +106,7 @@ struct ScalarSample {
 };
 
 __device__ __forceinline__ void fetch_scalar(const float *__restrict__ g, int gi, int gj, int gk, double dx,
-                                             double invdx, float px, float py, float pz, ScalarSample &s) {
+                                             double invdx, float px, float py, float pz, ScalarSample &s, int kOff = 0) {
     s.i = pos2idx(px, invdx);
     s.j = pos2idx(py, invdx);
     s.k = pos2idx(pz, invdx);
@@ -108,7 +116,7 @@ __device__ __forceinline__ void fetch_scalar(const float *__restrict__ g, int gi
     s.fx = dmul((double)fsub(px, gx), invdx);
     s.fy = dmul((double)fsub(py, gy), invdx);
     s.fz = dmul((double)fsub(pz, gz), invdx);
-    int i = s.i, j = s.j, k = s.k;
+    int i = s.i, j = s.j, k = s.k - kOff;   // local plane of a z-slab
     bool i0 = (i >= 0 && i < gi), i1 = (i + 1 >= 0 && i + 1 < gi);
     bool j0 = (j >= 0 && j < gj), j1 = (j + 1 >= 0 && j + 1 < gj);
     bool k0 = (k >= 0 && k < gk), k1 = (k + 1 >= 0 && k + 1 < gk);
@@ -132,9 +140,9 @@ __device__ __forceinline__ float scalar_value(const ScalarSample &s) {
 }
 
 __device__ __forceinline__ float sample_scalar(const float *__restrict__ g, int gi, int gj, int gk, double dx,
-                                               double invdx, float px, float py, float pz) {
+                                               double invdx, float px, float py, float pz, int kOff = 0) {
     ScalarSample s;
-    fetch_scalar(g, gi, gj, gk, dx, invdx, px, py, pz, s);
+    fetch_scalar(g, gi, gj, gk, dx, invdx, px, py, pz, s, kOff);
     return scalar_value(s);
 }
 

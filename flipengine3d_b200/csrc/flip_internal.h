@@ -17,6 +17,8 @@
 
 namespace flip {
 
+struct Comm;   // comm.cpp
+
 struct CudaError {
     std::string msg;
     explicit CudaError(const std::string &m) : msg(m) {}
@@ -28,12 +30,18 @@ struct ApiError {
 };
 
 // Grid geometry handed to kernels by value.
+// With a z-slab decomposition (flip_set_slab) every array is LOCAL: K planes = the owned planes
+// [kOwn0,kOwn1) plus halo planes on the sides that have a neighbour; local plane kl is global plane
+// kl + kOff.  Particle coordinates stay global.  Single GPU: kOff = 0, Kg = K, kOwn = [0,K).
 struct Dims {
-    int I, J, K;        // cells
-    int nU, nV, nW;     // face counts
-    int nC;             // cells
-    int nN;             // nodes (I+1)(J+1)(K+1)
+    int I, J, K;        // cells of the local grid
+    int nU, nV, nW;     // face counts (local)
+    int nC;             // cells (local)
+    int nN;             // nodes (I+1)(J+1)(K+1) (local)
     double dx;
+    int kOff;           // global k of local plane 0
+    int Kg;             // global K
+    int kOwn0, kOwn1;   // owned local planes
 };
 
 // Particle store: SoA, 6 float arrays (24 B/particle), double buffered for the per-step cell sort.
@@ -66,6 +74,10 @@ struct DeviceScalars {
     double pcgTol;
     // extrapolation frontier sizes
     int frontierCount[2];
+    // z-slab exchange: particle counts sent to / received from the lower [0] and upper [1] neighbour
+    int sendCount[2], recvCount[2];
+    int globalParticles;       // sum over ranks of the sort input (speed-limit rule)
+    int globalRows;
     // multigrid coarse solve etc.
     int pad[8];
 };
@@ -119,7 +131,8 @@ struct flip_ctx {
 
     // ---- device memory
     int capacity = 0;                         // particle capacity
-    int np = 0;                               // live particles (host copy)
+    int np = 0;                               // live OWNED particles (host copy)
+    int npStore = 0;                          // particles in the store (owned + ghosts of neighbouring slabs)
     flip::ParticleSoA P[2];                   // ping-pong
     int cur_buf = 0;
     int *cellOfParticle = nullptr;            // [capacity] destination cell or -1 (removed)
@@ -173,6 +186,14 @@ struct flip_ctx {
 
     // multi-GPU slab
     int rank = 0, nranks = 1;
+    int halo = 16;                            // halo planes towards each neighbour
+    int KgCfg = 0;                            // global K given to flip_create
+    flip::Comm *comm = nullptr;
+    int ownedBegin = 0, ownedEnd = 0;         // owned particles inside the sorted (ghost-extended) store
+    bool ghostsPresent = false;
+    float *sendBuf[2] = {nullptr, nullptr};   // emigrant staging, 7 arrays of sendCap entries each
+    int sendCap = 0;
+    int np_global = 0;
 };
 
 namespace flip {
@@ -192,7 +213,7 @@ void particles_upload_split(flip_ctx *c, const float *pos, const float *vel, int
 void particles_download_aos(flip_ctx *c, float *aos6);
 void particles_download_component(flip_ctx *c, float *xyz, int which);  // 0 pos, 1 vel
 void particles_download_ids(flip_ctx *c, int *ids);
-void particles_sort(flip_ctx *c, bool applyRemovalRules, double frameDt);
+void particles_sort(flip_ctx *c, bool applyRemovalRules, double frameDt, int srcOffset, int count, bool ownedOnly);
 void stage_liquid_sdf(flip_ctx *c);
 void stage_p2g(flip_ctx *c);
 void stage_g2p(flip_ctx *c);
@@ -209,11 +230,31 @@ void pressure_alloc(flip_ctx *c);
 void pressure_free(flip_ctx *c);
 void stage_pressure(flip_ctx *c, double dt);
 
+// comm.cpp: NCCL (loaded with dlopen) for the z-slab exchanges
+Comm *comm_create(int rank, int nranks, const void *uniqueId, int idBytes);
+void comm_destroy(Comm *);
+int comm_unique_id(void *out, int idBytes);
+void comm_group_begin(Comm *);
+void comm_group_end(Comm *);
+void comm_send(Comm *, const void *buf, size_t bytes, int peer, cudaStream_t st);
+void comm_recv(Comm *, void *buf, size_t bytes, int peer, cudaStream_t st);
+enum { COMM_SUM_F64 = 0, COMM_MAX_U64 = 1, COMM_SUM_I32 = 2, COMM_MAX_U32 = 3 };
+void comm_allreduce(Comm *, void *buf, size_t count, int kind, cudaStream_t st);
+
+// slab.cu: halo exchanges between neighbouring slabs
+void slab_exchange_ghosts(flip_ctx *c);                 // ghost particles within `halo` planes, then re-sort
+void slab_drop_ghosts_and_migrate(flip_ctx *c);         // after advance: emigrants out, immigrants in
+void slab_exchange_planes(flip_ctx *c, float *field, int planeElems, int facePlanes);   // halo planes of a float grid
+void slab_exchange_planes_u8(flip_ctx *c, unsigned char *field, int planeElems, int facePlanes);
+void slab_exchange_vector_halo(flip_ctx *c, double *v); // one cell plane each way (PCG search vector / pressure)
+inline bool slab_on(const flip_ctx *c);
+
 // helpers
 void scalars_to_host(flip_ctx *c);   // async copy + sync
 size_t kt_begin(flip_ctx *c);                    // records a start event, returns its slot (or 0 when disabled)
 void kt_end(flip_ctx *c, int cls, size_t slot);  // records the stop event
 void kt_collect(flip_ctx *c);                    // after a stream sync: folds pending pairs into the sums
 inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
+inline bool slab_on(const flip_ctx *c) { return c->nranks > 1; }
 
 }  // namespace flip

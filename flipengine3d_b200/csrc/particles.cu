@@ -49,12 +49,13 @@ void particles_alloc(flip_ctx *c, int capacity) {
     int *npid[2] = {nullptr, nullptr};
     FLIP_CUDA_CHECK(cudaMalloc(&npid[0], sizeof(int) * cap));
     FLIP_CUDA_CHECK(cudaMalloc(&npid[1], sizeof(int) * cap));
-    if (oldCap > 0 && c->np > 0)
-        FLIP_CUDA_CHECK(cudaMemcpyAsync(npid[c->cur_buf], c->pid[c->cur_buf], sizeof(int) * c->np, cudaMemcpyDeviceToDevice, c->stream));
-    if (oldCap > 0 && c->np > 0) {
+    const int live = c->npStore > c->np ? c->npStore : c->np;   // owned + ghosts
+    if (oldCap > 0 && live > 0)
+        FLIP_CUDA_CHECK(cudaMemcpyAsync(npid[c->cur_buf], c->pid[c->cur_buf], sizeof(int) * live, cudaMemcpyDeviceToDevice, c->stream));
+    if (oldCap > 0 && live > 0) {
         const ParticleSoA &s = old[c->cur_buf];
         ParticleSoA &t = nw[c->cur_buf];
-        size_t b = sizeof(float) * c->np;
+        size_t b = sizeof(float) * live;
         FLIP_CUDA_CHECK(cudaMemcpyAsync(t.px, s.px, b, cudaMemcpyDeviceToDevice, c->stream));
         FLIP_CUDA_CHECK(cudaMemcpyAsync(t.py, s.py, b, cudaMemcpyDeviceToDevice, c->stream));
         FLIP_CUDA_CHECK(cudaMemcpyAsync(t.pz, s.pz, b, cudaMemcpyDeviceToDevice, c->stream));
@@ -122,19 +123,29 @@ __global__ void k_soa_to_xyz(const float *x, const float *y, const float *z, int
 // ------------------------------------------------------------------------------------------------
 struct SortParams {
     int n;
-    int I, J, K;
+    int I, J, K;          // local grid
+    int kOff;             // global k of local plane 0
+    int kOwn0, kOwn1;     // owned local planes
+    int ownedOnly;        // z-slab: silently drop particles outside the owned planes (they were sent to a neighbour)
     double dx, invdx;
     int applyRules;
     int maxPerCell;
 };
 
+__device__ __forceinline__ bool sort_keeps(const SortParams &sp, float z) {
+    if (!sp.ownedOnly) return true;
+    int kl = pos2idx(z, sp.invdx) - sp.kOff;
+    return kl >= sp.kOwn0 && kl < sp.kOwn1;
+}
+
 // _getMarkerParticleSpeedLimit, first loop (:4300-4305): histogram of |v| in CFL*dx/dt_frame bins.
-__global__ void k_speed_hist(ParticleSoA p, int n, double speedLimitStep, int nbins, DeviceScalars *S) {
+__global__ void k_speed_hist(ParticleSoA p, SortParams sp, double speedLimitStep, int nbins, DeviceScalars *S) {
     __shared__ int sh[8];
     if (threadIdx.x < 8) sh[threadIdx.x] = 0;
     __syncthreads();
     int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < n) {
+    int n = sp.n;
+    if (t < n && sort_keeps(sp, p.pz[t])) {
         float len = length3(p.vx[t], p.vy[t], p.vz[t]);
         double speed = (double)len;
         double b = fmin(floor(speed / speedLimitStep), (double)(nbins - 1));
@@ -164,15 +175,18 @@ __global__ void k_classify(ParticleSoA p, SortParams sp, const float *__restrict
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= sp.n) return;
     float x = p.px[t], y = p.py[t], z = p.pz[t];
-    int i = pos2idx(x, sp.invdx), j = pos2idx(y, sp.invdx), k = pos2idx(z, sp.invdx);
+    int i = pos2idx(x, sp.invdx), j = pos2idx(y, sp.invdx), k = pos2idx(z, sp.invdx) - sp.kOff;
     int cell = -1;
     bool inRange = (i >= 0 && j >= 0 && k >= 0 && i < sp.I && j < sp.J && k < sp.K);
+    bool gone = sp.ownedOnly && (k < sp.kOwn0 || k >= sp.kOwn1);   // now lives on a neighbouring slab
     unsigned char f = 0;
-    if (inRange) {
+    if (gone) {
+        cell = -1;
+    } else if (inRange) {
         cell = i + sp.I * (j + sp.J * k);
         if (sp.applyRules) {
             // MeshLevelSet::trilinearInterpolateSolidPoints  meshlevelset.h:325-332
-            float phi = sample_scalar(phiS, sp.I + 1, sp.J + 1, sp.K + 1, sp.dx, sp.invdx, x, y, z);
+            float phi = sample_scalar(phiS, sp.I + 1, sp.J + 1, sp.K + 1, sp.dx, sp.invdx, x, y, z, sp.kOff);
             if (phi < 0.0f) {
                 cell = -1;
                 atomicAdd(&S->removedSolid, 1);
@@ -289,28 +303,42 @@ void scalars_to_host(flip_ctx *c) {
     FLIP_CUDA_CHECK(cudaStreamSynchronize(c->stream));
 }
 
-// Sorts P[cur] (c->np particles) into P[1-cur], grouped by cell, and rebuilds cellStart.
-void particles_sort(flip_ctx *c, bool applyRules, double frameDt) {
+static ParticleSoA soa_offset(const ParticleSoA &p, int off) {
+    ParticleSoA q = p;
+    q.px += off; q.py += off; q.pz += off; q.vx += off; q.vy += off; q.vz += off;
+    return q;
+}
+
+// Sorts `count` particles of P[cur] starting at `srcOffset` into P[1-cur] (from index 0), grouped by
+// cell, and rebuilds cellStart.  ownedOnly (z-slabs): particles outside the owned planes are dropped.
+void particles_sort(flip_ctx *c, bool applyRules, double frameDt, int srcOffset, int count, bool ownedOnly) {
     const Dims &d = c->d;
-    int n = c->np;
+    int n = count;
     cudaStream_t st = c->stream;
-    ParticleSoA &src = c->P[c->cur_buf];
+    ParticleSoA src = soa_offset(c->P[c->cur_buf], srcOffset);
     ParticleSoA &dst = c->P[1 - c->cur_buf];
     int nC = d.nC;
     size_t ktSort = kt_begin(c);
     k_reset_sort_scalars<<<1, 1, 0, st>>>(c->dS); c->launches++;
     FLIP_CUDA_CHECK(cudaMemsetAsync(c->cellCount, 0, sizeof(int) * (nC + 1), st));
-    if (n > 0) {
-        if (applyRules) {
-            // _removeMarkerParticles(_currentFrameDeltaTime): bins are CFL*dx/dt_FRAME wide
-            double speedLimitStep = c->CFL * d.dx / frameDt;
-            k_speed_hist<<<cdiv(n, TPB), TPB, 0, st>>>(src, n, speedLimitStep, c->maxSubsteps, c->dS); c->launches++;
-            k_speed_limit<<<1, 1, 0, st>>>(n, speedLimitStep, c->maxSubsteps, c->maxExtremeVelocityRemovalPercent,
-                                           c->maxExtremeVelocityRemovalAbsolute, c->dS); c->launches++;
+    SortParams sp;
+    sp.n = n; sp.I = d.I; sp.J = d.J; sp.K = d.K; sp.dx = d.dx; sp.invdx = 1.0 / d.dx;
+    sp.kOff = d.kOff; sp.kOwn0 = d.kOwn0; sp.kOwn1 = d.kOwn1; sp.ownedOnly = ownedOnly ? 1 : 0;
+    sp.applyRules = applyRules ? 1 : 0; sp.maxPerCell = c->maxParticlesPerCell;
+    if (applyRules) {
+        // _removeMarkerParticles(_currentFrameDeltaTime): bins are CFL*dx/dt_FRAME wide
+        double speedLimitStep = c->CFL * d.dx / frameDt;
+        int nGlobal = n;
+        if (n > 0) { k_speed_hist<<<cdiv(n, TPB), TPB, 0, st>>>(src, sp, speedLimitStep, c->maxSubsteps, c->dS); c->launches++; }
+        if (slab_on(c)) {
+            // the rule is global: histogram and particle count summed over the slabs
+            comm_allreduce(c->comm, c->dS->speedHist, 8, COMM_SUM_I32, st);
+            nGlobal = c->np_global;
         }
-        SortParams sp;
-        sp.n = n; sp.I = d.I; sp.J = d.J; sp.K = d.K; sp.dx = d.dx; sp.invdx = 1.0 / d.dx;
-        sp.applyRules = applyRules ? 1 : 0; sp.maxPerCell = c->maxParticlesPerCell;
+        k_speed_limit<<<1, 1, 0, st>>>(nGlobal, speedLimitStep, c->maxSubsteps, c->maxExtremeVelocityRemovalPercent,
+                                       c->maxExtremeVelocityRemovalAbsolute, c->dS); c->launches++;
+    }
+    if (n > 0) {
         k_classify<<<cdiv(n, TPB), TPB, 0, st>>>(src, sp, c->phiS, c->cellOfParticle, c->fastFlag, c->cellCount, c->dS);
         c->launches++;
     }
@@ -329,13 +357,26 @@ void particles_sort(flip_ctx *c, bool applyRules, double frameDt) {
     k_build_src<<<cdiv(nC, TPB), TPB, 0, st>>>(nC, c->cellStartA, c->cellStart, c->sortIdx, c->srcIdx, c->dS);
     c->launches++;
     if (n > 0) {
-        k_gather<<<cdiv(n, TPB), TPB, 0, st>>>(src, dst, c->srcIdx, n, c->dS, c->trackIds ? c->pid[c->cur_buf] : nullptr,
+        k_gather<<<cdiv(n, TPB), TPB, 0, st>>>(src, dst, c->srcIdx, n, c->dS, c->trackIds ? c->pid[c->cur_buf] + srcOffset : nullptr,
                                                c->pid[1 - c->cur_buf]); c->launches++;
+    }
+    if (slab_on(c) && ownedOnly) {
+        // CFL uses the maximum speed over all slabs; particle and removal counts of the whole domain
+        comm_allreduce(c->comm, &c->dS->maxSpeedSqBits, 1, COMM_MAX_U32, st);
+        FLIP_CUDA_CHECK(cudaMemcpyAsync(&c->dS->globalParticles, &c->dS->numParticles, sizeof(int), cudaMemcpyDeviceToDevice, st));
+        comm_allreduce(c->comm, &c->dS->globalParticles, 1, COMM_SUM_I32, st);
+        comm_allreduce(c->comm, &c->dS->removedSolid, 3, COMM_SUM_I32, st);
     }
     kt_end(c, FLIP_KERNEL_SORT, ktSort);
     scalars_to_host(c);
     c->np = c->hS->numParticles;
+    c->npStore = c->np;
+    if (!slab_on(c)) c->np_global = c->np;
+    else if (ownedOnly) c->np_global = c->hS->globalParticles;
     c->cur_buf = 1 - c->cur_buf;
+    c->ownedBegin = 0;
+    c->ownedEnd = c->np;
+    c->ghostsPresent = false;
 }
 
 void particles_upload_aos(flip_ctx *c, const float *aos6, int n) {
@@ -348,7 +389,7 @@ void particles_upload_aos(flip_ctx *c, const float *aos6, int n) {
         k_aos_to_soa<<<cdiv(n, TPB), TPB, 0, c->stream>>>(tmp, n, c->P[c->cur_buf]); c->launches++;
         if (c->trackIds) { k_iota<<<cdiv(n, TPB), TPB, 0, c->stream>>>(c->pid[c->cur_buf], n); c->launches++; }
     }
-    particles_sort(c, false, 0.0);
+    particles_sort(c, false, 0.0, 0, n, slab_on(c));
 }
 
 void particles_upload_split(flip_ctx *c, const float *pos, const float *vel, int n) {
@@ -362,21 +403,21 @@ void particles_upload_split(flip_ctx *c, const float *pos, const float *vel, int
         k_split_to_soa<<<cdiv(n, TPB), TPB, 0, c->stream>>>(tp, tv, n, c->P[c->cur_buf]); c->launches++;
         if (c->trackIds) { k_iota<<<cdiv(n, TPB), TPB, 0, c->stream>>>(c->pid[c->cur_buf], n); c->launches++; }
     }
-    particles_sort(c, false, 0.0);
+    particles_sort(c, false, 0.0, 0, n, slab_on(c));
 }
 
 void particles_download_aos(flip_ctx *c, float *aos6) {
     int n = c->np;
     if (n == 0) return;
     float *tmp = c->P[1 - c->cur_buf].px;
-    k_soa_to_aos<<<cdiv(n, TPB), TPB, 0, c->stream>>>(c->P[c->cur_buf], n, tmp); c->launches++;
+    k_soa_to_aos<<<cdiv(n, TPB), TPB, 0, c->stream>>>(soa_offset(c->P[c->cur_buf], c->ownedBegin), n, tmp); c->launches++;
     FLIP_CUDA_CHECK(cudaMemcpyAsync(aos6, tmp, sizeof(float) * 6ll * n, cudaMemcpyDeviceToHost, c->stream));
     FLIP_CUDA_CHECK(cudaStreamSynchronize(c->stream));
 }
 
 void particles_download_ids(flip_ctx *c, int *ids) {
     if (c->np == 0) return;
-    FLIP_CUDA_CHECK(cudaMemcpyAsync(ids, c->pid[c->cur_buf], sizeof(int) * c->np, cudaMemcpyDeviceToHost, c->stream));
+    FLIP_CUDA_CHECK(cudaMemcpyAsync(ids, c->pid[c->cur_buf] + c->ownedBegin, sizeof(int) * c->np, cudaMemcpyDeviceToHost, c->stream));
     FLIP_CUDA_CHECK(cudaStreamSynchronize(c->stream));
 }
 
@@ -384,7 +425,7 @@ void particles_download_component(flip_ctx *c, float *xyz, int which) {
     int n = c->np;
     if (n == 0) return;
     float *tmp = c->P[1 - c->cur_buf].px;
-    const ParticleSoA &p = c->P[c->cur_buf];
+    const ParticleSoA p = soa_offset(c->P[c->cur_buf], c->ownedBegin);
     if (which == 0) k_soa_to_xyz<<<cdiv(n, TPB), TPB, 0, c->stream>>>(p.px, p.py, p.pz, n, tmp);
     else k_soa_to_xyz<<<cdiv(n, TPB), TPB, 0, c->stream>>>(p.vx, p.vy, p.vz, n, tmp);
     c->launches++;
@@ -410,7 +451,8 @@ void particles_download_component(flip_ctx *c, float *xyz, int which) {
 // the same order and precision, so results are bit-identical per term for any dx.
 // ------------------------------------------------------------------------------------------------
 struct GatherParams {
-    int I, J, K;
+    int I, J, K;          // local grid
+    int kOff;             // global k of local plane 0 (block origins and node positions use global indices)
     double dx, invdx;
     float hw;             // (float)(0.5*dx): _getDirectionOffset, velocityadvector.cpp:153-164
     double blockdxP2G;    // _chunkWidth * _dx (double)            velocityadvector.cpp:411
@@ -438,8 +480,9 @@ __global__ void __launch_bounds__(128) k_sdf_p2g(ParticleSoA p, const int *__res
                                                  const float *__restrict__ phiS) {
     const int I = g.I, J = g.J, K = g.K;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int j = blockIdx.y, k = blockIdx.z;
+    int j = blockIdx.y, k = blockIdx.z;      // k: local plane
     if (i > I) return;
+    const int kg = k + g.kOff;               // global plane
     const bool hasU = (j < J && k < K);
     const bool hasV = (i < I && k < K);
     const bool hasW = (i < I && j < J);
@@ -447,8 +490,8 @@ __global__ void __launch_bounds__(128) k_sdf_p2g(ParticleSoA p, const int *__res
 
     // block of this node per axis and local node coordinate (the three components and the cell
     // share (i,j,k), blocks are 10 wide for both subsystems)
-    const int bi = i / 10, bj = j / 10, bk = k / 10;
-    const int li = i - bi * 10, lj = j - bj * 10, lk = k - bk * 10;
+    const int bi = i / 10, bj = j / 10, bk = kg / 10;
+    const int li = i - bi * 10, lj = j - bj * 10, lk = kg - bk * 10;
     // block origins  (float)bi * blockdx  -> float  (grid3d.h:81-83)
     const float oxP = (float)dmul((double)(float)bi, g.blockdxP2G);
     const float oyP = (float)dmul((double)(float)bj, g.blockdxP2G);
@@ -590,7 +633,7 @@ __global__ void __launch_bounds__(128) k_sdf_p2g(ParticleSoA p, const int *__res
 static GatherParams make_gather_params(const flip_ctx *c) {
     const Dims &d = c->d;
     GatherParams g;
-    g.I = d.I; g.J = d.J; g.K = d.K;
+    g.I = d.I; g.J = d.J; g.K = d.K; g.kOff = d.kOff;
     g.dx = d.dx; g.invdx = 1.0 / d.dx;
     g.hw = (float)(0.5 * d.dx);
     g.blockdxP2G = 10 * d.dx;
@@ -625,7 +668,10 @@ static void run_sdf_p2g(flip_ctx *c) {
     FLIP_CUDA_CHECK(cudaGetLastError());
 }
 
-void stage_liquid_sdf(flip_ctx *c) { run_sdf_p2g(c); }
+void stage_liquid_sdf(flip_ctx *c) {
+    if (slab_on(c)) slab_exchange_ghosts(c);    // neighbours' particles within the halo planes, then re-sort
+    run_sdf_p2g(c);
+}
 
 // _advectVelocityField (fluidsimulation.cpp:3253-3278): valid.reset(); MAC.clear(); advect().
 // The fused gather of stage_liquid_sdf already produced U,V,W and the valid masks from the same
@@ -638,7 +684,7 @@ void stage_p2g(flip_ctx *c) { (void)c; }
 // ------------------------------------------------------------------------------------------------
 struct AdvectParams {
     int n;
-    int I, J, K;
+    GridGeom G;
     double dx, invdx, hdx;
     float ratioPIC, ratioFLIP;     // (float)_ratioPICFLIP, (float)(1 - _ratioPICFLIP)   :4088
     float c1, c2, c3;              // (float)(0.5*dt), (float)(0.75*dt), (float)(dt/9.0f) :4191-4196
@@ -657,8 +703,8 @@ __global__ void k_g2p(ParticleSoA p, AdvectParams a, MacField fnew, MacField fol
     if (t >= a.n) return;
     float x = p.px[t], y = p.py[t], z = p.pz[t];
     float nx, ny, nz, ox, oy, oz;
-    sample_velocity(fnew, a.I, a.J, a.K, a.dx, a.invdx, a.hdx, x, y, z, nx, ny, nz);
-    sample_velocity(fold, a.I, a.J, a.K, a.dx, a.invdx, a.hdx, x, y, z, ox, oy, oz);
+    sample_velocity(fnew, a.G, a.dx, a.invdx, a.hdx, x, y, z, nx, ny, nz);
+    sample_velocity(fold, a.G, a.dx, a.invdx, a.hdx, x, y, z, ox, oy, oz);
     // vFLIP = v + vPIC - vOld ; v = ratio*vPIC + (1-ratio)*vFLIP   (fluidsimulation.cpp:4084-4090)
     float fx = fsub(fadd(p.vx[t], nx), ox);
     float fy = fsub(fadd(p.vy[t], ny), oy);
@@ -694,9 +740,9 @@ __device__ __forceinline__ bool near_solid(const unsigned char *__restrict__ ns,
 __device__ void resolve_collision(const AdvectParams &a, const float *__restrict__ phiS,
                                   const unsigned char *__restrict__ ns, float ox, float oy, float oz, float &nx,
                                   float &ny, float &nz) {
-    const int gi = a.I + 1, gj = a.J + 1, gk = a.K + 1;
+    const int gi = a.G.I + 1, gj = a.G.J + 1, gk = a.G.K + 1, ko = a.G.kOff;
     int ci = pos2idx(nx, a.invdx), cj = pos2idx(ny, a.invdx), ck = pos2idx(nz, a.invdx);
-    if (!(ci >= 0 && cj >= 0 && ck >= 0 && ci < a.I && cj < a.J && ck < a.K)) box_nearest(a, nx, ny, nz);
+    if (!(ci >= 0 && cj >= 0 && ck >= 0 && ci < a.G.I && cj < a.G.J && ck < a.G.Kg)) box_nearest(a, nx, ny, nz);
     if (!near_solid(ns, a, ox, oy, oz) && !near_solid(ns, a, nx, ny, nz)) return;
 
     const float eps = 1e-6f;
@@ -719,7 +765,7 @@ __device__ void resolve_collision(const AdvectParams &a, const float *__restrict
             float f = fmul((float)(s + 1), a.stepDistance);
             cx = fadd(ox, fmul(sx, f)); cy = fadd(oy, fmul(sy, f)); cz = fadd(oz, fmul(sz, f));
         }
-        fetch_scalar(phiS, gi, gj, gk, a.dx, a.invdx, cx, cy, cz, smp);
+        fetch_scalar(phiS, gi, gj, gk, a.dx, a.invdx, cx, cy, cz, smp, ko);
         float phi = scalar_value(smp);
         if (phi < 0.0f || !box_inside(a, cx, cy, cz)) { collisionPhi = phi; found = true; break; }
         lx = cx; ly = cy; lz = cz;
@@ -737,7 +783,7 @@ __device__ void resolve_collision(const AdvectParams &a, const float *__restrict
         // to float by operator*(float, vec3)
         float sc = (float)dsub((double)collisionPhi, a.pushOut);
         rx = fsub(cx, fmul(gx, sc)); ry = fsub(cy, fmul(gy, sc)); rz = fsub(cz, fmul(gz, sc));
-        float rphi = sample_scalar(phiS, gi, gj, gk, a.dx, a.invdx, rx, ry, rz);
+        float rphi = sample_scalar(phiS, gi, gj, gk, a.dx, a.invdx, rx, ry, rz, ko);
         float rdist = length3(fsub(rx, cx), fsub(ry, cy), fsub(rz, cz));
         if (rphi < 0 || rdist > a.maxResolvedDistance) { rx = lx; ry = ly; rz = lz; }
     } else {
@@ -746,7 +792,7 @@ __device__ void resolve_collision(const AdvectParams &a, const float *__restrict
     if (!box_inside(a, rx, ry, rz)) {
         float qx = rx, qy = ry, qz = rz;
         box_nearest(a, rx, ry, rz);
-        float rphi = sample_scalar(phiS, gi, gj, gk, a.dx, a.invdx, rx, ry, rz);
+        float rphi = sample_scalar(phiS, gi, gj, gk, a.dx, a.invdx, rx, ry, rz, ko);
         float rdist = length3(fsub(rx, qx), fsub(ry, qy), fsub(rz, qz));
         if (rphi < 0.0f || rdist > a.maxResolvedDistance) { rx = lx; ry = ly; rz = lz; }
     }
@@ -760,10 +806,10 @@ __global__ void k_advance(ParticleSoA p, AdvectParams a, MacField f, const float
     float x = p.px[t], y = p.py[t], z = p.pz[t];
     // _RK3  fluidsimulation.cpp:4191-4198
     float k1x, k1y, k1z, k2x, k2y, k2z, k3x, k3y, k3z;
-    sample_velocity(f, a.I, a.J, a.K, a.dx, a.invdx, a.hdx, x, y, z, k1x, k1y, k1z);
-    sample_velocity(f, a.I, a.J, a.K, a.dx, a.invdx, a.hdx, fadd(x, fmul(k1x, a.c1)), fadd(y, fmul(k1y, a.c1)),
+    sample_velocity(f, a.G, a.dx, a.invdx, a.hdx, x, y, z, k1x, k1y, k1z);
+    sample_velocity(f, a.G, a.dx, a.invdx, a.hdx, fadd(x, fmul(k1x, a.c1)), fadd(y, fmul(k1y, a.c1)),
                     fadd(z, fmul(k1z, a.c1)), k2x, k2y, k2z);
-    sample_velocity(f, a.I, a.J, a.K, a.dx, a.invdx, a.hdx, fadd(x, fmul(k2x, a.c2)), fadd(y, fmul(k2y, a.c2)),
+    sample_velocity(f, a.G, a.dx, a.invdx, a.hdx, fadd(x, fmul(k2x, a.c2)), fadd(y, fmul(k2y, a.c2)),
                     fadd(z, fmul(k2z, a.c2)), k3x, k3y, k3z);
     float sx = fadd(fadd(fmul(k1x, 2.0f), fmul(k2x, 3.0f)), fmul(k3x, 4.0f));
     float sy = fadd(fadd(fmul(k1y, 2.0f), fmul(k2y, 3.0f)), fmul(k3y, 4.0f));
@@ -777,7 +823,7 @@ static AdvectParams make_advect_params(const flip_ctx *c, double dt) {
     const Dims &d = c->d;
     AdvectParams a;
     a.n = c->np;
-    a.I = d.I; a.J = d.J; a.K = d.K;
+    a.G.I = d.I; a.G.J = d.J; a.G.K = d.K; a.G.Kg = d.Kg; a.G.kOff = d.kOff;
     a.dx = d.dx; a.invdx = 1.0 / d.dx; a.hdx = 0.5 * d.dx;
     a.ratioPIC = (float)c->ratioPICFLIP;
     a.ratioFLIP = (float)(1 - c->ratioPICFLIP);
@@ -787,7 +833,7 @@ static AdvectParams make_advect_params(const flip_ctx *c, double dt) {
     // _getBoundaryAABB + expand(-_solidBufferWidth*_dx): AABB::expand (aabb.cpp:122-128) with vec3 float position
     {
         float px = 0.f, py = 0.f, pz = 0.f;
-        double w = d.I * d.dx, h = d.J * d.dx, dp = d.K * d.dx;
+        double w = d.I * d.dx, h = d.J * d.dx, dp = d.Kg * d.dx;
         auto expand = [&](double v) {
             double hh = 0.5 * v;
             float hf = (float)hh;
@@ -814,7 +860,7 @@ void stage_g2p(flip_ctx *c) {
     AdvectParams a = make_advect_params(c, 0.0);
     MacField fn{c->U, c->V, c->W}, fo{c->sU, c->sV, c->sW};
     size_t kt = kt_begin(c);
-    k_g2p<<<cdiv(c->np, TPB), TPB, 0, c->stream>>>(c->P[c->cur_buf], a, fn, fo);
+    k_g2p<<<cdiv(c->np, TPB), TPB, 0, c->stream>>>(soa_offset(c->P[c->cur_buf], c->ownedBegin), a, fn, fo);
     kt_end(c, FLIP_KERNEL_G2P, kt);
     c->launches++;
     FLIP_CUDA_CHECK(cudaGetLastError());
@@ -825,13 +871,14 @@ void stage_advance(flip_ctx *c, double dt) {
         AdvectParams a = make_advect_params(c, dt);
         MacField fn{c->U, c->V, c->W};
         size_t kt = kt_begin(c);
-        k_advance<<<cdiv(c->np, TPB), TPB, 0, c->stream>>>(c->P[c->cur_buf], a, fn, c->phiS, c->nearSolid);
+        k_advance<<<cdiv(c->np, TPB), TPB, 0, c->stream>>>(soa_offset(c->P[c->cur_buf], c->ownedBegin), a, fn, c->phiS, c->nearSolid);
         kt_end(c, FLIP_KERNEL_ADVANCE, kt);
         c->launches++;
         FLIP_CUDA_CHECK(cudaGetLastError());
     }
     // _removeMarkerParticles(_currentFrameDeltaTime) + re-sort for the next step
-    particles_sort(c, true, c->frameDt);
+    if (slab_on(c)) slab_drop_ghosts_and_migrate(c);     // ends with the rules sort over the owned particles
+    else particles_sort(c, true, c->frameDt, 0, c->np, false);
 }
 
 }  // namespace flip

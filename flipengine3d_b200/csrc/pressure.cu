@@ -16,6 +16,7 @@
 // "acceptable" fallback (pressuresolver.cpp:810-840) are the reference's, in fp64.
 #include <cooperative_groups.h>
 #include <cub/device/device_scan.cuh>
+#include <algorithm>
 #include <cstring>
 #include <utility>
 #include "device_math.cuh"
@@ -29,15 +30,23 @@ static constexpr int TPB = 256;
 static constexpr int WPB = TPB / 32;
 
 struct PGrid {
-    int I, J, K;
+    int I, J, K;  // local grid
     int sj, sk;   // strides I, I*J
+    int kOff, Kg; // z-slab: global index of local plane 0, global K (single GPU: 0, K)
+    int kOwn0, kOwn1;   // owned local planes
 };
 
+// a pressure row of the GLOBAL system (pressuresolver.cpp:101-110): liquid cell in [1,N-2]^3
 __device__ __forceinline__ bool is_row(const float *__restrict__ phi, const PGrid &g, int c) {
     int i = c % g.I;
     int j = (c / g.I) % g.J;
+    int k = c / g.sk + g.kOff;
+    return i >= 1 && j >= 1 && k >= 1 && i < g.I - 1 && j < g.J - 1 && k < g.Kg - 1 && __ldg(phi + c) < 0.0f;
+}
+// ... that this slab owns
+__device__ __forceinline__ bool is_owned(const PGrid &g, int c) {
     int k = c / g.sk;
-    return i >= 1 && j >= 1 && k >= 1 && i < g.I - 1 && j < g.J - 1 && k < g.K - 1 && __ldg(phi + c) < 0.0f;
+    return k >= g.kOwn0 && k < g.kOwn1;
 }
 
 // ---- 1. rows -> segments (pressuresolver.cpp:101-114: cells with phi<0 in [1,N-2]^3, (k,j,i) order)
@@ -47,7 +56,7 @@ __global__ void k_seg_flag(const float *__restrict__ phi, PGrid g, int nC, int n
     int lane = threadIdx.x & 31;
     if (warp >= nSeg) return;
     int c = warp * 32 + lane;
-    bool row = (c < nC) && is_row(phi, g, c);
+    bool row = (c < nC) && is_owned(g, c) && is_row(phi, g, c);
     unsigned int m = __ballot_sync(0xffffffffu, row);
     if (lane == 0) {
         mask[warp] = m;
@@ -140,10 +149,11 @@ __global__ void k_build_system(const int *__restrict__ segCell, const unsigned i
         AoffU[c] = rR ? (float)volRight : 0.0f;
         AoffV[c] = rT ? (float)volTop : 0.0f;
         AoffW[c] = rF ? (float)volFront : 0.0f;
-        // entries this row reads that no row owns
+        // entries this row reads that no row of this slab owns
         if (!rL) AoffU[c - 1] = 0.0f;
         if (!rB) AoffV[c - g.sj] = 0.0f;
         if (!rK) AoffW[c - g.sk] = 0.0f;
+        else if (!is_owned(g, c - g.sk)) AoffW[c - g.sk] = (float)volBack;   // row of the lower neighbouring slab
     }
     babs = warp_maxd(babs);
     if (lane == 0 && babs > 0.0) atomicMax(&S->rhsMaxBits, (unsigned long long)__double_as_longlong(babs));
@@ -992,15 +1002,18 @@ __global__ void k_apply_pressure(ApplyParams ap, const float *__restrict__ phi, 
     long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (t >= n) return;
     int i = (int)(t % gi), j = (int)((t / gi) % gj), k = (int)(t / ((long long)gi * gj));
-    int a = (DIR == 0) ? i : (DIR == 1 ? j : k);
-    int amax = (DIR == 0) ? g.I : (DIR == 1 ? g.J : g.K);
+    int a = (DIR == 0) ? i : (DIR == 1 ? j : k + g.kOff);          // global index along DIR
+    int amax = (DIR == 0) ? g.I : (DIR == 1 ? g.J : g.Kg);
     unsigned char vflag = 0;
+    // z-slab: the lowest local face plane has no cell below it in local storage (halo, re-imported later)
+    const bool noLowerCell = (DIR == 2) && (k == 0);
+    if (noLowerCell && a != 0) { valid[t] = 0; return; }
     if (!(a == 0 || a == amax - 1)) {
         const int stride = (DIR == 0) ? 1 : (DIR == 1 ? g.sj : g.sk);
         // cell "2" is (i,j,k), cell "1" is one step back along DIR (pi,pj,pk)
         int c2 = i + g.I * (j + g.J * k);
         int c1 = c2 - stride;
-        bool in2 = (a < amax);       // a == amax: the face past the last cell
+        bool in2 = (DIR == 2) ? (k < g.K) : (a < amax);       // the face past the last (local) cell
         // FluidMaterialGrid::isFaceBorderingMaterial{U,V,W}  fluidmaterialgrid.cpp:126-150
         bool f1 = phi[c1] < 0.0f;
         bool f2 = in2 ? (phi[c2] < 0.0f) : false;
@@ -1145,7 +1158,7 @@ void stage_pressure(flip_ctx *c, double dt) {
     const Dims &d = c->d;
     cudaStream_t st = c->stream;
     PressureScratch *ps = (PressureScratch *)c->mg;
-    PGrid g{d.I, d.J, d.K, d.I, d.I * d.J};
+    PGrid g{d.I, d.J, d.K, d.I, d.I * d.J, d.kOff, d.Kg, d.kOwn0, d.kOwn1};
     int nSeg = ps->nSegAll;
 
     size_t ktBuild = kt_begin(c);
@@ -1167,7 +1180,7 @@ void stage_pressure(flip_ctx *c, double dt) {
     // bound we can derive on the host without a sync: every particle's cell could be its own segment.
     int segBound = nSeg;
     {
-        long long byParticles = (long long)c->np * 27;   // a particle makes at most 27 cells liquid
+        long long byParticles = (long long)c->npStore * 27;   // a particle makes at most 27 cells liquid
         if (byParticles < segBound) segBound = (int)byParticles;
         if (segBound < 1) segBound = 1;
     }
@@ -1181,8 +1194,15 @@ void stage_pressure(flip_ctx *c, double dt) {
                                              c->wW, c->Adiag, c->AoffU, c->AoffV, c->AoffW, c->vb, c->vx_, c->dS);
     c->launches++;
     kt_end(c, FLIP_KERNEL_PRESSURE_BUILD, ktBuild);
+    const bool slab = slab_on(c);
+    if (slab) {
+        // the system is global: ||b||_inf and the row count over all slabs
+        comm_allreduce(c->comm, &c->dS->rhsMaxBits, 1, COMM_MAX_U64, st);
+        FLIP_CUDA_CHECK(cudaMemcpyAsync(&c->dS->globalRows, &c->dS->numRows, sizeof(int), cudaMemcpyDeviceToDevice, st));
+        comm_allreduce(c->comm, &c->dS->globalRows, 1, COMM_SUM_I32, st);
+    }
     scalars_to_host(c);
-    int n = c->hS->numRows;
+    int n = slab ? c->hS->globalRows : c->hS->numRows;
     int numSeg = c->hS->numSegments;
     double bmax;
     {
@@ -1198,12 +1218,18 @@ void stage_pressure(flip_ctx *c, double dt) {
     // early out (pressuresolver.cpp:52-62): velocities and the valid mask stay untouched
     if (n == 0 || bmax < c->pressureTol) return;
 
-    segBlocks = cdiv((long long)numSeg * 32, TPB);
+    segBlocks = std::max(1, cdiv((long long)numSeg * 32, TPB));
     PcgParams pp;
     pp.g = g;
     pp.factor = bp.factor;
     pp.tolFactor = fmax(c->pressureTol, 1e-30);
     const bool useMg = (c->preconditioner == 1) && ps->numLevels >= 2;
+    if (slab && useMg) {
+        // block-local V-cycle per slab: the correction is zero on the neighbours' rows, which the level-0
+        // sweeps read through the halo planes of the iterate buffers
+        FLIP_CUDA_CHECK(cudaMemsetAsync(ps->lv[0].x, 0, sizeof(float) * (size_t)d.nC, st));
+        FLIP_CUDA_CHECK(cudaMemsetAsync(ps->lv[0].x2, 0, sizeof(float) * (size_t)d.nC, st));
+    }
     int jacobi = useMg ? 0 : 1;
     Mg0 m0;
     MgParams mp;
@@ -1294,7 +1320,7 @@ void stage_pressure(flip_ctx *c, double dt) {
     };
 
     k_pcg_scalars_init<<<1, 1, 0, st>>>(c->dS, pp.tolFactor); c->launches++;
-    if (c->pcgPersistent) {
+    if (c->pcgPersistent && !slab) {
         PcgDev P;
         P.segCell = c->segCell; P.segMask = c->segMask; P.g = g; P.factor = pp.factor;
         P.Adiag = c->Adiag; P.oU = c->AoffU; P.oV = c->AoffV; P.oW = c->AoffW;
@@ -1324,6 +1350,7 @@ void stage_pressure(flip_ctx *c, double dt) {
         vcycle(0);
         k_pcg_copy_zs<<<segBlocks, TPB, 0, st>>>(c->segCell, c->segMask, c->vz, c->vs, c->dS); c->launches++;
     }
+    if (slab) comm_allreduce(c->comm, &c->dS->rho[0], 1, COMM_SUM_F64, st);
 
     int it = 0;
     const int batch = useMg ? 4 : 16;
@@ -1333,14 +1360,18 @@ void stage_pressure(flip_ctx *c, double dt) {
         if (stop > c->pressureMaxIter) stop = c->pressureMaxIter;
         for (; it < stop; it++) {
             size_t ktIt = kt_begin(c);
+            if (slab) slab_exchange_vector_halo(c, c->vs);     // the neighbours' boundary plane of the search vector
             size_t ktSp = kt_begin(c);
             k_pcg_spmv<<<segBlocks, TPB, 0, st>>>(c->segCell, c->segMask, pp, c->Adiag, c->AoffU, c->AoffV, c->AoffW,
                                                   c->vs, c->vz, c->dS, it);
             kt_end(c, FLIP_KERNEL_PCG_SPMV, ktSp);
+            if (slab) comm_allreduce(c->comm, &c->dS->dotSZ[it % 3], 1, COMM_SUM_F64, st);
             k_pcg_update<<<segBlocks, TPB, 0, st>>>(c->segCell, c->segMask, c->Adiag, c->vs, c->vz, c->vx_, c->vr,
                                                     c->dS, it, jacobi);
             c->launches += 2;
+            if (slab) comm_allreduce(c->comm, &c->dS->rMaxBits[it % 3], 1, COMM_MAX_U64, st);
             if (useMg) vcycle((it + 1) % 3);
+            if (slab) comm_allreduce(c->comm, &c->dS->rho[(it + 1) % 3], 1, COMM_SUM_F64, st);
             k_pcg_direction<<<segBlocks, TPB, 0, st>>>(c->segCell, c->segMask, c->vz, c->vs, c->dS, it);
             kt_end(c, FLIP_KERNEL_PCG_ITER, ktIt);
             c->launches++;
@@ -1359,6 +1390,7 @@ void stage_pressure(flip_ctx *c, double dt) {
     // _solveLinearSystem failure: solve() returns before applying (pressuresolver.cpp:70-72)
     if (c->cur.pcg_converged == 0) return;
 
+    if (slab) slab_exchange_vector_halo(c, c->vx_);     // pressure of the neighbours' boundary planes
     ApplyParams ap;
     ap.g = g;
     ap.factor = (float)(dt / d.dx);
@@ -1373,7 +1405,7 @@ void stage_pressure(flip_ctx *c, double dt) {
 
 void pressure_to_float(flip_ctx *c, float *devOut) {
     const Dims &d = c->d;
-    PGrid g{d.I, d.J, d.K, d.I, d.I * d.J};
+    PGrid g{d.I, d.J, d.K, d.I, d.I * d.J, d.kOff, d.Kg, d.kOwn0, d.kOwn1};
     k_pressure_to_float<<<cdiv(d.nC, TPB), TPB, 0, c->stream>>>(c->phiL, c->vx_, g, d.nC, devOut);
     c->launches++;
 }

@@ -1,0 +1,239 @@
+// z-slab decomposition across the GPUs of one box.  The reference has no multi-process
+// path; this is new.  One process per GPU; rank r owns the global cell planes [K0_r, K1_r) and keeps
+// `halo` extra planes towards each neighbour, in which every grid stage is computed redundantly from
+// ghost particles, so the only exchanges per substep are:
+//   1. ghost particles (the neighbour's particles within `halo` planes of the shared face) before the
+//      liquid-SDF / P2G gather;
+//   2. one plane of the PCG search vector per iteration + the scalar all-reduces (pressure.cu);
+//   3. the projected velocity (and valid mask) halo planes after the pressure update;
+//   4. migrating particles after the RK3 advection.
+// k is the slowest array index, so every range below is contiguous: halo planes of a grid, and — the
+// particle store being sorted by cell — the particles of a range of planes.
+#include <algorithm>
+#include "device_math.cuh"
+#include "flip_internal.h"
+
+namespace flip {
+
+static constexpr int TPB = 256;
+
+__global__ void k_slab_ghost_counts(const int *__restrict__ cellStart, int IJ, int kOwn0, int kOwn1, int halo, int hasLo,
+                                    int hasHi, DeviceScalars *S) {
+    S->sendCount[0] = hasLo ? cellStart[(kOwn0 + halo) * IJ] - cellStart[kOwn0 * IJ] : 0;
+    S->sendCount[1] = hasHi ? cellStart[kOwn1 * IJ] - cellStart[(kOwn1 - halo) * IJ] : 0;
+    S->recvCount[0] = 0;
+    S->recvCount[1] = 0;
+}
+
+static void exchange_counts(flip_ctx *c) {
+    cudaStream_t st = c->stream;
+    const bool hasLo = c->rank > 0, hasHi = c->rank < c->nranks - 1;
+    comm_group_begin(c->comm);
+    if (hasLo) {
+        comm_send(c->comm, &c->dS->sendCount[0], sizeof(int), c->rank - 1, st);
+        comm_recv(c->comm, &c->dS->recvCount[0], sizeof(int), c->rank - 1, st);
+    }
+    if (hasHi) {
+        comm_send(c->comm, &c->dS->sendCount[1], sizeof(int), c->rank + 1, st);
+        comm_recv(c->comm, &c->dS->recvCount[1], sizeof(int), c->rank + 1, st);
+    }
+    comm_group_end(c->comm);
+    scalars_to_host(c);
+}
+
+struct SoAPtrs {
+    float *a[6];
+    int *id;
+};
+static SoAPtrs ptrs_of(flip_ctx *c, int buf) {
+    ParticleSoA &p = c->P[buf];
+    SoAPtrs q;
+    q.a[0] = p.px; q.a[1] = p.py; q.a[2] = p.pz; q.a[3] = p.vx; q.a[4] = p.vy; q.a[5] = p.vz;
+    q.id = c->pid[buf];
+    return q;
+}
+
+void slab_exchange_ghosts(flip_ctx *c) {
+    const Dims &d = c->d;
+    cudaStream_t st = c->stream;
+    const bool hasLo = c->rank > 0, hasHi = c->rank < c->nranks - 1;
+    const int IJ = d.I * d.J;
+    // the store holds exactly the owned particles, sorted: the two boundary layers are its head and tail
+    k_slab_ghost_counts<<<1, 1, 0, st>>>(c->cellStart, IJ, d.kOwn0, d.kOwn1, c->halo, hasLo ? 1 : 0, hasHi ? 1 : 0, c->dS);
+    c->launches++;
+    exchange_counts(c);
+    const int sendLo = c->hS->sendCount[0], sendHi = c->hS->sendCount[1];
+    const int recvLo = c->hS->recvCount[0], recvHi = c->hS->recvCount[1];
+    const int n = c->np;
+    const int total = n + recvLo + recvHi;
+    c->npStore = n;
+    particles_alloc(c, total);
+    SoAPtrs P = ptrs_of(c, c->cur_buf);
+    comm_group_begin(c->comm);
+    for (int a = 0; a < 6; a++) {
+        if (hasLo) {
+            comm_send(c->comm, P.a[a], sizeof(float) * (size_t)sendLo, c->rank - 1, st);
+            comm_recv(c->comm, P.a[a] + n, sizeof(float) * (size_t)recvLo, c->rank - 1, st);
+        }
+        if (hasHi) {
+            comm_send(c->comm, P.a[a] + (n - sendHi), sizeof(float) * (size_t)sendHi, c->rank + 1, st);
+            comm_recv(c->comm, P.a[a] + n + recvLo, sizeof(float) * (size_t)recvHi, c->rank + 1, st);
+        }
+    }
+    if (c->trackIds) {
+        if (hasLo) {
+            comm_send(c->comm, P.id, sizeof(int) * (size_t)sendLo, c->rank - 1, st);
+            comm_recv(c->comm, P.id + n, sizeof(int) * (size_t)recvLo, c->rank - 1, st);
+        }
+        if (hasHi) {
+            comm_send(c->comm, P.id + (n - sendHi), sizeof(int) * (size_t)sendHi, c->rank + 1, st);
+            comm_recv(c->comm, P.id + n + recvLo, sizeof(int) * (size_t)recvHi, c->rank + 1, st);
+        }
+    }
+    comm_group_end(c->comm);
+    // sort owned + ghosts over the extended local grid
+    particles_sort(c, false, 0.0, 0, total, false);
+    int range[2] = {0, 0};
+    FLIP_CUDA_CHECK(cudaMemcpyAsync(&range[0], c->cellStart + (size_t)d.kOwn0 * IJ, sizeof(int), cudaMemcpyDeviceToHost, st));
+    FLIP_CUDA_CHECK(cudaMemcpyAsync(&range[1], c->cellStart + (size_t)d.kOwn1 * IJ, sizeof(int), cudaMemcpyDeviceToHost, st));
+    FLIP_CUDA_CHECK(cudaStreamSynchronize(st));
+    c->npStore = c->np;              // everything the sort kept (owned + ghosts)
+    c->ownedBegin = range[0];
+    c->ownedEnd = range[1];
+    c->np = range[1] - range[0];
+    c->ghostsPresent = true;
+    if (c->np != n) throw CudaError("z-slab ghost exchange lost owned particles (halo wider than a neighbouring slab?)");
+}
+
+// Owned particles whose new plane belongs to a neighbour are appended (unordered) to the send buffers.
+__global__ void k_slab_pack_emigrants(ParticleSoA p, const int *__restrict__ ids, int n, double invdx, int kOff, int kOwn0,
+                                      int kOwn1, float *lo, float *hi, int cap, DeviceScalars *S) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    int kl = pos2idx(p.pz[t], invdx) - kOff;
+    int side = (kl < kOwn0) ? 0 : (kl >= kOwn1 ? 1 : -1);
+    if (side < 0) return;
+    int slot = atomicAdd(&S->sendCount[side], 1);
+    if (slot >= cap) return;     // overflow is detected on the host from the count
+    float *b = side ? hi : lo;
+    b[slot] = p.px[t];
+    b[(size_t)cap + slot] = p.py[t];
+    b[2ull * cap + slot] = p.pz[t];
+    b[3ull * cap + slot] = p.vx[t];
+    b[4ull * cap + slot] = p.vy[t];
+    b[5ull * cap + slot] = p.vz[t];
+    if (ids) ((int *)b)[6ull * cap + slot] = ids[t];
+}
+
+__global__ void k_slab_reset_counts(DeviceScalars *S) {
+    S->sendCount[0] = S->sendCount[1] = 0;
+    S->recvCount[0] = S->recvCount[1] = 0;
+}
+
+void slab_drop_ghosts_and_migrate(flip_ctx *c) {
+    const Dims &d = c->d;
+    cudaStream_t st = c->stream;
+    const bool hasLo = c->rank > 0, hasHi = c->rank < c->nranks - 1;
+    const int n = c->np;      // owned, at [ownedBegin, ownedEnd)
+    int wantCap = std::max(1 << 16, c->capacity / 8);
+    if (wantCap > c->sendCap) {
+        for (int s = 0; s < 2; s++) {
+            cudaFree(c->sendBuf[s]);
+            c->sendBuf[s] = nullptr;
+            FLIP_CUDA_CHECK(cudaMalloc(&c->sendBuf[s], sizeof(float) * 7ull * wantCap));
+        }
+        c->sendCap = wantCap;
+    }
+    k_slab_reset_counts<<<1, 1, 0, st>>>(c->dS); c->launches++;
+    if (n > 0) {
+        ParticleSoA p = c->P[c->cur_buf];
+        p.px += c->ownedBegin; p.py += c->ownedBegin; p.pz += c->ownedBegin;
+        p.vx += c->ownedBegin; p.vy += c->ownedBegin; p.vz += c->ownedBegin;
+        k_slab_pack_emigrants<<<cdiv(n, TPB), TPB, 0, st>>>(p, c->trackIds ? c->pid[c->cur_buf] + c->ownedBegin : nullptr, n,
+                                                           1.0 / d.dx, d.kOff, d.kOwn0, d.kOwn1, c->sendBuf[0],
+                                                           c->sendBuf[1], c->sendCap, c->dS);
+        c->launches++;
+    }
+    exchange_counts(c);
+    const int sendLo = c->hS->sendCount[0], sendHi = c->hS->sendCount[1];
+    const int recvLo = c->hS->recvCount[0], recvHi = c->hS->recvCount[1];
+    if (sendLo > c->sendCap || sendHi > c->sendCap) throw CudaError("z-slab migration buffer overflow");
+    const int total = n + recvLo + recvHi;
+    particles_alloc(c, c->ownedBegin + total);
+    SoAPtrs P = ptrs_of(c, c->cur_buf);
+    const int at = c->ownedEnd;     // immigrants overwrite the upper ghosts, which are no longer needed
+    const size_t cap = c->sendCap;
+    comm_group_begin(c->comm);
+    for (int a = 0; a < 6; a++) {
+        if (hasLo) {
+            comm_send(c->comm, c->sendBuf[0] + a * cap, sizeof(float) * (size_t)sendLo, c->rank - 1, st);
+            comm_recv(c->comm, P.a[a] + at, sizeof(float) * (size_t)recvLo, c->rank - 1, st);
+        }
+        if (hasHi) {
+            comm_send(c->comm, c->sendBuf[1] + a * cap, sizeof(float) * (size_t)sendHi, c->rank + 1, st);
+            comm_recv(c->comm, P.a[a] + at + recvLo, sizeof(float) * (size_t)recvHi, c->rank + 1, st);
+        }
+    }
+    if (c->trackIds) {
+        if (hasLo) {
+            comm_send(c->comm, c->sendBuf[0] + 6 * cap, sizeof(int) * (size_t)sendLo, c->rank - 1, st);
+            comm_recv(c->comm, P.id + at, sizeof(int) * (size_t)recvLo, c->rank - 1, st);
+        }
+        if (hasHi) {
+            comm_send(c->comm, c->sendBuf[1] + 6 * cap, sizeof(int) * (size_t)sendHi, c->rank + 1, st);
+            comm_recv(c->comm, P.id + at + recvLo, sizeof(int) * (size_t)recvHi, c->rank + 1, st);
+        }
+    }
+    comm_group_end(c->comm);
+    // removal rules + sort over (owned - emigrants + immigrants); emigrants are dropped by the owned-plane test
+    particles_sort(c, true, c->frameDt, c->ownedBegin, total, true);
+    c->npStore = c->np;
+}
+
+// Halo planes of a grid whose plane kl holds `planeElems` entries.  shift = 0 for cell-plane grids
+// (U, V, masks of U/V), 1 for the face-plane grid W: face plane kOwn0 / kOwn1 is computed identically
+// on both sides, so W halos start one plane further out.
+template <class T>
+static void exchange_planes(flip_ctx *c, T *f, int planeElems, int shift) {
+    const Dims &d = c->d;
+    cudaStream_t st = c->stream;
+    const bool hasLo = c->rank > 0, hasHi = c->rank < c->nranks - 1;
+    const int H = c->halo;
+    const size_t pe = (size_t)planeElems;
+    const size_t bytes = sizeof(T) * pe * H;
+    comm_group_begin(c->comm);
+    if (hasLo) {
+        comm_send(c->comm, f + pe * (d.kOwn0 + shift), bytes, c->rank - 1, st);
+        comm_recv(c->comm, f + pe * (d.kOwn0 - H), bytes, c->rank - 1, st);
+    }
+    if (hasHi) {
+        comm_send(c->comm, f + pe * (d.kOwn1 - H), bytes, c->rank + 1, st);
+        comm_recv(c->comm, f + pe * (d.kOwn1 + shift), bytes, c->rank + 1, st);
+    }
+    comm_group_end(c->comm);
+}
+
+void slab_exchange_planes(flip_ctx *c, float *f, int planeElems, int facePlanes) { exchange_planes(c, f, planeElems, facePlanes); }
+void slab_exchange_planes_u8(flip_ctx *c, unsigned char *f, int planeElems, int facePlanes) { exchange_planes(c, f, planeElems, facePlanes); }
+
+// One cell plane of a dense fp64 vector each way: my first owned plane -> lower neighbour's plane
+// kOwn1, my last owned plane -> upper neighbour's plane kOwn0-1.
+void slab_exchange_vector_halo(flip_ctx *c, double *v) {
+    const Dims &d = c->d;
+    cudaStream_t st = c->stream;
+    const bool hasLo = c->rank > 0, hasHi = c->rank < c->nranks - 1;
+    const size_t pe = (size_t)d.I * d.J;
+    const size_t bytes = sizeof(double) * pe;
+    comm_group_begin(c->comm);
+    if (hasLo) {
+        comm_send(c->comm, v + pe * d.kOwn0, bytes, c->rank - 1, st);
+        comm_recv(c->comm, v + pe * (d.kOwn0 - 1), bytes, c->rank - 1, st);
+    }
+    if (hasHi) {
+        comm_send(c->comm, v + pe * (d.kOwn1 - 1), bytes, c->rank + 1, st);
+        comm_recv(c->comm, v + pe * d.kOwn1, bytes, c->rank + 1, st);
+    }
+    comm_group_end(c->comm);
+}
+
+}  // namespace flip

@@ -107,8 +107,31 @@ def load_library():
     L.flip_synchronize.argtypes = [vp]
     L.flip_set_slab.argtypes = [vp, ci, ci, vp, ci]
     L.flip_get_nccl_unique_id.argtypes = [vp, ci]
+    L.flip_slab_range.argtypes = [ci, ci, ci, C.POINTER(ci), C.POINTER(ci)]
+    L.flip_get_slab_info.argtypes = [vp] + [C.POINTER(ci)] * 4
+    L.flip_set_halo.argtypes = [vp, ci]
     _lib = L
     return L
+
+
+def nccl_unique_id():
+    """128-byte ncclUniqueId (rank 0 creates it, the caller distributes it)."""
+    L = load_library()
+    buf = C.create_string_buffer(128)
+    rc = L.flip_get_nccl_unique_id(buf, 128)
+    if rc != FLIP_OK:
+        raise _EXC.get(rc, RuntimeError)(L.flip_create_error().decode())
+    return bytes(buf.raw)
+
+
+def slab_range(K, nranks, rank):
+    """Owned global planes [k0, k1) of `rank` (flip_slab_range)."""
+    L = load_library()
+    a, b = C.c_int(), C.c_int()
+    rc = L.flip_slab_range(int(K), int(nranks), int(rank), C.byref(a), C.byref(b))
+    if rc != FLIP_OK:
+        raise IndexError("bad rank / nranks")
+    return a.value, b.value
 
 
 class MarkerParticleData:
@@ -135,6 +158,7 @@ class FluidSimulation:
             raise _EXC.get(rc, RuntimeError)(self.L.flip_create_error().decode())
         self.dims = (int(isize), int(jsize), int(ksize))
         self.dx = float(dx)
+        self.local_K, self.k_offset, self.k_own = int(ksize), 0, (0, int(ksize))
 
     # -- plumbing
     def _check(self, rc):
@@ -151,6 +175,17 @@ class FluidSimulation:
             self.close()
         except Exception:
             pass
+
+    # -- z-slab decomposition (one process per GPU)
+    def setSlab(self, rank, nranks, unique_id):
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self._check(self.L.flip_set_slab(self.h, int(rank), int(nranks), buf, 128))
+        ko, kl, a, b = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        self._check(self.L.flip_get_slab_info(self.h, C.byref(ko), C.byref(kl), C.byref(a), C.byref(b)))
+        self.local_K, self.k_offset, self.k_own = kl.value, ko.value, (a.value, b.value)
+
+    def setHalo(self, planes):
+        self._check(self.L.flip_set_halo(self.h, int(planes)))
 
     # -- configuration
     def addBodyForce(self, fx, fy, fz):
@@ -332,6 +367,8 @@ class FluidSimulation:
 
     def shape_of(self, name):
         I, J, K = self.dims
+        if name != "solid_phi_global":
+            K = self.local_K
         if name in ("U", "validU", "weightU", "savedU"):
             return (K, J, I + 1)
         if name in ("V", "validV", "weightV", "savedV"):

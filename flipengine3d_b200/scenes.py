@@ -73,6 +73,14 @@ def dam_break(n=128, seed=12345):
     return dict(name=f"dambreak{n}", dims=(n, n, n), dx=DX, pos=pos, vel=vel)
 
 
+def dam_break_z(n=64, seed=12347):
+    """A column against the low-z wall that collapses along +z: particles cross z-slab boundaries
+    (migration test of the multi-GPU decomposition)."""
+    cells = box_cells(3, n - 3, 3, max(n // 2 + 3, 4), 3, max(n // 4 + 3, 4))
+    pos, vel = seed_cells(cells, DX, seed)
+    return dict(name=f"dambreakz{n}", dims=(n, n, n), dx=DX, pos=pos, vel=vel)
+
+
 def sphere_drop(n=256, seed=12346):
     """Config 3: pool i,k∈[3s,n-3s) j∈[2s,32s) + sphere radius 32s cells at (n/2, 160s, n/2), s=n/256."""
     s = n / 256.0
@@ -98,4 +106,4 @@ def pressure_stress(n=256, seed=777):
     return dict(name=f"pressurestress{n}", dims=(n, n, n), dx=DX, pos=pos, vel=vel)
 
 
-SCENES = {"default": default_scene, "dambreak": dam_break, "spheredrop": sphere_drop, "pressurestress": pressure_stress}
+SCENES = {"default": default_scene, "dambreak": dam_break, "dambreakz": dam_break_z, "spheredrop": sphere_drop, "pressurestress": pressure_stress}

@@ -205,11 +205,20 @@ int flip_synchronize(flip_ctx *ctx);
 
 /* ---- multi-GPU z-slab decomposition ------------------------------------------- */
 
-/* Make this context one z-slab [k0,k1) of a global I x J x Kglobal domain shared by `nranks`
- * processes of one box.  nccl_unique_id: the 128 bytes of an ncclUniqueId created by rank 0 and
- * distributed by the caller (e.g. torch.distributed broadcast).  Must precede flip_initialize. */
+/* Make this context one z-slab of the global I x J x K domain given to flip_create, shared by the
+ * `nranks` processes of one box (one process per GPU).  Rank r owns the global cell planes of
+ * flip_slab_range(K, nranks, r) and keeps `halo` (default 16) extra planes towards each neighbour.
+ * nccl_unique_id: the 128 bytes of an ncclUniqueId created by rank 0 (flip_get_nccl_unique_id) and
+ * distributed by the caller (e.g. a torch.distributed broadcast).  Must precede flip_initialize.
+ * Afterwards: flip_load_particles / flip_set_particles may be handed the whole scene (each rank keeps
+ * its own planes); flip_get_particles returns the owned particles; flip_get_array / flip_set_array
+ * address the LOCAL arrays (flip_get_slab_info); flip_set_solid_sdf still takes the GLOBAL array;
+ * flip_step_stats counts are global.  New: the reference has no multi-process path. */
 int flip_set_slab(flip_ctx *ctx, int rank, int nranks, const void *nccl_unique_id, int id_bytes);
 int flip_get_nccl_unique_id(void *out_id, int id_bytes);
+int flip_slab_range(int K, int nranks, int rank, int *k0, int *k1);
+int flip_get_slab_info(const flip_ctx *ctx, int *k_offset, int *k_local, int *k_own0, int *k_own1);
+int flip_set_halo(flip_ctx *ctx, int planes);
 
 #ifdef __cplusplus
 }
