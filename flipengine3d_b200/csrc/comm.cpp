@@ -16,6 +16,7 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
@@ -38,6 +39,7 @@ void load_api() {
     g_api.CommInitRank = (decltype(g_api.CommInitRank))sym("ncclCommInitRank");
     g_api.CommDestroy = (decltype(g_api.CommDestroy))sym("ncclCommDestroy");
     g_api.AllReduce = (decltype(g_api.AllReduce))sym("ncclAllReduce");
+    g_api.AllGather = (decltype(g_api.AllGather))sym("ncclAllGather");
     g_api.Send = (decltype(g_api.Send))sym("ncclSend");
     g_api.Recv = (decltype(g_api.Recv))sym("ncclRecv");
     g_api.GroupStart = (decltype(g_api.GroupStart))sym("ncclGroupStart");
@@ -93,6 +95,10 @@ void comm_send(Comm *c, const void *buf, size_t bytes, int peer, cudaStream_t st
 void comm_recv(Comm *c, void *buf, size_t bytes, int peer, cudaStream_t st) {
     if (bytes == 0) return;
     check(g_api.Recv(buf, bytes, ncclChar, peer, c->comm, st), "ncclRecv");
+}
+
+void comm_allgather_f32(Comm *c, const float *send, float *recv, size_t countPerRank, cudaStream_t st) {
+    check(g_api.AllGather(send, recv, countPerRank, ncclFloat32, c->comm, st), "ncclAllGather");
 }
 
 void comm_allreduce(Comm *c, void *buf, size_t count, int kind, cudaStream_t st) {

@@ -240,6 +240,7 @@ void comm_send(Comm *, const void *buf, size_t bytes, int peer, cudaStream_t st)
 void comm_recv(Comm *, void *buf, size_t bytes, int peer, cudaStream_t st);
 enum { COMM_SUM_F64 = 0, COMM_MAX_U64 = 1, COMM_SUM_I32 = 2, COMM_MAX_U32 = 3 };
 void comm_allreduce(Comm *, void *buf, size_t count, int kind, cudaStream_t st);
+void comm_allgather_f32(Comm *, const float *send, float *recv, size_t countPerRank, cudaStream_t st);
 
 // slab.cu: halo exchanges between neighbouring slabs
 void slab_exchange_ghosts(flip_ctx *c);                 // ghost particles within `halo` planes, then re-sort

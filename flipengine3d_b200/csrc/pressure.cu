@@ -17,6 +17,7 @@
 #include <cooperative_groups.h>
 #include <cub/device/device_scan.cuh>
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <utility>
 #include "device_math.cuh"
@@ -393,6 +394,8 @@ __device__ __forceinline__ float mg_offsum(const MgLevel &L, const float *x, int
 // x + scale * (P e)(c) at a cell and at its six neighbours is what the fused prolongation+sweep reads
 __device__ __forceinline__ float mg_corrected(const MgLevel &L, const MgLevel &C, const float *x, const float *e,
                                               float scale, int c, int i, int j, int k) {
+    // an inactive cell (no row below it: outside the liquid, or beyond a z-slab cut) stays zero
+    if (L.invD[c] == 0.0f) return 0.0f;
     return x[c] + scale * e[(i >> 1) + C.sj * (j >> 1) + C.sk * (k >> 1)];
 }
 
@@ -550,13 +553,15 @@ __device__ __forceinline__ float mg0_offsum_corr(const Mg0 &M, const MgLevel &C,
     int pi = i >> 1, pj = C.sj * (j >> 1), pk = C.sk * (k >> 1);
     float e0 = e[pi + pj + C.sk * ((k - 1) >> 1)], e1 = e[pi + C.sj * ((j - 1) >> 1) + pk], e2 = e[((i - 1) >> 1) + pj + pk];
     float e3 = e[((i + 1) >> 1) + pj + pk], e4 = e[pi + C.sj * ((j + 1) >> 1) + pk], e5 = e[pi + pj + C.sk * ((k + 1) >> 1)];
+    // rows of a neighbouring z-slab (beyond the cut) take no part in the block-local correction
+    const bool own0 = (k - 1 >= M.g.kOwn0), own5 = (k + 1 < M.g.kOwn1);
     float s = 0.0f;
-    s += (a0 != 0.0f) ? a0 * (x0 + scale * e0) : 0.0f;
+    s += (a0 != 0.0f && own0) ? a0 * (x0 + scale * e0) : 0.0f;
     s += (a1 != 0.0f) ? a1 * (x1 + scale * e1) : 0.0f;
     s += (a2 != 0.0f) ? a2 * (x2 + scale * e2) : 0.0f;
     s += (a3 != 0.0f) ? a3 * (x3 + scale * e3) : 0.0f;
     s += (a4 != 0.0f) ? a4 * (x4 + scale * e4) : 0.0f;
-    s += (a5 != 0.0f) ? a5 * (x5 + scale * e5) : 0.0f;
+    s += (a5 != 0.0f && own5) ? a5 * (x5 + scale * e5) : 0.0f;
     return M.fac * s;
 }
 
@@ -636,6 +641,7 @@ __global__ void k_mg_coarsen0(Mg0 M, MgLevel C) {
         if (!((M.rowBits[c >> 5] >> (c & 31)) & 1u)) continue;
         d += (float)M.Adiag[c];
         float au = M.fac * M.oU[c], av = M.fac * M.oV[c], aw = M.fac * M.oW[c];
+        if (qk == 0 && k + 1 >= M.g.kOwn1) aw = 0.0f;   // partner inside the aggregate belongs to another z-slab
         if (qi == 0) d -= 2.0f * au; else u += au;
         if (qj == 0) d -= 2.0f * av; else v += av;
         if (qk == 0) d -= 2.0f * aw; else w += aw;
@@ -666,6 +672,13 @@ __global__ void k_mg_coarsen(MgLevel F, MgLevel C) {
     C.diag[cc] = d;
     C.invD[cc] = (d > 0.0f) ? 1.0f / d : 0.0f;
     C.oU[cc] = u; C.oV[cc] = v; C.oW[cc] = w;
+}
+
+__global__ void k_mg_invdiag(MgLevel L) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= L.n) return;
+    float d = L.diag[c];
+    L.invD[c] = (d > 0.0f) ? 1.0f / d : 0.0f;
 }
 
 // s = z on rows (start of PCG with a preconditioner that produced z in separate passes)
@@ -1072,6 +1085,13 @@ struct PressureScratch {
     MgLevel lv[MG_MAX_LEVELS];         // lv[0]: only invD, x, x2 are used (dense over cells)
     float *pool = nullptr;             // one allocation behind all level arrays
     int coopBlocks = 0;                // grid of the persistent solver (SMs x resident CTAs)
+    // z-slabs: levels >= Lc span the WHOLE domain and are held (redundantly) by every rank; the
+    // restricted residual of level Lc is all-gathered once per V-cycle.  Lc == 0: every level is local.
+    int Lc = 0;
+    int gLevels = 0;                   // total number of levels when Lc > 0 (levels Lc..gLevels-1 are in glv)
+    int gFirstSmall = 0;
+    MgLevel glv[MG_MAX_LEVELS];
+    float *gpool = nullptr;
 };
 
 void pressure_alloc(flip_ctx *c) {
@@ -1140,6 +1160,44 @@ void pressure_alloc(flip_ctx *c) {
             }
         }
     }
+    // z-slabs: global coarse levels from level Lc on, if the slab boundaries are aligned to 2^Lc planes
+    ps->Lc = 0;
+    if (slab_on(c)) {
+        int Lc = 3;
+        if (const char *e = getenv("FLIP_MG_GLOBAL_FROM")) Lc = std::max(0, std::min(6, atoi(e)));   // tuning knob
+        auto aligned = [&](int l) {
+            int m = (1 << l) - 1;
+            return !(d.kOff & m) && !(d.kOwn0 & m) && !(d.kOwn1 & m) && !(d.K & m) && !(d.Kg & m) && (d.Kg % c->nranks) == 0 &&
+                   !((d.Kg / c->nranks) & m);
+        };
+        while (Lc > 0 && (!aligned(Lc) || Lc >= ps->numLevels)) Lc--;
+        ps->Lc = Lc;
+        if (Lc > 0) {
+            int I = ps->lv[Lc].I, J = ps->lv[Lc].J, K = d.Kg >> Lc;
+            int L = Lc;
+            size_t total = 0;
+            while (L < MG_MAX_LEVELS) {
+                MgLevel &lv = ps->glv[L];
+                lv.I = I; lv.J = J; lv.K = K; lv.sj = I; lv.sk = I * J; lv.n = I * J * K;
+                total += 8 * ((size_t)lv.n + 64);
+                L++;
+                if (I <= 2 && J <= 2 && K <= 2) break;
+                I = (I + 1) / 2; J = (J + 1) / 2; K = (K + 1) / 2;
+            }
+            ps->gLevels = L;
+            FLIP_CUDA_CHECK(cudaMalloc(&ps->gpool, sizeof(float) * total));
+            FLIP_CUDA_CHECK(cudaMemset(ps->gpool, 0, sizeof(float) * total));
+            float *q = ps->gpool;
+            ps->gFirstSmall = 0;
+            for (int l = Lc; l < L; l++) {
+                MgLevel &lv = ps->glv[l];
+                size_t np = (size_t)lv.n + 64;
+                lv.invD = q; q += np; lv.x = q; q += np; lv.x2 = q; q += np; lv.diag = q; q += np;
+                lv.oU = q; q += np; lv.oV = q; q += np; lv.oW = q; q += np; lv.b = q; q += np;
+                if (ps->gFirstSmall == 0 && lv.n <= MG_SMALL) ps->gFirstSmall = l;
+            }
+        }
+    }
 }
 
 void pressure_free(flip_ctx *c) {
@@ -1148,7 +1206,7 @@ void pressure_free(flip_ctx *c) {
     cudaFree(c->vx_); cudaFree(c->vr); cudaFree(c->vs); cudaFree(c->vz); cudaFree(c->vb);
     if (c->mg) {
         PressureScratch *ps = (PressureScratch *)c->mg;
-        cudaFree(ps->maskAll); cudaFree(ps->flagAll); cudaFree(ps->posAll); cudaFree(ps->pool);
+        cudaFree(ps->maskAll); cudaFree(ps->flagAll); cudaFree(ps->posAll); cudaFree(ps->pool); cudaFree(ps->gpool);
         delete ps;
         c->mg = nullptr;
     }
@@ -1241,32 +1299,70 @@ void stage_pressure(flip_ctx *c, double dt) {
         size_t ktB = kt_begin(c);
         k_mg0_build<<<segBlocks, TPB, 0, st>>>(c->segCell, c->segMask, c->Adiag, ps->lv[0].invD, c->dS); c->launches++;
         k_mg_coarsen0<<<cdiv(ps->lv[1].n, TPB), TPB, 0, st>>>(m0, ps->lv[1]); c->launches++;
-        for (int l = 1; l + 1 < ps->numLevels; l++) {
-            k_mg_coarsen<<<cdiv(ps->lv[l + 1].n, TPB), TPB, 0, st>>>(ps->lv[l], ps->lv[l + 1]); c->launches++;
+        const int Lc = slab ? ps->Lc : 0;
+        if (Lc == 0) {
+            for (int l = 1; l + 1 < ps->numLevels; l++) {
+                k_mg_coarsen<<<cdiv(ps->lv[l + 1].n, TPB), TPB, 0, st>>>(ps->lv[l], ps->lv[l + 1]); c->launches++;
+            }
+        } else {
+            for (int l = 1; l < Lc; l++) {
+                k_mg_coarsen<<<cdiv(ps->lv[l + 1].n, TPB), TPB, 0, st>>>(ps->lv[l], ps->lv[l + 1]); c->launches++;
+            }
+            // every rank contributes the operator rows of its owned coarse planes
+            MgLevel &Ll = ps->lv[Lc], &Gl = ps->glv[Lc];
+            size_t off = (size_t)(d.kOwn0 >> Lc) * Ll.sk, cnt = (size_t)((d.kOwn1 - d.kOwn0) >> Lc) * Ll.sk;
+            comm_allgather_f32(c->comm, Ll.diag + off, Gl.diag, cnt, st);
+            comm_allgather_f32(c->comm, Ll.oU + off, Gl.oU, cnt, st);
+            comm_allgather_f32(c->comm, Ll.oV + off, Gl.oV, cnt, st);
+            comm_allgather_f32(c->comm, Ll.oW + off, Gl.oW, cnt, st);
+            k_mg_invdiag<<<cdiv(Gl.n, TPB), TPB, 0, st>>>(Gl); c->launches++;
+            for (int l = Lc; l + 1 < ps->gLevels; l++) {
+                k_mg_coarsen<<<cdiv(ps->glv[l + 1].n, TPB), TPB, 0, st>>>(ps->glv[l], ps->glv[l + 1]); c->launches++;
+            }
         }
         kt_end(c, FLIP_KERNEL_PRESSURE_BUILD, ktB);
     }
+    // effective level table: local levels below Lc, global (replicated) levels from Lc on
+    const int Lc = (slab && useMg) ? ps->Lc : 0;
+    const int L = Lc ? ps->gLevels : ps->numLevels;
+    MgLevel *LV[MG_MAX_LEVELS];
+    for (int l = 0; l < L; l++) LV[l] = (Lc && l >= Lc) ? &ps->glv[l] : &ps->lv[l];
+    const int fsCfg = Lc ? ps->gFirstSmall : ps->firstSmall;
+    const int fs = fsCfg ? std::max(fsCfg, std::max(Lc, 1)) : L;    // first level run by the single-CTA kernel
+    // what level l sees of level l+1: the descriptor its parent indices refer to, and the coarse solution
+    auto up_desc = [&](int l) -> MgLevel & { return (Lc && l + 1 == Lc) ? ps->lv[Lc] : *LV[l + 1]; };
+    auto up_x = [&](int l) -> const float * {
+        if (Lc && l + 1 == Lc) return ps->glv[Lc].x + (size_t)(d.kOff >> Lc) * ps->lv[Lc].sk;
+        return LV[l + 1]->x;
+    };
+    // after restricting into level l+1: the global level needs every rank's owned planes
+    auto after_restrict = [&](int l) {
+        if (Lc && l + 1 == Lc) {
+            MgLevel &Ll = ps->lv[Lc], &Gl = ps->glv[Lc];
+            size_t off = (size_t)(d.kOwn0 >> Lc) * Ll.sk, cnt = (size_t)((d.kOwn1 - d.kOwn0) >> Lc) * Ll.sk;
+            comm_allgather_f32(c->comm, Ll.b + off, Gl.b, cnt, st);
+        }
+    };
     // one V-cycle: z = M^-1 r, rho[rhoSlot] += z.r
     auto vcycle = [&](int rhoSlot) {
-        const int L = ps->numLevels;
-        const int fs = ps->firstSmall ? ps->firstSmall : L;      // first level run by the single-CTA kernel
         const int nu = mp.nu;
         size_t ktV = kt_begin(c);
         // ---- down
-        {   // level 0 pre-smoothing, result in cur0
+        {   // level 0 pre-smoothing
             float *xa = ps->lv[0].x, *xb = ps->lv[0].x2;
             for (int sw = 0; sw < nu; sw++) {
-                k_mg0_sweep<<<segBlocks, TPB, 0, st>>>(c->segCell, c->segMask, m0, ps->lv[1], c->vr, xa, nullptr, xb, mp.omega,
+                k_mg0_sweep<<<segBlocks, TPB, 0, st>>>(c->segCell, c->segMask, m0, up_desc(0), c->vr, xa, nullptr, xb, mp.omega,
                                                       mp.scale, sw == 0 ? 0 : 1, 0, nullptr, c->dS, 0);
                 c->launches++;
                 std::swap(xa, xb);
             }
             // xa holds the result
-            k_mg0_restrict<<<cdiv(ps->lv[1].n, TPB), TPB, 0, st>>>(m0, ps->lv[1], c->vr, xa, c->dS); c->launches++;
+            k_mg0_restrict<<<cdiv(up_desc(0).n, TPB), TPB, 0, st>>>(m0, up_desc(0), c->vr, xa, c->dS); c->launches++;
             ps->lv[0].x = xa; ps->lv[0].x2 = xb;
+            after_restrict(0);
         }
         for (int l = 1; l < fs && l < L - 1; l++) {
-            MgLevel &lv = ps->lv[l];
+            MgLevel &lv = *LV[l];
             float *xa = lv.x, *xb = lv.x2;
             for (int sw = 0; sw < nu; sw++) {
                 k_mg_sweep<<<cdiv(lv.n, TPB), TPB, 0, st>>>(lv, lv, xa, nullptr, xb, mp.omega, mp.scale, sw == 0 ? 0 : 1, c->dS);
@@ -1274,16 +1370,17 @@ void stage_pressure(flip_ctx *c, double dt) {
                 std::swap(xa, xb);
             }
             lv.x = xa; lv.x2 = xb;
-            k_mg_restrict<<<cdiv(ps->lv[l + 1].n, TPB), TPB, 0, st>>>(lv, ps->lv[l + 1], lv.x, c->dS); c->launches++;
+            k_mg_restrict<<<cdiv(up_desc(l).n, TPB), TPB, 0, st>>>(lv, up_desc(l), lv.x, c->dS); c->launches++;
+            after_restrict(l);
         }
         // ---- bottom: small levels in one CTA, or coarsest-level sweeps
         if (fs < L) {
             MgSmallArgs A;
-            for (int l = 0; l < L; l++) A.lv[l] = ps->lv[l];
+            for (int l = 0; l < L; l++) A.lv[l] = *LV[l];
             A.first = fs; A.last = L - 1; A.p = mp;
             k_mg_small<<<1, 1024, 0, st>>>(A, c->dS); c->launches++;
         } else {
-            MgLevel &lv = ps->lv[L - 1];
+            MgLevel &lv = *LV[L - 1];
             float *xa = lv.x, *xb = lv.x2;
             for (int sw = 0; sw < mp.coarseSweeps; sw++) {
                 k_mg_sweep<<<cdiv(lv.n, TPB), TPB, 0, st>>>(lv, lv, xa, nullptr, xb, mp.omega, mp.scale, sw == 0 ? 0 : 1, c->dS);
@@ -1295,10 +1392,10 @@ void stage_pressure(flip_ctx *c, double dt) {
         // ---- up
         int top = (fs < L ? fs : L - 1) - 1;     // highest-numbered level handled by per-level launches on the way up
         for (int l = top; l >= 1; l--) {
-            MgLevel &lv = ps->lv[l];
+            MgLevel &lv = *LV[l];
             float *xa = lv.x, *xb = lv.x2;
             for (int sw = 0; sw < nu; sw++) {
-                k_mg_sweep<<<cdiv(lv.n, TPB), TPB, 0, st>>>(lv, ps->lv[l + 1], xa, ps->lv[l + 1].x, xb, mp.omega, mp.scale,
+                k_mg_sweep<<<cdiv(lv.n, TPB), TPB, 0, st>>>(lv, up_desc(l), xa, up_x(l), xb, mp.omega, mp.scale,
                                                           sw == 0 ? 2 : 1, c->dS);
                 c->launches++;
                 std::swap(xa, xb);
@@ -1309,7 +1406,7 @@ void stage_pressure(flip_ctx *c, double dt) {
             float *xa = ps->lv[0].x, *xb = ps->lv[0].x2;
             for (int sw = 0; sw < nu; sw++) {
                 int last = (sw == nu - 1) ? 1 : 0;
-                k_mg0_sweep<<<segBlocks, TPB, 0, st>>>(c->segCell, c->segMask, m0, ps->lv[1], c->vr, xa, ps->lv[1].x, xb, mp.omega,
+                k_mg0_sweep<<<segBlocks, TPB, 0, st>>>(c->segCell, c->segMask, m0, up_desc(0), c->vr, xa, up_x(0), xb, mp.omega,
                                                       mp.scale, sw == 0 ? 2 : 1, last, c->vz, c->dS, rhoSlot);
                 c->launches++;
                 std::swap(xa, xb);
