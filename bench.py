@@ -119,22 +119,23 @@ class quiet_stdout:
         os.close(self.saved)
 
 
-def workload(grid):
+def workload(grid, name="spheredrop", krange=None):
     from flipengine3d_b200 import scenes
-    sc = scenes.sphere_drop(grid)
-    return sc
+    if name == "dambreak":
+        return scenes.dam_break(grid, krange=krange)
+    return scenes.sphere_drop(grid)
 
 
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the unmodified reference engine on the host cores
 # ------------------------------------------------------------------------------------------------
-def run_reference(grid, steps, warmup, threads=None):
+def run_reference(grid, steps, warmup, threads=None, name="spheredrop"):
     """Returns (particle_steps_per_s, ms_per_step, info). One step = one update(1/30)."""
     from oracle import refengine
     kind = "fast" if refengine.available("fast") else "golden"
     if not refengine.available(kind):
         raise RuntimeError("oracle/_ref is not built (run __graft_entry__.build() where /root/reference exists)")
-    sc = workload(grid)
+    sc = workload(grid, name)
     with quiet_stdout():
         ref = refengine.RefEngine(sc["dims"], sc["dx"], sc["pos"], sc["vel"], kind=kind, threads=threads)
         cores = ref.L.ref_get_threads()
@@ -147,7 +148,7 @@ def run_reference(grid, steps, warmup, threads=None):
             psteps += n_before * max(ref.substeps, 1)
         el = time.perf_counter() - t0
     info = dict(kind="reference", cores=int(cores), build=kind,
-                substeps_per_frame=int(ref.substeps), sample=f"spheredrop{grid} ({sc['pos'].shape[0]} particles, same seeding rule as the GPU workload), "
+                substeps_per_frame=int(ref.substeps), sample=f"{name}{grid} ({sc['pos'].shape[0]} particles, same seeding rule as the GPU workload), "
                        f"{steps} frame(s) of update(1/30) after {warmup} warm-up frame(s), surface reconstruction off")
     ref.close()
     return psteps / el, 1e3 * el / max(steps, 1), info
@@ -156,11 +157,13 @@ def run_reference(grid, steps, warmup, threads=None):
 def reference_arm(args, rank, world):
     if rank != 0:
         return
-    v, ms, info = run_reference(args.ref_grid, args.steps, args.warmup)
+    wl = args.workload or ("spheredrop" if args.gpus == 1 else "dambreak")
+    v, ms, info = run_reference(args.ref_grid, args.steps, args.warmup, name=wl)
+    grid_name = (f"{wl}256" if args.gpus == 1 else f"{wl}512") if args.workload is None else f"{args.workload}{args.grid}"
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 fields / f64 PCG", "data": "synthetic",
-            "config": {"workload": f"spheredrop{args.grid}", "sample_grid": args.ref_grid, "dx": 0.125,
+            "config": {"workload": grid_name, "sample_grid": args.ref_grid, "dx": 0.125,
                        "frame_dt": FRAME_DT, "step": "one frame = FluidSimulation::update(1/30)"},
             "cpu_baseline": dict(info, value=v, unit=UNIT),
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -196,25 +199,75 @@ def algorithmic_bytes(Np, dims, n_rows, nf_liq):
     }
 
 
+def make_sim(args, wl_name, grid, rank, world, local_rank, dist):
+    """One context per rank; with world > 1 the domain is split into z-slabs (flip_set_slab)."""
+    from flipengine3d_b200 import engine as fe
+    I = J = K = grid
+    sim = fe.FluidSimulation(I, J, K, 0.125, device=local_rank)
+    sim.addBodyForce(0.0, -25.0, 0.0)
+    if args.preconditioner:
+        sim.setPreconditioner(args.preconditioner)
+    krange = None
+    if world > 1:
+        ident = [fe.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ident, src=0)
+        sim.setSlab(rank, world, ident[0])
+        krange = fe.slab_range(K, world, rank)
+    sc = workload(grid, wl_name, krange=krange)
+    sim.loadMarkerParticleData(fe.MarkerParticleData(sc["pos"], sc["vel"]))
+    sim.initialize()
+    return sim, sc
+
+
+def timed_frames(sim, steps, stream, torch, barrier):
+    """K frames with the state resident in HBM; returns (ms, particle-steps, substeps, pcg its, rows, stage_ms)."""
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    psteps, substeps, pcg_iters, rows = 0, 0, 0, []
+    stage_ms = {}
+    for _ in range(steps):
+        sim.update(FRAME_DT)
+        for st in sim.substep_stats():
+            # particles that went through the substep = survivors + those removed at its end (global counts)
+            psteps += st["particles"] + st["removed_solid"] + st["removed_crowded"] + st["removed_fast"]
+            substeps += 1
+            pcg_iters += st["pcg_iterations"]
+            rows.append(st["pressure_rows"])
+        for k, v in sim.stage_times_ms().items():
+            stage_ms[k] = stage_ms.get(k, 0.0) + v
+    e1.record(stream)
+    barrier()
+    return e0.elapsed_time(e1), psteps, substeps, pcg_iters, rows, stage_ms
+
+
 def ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
-    from flipengine3d_b200 import engine as fe
 
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device: libflip_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    wl_name, grid = args.workload, args.grid
+    if wl_name is None:
+        wl_name, grid = ("spheredrop", 256) if world == 1 else ("dambreak", 512)
 
-    sc = workload(args.grid)
+    def maxreduce(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sumreduce(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    sim, sc = make_sim(args, wl_name, grid, rank, world, local_rank, dist)
     I, J, K = sc["dims"]
-    sim = fe.FluidSimulation(I, J, K, sc["dx"], device=local_rank)
-    sim.addBodyForce(0.0, -25.0, 0.0)
-    if args.preconditioner:
-        sim.setPreconditioner(args.preconditioner)
-    sim.loadMarkerParticleData(fe.MarkerParticleData(sc["pos"], sc["vel"]))
-    sim.initialize()
     stream = torch.cuda.ExternalStream(sim.stream(), device=torch.device("cuda", local_rank))
 
     def barrier():
@@ -233,42 +286,18 @@ def ours(args, rank, world, local_rank):
     sim.enable_kernel_timing(True)
     sim.reset_kernel_timing()
     launches0 = sim.kernel_launches()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record(stream)
-    psteps, substeps, pcg_iters, rows = 0, 0, 0, []
-    stage_ms = {}
-    for _ in range(args.steps):
-        sim.update(FRAME_DT)
-        n_in = None
-        for st in sim.substep_stats():
-            # particles that went through the substep = survivors + those removed at its end
-            n_in = st["particles"] + st["removed_solid"] + st["removed_crowded"] + st["removed_fast"]
-            psteps += n_in
-            substeps += 1
-            pcg_iters += st["pcg_iterations"]
-            rows.append(st["pressure_rows"])
-        for k, v in sim.stage_times_ms().items():
-            stage_ms[k] = stage_ms.get(k, 0.0) + v
-    e1.record(stream)
-    barrier()
-    ms = e0.elapsed_time(e1)
+    ms, psteps, substeps, pcg_iters, rows, stage_ms = timed_frames(sim, args.steps, stream, torch, barrier)
     launches = sim.kernel_launches() - launches0
     kt = sim.kernel_timing()
     sim.enable_kernel_timing(False)
     clocks = sampler.stop()
+    ms_max = maxreduce(ms)
+    launches_all = sumreduce(float(launches))
+    value = psteps / (ms_max * 1e-3)      # particle counts in the step stats are global
 
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    tot = torch.tensor([float(psteps), float(launches)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    ms_max = float(t.item())
-    value = float(tot[0].item()) / (ms_max * 1e-3)
-
-    # ---- e2e leg: the same frames through the C-ABI with host buffers
-    Np = sim.getNumMarkerParticles()
-    host = torch.empty((Np + 4096, 6), dtype=torch.float32).pin_memory().numpy()
+    # ---- e2e leg: the same frames through the C-ABI with host buffers (each rank moves its own slab's particles)
+    Np_local = sim.getNumMarkerParticles()
+    host = torch.empty((Np_local + Np_local // 4 + 65536, 6), dtype=torch.float32).pin_memory().numpy()
     sim.getMarkerParticles(out=host)
     barrier()
     e2e_psteps, h2d, d2h = 0, 0, 0
@@ -281,68 +310,96 @@ def ours(args, rank, world, local_rank):
         for st in sim.substep_stats():
             e2e_psteps += st["particles"] + st["removed_solid"] + st["removed_crowded"] + st["removed_fast"]
         n = sim.getNumMarkerParticles()
+        if n > host.shape[0]:
+            host = torch.empty((n + n // 4, 6), dtype=torch.float32).pin_memory().numpy()
         sim.getMarkerParticles(out=host)             # device -> host (pinned)
         d2h += n * 24
     sim.synchronize()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    tp = torch.tensor([float(e2e_psteps)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tp, op=dist.ReduceOp.SUM)
-    e2e_value = float(tp.item()) / float(te.item())
+    e2e_s = maxreduce(time.perf_counter() - t0)
+    e2e_value = e2e_psteps / e2e_s
+    h2d_all, d2h_all = sumreduce(float(h2d)), sumreduce(float(d2h))
+    Np = int(sumreduce(float(Np_local)))
 
+    line = None
     if rank == 0:
         peak, peak_kind = measured_hbm_peak()
         n_rows = int(np.mean(rows)) if rows else 0
-        nf_liq = liquid_face_count(sim.array("liquid_phi"))
-        ab = algorithmic_bytes(Np, (I, J, K), n_rows, nf_liq)
-        kernels = {}
-        for name, (tot_ms, n) in kt.items():
-            if n == 0:
-                continue
-            avg_ms = tot_ms / n
-            ent = {"launches": int(n), "avg_ms": avg_ms, "total_ms": tot_ms, "share_of_step": tot_ms / ms}
-            if name in ab:
-                gbs = ab[name] / (avg_ms * 1e-3) / 1e9
-                ent.update(algorithmic_bytes=int(ab[name]), achieved_gbs=gbs, frac=gbs / peak)
-            kernels[name] = ent
-        # the dominant kernel: largest share of the step among single-kernel classes
-        singles = [k for k in ("sdf_p2g", "g2p", "advance", "pcg_spmv") if k in kernels]
-        dom = max(singles, key=lambda k: kernels[k]["total_ms"])
-        roof = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["achieved_gbs"], "peak": peak,
-                "peak_kind": peak_kind, "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": None,
-                "algorithmic_bytes": kernels[dom]["algorithmic_bytes"], "avg_launch_ms": kernels[dom]["avg_ms"],
-                "share_of_step": kernels[dom]["share_of_step"]}
-        tp_file = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tp_file):
-            try:
-                roof["traffic"] = json.load(open(tp_file)).get(dom)
-            except Exception:
-                pass
-        cpu = None
-        if world == 1 or True:
-            try:
-                v, cms, info = run_reference(args.ref_grid, args.cpu_steps, 1)
-                cpu = dict(info, value=v, unit=UNIT, ms_per_step=cms)
-            except Exception as e:   # the oracle always exists on the GPU box; report loudly if not
-                cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"FAILED: {e}"}
+        kernels, roof = {}, None
+        if world == 1:
+            nf_liq = liquid_face_count(sim.array("liquid_phi"))
+            ab = algorithmic_bytes(Np, (I, J, K), n_rows, nf_liq)
+            for name, (tot_ms, n) in kt.items():
+                if n == 0:
+                    continue
+                avg_ms = tot_ms / n
+                ent = {"launches": int(n), "avg_ms": avg_ms, "total_ms": tot_ms, "share_of_step": tot_ms / ms}
+                if name in ab:
+                    gbs = ab[name] / (avg_ms * 1e-3) / 1e9
+                    ent.update(algorithmic_bytes=int(ab[name]), achieved_gbs=gbs, frac=gbs / peak)
+                kernels[name] = ent
+            # the dominant kernel: largest share of the step among single-kernel classes
+            singles = [k for k in ("sdf_p2g", "g2p", "advance", "pcg_spmv") if k in kernels]
+            dom = max(singles, key=lambda k: kernels[k]["total_ms"])
+            roof = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["achieved_gbs"], "peak": peak,
+                    "peak_kind": peak_kind, "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": None,
+                    "algorithmic_bytes": kernels[dom]["algorithmic_bytes"], "avg_launch_ms": kernels[dom]["avg_ms"],
+                    "share_of_step": kernels[dom]["share_of_step"]}
+            tp_file = os.path.join(ROOT, "profiles", "traffic.json")
+            if os.path.exists(tp_file):
+                try:
+                    roof["traffic"] = json.load(open(tp_file)).get(dom)
+                except Exception:
+                    pass
+        else:
+            for name, (tot_ms, n) in kt.items():
+                if n:
+                    kernels[name] = {"launches": int(n), "avg_ms": tot_ms / n, "total_ms": tot_ms, "share_of_step": tot_ms / ms,
+                                     "note": "rank 0's slab"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32 fields / f64 PCG vectors", "data": "synthetic",
-                "config": {"workload": f"spheredrop{args.grid}", "grid": [I, J, K], "dx": sc["dx"], "particles": int(Np),
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32 fields / f64 PCG vectors", "data": "synthetic",
+                "config": {"workload": f"{wl_name}{grid}", "grid": [I, J, K], "dx": 0.125, "particles": Np,
                            "frame_dt": FRAME_DT, "step": "one frame = flip_update(1/30), all CFL substeps",
                            "substeps_timed": substeps, "pcg_iterations_timed": pcg_iters, "pressure_rows": n_rows,
-                           "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (z-slab decomposition not built yet)",
-                           "l2": "inputs larger than L2 (particles 386 MB, each MAC field 202 MB vs 126 MB L2)"},
+                           "parallelism": "single GPU" if world == 1 else f"{world} z-slabs (one process per GPU, NCCL halo exchange, distributed PCG)",
+                           "l2": "inputs larger than L2 (particles and each MAC field exceed the 126 MB L2)",
+                           "note": "N=1 runs the single-GPU headline config (spheredrop256); N>1 runs dambreak512 split into "
+                                   "z-slabs (fixed total work); the N=1 point of that series is in scaling_ref"},
                 "roofline": roof, "kernels": kernels, "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
-                "cpu_baseline": cpu,
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // args.steps,
-                        "d2h_bytes_per_step": d2h // args.steps, "ms_per_step": 1e3 * float(te.item()) / args.steps},
-                "gpu_launches": int(tot[1].item()), "clocks": clocks}
-        print(json.dumps(line), flush=True)
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_all) // args.steps,
+                        "d2h_bytes_per_step": int(d2h_all) // args.steps, "ms_per_step": 1e3 * e2e_s / args.steps},
+                "gpu_launches": int(launches_all), "clocks": clocks}
     sim.close()
+    del sim
+
+    # ---- N=1 only: the single-GPU point of the 512^3 strong-scaling series, and the CPU baseline
+    if world == 1 and rank == 0:
+        if args.scaling_ref and args.workload is None:
+            try:
+                sim2, sc2 = make_sim(args, "dambreak", 512, 0, 1, local_rank, dist)
+                stream2 = torch.cuda.ExternalStream(sim2.stream(), device=torch.device("cuda", local_rank))
+
+                def barrier2():
+                    sim2.synchronize()
+                    torch.cuda.synchronize()
+                for _ in range(3):
+                    sim2.update(FRAME_DT)
+                ms2, ps2, sub2, it2, rows2, _ = timed_frames(sim2, args.ref_steps, stream2, torch, barrier2)
+                line["scaling_ref"] = {"workload": "dambreak512", "n_gpus": 1, "value": ps2 / (ms2 * 1e-3), "unit": UNIT,
+                                       "ms_per_step": ms2 / args.ref_steps, "steps": args.ref_steps, "warmup": 3,
+                                       "particles": int(sim2.getNumMarkerParticles()), "pcg_iterations_timed": it2}
+                sim2.close()
+            except Exception as e:
+                line["scaling_ref"] = {"workload": "dambreak512", "error": str(e)[:200]}
+        try:
+            v, cms, info = run_reference(args.ref_grid, args.cpu_steps, 1)
+            line["cpu_baseline"] = dict(info, value=v, unit=UNIT, ms_per_step=cms)
+        except Exception as e:   # the oracle always exists on the GPU box; report loudly if not
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"FAILED: {e}"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -352,7 +409,12 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--grid", type=int, default=256, help="sphere-drop grid size (headline: 256)")
+    ap.add_argument("--workload", default=None, choices=[None, "spheredrop", "dambreak"],
+                    help="default: spheredrop256 on 1 GPU, dambreak512 in z-slabs on N > 1")
+    ap.add_argument("--grid", type=int, default=256, help="grid size when --workload is given")
+    ap.add_argument("--no-scaling-ref", dest="scaling_ref", action="store_false",
+                    help="skip the single-GPU dambreak512 point of the strong-scaling series (N=1 runs only)")
+    ap.add_argument("--ref-steps", type=int, default=4, help="timed frames of that reference point")
     ap.add_argument("--ref-grid", type=int, default=128,
                     help="grid of the bounded CPU sample of the same workload (reference arm / cpu_baseline)")
     ap.add_argument("--cpu-steps", type=int, default=3, help="frames of the cpu_baseline sample in our arm")

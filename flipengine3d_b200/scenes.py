@@ -14,12 +14,27 @@ GRAVITY = (0.0, -25.0, 0.0)
 FRAME_DT = 1.0 / 30.0
 
 
-def lcg_uniform(n, seed):
-    """n numbers in [0,1): s <- s*1664525 + 1013904223 (mod 2^32), bits 8..23 of each state."""
+def _lcg_jump(k):
+    """(A, C) with s_{i+k} = A*s_i + C (mod 2^32) for the LCG below."""
+    M = 0xFFFFFFFF
+    A, C = 1, 0
+    a, c = 1664525, 1013904223
+    while k:
+        if k & 1:
+            A, C = (A * a) & M, (C * a + c) & M
+        a, c = (a * a) & M, (c * a + c) & M
+        k >>= 1
+    return A, C
+
+
+def lcg_uniform(n, seed, skip=0):
+    """n numbers in [0,1): s <- s*1664525 + 1013904223 (mod 2^32), bits 8..23 of each state; `skip`
+    leading numbers of the sequence are jumped over (so a z-slab can generate just its own part)."""
     a, c = np.uint64(1664525), np.uint64(1013904223)
     mask = np.uint64(0xFFFFFFFF)
     out = np.empty(max(n, 1), dtype=np.uint64)
-    out[0] = (np.uint64(seed) * a + c) & mask
+    A0, C0 = _lcg_jump(int(skip) + 1)
+    out[0] = np.uint64((A0 * int(seed) + C0) & 0xFFFFFFFF)
     filled = 1
     A, C = a, c  # jump by `filled` steps: s_{i+filled} = A*s_i + C
     while filled < n:
@@ -32,15 +47,16 @@ def lcg_uniform(n, seed):
     return bits.astype(np.float64) / 65536.0
 
 
-def seed_cells(cells_ijk, dx, seed, velocity=None):
-    """cells_ijk: (M,3) int array in the order the particles are emitted. Returns (pos, vel) float32."""
+def seed_cells(cells_ijk, dx, seed, velocity=None, skip_cells=0):
+    """cells_ijk: (M,3) int array in the order the particles are emitted. Returns (pos, vel) float32.
+    skip_cells: number of cells of the full scene that precede cells_ijk (jitter sequence offset)."""
     cells = np.asarray(cells_ijk, dtype=np.int64).reshape(-1, 3)
     m = cells.shape[0]
     q = 0.25 * dx
     sub = np.array([[sx, sy, sz] for sz in (-q, q) for sy in (-q, q) for sx in (-q, q)], dtype=np.float64)
     centre = (cells.astype(np.float64) + 0.5) * dx
     pos = centre[:, None, :] + sub[None, :, :]
-    jit = lcg_uniform(m * 8 * 3, seed).reshape(m, 8, 3)
+    jit = lcg_uniform(m * 8 * 3, seed, skip=skip_cells * 24).reshape(m, 8, 3)
     pos = pos + 0.05 * q * (jit - 0.5)
     pos = pos.reshape(-1, 3).astype(np.float32)
     vel = np.zeros_like(pos)
@@ -62,14 +78,23 @@ def default_scene(n=30, seed=12344):
     return dict(name=f"default{n}", dims=(n, n, n), dx=DX, pos=pos, vel=vel)
 
 
-def dam_break(n=128, seed=12345):
-    """Config 2 (n=128) / config 5 (n=512): column i∈[3s,35s) j∈[3s,67s) k∈[3s,n-3s), s=n/128."""
+def dam_break(n=128, seed=12345, krange=None):
+    """Config 2 (n=128) / config 5 (n=512): column i∈[3s,35s) j∈[3s,67s) k∈[3s,n-3s), s=n/128.
+    krange=(k0,k1): only the particles seeded in cell planes [k0,k1) (identical to that part of the full
+    scene), for z-slab ranks that must not materialise 128 M particles each."""
     s = max(n // 128, 1)
     if n >= 128:
-        cells = box_cells(3 * s, 35 * s, 3 * s, 67 * s, 3 * s, n - 3 * s)
+        box = (3 * s, 35 * s, 3 * s, 67 * s, 3 * s, n - 3 * s)
     else:  # small test sizes keep the same proportions
-        cells = box_cells(3, max(n // 4 + 3, 4), 3, max(n // 2 + 3, 4), 3, n - 3)
-    pos, vel = seed_cells(cells, DX, seed)
+        box = (3, max(n // 4 + 3, 4), 3, max(n // 2 + 3, 4), 3, n - 3)
+    i0, i1, j0, j1, k0, k1 = box
+    skip = 0
+    if krange is not None:
+        ka, kb = max(k0, krange[0]), min(k1, krange[1])
+        skip = max(ka - k0, 0) * (i1 - i0) * (j1 - j0)
+        k0, k1 = ka, max(kb, ka)
+    cells = box_cells(i0, i1, j0, j1, k0, k1)
+    pos, vel = seed_cells(cells, DX, seed, skip_cells=skip)
     return dict(name=f"dambreak{n}", dims=(n, n, n), dx=DX, pos=pos, vel=vel)
 
 
