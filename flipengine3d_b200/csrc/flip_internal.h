@@ -248,6 +248,7 @@ void slab_drop_ghosts_and_migrate(flip_ctx *c);         // after advance: emigra
 void slab_exchange_planes(flip_ctx *c, float *field, int planeElems, int facePlanes);   // halo planes of a float grid
 void slab_exchange_planes_u8(flip_ctx *c, unsigned char *field, int planeElems, int facePlanes);
 void slab_exchange_vector_halo(flip_ctx *c, double *v); // one cell plane each way (PCG search vector / pressure)
+void slab_exchange_cell_plane_f32(flip_ctx *c, float *v, int planeElems, int k0, int k1);
 inline bool slab_on(const flip_ctx *c);
 
 // helpers

@@ -35,6 +35,8 @@ struct PGrid {
     int sj, sk;   // strides I, I*J
     int kOff, Kg; // z-slab: global index of local plane 0, global K (single GPU: 0, K)
     int kOwn0, kOwn1;   // owned local planes
+    int cut;            // z-slabs whose boundaries are not aligned to the multigrid aggregates: the V-cycle is
+                        // block-local per slab and rows beyond the cut take no part in it
 };
 
 // a pressure row of the GLOBAL system (pressuresolver.cpp:101-110): liquid cell in [1,N-2]^3
@@ -369,6 +371,7 @@ static constexpr int MG_SMALL = 4096;
 
 struct MgLevel {
     int I, J, K, sj, sk, n;
+    int cut;   // see PGrid::cut
     float *diag, *invD, *oU, *oV, *oW, *x, *x2, *b;
 };
 
@@ -395,7 +398,7 @@ __device__ __forceinline__ float mg_offsum(const MgLevel &L, const float *x, int
 __device__ __forceinline__ float mg_corrected(const MgLevel &L, const MgLevel &C, const float *x, const float *e,
                                               float scale, int c, int i, int j, int k) {
     // an inactive cell (no row below it: outside the liquid, or beyond a z-slab cut) stays zero
-    if (L.invD[c] == 0.0f) return 0.0f;
+    if (L.cut && L.invD[c] == 0.0f) return 0.0f;
     return x[c] + scale * e[(i >> 1) + C.sj * (j >> 1) + C.sk * (k >> 1)];
 }
 
@@ -554,7 +557,7 @@ __device__ __forceinline__ float mg0_offsum_corr(const Mg0 &M, const MgLevel &C,
     float e0 = e[pi + pj + C.sk * ((k - 1) >> 1)], e1 = e[pi + C.sj * ((j - 1) >> 1) + pk], e2 = e[((i - 1) >> 1) + pj + pk];
     float e3 = e[((i + 1) >> 1) + pj + pk], e4 = e[pi + C.sj * ((j + 1) >> 1) + pk], e5 = e[pi + pj + C.sk * ((k + 1) >> 1)];
     // rows of a neighbouring z-slab (beyond the cut) take no part in the block-local correction
-    const bool own0 = (k - 1 >= M.g.kOwn0), own5 = (k + 1 < M.g.kOwn1);
+    const bool own0 = !M.g.cut || (k - 1 >= M.g.kOwn0), own5 = !M.g.cut || (k + 1 < M.g.kOwn1);
     float s = 0.0f;
     s += (a0 != 0.0f && own0) ? a0 * (x0 + scale * e0) : 0.0f;
     s += (a1 != 0.0f) ? a1 * (x1 + scale * e1) : 0.0f;
@@ -641,7 +644,7 @@ __global__ void k_mg_coarsen0(Mg0 M, MgLevel C) {
         if (!((M.rowBits[c >> 5] >> (c & 31)) & 1u)) continue;
         d += (float)M.Adiag[c];
         float au = M.fac * M.oU[c], av = M.fac * M.oV[c], aw = M.fac * M.oW[c];
-        if (qk == 0 && k + 1 >= M.g.kOwn1) aw = 0.0f;   // partner inside the aggregate belongs to another z-slab
+        if (M.g.cut && qk == 0 && k + 1 >= M.g.kOwn1) aw = 0.0f;   // partner inside the aggregate belongs to another z-slab
         if (qi == 0) d -= 2.0f * au; else u += au;
         if (qj == 0) d -= 2.0f * av; else v += av;
         if (qk == 0) d -= 2.0f * aw; else w += aw;
@@ -1131,7 +1134,7 @@ void pressure_alloc(flip_ctx *c) {
         size_t total = 0;
         while (L < MG_MAX_LEVELS) {
             MgLevel &lv = ps->lv[L];
-            lv.I = I; lv.J = J; lv.K = K; lv.sj = I; lv.sk = I * J; lv.n = I * J * K;
+            lv.I = I; lv.J = J; lv.K = K; lv.sj = I; lv.sk = I * J; lv.n = I * J * K; lv.cut = 0;
             size_t np = (size_t)lv.n + 64;
             total += (L == 0) ? 3 * np : 8 * np;
             L++;
@@ -1172,13 +1175,14 @@ void pressure_alloc(flip_ctx *c) {
         };
         while (Lc > 0 && (!aligned(Lc) || Lc >= ps->numLevels)) Lc--;
         ps->Lc = Lc;
+        for (int l = 0; l < ps->numLevels; l++) ps->lv[l].cut = (Lc == 0) ? 1 : 0;
         if (Lc > 0) {
             int I = ps->lv[Lc].I, J = ps->lv[Lc].J, K = d.Kg >> Lc;
             int L = Lc;
             size_t total = 0;
             while (L < MG_MAX_LEVELS) {
                 MgLevel &lv = ps->glv[L];
-                lv.I = I; lv.J = J; lv.K = K; lv.sj = I; lv.sk = I * J; lv.n = I * J * K;
+                lv.I = I; lv.J = J; lv.K = K; lv.sj = I; lv.sk = I * J; lv.n = I * J * K; lv.cut = 0;
                 total += 8 * ((size_t)lv.n + 64);
                 L++;
                 if (I <= 2 && J <= 2 && K <= 2) break;
@@ -1216,7 +1220,7 @@ void stage_pressure(flip_ctx *c, double dt) {
     const Dims &d = c->d;
     cudaStream_t st = c->stream;
     PressureScratch *ps = (PressureScratch *)c->mg;
-    PGrid g{d.I, d.J, d.K, d.I, d.I * d.J, d.kOff, d.Kg, d.kOwn0, d.kOwn1};
+    PGrid g{d.I, d.J, d.K, d.I, d.I * d.J, d.kOff, d.Kg, d.kOwn0, d.kOwn1, 0};
     int nSeg = ps->nSegAll;
 
     size_t ktBuild = kt_begin(c);
@@ -1282,9 +1286,10 @@ void stage_pressure(flip_ctx *c, double dt) {
     pp.factor = bp.factor;
     pp.tolFactor = fmax(c->pressureTol, 1e-30);
     const bool useMg = (c->preconditioner == 1) && ps->numLevels >= 2;
-    if (slab && useMg) {
-        // block-local V-cycle per slab: the correction is zero on the neighbours' rows, which the level-0
-        // sweeps read through the halo planes of the iterate buffers
+    if (slab && useMg && ps->Lc == 0) {
+        // unaligned slabs: block-local V-cycle per slab; the correction is zero on the neighbours' rows,
+        // which the level-0 sweeps read through the halo planes of the iterate buffers
+        g.cut = 1;
         FLIP_CUDA_CHECK(cudaMemsetAsync(ps->lv[0].x, 0, sizeof(float) * (size_t)d.nC, st));
         FLIP_CUDA_CHECK(cudaMemsetAsync(ps->lv[0].x2, 0, sizeof(float) * (size_t)d.nC, st));
     }
@@ -1308,6 +1313,9 @@ void stage_pressure(flip_ctx *c, double dt) {
             for (int l = 1; l < Lc; l++) {
                 k_mg_coarsen<<<cdiv(ps->lv[l + 1].n, TPB), TPB, 0, st>>>(ps->lv[l], ps->lv[l + 1]); c->launches++;
             }
+            // the coupling of my lowest owned coarse plane to the slab below is stored with the cell below
+            for (int l = 1; l < Lc; l++)
+                slab_exchange_cell_plane_f32(c, ps->lv[l].oW, ps->lv[l].sk, d.kOwn0 >> l, d.kOwn1 >> l);
             // every rank contributes the operator rows of its owned coarse planes
             MgLevel &Ll = ps->lv[Lc], &Gl = ps->glv[Lc];
             size_t off = (size_t)(d.kOwn0 >> Lc) * Ll.sk, cnt = (size_t)((d.kOwn1 - d.kOwn0) >> Lc) * Ll.sk;
@@ -1343,6 +1351,11 @@ void stage_pressure(flip_ctx *c, double dt) {
             comm_allgather_f32(c->comm, Ll.b + off, Gl.b, cnt, st);
         }
     };
+    // aligned z-slabs: the local levels exchange one boundary plane of the iterate after every sweep, so the
+    // V-cycle is the same operator as on a single GPU
+    auto xchg = [&](int l, float *x) {
+        if (Lc && l < Lc) slab_exchange_cell_plane_f32(c, x, ps->lv[l].sk, d.kOwn0 >> l, d.kOwn1 >> l);
+    };
     // one V-cycle: z = M^-1 r, rho[rhoSlot] += z.r
     auto vcycle = [&](int rhoSlot) {
         const int nu = mp.nu;
@@ -1355,6 +1368,7 @@ void stage_pressure(flip_ctx *c, double dt) {
                                                       mp.scale, sw == 0 ? 0 : 1, 0, nullptr, c->dS, 0);
                 c->launches++;
                 std::swap(xa, xb);
+                xchg(0, xa);
             }
             // xa holds the result
             k_mg0_restrict<<<cdiv(up_desc(0).n, TPB), TPB, 0, st>>>(m0, up_desc(0), c->vr, xa, c->dS); c->launches++;
@@ -1368,6 +1382,7 @@ void stage_pressure(flip_ctx *c, double dt) {
                 k_mg_sweep<<<cdiv(lv.n, TPB), TPB, 0, st>>>(lv, lv, xa, nullptr, xb, mp.omega, mp.scale, sw == 0 ? 0 : 1, c->dS);
                 c->launches++;
                 std::swap(xa, xb);
+                xchg(l, xa);
             }
             lv.x = xa; lv.x2 = xb;
             k_mg_restrict<<<cdiv(up_desc(l).n, TPB), TPB, 0, st>>>(lv, up_desc(l), lv.x, c->dS); c->launches++;
@@ -1399,6 +1414,7 @@ void stage_pressure(flip_ctx *c, double dt) {
                                                           sw == 0 ? 2 : 1, c->dS);
                 c->launches++;
                 std::swap(xa, xb);
+                xchg(l, xa);      // the next sweep, and the finer level's prolongation, read the neighbours' planes
             }
             lv.x = xa; lv.x2 = xb;
         }
@@ -1410,6 +1426,7 @@ void stage_pressure(flip_ctx *c, double dt) {
                                                       mp.scale, sw == 0 ? 2 : 1, last, c->vz, c->dS, rhoSlot);
                 c->launches++;
                 std::swap(xa, xb);
+                if (!last) xchg(0, xa);
             }
             ps->lv[0].x = xa; ps->lv[0].x2 = xb;
         }
@@ -1502,7 +1519,7 @@ void stage_pressure(flip_ctx *c, double dt) {
 
 void pressure_to_float(flip_ctx *c, float *devOut) {
     const Dims &d = c->d;
-    PGrid g{d.I, d.J, d.K, d.I, d.I * d.J, d.kOff, d.Kg, d.kOwn0, d.kOwn1};
+    PGrid g{d.I, d.J, d.K, d.I, d.I * d.J, d.kOff, d.Kg, d.kOwn0, d.kOwn1, 0};
     k_pressure_to_float<<<cdiv(d.nC, TPB), TPB, 0, c->stream>>>(c->phiL, c->vx_, g, d.nC, devOut);
     c->launches++;
 }

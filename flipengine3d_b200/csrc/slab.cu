@@ -216,6 +216,25 @@ static void exchange_planes(flip_ctx *c, T *f, int planeElems, int shift) {
 void slab_exchange_planes(flip_ctx *c, float *f, int planeElems, int facePlanes) { exchange_planes(c, f, planeElems, facePlanes); }
 void slab_exchange_planes_u8(flip_ctx *c, unsigned char *f, int planeElems, int facePlanes) { exchange_planes(c, f, planeElems, facePlanes); }
 
+// One cell plane of a float array each way, for a (multigrid) level whose owned planes are [k0,k1) and whose
+// plane holds planeElems entries.
+void slab_exchange_cell_plane_f32(flip_ctx *c, float *v, int planeElems, int k0, int k1) {
+    cudaStream_t st = c->stream;
+    const bool hasLo = c->rank > 0, hasHi = c->rank < c->nranks - 1;
+    const size_t pe = (size_t)planeElems;
+    const size_t bytes = sizeof(float) * pe;
+    comm_group_begin(c->comm);
+    if (hasLo) {
+        comm_send(c->comm, v + pe * k0, bytes, c->rank - 1, st);
+        comm_recv(c->comm, v + pe * (k0 - 1), bytes, c->rank - 1, st);
+    }
+    if (hasHi) {
+        comm_send(c->comm, v + pe * (k1 - 1), bytes, c->rank + 1, st);
+        comm_recv(c->comm, v + pe * k1, bytes, c->rank + 1, st);
+    }
+    comm_group_end(c->comm);
+}
+
 // One cell plane of a dense fp64 vector each way: my first owned plane -> lower neighbour's plane
 // kOwn1, my last owned plane -> upper neighbour's plane kOwn0-1.
 void slab_exchange_vector_halo(flip_ctx *c, double *v) {
