@@ -78,7 +78,7 @@ static void free_all(flip_ctx *c) {
     cudaFree(c->scanTemp);
     cudaFree(c->nearSolid); cudaFree(c->pressure);
     cudaFree(c->dS);
-    cudaFree(c->sendBuf[0]); cudaFree(c->sendBuf[1]);
+    cudaFree(c->sendBuf[0]); cudaFree(c->sendBuf[1]); cudaFree(c->occ);
     comm_destroy(c->comm); c->comm = nullptr;
     if (c->hS) cudaFreeHost(c->hS);
     if (c->eventsCreated) for (auto &e : c->evStage) cudaEventDestroy(e);

@@ -141,6 +141,8 @@ struct flip_ctx {
     int *pid[2] = {nullptr, nullptr};         // optional particle ids carried through the sorts
     bool trackIds = false;
     unsigned char *fastFlag = nullptr;        // [capacity] extreme-velocity flag
+    unsigned char *occ = nullptr;             // 4x4x4-cell blocks that hold particles (rebuilt by every sort)
+    size_t occBytes = 0;
     int *cellCount = nullptr;                 // [nC+1]
     int *cellStart = nullptr;                 // [nC+1] exclusive scan of kept counts (valid for current particles)
     int *cellStartA = nullptr;                // [nC+1] scan of candidate counts

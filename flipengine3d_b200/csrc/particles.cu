@@ -2,6 +2,8 @@
 // rules), liquid SDF + particle-to-grid gather, PIC/FLIP grid-to-particle update and RK3 advection
 // with solid collision.  Each kernel cites the reference code whose results it reproduces.
 #include <cub/device/device_scan.cuh>
+#include <algorithm>
+#include <cmath>
 #include <cstring>
 #include "device_math.cuh"
 #include "flip_internal.h"
@@ -42,7 +44,7 @@ void particles_alloc(flip_ctx *c, int capacity) {
     // keep live particles when growing
     ParticleSoA old[2] = {c->P[0], c->P[1]};
     int oldCap = c->capacity;
-    int cap = capacity + capacity / 16 + 1024;
+    int cap = (capacity + capacity / 16 + 1024 + 3) & ~3;   // multiple of 4: every component array stays 16-byte aligned
     ParticleSoA nw[2];
     soa_alloc(nw[0], cap);
     soa_alloc(nw[1], cap);
@@ -250,11 +252,17 @@ __global__ void k_cell_finalize(int nC, const int *__restrict__ startA, int *__r
     keptCount[c] = kept;
 }
 
+// also marks the 4x4x4-cell blocks that hold particles (the gather kernel skips empty space with it)
 __global__ void k_build_src(int nC, const int *__restrict__ startA, const int *__restrict__ start,
-                            const int *__restrict__ sortIdx, int *__restrict__ srcIdx, DeviceScalars *S) {
+                            const int *__restrict__ sortIdx, int *__restrict__ srcIdx, DeviceScalars *S,
+                            unsigned char *__restrict__ occ, int I, int J, int oI, int oJ) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nC) return;
     int b = start[c], e = start[c + 1];
+    if (e > b) {
+        int i = c % I, j = (c / I) % J, k = c / (I * J);
+        occ[(i >> 2) + oI * ((j >> 2) + oJ * (k >> 2))] = 1;
+    }
     int a = startA[c];
     for (int q = b; q < e; q++) srcIdx[q] = sortIdx[a + (q - b)];
     if (c == nC - 1) S->numParticles = e;
@@ -354,8 +362,19 @@ void particles_sort(flip_ctx *c, bool applyRules, double frameDt, int srcOffset,
     c->launches++;
     FLIP_CUDA_CHECK(cudaMemsetAsync(c->cellCount + nC, 0, sizeof(int), st));
     cub::DeviceScan::ExclusiveSum(c->scanTemp, c->scanTempBytes, c->cellCount, c->cellStart, nC + 1, st); c->launches++;
-    k_build_src<<<cdiv(nC, TPB), TPB, 0, st>>>(nC, c->cellStartA, c->cellStart, c->sortIdx, c->srcIdx, c->dS);
-    c->launches++;
+    {
+        int oI = (d.I + 3) >> 2, oJ = (d.J + 3) >> 2, oK = (d.K + 3) >> 2;
+        size_t need = (size_t)oI * oJ * oK;
+        if (need > c->occBytes) {
+            cudaFree(c->occ);
+            FLIP_CUDA_CHECK(cudaMalloc(&c->occ, need));
+            c->occBytes = need;
+        }
+        FLIP_CUDA_CHECK(cudaMemsetAsync(c->occ, 0, need, st));
+        k_build_src<<<cdiv(nC, TPB), TPB, 0, st>>>(nC, c->cellStartA, c->cellStart, c->sortIdx, c->srcIdx, c->dS, c->occ, d.I,
+                                                   d.J, oI, oJ);
+        c->launches++;
+    }
     if (n > 0) {
         k_gather<<<cdiv(n, TPB), TPB, 0, st>>>(src, dst, c->srcIdx, n, c->dS, c->trackIds ? c->pid[c->cur_buf] + srcOffset : nullptr,
                                                c->pid[1 - c->cur_buf]); c->launches++;
@@ -473,11 +492,122 @@ __device__ __forceinline__ float kernel_weight(float d2, const GatherParams &g) 
     return fsub(fadd(fsub(1.0f, a), b), cc);
 }
 
+// Geometry of one node/cell in the reference's block-local frame (10-cell blocks).
+struct NodeFrame {
+    int bi, bj, bk, li, lj, lk;
+    float ox, oy, oz;      // block origin
+    float gx, gy, gz;      // node position in the block
+    float cx, cy, cz;      // cell centre in the block
+};
+
+__device__ __forceinline__ NodeFrame node_frame(const GatherParams &g, int i, int j, int kg) {
+    NodeFrame f;
+    f.bi = i / 10; f.bj = j / 10; f.bk = kg / 10;
+    f.li = i - f.bi * 10; f.lj = j - f.bj * 10; f.lk = kg - f.bk * 10;
+    // block origins  (float)bi * blockdx  -> float  (grid3d.h:81-83)
+    f.ox = (float)dmul((double)(float)f.bi, g.blockdxP2G);
+    f.oy = (float)dmul((double)(float)f.bj, g.blockdxP2G);
+    f.oz = (float)dmul((double)(float)f.bk, g.blockdxP2G);
+    // node position (float)l*dx -> float   (grid3d.h:81)
+    f.gx = (float)dmul((double)(float)f.li, g.dx);
+    f.gy = (float)dmul((double)(float)f.lj, g.dx);
+    f.gz = (float)dmul((double)(float)f.lk, g.dx);
+    // cell centre (float)l*dx + hw in double -> float  (grid3d.h:101-104)
+    const double hwd = 0.5 * g.dx;
+    f.cx = (float)dadd(dmul((double)(float)f.li, g.dx), hwd);
+    f.cy = (float)dadd(dmul((double)(float)f.lj, g.dx), hwd);
+    f.cz = (float)dadd(dmul((double)(float)f.lk, g.dx), hwd);
+    return f;
+}
+
+// dist = length(gpos - p) - r ; phi = min(3dx, dist) (particlelevelset.cpp:615-621, :295), then
+// postProcessSignedDistanceField (particlelevelset.cpp:172-196)
+__device__ __forceinline__ float finish_phi(const GatherParams &g, const float *__restrict__ phiS, float best2, int i, int j,
+                                            int k) {
+    const int I = g.I, J = g.J;
+    float phi = g.maxDist;
+    if (best2 < 1.0e38f) {
+        float dist = fsub(__fsqrt_rn(best2), g.rS);
+        if (dist < phi) phi = dist;
+    }
+    double dxd = g.dx;
+    if ((double)phi < 0.5 * dxd) {
+        // MeshLevelSet::getDistanceAtCellCenter  meshlevelset.cpp:152-162
+        int ni = I + 1;
+        long long nj = (long long)(I + 1) * (J + 1);
+        long long n0 = (long long)i + (long long)ni * j + nj * k;
+        float s = __ldg(phiS + n0);
+        s = fadd(s, __ldg(phiS + n0 + 1));
+        s = fadd(s, __ldg(phiS + n0 + ni));
+        s = fadd(s, __ldg(phiS + n0 + ni + 1));
+        s = fadd(s, __ldg(phiS + n0 + nj));
+        s = fadd(s, __ldg(phiS + n0 + nj + 1));
+        s = fadd(s, __ldg(phiS + n0 + nj + ni));
+        s = fadd(s, __ldg(phiS + n0 + nj + ni + 1));
+        if (fmul(0.125f, s) < 0.0f) phi = (float)dmul((double)-0.5f, dxd);
+    }
+    float epsf = (float)(0.005 * dxd);
+    if (fabsf(phi) < epsf) phi = (phi > 0.0f) ? epsf : -epsf;
+    return phi;
+}
+
+// One row (cj,ck) of the 3x3 cell rows around a node: particles [qb,qe).  DOV / DOW: whether particles of this
+// row can reach the V / W face of the node (they cannot from row j+1 / plane k+1: r < dx).
+template <bool DYADIC, bool DOV, bool DOW>
+__device__ __forceinline__ void gather_row(const ParticleSoA &p, const GatherParams &g, const NodeFrame &f, int qb, int qe,
+                                           float Xn, float Yn, float Zn, float Xh, float Yh, float Zh, float &su,
+                                           float &wu, float &sv, float &wv, float &sw, float &ww, float &best2) {
+    // four particles per step through 16-byte loads of each coordinate array (16-byte aligned, padded): lanes of
+    // a warp read windows ~8 particles apart, so this cuts the L1 wavefronts per particle by four.  Summation
+    // order stays q ascending.
+    for (int q4 = qb & ~3; q4 < qe; q4 += 4) {
+        const float4 X4 = __ldg(reinterpret_cast<const float4 *>(p.px + q4));
+        const float4 Y4 = __ldg(reinterpret_cast<const float4 *>(p.py + q4));
+        const float4 Z4 = __ldg(reinterpret_cast<const float4 *>(p.pz + q4));
+        const float xs[4] = {X4.x, X4.y, X4.z, X4.w}, ys[4] = {Y4.x, Y4.y, Y4.z, Y4.w}, zs[4] = {Z4.x, Z4.y, Z4.z, Z4.w};
+#pragma unroll
+        for (int m = 0; m < 4; m++) {
+            const int q = q4 + m;
+            if (q < qb || q >= qe) continue;
+            const float x = xs[m], y = ys[m], z = zs[m];
+            float ax, ay, az, bx, by, bz, d2c;
+            if (DYADIC) {
+                ax = fsub(Xn, x); ay = fsub(Yn, y); az = fsub(Zn, z);
+                bx = fsub(Xh, x); by = fsub(Yh, y); bz = fsub(Zh, z);
+            } else {
+                // block-local particle coordinates for the P2G components: (p - offset) - origin
+                float xl = fsub(x, f.ox), yl = fsub(y, f.oy), zl = fsub(z, f.oz);                 // offset 0 on that axis
+                float xh = fsub(fsub(x, g.hw), f.ox), yh = fsub(fsub(y, g.hw), f.oy), zh = fsub(fsub(z, g.hw), f.oz);
+                ax = fsub(f.gx, xl); ay = fsub(f.gy, yl); az = fsub(f.gz, zl);                   // v = gpos - p
+                bx = fsub(f.gx, xh); by = fsub(f.gy, yh); bz = fsub(f.gz, zh);
+                d2c = lengthsq3(fsub(f.cx, xl), fsub(f.cy, yl), fsub(f.cz, zl));
+            }
+            const float ax2 = fmul(ax, ax), bx2 = fmul(bx, bx), by2 = fmul(by, by), bz2 = fmul(bz, bz);
+            const float d2u = fadd(fadd(ax2, by2), bz2);
+            if (d2u < g.rsq) { float w = kernel_weight(d2u, g); su = fadd(su, fmul(w, __ldg(p.vx + q))); wu = fadd(wu, w); }
+            if (DOV) {
+                const float d2v = fadd(fadd(bx2, fmul(ay, ay)), bz2);
+                if (d2v < g.rsq) { float w = kernel_weight(d2v, g); sv = fadd(sv, fmul(w, __ldg(p.vy + q))); wv = fadd(wv, w); }
+            }
+            if (DOW) {
+                const float d2w = fadd(fadd(bx2, by2), fmul(az, az));
+                if (d2w < g.rsq) { float w = kernel_weight(d2w, g); sw = fadd(sw, fmul(w, __ldg(p.vz + q))); ww = fadd(ww, w); }
+            }
+            // SDF: all particles of the 3x3x3 neighbourhood are inside the reference's search box
+            // (|c-p|_inf < 1.5dx < 2r+0.5dx); block origin is the same number for both subsystems
+            if (DYADIC) d2c = fadd(fadd(bx2, by2), bz2);
+            best2 = fminf(best2, d2c);
+        }
+    }
+}
+
+template <bool DYADIC>
 __global__ void __launch_bounds__(128) k_sdf_p2g(ParticleSoA p, const int *__restrict__ cellStart, GatherParams g,
                                                  float *__restrict__ U, float *__restrict__ V, float *__restrict__ W,
                                                  unsigned char *__restrict__ validU, unsigned char *__restrict__ validV,
                                                  unsigned char *__restrict__ validW, float *__restrict__ phiL,
-                                                 const float *__restrict__ phiS) {
+                                                 const float *__restrict__ phiS, const unsigned char *__restrict__ occ,
+                                                 int *__restrict__ farCells, float *__restrict__ farBest, int *farCount) {
     const int I = g.I, J = g.J, K = g.K;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int j = blockIdx.y, k = blockIdx.z;      // k: local plane
@@ -488,57 +618,50 @@ __global__ void __launch_bounds__(128) k_sdf_p2g(ParticleSoA p, const int *__res
     const bool hasW = (i < I && j < J);
     const bool hasC = (i < I && j < J && k < K);
 
-    // block of this node per axis and local node coordinate (the three components and the cell
-    // share (i,j,k), blocks are 10 wide for both subsystems)
-    const int bi = i / 10, bj = j / 10, bk = kg / 10;
-    const int li = i - bi * 10, lj = j - bj * 10, lk = kg - bk * 10;
-    // block origins  (float)bi * blockdx  -> float  (grid3d.h:81-83)
-    const float oxP = (float)dmul((double)(float)bi, g.blockdxP2G);
-    const float oyP = (float)dmul((double)(float)bj, g.blockdxP2G);
-    const float ozP = (float)dmul((double)(float)bk, g.blockdxP2G);
-    // node position (float)l*dx -> float   (grid3d.h:81)
-    const float gx = (float)dmul((double)(float)li, g.dx);
-    const float gy = (float)dmul((double)(float)lj, g.dx);
-    const float gz = (float)dmul((double)(float)lk, g.dx);
-    // cell centre (float)l*dx + hw in double -> float  (grid3d.h:101-104)
-    const double hwd = 0.5 * g.dx;
-    const float cx = (float)dadd(dmul((double)(float)li, g.dx), hwd);
-    const float cy = (float)dadd(dmul((double)(float)lj, g.dx), hwd);
-    const float cz = (float)dadd(dmul((double)(float)lk, g.dx), hwd);
+    // Empty space (most of the box): no particle within the 5x5x5 cells around the node, per the 4^3-cell
+    // occupancy blocks -> faces are 0 / invalid and phi keeps its "no particles" value.
+    {
+        const int oI = (I + 3) >> 2, oJ = (J + 3) >> 2, oK = (K + 3) >> 2;
+        const int bi0 = max(i - 2, 0) >> 2, bi1 = min(min(i + 2, I - 1) >> 2, oI - 1);
+        const int bj0 = max(j - 2, 0) >> 2, bj1 = min(min(j + 2, J - 1) >> 2, oJ - 1);
+        const int bk0 = max(k - 2, 0) >> 2, bk1 = min(min(k + 2, K - 1) >> 2, oK - 1);
+        bool any = false;
+        for (int bk = bk0; bk <= bk1; bk++)
+            for (int bj = bj0; bj <= bj1; bj++)
+                for (int bi = bi0; bi <= bi1; bi++) any |= __ldg(occ + bi + oI * (bj + oJ * bk)) != 0;
+        if (!any) {
+            if (hasU) { long long idx = (long long)i + (long long)(I + 1) * (j + (long long)J * k); U[idx] = 0.0f; validU[idx] = 0; }
+            if (hasV) { long long idx = (long long)i + (long long)I * (j + (long long)(J + 1) * k); V[idx] = 0.0f; validV[idx] = 0; }
+            if (hasW) { long long idx = (long long)i + (long long)I * (j + (long long)J * k); W[idx] = 0.0f; validW[idx] = 0; }
+            if (hasC) phiL[(long long)i + (long long)I * (j + (long long)J * k)] = g.maxDist;
+            return;
+        }
+    }
 
+    const NodeFrame f = node_frame(g, i, j, kg);
     float su = 0.f, wu = 0.f, sv = 0.f, wv = 0.f, sw = 0.f, ww = 0.f;
     float best2 = 3.0e38f;   // min squared distance cell centre <-> particle (block-local arithmetic)
 
     const int jlo = max(j - 1, 0), jhi = min(j + 1, J - 1);
     const int klo = max(k - 1, 0), khi = min(k + 1, K - 1);
     const int ilo = max(i - 1, 0), ihi = min(i + 1, I - 1);
+    // DYADIC (dx a power of two): every subtraction of the block-local formulation is exact, so
+    //   gpos - ((p - offset) - origin)  ==  (node + offset) - p   bit for bit,
+    // and the cell-centre distance of the SDF is the fully staggered one.  Xn.. = global node coordinates.
+    const float Xn = (float)dmul((double)(float)i, g.dx), Yn = (float)dmul((double)(float)j, g.dx),
+                Zn = (float)dmul((double)(float)kg, g.dx);
+    const float Xh = fadd(Xn, g.hw), Yh = fadd(Yn, g.hw), Zh = fadd(Zn, g.hw);
     for (int ck = klo; ck <= khi; ck++) {
         for (int cj = jlo; cj <= jhi; cj++) {
             int rowBase = I * (cj + J * ck);
-            int qb = __ldg(cellStart + rowBase + ilo);
-            int qe = __ldg(cellStart + rowBase + ihi + 1);
-            for (int q = qb; q < qe; q++) {
-                float x = __ldg(p.px + q), y = __ldg(p.py + q), z = __ldg(p.pz + q);
-                // block-local particle coordinates for the P2G components: (p - offset) - origin
-                float xl = fsub(x, oxP), yl = fsub(y, oyP), zl = fsub(z, ozP);                 // offset 0 on that axis
-                float xh = fsub(fsub(x, g.hw), oxP), yh = fsub(fsub(y, g.hw), oyP), zh = fsub(fsub(z, g.hw), ozP);
-                // v = gpos - p
-                float ax = fsub(gx, xl), ay = fsub(gy, yl), az = fsub(gz, zl);
-                float bx = fsub(gx, xh), by = fsub(gy, yh), bz = fsub(gz, zh);
-                float ax2 = fmul(ax, ax), ay2 = fmul(ay, ay), az2 = fmul(az, az);
-                float bx2 = fmul(bx, bx), by2 = fmul(by, by), bz2 = fmul(bz, bz);
-                float d2u = fadd(fadd(ax2, by2), bz2);
-                float d2v = fadd(fadd(bx2, ay2), bz2);
-                float d2w = fadd(fadd(bx2, by2), az2);
-                if (d2u < g.rsq) { float w = kernel_weight(d2u, g); su = fadd(su, fmul(w, __ldg(p.vx + q))); wu = fadd(wu, w); }
-                if (d2v < g.rsq) { float w = kernel_weight(d2v, g); sv = fadd(sv, fmul(w, __ldg(p.vy + q))); wv = fadd(wv, w); }
-                if (d2w < g.rsq) { float w = kernel_weight(d2w, g); sw = fadd(sw, fmul(w, __ldg(p.vz + q))); ww = fadd(ww, w); }
-                // SDF: all particles of the 3x3x3 neighbourhood are inside the reference's search box
-                // (|c-p|_inf < 1.5dx < 2r+0.5dx); block origin is the same number for both subsystems
-                float ex = fsub(cx, xl), ey = fsub(cy, yl), ez = fsub(cz, zl);
-                float d2c = lengthsq3(ex, ey, ez);
-                best2 = fminf(best2, d2c);
-            }
+            const int qb = __ldg(cellStart + rowBase + ilo);
+            const int qe = __ldg(cellStart + rowBase + ihi + 1);
+            if (qb == qe) continue;
+            const bool doV = (cj <= j), doW = (ck <= k);     // uniform over the block
+            if (doV && doW) gather_row<DYADIC, true, true>(p, g, f, qb, qe, Xn, Yn, Zn, Xh, Yh, Zh, su, wu, sv, wv, sw, ww, best2);
+            else if (doV) gather_row<DYADIC, true, false>(p, g, f, qb, qe, Xn, Yn, Zn, Xh, Yh, Zh, su, wu, sv, wv, sw, ww, best2);
+            else if (doW) gather_row<DYADIC, false, true>(p, g, f, qb, qe, Xn, Yn, Zn, Xh, Yh, Zh, su, wu, sv, wv, sw, ww, best2);
+            else gather_row<DYADIC, false, false>(p, g, f, qb, qe, Xn, Yn, Zn, Xh, Yh, Zh, su, wu, sv, wv, sw, ww, best2);
         }
     }
 
@@ -562,12 +685,42 @@ __global__ void __launch_bounds__(128) k_sdf_p2g(ParticleSoA p, const int *__res
     }
     if (!hasC) return;
 
-    // ---- SDF phase 2: particles outside the 3x3x3 neighbourhood can only matter if nothing nearer
-    // than 1.5dx was found (they are at least 1.5dx away along one axis).
-    float thr = fmul(fmul(1.45f, (float)g.dx), fmul(1.45f, (float)g.dx));
+    // Particles outside the 3x3x3 neighbourhood can only matter if nothing nearer than 1.5dx was found (they are
+    // at least 1.5dx away along one axis).  Those few cells (a shell around the liquid) are queued for
+    // k_sdf_far, which searches the 5x5x5 box with all lanes busy.
+    const float thr = fmul(fmul(1.45f, (float)g.dx), fmul(1.45f, (float)g.dx));
+    const int cell = i + I * (j + J * k);
     if (!(best2 < thr)) {
+        int slot = atomicAdd(farCount, 1);
+        farCells[slot] = cell;
+        farBest[slot] = best2;
+        return;
+    }
+    phiL[cell] = finish_phi(g, phiS, best2, i, j, k);
+}
+
+// Liquid SDF of the queued cells: the rest of the 5x5x5 search box (particlelevelset.cpp:476-513, :596-621).
+// A particle of a cell two away along some axis lies inside the reference's search box for roughly 3/4 of that
+// cell; the decision is taken in float with a margin far above the rounding of the reference's block-local
+// arithmetic, and only the borderline cases run the literal double-precision index computation.
+__global__ void k_sdf_far(ParticleSoA p, const int *__restrict__ cellStart, GatherParams g, float *__restrict__ phiL,
+                          const float *__restrict__ phiS, const int *__restrict__ farCells,
+                          const float *__restrict__ farBest, const int *__restrict__ farCount) {
+    const int I = g.I, J = g.J, K = g.K;
+    const int n = *farCount;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+        const int cell = farCells[t];
+        float best2 = farBest[t];
+        const int i = cell % I, j = (cell / I) % J, k = cell / (I * J);
+        const NodeFrame f = node_frame(g, i, j, k + g.kOff);
         const float sr = g.srS;
         const double invdx = g.invdx;
+        const float dxf = (float)g.dx, margin = 1.0e-3f * dxf;
+        const float Xn = (float)dmul((double)(float)i, g.dx), Yn = (float)dmul((double)(float)j, g.dx),
+                    Zn = (float)dmul((double)(float)(k + g.kOff), g.dx);
+        const float loIn = -sr + margin, hiIn = dxf + sr - margin, loOut = -sr - margin, hiOut = dxf + sr + margin;
+        const int jlo = max(j - 1, 0), jhi = min(j + 1, J - 1), klo = max(k - 1, 0), khi = min(k + 1, K - 1);
+        const int ilo = max(i - 1, 0), ihi = min(i + 1, I - 1);
         const int j2lo = max(j - 2, 0), j2hi = min(j + 2, J - 1);
         const int k2lo = max(k - 2, 0), k2hi = min(k + 2, K - 1);
         const int i2lo = max(i - 2, 0), i2hi = min(i + 2, I - 1);
@@ -577,57 +730,36 @@ __global__ void __launch_bounds__(128) k_sdf_p2g(ParticleSoA p, const int *__res
                 int rowBase = I * (cj + J * ck);
                 int qb = __ldg(cellStart + rowBase + i2lo);
                 int qe = __ldg(cellStart + rowBase + i2hi + 1);
-                int sb = 0, se = 0;   // range already visited in phase 1 (skip)
+                if (qb == qe) continue;
+                int sb = 0, se = 0;   // range already visited by k_sdf_p2g (skip)
                 if (innerRow) { sb = __ldg(cellStart + rowBase + ilo); se = __ldg(cellStart + rowBase + ihi + 1); }
                 for (int q = qb; q < qe; q++) {
                     if (innerRow && q >= sb && q < se) { q = se - 1; continue; }
                     float x = __ldg(p.px + q), y = __ldg(p.py + q), z = __ldg(p.pz + q);
-                    // block membership of the particle (particlelevelset.cpp:476-513): the blocks
-                    // overlapped by [p-sr, p+sr] in global coordinates
-                    int bminx = pos2idx_d((double)fsub(x, sr), g.invBlockdxSDF), bmaxx = pos2idx_d((double)fadd(x, sr), g.invBlockdxSDF);
-                    int bminy = pos2idx_d((double)fsub(y, sr), g.invBlockdxSDF), bmaxy = pos2idx_d((double)fadd(y, sr), g.invBlockdxSDF);
-                    int bminz = pos2idx_d((double)fsub(z, sr), g.invBlockdxSDF), bmaxz = pos2idx_d((double)fadd(z, sr), g.invBlockdxSDF);
-                    if (bi < bminx || bi > bmaxx || bj < bminy || bj > bmaxy || bk < bminz || bk > bmaxz) continue;
-                    // block-local search box (particlelevelset.cpp:596-607)
-                    float xl = fsub(x, oxP), yl = fsub(y, oyP), zl = fsub(z, ozP);
-                    int gminx = pos2idx(fsub(xl, sr), invdx), gmaxx = pos2idx(fadd(xl, sr), invdx);
-                    int gminy = pos2idx(fsub(yl, sr), invdx), gmaxy = pos2idx(fadd(yl, sr), invdx);
-                    int gminz = pos2idx(fsub(zl, sr), invdx), gmaxz = pos2idx(fadd(zl, sr), invdx);
-                    if (li < gminx || li > gmaxx || lj < gminy || lj > gmaxy || lk < gminz || lk > gmaxz) continue;
-                    float ex = fsub(cx, xl), ey = fsub(cy, yl), ez = fsub(cz, zl);
-                    best2 = fminf(best2, lengthsq3(ex, ey, ez));
+                    // position relative to the cell's lower corner: inside the search box iff -sr <= u < dx + sr
+                    float ux = fsub(x, Xn), uy = fsub(y, Yn), uz = fsub(z, Zn);
+                    bool out = ux < loOut || ux >= hiOut || uy < loOut || uy >= hiOut || uz < loOut || uz >= hiOut;
+                    if (out) continue;
+                    bool in = ux >= loIn && ux < hiIn && uy >= loIn && uy < hiIn && uz >= loIn && uz < hiIn;
+                    float xl = fsub(x, f.ox), yl = fsub(y, f.oy), zl = fsub(z, f.oz);
+                    if (!in) {
+                        // borderline: the literal test.  Block membership of the particle: the blocks overlapped by
+                        // [p-sr, p+sr] in global coordinates; then the block-local search box.
+                        int bminx = pos2idx_d((double)fsub(x, sr), g.invBlockdxSDF), bmaxx = pos2idx_d((double)fadd(x, sr), g.invBlockdxSDF);
+                        int bminy = pos2idx_d((double)fsub(y, sr), g.invBlockdxSDF), bmaxy = pos2idx_d((double)fadd(y, sr), g.invBlockdxSDF);
+                        int bminz = pos2idx_d((double)fsub(z, sr), g.invBlockdxSDF), bmaxz = pos2idx_d((double)fadd(z, sr), g.invBlockdxSDF);
+                        if (f.bi < bminx || f.bi > bmaxx || f.bj < bminy || f.bj > bmaxy || f.bk < bminz || f.bk > bmaxz) continue;
+                        int gminx = pos2idx(fsub(xl, sr), invdx), gmaxx = pos2idx(fadd(xl, sr), invdx);
+                        int gminy = pos2idx(fsub(yl, sr), invdx), gmaxy = pos2idx(fadd(yl, sr), invdx);
+                        int gminz = pos2idx(fsub(zl, sr), invdx), gmaxz = pos2idx(fadd(zl, sr), invdx);
+                        if (f.li < gminx || f.li > gmaxx || f.lj < gminy || f.lj > gmaxy || f.lk < gminz || f.lk > gmaxz) continue;
+                    }
+                    best2 = fminf(best2, lengthsq3(fsub(f.cx, xl), fsub(f.cy, yl), fsub(f.cz, zl)));
                 }
             }
         }
+        phiL[cell] = finish_phi(g, phiS, best2, i, j, k);
     }
-    // dist = length(gpos - p) - r ; phi = min(3dx, dist)   (particlelevelset.cpp:615-621, :295)
-    float phi = g.maxDist;
-    if (best2 < 1.0e38f) {
-        float dist = fsub(__fsqrt_rn(best2), g.rS);
-        if (dist < phi) phi = dist;
-    }
-    // postProcessSignedDistanceField (particlelevelset.cpp:172-196)
-    {
-        double dxd = g.dx;
-        if ((double)phi < 0.5 * dxd) {
-            // MeshLevelSet::getDistanceAtCellCenter  meshlevelset.cpp:152-162
-            int ni = I + 1;
-            long long nj = (long long)(I + 1) * (J + 1);
-            long long n0 = (long long)i + (long long)ni * j + nj * k;
-            float s = __ldg(phiS + n0);
-            s = fadd(s, __ldg(phiS + n0 + 1));
-            s = fadd(s, __ldg(phiS + n0 + ni));
-            s = fadd(s, __ldg(phiS + n0 + ni + 1));
-            s = fadd(s, __ldg(phiS + n0 + nj));
-            s = fadd(s, __ldg(phiS + n0 + nj + 1));
-            s = fadd(s, __ldg(phiS + n0 + nj + ni));
-            s = fadd(s, __ldg(phiS + n0 + nj + ni + 1));
-            if (fmul(0.125f, s) < 0.0f) phi = (float)dmul((double)-0.5f, dxd);
-        }
-        float epsf = (float)(0.005 * dxd);
-        if (fabsf(phi) < epsf) phi = (phi > 0.0f) ? epsf : -epsf;
-    }
-    phiL[(long long)i + (long long)I * (j + (long long)J * k)] = phi;
 }
 
 static GatherParams make_gather_params(const flip_ctx *c) {
@@ -661,8 +793,22 @@ static void run_sdf_p2g(flip_ctx *c) {
     dim3 block(128, 1, 1);
     dim3 grid(cdiv(d.I + 1, 128), d.J + 1, d.K + 1);
     size_t kt = kt_begin(c);
-    k_sdf_p2g<<<grid, block, 0, c->stream>>>(c->P[c->cur_buf], c->cellStart, g, c->U, c->V, c->W, c->validU, c->validV,
-                                             c->validW, c->phiL, c->phiS);
+    // power-of-two dx (every BASELINE config: 0.125) and moderate extents: the exact fast path
+    int ex = 0;
+    const bool dyadic = (frexp(d.dx, &ex) == 0.5) && std::max(d.I, std::max(d.J, d.Kg)) <= 4096;
+    // far-cell queue in the extrapolation scratch (idle at this point of the step)
+    int *farCells = c->frontier[0];
+    float *farBest = reinterpret_cast<float *>(c->frontier[1]);
+    int *farCount = &c->dS->frontierCount[0];
+    FLIP_CUDA_CHECK(cudaMemsetAsync(farCount, 0, sizeof(int), c->stream));
+    if (dyadic)
+        k_sdf_p2g<true><<<grid, block, 0, c->stream>>>(c->P[c->cur_buf], c->cellStart, g, c->U, c->V, c->W, c->validU, c->validV,
+                                                       c->validW, c->phiL, c->phiS, c->occ, farCells, farBest, farCount);
+    else
+        k_sdf_p2g<false><<<grid, block, 0, c->stream>>>(c->P[c->cur_buf], c->cellStart, g, c->U, c->V, c->W, c->validU, c->validV,
+                                                        c->validW, c->phiL, c->phiS, c->occ, farCells, farBest, farCount);
+    k_sdf_far<<<148 * 8, 128, 0, c->stream>>>(c->P[c->cur_buf], c->cellStart, g, c->phiL, c->phiS, farCells, farBest, farCount);
+    c->launches++;
     kt_end(c, FLIP_KERNEL_SDF_P2G, kt);
     c->launches++;
     FLIP_CUDA_CHECK(cudaGetLastError());
