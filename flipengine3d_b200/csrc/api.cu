@@ -117,9 +117,9 @@ static void allocate_grids(flip_ctx *c) {
     dev_alloc(c->U, d.nU); dev_alloc(c->V, d.nV); dev_alloc(c->W, d.nW);
     dev_alloc(c->sU, d.nU); dev_alloc(c->sV, d.nV); dev_alloc(c->sW, d.nW);
     dev_alloc(c->validU, d.nU); dev_alloc(c->validV, d.nV); dev_alloc(c->validW, d.nW);
-    size_t nmax = std::max(d.nU, std::max(d.nV, d.nW));
-    dev_alloc(c->status, nmax);
-    dev_alloc(c->frontier[0], nmax); dev_alloc(c->frontier[1], nmax);
+    // extrapolation scratch: level bytes and two frontier lists for each of the three components
+    dev_alloc(c->status, 3 * ext_stride(d));
+    dev_alloc(c->frontier[0], 3 * ext_stride(d)); dev_alloc(c->frontier[1], 3 * ext_stride(d));
     dev_alloc(c->phiL, d.nC); dev_alloc(c->phiS, d.nN);
     dev_alloc(c->wU, d.nU); dev_alloc(c->wV, d.nV); dev_alloc(c->wW, d.nW);
     dev_alloc(c->cellCount, (size_t)d.nC + 1); dev_alloc(c->cellStart, (size_t)d.nC + 1);
@@ -254,6 +254,14 @@ int flip_set_multigrid(flip_ctx *c, int sweeps, double damping, double weight, i
         if (sweeps < 1 || sweeps > 8 || !(damping > 0.0 && damping <= 1.0) || !(weight > 0.0) || coarsest < 1)
             throw ApiError(FLIP_ERR_DOMAIN, "Error: bad multigrid parameters.");
         c->mgNu = sweeps; c->mgOmega = damping; c->mgScale = weight; c->mgCoarseSweeps = coarsest;
+    });
+}
+
+int flip_set_sampling_mode(flip_ctx *c, int mode) {
+    if (!c) return FLIP_ERR_RUNTIME;
+    return guarded(c, [&] {
+        if (mode != FLIP_SAMPLING_EXACT && mode != FLIP_SAMPLING_FAST) throw ApiError(FLIP_ERR_DOMAIN, "sampling mode must be FLIP_SAMPLING_EXACT or FLIP_SAMPLING_FAST");
+        c->samplingMode = mode;
     });
 }
 

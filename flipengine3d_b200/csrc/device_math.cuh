@@ -97,6 +97,73 @@ __device__ __forceinline__ void sample_velocity(const MacField &f, const GridGeo
     oz = (float)sample_mac<1, 1, 0>(f.W, G.I, G.J, G.K + 1, x, y, z, dx, invdx, hdx, G.kOff);
 }
 
+// ---- single-precision sampling (FLIP_SAMPLING_FAST) ---------------------------------------------
+// Valid when dx is a power of two and the position lies at least one cell inside the local arrays on
+// every axis.  Then p/dx, the half-cell shift, floor() and the fraction are all EXACT in float (the
+// shifted coordinate is a multiple of ulp(p) no larger than p; scaling by 1/dx only changes the
+// exponent), so the cell indices and the interpolation weights are bit-identical to the reference's
+// double-precision ones (macvelocityfield.cpp:519-613) and all 8 samples are in range.  Only the
+// trilinear blend itself is evaluated in float (7 lerps, FMA) instead of double: <= a few ulp of the
+// sampled values, far inside the 1e-4 rel-L2 tolerance of the parity contract.
+struct FastGeom {
+    float invdx, hdx;                 // 1/dx and dx/2 (exact: powers of two)
+    float lox, loy, loz, hix, hiy, hiz;   // interior box [dx, (N-1)dx) of the LOCAL arrays, world coordinates
+    int I, J, kOff;                   // cells per row / rows per plane of the local grid, global k of local plane 0
+};
+
+__device__ __forceinline__ bool fast_interior(const FastGeom &F, float x, float y, float z) {
+    return x >= F.lox && x < F.hix && y >= F.loy && y < F.hiy && z >= F.loz && z < F.hiz;
+}
+
+__device__ __forceinline__ float trilerp_fast(const float *__restrict__ g, int base, int sj, int sk, float fx, float fy,
+                                              float fz) {
+    const float p000 = __ldg(g + base), p100 = __ldg(g + base + 1);
+    const float p010 = __ldg(g + base + sj), p110 = __ldg(g + base + sj + 1);
+    const float p001 = __ldg(g + base + sk), p101 = __ldg(g + base + sk + 1);
+    const float p011 = __ldg(g + base + sk + sj), p111 = __ldg(g + base + sk + sj + 1);
+    const float a = fmaf(fx, p100 - p000, p000), b = fmaf(fx, p110 - p010, p010);
+    const float c = fmaf(fx, p101 - p001, p001), d = fmaf(fx, p111 - p011, p011);
+    const float e = fmaf(fy, b - a, a), f = fmaf(fy, d - c, c);
+    return fmaf(fz, f - e, e);
+}
+
+// cell index and fraction of the unshifted / half-cell-shifted coordinate along one axis
+struct FastAxis {
+    int i0, i1;       // floor(p/dx), floor((p - dx/2)/dx)
+    float f0, f1;     // fractions
+};
+__device__ __forceinline__ FastAxis fast_axis(float p, float invdx, float hdx) {
+    FastAxis a;
+    const float s0 = p * invdx, s1 = (p - hdx) * invdx;
+    const float q0 = floorf(s0), q1 = floorf(s1);
+    a.i0 = (int)q0; a.i1 = (int)q1;
+    a.f0 = s0 - q0; a.f1 = s1 - q1;
+    return a;
+}
+
+struct FastStencil {
+    int bu, bv, bw;            // base index of the 2x2x2 stencil in U, V, W
+    float ux, uy, uz, vx, vy, vz, wx, wy, wz;   // fractions per component
+};
+__device__ __forceinline__ FastStencil fast_stencil(const FastGeom &F, float x, float y, float z) {
+    const FastAxis ax = fast_axis(x, F.invdx, F.hdx), ay = fast_axis(y, F.invdx, F.hdx), az = fast_axis(z, F.invdx, F.hdx);
+    const int k0 = az.i0 - F.kOff, k1 = az.i1 - F.kOff;
+    FastStencil s;
+    s.bu = ax.i0 + (F.I + 1) * (ay.i1 + F.J * k1);        // U: (x, y - h, z - h), array (I+1, J, K)
+    s.bv = ax.i1 + F.I * (ay.i0 + (F.J + 1) * k1);        // V: (x - h, y, z - h), array (I, J+1, K)
+    s.bw = ax.i1 + F.I * (ay.i1 + F.J * k0);              // W: (x - h, y - h, z), array (I, J, K+1)
+    s.ux = ax.f0; s.uy = ay.f1; s.uz = az.f1;
+    s.vx = ax.f1; s.vy = ay.f0; s.vz = az.f1;
+    s.wx = ax.f1; s.wy = ay.f1; s.wz = az.f0;
+    return s;
+}
+__device__ __forceinline__ void fast_sample(const MacField &f, const FastGeom &F, const FastStencil &s, float &ox, float &oy,
+                                            float &oz) {
+    ox = trilerp_fast(f.U, s.bu, F.I + 1, (F.I + 1) * F.J, s.ux, s.uy, s.uz);
+    oy = trilerp_fast(f.V, s.bv, F.I, F.I * (F.J + 1), s.vx, s.vy, s.vz);
+    oz = trilerp_fast(f.W, s.bw, F.I, F.I * F.J, s.wx, s.wy, s.wz);
+}
+
 // Interpolation::trilinearInterpolate(vec3 p, double dx, Array3d<float>&)  interpolation.cpp:72-110
 // (node position narrowed to float, fraction = (float - float) * inv_dx in double)
 struct ScalarSample {
@@ -160,6 +227,18 @@ __device__ __forceinline__ void scalar_gradient(const ScalarSample &s, float &gx
     gx = (float)bilerp(fsub(v100, v000), fsub(v110, v010), fsub(v101, v001), fsub(v111, v011), s.fy, s.fz);
     gy = (float)bilerp(fsub(v010, v000), fsub(v110, v100), fsub(v011, v001), fsub(v111, v101), s.fx, s.fz);
     gz = (float)bilerp(fsub(v001, v000), fsub(v101, v100), fsub(v011, v010), fsub(v111, v110), s.fx, s.fy);
+}
+
+// Warp-aggregated append: the lanes that reach this call together take consecutive slots with ONE atomic
+// (queues fed by hundreds of thousands of threads would otherwise serialise on a single address in L2).
+__device__ __forceinline__ int warp_append_slot(int *counter) {
+    const unsigned int m = __activemask();
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(counter, __popc(m));
+    base = __shfl_sync(m, base, leader);
+    return base + __popc(m & ((1u << lane) - 1u));
 }
 
 // warp reductions

@@ -78,6 +78,8 @@ struct DeviceScalars {
     int sendCount[2], recvCount[2];
     int globalParticles;       // sum over ranks of the sort input (speed-limit rule)
     int globalRows;
+    int extCount[6];           // extrapolation frontier sizes, [component][parity]
+    int deferredCount;         // particles the single-precision G2P / RK3 kernels left to the literal ones
     // multigrid coarse solve etc.
     int pad[8];
 };
@@ -100,6 +102,7 @@ struct flip_ctx {
     int pressureMaxIter = 1000;
     int preconditioner = 1;
     int mgNu = 2, mgCoarseSweeps = 8;
+    int samplingMode = FLIP_SAMPLING_FAST;   // trilinear blend of G2P / RK3 in float (indices and weights stay exact)
     int pcgPersistent = 0;   // measured slower than the multi-launch solver at 2 M rows (occupancy-limited), kept selectable
     double mgOmega = 0.9, mgScale = 1.8;
     int maxParticlesPerCell = 250;
@@ -259,6 +262,12 @@ size_t kt_begin(flip_ctx *c);                    // records a start event, retur
 void kt_end(flip_ctx *c, int cls, size_t slot);  // records the stop event
 void kt_collect(flip_ctx *c);                    // after a stream sync: folds pending pairs into the sums
 inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
+// per-component stride of the extrapolation scratch arrays (level bytes, frontier lists): the largest face
+// count, padded and rounded so that every component's slice stays 256-byte aligned
+inline size_t ext_stride(const Dims &d) {
+    size_t m = (size_t)(d.nU > d.nV ? (d.nU > d.nW ? d.nU : d.nW) : (d.nV > d.nW ? d.nV : d.nW));
+    return ((m + 63) / 64 + 1) * 64;
+}
 inline bool slab_on(const flip_ctx *c) { return c->nranks > 1; }
 
 }  // namespace flip

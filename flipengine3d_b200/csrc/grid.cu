@@ -1,5 +1,6 @@
 // Grid-side streaming kernels of the FLIP step: layered velocity extrapolation, save, body force,
 // solid constraint.
+#include <algorithm>
 #include "device_math.cuh"
 #include "flip_internal.h"
 
@@ -8,73 +9,99 @@ namespace flip {
 static constexpr int TPB = 256;
 
 // ------------------------------------------------------------------------------------------------
-// GridUtils::extrapolateGrid  gridutils.cpp:32-228, restated as a frontier sweep.
+// GridUtils::extrapolateGrid  gridutils.cpp:32-228, restated as a frontier sweep over all three MAC
+// components at once (blockIdx.y = component).
 //
 // level grid (1 byte per face): 0 = KNOWN from the start (valid and not on the border),
 // 1..L = filled in layer l, 0xFE = border (the reference's DONE-from-the-start: never written, never
 // a source of propagation, but counted as a DONE neighbour), 0xFF = UNKNOWN.
-// Layer l: every face of the previous frontier (level l-1) claims its UNKNOWN 6-neighbours
-// (atomicCAS, so each face is listed once); each claimed face then takes the mean of its neighbours
-// that were DONE at that time (level < l, or border), summed in the order +i,-i,+j,-j,+k,-k
-// (gridutils.cpp:190-224).  Claiming and filling are separate launches, as in the reference, so the
-// result does not depend on thread order: bit-reproducible and equal to the reference's.
+// Layer l: every face of the previous frontier (level l-1) claims its UNKNOWN 6-neighbours by
+// setting their level to l (byte-wide atomicCAS, so each face is listed once); each claimed face then
+// takes the mean of its neighbours that were DONE before this layer (level < l, or border) -- faces
+// claimed in the same layer carry level l and are therefore not counted, which is the reference's
+// WAITING state -- summed in the order +i,-i,+j,-j,+k,-k (gridutils.cpp:190-224).  Claiming and filling
+// are separate launches, as in the reference, so the result does not depend on thread order:
+// bit-reproducible and equal to the reference's.
 // ------------------------------------------------------------------------------------------------
-__global__ void k_ext_init(const unsigned char *__restrict__ valid, unsigned char *__restrict__ level, int gi, int gj,
-                           int gk, int *__restrict__ frontier, int *__restrict__ count) {
-    long long n = (long long)gi * gj * gk;
-    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (t >= n) return;
-    int i = (int)(t % gi);
-    int j = (int)((t / gi) % gj);
-    int k = (int)(t / ((long long)gi * gj));
-    // Grid3d::isGridIndexOnBorder
-    bool border = (i == 0 || j == 0 || k == 0 || i == gi - 1 || j == gj - 1 || k == gk - 1);
-    unsigned char lv = 0xFF;
-    if (border) lv = 0xFE;
-    else if (valid[t]) lv = 0;
-    level[t] = lv;
-    if (lv == 0) {
-        // only faces with at least one non-valid, non-border neighbour can claim anything
-        long long sj = gi, sk = (long long)gi * gj;
-        bool open = false;
-        // neighbours are in range because the face is not on the border
-        auto unk = [&](long long q, int qi, int qj, int qk) {
-            bool b = (qi == 0 || qj == 0 || qk == 0 || qi == gi - 1 || qj == gj - 1 || qk == gk - 1);
-            return !b && !valid[q];
-        };
-        open = unk(t + 1, i + 1, j, k) || unk(t - 1, i - 1, j, k) || unk(t + sj, i, j + 1, k) ||
-               unk(t - sj, i, j - 1, k) || unk(t + sk, i, j, k + 1) || unk(t - sk, i, j, k - 1);
-        if (open) {
-            int slot = atomicAdd(count, 1);
-            frontier[slot] = (int)t;
+struct ExtComp {
+    float *grid;
+    const unsigned char *valid;
+    unsigned char *level;
+    int *frontier[2];
+    int *count;          // [2]
+    int gi, gj, gk;
+};
+struct ExtArgs {
+    ExtComp c[3];
+};
+
+// four consecutive faces per thread (the arrays are padded by 64 entries, so whole-word accesses stay in bounds)
+__global__ void k_ext_init(ExtArgs A) {
+    const ExtComp &C = A.c[blockIdx.y];
+    const int gi = C.gi, gj = C.gj, gk = C.gk;
+    const long long n = (long long)gi * gj * gk;
+    const long long t0 = 4 * (blockIdx.x * (long long)blockDim.x + threadIdx.x);
+    if (t0 >= n) return;
+    const unsigned int v4 = *reinterpret_cast<const unsigned int *>(C.valid + t0);
+    int i = (int)(t0 % gi);
+    int j = (int)((t0 / gi) % gj);
+    int k = (int)(t0 / ((long long)gi * gj));
+    const long long sj = gi, sk = (long long)gi * gj;
+    unsigned int l4 = 0;
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+        const long long t = t0 + m;
+        unsigned int lv = 0xFFu;
+        if (t < n) {
+            // Grid3d::isGridIndexOnBorder
+            const bool border = (i == 0 || j == 0 || k == 0 || i == gi - 1 || j == gj - 1 || k == gk - 1);
+            const bool val = ((v4 >> (8 * m)) & 0xFFu) != 0;
+            if (border) lv = 0xFEu;
+            else if (val) {
+                lv = 0u;
+                // only faces with at least one non-valid, non-border neighbour can claim anything
+                // (neighbours are in range because the face is not on the border)
+                auto unk = [&](long long q, int qi, int qj, int qk) {
+                    bool b = (qi == 0 || qj == 0 || qk == 0 || qi == gi - 1 || qj == gj - 1 || qk == gk - 1);
+                    return !b && !C.valid[q];
+                };
+                const bool open = unk(t + 1, i + 1, j, k) || unk(t - 1, i - 1, j, k) || unk(t + sj, i, j + 1, k) ||
+                                  unk(t - sj, i, j - 1, k) || unk(t + sk, i, j, k + 1) || unk(t - sk, i, j, k - 1);
+                if (open) C.frontier[0][warp_append_slot(&C.count[0])] = (int)t;
+            }
         }
+        l4 |= lv << (8 * m);
+        if (++i == gi) { i = 0; if (++j == gj) { j = 0; k++; } }
     }
+    *reinterpret_cast<unsigned int *>(C.level + t0) = l4;
 }
 
 // _findExtrapolationCells (gridutils.cpp:123-177): frontier faces claim UNKNOWN neighbours.
-__global__ void k_ext_claim(unsigned char *__restrict__ level, int gi, int gj, const int *__restrict__ frontierIn,
-                            const int *__restrict__ countIn, int *__restrict__ frontierOut, int *__restrict__ countOut,
-                            int layer) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    int n = *countIn;
+__global__ void k_ext_claim(ExtArgs A, int layer) {
+    const ExtComp &C = A.c[blockIdx.y];
+    const int in = (layer - 1) & 1, out = layer & 1;
+    const int *__restrict__ frontierIn = C.frontier[in];
+    int *__restrict__ frontierOut = C.frontier[out];
+    unsigned char *level = C.level;
+    const int n = C.count[in];
+    const int sj = C.gi, sk = C.gi * C.gj;
     // grid-stride: the launch is sized for the worst case known on the host
-    for (; t < n; t += gridDim.x * blockDim.x) {
-        int f = frontierIn[t];
-        int sj = gi, sk = gi * gj;
-        int nb[6] = {f + 1, f - 1, f + sj, f - sj, f + sk, f - sk};
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+        const int f = frontierIn[t];
+        const int nb[6] = {f + 1, f - 1, f + sj, f - sj, f + sk, f - sk};
 #pragma unroll
         for (int m = 0; m < 6; m++) {
-            int q = nb[m];
+            const int q = nb[m];
+            if (level[q] != 0xFFu) continue;
             // byte-wide compare-and-swap through the containing 32-bit word
             unsigned int *word = (unsigned int *)(level + (q & ~3));
-            int shift = (q & 3) * 8;
+            const int shift = (q & 3) * 8;
             unsigned int old = *word;
             while (((old >> shift) & 0xFFu) == 0xFFu) {
-                unsigned int nw = (old & ~(0xFFu << shift)) | ((unsigned int)(0x80 | layer) << shift);
+                unsigned int nw = (old & ~(0xFFu << shift)) | ((unsigned int)layer << shift);
                 unsigned int prev = atomicCAS(word, old, nw);
                 if (prev == old) {
-                    int slot = atomicAdd(countOut, 1);
-                    frontierOut[slot] = q;
+                    frontierOut[warp_append_slot(&C.count[out])] = q;
                     break;
                 }
                 old = prev;
@@ -83,16 +110,19 @@ __global__ void k_ext_claim(unsigned char *__restrict__ level, int gi, int gj, c
     }
 }
 
-// _extrapolateCellsThread (gridutils.cpp:179-228). Claimed faces carry level 0x80|layer ("WAITING")
-// until this kernel ends, so they are never counted as DONE neighbours of each other.
-__global__ void k_ext_fill(float *__restrict__ grid, unsigned char *__restrict__ level, int gi, int gj,
-                           const int *__restrict__ frontier, const int *__restrict__ count, int layer) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    int n = *count;
-    for (; t < n; t += gridDim.x * blockDim.x) {
-        int f = frontier[t];
-        int sj = gi, sk = gi * gj;
-        int nb[6] = {f + 1, f - 1, f + sj, f - sj, f + sk, f - sk};
+// _extrapolateCellsThread (gridutils.cpp:179-228).  Also clears the counter the next layer appends to.
+__global__ void k_ext_fill(ExtArgs A, int layer) {
+    const ExtComp &C = A.c[blockIdx.y];
+    const int in = (layer - 1) & 1, out = layer & 1;
+    const int *__restrict__ frontier = C.frontier[out];
+    const unsigned char *__restrict__ level = C.level;
+    float *grid = C.grid;
+    const int n = C.count[out];
+    const int sj = C.gi, sk = C.gi * C.gj;
+    if (blockIdx.x == 0 && threadIdx.x == 0) C.count[in] = 0;    // consumed by this layer's claim launch
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+        const int f = frontier[t];
+        const int nb[6] = {f + 1, f - 1, f + sj, f - sj, f + sk, f - sk};
         float sum = 0.0f;
         int cnt = 0;
 #pragma unroll
@@ -105,43 +135,37 @@ __global__ void k_ext_fill(float *__restrict__ grid, unsigned char *__restrict__
     }
 }
 
-// WAITING -> KNOWN for the next layer (gridutils.cpp:96-98)
-__global__ void k_ext_commit(unsigned char *__restrict__ level, const int *__restrict__ frontier,
-                             const int *__restrict__ count, int layer, int *__restrict__ nextCountToZero) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    int n = *count;
-    if (t == 0 && nextCountToZero) *nextCountToZero = 0;
-    for (; t < n; t += gridDim.x * blockDim.x) level[frontier[t]] = (unsigned char)layer;
-}
-
-static void extrapolate_component(flip_ctx *c, float *grid, const unsigned char *valid, int gi, int gj, int gk) {
-    cudaStream_t st = c->stream;
-    long long n = (long long)gi * gj * gk;
-    int *cnt0 = &c->dS->frontierCount[0];
-    int *cnt1 = &c->dS->frontierCount[1];
-    FLIP_CUDA_CHECK(cudaMemsetAsync(cnt0, 0, 2 * sizeof(int), st));
-    k_ext_init<<<cdiv(n, TPB), TPB, 0, st>>>(valid, c->status, gi, gj, gk, c->frontier[0], cnt0);
-    c->launches++;
-    // frontier sizes live on the device; launches use a fixed grid with a grid-stride loop
-    int blocks = 148 * 8;
-    int *cnt[2] = {cnt0, cnt1};
-    for (int layer = 1; layer <= c->extrapolationLayers; layer++) {
-        int in = (layer - 1) & 1, out = layer & 1;
-        k_ext_claim<<<blocks, TPB, 0, st>>>(c->status, gi, gj, c->frontier[in], cnt[in], c->frontier[out], cnt[out], layer);
-        k_ext_fill<<<blocks, TPB, 0, st>>>(grid, c->status, gi, gj, c->frontier[out], cnt[out], layer);
-        k_ext_commit<<<blocks, TPB, 0, st>>>(c->status, c->frontier[out], cnt[out], layer, cnt[in]);
-        c->launches += 3;
-    }
-    FLIP_CUDA_CHECK(cudaGetLastError());
-}
-
 // MACVelocityField::extrapolateVelocityField  macvelocityfield.cpp:671-677
 void stage_extrapolate(flip_ctx *c) {
     const Dims &d = c->d;
+    cudaStream_t st = c->stream;
     size_t kt = kt_begin(c);
-    extrapolate_component(c, c->U, c->validU, d.I + 1, d.J, d.K);
-    extrapolate_component(c, c->V, c->validV, d.I, d.J + 1, d.K);
-    extrapolate_component(c, c->W, c->validW, d.I, d.J, d.K + 1);
+    const size_t nmax = ext_stride(d);   // per-component stride of the scratch arrays
+    ExtArgs A;
+    float *grids[3] = {c->U, c->V, c->W};
+    const unsigned char *valids[3] = {c->validU, c->validV, c->validW};
+    const int gi[3] = {d.I + 1, d.I, d.I}, gj[3] = {d.J, d.J + 1, d.J}, gk[3] = {d.K, d.K, d.K + 1};
+    long long nbig = 0;
+    for (int m = 0; m < 3; m++) {
+        A.c[m].grid = grids[m]; A.c[m].valid = valids[m];
+        A.c[m].level = c->status + m * nmax;
+        A.c[m].frontier[0] = c->frontier[0] + m * nmax;
+        A.c[m].frontier[1] = c->frontier[1] + m * nmax;
+        A.c[m].count = &c->dS->extCount[2 * m];
+        A.c[m].gi = gi[m]; A.c[m].gj = gj[m]; A.c[m].gk = gk[m];
+        nbig = std::max(nbig, (long long)gi[m] * gj[m] * gk[m]);
+    }
+    FLIP_CUDA_CHECK(cudaMemsetAsync(c->dS->extCount, 0, 6 * sizeof(int), st));
+    k_ext_init<<<dim3(cdiv(cdiv(nbig, 4), TPB), 3), TPB, 0, st>>>(A);
+    c->launches++;
+    // frontier sizes live on the device; launches use a fixed grid with a grid-stride loop
+    const dim3 blocks(148 * 3, 3);
+    for (int layer = 1; layer <= c->extrapolationLayers; layer++) {
+        k_ext_claim<<<blocks, TPB, 0, st>>>(A, layer);
+        k_ext_fill<<<blocks, TPB, 0, st>>>(A, layer);
+        c->launches += 2;
+    }
+    FLIP_CUDA_CHECK(cudaGetLastError());
     kt_end(c, FLIP_KERNEL_EXTRAPOLATE, kt);
 }
 

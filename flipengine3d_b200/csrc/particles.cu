@@ -286,8 +286,18 @@ __global__ void k_gather(ParticleSoA src, ParticleSoA dst, const int *__restrict
         dst.vx[t] = vx; dst.vy[t] = vy; dst.vz[t] = vz;
         sp2 = lengthsq3(vx, vy, vz);   // vmath::dot(mp.velocity, mp.velocity)  :5558
     }
+    // one atomic per block at most, and only when it can raise the maximum (hundreds of thousands of
+    // same-address atomics would serialise in L2)
+    __shared__ float shmax[TPB / 32];
     sp2 = warp_max(sp2);
-    if ((threadIdx.x & 31) == 0 && sp2 > 0.0f) atomicMax(&S->maxSpeedSqBits, __float_as_uint(sp2));
+    if ((threadIdx.x & 31) == 0) shmax[threadIdx.x >> 5] = sp2;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = (threadIdx.x < TPB / 32) ? shmax[threadIdx.x] : 0.0f;
+        v = warp_max(v);
+        if (threadIdx.x == 0 && v > 0.0f && __float_as_uint(v) > __ldcg(&S->maxSpeedSqBits))
+            atomicMax(&S->maxSpeedSqBits, __float_as_uint(v));
+    }
 }
 
 __global__ void k_reset_sort_scalars(DeviceScalars *S) {
@@ -691,7 +701,7 @@ __global__ void __launch_bounds__(128) k_sdf_p2g(ParticleSoA p, const int *__res
     const float thr = fmul(fmul(1.45f, (float)g.dx), fmul(1.45f, (float)g.dx));
     const int cell = i + I * (j + J * k);
     if (!(best2 < thr)) {
-        int slot = atomicAdd(farCount, 1);
+        int slot = warp_append_slot(farCount);
         farCells[slot] = cell;
         farBest[slot] = best2;
         return;
@@ -842,22 +852,54 @@ struct AdvectParams {
     float stepDistance;            // _markerParticleStepDistanceFactor * (float)_dx
     float maxResolvedDistance;     // _CFLConditionNumber * _dx
     double pushOut;                // _solidBufferWidth * _dx (float*double -> double)
+    FastGeom F;                    // single-precision sampling fast path (device_math.cuh)
 };
 
-__global__ void k_g2p(ParticleSoA p, AdvectParams a, MacField fnew, MacField fold) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= a.n) return;
-    float x = p.px[t], y = p.py[t], z = p.pz[t];
-    float nx, ny, nz, ox, oy, oz;
-    sample_velocity(fnew, a.G, a.dx, a.invdx, a.hdx, x, y, z, nx, ny, nz);
-    sample_velocity(fold, a.G, a.dx, a.invdx, a.hdx, x, y, z, ox, oy, oz);
-    // vFLIP = v + vPIC - vOld ; v = ratio*vPIC + (1-ratio)*vFLIP   (fluidsimulation.cpp:4084-4090)
+// Velocity sample for the particle kernels.  FAST (flip_set_sampling_mode, power-of-two dx): single-precision
+// blend on the interior fast path of device_math.cuh, the literal double-precision restatement elsewhere.
+// FLIP update of one particle from the two sampled velocities: vFLIP = v + vPIC - vOld ;
+// v = ratio*vPIC + (1-ratio)*vFLIP   (fluidsimulation.cpp:4084-4090)
+__device__ __forceinline__ void picflip_update(ParticleSoA &p, const AdvectParams &a, int t, float nx, float ny, float nz,
+                                               float ox, float oy, float oz) {
     float fx = fsub(fadd(p.vx[t], nx), ox);
     float fy = fsub(fadd(p.vy[t], ny), oy);
     float fz = fsub(fadd(p.vz[t], nz), oz);
     p.vx[t] = fadd(fmul(a.ratioPIC, nx), fmul(a.ratioFLIP, fx));
     p.vy[t] = fadd(fmul(a.ratioPIC, ny), fmul(a.ratioFLIP, fy));
     p.vz[t] = fadd(fmul(a.ratioPIC, nz), fmul(a.ratioFLIP, fz));
+}
+
+// Literal double-precision sampling (FLIP_SAMPLING_EXACT, non-power-of-two dx, and the particles the
+// single-precision kernel deferred).  list == nullptr: every particle; else the listed ones.
+__global__ void k_g2p(ParticleSoA p, AdvectParams a, MacField fnew, MacField fold, const int *__restrict__ list,
+                      const int *__restrict__ listCount) {
+    const int n = list ? *listCount : a.n;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+        const int t = list ? list[q] : q;
+        float x = p.px[t], y = p.py[t], z = p.pz[t];
+        float nx, ny, nz, ox, oy, oz;
+        sample_velocity(fnew, a.G, a.dx, a.invdx, a.hdx, x, y, z, nx, ny, nz);
+        sample_velocity(fold, a.G, a.dx, a.invdx, a.hdx, x, y, z, ox, oy, oz);
+        picflip_update(p, a, t, nx, ny, nz, ox, oy, oz);
+    }
+}
+
+// Single-precision blend (FLIP_SAMPLING_FAST): exact indices and weights, see device_math.cuh.  Particles
+// outside the interior box (none in a walled domain) are queued for the literal kernel.
+__global__ void k_g2p_fast(ParticleSoA p, AdvectParams a, MacField fnew, MacField fold, int *__restrict__ deferred,
+                           int *__restrict__ deferredCount) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.n) return;
+    float x = p.px[t], y = p.py[t], z = p.pz[t];
+    if (!fast_interior(a.F, x, y, z)) {
+        deferred[warp_append_slot(deferredCount)] = t;
+        return;
+    }
+    float nx, ny, nz, ox, oy, oz;
+    const FastStencil s = fast_stencil(a.F, x, y, z);   // both fields share indices and weights
+    fast_sample(fnew, a.F, s, nx, ny, nz);
+    fast_sample(fold, a.F, s, ox, oy, oz);
+    picflip_update(p, a, t, nx, ny, nz, ox, oy, oz);
 }
 
 // AABB::isPointInside  aabb.cpp:130-133
@@ -945,24 +987,74 @@ __device__ void resolve_collision(const AdvectParams &a, const float *__restrict
     nx = rx; ny = ry; nz = rz;
 }
 
-__global__ void k_advance(ParticleSoA p, AdvectParams a, MacField f, const float *__restrict__ phiS,
-                          const unsigned char *__restrict__ ns) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= a.n) return;
-    float x = p.px[t], y = p.py[t], z = p.pz[t];
-    // _RK3  fluidsimulation.cpp:4191-4198
-    float k1x, k1y, k1z, k2x, k2y, k2z, k3x, k3y, k3z;
-    sample_velocity(f, a.G, a.dx, a.invdx, a.hdx, x, y, z, k1x, k1y, k1z);
-    sample_velocity(f, a.G, a.dx, a.invdx, a.hdx, fadd(x, fmul(k1x, a.c1)), fadd(y, fmul(k1y, a.c1)),
-                    fadd(z, fmul(k1z, a.c1)), k2x, k2y, k2z);
-    sample_velocity(f, a.G, a.dx, a.invdx, a.hdx, fadd(x, fmul(k2x, a.c2)), fadd(y, fmul(k2y, a.c2)),
-                    fadd(z, fmul(k2z, a.c2)), k3x, k3y, k3z);
+// Ralston RK3 increment from the three samples (_RK3  fluidsimulation.cpp:4191-4198)
+__device__ __forceinline__ void rk3_combine(const AdvectParams &a, float x, float y, float z, float k1x, float k1y, float k1z,
+                                            float k2x, float k2y, float k2z, float k3x, float k3y, float k3z, float &nx,
+                                            float &ny, float &nz) {
     float sx = fadd(fadd(fmul(k1x, 2.0f), fmul(k2x, 3.0f)), fmul(k3x, 4.0f));
     float sy = fadd(fadd(fmul(k1y, 2.0f), fmul(k2y, 3.0f)), fmul(k3y, 4.0f));
     float sz = fadd(fadd(fmul(k1z, 2.0f), fmul(k2z, 3.0f)), fmul(k3z, 4.0f));
-    float nx = fadd(x, fmul(sx, a.c3)), ny = fadd(y, fmul(sy, a.c3)), nz = fadd(z, fmul(sz, a.c3));
+    nx = fadd(x, fmul(sx, a.c3)); ny = fadd(y, fmul(sy, a.c3)); nz = fadd(z, fmul(sz, a.c3));
+}
+
+// literal sampling; list as in k_g2p
+__global__ void k_advance(ParticleSoA p, AdvectParams a, MacField f, const float *__restrict__ phiS,
+                          const unsigned char *__restrict__ ns, const int *__restrict__ list,
+                          const int *__restrict__ listCount) {
+    const int n = list ? *listCount : a.n;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+        const int t = list ? list[q] : q;
+        float x = p.px[t], y = p.py[t], z = p.pz[t];
+        float k1x, k1y, k1z, k2x, k2y, k2z, k3x, k3y, k3z;
+        sample_velocity(f, a.G, a.dx, a.invdx, a.hdx, x, y, z, k1x, k1y, k1z);
+        sample_velocity(f, a.G, a.dx, a.invdx, a.hdx, fadd(x, fmul(k1x, a.c1)), fadd(y, fmul(k1y, a.c1)),
+                        fadd(z, fmul(k1z, a.c1)), k2x, k2y, k2z);
+        sample_velocity(f, a.G, a.dx, a.invdx, a.hdx, fadd(x, fmul(k2x, a.c2)), fadd(y, fmul(k2y, a.c2)),
+                        fadd(z, fmul(k2z, a.c2)), k3x, k3y, k3z);
+        float nx, ny, nz;
+        rk3_combine(a, x, y, z, k1x, k1y, k1z, k2x, k2y, k2z, k3x, k3y, k3z, nx, ny, nz);
+        resolve_collision(a, phiS, ns, x, y, z, nx, ny, nz);
+        p.px[t] = nx; p.py[t] = ny; p.pz[t] = nz;
+    }
+}
+
+// single-precision blend; a particle whose start or intermediate RK positions leave the interior box is queued
+// for the literal kernel (untouched here)
+__global__ void k_advance_fast(ParticleSoA p, AdvectParams a, MacField f, const float *__restrict__ phiS,
+                               const unsigned char *__restrict__ ns, int *__restrict__ deferred,
+                               int *__restrict__ deferredCount) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.n) return;
+    const float x = p.px[t], y = p.py[t], z = p.pz[t];
+    float k1x, k1y, k1z, k2x, k2y, k2z, k3x, k3y, k3z;
+    bool ok = fast_interior(a.F, x, y, z);
+    if (ok) {
+        fast_sample(f, a.F, fast_stencil(a.F, x, y, z), k1x, k1y, k1z);
+        const float x2 = fadd(x, fmul(k1x, a.c1)), y2 = fadd(y, fmul(k1y, a.c1)), z2 = fadd(z, fmul(k1z, a.c1));
+        ok = fast_interior(a.F, x2, y2, z2);
+        if (ok) {
+            fast_sample(f, a.F, fast_stencil(a.F, x2, y2, z2), k2x, k2y, k2z);
+            const float x3 = fadd(x, fmul(k2x, a.c2)), y3 = fadd(y, fmul(k2y, a.c2)), z3 = fadd(z, fmul(k2z, a.c2));
+            ok = fast_interior(a.F, x3, y3, z3);
+            if (ok) fast_sample(f, a.F, fast_stencil(a.F, x3, y3, z3), k3x, k3y, k3z);
+        }
+    }
+    if (!ok) {
+        deferred[warp_append_slot(deferredCount)] = t;
+        return;
+    }
+    float nx, ny, nz;
+    rk3_combine(a, x, y, z, k1x, k1y, k1z, k2x, k2y, k2z, k3x, k3y, k3z, nx, ny, nz);
     resolve_collision(a, phiS, ns, x, y, z, nx, ny, nz);
     p.px[t] = nx; p.py[t] = ny; p.pz[t] = nz;
+}
+
+// single-precision sampling needs a power-of-two dx (exact index / weight arithmetic in float) and extents
+// whose coordinates stay far below 2^24 ulps
+static bool sampling_fast(const flip_ctx *c) {
+    int ex = 0;
+    return c->samplingMode == FLIP_SAMPLING_FAST && frexp(c->d.dx, &ex) == 0.5 &&
+           std::max(c->d.I, std::max(c->d.J, c->d.Kg)) <= 4096;
 }
 
 static AdvectParams make_advect_params(const flip_ctx *c, double dt) {
@@ -998,6 +1090,10 @@ static AdvectParams make_advect_params(const flip_ctx *c, double dt) {
     a.stepDistance = c->markerParticleStepDistanceFactor * (float)d.dx;
     a.maxResolvedDistance = (float)(c->CFL * d.dx);
     a.pushOut = (double)(float)c->solidBufferWidth * d.dx;
+    a.F.invdx = (float)(1.0 / d.dx); a.F.hdx = (float)(0.5 * d.dx);
+    a.F.lox = a.F.loy = (float)d.dx; a.F.loz = (float)((d.kOff + 1) * d.dx);
+    a.F.hix = (float)((d.I - 1) * d.dx); a.F.hiy = (float)((d.J - 1) * d.dx); a.F.hiz = (float)((d.kOff + d.K - 1) * d.dx);
+    a.F.I = d.I; a.F.J = d.J; a.F.kOff = d.kOff;
     return a;
 }
 
@@ -1006,7 +1102,16 @@ void stage_g2p(flip_ctx *c) {
     AdvectParams a = make_advect_params(c, 0.0);
     MacField fn{c->U, c->V, c->W}, fo{c->sU, c->sV, c->sW};
     size_t kt = kt_begin(c);
-    k_g2p<<<cdiv(c->np, TPB), TPB, 0, c->stream>>>(soa_offset(c->P[c->cur_buf], c->ownedBegin), a, fn, fo);
+    const ParticleSoA P = soa_offset(c->P[c->cur_buf], c->ownedBegin);
+    if (sampling_fast(c)) {
+        int *deferred = c->sortIdx, *cnt = &c->dS->deferredCount;     // the sort scratch is idle between sorts
+        FLIP_CUDA_CHECK(cudaMemsetAsync(cnt, 0, sizeof(int), c->stream));
+        k_g2p_fast<<<cdiv(c->np, TPB), TPB, 0, c->stream>>>(P, a, fn, fo, deferred, cnt);
+        k_g2p<<<148, TPB, 0, c->stream>>>(P, a, fn, fo, deferred, cnt);
+        c->launches++;
+    } else {
+        k_g2p<<<cdiv(c->np, TPB), TPB, 0, c->stream>>>(P, a, fn, fo, nullptr, nullptr);
+    }
     kt_end(c, FLIP_KERNEL_G2P, kt);
     c->launches++;
     FLIP_CUDA_CHECK(cudaGetLastError());
@@ -1017,7 +1122,16 @@ void stage_advance(flip_ctx *c, double dt) {
         AdvectParams a = make_advect_params(c, dt);
         MacField fn{c->U, c->V, c->W};
         size_t kt = kt_begin(c);
-        k_advance<<<cdiv(c->np, TPB), TPB, 0, c->stream>>>(soa_offset(c->P[c->cur_buf], c->ownedBegin), a, fn, c->phiS, c->nearSolid);
+        const ParticleSoA P = soa_offset(c->P[c->cur_buf], c->ownedBegin);
+        if (sampling_fast(c)) {
+            int *deferred = c->sortIdx, *cnt = &c->dS->deferredCount;
+            FLIP_CUDA_CHECK(cudaMemsetAsync(cnt, 0, sizeof(int), c->stream));
+            k_advance_fast<<<cdiv(c->np, TPB), TPB, 0, c->stream>>>(P, a, fn, c->phiS, c->nearSolid, deferred, cnt);
+            k_advance<<<148, TPB, 0, c->stream>>>(P, a, fn, c->phiS, c->nearSolid, deferred, cnt);
+            c->launches++;
+        } else {
+            k_advance<<<cdiv(c->np, TPB), TPB, 0, c->stream>>>(P, a, fn, c->phiS, c->nearSolid, nullptr, nullptr);
+        }
         kt_end(c, FLIP_KERNEL_ADVANCE, kt);
         c->launches++;
         FLIP_CUDA_CHECK(cudaGetLastError());

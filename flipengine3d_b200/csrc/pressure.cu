@@ -248,47 +248,53 @@ __global__ void k_pcg_scalars_init(DeviceScalars *S, double tolFactor) {
     for (int q = 0; q < 3; q++) { S->dotSZ[q] = 0.0; S->rho[q] = 0.0; S->rMaxBits[q] = 0ull; }
 }
 
+// The PCG passes below run grid-stride over the active segments with a grid capped at one resident wave
+// (seg_blocks): per-thread partial sums span several segments, so a pass issues ~1 k instead of ~9 k
+// same-address atomics for its dot product / norm.
+
 // z = A s ; dotSZ += s.z
-__global__ void k_pcg_spmv(const int *__restrict__ segCell, const unsigned int *__restrict__ segMask, PcgParams pp,
-                           const double *__restrict__ Adiag, const float *__restrict__ AoffU,
-                           const float *__restrict__ AoffV, const float *__restrict__ AoffW,
-                           const double *__restrict__ s, double *__restrict__ z, DeviceScalars *S, int it) {
+__global__ void __launch_bounds__(TPB, 6) k_pcg_spmv(const int *__restrict__ segCell, const unsigned int *__restrict__ segMask,
+                                                     PcgParams pp, const double *__restrict__ Adiag,
+                                                     const float *__restrict__ AoffU, const float *__restrict__ AoffV,
+                                                     const float *__restrict__ AoffW, const double *__restrict__ s,
+                                                     double *__restrict__ z, DeviceScalars *S, int it) {
     if (S->pcgDone) return;
-    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31;
+    const int nseg = S->numSegments, nw = (gridDim.x * blockDim.x) >> 5;
     double part = 0.0;
-    if (warp < S->numSegments) {
-        int c = segCell[warp] + lane;
-        if ((segMask[warp] >> lane) & 1u) {
+    for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nseg; w += nw) {
+        int c = segCell[w] + lane;
+        if ((segMask[w] >> lane) & 1u) {
             double zv = apply_row(pp.g, c, pp.factor, Adiag, AoffU, AoffV, AoffW, s);
             z[c] = zv;
-            part = s[c] * zv;
+            part += s[c] * zv;
         }
     }
     block_add(part, &S->dotSZ[it % 3]);
 }
 
 // alpha = rho/(s.z); x += alpha s; r -= alpha z; rmax = ||r||_inf; [Jacobi: z = r/diag; rhoNew += z.r]
-__global__ void k_pcg_update(const int *__restrict__ segCell, const unsigned int *__restrict__ segMask,
-                             const double *__restrict__ Adiag, const double *__restrict__ s, double *__restrict__ z,
-                             double *__restrict__ x, double *__restrict__ r, DeviceScalars *S, int it, int jacobi) {
+__global__ void __launch_bounds__(TPB, 6) k_pcg_update(const int *__restrict__ segCell, const unsigned int *__restrict__ segMask,
+                                                       const double *__restrict__ Adiag, const double *__restrict__ s,
+                                                       double *__restrict__ z, double *__restrict__ x, double *__restrict__ r,
+                                                       DeviceScalars *S, int it, int jacobi) {
     if (S->pcgDone) return;
-    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    int lane = threadIdx.x & 31;
-    double alpha = S->rho[it % 3] / S->dotSZ[it % 3];
+    const int lane = threadIdx.x & 31;
+    const int nseg = S->numSegments, nw = (gridDim.x * blockDim.x) >> 5;
+    const double alpha = S->rho[it % 3] / S->dotSZ[it % 3];
     double part = 0.0, rabs = 0.0;
-    if (warp < S->numSegments) {
-        int c = segCell[warp] + lane;
-        if ((segMask[warp] >> lane) & 1u) {
+    for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nseg; w += nw) {
+        int c = segCell[w] + lane;
+        if ((segMask[w] >> lane) & 1u) {
             x[c] += alpha * s[c];
             double rv = r[c] - alpha * z[c];
             r[c] = rv;
-            rabs = fabs(rv);
+            rabs = fmax(rabs, fabs(rv));
             if (jacobi) {
                 double d = Adiag[c];
                 double zv = (d != 0.0) ? rv / d : 0.0;
                 z[c] = zv;
-                part = zv * rv;
+                part += zv * rv;
             }
         }
     }
@@ -318,12 +324,14 @@ __global__ void k_pcg_direction(const int *__restrict__ segCell, const unsigned 
     double rho = S->rho[it % 3], rhoNew = S->rho[(it + 1) % 3];
     bool converged = rmax <= S->pcgTol;
     bool breakdown = !converged && (rhoNew == 0.0 || rhoNew != rhoNew);
-    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    int lane = threadIdx.x & 31;
-    if (!converged && !breakdown && warp < S->numSegments) {
-        double beta = rhoNew / rho;
-        int c = segCell[warp] + lane;
-        if ((segMask[warp] >> lane) & 1u) s[c] = z[c] + beta * s[c];
+    const int lane = threadIdx.x & 31;
+    if (!converged && !breakdown) {
+        const double beta = rhoNew / rho;
+        const int nseg = S->numSegments, nw = (gridDim.x * blockDim.x) >> 5;
+        for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nseg; w += nw) {
+            int c = segCell[w] + lane;
+            if ((segMask[w] >> lane) & 1u) s[c] = z[c] + beta * s[c];
+        }
     }
     // the last block to finish publishes the scalars (no other block reads them after this point in
     // this launch: every block sampled them above, before any block can reach the ticket below only
@@ -414,8 +422,25 @@ __device__ __forceinline__ float mg_offsum_corrected(const MgLevel &L, const MgL
     return s;
 }
 
+// the iterate after one sweep from a zero guess, at any cell q: what mode 3 reads instead of a stored array
+__device__ __forceinline__ float mg_first(const MgLevel &L, int q, float omega) {
+    float inv = L.invD[q];
+    return (inv == 0.0f) ? 0.0f : omega * inv * L.b[q];
+}
+__device__ __forceinline__ float mg_offsum_first(const MgLevel &L, int c, int i, int j, int k, float omega) {
+    float s = 0.0f, a;
+    if (k > 0) { a = L.oW[c - L.sk]; if (a != 0.0f) s += a * mg_first(L, c - L.sk, omega); }
+    if (j > 0) { a = L.oV[c - L.sj]; if (a != 0.0f) s += a * mg_first(L, c - L.sj, omega); }
+    if (i > 0) { a = L.oU[c - 1];    if (a != 0.0f) s += a * mg_first(L, c - 1, omega); }
+    a = L.oU[c]; if (a != 0.0f) s += a * mg_first(L, c + 1, omega);
+    a = L.oV[c]; if (a != 0.0f) s += a * mg_first(L, c + L.sj, omega);
+    a = L.oW[c]; if (a != 0.0f) s += a * mg_first(L, c + L.sk, omega);
+    return s;
+}
+
 // one damped-Jacobi sweep at cell c of a dense level.  mode 0: from a zero guess; 1: regular;
-// 2: regular on (xin + scale * P e)
+// 2: regular on (xin + scale * P e); 3: the first TWO sweeps from a zero guess in one pass (the first one is
+// pointwise, so its result at the six neighbours is recomputed instead of being stored and re-read)
 __device__ __forceinline__ float mg_sweep_cell(const MgLevel &L, const MgLevel &C, const float *xin, const float *e,
                                                float omega, float scale, int mode, int c, int i, int j, int k) {
     float inv = L.invD[c];
@@ -423,7 +448,8 @@ __device__ __forceinline__ float mg_sweep_cell(const MgLevel &L, const MgLevel &
     float b = L.b[c];
     if (mode == 0) return omega * inv * b;
     float xc, ns;
-    if (mode == 1) { xc = xin[c]; ns = mg_offsum(L, xin, c, i, j, k); }
+    if (mode == 3) { xc = omega * inv * b; ns = mg_offsum_first(L, c, i, j, k, omega); }
+    else if (mode == 1) { xc = xin[c]; ns = mg_offsum(L, xin, c, i, j, k); }
     else { xc = mg_corrected(L, C, xin, e, scale, c, i, j, k); ns = mg_offsum_corrected(L, C, xin, e, scale, c, i, j, k); }
     return (1.0f - omega) * xc + omega * inv * (b + ns);
 }
@@ -463,6 +489,57 @@ __global__ void k_mg_restrict(MgLevel F, MgLevel C, const float *x, const Device
     C.b[c] = mg_restrict_cell(F, x, i, j, k);
 }
 
+// ---- the same passes driven by the list of ACTIVE 32-cell segments of a level (rebuilt every solve): most of
+// the box is air, and a dense launch over a coarse level spends its time finding that out
+__global__ void k_mg_build_list(MgLevel L, int *__restrict__ list, int *__restrict__ count) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    int c = warp * 32 + lane;
+    bool act = (c < L.n) && L.invD[c] != 0.0f;
+    unsigned int m = __ballot_sync(0xffffffffu, act);
+    if (lane == 0 && m) list[atomicAdd(count, 1)] = warp * 32;
+}
+
+__global__ void k_mg_sweep_list(MgLevel L, MgLevel C, const float *xin, const float *e, float *xout, float omega,
+                                float scale, int mode, const int *__restrict__ list, const int *__restrict__ count,
+                                const DeviceScalars *S) {
+    if (S->pcgDone) return;
+    const int nseg = *count;
+    const int lane = threadIdx.x & 31;
+    const int nw = (gridDim.x * blockDim.x) >> 5;
+    for (int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < nseg; s += nw) {
+        int c = list[s] + lane;
+        if (c < L.n) {
+            int i = c % L.I, j = (c / L.I) % L.J, k = c / L.sk;
+            xout[c] = mg_sweep_cell(L, C, xin, e, omega, scale, mode, c, i, j, k);
+        }
+    }
+}
+
+// b_C = P^T (b_F - A_F x_F) with EIGHT threads per coarse cell (one per child, summed by a fixed shuffle tree:
+// deterministic), coarse cells taken from the active list of level C; one 256-thread block per coarse segment
+__global__ void __launch_bounds__(256) k_mg_restrict_list(MgLevel F, MgLevel C, const float *x,
+                                                          const int *__restrict__ list, const int *__restrict__ count,
+                                                          const DeviceScalars *S) {
+    if (S->pcgDone) return;
+    const int nseg = *count;
+    const int t = threadIdx.x, q = t & 7;
+    for (int s = blockIdx.x; s < nseg; s += gridDim.x) {
+        const int cc = list[s] + (t >> 3);
+        float v = 0.0f;
+        const bool act = (cc < C.n) && C.invD[cc] != 0.0f;
+        if (act) {
+            int ci = cc % C.I, cj = (cc / C.I) % C.J, ck = cc / C.sk;
+            int i = 2 * ci + (q & 1), j = 2 * cj + ((q >> 1) & 1), k = 2 * ck + (q >> 2);
+            if (i < F.I && j < F.J && k < F.K) v = mg_residual_cell(F, x, i + F.sj * j + F.sk * k, i, j, k);
+        }
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        if (q == 0 && cc < C.n) C.b[cc] = act ? v : 0.0f;
+    }
+}
+
 struct MgSmallArgs {
     MgLevel lv[MG_MAX_LEVELS];
     int first, last;   // levels first..last are run by this launch (b of `first` is already set)
@@ -470,13 +547,12 @@ struct MgSmallArgs {
 };
 
 // the small levels of the V-cycle in one CTA: down, coarsest sweeps, up.  Leaves the result in lv[first].x.
-__global__ void __launch_bounds__(1024) k_mg_small(MgSmallArgs A, const DeviceScalars *S) {
-    if (S->pcgDone) return;
+__device__ __forceinline__ void mg_small_body(const MgLevel *lv, int first, int last, const MgParams &p) {
     const int tid = threadIdx.x, nt = blockDim.x;
-    const float omega = A.p.omega, scale = A.p.scale;
-    for (int l = A.first; l <= A.last; l++) {
-        const MgLevel &L = A.lv[l];
-        int sweeps = (l == A.last) ? A.p.coarseSweeps : A.p.nu;
+    const float omega = p.omega, scale = p.scale;
+    for (int l = first; l <= last; l++) {
+        const MgLevel &L = lv[l];
+        int sweeps = (l == last) ? p.coarseSweeps : p.nu;
         float *xa = L.x, *xb = L.x2;
         for (int s = 0; s < sweeps; s++) {
             for (int c = tid; c < L.n; c += nt) {
@@ -491,8 +567,8 @@ __global__ void __launch_bounds__(1024) k_mg_small(MgSmallArgs A, const DeviceSc
             for (int c = tid; c < L.n; c += nt) L.x[c] = L.x2[c];
             __syncthreads();
         }
-        if (l < A.last) {
-            const MgLevel &C = A.lv[l + 1];
+        if (l < last) {
+            const MgLevel &C = lv[l + 1];
             for (int c = tid; c < C.n; c += nt) {
                 int i = c % C.I, j = (c / C.I) % C.J, k = c / C.sk;
                 C.b[c] = (C.invD[c] == 0.0f) ? 0.0f : mg_restrict_cell(L, L.x, i, j, k);
@@ -500,11 +576,11 @@ __global__ void __launch_bounds__(1024) k_mg_small(MgSmallArgs A, const DeviceSc
             __syncthreads();
         }
     }
-    for (int l = A.last - 1; l >= A.first; l--) {
-        const MgLevel &L = A.lv[l];
-        const MgLevel &C = A.lv[l + 1];
+    for (int l = last - 1; l >= first; l--) {
+        const MgLevel &L = lv[l];
+        const MgLevel &C = lv[l + 1];
         float *xa = L.x, *xb = L.x2;
-        for (int s = 0; s < A.p.nu; s++) {
+        for (int s = 0; s < p.nu; s++) {
             for (int c = tid; c < L.n; c += nt) {
                 int i = c % L.I, j = (c / L.I) % L.J, k = c / L.sk;
                 xb[c] = mg_sweep_cell(L, C, xa, C.x, omega, scale, s == 0 ? 2 : 1, c, i, j, k);
@@ -512,10 +588,50 @@ __global__ void __launch_bounds__(1024) k_mg_small(MgSmallArgs A, const DeviceSc
             __syncthreads();
             float *t = xa; xa = xb; xb = t;
         }
-        if (A.p.nu & 1) {
+        if (p.nu & 1) {
             for (int c = tid; c < L.n; c += nt) L.x[c] = L.x2[c];
             __syncthreads();
         }
+    }
+}
+
+__global__ void __launch_bounds__(1024) k_mg_small(MgSmallArgs A, const DeviceScalars *S) {
+    if (S->pcgDone) return;
+    mg_small_body(A.lv, A.first, A.last, A.p);
+}
+
+// The same with every array of the small levels staged in shared memory (8 floats per cell; the levels below
+// MG_SMALL cells total ~150 KB): the ~30 barrier-separated phases then run at shared-memory instead of L2 latency.
+__global__ void __launch_bounds__(1024) k_mg_small_smem(MgSmallArgs A, const DeviceScalars *S) {
+    extern __shared__ float smf[];
+    __shared__ MgLevel sl[MG_MAX_LEVELS];
+    if (S->pcgDone) return;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    if (tid == 0) {
+        float *q = smf;
+        for (int l = A.first; l <= A.last; l++) {
+            MgLevel L = A.lv[l];
+            const int n = L.n;
+            L.diag = q; q += n; L.invD = q; q += n; L.oU = q; q += n; L.oV = q; q += n; L.oW = q; q += n;
+            L.b = q; q += n; L.x = q; q += n; L.x2 = q; q += n;
+            sl[l] = L;
+        }
+    }
+    __syncthreads();
+    for (int l = A.first; l <= A.last; l++) {
+        const MgLevel &G = A.lv[l];
+        const MgLevel &L = sl[l];
+        for (int c = tid; c < G.n; c += nt) {
+            L.diag[c] = G.diag[c]; L.invD[c] = G.invD[c]; L.oU[c] = G.oU[c]; L.oV[c] = G.oV[c]; L.oW[c] = G.oW[c];
+            if (l == A.first) L.b[c] = G.b[c];
+        }
+    }
+    __syncthreads();
+    mg_small_body(sl, A.first, A.last, A.p);
+    {
+        const MgLevel &G = A.lv[A.first];
+        const MgLevel &L = sl[A.first];
+        for (int c = tid; c < G.n; c += nt) G.x[c] = L.x[c];
     }
 }
 
@@ -568,29 +684,47 @@ __device__ __forceinline__ float mg0_offsum_corr(const Mg0 &M, const MgLevel &C,
     return M.fac * s;
 }
 
+// level-0 analogue of mg_offsum_first: the first sweep from a zero guess is omega * invD * (float)r, pointwise
+__device__ __forceinline__ float mg0_offsum_first(const Mg0 &M, const double *__restrict__ r, int c, float omega) {
+    const int sj = M.g.sj, sk = M.g.sk;
+    float a0 = M.oW[c - sk], a1 = M.oV[c - sj], a2 = M.oU[c - 1], a3 = M.oU[c], a4 = M.oV[c], a5 = M.oW[c];
+    double r0 = r[c - sk], r1 = r[c - sj], r2 = r[c - 1], r3 = r[c + 1], r4 = r[c + sj], r5 = r[c + sk];
+    float d0 = M.invD[c - sk], d1 = M.invD[c - sj], d2 = M.invD[c - 1], d3 = M.invD[c + 1], d4 = M.invD[c + sj], d5 = M.invD[c + sk];
+    float s = 0.0f;
+    s += (a0 != 0.0f && d0 != 0.0f) ? a0 * (omega * d0 * (float)r0) : 0.0f;
+    s += (a1 != 0.0f && d1 != 0.0f) ? a1 * (omega * d1 * (float)r1) : 0.0f;
+    s += (a2 != 0.0f && d2 != 0.0f) ? a2 * (omega * d2 * (float)r2) : 0.0f;
+    s += (a3 != 0.0f && d3 != 0.0f) ? a3 * (omega * d3 * (float)r3) : 0.0f;
+    s += (a4 != 0.0f && d4 != 0.0f) ? a4 * (omega * d4 * (float)r4) : 0.0f;
+    s += (a5 != 0.0f && d5 != 0.0f) ? a5 * (omega * d5 * (float)r5) : 0.0f;
+    return M.fac * s;
+}
+
 // mode as in mg_sweep_cell.  last != 0: also write z (fp64) and accumulate rho = z.r into slot `rhoSlot`.
-__global__ void k_mg0_sweep(const int *__restrict__ segCell, const unsigned int *__restrict__ segMask, Mg0 M, MgLevel C,
-                            const double *__restrict__ r, const float *xin, const float *e, float *xout, float omega,
-                            float scale, int mode, int last, double *zout, DeviceScalars *S, int rhoSlot) {
+__global__ void __launch_bounds__(TPB, 6) k_mg0_sweep(const int *__restrict__ segCell, const unsigned int *__restrict__ segMask,
+                                                      Mg0 M, MgLevel C, const double *__restrict__ r, const float *xin,
+                                                      const float *e, float *xout, float omega, float scale, int mode, int last,
+                                                      double *zout, DeviceScalars *S, int rhoSlot) {
     if (S->pcgDone) return;
-    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31;
+    const int nseg = S->numSegments, nw = (gridDim.x * blockDim.x) >> 5;
     double part = 0.0;
-    if (warp < S->numSegments) {
-        int c = segCell[warp] + lane;
-        if ((segMask[warp] >> lane) & 1u) {
+    for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nseg; w += nw) {
+        int c = segCell[w] + lane;
+        if ((segMask[w] >> lane) & 1u) {
             float inv = M.invD[c];
             double rd = r[c];
             float b = (float)rd;
             float xn;
             if (inv == 0.0f) xn = 0.0f;
             else if (mode == 0) xn = omega * inv * b;
+            else if (mode == 3) xn = (1.0f - omega) * (omega * inv * b) + omega * inv * (b + mg0_offsum_first(M, r, c, omega));
             else if (mode == 1) xn = (1.0f - omega) * xin[c] + omega * inv * (b + mg0_offsum(M, xin, c));
             else xn = (1.0f - omega) * mg0_corr(M, C, xin, e, scale, c) + omega * inv * (b + mg0_offsum_corr(M, C, xin, e, scale, c));
             xout[c] = xn;
             if (last) {
                 zout[c] = (double)xn;
-                part = (double)xn * rd;
+                part += (double)xn * rd;
             }
         }
     }
@@ -614,6 +748,32 @@ __global__ void k_mg0_restrict(Mg0 M, MgLevel C, const double *__restrict__ r, c
         s += (float)r[c] - ((float)M.Adiag[c] * x[c] - mg0_offsum(M, x, c));
     }
     C.b[cc] = s;
+}
+
+// the same with eight threads per coarse cell over the active segments of level 1 (see k_mg_restrict_list)
+__global__ void __launch_bounds__(256) k_mg0_restrict_list(Mg0 M, MgLevel C, const double *__restrict__ r, const float *x,
+                                                           const int *__restrict__ list, const int *__restrict__ count,
+                                                           const DeviceScalars *S) {
+    if (S->pcgDone) return;
+    const int nseg = *count;
+    const int t = threadIdx.x, q = t & 7;
+    for (int s = blockIdx.x; s < nseg; s += gridDim.x) {
+        const int cc = list[s] + (t >> 3);
+        float v = 0.0f;
+        const bool act = (cc < C.n) && C.invD[cc] != 0.0f;
+        if (act) {
+            int ci = cc % C.I, cj = (cc / C.I) % C.J, ck = cc / C.sk;
+            int i = 2 * ci + (q & 1), j = 2 * cj + ((q >> 1) & 1), k = 2 * ck + (q >> 2);
+            if (i < M.g.I && j < M.g.J && k < M.g.K) {
+                int c = i + M.g.sj * j + M.g.sk * k;
+                if ((M.rowBits[c >> 5] >> (c & 31)) & 1u) v = (float)r[c] - ((float)M.Adiag[c] * x[c] - mg0_offsum(M, x, c));
+            }
+        }
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        if (q == 0 && cc < C.n) C.b[cc] = act ? v : 0.0f;
+    }
 }
 
 // ---- hierarchy construction (every solve: the liquid region changes every substep)
@@ -1087,6 +1247,11 @@ struct PressureScratch {
     int firstSmall = 0;                // levels firstSmall..numLevels-1 run in one CTA (0: none)
     MgLevel lv[MG_MAX_LEVELS];         // lv[0]: only invD, x, x2 are used (dense over cells)
     float *pool = nullptr;             // one allocation behind all level arrays
+    // active 32-cell segments of the levels >= 1 (single-GPU solver): lists and their sizes on the device
+    int *segPool = nullptr;
+    int *lvSeg[MG_MAX_LEVELS] = {nullptr};
+    int *lvSegCount = nullptr;         // [MG_MAX_LEVELS]
+    size_t smallSmemBytes = 0;         // dynamic shared memory of k_mg_small_smem (0: does not fit, use k_mg_small)
     int coopBlocks = 0;                // grid of the persistent solver (SMs x resident CTAs)
     // z-slabs: levels >= Lc span the WHOLE domain and are held (redundantly) by every rank; the
     // restricted residual of level Lc is all-gathered once per V-cycle.  Lc == 0: every level is local.
@@ -1163,6 +1328,27 @@ void pressure_alloc(flip_ctx *c) {
             }
         }
     }
+    // active-segment lists of the coarse levels, and the shared-memory budget of the single-CTA levels
+    {
+        size_t ints = 0;
+        for (int l = 1; l < ps->numLevels; l++) ints += (size_t)cdiv(ps->lv[l].n, 32) + 1;
+        FLIP_CUDA_CHECK(cudaMalloc(&ps->segPool, sizeof(int) * (ints + MG_MAX_LEVELS)));
+        FLIP_CUDA_CHECK(cudaMemset(ps->segPool, 0, sizeof(int) * (ints + MG_MAX_LEVELS)));
+        ps->lvSegCount = ps->segPool;
+        int *q = ps->segPool + MG_MAX_LEVELS;
+        for (int l = 1; l < ps->numLevels; l++) { ps->lvSeg[l] = q; q += cdiv(ps->lv[l].n, 32) + 1; }
+        ps->smallSmemBytes = 0;
+        if (ps->firstSmall) {
+            size_t bytes = 0;
+            for (int l = ps->firstSmall; l < ps->numLevels; l++) bytes += 8ull * sizeof(float) * ps->lv[l].n;
+            int maxOptin = 0;
+            FLIP_CUDA_CHECK(cudaDeviceGetAttribute(&maxOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
+            if (bytes + 2048 <= (size_t)maxOptin) {
+                FLIP_CUDA_CHECK(cudaFuncSetAttribute(k_mg_small_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+                ps->smallSmemBytes = bytes;
+            }
+        }
+    }
     // z-slabs: global coarse levels from level Lc on, if the slab boundaries are aligned to 2^Lc planes
     ps->Lc = 0;
     if (slab_on(c)) {
@@ -1211,6 +1397,7 @@ void pressure_free(flip_ctx *c) {
     if (c->mg) {
         PressureScratch *ps = (PressureScratch *)c->mg;
         cudaFree(ps->maskAll); cudaFree(ps->flagAll); cudaFree(ps->posAll); cudaFree(ps->pool); cudaFree(ps->gpool);
+        cudaFree(ps->segPool);
         delete ps;
         c->mg = nullptr;
     }
@@ -1281,6 +1468,7 @@ void stage_pressure(flip_ctx *c, double dt) {
     if (n == 0 || bmax < c->pressureTol) return;
 
     segBlocks = std::max(1, cdiv((long long)numSeg * 32, TPB));
+    const int loopBlocks = std::min(segBlocks, 148 * 6);    // grid-stride passes: one resident wave
     PcgParams pp;
     pp.g = g;
     pp.factor = bp.factor;
@@ -1308,6 +1496,17 @@ void stage_pressure(flip_ctx *c, double dt) {
         if (Lc == 0) {
             for (int l = 1; l + 1 < ps->numLevels; l++) {
                 k_mg_coarsen<<<cdiv(ps->lv[l + 1].n, TPB), TPB, 0, st>>>(ps->lv[l], ps->lv[l + 1]); c->launches++;
+            }
+            if (!slab) {
+                // active segments of the coarse levels; cells outside them keep a zero iterate for the whole solve
+                FLIP_CUDA_CHECK(cudaMemsetAsync(ps->lvSegCount, 0, sizeof(int) * MG_MAX_LEVELS, st));
+                const int lastListed = ps->firstSmall ? ps->firstSmall : ps->numLevels - 1;
+                for (int l = 1; l <= lastListed; l++) {
+                    MgLevel &lv = ps->lv[l];
+                    FLIP_CUDA_CHECK(cudaMemsetAsync(lv.x, 0, sizeof(float) * lv.n, st));
+                    FLIP_CUDA_CHECK(cudaMemsetAsync(lv.x2, 0, sizeof(float) * lv.n, st));
+                    k_mg_build_list<<<cdiv(lv.n, TPB), TPB, 0, st>>>(lv, ps->lvSeg[l], &ps->lvSegCount[l]); c->launches++;
+                }
             }
         } else {
             for (int l = 1; l < Lc; l++) {
@@ -1364,7 +1563,7 @@ void stage_pressure(flip_ctx *c, double dt) {
         {   // level 0 pre-smoothing
             float *xa = ps->lv[0].x, *xb = ps->lv[0].x2;
             for (int sw = 0; sw < nu; sw++) {
-                k_mg0_sweep<<<segBlocks, TPB, 0, st>>>(c->segCell, c->segMask, m0, up_desc(0), c->vr, xa, nullptr, xb, mp.omega,
+                k_mg0_sweep<<<loopBlocks, TPB, 0, st>>>(c->segCell, c->segMask, m0, up_desc(0), c->vr, xa, nullptr, xb, mp.omega,
                                                       mp.scale, sw == 0 ? 0 : 1, 0, nullptr, c->dS, 0);
                 c->launches++;
                 std::swap(xa, xb);
@@ -1422,7 +1621,7 @@ void stage_pressure(flip_ctx *c, double dt) {
             float *xa = ps->lv[0].x, *xb = ps->lv[0].x2;
             for (int sw = 0; sw < nu; sw++) {
                 int last = (sw == nu - 1) ? 1 : 0;
-                k_mg0_sweep<<<segBlocks, TPB, 0, st>>>(c->segCell, c->segMask, m0, up_desc(0), c->vr, xa, up_x(0), xb, mp.omega,
+                k_mg0_sweep<<<loopBlocks, TPB, 0, st>>>(c->segCell, c->segMask, m0, up_desc(0), c->vr, xa, up_x(0), xb, mp.omega,
                                                       mp.scale, sw == 0 ? 2 : 1, last, c->vz, c->dS, rhoSlot);
                 c->launches++;
                 std::swap(xa, xb);
@@ -1432,6 +1631,96 @@ void stage_pressure(flip_ctx *c, double dt) {
         }
         kt_end(c, FLIP_KERNEL_PRECOND, ktV);
     };
+
+    // Single-GPU V-cycle: the coarse levels run over their active-segment lists, the first two pre-sweeps of every
+    // level are one pass (mode 3), restrictions use eight threads per coarse cell, and the single-CTA levels live
+    // in shared memory.  Same operator as `vcycle` up to float summation order in the restrictions.
+    auto list_blocks = [&](const MgLevel &lv) { return std::max(1, std::min(cdiv(cdiv(lv.n, 32), WPB), 148 * 8)); };
+    auto restrict_blocks = [&](const MgLevel &coarse) { return std::max(1, std::min(cdiv(coarse.n, 32), 148 * 8)); };
+    auto vcycle_list = [&](int rhoSlot) {
+        const int nu = mp.nu;
+        size_t ktV = kt_begin(c);
+        // ---- down
+        {
+            float *xa = ps->lv[0].x, *xb = ps->lv[0].x2;
+            int sw = 0;
+            if (nu >= 2) {
+                k_mg0_sweep<<<loopBlocks, TPB, 0, st>>>(c->segCell, c->segMask, m0, ps->lv[1], c->vr, xa, nullptr, xb, mp.omega,
+                                                      mp.scale, 3, 0, nullptr, c->dS, 0);
+                c->launches++;
+                std::swap(xa, xb);
+                sw = 2;
+            }
+            for (; sw < nu; sw++) {
+                k_mg0_sweep<<<loopBlocks, TPB, 0, st>>>(c->segCell, c->segMask, m0, ps->lv[1], c->vr, xa, nullptr, xb, mp.omega,
+                                                      mp.scale, sw == 0 ? 0 : 1, 0, nullptr, c->dS, 0);
+                c->launches++;
+                std::swap(xa, xb);
+            }
+            k_mg0_restrict_list<<<restrict_blocks(ps->lv[1]), 256, 0, st>>>(m0, ps->lv[1], c->vr, xa, ps->lvSeg[1],
+                                                                           &ps->lvSegCount[1], c->dS);
+            c->launches++;
+            ps->lv[0].x = xa; ps->lv[0].x2 = xb;
+        }
+        for (int l = 1; l < fs && l < L - 1; l++) {
+            MgLevel &lv = ps->lv[l];
+            float *xa = lv.x, *xb = lv.x2;
+            int sw = 0;
+            if (nu >= 2) {
+                k_mg_sweep_list<<<list_blocks(lv), TPB, 0, st>>>(lv, lv, xa, nullptr, xb, mp.omega, mp.scale, 3, ps->lvSeg[l],
+                                                                &ps->lvSegCount[l], c->dS);
+                c->launches++;
+                std::swap(xa, xb);
+                sw = 2;
+            }
+            for (; sw < nu; sw++) {
+                k_mg_sweep_list<<<list_blocks(lv), TPB, 0, st>>>(lv, lv, xa, nullptr, xb, mp.omega, mp.scale, sw == 0 ? 0 : 1,
+                                                                ps->lvSeg[l], &ps->lvSegCount[l], c->dS);
+                c->launches++;
+                std::swap(xa, xb);
+            }
+            lv.x = xa; lv.x2 = xb;
+            k_mg_restrict_list<<<restrict_blocks(ps->lv[l + 1]), 256, 0, st>>>(lv, ps->lv[l + 1], lv.x, ps->lvSeg[l + 1],
+                                                                              &ps->lvSegCount[l + 1], c->dS);
+            c->launches++;
+        }
+        // ---- bottom: the small levels in one CTA
+        {
+            MgSmallArgs A;
+            for (int l = 0; l < L; l++) A.lv[l] = ps->lv[l];
+            A.first = fs; A.last = L - 1; A.p = mp;
+            if (ps->smallSmemBytes) k_mg_small_smem<<<1, 1024, ps->smallSmemBytes, st>>>(A, c->dS);
+            else k_mg_small<<<1, 1024, 0, st>>>(A, c->dS);
+            c->launches++;
+        }
+        // ---- up
+        for (int l = fs - 1; l >= 1; l--) {
+            MgLevel &lv = ps->lv[l];
+            float *xa = lv.x, *xb = lv.x2;
+            for (int sw = 0; sw < nu; sw++) {
+                k_mg_sweep_list<<<list_blocks(lv), TPB, 0, st>>>(lv, ps->lv[l + 1], xa, ps->lv[l + 1].x, xb, mp.omega, mp.scale,
+                                                                sw == 0 ? 2 : 1, ps->lvSeg[l], &ps->lvSegCount[l], c->dS);
+                c->launches++;
+                std::swap(xa, xb);
+            }
+            lv.x = xa; lv.x2 = xb;
+        }
+        {
+            float *xa = ps->lv[0].x, *xb = ps->lv[0].x2;
+            for (int sw = 0; sw < nu; sw++) {
+                int last = (sw == nu - 1) ? 1 : 0;
+                k_mg0_sweep<<<loopBlocks, TPB, 0, st>>>(c->segCell, c->segMask, m0, ps->lv[1], c->vr, xa, ps->lv[1].x, xb, mp.omega,
+                                                      mp.scale, sw == 0 ? 2 : 1, last, c->vz, c->dS, rhoSlot);
+                c->launches++;
+                std::swap(xa, xb);
+            }
+            ps->lv[0].x = xa; ps->lv[0].x2 = xb;
+        }
+        kt_end(c, FLIP_KERNEL_PRECOND, ktV);
+    };
+    // the list-driven cycle needs the single-CTA levels to start above level 0 and below the top
+    const bool useLists = useMg && !slab && fs >= 1 && fs < L;
+    auto apply_precond = [&](int rhoSlot) { if (useLists) vcycle_list(rhoSlot); else vcycle(rhoSlot); };
 
     k_pcg_scalars_init<<<1, 1, 0, st>>>(c->dS, pp.tolFactor); c->launches++;
     if (c->pcgPersistent && !slab) {
@@ -1461,7 +1750,7 @@ void stage_pressure(flip_ctx *c, double dt) {
     k_pcg_init<<<segBlocks, TPB, 0, st>>>(c->segCell, c->segMask, pp, c->vb, c->Adiag, c->vr, c->vz, c->vs, c->dS, jacobi);
     c->launches++;
     if (useMg) {
-        vcycle(0);
+        apply_precond(0);
         k_pcg_copy_zs<<<segBlocks, TPB, 0, st>>>(c->segCell, c->segMask, c->vz, c->vs, c->dS); c->launches++;
     }
     if (slab) comm_allreduce(c->comm, &c->dS->rho[0], 1, COMM_SUM_F64, st);
@@ -1476,17 +1765,17 @@ void stage_pressure(flip_ctx *c, double dt) {
             size_t ktIt = kt_begin(c);
             if (slab) slab_exchange_vector_halo(c, c->vs);     // the neighbours' boundary plane of the search vector
             size_t ktSp = kt_begin(c);
-            k_pcg_spmv<<<segBlocks, TPB, 0, st>>>(c->segCell, c->segMask, pp, c->Adiag, c->AoffU, c->AoffV, c->AoffW,
+            k_pcg_spmv<<<loopBlocks, TPB, 0, st>>>(c->segCell, c->segMask, pp, c->Adiag, c->AoffU, c->AoffV, c->AoffW,
                                                   c->vs, c->vz, c->dS, it);
             kt_end(c, FLIP_KERNEL_PCG_SPMV, ktSp);
             if (slab) comm_allreduce(c->comm, &c->dS->dotSZ[it % 3], 1, COMM_SUM_F64, st);
-            k_pcg_update<<<segBlocks, TPB, 0, st>>>(c->segCell, c->segMask, c->Adiag, c->vs, c->vz, c->vx_, c->vr,
+            k_pcg_update<<<loopBlocks, TPB, 0, st>>>(c->segCell, c->segMask, c->Adiag, c->vs, c->vz, c->vx_, c->vr,
                                                     c->dS, it, jacobi);
             c->launches += 2;
             if (slab) comm_allreduce(c->comm, &c->dS->rMaxBits[it % 3], 1, COMM_MAX_U64, st);
-            if (useMg) vcycle((it + 1) % 3);
+            if (useMg) apply_precond((it + 1) % 3);
             if (slab) comm_allreduce(c->comm, &c->dS->rho[(it + 1) % 3], 1, COMM_SUM_F64, st);
-            k_pcg_direction<<<segBlocks, TPB, 0, st>>>(c->segCell, c->segMask, c->vz, c->vs, c->dS, it);
+            k_pcg_direction<<<loopBlocks, TPB, 0, st>>>(c->segCell, c->segMask, c->vz, c->vs, c->dS, it);
             kt_end(c, FLIP_KERNEL_PCG_ITER, ktIt);
             c->launches++;
         }

@@ -73,6 +73,7 @@ def load_library():
     L.flip_set_preconditioner.argtypes = [vp, ci]
     L.flip_set_multigrid.argtypes = [vp, ci, cd, cd, ci]
     L.flip_set_solver_mode.argtypes = [vp, ci]
+    L.flip_set_sampling_mode.argtypes = [vp, ci]
     L.flip_load_particles.argtypes = [vp, ci, vp, vp]
     L.flip_add_fluid_box.argtypes = [vp, C.POINTER(cd), C.POINTER(cd), C.POINTER(cd)]
     L.flip_add_marker_particle.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
@@ -208,6 +209,14 @@ class FluidSimulation:
 
     def setMultigrid(self, sweeps=2, damping=0.8, coarse_weight=1.8, coarsest_sweeps=8):
         self._check(self.L.flip_set_multigrid(self.h, sweeps, damping, coarse_weight, coarsest_sweeps))
+
+    def setSamplingMode(self, mode):
+        """'exact': the reference's double-precision trilinear blend (bit-identical G2P / RK3);
+        'fast' (default): exact indices and weights, single-precision blend."""
+        kinds = {"exact": 0, "fast": 1}
+        if mode not in kinds:
+            raise ValueError(f"sampling mode must be one of {sorted(kinds)}")
+        self._check(self.L.flip_set_sampling_mode(self.h, kinds[mode]))
 
     def setSolverMode(self, persistent=True):
         self._check(self.L.flip_set_solver_mode(self.h, 1 if persistent else 0))

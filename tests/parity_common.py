@@ -32,7 +32,7 @@ def max_abs(a, b):
     return float(np.max(np.abs(np.asarray(a, dtype=np.float64) - np.asarray(b, dtype=np.float64))))
 
 
-def make_pair(scene, tol=None, threads=None, gravity=(0.0, -25.0, 0.0), preconditioner=None):
+def make_pair(scene, tol=None, threads=None, gravity=(0.0, -25.0, 0.0), preconditioner=None, sampling=None):
     """Returns (ref, gpu) engines initialised from the same scene; the GPU engine gets the oracle's
     own static solid SDF and the oracle's LOGICAL particle list."""
     ref = refengine.RefEngine(scene["dims"], scene["dx"], scene["pos"], scene["vel"], gravity=gravity, threads=threads, tol=tol)
@@ -44,6 +44,8 @@ def make_pair(scene, tol=None, threads=None, gravity=(0.0, -25.0, 0.0), precondi
         gpu.setPressureSolver(tolerance=tol)
     if preconditioner is not None:
         gpu.setPreconditioner(preconditioner)
+    if sampling is not None:
+        gpu.setSamplingMode(sampling)
     gpu.enableParticleIds(True)
     gpu.setSolidSDF(ref.array("solid_phi"))
     gpu.initialize()
@@ -180,8 +182,9 @@ def lockstep_substep(ref, gpu, dt, isolate=True, report=None):
     return rep
 
 
-def lockstep_frames(scene, frames=1, isolate=True, tol=None, threads=None, preconditioner=None, verbose=False):
-    ref, gpu = make_pair(scene, tol=tol, threads=threads, preconditioner=preconditioner)
+def lockstep_frames(scene, frames=1, isolate=True, tol=None, threads=None, preconditioner=None, verbose=False,
+                    sampling=None):
+    ref, gpu = make_pair(scene, tol=tol, threads=threads, preconditioner=preconditioner, sampling=sampling)
     reports = []
     for f in range(frames):
         ref.begin_frame(1.0 / 30.0)
@@ -223,10 +226,15 @@ def print_report(rep):
 TOL_REL_L2 = 1e-4
 TOL_P2G_REL_L2 = 1e-5      # P2G differs from the reference by float summation order only
 TOL_POS_MAX_ABS_DX = 1e-3  # particle positions: max-abs <= 1e-3 dx
+# FLIP_SAMPLING_FAST (the default): exact indices/weights, single-precision 8-point blend -> a few ulp of the
+# sampled velocities per sample instead of bit-identity
+TOL_FAST_VEL_REL_L2 = 5e-6
+TOL_FAST_POS_REL_L2 = 1e-6
 
 
-def check_report(rep, dx=0.125, isolate=True):
-    """Asserts the parity contract on one lock-step substep report."""
+def check_report(rep, dx=0.125, isolate=True, exact_sampling=False):
+    """Asserts the parity contract on one lock-step substep report.  exact_sampling: the engine ran with
+    FLIP_SAMPLING_EXACT, so G2P and RK3 must be bit-identical from identical inputs."""
     # integer bookkeeping: exact
     assert rep["sdf.sign_flips"] == 0, rep
     assert rep["gpu.pressure_rows"] == rep["ref.fluid_cells"] or rep["ref.fluid_cells"] == 0, rep
@@ -242,9 +250,14 @@ def check_report(rep, dx=0.125, isolate=True):
             assert rep[f"extrapolate_b.{comp}.max_abs"] == 0.0, rep
             assert rep[f"body_force.{comp}.max_abs"] == 0.0, rep
             assert rep[f"constrain.{comp}.max_abs"] == 0.0, rep
-        assert rep["g2p.vel.mismatch"] == 0, rep
-        if "advance.pos.mismatch" in rep:
-            assert rep["advance.pos.mismatch"] == 0, rep
+        if exact_sampling:
+            assert rep["g2p.vel.mismatch"] == 0, rep
+            if "advance.pos.mismatch" in rep:
+                assert rep["advance.pos.mismatch"] == 0, rep
+        else:
+            assert rep["g2p.vel.rel_l2"] <= TOL_FAST_VEL_REL_L2, rep
+            if "advance.pos.rel_l2" in rep:
+                assert rep["advance.pos.rel_l2"] <= TOL_FAST_POS_REL_L2, rep
     # float fields
     for comp in "UVW":
         assert rep[f"p2g.{comp}.rel_l2"] <= TOL_P2G_REL_L2, rep
