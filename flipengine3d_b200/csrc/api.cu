@@ -254,7 +254,24 @@ int flip_set_multigrid(flip_ctx *c, int sweeps, double damping, double weight, i
         if (sweeps < 1 || sweeps > 8 || !(damping > 0.0 && damping <= 1.0) || !(weight > 0.0) || coarsest < 1)
             throw ApiError(FLIP_ERR_DOMAIN, "Error: bad multigrid parameters.");
         c->mgNu = sweeps; c->mgOmega = damping; c->mgScale = weight; c->mgCoarseSweeps = coarsest;
+        for (double &w : c->mgOmegaSched) w = damping;
     });
+}
+
+int flip_set_multigrid_schedule(flip_ctx *c, int sweeps, const double *damping) {
+    if (!c) return FLIP_ERR_RUNTIME;
+    return guarded(c, [&] {
+        if (sweeps < 1 || sweeps > 8 || !damping) throw ApiError(FLIP_ERR_DOMAIN, "Error: bad multigrid parameters.");
+        for (int q = 0; q < sweeps; q++)
+            if (!(damping[q] > 0.0 && damping[q] < 2.0)) throw ApiError(FLIP_ERR_DOMAIN, "Error: bad multigrid parameters.");
+        c->mgNu = sweeps;
+        for (int q = 0; q < 8; q++) c->mgOmegaSched[q] = damping[q < sweeps ? q : sweeps - 1];
+    });
+}
+
+int flip_set_pressure_warm_start(flip_ctx *c, int on) {
+    if (!c) return FLIP_ERR_RUNTIME;
+    return guarded(c, [&] { c->pressureWarmStart = on ? 1 : 0; });
 }
 
 int flip_set_sampling_mode(flip_ctx *c, int mode) {

@@ -17,6 +17,7 @@
 #include <cooperative_groups.h>
 #include <cub/device/device_scan.cuh>
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <utility>
@@ -94,7 +95,7 @@ __global__ void k_build_system(const int *__restrict__ segCell, const unsigned i
                                const float *__restrict__ wU, const float *__restrict__ wV, const float *__restrict__ wW,
                                double *__restrict__ Adiag, float *__restrict__ AoffU, float *__restrict__ AoffV,
                                float *__restrict__ AoffW, double *__restrict__ b, double *__restrict__ x,
-                               DeviceScalars *S) {
+                               DeviceScalars *S, const unsigned int *__restrict__ prevRowBits) {
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     if (warp >= S->numSegments) return;
@@ -121,7 +122,9 @@ __global__ void k_build_system(const int *__restrict__ segCell, const unsigned i
         div = dadd(div, dmul(dmul(-f, volFront), (double)W[fw + g.sk]));
         div = dadd(div, dmul(dmul(f, volBack), (double)W[fw]));
         b[c] = div;
-        x[c] = 0.0;
+        // initial guess: 0 as in the reference (pcgsolver.h:258), or -- warm start -- the pressure this cell had in
+        // the previous solve if it was a row then (segments are aligned: bit `lane` of word c/32)
+        if (!(prevRowBits && ((prevRowBits[c >> 5] >> lane) & 1u))) x[c] = 0.0;
         babs = fabs(div);
 
         // _calculateMatrixCoefficientsThread  pressuresolver.cpp:723-808
@@ -215,10 +218,12 @@ __device__ __forceinline__ void block_max(double v, unsigned long long *target) 
     __syncthreads();
 }
 
-// r = b; z = M^-1 r (Jacobi); s = z; rho = z.r     (pcgsolver.h:258-276)
+// r = b [- A x0 with a warm start]; z = M^-1 r (Jacobi); s = z; rho = z.r     (pcgsolver.h:258-276)
 __global__ void k_pcg_init(const int *__restrict__ segCell, const unsigned int *__restrict__ segMask, PcgParams pp,
                            const double *__restrict__ b, const double *__restrict__ Adiag, double *__restrict__ r,
-                           double *__restrict__ z, double *__restrict__ s, DeviceScalars *S, int jacobi) {
+                           double *__restrict__ z, double *__restrict__ s, DeviceScalars *S, int jacobi,
+                           const float *__restrict__ AoffU, const float *__restrict__ AoffV, const float *__restrict__ AoffW,
+                           const double *__restrict__ x0) {
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     double part = 0.0;
@@ -226,6 +231,7 @@ __global__ void k_pcg_init(const int *__restrict__ segCell, const unsigned int *
         int c = segCell[warp] + lane;
         if ((segMask[warp] >> lane) & 1u) {
             double rv = b[c];
+            if (x0) rv -= apply_row(pp.g, c, pp.factor, Adiag, AoffU, AoffV, AoffW, x0);
             r[c] = rv;
             if (jacobi) {
                 double d = Adiag[c];
@@ -253,6 +259,7 @@ __global__ void k_pcg_scalars_init(DeviceScalars *S, double tolFactor) {
 // same-address atomics for its dot product / norm.
 
 // z = A s ; dotSZ += s.z
+// (two segments per loop trip: the loads of the second do not wait for the first to retire)
 __global__ void __launch_bounds__(TPB, 6) k_pcg_spmv(const int *__restrict__ segCell, const unsigned int *__restrict__ segMask,
                                                      PcgParams pp, const double *__restrict__ Adiag,
                                                      const float *__restrict__ AoffU, const float *__restrict__ AoffV,
@@ -262,19 +269,25 @@ __global__ void __launch_bounds__(TPB, 6) k_pcg_spmv(const int *__restrict__ seg
     const int lane = threadIdx.x & 31;
     const int nseg = S->numSegments, nw = (gridDim.x * blockDim.x) >> 5;
     double part = 0.0;
-    for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nseg; w += nw) {
-        int c = segCell[w] + lane;
-        if ((segMask[w] >> lane) & 1u) {
-            double zv = apply_row(pp.g, c, pp.factor, Adiag, AoffU, AoffV, AoffW, s);
-            z[c] = zv;
-            part += s[c] * zv;
-        }
+    for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nseg; w += 2 * nw) {
+        const int w2 = w + nw;
+        const bool has2 = w2 < nseg;
+        const int cA = segCell[w] + lane;
+        const unsigned int mA = segMask[w];
+        const int cB = has2 ? segCell[w2] + lane : cA;
+        const unsigned int mB = has2 ? segMask[w2] : 0u;
+        const bool rA = (mA >> lane) & 1u, rB = (mB >> lane) & 1u;
+        double zA = 0.0, zB = 0.0, sA = 0.0, sB = 0.0;
+        if (rA) { zA = apply_row(pp.g, cA, pp.factor, Adiag, AoffU, AoffV, AoffW, s); sA = s[cA]; }
+        if (rB) { zB = apply_row(pp.g, cB, pp.factor, Adiag, AoffU, AoffV, AoffW, s); sB = s[cB]; }
+        if (rA) { z[cA] = zA; part += sA * zA; }
+        if (rB) { z[cB] = zB; part += sB * zB; }
     }
     block_add(part, &S->dotSZ[it % 3]);
 }
 
 // alpha = rho/(s.z); x += alpha s; r -= alpha z; rmax = ||r||_inf; [Jacobi: z = r/diag; rhoNew += z.r]
-__global__ void __launch_bounds__(TPB, 6) k_pcg_update(const int *__restrict__ segCell, const unsigned int *__restrict__ segMask,
+__global__ void __launch_bounds__(TPB, 5) k_pcg_update(const int *__restrict__ segCell, const unsigned int *__restrict__ segMask,
                                                        const double *__restrict__ Adiag, const double *__restrict__ s,
                                                        double *__restrict__ z, double *__restrict__ x, double *__restrict__ r,
                                                        DeviceScalars *S, int it, int jacobi) {
@@ -283,17 +296,36 @@ __global__ void __launch_bounds__(TPB, 6) k_pcg_update(const int *__restrict__ s
     const int nseg = S->numSegments, nw = (gridDim.x * blockDim.x) >> 5;
     const double alpha = S->rho[it % 3] / S->dotSZ[it % 3];
     double part = 0.0, rabs = 0.0;
-    for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nseg; w += nw) {
-        int c = segCell[w] + lane;
-        if ((segMask[w] >> lane) & 1u) {
-            x[c] += alpha * s[c];
-            double rv = r[c] - alpha * z[c];
-            r[c] = rv;
+    for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nseg; w += 2 * nw) {
+        const int w2 = w + nw;
+        const bool has2 = w2 < nseg;
+        const int cA = segCell[w] + lane;
+        const unsigned int mA = segMask[w];
+        const int cB = has2 ? segCell[w2] + lane : cA;
+        const unsigned int mB = has2 ? segMask[w2] : 0u;
+        const bool rA = (mA >> lane) & 1u, rB = (mB >> lane) & 1u;
+        double xA = 0.0, sA = 0.0, qA = 0.0, zA = 0.0, xB = 0.0, sB = 0.0, qB = 0.0, zB = 0.0, dA = 1.0, dB = 1.0;
+        if (rA) { xA = x[cA]; sA = s[cA]; qA = r[cA]; zA = z[cA]; if (jacobi) dA = Adiag[cA]; }
+        if (rB) { xB = x[cB]; sB = s[cB]; qB = r[cB]; zB = z[cB]; if (jacobi) dB = Adiag[cB]; }
+        if (rA) {
+            x[cA] = xA + alpha * sA;
+            double rv = qA - alpha * zA;
+            r[cA] = rv;
             rabs = fmax(rabs, fabs(rv));
             if (jacobi) {
-                double d = Adiag[c];
-                double zv = (d != 0.0) ? rv / d : 0.0;
-                z[c] = zv;
+                double zv = (dA != 0.0) ? rv / dA : 0.0;
+                z[cA] = zv;
+                part += zv * rv;
+            }
+        }
+        if (rB) {
+            x[cB] = xB + alpha * sB;
+            double rv = qB - alpha * zB;
+            r[cB] = rv;
+            rabs = fmax(rabs, fabs(rv));
+            if (jacobi) {
+                double zv = (dB != 0.0) ? rv / dB : 0.0;
+                z[cB] = zv;
                 part += zv * rv;
             }
         }
@@ -328,9 +360,19 @@ __global__ void k_pcg_direction(const int *__restrict__ segCell, const unsigned 
     if (!converged && !breakdown) {
         const double beta = rhoNew / rho;
         const int nseg = S->numSegments, nw = (gridDim.x * blockDim.x) >> 5;
-        for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nseg; w += nw) {
-            int c = segCell[w] + lane;
-            if ((segMask[w] >> lane) & 1u) s[c] = z[c] + beta * s[c];
+        for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nseg; w += 2 * nw) {
+            const int w2 = w + nw;
+            const bool has2 = w2 < nseg;
+            const int cA = segCell[w] + lane;
+            const unsigned int mA = segMask[w];
+            const int cB = has2 ? segCell[w2] + lane : cA;
+            const unsigned int mB = has2 ? segMask[w2] : 0u;
+            const bool rA = (mA >> lane) & 1u, rB = (mB >> lane) & 1u;
+            double zA = 0.0, sA = 0.0, zB = 0.0, sB = 0.0;
+            if (rA) { zA = z[cA]; sA = s[cA]; }
+            if (rB) { zB = z[cB]; sB = s[cB]; }
+            if (rA) s[cA] = zA + beta * sA;
+            if (rB) s[cB] = zB + beta * sB;
         }
     }
     // the last block to finish publishes the scalars (no other block reads them after this point in
@@ -375,6 +417,8 @@ __global__ void k_pcg_direction(const int *__restrict__ segCell, const unsigned 
 // Levels with <= MG_SMALL cells are run by one CTA in a single launch.
 // ------------------------------------------------------------------------------------------------
 static constexpr int MG_MAX_LEVELS = 12;
+// zero padding (floats) in front of and behind every array of a level >= 1: one plane + one cell, 256-byte aligned
+inline int mg_pad(int sk) { return ((sk + 1 + 63) / 64) * 64; }
 static constexpr int MG_SMALL = 4096;
 
 struct MgLevel {
@@ -383,8 +427,10 @@ struct MgLevel {
     float *diag, *invD, *oU, *oV, *oW, *x, *x2, *b;
 };
 
+static constexpr int MG_MAX_SWEEPS = 8;
 struct MgParams {
-    float omega;      // Jacobi damping
+    float om[MG_MAX_SWEEPS];   // damping of pre-sweep s; post-sweep s uses om[nu-1-s] (the V-cycle stays symmetric)
+    float omegaCoarse;         // damping of the sweeps on the coarsest level
     float scale;      // coarse-correction weight
     int nu;           // pre = post sweeps
     int coarseSweeps;
@@ -442,13 +488,14 @@ __device__ __forceinline__ float mg_offsum_first(const MgLevel &L, int c, int i,
 // 2: regular on (xin + scale * P e); 3: the first TWO sweeps from a zero guess in one pass (the first one is
 // pointwise, so its result at the six neighbours is recomputed instead of being stored and re-read)
 __device__ __forceinline__ float mg_sweep_cell(const MgLevel &L, const MgLevel &C, const float *xin, const float *e,
-                                               float omega, float scale, int mode, int c, int i, int j, int k) {
+                                               float omega, float scale, int mode, int c, int i, int j, int k,
+                                               float omega0 = 0.0f) {
     float inv = L.invD[c];
     if (inv == 0.0f) return 0.0f;
     float b = L.b[c];
     if (mode == 0) return omega * inv * b;
     float xc, ns;
-    if (mode == 3) { xc = omega * inv * b; ns = mg_offsum_first(L, c, i, j, k, omega); }
+    if (mode == 3) { xc = omega0 * inv * b; ns = mg_offsum_first(L, c, i, j, k, omega0); }
     else if (mode == 1) { xc = xin[c]; ns = mg_offsum(L, xin, c, i, j, k); }
     else { xc = mg_corrected(L, C, xin, e, scale, c, i, j, k); ns = mg_offsum_corrected(L, C, xin, e, scale, c, i, j, k); }
     return (1.0f - omega) * xc + omega * inv * (b + ns);
@@ -502,7 +549,7 @@ __global__ void k_mg_build_list(MgLevel L, int *__restrict__ list, int *__restri
 
 __global__ void k_mg_sweep_list(MgLevel L, MgLevel C, const float *xin, const float *e, float *xout, float omega,
                                 float scale, int mode, const int *__restrict__ list, const int *__restrict__ count,
-                                const DeviceScalars *S) {
+                                const DeviceScalars *S, float omega0) {
     if (S->pcgDone) return;
     const int nseg = *count;
     const int lane = threadIdx.x & 31;
@@ -511,7 +558,7 @@ __global__ void k_mg_sweep_list(MgLevel L, MgLevel C, const float *xin, const fl
         int c = list[s] + lane;
         if (c < L.n) {
             int i = c % L.I, j = (c / L.I) % L.J, k = c / L.sk;
-            xout[c] = mg_sweep_cell(L, C, xin, e, omega, scale, mode, c, i, j, k);
+            xout[c] = mg_sweep_cell(L, C, xin, e, omega, scale, mode, c, i, j, k, omega0);
         }
     }
 }
@@ -549,12 +596,13 @@ struct MgSmallArgs {
 // the small levels of the V-cycle in one CTA: down, coarsest sweeps, up.  Leaves the result in lv[first].x.
 __device__ __forceinline__ void mg_small_body(const MgLevel *lv, int first, int last, const MgParams &p) {
     const int tid = threadIdx.x, nt = blockDim.x;
-    const float omega = p.omega, scale = p.scale;
+    const float scale = p.scale;
     for (int l = first; l <= last; l++) {
         const MgLevel &L = lv[l];
         int sweeps = (l == last) ? p.coarseSweeps : p.nu;
         float *xa = L.x, *xb = L.x2;
         for (int s = 0; s < sweeps; s++) {
+            const float omega = (l == last) ? p.omegaCoarse : p.om[s];
             for (int c = tid; c < L.n; c += nt) {
                 int i = c % L.I, j = (c / L.I) % L.J, k = c / L.sk;
                 xb[c] = mg_sweep_cell(L, L, xa, nullptr, omega, scale, s == 0 ? 0 : 1, c, i, j, k);
@@ -581,6 +629,7 @@ __device__ __forceinline__ void mg_small_body(const MgLevel *lv, int first, int 
         const MgLevel &C = lv[l + 1];
         float *xa = L.x, *xb = L.x2;
         for (int s = 0; s < p.nu; s++) {
+            const float omega = p.om[p.nu - 1 - s];
             for (int c = tid; c < L.n; c += nt) {
                 int i = c % L.I, j = (c / L.I) % L.J, k = c / L.sk;
                 xb[c] = mg_sweep_cell(L, C, xa, C.x, omega, scale, s == 0 ? 2 : 1, c, i, j, k);
@@ -600,38 +649,312 @@ __global__ void __launch_bounds__(1024) k_mg_small(MgSmallArgs A, const DeviceSc
     mg_small_body(A.lv, A.first, A.last, A.p);
 }
 
-// The same with every array of the small levels staged in shared memory (8 floats per cell; the levels below
-// MG_SMALL cells total ~150 KB): the ~30 barrier-separated phases then run at shared-memory instead of L2 latency.
-__global__ void __launch_bounds__(1024) k_mg_small_smem(MgSmallArgs A, const DeviceScalars *S) {
-    extern __shared__ float smf[];
-    __shared__ MgLevel sl[MG_MAX_LEVELS];
-    if (S->pcgDone) return;
+// ------------------------------------------------------------------------------------------------
+// All coarse levels (1 .. coarsest) of the V-cycle in ONE cooperative kernel.
+//
+// A level >= 1 holds at most 1/8 of the rows of the level below, so its passes are pure latency: as separate
+// launches the ~17 coarse passes of a cycle cost more than the level-0 passes that move all the data.  Here one
+// CTA per SM walks them with grid-wide barriers in between (list-driven, same device functions as the
+// per-pass kernels); the levels of <= MG_SMALL cells are run by block 0 alone out of SHARED memory, with the
+// arrays zero-padded by one plane on both sides so that the 7-point sums need neither bounds checks nor
+// a != 0 tests (couplings that would wrap around a row or plane are zero by construction: border cells are
+// never pressure rows) -- twelve independent loads per cell instead of six dependent pairs.
+// ------------------------------------------------------------------------------------------------
+struct SmLevel {
+    int I, J, K, sj, sk, n;
+    float *diag, *invD, *b;             // [n]
+    float *oU, *oV, *oW, *x, *x2;       // [n], zero-padded by `sm_pad` entries on both sides
+};
+__host__ __device__ inline int sm_pad(int sk) { return (sk + 1 + 3) & ~3; }
+__host__ __device__ inline size_t sm_level_floats(int n, int sk) { return 3 * (size_t)n + 5 * ((size_t)n + 2 * sm_pad(sk)); }
+
+__device__ __forceinline__ float sm_offsum(const SmLevel &L, const float *x, int c) {
+    float s = 0.0f;
+    s += L.oW[c - L.sk] * x[c - L.sk];
+    s += L.oV[c - L.sj] * x[c - L.sj];
+    s += L.oU[c - 1] * x[c - 1];
+    s += L.oU[c] * x[c + 1];
+    s += L.oV[c] * x[c + L.sj];
+    s += L.oW[c] * x[c + L.sk];
+    return s;
+}
+__device__ __forceinline__ float sm_residual(const SmLevel &L, const float *x, int c) {
+    return (L.invD[c] == 0.0f) ? 0.0f : L.b[c] - (L.diag[c] * x[c] - sm_offsum(L, x, c));
+}
+
+// down, coarsest sweeps, up over the shared-memory levels first..last; leaves the result in sl[first].x
+__device__ __forceinline__ void sm_small_body(const SmLevel *sl, int first, int last, const MgParams &p) {
     const int tid = threadIdx.x, nt = blockDim.x;
-    if (tid == 0) {
-        float *q = smf;
-        for (int l = A.first; l <= A.last; l++) {
-            MgLevel L = A.lv[l];
-            const int n = L.n;
-            L.diag = q; q += n; L.invD = q; q += n; L.oU = q; q += n; L.oV = q; q += n; L.oW = q; q += n;
-            L.b = q; q += n; L.x = q; q += n; L.x2 = q; q += n;
-            sl[l] = L;
+    const float scale = p.scale;
+    for (int l = first; l <= last; l++) {
+        const SmLevel &L = sl[l];
+        const int sweeps = (l == last) ? p.coarseSweeps : p.nu;
+        float *xa = L.x, *xb = L.x2;
+        for (int s = 0; s < sweeps; s++) {
+            const float omega = (l == last) ? p.omegaCoarse : p.om[s];
+            for (int c = tid; c < L.n; c += nt) {
+                const float inv = L.invD[c];
+                float v = 0.0f;
+                if (inv != 0.0f) {
+                    if (s == 0) v = omega * inv * L.b[c];
+                    else v = (1.0f - omega) * xa[c] + omega * inv * (L.b[c] + sm_offsum(L, xa, c));
+                }
+                xb[c] = v;
+            }
+            __syncthreads();
+            float *t = xa; xa = xb; xb = t;
+        }
+        if (sweeps & 1) {
+            for (int c = tid; c < L.n; c += nt) L.x[c] = L.x2[c];
+            __syncthreads();
+        }
+        if (l < last) {
+            const SmLevel &C = sl[l + 1];
+            for (int cc = tid; cc < C.n; cc += nt) {
+                float acc = 0.0f;
+                if (C.invD[cc] != 0.0f) {
+                    const int ci = cc % C.I, cj = (cc / C.I) % C.J, ck = cc / C.sk;
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        const int i = 2 * ci + (q & 1), j = 2 * cj + ((q >> 1) & 1), k = 2 * ck + (q >> 2);
+                        if (i < L.I && j < L.J && k < L.K) acc += sm_residual(L, L.x, i + L.sj * j + L.sk * k);
+                    }
+                }
+                C.b[cc] = acc;
+            }
+            __syncthreads();
         }
     }
-    __syncthreads();
-    for (int l = A.first; l <= A.last; l++) {
-        const MgLevel &G = A.lv[l];
-        const MgLevel &L = sl[l];
-        for (int c = tid; c < G.n; c += nt) {
-            L.diag[c] = G.diag[c]; L.invD[c] = G.invD[c]; L.oU[c] = G.oU[c]; L.oV[c] = G.oV[c]; L.oW[c] = G.oW[c];
-            if (l == A.first) L.b[c] = G.b[c];
+    for (int l = last - 1; l >= first; l--) {
+        const SmLevel &L = sl[l];
+        const SmLevel &C = sl[l + 1];
+        const float *e = C.x;
+        float *xa = L.x, *xb = L.x2;
+        for (int s = 0; s < p.nu; s++) {
+            const float omega = p.om[p.nu - 1 - s];
+            for (int c = tid; c < L.n; c += nt) {
+                const float inv = L.invD[c];
+                float v = 0.0f;
+                if (inv != 0.0f) {
+                    if (s == 0) {
+                        // sweep on (x + scale * P e): parents of the cell and of its six neighbours
+                        const int i = c % L.I, j = (c / L.I) % L.J, k = c / L.sk;
+                        const int pi = i >> 1, pj = C.sj * (j >> 1), pk = C.sk * (k >> 1);
+                        const float xc = xa[c] + scale * e[pi + pj + pk];
+                        float ns = 0.0f;
+                        ns += L.oW[c - L.sk] * (xa[c - L.sk] + scale * e[pi + pj + C.sk * ((k - 1) >> 1)]);
+                        ns += L.oV[c - L.sj] * (xa[c - L.sj] + scale * e[pi + C.sj * ((j - 1) >> 1) + pk]);
+                        ns += L.oU[c - 1] * (xa[c - 1] + scale * e[((i - 1) >> 1) + pj + pk]);
+                        ns += L.oU[c] * (xa[c + 1] + scale * e[((i + 1) >> 1) + pj + pk]);
+                        ns += L.oV[c] * (xa[c + L.sj] + scale * e[pi + C.sj * ((j + 1) >> 1) + pk]);
+                        ns += L.oW[c] * (xa[c + L.sk] + scale * e[pi + pj + C.sk * ((k + 1) >> 1)]);
+                        v = (1.0f - omega) * xc + omega * inv * (L.b[c] + ns);
+                    } else {
+                        v = (1.0f - omega) * xa[c] + omega * inv * (L.b[c] + sm_offsum(L, xa, c));
+                    }
+                }
+                xb[c] = v;
+            }
+            __syncthreads();
+            float *t = xa; xa = xb; xb = t;
+        }
+        if (p.nu & 1) {
+            for (int c = tid; c < L.n; c += nt) L.x[c] = L.x2[c];
+            __syncthreads();
         }
     }
-    __syncthreads();
-    mg_small_body(sl, A.first, A.last, A.p);
-    {
-        const MgLevel &G = A.lv[A.first];
-        const MgLevel &L = sl[A.first];
+}
+
+// ---- branch-free passes on the zero-padded global arrays of the levels >= 1 (same arithmetic as mg_sweep_cell /
+// mg_residual_cell; a zero coupling multiplies a finite neighbour value instead of skipping the load)
+__device__ __forceinline__ float mgp_offsum(const MgLevel &L, const float *x, int c) {
+    const float a0 = L.oW[c - L.sk], a1 = L.oV[c - L.sj], a2 = L.oU[c - 1], a3 = L.oU[c], a4 = L.oV[c], a5 = L.oW[c];
+    const float x0 = x[c - L.sk], x1 = x[c - L.sj], x2 = x[c - 1], x3 = x[c + 1], x4 = x[c + L.sj], x5 = x[c + L.sk];
+    float s = 0.0f;
+    s += a0 * x0; s += a1 * x1; s += a2 * x2; s += a3 * x3; s += a4 * x4; s += a5 * x5;
+    return s;
+}
+__device__ __forceinline__ float mgp_residual(const MgLevel &L, const float *x, int c) {
+    const float inv = L.invD[c], b = L.b[c], d = L.diag[c], xc = x[c];
+    const float ns = mgp_offsum(L, x, c);
+    return (inv == 0.0f) ? 0.0f : b - (d * xc - ns);
+}
+__device__ __forceinline__ float mgp_sweep(const MgLevel &L, const MgLevel &C, const float *xin, const float *e, float omega,
+                                           float scale, int mode, int c, float omega0) {
+    const float inv = L.invD[c], b = L.b[c];
+    float xc, ns;
+    if (mode == 0) {
+        return (inv == 0.0f) ? 0.0f : omega * inv * b;
+    } else if (mode == 3) {
+        const int sj = L.sj, sk = L.sk;
+        const float a0 = L.oW[c - sk], a1 = L.oV[c - sj], a2 = L.oU[c - 1], a3 = L.oU[c], a4 = L.oV[c], a5 = L.oW[c];
+        const float d0 = L.invD[c - sk], d1 = L.invD[c - sj], d2 = L.invD[c - 1], d3 = L.invD[c + 1], d4 = L.invD[c + sj], d5 = L.invD[c + sk];
+        const float b0 = L.b[c - sk], b1 = L.b[c - sj], b2 = L.b[c - 1], b3 = L.b[c + 1], b4 = L.b[c + sj], b5 = L.b[c + sk];
+        xc = omega0 * inv * b;
+        ns = 0.0f;
+        ns += a0 * (omega0 * d0 * b0); ns += a1 * (omega0 * d1 * b1); ns += a2 * (omega0 * d2 * b2);
+        ns += a3 * (omega0 * d3 * b3); ns += a4 * (omega0 * d4 * b4); ns += a5 * (omega0 * d5 * b5);
+    } else if (mode == 1) {
+        xc = xin[c];
+        ns = mgp_offsum(L, xin, c);
+    } else {
+        const int i = c % L.I, j = (c / L.I) % L.J, k = c / L.sk;
+        const int pi = i >> 1, pj = C.sj * (j >> 1), pk = C.sk * (k >> 1);
+        const float a0 = L.oW[c - L.sk], a1 = L.oV[c - L.sj], a2 = L.oU[c - 1], a3 = L.oU[c], a4 = L.oV[c], a5 = L.oW[c];
+        const float x0 = xin[c - L.sk], x1 = xin[c - L.sj], x2 = xin[c - 1], x3 = xin[c + 1], x4 = xin[c + L.sj], x5 = xin[c + L.sk];
+        const float e0 = e[pi + pj + C.sk * ((k - 1) >> 1)], e1 = e[pi + C.sj * ((j - 1) >> 1) + pk], e2 = e[((i - 1) >> 1) + pj + pk];
+        const float e3 = e[((i + 1) >> 1) + pj + pk], e4 = e[pi + C.sj * ((j + 1) >> 1) + pk], e5 = e[pi + pj + C.sk * ((k + 1) >> 1)];
+        xc = xin[c] + scale * e[pi + pj + pk];
+        ns = 0.0f;
+        ns += a0 * (x0 + scale * e0); ns += a1 * (x1 + scale * e1); ns += a2 * (x2 + scale * e2);
+        ns += a3 * (x3 + scale * e3); ns += a4 * (x4 + scale * e4); ns += a5 * (x5 + scale * e5);
+    }
+    return (inv == 0.0f) ? 0.0f : (1.0f - omega) * xc + omega * inv * (b + ns);
+}
+
+struct MgCoarseArgs {
+    MgLevel lv[MG_MAX_LEVELS];
+    const int *seg[MG_MAX_LEVELS];   // active-segment lists of levels 1..fs
+    const int *segCount;             // [MG_MAX_LEVELS]
+    int fs, last;                    // levels fs..last: block 0, shared memory
+    MgParams p;
+    int smemFloats;
+    unsigned long long *trace;       // developer probe (FLIP_MG_TRACE): globaltimer at every phase boundary, block 0
+};
+
+__global__ void __launch_bounds__(1024) k_mg_coarse(MgCoarseArgs A, const DeviceScalars *S) {
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ float smf[];
+    __shared__ SmLevel sl[MG_MAX_LEVELS];
+    if (S->pcgDone) return;      // grid-uniform: written by the previous launch only
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+    const int gw = (blockIdx.x * nt + tid) >> 5, nw = (gridDim.x * nt) >> 5;
+    const int nu = A.p.nu;
+    const float scale = A.p.scale;
+    int ntrace = 0;
+    auto stamp = [&]() {
+        if (A.trace && blockIdx.x == 0 && tid == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+            A.trace[ntrace++] = t;
+        }
+    };
+    stamp();
+
+    // block 0 stages the operators of its levels while the other blocks start on level 1
+    if (blockIdx.x == 0) {
+        if (tid == 0) {
+            float *q = smf;
+            for (int l = A.fs; l <= A.last; l++) {
+                const MgLevel &G = A.lv[l];
+                SmLevel L;
+                L.I = G.I; L.J = G.J; L.K = G.K; L.sj = G.sj; L.sk = G.sk; L.n = G.n;
+                const int pad = sm_pad(G.sk);
+                L.diag = q; q += G.n; L.invD = q; q += G.n; L.b = q; q += G.n;
+                L.oU = q + pad; q += G.n + 2 * pad; L.oV = q + pad; q += G.n + 2 * pad; L.oW = q + pad; q += G.n + 2 * pad;
+                L.x = q + pad; q += G.n + 2 * pad; L.x2 = q + pad; q += G.n + 2 * pad;
+                sl[l] = L;
+            }
+        }
+        for (int q = tid; q < A.smemFloats; q += nt) smf[q] = 0.0f;
+        __syncthreads();
+        for (int l = A.fs; l <= A.last; l++) {
+            const MgLevel &G = A.lv[l];
+            const SmLevel &L = sl[l];
+            for (int c = tid; c < G.n; c += nt) {
+                L.diag[c] = G.diag[c]; L.invD[c] = G.invD[c]; L.oU[c] = G.oU[c]; L.oV[c] = G.oV[c]; L.oW[c] = G.oW[c];
+            }
+        }
+        __syncthreads();
+    }
+    stamp();
+
+    const float *lx[MG_MAX_LEVELS];
+    // ---- down through the list-driven levels
+    for (int l = 1; l < A.fs; l++) {
+        const MgLevel &L = A.lv[l];
+        const int *__restrict__ list = A.seg[l];
+        const int nseg = A.segCount[l];
+        float *xa = L.x, *xb = L.x2;
+        int sw = 0;
+        if (nu >= 2) {
+            for (int s = gw; s < nseg; s += nw) {
+                const int c = list[s] + lane;
+                if (c < L.n) xb[c] = mgp_sweep(L, L, xa, nullptr, A.p.om[1], scale, 3, c, A.p.om[0]);
+            }
+            grid.sync();
+            stamp();
+            float *t = xa; xa = xb; xb = t;
+            sw = 2;
+        }
+        for (; sw < nu; sw++) {
+            for (int s = gw; s < nseg; s += nw) {
+                const int c = list[s] + lane;
+                if (c < L.n) xb[c] = mgp_sweep(L, L, xa, nullptr, A.p.om[sw], scale, sw == 0 ? 0 : 1, c, 0.0f);
+            }
+            grid.sync();
+            stamp();
+            float *t = xa; xa = xb; xb = t;
+        }
+        lx[l] = xa;
+        // restriction into level l+1: eight threads per coarse cell, four coarse segments per CTA pass
+        {
+            const MgLevel &C = A.lv[l + 1];
+            const int *__restrict__ listC = A.seg[l + 1];
+            const int nsegC = A.segCount[l + 1];
+            const int t = tid & 255, q = t & 7;
+            for (int s = blockIdx.x * (nt >> 8) + (tid >> 8); s < nsegC; s += gridDim.x * (nt >> 8)) {
+                const int cc = listC[s] + (t >> 3);
+                float v = 0.0f;
+                const bool act = (cc < C.n) && C.invD[cc] != 0.0f;
+                if (act) {
+                    const int ci = cc % C.I, cj = (cc / C.I) % C.J, ck = cc / C.sk;
+                    const int i = 2 * ci + (q & 1), j = 2 * cj + ((q >> 1) & 1), k = 2 * ck + (q >> 2);
+                    if (i < L.I && j < L.J && k < L.K) v = mgp_residual(L, xa, i + L.sj * j + L.sk * k);
+                }
+                v += __shfl_xor_sync(0xffffffffu, v, 1);
+                v += __shfl_xor_sync(0xffffffffu, v, 2);
+                v += __shfl_xor_sync(0xffffffffu, v, 4);
+                if (q == 0 && cc < C.n) C.b[cc] = act ? v : 0.0f;
+            }
+        }
+        grid.sync();
+        stamp();
+    }
+    // ---- the single-CTA levels
+    if (blockIdx.x == 0) {
+        const MgLevel &G = A.lv[A.fs];
+        const SmLevel &L = sl[A.fs];
+        for (int c = tid; c < G.n; c += nt) L.b[c] = G.b[c];
+        __syncthreads();
+        stamp();
+        sm_small_body(sl, A.fs, A.last, A.p);
+        stamp();
         for (int c = tid; c < G.n; c += nt) G.x[c] = L.x[c];
+    }
+    grid.sync();
+    stamp();
+    lx[A.fs] = A.lv[A.fs].x;
+    // ---- up
+    for (int l = A.fs - 1; l >= 1; l--) {
+        const MgLevel &L = A.lv[l];
+        const MgLevel &C = A.lv[l + 1];
+        const int *__restrict__ list = A.seg[l];
+        const int nseg = A.segCount[l];
+        float *xa = const_cast<float *>(lx[l]);
+        float *xb = (xa == L.x) ? L.x2 : L.x;
+        const float *e = lx[l + 1];
+        for (int sw = 0; sw < nu; sw++) {
+            const float omega = A.p.om[nu - 1 - sw];
+            for (int s = gw; s < nseg; s += nw) {
+                const int c = list[s] + lane;
+                if (c < L.n) xb[c] = mgp_sweep(L, C, xa, e, omega, scale, sw == 0 ? 2 : 1, c, 0.0f);
+            }
+            grid.sync();
+            stamp();
+            float *t = xa; xa = xb; xb = t;
+        }
+        lx[l] = xa;
     }
 }
 
@@ -701,34 +1024,62 @@ __device__ __forceinline__ float mg0_offsum_first(const Mg0 &M, const double *__
 }
 
 // mode as in mg_sweep_cell.  last != 0: also write z (fp64) and accumulate rho = z.r into slot `rhoSlot`.
+template <int MODE>
+__device__ __forceinline__ float mg0_sweep_row(const Mg0 &M, const MgLevel &C, const double *__restrict__ r, const float *xin,
+                                               const float *e, float omega, float omega0, float scale, int c, double &rd) {
+    const float inv = M.invD[c];
+    rd = r[c];
+    const float b = (float)rd;
+    if (inv == 0.0f) return 0.0f;
+    if (MODE == 0) return omega * inv * b;
+    if (MODE == 3) return (1.0f - omega) * (omega0 * inv * b) + omega * inv * (b + mg0_offsum_first(M, r, c, omega0));
+    if (MODE == 1) return (1.0f - omega) * xin[c] + omega * inv * (b + mg0_offsum(M, xin, c));
+    return (1.0f - omega) * mg0_corr(M, C, xin, e, scale, c) + omega * inv * (b + mg0_offsum_corr(M, C, xin, e, scale, c));
+}
+
+template <int MODE>
 __global__ void __launch_bounds__(TPB, 6) k_mg0_sweep(const int *__restrict__ segCell, const unsigned int *__restrict__ segMask,
                                                       Mg0 M, MgLevel C, const double *__restrict__ r, const float *xin,
-                                                      const float *e, float *xout, float omega, float scale, int mode, int last,
-                                                      double *zout, DeviceScalars *S, int rhoSlot) {
+                                                      const float *e, float *xout, float omega, float scale, int last,
+                                                      double *zout, DeviceScalars *S, int rhoSlot, float omega0) {
     if (S->pcgDone) return;
     const int lane = threadIdx.x & 31;
     const int nseg = S->numSegments, nw = (gridDim.x * blockDim.x) >> 5;
     double part = 0.0;
-    for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nseg; w += nw) {
-        int c = segCell[w] + lane;
-        if ((segMask[w] >> lane) & 1u) {
-            float inv = M.invD[c];
-            double rd = r[c];
-            float b = (float)rd;
-            float xn;
-            if (inv == 0.0f) xn = 0.0f;
-            else if (mode == 0) xn = omega * inv * b;
-            else if (mode == 3) xn = (1.0f - omega) * (omega * inv * b) + omega * inv * (b + mg0_offsum_first(M, r, c, omega));
-            else if (mode == 1) xn = (1.0f - omega) * xin[c] + omega * inv * (b + mg0_offsum(M, xin, c));
-            else xn = (1.0f - omega) * mg0_corr(M, C, xin, e, scale, c) + omega * inv * (b + mg0_offsum_corr(M, C, xin, e, scale, c));
-            xout[c] = xn;
-            if (last) {
-                zout[c] = (double)xn;
-                part += (double)xn * rd;
-            }
+    for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nseg; w += 2 * nw) {
+        const int w2 = w + nw;
+        const bool has2 = w2 < nseg;
+        const int cA = segCell[w] + lane;
+        const unsigned int mA = segMask[w];
+        const int cB = has2 ? segCell[w2] + lane : cA;
+        const unsigned int mB = has2 ? segMask[w2] : 0u;
+        const bool rA = (mA >> lane) & 1u, rB = (mB >> lane) & 1u;
+        float xA = 0.0f, xB = 0.0f;
+        double rdA = 0.0, rdB = 0.0;
+        if (rA) xA = mg0_sweep_row<MODE>(M, C, r, xin, e, omega, omega0, scale, cA, rdA);
+        if (rB) xB = mg0_sweep_row<MODE>(M, C, r, xin, e, omega, omega0, scale, cB, rdB);
+        if (rA) {
+            xout[cA] = xA;
+            if (last) { zout[cA] = (double)xA; part += (double)xA * rdA; }
+        }
+        if (rB) {
+            xout[cB] = xB;
+            if (last) { zout[cB] = (double)xB; part += (double)xB * rdB; }
         }
     }
     if (last) block_add(part, &S->rho[rhoSlot]);
+}
+
+// host-side dispatch on the sweep mode
+static void launch_mg0_sweep(int blocks, cudaStream_t st, const int *segCell, const unsigned int *segMask, const Mg0 &M,
+                             const MgLevel &C, const double *r, const float *xin, const float *e, float *xout, float omega,
+                             float scale, int mode, int last, double *zout, DeviceScalars *S, int rhoSlot, float omega0) {
+    switch (mode) {
+        case 0: k_mg0_sweep<0><<<blocks, TPB, 0, st>>>(segCell, segMask, M, C, r, xin, e, xout, omega, scale, last, zout, S, rhoSlot, omega0); break;
+        case 1: k_mg0_sweep<1><<<blocks, TPB, 0, st>>>(segCell, segMask, M, C, r, xin, e, xout, omega, scale, last, zout, S, rhoSlot, omega0); break;
+        case 2: k_mg0_sweep<2><<<blocks, TPB, 0, st>>>(segCell, segMask, M, C, r, xin, e, xout, omega, scale, last, zout, S, rhoSlot, omega0); break;
+        default: k_mg0_sweep<3><<<blocks, TPB, 0, st>>>(segCell, segMask, M, C, r, xin, e, xout, omega, scale, last, zout, S, rhoSlot, omega0); break;
+    }
 }
 
 // b_1(C) = sum over the row children of (r - A0 x0)
@@ -883,6 +1234,7 @@ struct PcgDev {
     int numLevels, firstSmall;
     MgParams mp;
     int useMg, maxIter;
+    int warm;          // x holds an initial guess
     DeviceScalars *S;
 };
 
@@ -912,8 +1264,11 @@ __global__ void __launch_bounds__(TPB) k_pcg_persistent(PcgDev P) {
     const int gthreads = gridDim.x * blockDim.x;
     const int gwarp = gtid >> 5, nwarps = gthreads >> 5;
     const int nseg = S->numSegments;
-    const float omega = P.mp.omega, scale = P.mp.scale;
+    const float scale = P.mp.scale;
     const int nu = P.mp.nu;
+    const float omCoarse = P.mp.omegaCoarse;
+    auto preOm = [&](int sw) { return P.mp.om[sw]; };
+    auto postOm = [&](int sw) { return P.mp.om[nu - 1 - sw]; };
     const int L = P.numLevels;
     const int fs = P.firstSmall ? P.firstSmall : L;
     float *x0a = P.lv[0].x, *x0b = P.lv[0].x2;
@@ -923,6 +1278,7 @@ __global__ void __launch_bounds__(TPB) k_pcg_persistent(PcgDev P) {
     auto vcycle_after_first_sweep = [&](int rhoSlot) {
         float *xa = x0a, *xb = x0b;
         for (int sw = 1; sw < nu; sw++) {
+            const float omega = preOm(sw);
             for (int seg = gwarp; seg < nseg; seg += nwarps) {
                 if ((P.segMask[seg] >> lane) & 1u) {
                     int c = P.segCell[seg] + lane;
@@ -959,7 +1315,7 @@ __global__ void __launch_bounds__(TPB) k_pcg_persistent(PcgDev P) {
             const MgLevel &Lv = P.lv[l];
             float *ya = Lv.x, *yb = Lv.x2;
             for (int sw = 0; sw < nu; sw++) {
-                pg_sweep_level(Lv, Lv, ya, nullptr, yb, omega, scale, sw == 0 ? 0 : 1, gtid, gthreads);
+                pg_sweep_level(Lv, Lv, ya, nullptr, yb, preOm(sw), scale, sw == 0 ? 0 : 1, gtid, gthreads);
                 grid.sync();
                 float *t = ya; ya = yb; yb = t;
             }
@@ -976,7 +1332,7 @@ __global__ void __launch_bounds__(TPB) k_pcg_persistent(PcgDev P) {
                     int sweeps = (l == L - 1) ? P.mp.coarseSweeps : nu;
                     float *ya = Lv.x, *yb = Lv.x2;
                     for (int sw = 0; sw < sweeps; sw++) {
-                        pg_sweep_level(Lv, Lv, ya, nullptr, yb, omega, scale, sw == 0 ? 0 : 1, tid, nt);
+                        pg_sweep_level(Lv, Lv, ya, nullptr, yb, (l == L - 1) ? omCoarse : preOm(sw), scale, sw == 0 ? 0 : 1, tid, nt);
                         __syncthreads();
                         float *t = ya; ya = yb; yb = t;
                     }
@@ -990,7 +1346,7 @@ __global__ void __launch_bounds__(TPB) k_pcg_persistent(PcgDev P) {
                     const MgLevel &Lv = P.lv[l];
                     float *ya = lx[l], *yb = (ya == Lv.x) ? Lv.x2 : Lv.x;
                     for (int sw = 0; sw < nu; sw++) {
-                        pg_sweep_level(Lv, P.lv[l + 1], ya, lx[l + 1], yb, omega, scale, sw == 0 ? 2 : 1, tid, nt);
+                        pg_sweep_level(Lv, P.lv[l + 1], ya, lx[l + 1], yb, postOm(sw), scale, sw == 0 ? 2 : 1, tid, nt);
                         __syncthreads();
                         float *t = ya; ya = yb; yb = t;
                     }
@@ -1008,7 +1364,7 @@ __global__ void __launch_bounds__(TPB) k_pcg_persistent(PcgDev P) {
             const MgLevel &Lv = P.lv[L - 1];
             float *ya = Lv.x, *yb = Lv.x2;
             for (int sw = 0; sw < P.mp.coarseSweeps; sw++) {
-                pg_sweep_level(Lv, Lv, ya, nullptr, yb, omega, scale, sw == 0 ? 0 : 1, gtid, gthreads);
+                pg_sweep_level(Lv, Lv, ya, nullptr, yb, omCoarse, scale, sw == 0 ? 0 : 1, gtid, gthreads);
                 grid.sync();
                 float *t = ya; ya = yb; yb = t;
             }
@@ -1020,7 +1376,7 @@ __global__ void __launch_bounds__(TPB) k_pcg_persistent(PcgDev P) {
             const MgLevel &Lv = P.lv[l];
             float *ya = lx[l], *yb = (ya == Lv.x) ? Lv.x2 : Lv.x;
             for (int sw = 0; sw < nu; sw++) {
-                pg_sweep_level(Lv, P.lv[l + 1], ya, lx[l + 1], yb, omega, scale, sw == 0 ? 2 : 1, gtid, gthreads);
+                pg_sweep_level(Lv, P.lv[l + 1], ya, lx[l + 1], yb, postOm(sw), scale, sw == 0 ? 2 : 1, gtid, gthreads);
                 grid.sync();
                 float *t = ya; ya = yb; yb = t;
             }
@@ -1032,6 +1388,7 @@ __global__ void __launch_bounds__(TPB) k_pcg_persistent(PcgDev P) {
         double part = 0.0;
         for (int sw = 0; sw < nu; sw++) {
             const bool last = (sw == nu - 1);
+            const float omega = postOm(sw);
             for (int seg = gwarp; seg < nseg; seg += nwarps) {
                 if ((P.segMask[seg] >> lane) & 1u) {
                     int c = P.segCell[seg] + lane;
@@ -1060,9 +1417,10 @@ __global__ void __launch_bounds__(TPB) k_pcg_persistent(PcgDev P) {
             if ((P.segMask[seg] >> lane) & 1u) {
                 int c = P.segCell[seg] + lane;
                 double rv = P.b[c];
+                if (P.warm) rv -= apply_row(P.g, c, P.factor, P.Adiag, P.oU, P.oV, P.oW, P.x);
                 P.r[c] = rv;
                 if (P.useMg) {
-                    x0a[c] = omega * P.m0.invD[c] * (float)rv;
+                    x0a[c] = preOm(0) * P.m0.invD[c] * (float)rv;
                 } else {
                     double d = P.Adiag[c];
                     double zv = (d != 0.0) ? rv / d : 0.0;
@@ -1118,7 +1476,7 @@ __global__ void __launch_bounds__(TPB) k_pcg_persistent(PcgDev P) {
                     P.r[c] = rv;
                     rabs = fmax(rabs, fabs(rv));
                     if (P.useMg) {
-                        x0a[c] = omega * P.m0.invD[c] * (float)rv;
+                        x0a[c] = preOm(0) * P.m0.invD[c] * (float)rv;
                     } else {
                         double d = P.Adiag[c];
                         double zv = (d != 0.0) ? rv / d : 0.0;
@@ -1239,6 +1597,7 @@ __global__ void k_reset_pressure_scalars(DeviceScalars *S) {
 // ------------------------------------------------------------------------------------------------
 struct PressureScratch {
     unsigned int *maskAll = nullptr;
+    unsigned int *maskPrev = nullptr;  // row bits of the previous solve (warm start)
     int *flagAll = nullptr;
     int *posAll = nullptr;
     int nSegAll = 0;
@@ -1251,7 +1610,11 @@ struct PressureScratch {
     int *segPool = nullptr;
     int *lvSeg[MG_MAX_LEVELS] = {nullptr};
     int *lvSegCount = nullptr;         // [MG_MAX_LEVELS]
-    size_t smallSmemBytes = 0;         // dynamic shared memory of k_mg_small_smem (0: does not fit, use k_mg_small)
+    size_t coarseSmemBytes = 0;        // dynamic shared memory of k_mg_coarse (0: not usable, per-pass launches instead)
+    int coarseBlocks = 0;              // its cooperative grid: one CTA per SM
+    float *coarseBase = nullptr;       // levels >= 1 inside `pool` (L2 persistence window)
+    size_t coarseBytes = 0, l2SetAside = 0, l2Window = 0;
+    unsigned long long *trace = nullptr;   // FLIP_MG_TRACE developer probe
     int coopBlocks = 0;                // grid of the persistent solver (SMs x resident CTAs)
     // z-slabs: levels >= Lc span the WHOLE domain and are held (redundantly) by every rank; the
     // restricted residual of level Lc is all-gathered once per V-cycle.  Lc == 0: every level is local.
@@ -1288,6 +1651,9 @@ void pressure_alloc(flip_ctx *c) {
     PressureScratch *ps = new PressureScratch();
     ps->nSegAll = nSeg;
     FLIP_CUDA_CHECK(cudaMalloc(&ps->maskAll, sizeof(unsigned int) * nSeg));
+    FLIP_CUDA_CHECK(cudaMalloc(&ps->maskPrev, sizeof(unsigned int) * nSeg));
+    FLIP_CUDA_CHECK(cudaMemset(ps->maskAll, 0, sizeof(unsigned int) * nSeg));
+    FLIP_CUDA_CHECK(cudaMemset(ps->maskPrev, 0, sizeof(unsigned int) * nSeg));
     FLIP_CUDA_CHECK(cudaMalloc(&ps->flagAll, sizeof(int) * (nSeg + 1)));
     FLIP_CUDA_CHECK(cudaMalloc(&ps->posAll, sizeof(int) * (nSeg + 1)));
     c->mg = ps;
@@ -1300,7 +1666,7 @@ void pressure_alloc(flip_ctx *c) {
         while (L < MG_MAX_LEVELS) {
             MgLevel &lv = ps->lv[L];
             lv.I = I; lv.J = J; lv.K = K; lv.sj = I; lv.sk = I * J; lv.n = I * J * K; lv.cut = 0;
-            size_t np = (size_t)lv.n + 64;
+            size_t np = (size_t)lv.n + 64 + (L == 0 ? 0 : 2 * (size_t)mg_pad(lv.sk));
             total += (L == 0) ? 3 * np : 8 * np;
             L++;
             if (I <= 2 && J <= 2 && K <= 2) break;
@@ -1313,19 +1679,38 @@ void pressure_alloc(flip_ctx *c) {
         ps->firstSmall = 0;
         for (int l = 0; l < L; l++) {
             MgLevel &lv = ps->lv[l];
-            size_t np = (size_t)lv.n + 64;
+            // levels >= 1: every array is zero-padded by at least one plane on both sides (the branch-free passes
+            // of k_mg_coarse read neighbours unconditionally); the pads are never written
+            const size_t pad = (l == 0) ? 0 : (size_t)mg_pad(lv.sk);
+            size_t np = (size_t)lv.n + 64 + 2 * pad;
             lv.diag = lv.oU = lv.oV = lv.oW = lv.b = nullptr;
-            lv.invD = q; q += np;
-            lv.x = q; q += np;
-            lv.x2 = q; q += np;
+            if (l == 1) { ps->coarseBase = q; ps->coarseBytes = sizeof(float) * (total - (size_t)(q - ps->pool)); }
+            lv.invD = q + pad; q += np;
+            lv.x = q + pad; q += np;
+            lv.x2 = q + pad; q += np;
             if (l > 0) {
-                lv.diag = q; q += np;
-                lv.oU = q; q += np;
-                lv.oV = q; q += np;
-                lv.oW = q; q += np;
-                lv.b = q; q += np;
+                lv.diag = q + pad; q += np;
+                lv.oU = q + pad; q += np;
+                lv.oV = q + pad; q += np;
+                lv.oW = q + pad; q += np;
+                lv.b = q + pad; q += np;
                 if (ps->firstSmall == 0 && lv.n <= MG_SMALL) ps->firstSmall = l;
             }
+        }
+        // L2 set-aside for the coarse levels (see stage_pressure)
+        {
+            int maxPersist = 0, maxWindow = 0;
+            cudaDeviceGetAttribute(&maxPersist, cudaDevAttrMaxPersistingL2CacheSize, c->device);
+            cudaDeviceGetAttribute(&maxWindow, cudaDevAttrMaxAccessPolicyWindowSize, c->device);
+            ps->l2SetAside = 0;
+            if (maxPersist > 0 && maxWindow > 0 && ps->coarseBase && !getenv("FLIP_MG_NO_L2PIN")) {
+                size_t want = std::min((size_t)maxPersist, (size_t)48 << 20);
+                if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
+                    ps->l2SetAside = want;
+                    ps->l2Window = std::min(ps->coarseBytes, (size_t)maxWindow);
+                }
+            }
+            cudaGetLastError();
         }
     }
     // active-segment lists of the coarse levels, and the shared-memory budget of the single-CTA levels
@@ -1337,15 +1722,22 @@ void pressure_alloc(flip_ctx *c) {
         ps->lvSegCount = ps->segPool;
         int *q = ps->segPool + MG_MAX_LEVELS;
         for (int l = 1; l < ps->numLevels; l++) { ps->lvSeg[l] = q; q += cdiv(ps->lv[l].n, 32) + 1; }
-        ps->smallSmemBytes = 0;
-        if (ps->firstSmall) {
+        ps->coarseSmemBytes = 0;
+        if (ps->firstSmall && !getenv("FLIP_MG_NO_COOP")) {
             size_t bytes = 0;
-            for (int l = ps->firstSmall; l < ps->numLevels; l++) bytes += 8ull * sizeof(float) * ps->lv[l].n;
-            int maxOptin = 0;
+            for (int l = ps->firstSmall; l < ps->numLevels; l++) bytes += sizeof(float) * sm_level_floats(ps->lv[l].n, ps->lv[l].sk);
+            int maxOptin = 0, coop = 0, sms = 0, perSm = 0;
             FLIP_CUDA_CHECK(cudaDeviceGetAttribute(&maxOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
-            if (bytes + 2048 <= (size_t)maxOptin) {
-                FLIP_CUDA_CHECK(cudaFuncSetAttribute(k_mg_small_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-                ps->smallSmemBytes = bytes;
+            FLIP_CUDA_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device));
+            FLIP_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+            if (coop && bytes + 4096 <= (size_t)maxOptin) {
+                FLIP_CUDA_CHECK(cudaFuncSetAttribute(k_mg_coarse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+                FLIP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_mg_coarse, 1024, bytes));
+                if (perSm >= 1) { ps->coarseSmemBytes = bytes; ps->coarseBlocks = sms; }
+                if (getenv("FLIP_MG_TRACE")) {
+                    FLIP_CUDA_CHECK(cudaMalloc(&ps->trace, 64 * sizeof(unsigned long long)));
+                    FLIP_CUDA_CHECK(cudaMemset(ps->trace, 0, 64 * sizeof(unsigned long long)));
+                }
             }
         }
     }
@@ -1396,8 +1788,8 @@ void pressure_free(flip_ctx *c) {
     cudaFree(c->vx_); cudaFree(c->vr); cudaFree(c->vs); cudaFree(c->vz); cudaFree(c->vb);
     if (c->mg) {
         PressureScratch *ps = (PressureScratch *)c->mg;
-        cudaFree(ps->maskAll); cudaFree(ps->flagAll); cudaFree(ps->posAll); cudaFree(ps->pool); cudaFree(ps->gpool);
-        cudaFree(ps->segPool);
+        cudaFree(ps->maskAll); cudaFree(ps->maskPrev); cudaFree(ps->flagAll); cudaFree(ps->posAll); cudaFree(ps->pool); cudaFree(ps->gpool);
+        cudaFree(ps->segPool); cudaFree(ps->trace);
         delete ps;
         c->mg = nullptr;
     }
@@ -1410,6 +1802,9 @@ void stage_pressure(flip_ctx *c, double dt) {
     PGrid g{d.I, d.J, d.K, d.I, d.I * d.J, d.kOff, d.Kg, d.kOwn0, d.kOwn1, 0};
     int nSeg = ps->nSegAll;
 
+    // warm start: the row bits of the previous solve say where vx_ holds a pressure worth starting from
+    const bool warm = c->pressureWarmStart != 0;
+    std::swap(ps->maskAll, ps->maskPrev);
     size_t ktBuild = kt_begin(c);
     k_reset_pressure_scalars<<<1, 1, 0, st>>>(c->dS); c->launches++;
     k_seg_flag<<<cdiv((long long)nSeg * 32, TPB), TPB, 0, st>>>(c->phiL, g, d.nC, nSeg, ps->maskAll, ps->flagAll, c->dS);
@@ -1440,7 +1835,8 @@ void stage_pressure(flip_ctx *c, double dt) {
     bp.invdx = 1.0 / d.dx;
     bp.factor = dt / (d.dx * d.dx);
     k_build_system<<<segBlocks, TPB, 0, st>>>(c->segCell, c->segMask, bp, c->phiL, c->U, c->V, c->W, c->wU, c->wV,
-                                             c->wW, c->Adiag, c->AoffU, c->AoffV, c->AoffW, c->vb, c->vx_, c->dS);
+                                             c->wW, c->Adiag, c->AoffU, c->AoffV, c->AoffW, c->vb, c->vx_, c->dS,
+                                             warm ? ps->maskPrev : nullptr);
     c->launches++;
     kt_end(c, FLIP_KERNEL_PRESSURE_BUILD, ktBuild);
     const bool slab = slab_on(c);
@@ -1467,6 +1863,23 @@ void stage_pressure(flip_ctx *c, double dt) {
     // early out (pressuresolver.cpp:52-62): velocities and the valid mask stay untouched
     if (n == 0 || bmax < c->pressureTol) return;
 
+    // The coarse levels are a few MB that every V-cycle walks through ~17 latency-bound passes, while the level-0
+    // passes stream ~0.5 GB through L2 in between: keep the coarse levels resident in the L2 set-aside so that
+    // their dependent loads cost an L2 hit instead of a DRAM round trip.
+    if (ps->l2SetAside && !slab) {
+        cudaStreamAttrValue attr;
+        memset(&attr, 0, sizeof(attr));
+        attr.accessPolicyWindow.base_ptr = ps->coarseBase;
+        attr.accessPolicyWindow.num_bytes = ps->l2Window;
+        const double touched = 6.0 * (double)n + (double)(1 << 20);      // ~32 B per coarse cell, ~n/7 * 1.3 cells
+        attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)ps->l2SetAside / touched);
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) {
+            cudaGetLastError();
+            ps->l2SetAside = 0;
+        }
+    }
     segBlocks = std::max(1, cdiv((long long)numSeg * 32, TPB));
     const int loopBlocks = std::min(segBlocks, 148 * 6);    // grid-stride passes: one resident wave
     PcgParams pp;
@@ -1484,7 +1897,11 @@ void stage_pressure(flip_ctx *c, double dt) {
     int jacobi = useMg ? 0 : 1;
     Mg0 m0;
     MgParams mp;
-    mp.omega = (float)c->mgOmega; mp.scale = (float)c->mgScale; mp.nu = c->mgNu; mp.coarseSweeps = c->mgCoarseSweeps;
+    for (int q = 0; q < MG_MAX_SWEEPS; q++) mp.om[q] = (float)c->mgOmegaSched[q];
+    mp.omegaCoarse = (float)c->mgOmega;
+    mp.scale = (float)c->mgScale; mp.nu = c->mgNu; mp.coarseSweeps = c->mgCoarseSweeps;
+    auto pre_om = [&](int sw) { return mp.om[sw]; };
+    auto post_om = [&](int sw) { return mp.om[mp.nu - 1 - sw]; };
     if (useMg) {
         m0.g = g; m0.fac = (float)bp.factor; m0.Adiag = c->Adiag;
         m0.oU = c->AoffU; m0.oV = c->AoffV; m0.oW = c->AoffW;
@@ -1563,8 +1980,8 @@ void stage_pressure(flip_ctx *c, double dt) {
         {   // level 0 pre-smoothing
             float *xa = ps->lv[0].x, *xb = ps->lv[0].x2;
             for (int sw = 0; sw < nu; sw++) {
-                k_mg0_sweep<<<loopBlocks, TPB, 0, st>>>(c->segCell, c->segMask, m0, up_desc(0), c->vr, xa, nullptr, xb, mp.omega,
-                                                      mp.scale, sw == 0 ? 0 : 1, 0, nullptr, c->dS, 0);
+                launch_mg0_sweep(loopBlocks, st, c->segCell, c->segMask, m0, up_desc(0), c->vr, xa, nullptr, xb, pre_om(sw),
+                                                      mp.scale, sw == 0 ? 0 : 1, 0, nullptr, c->dS, 0, 0.0f);
                 c->launches++;
                 std::swap(xa, xb);
                 xchg(0, xa);
@@ -1578,7 +1995,7 @@ void stage_pressure(flip_ctx *c, double dt) {
             MgLevel &lv = *LV[l];
             float *xa = lv.x, *xb = lv.x2;
             for (int sw = 0; sw < nu; sw++) {
-                k_mg_sweep<<<cdiv(lv.n, TPB), TPB, 0, st>>>(lv, lv, xa, nullptr, xb, mp.omega, mp.scale, sw == 0 ? 0 : 1, c->dS);
+                k_mg_sweep<<<cdiv(lv.n, TPB), TPB, 0, st>>>(lv, lv, xa, nullptr, xb, pre_om(sw), mp.scale, sw == 0 ? 0 : 1, c->dS);
                 c->launches++;
                 std::swap(xa, xb);
                 xchg(l, xa);
@@ -1597,7 +2014,7 @@ void stage_pressure(flip_ctx *c, double dt) {
             MgLevel &lv = *LV[L - 1];
             float *xa = lv.x, *xb = lv.x2;
             for (int sw = 0; sw < mp.coarseSweeps; sw++) {
-                k_mg_sweep<<<cdiv(lv.n, TPB), TPB, 0, st>>>(lv, lv, xa, nullptr, xb, mp.omega, mp.scale, sw == 0 ? 0 : 1, c->dS);
+                k_mg_sweep<<<cdiv(lv.n, TPB), TPB, 0, st>>>(lv, lv, xa, nullptr, xb, mp.omegaCoarse, mp.scale, sw == 0 ? 0 : 1, c->dS);
                 c->launches++;
                 std::swap(xa, xb);
             }
@@ -1609,7 +2026,7 @@ void stage_pressure(flip_ctx *c, double dt) {
             MgLevel &lv = *LV[l];
             float *xa = lv.x, *xb = lv.x2;
             for (int sw = 0; sw < nu; sw++) {
-                k_mg_sweep<<<cdiv(lv.n, TPB), TPB, 0, st>>>(lv, up_desc(l), xa, up_x(l), xb, mp.omega, mp.scale,
+                k_mg_sweep<<<cdiv(lv.n, TPB), TPB, 0, st>>>(lv, up_desc(l), xa, up_x(l), xb, post_om(sw), mp.scale,
                                                           sw == 0 ? 2 : 1, c->dS);
                 c->launches++;
                 std::swap(xa, xb);
@@ -1621,8 +2038,8 @@ void stage_pressure(flip_ctx *c, double dt) {
             float *xa = ps->lv[0].x, *xb = ps->lv[0].x2;
             for (int sw = 0; sw < nu; sw++) {
                 int last = (sw == nu - 1) ? 1 : 0;
-                k_mg0_sweep<<<loopBlocks, TPB, 0, st>>>(c->segCell, c->segMask, m0, up_desc(0), c->vr, xa, up_x(0), xb, mp.omega,
-                                                      mp.scale, sw == 0 ? 2 : 1, last, c->vz, c->dS, rhoSlot);
+                launch_mg0_sweep(loopBlocks, st, c->segCell, c->segMask, m0, up_desc(0), c->vr, xa, up_x(0), xb, post_om(sw),
+                                                      mp.scale, sw == 0 ? 2 : 1, last, c->vz, c->dS, rhoSlot, 0.0f);
                 c->launches++;
                 std::swap(xa, xb);
                 if (!last) xchg(0, xa);
@@ -1645,15 +2062,15 @@ void stage_pressure(flip_ctx *c, double dt) {
             float *xa = ps->lv[0].x, *xb = ps->lv[0].x2;
             int sw = 0;
             if (nu >= 2) {
-                k_mg0_sweep<<<loopBlocks, TPB, 0, st>>>(c->segCell, c->segMask, m0, ps->lv[1], c->vr, xa, nullptr, xb, mp.omega,
-                                                      mp.scale, 3, 0, nullptr, c->dS, 0);
+                launch_mg0_sweep(loopBlocks, st, c->segCell, c->segMask, m0, ps->lv[1], c->vr, xa, nullptr, xb, pre_om(1),
+                                                      mp.scale, 3, 0, nullptr, c->dS, 0, pre_om(0));
                 c->launches++;
                 std::swap(xa, xb);
                 sw = 2;
             }
             for (; sw < nu; sw++) {
-                k_mg0_sweep<<<loopBlocks, TPB, 0, st>>>(c->segCell, c->segMask, m0, ps->lv[1], c->vr, xa, nullptr, xb, mp.omega,
-                                                      mp.scale, sw == 0 ? 0 : 1, 0, nullptr, c->dS, 0);
+                launch_mg0_sweep(loopBlocks, st, c->segCell, c->segMask, m0, ps->lv[1], c->vr, xa, nullptr, xb, pre_om(sw),
+                                                      mp.scale, sw == 0 ? 0 : 1, 0, nullptr, c->dS, 0, 0.0f);
                 c->launches++;
                 std::swap(xa, xb);
             }
@@ -1662,55 +2079,73 @@ void stage_pressure(flip_ctx *c, double dt) {
             c->launches++;
             ps->lv[0].x = xa; ps->lv[0].x2 = xb;
         }
-        for (int l = 1; l < fs && l < L - 1; l++) {
-            MgLevel &lv = ps->lv[l];
-            float *xa = lv.x, *xb = lv.x2;
-            int sw = 0;
-            if (nu >= 2) {
-                k_mg_sweep_list<<<list_blocks(lv), TPB, 0, st>>>(lv, lv, xa, nullptr, xb, mp.omega, mp.scale, 3, ps->lvSeg[l],
-                                                                &ps->lvSegCount[l], c->dS);
-                c->launches++;
-                std::swap(xa, xb);
-                sw = 2;
-            }
-            for (; sw < nu; sw++) {
-                k_mg_sweep_list<<<list_blocks(lv), TPB, 0, st>>>(lv, lv, xa, nullptr, xb, mp.omega, mp.scale, sw == 0 ? 0 : 1,
-                                                                ps->lvSeg[l], &ps->lvSegCount[l], c->dS);
-                c->launches++;
-                std::swap(xa, xb);
-            }
-            lv.x = xa; lv.x2 = xb;
-            k_mg_restrict_list<<<restrict_blocks(ps->lv[l + 1]), 256, 0, st>>>(lv, ps->lv[l + 1], lv.x, ps->lvSeg[l + 1],
-                                                                              &ps->lvSegCount[l + 1], c->dS);
+        if (ps->coarseSmemBytes) {
+            // levels 1..coarsest in one cooperative launch
+            MgCoarseArgs A;
+            for (int l = 0; l < MG_MAX_LEVELS; l++) { A.lv[l] = ps->lv[l < L ? l : 0]; A.seg[l] = ps->lvSeg[l < L ? l : 0]; }
+            A.segCount = ps->lvSegCount;
+            A.fs = fs; A.last = L - 1; A.p = mp;
+            A.smemFloats = (int)(ps->coarseSmemBytes / sizeof(float));
+            A.trace = ps->trace;
+            const DeviceScalars *Sdev = c->dS;
+            void *args[] = {&A, &Sdev};
+            FLIP_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)k_mg_coarse, dim3(ps->coarseBlocks), dim3(1024), args,
+                                                        ps->coarseSmemBytes, st));
             c->launches++;
-        }
-        // ---- bottom: the small levels in one CTA
-        {
-            MgSmallArgs A;
-            for (int l = 0; l < L; l++) A.lv[l] = ps->lv[l];
-            A.first = fs; A.last = L - 1; A.p = mp;
-            if (ps->smallSmemBytes) k_mg_small_smem<<<1, 1024, ps->smallSmemBytes, st>>>(A, c->dS);
-            else k_mg_small<<<1, 1024, 0, st>>>(A, c->dS);
-            c->launches++;
-        }
-        // ---- up
-        for (int l = fs - 1; l >= 1; l--) {
-            MgLevel &lv = ps->lv[l];
-            float *xa = lv.x, *xb = lv.x2;
-            for (int sw = 0; sw < nu; sw++) {
-                k_mg_sweep_list<<<list_blocks(lv), TPB, 0, st>>>(lv, ps->lv[l + 1], xa, ps->lv[l + 1].x, xb, mp.omega, mp.scale,
-                                                                sw == 0 ? 2 : 1, ps->lvSeg[l], &ps->lvSegCount[l], c->dS);
+            // the kernel ping-pongs x/x2 of the list-driven levels: replay the parity to find the results
+            const int swaps = (nu >= 2 ? nu - 1 : nu) + nu;
+            if (swaps & 1)
+                for (int l = 1; l < fs; l++) std::swap(ps->lv[l].x, ps->lv[l].x2);
+        } else {
+            for (int l = 1; l < fs && l < L - 1; l++) {
+                MgLevel &lv = ps->lv[l];
+                float *xa = lv.x, *xb = lv.x2;
+                int sw = 0;
+                if (nu >= 2) {
+                    k_mg_sweep_list<<<list_blocks(lv), TPB, 0, st>>>(lv, lv, xa, nullptr, xb, pre_om(1), mp.scale, 3, ps->lvSeg[l],
+                                                                    &ps->lvSegCount[l], c->dS, pre_om(0));
+                    c->launches++;
+                    std::swap(xa, xb);
+                    sw = 2;
+                }
+                for (; sw < nu; sw++) {
+                    k_mg_sweep_list<<<list_blocks(lv), TPB, 0, st>>>(lv, lv, xa, nullptr, xb, pre_om(sw), mp.scale, sw == 0 ? 0 : 1,
+                                                                    ps->lvSeg[l], &ps->lvSegCount[l], c->dS, 0.0f);
+                    c->launches++;
+                    std::swap(xa, xb);
+                }
+                lv.x = xa; lv.x2 = xb;
+                k_mg_restrict_list<<<restrict_blocks(ps->lv[l + 1]), 256, 0, st>>>(lv, ps->lv[l + 1], lv.x, ps->lvSeg[l + 1],
+                                                                                  &ps->lvSegCount[l + 1], c->dS);
                 c->launches++;
-                std::swap(xa, xb);
             }
-            lv.x = xa; lv.x2 = xb;
+            // ---- bottom: the small levels in one CTA
+            {
+                MgSmallArgs A;
+                for (int l = 0; l < L; l++) A.lv[l] = ps->lv[l];
+                A.first = fs; A.last = L - 1; A.p = mp;
+                k_mg_small<<<1, 1024, 0, st>>>(A, c->dS);
+                c->launches++;
+            }
+            // ---- up
+            for (int l = fs - 1; l >= 1; l--) {
+                MgLevel &lv = ps->lv[l];
+                float *xa = lv.x, *xb = lv.x2;
+                for (int sw = 0; sw < nu; sw++) {
+                    k_mg_sweep_list<<<list_blocks(lv), TPB, 0, st>>>(lv, ps->lv[l + 1], xa, ps->lv[l + 1].x, xb, post_om(sw), mp.scale,
+                                                                    sw == 0 ? 2 : 1, ps->lvSeg[l], &ps->lvSegCount[l], c->dS, 0.0f);
+                    c->launches++;
+                    std::swap(xa, xb);
+                }
+                lv.x = xa; lv.x2 = xb;
+            }
         }
         {
             float *xa = ps->lv[0].x, *xb = ps->lv[0].x2;
             for (int sw = 0; sw < nu; sw++) {
                 int last = (sw == nu - 1) ? 1 : 0;
-                k_mg0_sweep<<<loopBlocks, TPB, 0, st>>>(c->segCell, c->segMask, m0, ps->lv[1], c->vr, xa, ps->lv[1].x, xb, mp.omega,
-                                                      mp.scale, sw == 0 ? 2 : 1, last, c->vz, c->dS, rhoSlot);
+                launch_mg0_sweep(loopBlocks, st, c->segCell, c->segMask, m0, ps->lv[1], c->vr, xa, ps->lv[1].x, xb, post_om(sw),
+                                                      mp.scale, sw == 0 ? 2 : 1, last, c->vz, c->dS, rhoSlot, 0.0f);
                 c->launches++;
                 std::swap(xa, xb);
             }
@@ -1732,7 +2167,7 @@ void stage_pressure(flip_ctx *c, double dt) {
         if (!useMg) { P.m0.g = g; P.m0.fac = 0.f; P.m0.Adiag = c->Adiag; P.m0.oU = c->AoffU; P.m0.oV = c->AoffV; P.m0.oW = c->AoffW; P.m0.invD = ps->lv[0].invD; P.m0.rowBits = ps->maskAll; }
         for (int l = 0; l < MG_MAX_LEVELS; l++) P.lv[l] = ps->lv[l < ps->numLevels ? l : 0];
         P.numLevels = ps->numLevels; P.firstSmall = ps->firstSmall; P.mp = mp;
-        P.useMg = useMg ? 1 : 0; P.maxIter = c->pressureMaxIter; P.S = c->dS;
+        P.useMg = useMg ? 1 : 0; P.maxIter = c->pressureMaxIter; P.S = c->dS; P.warm = warm ? 1 : 0;
         if (ps->coopBlocks == 0) {
             int perSm = 0, sms = 0;
             FLIP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_pcg_persistent, TPB, 0));
@@ -1747,7 +2182,9 @@ void stage_pressure(flip_ctx *c, double dt) {
         c->launches++;
         scalars_to_host(c);
     } else {
-    k_pcg_init<<<segBlocks, TPB, 0, st>>>(c->segCell, c->segMask, pp, c->vb, c->Adiag, c->vr, c->vz, c->vs, c->dS, jacobi);
+    if (slab && warm) slab_exchange_vector_halo(c, c->vx_);     // the initial guess on the neighbours' boundary planes
+    k_pcg_init<<<segBlocks, TPB, 0, st>>>(c->segCell, c->segMask, pp, c->vb, c->Adiag, c->vr, c->vz, c->vs, c->dS, jacobi,
+                                          c->AoffU, c->AoffV, c->AoffW, warm ? c->vx_ : nullptr);
     c->launches++;
     if (useMg) {
         apply_precond(0);
@@ -1784,6 +2221,13 @@ void stage_pressure(flip_ctx *c, double dt) {
     }
     }   // multi-launch path
     FLIP_CUDA_CHECK(cudaGetLastError());
+    if (ps->trace) {
+        unsigned long long h[64];
+        FLIP_CUDA_CHECK(cudaMemcpy(h, ps->trace, sizeof(h), cudaMemcpyDeviceToHost));
+        fprintf(stderr, "k_mg_coarse phase ns:");
+        for (int q = 1; q < 64 && h[q]; q++) fprintf(stderr, " %llu", h[q] - h[q - 1]);
+        fprintf(stderr, "\n");
+    }
     c->cur.pcg_iterations = c->hS->pcgIterations;
     c->cur.pcg_error = c->hS->pcgError;
     bool success = c->hS->pcgDone == 1;
@@ -1791,7 +2235,11 @@ void stage_pressure(flip_ctx *c, double dt) {
     else if (c->hS->pcgIterations == c->pressureMaxIter && c->hS->pcgError < c->pressureAcceptableTol) c->cur.pcg_converged = 2;
     else c->cur.pcg_converged = 0;
     // _solveLinearSystem failure: solve() returns before applying (pressuresolver.cpp:70-72)
-    if (c->cur.pcg_converged == 0) return;
+    if (c->cur.pcg_converged == 0) {
+        // nothing worth a warm start from
+        FLIP_CUDA_CHECK(cudaMemsetAsync(ps->maskAll, 0, sizeof(unsigned int) * ps->nSegAll, st));
+        return;
+    }
 
     if (slab) slab_exchange_vector_halo(c, c->vx_);     // pressure of the neighbours' boundary planes
     ApplyParams ap;

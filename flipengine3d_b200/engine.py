@@ -73,6 +73,8 @@ def load_library():
     L.flip_set_preconditioner.argtypes = [vp, ci]
     L.flip_set_multigrid.argtypes = [vp, ci, cd, cd, ci]
     L.flip_set_solver_mode.argtypes = [vp, ci]
+    L.flip_set_pressure_warm_start.argtypes = [vp, ci]
+    L.flip_set_multigrid_schedule.argtypes = [vp, ci, C.POINTER(cd)]
     L.flip_set_sampling_mode.argtypes = [vp, ci]
     L.flip_load_particles.argtypes = [vp, ci, vp, vp]
     L.flip_add_fluid_box.argtypes = [vp, C.POINTER(cd), C.POINTER(cd), C.POINTER(cd)]
@@ -209,6 +211,14 @@ class FluidSimulation:
 
     def setMultigrid(self, sweeps=2, damping=0.8, coarse_weight=1.8, coarsest_sweeps=8):
         self._check(self.L.flip_set_multigrid(self.h, sweeps, damping, coarse_weight, coarsest_sweeps))
+
+    def setMultigridSchedule(self, dampings):
+        """Per-sweep damping factors of the pre-smoothing passes (post-smoothing mirrors them)."""
+        arr = (C.c_double * len(dampings))(*[float(w) for w in dampings])
+        self._check(self.L.flip_set_multigrid_schedule(self.h, len(dampings), arr))
+
+    def setPressureWarmStart(self, on=True):
+        self._check(self.L.flip_set_pressure_warm_start(self.h, 1 if on else 0))
 
     def setSamplingMode(self, mode):
         """'exact': the reference's double-precision trilinear blend (bit-identical G2P / RK3);

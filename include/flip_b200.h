@@ -108,6 +108,15 @@ int flip_set_preconditioner(flip_ctx *ctx, int kind);
 /* Tuning of the multigrid V-cycle: damped-Jacobi sweeps before/after the coarse correction,
  * damping, weight of the coarse correction, sweeps on the coarsest level. */
 int flip_set_multigrid(flip_ctx *ctx, int sweeps, double damping, double coarse_weight, int coarsest_sweeps);
+/* Per-sweep damping of the `sweeps` pre-smoothing passes (the post-smoothing passes use the mirrored order,
+ * which keeps the V-cycle symmetric as CG requires).  Reciprocals of the Chebyshev nodes of the interval of
+ * the Jacobi-scaled spectrum to be damped turn the sweeps into a polynomial smoother at no extra cost. */
+int flip_set_multigrid_schedule(flip_ctx *ctx, int sweeps, const double *damping);
+/* Initial guess of the PCG.  0: zero, as the reference (pcgsolver.h:258).  1 (default): the pressure of the
+ * previous substep on the cells that were pressure rows then (zero elsewhere).  The stopping rule is unchanged
+ * (||r||_inf <= tol * ||b||_inf with r = b - A x), so the answer agrees to the solver tolerance; only the
+ * number of iterations drops. */
+int flip_set_pressure_warm_start(flip_ctx *ctx, int on);
 /* 1: the PCG solve runs as one persistent cooperative kernel (device-side iteration loop,
  * grid-wide barriers); 0 (default): one launch per solver pass, host polls the convergence flag. Same arithmetic. */
 int flip_set_solver_mode(flip_ctx *ctx, int persistent);
