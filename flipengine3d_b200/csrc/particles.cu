@@ -20,6 +20,8 @@ static constexpr int TPB = 256;
 static void soa_alloc(ParticleSoA &p, int cap) {
     float *blk = nullptr;
     FLIP_CUDA_CHECK(cudaMalloc(&blk, sizeof(float) * 6ull * cap));
+    // the gather reads aligned 4-particle windows that may reach past the last particle: keep the slack finite
+    FLIP_CUDA_CHECK(cudaMemset(blk, 0, sizeof(float) * 6ull * cap));
     p.px = blk; p.py = blk + (size_t)cap; p.pz = blk + 2ull * cap;
     p.vx = blk + 3ull * cap; p.vy = blk + 4ull * cap; p.vz = blk + 5ull * cap;
 }
@@ -132,6 +134,7 @@ struct SortParams {
     double dx, invdx;
     int applyRules;
     int maxPerCell;
+    float farFromSolid;   // 3dx
 };
 
 __device__ __forceinline__ bool sort_keeps(const SortParams &sp, float z) {
@@ -187,8 +190,13 @@ __global__ void k_classify(ParticleSoA p, SortParams sp, const float *__restrict
     } else if (inRange) {
         cell = i + sp.I * (j + sp.J * k);
         if (sp.applyRules) {
-            // MeshLevelSet::trilinearInterpolateSolidPoints  meshlevelset.h:325-332
-            float phi = sample_scalar(phiS, sp.I + 1, sp.J + 1, sp.K + 1, sp.dx, sp.invdx, x, y, z, sp.kOff);
+            // MeshLevelSet::trilinearInterpolateSolidPoints  meshlevelset.h:325-332.  Only its sign is used: where the
+            // lower corner node of the cell is at least 3dx outside the solid, the other seven nodes of the cell are
+            // outside too (a distance field changes by at most sqrt(3)dx across a cell) and so is their blend.
+            float phi = 1.0f;
+            const float corner = __ldg(phiS + (size_t)i + (size_t)(sp.I + 1) * ((size_t)j + (size_t)(sp.J + 1) * (size_t)k));
+            if (!(corner >= sp.farFromSolid))
+                phi = sample_scalar(phiS, sp.I + 1, sp.J + 1, sp.K + 1, sp.dx, sp.invdx, x, y, z, sp.kOff);
             if (phi < 0.0f) {
                 cell = -1;
                 atomicAdd(&S->removedSolid, 1);
@@ -228,7 +236,32 @@ __global__ void k_cell_finalize(int nC, const int *__restrict__ startA, int *__r
     int b = startA[c], e = startA[c + 1];
     int n = e - b;
     if (n == 0) { keptCount[c] = 0; return; }
-    // insertion sort (cells hold ~8 particles; the cap is 250)
+    constexpr int SMALL = 16;
+    if (n <= SMALL && n <= maxPerCell) {
+        // the usual cell (~8 particles): every load is independent, the order comes from a rank count in registers.
+        // final slot of a kept particle = number of kept particles of the cell with a smaller previous index
+        int v[SMALL];
+        bool drop[SMALL];
+#pragma unroll
+        for (int a = 0; a < SMALL; a++) v[a] = (a < n) ? sortIdx[b + a] : 0x7fffffff;
+#pragma unroll
+        for (int a = 0; a < SMALL; a++) drop[a] = (a < n) ? (applyRules && fast[v[a]] != 0) : true;
+        int kept = 0;
+#pragma unroll
+        for (int a = 0; a < SMALL; a++) {
+            if (a < n && !drop[a]) {
+                int r = 0;
+#pragma unroll
+                for (int q = 0; q < SMALL; q++) r += (!drop[q] && v[q] < v[a]) ? 1 : 0;
+                sortIdx[b + r] = v[a];
+                kept++;
+            }
+        }
+        if (kept != n) atomicAdd(&S->removedFast, n - kept);
+        keptCount[c] = kept;
+        return;
+    }
+    // insertion sort (the cap is 250)
     for (int a = b + 1; a < e; a++) {
         int v = sortIdx[a];
         int q = a - 1;
@@ -343,6 +376,7 @@ void particles_sort(flip_ctx *c, bool applyRules, double frameDt, int srcOffset,
     sp.n = n; sp.I = d.I; sp.J = d.J; sp.K = d.K; sp.dx = d.dx; sp.invdx = 1.0 / d.dx;
     sp.kOff = d.kOff; sp.kOwn0 = d.kOwn0; sp.kOwn1 = d.kOwn1; sp.ownedOnly = ownedOnly ? 1 : 0;
     sp.applyRules = applyRules ? 1 : 0; sp.maxPerCell = c->maxParticlesPerCell;
+    sp.farFromSolid = (float)(3.0 * d.dx);
     if (applyRules) {
         // _removeMarkerParticles(_currentFrameDeltaTime): bins are CFL*dx/dt_FRAME wide
         double speedLimitStep = c->CFL * d.dx / frameDt;
@@ -716,59 +750,59 @@ __global__ void __launch_bounds__(128) k_sdf_p2g(ParticleSoA p, const int *__res
 __global__ void k_sdf_far(ParticleSoA p, const int *__restrict__ cellStart, GatherParams g, float *__restrict__ phiL,
                           const float *__restrict__ phiS, const int *__restrict__ farCells,
                           const float *__restrict__ farBest, const int *__restrict__ farCount) {
+    // one WARP per queued cell: lane r < 25 scans row r of the 5x5 rows of the search box, then a warp minimum
     const int I = g.I, J = g.J, K = g.K;
     const int n = *farCount;
-    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+    const int lane = threadIdx.x & 31;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < n; t += nwarps) {
         const int cell = farCells[t];
         float best2 = farBest[t];
         const int i = cell % I, j = (cell / I) % J, k = cell / (I * J);
-        const NodeFrame f = node_frame(g, i, j, k + g.kOff);
-        const float sr = g.srS;
-        const double invdx = g.invdx;
-        const float dxf = (float)g.dx, margin = 1.0e-3f * dxf;
-        const float Xn = (float)dmul((double)(float)i, g.dx), Yn = (float)dmul((double)(float)j, g.dx),
-                    Zn = (float)dmul((double)(float)(k + g.kOff), g.dx);
-        const float loIn = -sr + margin, hiIn = dxf + sr - margin, loOut = -sr - margin, hiOut = dxf + sr + margin;
-        const int jlo = max(j - 1, 0), jhi = min(j + 1, J - 1), klo = max(k - 1, 0), khi = min(k + 1, K - 1);
-        const int ilo = max(i - 1, 0), ihi = min(i + 1, I - 1);
-        const int j2lo = max(j - 2, 0), j2hi = min(j + 2, J - 1);
-        const int k2lo = max(k - 2, 0), k2hi = min(k + 2, K - 1);
-        const int i2lo = max(i - 2, 0), i2hi = min(i + 2, I - 1);
-        for (int ck = k2lo; ck <= k2hi; ck++) {
-            for (int cj = j2lo; cj <= j2hi; cj++) {
-                bool innerRow = (ck >= klo && ck <= khi && cj >= jlo && cj <= jhi);
-                int rowBase = I * (cj + J * ck);
-                int qb = __ldg(cellStart + rowBase + i2lo);
-                int qe = __ldg(cellStart + rowBase + i2hi + 1);
-                if (qb == qe) continue;
-                int sb = 0, se = 0;   // range already visited by k_sdf_p2g (skip)
-                if (innerRow) { sb = __ldg(cellStart + rowBase + ilo); se = __ldg(cellStart + rowBase + ihi + 1); }
-                for (int q = qb; q < qe; q++) {
-                    if (innerRow && q >= sb && q < se) { q = se - 1; continue; }
-                    float x = __ldg(p.px + q), y = __ldg(p.py + q), z = __ldg(p.pz + q);
-                    // position relative to the cell's lower corner: inside the search box iff -sr <= u < dx + sr
-                    float ux = fsub(x, Xn), uy = fsub(y, Yn), uz = fsub(z, Zn);
-                    bool out = ux < loOut || ux >= hiOut || uy < loOut || uy >= hiOut || uz < loOut || uz >= hiOut;
-                    if (out) continue;
-                    bool in = ux >= loIn && ux < hiIn && uy >= loIn && uy < hiIn && uz >= loIn && uz < hiIn;
-                    float xl = fsub(x, f.ox), yl = fsub(y, f.oy), zl = fsub(z, f.oz);
-                    if (!in) {
-                        // borderline: the literal test.  Block membership of the particle: the blocks overlapped by
-                        // [p-sr, p+sr] in global coordinates; then the block-local search box.
-                        int bminx = pos2idx_d((double)fsub(x, sr), g.invBlockdxSDF), bmaxx = pos2idx_d((double)fadd(x, sr), g.invBlockdxSDF);
-                        int bminy = pos2idx_d((double)fsub(y, sr), g.invBlockdxSDF), bmaxy = pos2idx_d((double)fadd(y, sr), g.invBlockdxSDF);
-                        int bminz = pos2idx_d((double)fsub(z, sr), g.invBlockdxSDF), bmaxz = pos2idx_d((double)fadd(z, sr), g.invBlockdxSDF);
-                        if (f.bi < bminx || f.bi > bmaxx || f.bj < bminy || f.bj > bmaxy || f.bk < bminz || f.bk > bmaxz) continue;
-                        int gminx = pos2idx(fsub(xl, sr), invdx), gmaxx = pos2idx(fadd(xl, sr), invdx);
-                        int gminy = pos2idx(fsub(yl, sr), invdx), gmaxy = pos2idx(fadd(yl, sr), invdx);
-                        int gminz = pos2idx(fsub(zl, sr), invdx), gmaxz = pos2idx(fadd(zl, sr), invdx);
-                        if (f.li < gminx || f.li > gmaxx || f.lj < gminy || f.lj > gmaxy || f.lk < gminz || f.lk > gmaxz) continue;
-                    }
-                    best2 = fminf(best2, lengthsq3(fsub(f.cx, xl), fsub(f.cy, yl), fsub(f.cz, zl)));
+        const int cj = j + (lane % 5) - 2, ck = k + (lane / 5) - 2;
+        if (lane < 25 && cj >= 0 && cj < J && ck >= 0 && ck < K) {
+            const NodeFrame f = node_frame(g, i, j, k + g.kOff);
+            const float sr = g.srS;
+            const double invdx = g.invdx;
+            const float dxf = (float)g.dx, margin = 1.0e-3f * dxf;
+            const float Xn = (float)dmul((double)(float)i, g.dx), Yn = (float)dmul((double)(float)j, g.dx),
+                        Zn = (float)dmul((double)(float)(k + g.kOff), g.dx);
+            const float loIn = -sr + margin, hiIn = dxf + sr - margin, loOut = -sr - margin, hiOut = dxf + sr + margin;
+            const int ilo = max(i - 1, 0), ihi = min(i + 1, I - 1);
+            const int i2lo = max(i - 2, 0), i2hi = min(i + 2, I - 1);
+            const bool innerRow = (ck >= k - 1 && ck <= k + 1 && cj >= j - 1 && cj <= j + 1);
+            const int rowBase = I * (cj + J * ck);
+            const int qb = __ldg(cellStart + rowBase + i2lo);
+            const int qe = __ldg(cellStart + rowBase + i2hi + 1);
+            int sb = 0, se = 0;   // range already visited by k_sdf_p2g (skip)
+            if (innerRow) { sb = __ldg(cellStart + rowBase + ilo); se = __ldg(cellStart + rowBase + ihi + 1); }
+            for (int q = qb; q < qe; q++) {
+                if (innerRow && q >= sb && q < se) { q = se - 1; continue; }
+                float x = __ldg(p.px + q), y = __ldg(p.py + q), z = __ldg(p.pz + q);
+                // position relative to the cell's lower corner: inside the search box iff -sr <= u < dx + sr
+                float ux = fsub(x, Xn), uy = fsub(y, Yn), uz = fsub(z, Zn);
+                bool out = ux < loOut || ux >= hiOut || uy < loOut || uy >= hiOut || uz < loOut || uz >= hiOut;
+                if (out) continue;
+                bool in = ux >= loIn && ux < hiIn && uy >= loIn && uy < hiIn && uz >= loIn && uz < hiIn;
+                float xl = fsub(x, f.ox), yl = fsub(y, f.oy), zl = fsub(z, f.oz);
+                if (!in) {
+                    // borderline: the literal test.  Block membership of the particle: the blocks overlapped by
+                    // [p-sr, p+sr] in global coordinates; then the block-local search box.
+                    int bminx = pos2idx_d((double)fsub(x, sr), g.invBlockdxSDF), bmaxx = pos2idx_d((double)fadd(x, sr), g.invBlockdxSDF);
+                    int bminy = pos2idx_d((double)fsub(y, sr), g.invBlockdxSDF), bmaxy = pos2idx_d((double)fadd(y, sr), g.invBlockdxSDF);
+                    int bminz = pos2idx_d((double)fsub(z, sr), g.invBlockdxSDF), bmaxz = pos2idx_d((double)fadd(z, sr), g.invBlockdxSDF);
+                    if (f.bi < bminx || f.bi > bmaxx || f.bj < bminy || f.bj > bmaxy || f.bk < bminz || f.bk > bmaxz) continue;
+                    int gminx = pos2idx(fsub(xl, sr), invdx), gmaxx = pos2idx(fadd(xl, sr), invdx);
+                    int gminy = pos2idx(fsub(yl, sr), invdx), gmaxy = pos2idx(fadd(yl, sr), invdx);
+                    int gminz = pos2idx(fsub(zl, sr), invdx), gmaxz = pos2idx(fadd(zl, sr), invdx);
+                    if (f.li < gminx || f.li > gmaxx || f.lj < gminy || f.lj > gmaxy || f.lk < gminz || f.lk > gmaxz) continue;
                 }
+                best2 = fminf(best2, lengthsq3(fsub(f.cx, xl), fsub(f.cy, yl), fsub(f.cz, zl)));
             }
         }
-        phiL[cell] = finish_phi(g, phiS, best2, i, j, k);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) best2 = fminf(best2, __shfl_xor_sync(0xffffffffu, best2, o));
+        if (lane == 0) phiL[cell] = finish_phi(g, phiS, best2, i, j, k);
     }
 }
 
@@ -817,7 +851,7 @@ static void run_sdf_p2g(flip_ctx *c) {
     else
         k_sdf_p2g<false><<<grid, block, 0, c->stream>>>(c->P[c->cur_buf], c->cellStart, g, c->U, c->V, c->W, c->validU, c->validV,
                                                         c->validW, c->phiL, c->phiS, c->occ, farCells, farBest, farCount);
-    k_sdf_far<<<148 * 8, 128, 0, c->stream>>>(c->P[c->cur_buf], c->cellStart, g, c->phiL, c->phiS, farCells, farBest, farCount);
+    k_sdf_far<<<148 * 16, 128, 0, c->stream>>>(c->P[c->cur_buf], c->cellStart, g, c->phiL, c->phiS, farCells, farBest, farCount);
     c->launches++;
     kt_end(c, FLIP_KERNEL_SDF_P2G, kt);
     c->launches++;
