@@ -79,6 +79,7 @@ static void free_all(flip_ctx *c) {
     cudaFree(c->nearSolid); cudaFree(c->pressure);
     cudaFree(c->dS);
     cudaFree(c->sendBuf[0]); cudaFree(c->sendBuf[1]); cudaFree(c->occ);
+    peer_free(c);
     comm_destroy(c->comm); c->comm = nullptr;
     if (c->hS) cudaFreeHost(c->hS);
     if (c->eventsCreated) for (auto &e : c->evStage) cudaEventDestroy(e);
@@ -674,6 +675,7 @@ int flip_set_slab(flip_ctx *c, int rank, int nranks, const void *id, int idBytes
         free_grids(c);
         set_geometry(c, c->d.I, c->d.J, (k1 - k0) + lo + hi, c->d.dx, k0 - lo, Kg, lo, lo + (k1 - k0));
         allocate_grids(c);
+        peer_setup(c);
     });
 }
 int flip_get_nccl_unique_id(void *out, int idBytes) {

@@ -201,6 +201,7 @@ struct flip_ctx {
     flip::Comm *comm = nullptr;
     int ownedBegin = 0, ownedEnd = 0;         // owned particles inside the sorted (ghost-extended) store
     bool ghostsPresent = false;
+    void *peer = nullptr;                     // peer-memory exchange state (peer.cu); NCCL is used when it is off
     float *sendBuf[2] = {nullptr, nullptr};   // emigrant staging, 7 arrays of sendCap entries each
     int sendCap = 0;
     int np_global = 0;
@@ -252,7 +253,15 @@ enum { COMM_SUM_F64 = 0, COMM_MAX_U64 = 1, COMM_SUM_I32 = 2, COMM_MAX_U32 = 3 };
 void comm_allreduce(Comm *, void *buf, size_t count, int kind, cudaStream_t st);
 void comm_allgather_f32(Comm *, const float *send, float *recv, size_t countPerRank, cudaStream_t st);
 
+// peer.cu: halo planes and PCG scalars through CUDA-IPC peer memory (NVLink), one kernel per exchange
+void peer_setup(flip_ctx *c);                           // collective, after the communicator exists
+void peer_free(flip_ctx *c);
+bool peer_on(const flip_ctx *c);
+void peer_exchange_planes(flip_ctx *c, const void *sendLo, void *recvLo, const void *sendHi, void *recvHi, size_t bytes);
+void peer_allreduce(flip_ctx *c, void *val, int count, int kind);   // COMM_SUM_F64 / COMM_MAX_U64, count <= 8
+
 // slab.cu: halo exchanges between neighbouring slabs
+void slab_allreduce_scalar(flip_ctx *c, void *val, int kind);      // one fp64 sum / u64 max on the solver's stream
 void slab_exchange_ghosts(flip_ctx *c);                 // ghost particles within `halo` planes, then re-sort
 void slab_drop_ghosts_and_migrate(flip_ctx *c);         // after advance: emigrants out, immigrants in
 void slab_exchange_planes(flip_ctx *c, float *field, int planeElems, int facePlanes);   // halo planes of a float grid

@@ -1842,7 +1842,7 @@ void stage_pressure(flip_ctx *c, double dt) {
     const bool slab = slab_on(c);
     if (slab) {
         // the system is global: ||b||_inf and the row count over all slabs
-        comm_allreduce(c->comm, &c->dS->rhsMaxBits, 1, COMM_MAX_U64, st);
+        slab_allreduce_scalar(c, &c->dS->rhsMaxBits, COMM_MAX_U64);
         FLIP_CUDA_CHECK(cudaMemcpyAsync(&c->dS->globalRows, &c->dS->numRows, sizeof(int), cudaMemcpyDeviceToDevice, st));
         comm_allreduce(c->comm, &c->dS->globalRows, 1, COMM_SUM_I32, st);
     }
@@ -2190,7 +2190,7 @@ void stage_pressure(flip_ctx *c, double dt) {
         apply_precond(0);
         k_pcg_copy_zs<<<segBlocks, TPB, 0, st>>>(c->segCell, c->segMask, c->vz, c->vs, c->dS); c->launches++;
     }
-    if (slab) comm_allreduce(c->comm, &c->dS->rho[0], 1, COMM_SUM_F64, st);
+    if (slab) slab_allreduce_scalar(c, &c->dS->rho[0], COMM_SUM_F64);
 
     int it = 0;
     const int batch = useMg ? 4 : 16;
@@ -2205,13 +2205,13 @@ void stage_pressure(flip_ctx *c, double dt) {
             k_pcg_spmv<<<loopBlocks, TPB, 0, st>>>(c->segCell, c->segMask, pp, c->Adiag, c->AoffU, c->AoffV, c->AoffW,
                                                   c->vs, c->vz, c->dS, it);
             kt_end(c, FLIP_KERNEL_PCG_SPMV, ktSp);
-            if (slab) comm_allreduce(c->comm, &c->dS->dotSZ[it % 3], 1, COMM_SUM_F64, st);
+            if (slab) slab_allreduce_scalar(c, &c->dS->dotSZ[it % 3], COMM_SUM_F64);
             k_pcg_update<<<loopBlocks, TPB, 0, st>>>(c->segCell, c->segMask, c->Adiag, c->vs, c->vz, c->vx_, c->vr,
                                                     c->dS, it, jacobi);
             c->launches += 2;
-            if (slab) comm_allreduce(c->comm, &c->dS->rMaxBits[it % 3], 1, COMM_MAX_U64, st);
+            if (slab) slab_allreduce_scalar(c, &c->dS->rMaxBits[it % 3], COMM_MAX_U64);
             if (useMg) apply_precond((it + 1) % 3);
-            if (slab) comm_allreduce(c->comm, &c->dS->rho[(it + 1) % 3], 1, COMM_SUM_F64, st);
+            if (slab) slab_allreduce_scalar(c, &c->dS->rho[(it + 1) % 3], COMM_SUM_F64);
             k_pcg_direction<<<loopBlocks, TPB, 0, st>>>(c->segCell, c->segMask, c->vz, c->vs, c->dS, it);
             kt_end(c, FLIP_KERNEL_PCG_ITER, ktIt);
             c->launches++;

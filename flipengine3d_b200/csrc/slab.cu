@@ -223,6 +223,10 @@ void slab_exchange_cell_plane_f32(flip_ctx *c, float *v, int planeElems, int k0,
     const bool hasLo = c->rank > 0, hasHi = c->rank < c->nranks - 1;
     const size_t pe = (size_t)planeElems;
     const size_t bytes = sizeof(float) * pe;
+    if (peer_on(c)) {
+        peer_exchange_planes(c, v + pe * k0, v + pe * (k0 - 1), v + pe * (k1 - 1), v + pe * k1, bytes);
+        return;
+    }
     comm_group_begin(c->comm);
     if (hasLo) {
         comm_send(c->comm, v + pe * k0, bytes, c->rank - 1, st);
@@ -243,6 +247,10 @@ void slab_exchange_vector_halo(flip_ctx *c, double *v) {
     const bool hasLo = c->rank > 0, hasHi = c->rank < c->nranks - 1;
     const size_t pe = (size_t)d.I * d.J;
     const size_t bytes = sizeof(double) * pe;
+    if (peer_on(c)) {
+        peer_exchange_planes(c, v + pe * d.kOwn0, v + pe * (d.kOwn0 - 1), v + pe * (d.kOwn1 - 1), v + pe * d.kOwn1, bytes);
+        return;
+    }
     comm_group_begin(c->comm);
     if (hasLo) {
         comm_send(c->comm, v + pe * d.kOwn0, bytes, c->rank - 1, st);
@@ -253,6 +261,12 @@ void slab_exchange_vector_halo(flip_ctx *c, double *v) {
         comm_recv(c->comm, v + pe * d.kOwn1, bytes, c->rank + 1, st);
     }
     comm_group_end(c->comm);
+}
+
+// One scalar of the distributed PCG (dot product or residual maximum) over all slabs, in place on the device.
+void slab_allreduce_scalar(flip_ctx *c, void *val, int kind) {
+    if (peer_on(c)) peer_allreduce(c, val, 1, kind);
+    else comm_allreduce(c->comm, val, 1, kind, c->stream);
 }
 
 }  // namespace flip

@@ -13,9 +13,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_two_slabs_match_single_gpu():
+@pytest.mark.parametrize("peer", ["1", "0"])
+def test_two_slabs_match_single_gpu(peer):
+    """peer=1: PCG / multigrid halo planes and scalars through CUDA-IPC peer memory (csrc/peer.cu);
+    peer=0: the same exchanges as NCCL send/recv groups and all-reduces."""
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", "29533", os.path.join(ROOT, "scripts", "slab_check.py"), "damz64", "12"]
-    r = subprocess.run(cmd, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    r = subprocess.run(cmd, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600,
+                       env=dict(os.environ, FLIP_PEER=peer))
     assert r.returncode == 0, r.stdout[-3000:]
     assert "SLAB_CHECK OK" in r.stdout, r.stdout[-3000:]
