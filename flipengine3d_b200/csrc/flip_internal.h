@@ -143,12 +143,11 @@ struct flip_ctx {
     int npStore = 0;                          // particles in the store (owned + ghosts of neighbouring slabs)
     flip::ParticleSoA P[2];                   // ping-pong
     int cur_buf = 0;
-    int *cellOfParticle = nullptr;            // [capacity] destination cell or -1 (removed)
+    int *cellOfParticle = nullptr;            // [capacity] destination cell (+ extreme-velocity flag in bit 30) or -1 (removed)
     int *sortIdx = nullptr;                   // [capacity] particle indices grouped by cell
     int *srcIdx = nullptr;                    // [capacity] final gather map
     int *pid[2] = {nullptr, nullptr};         // optional particle ids carried through the sorts
     bool trackIds = false;
-    unsigned char *fastFlag = nullptr;        // [capacity] extreme-velocity flag
     unsigned char *occ = nullptr;             // 4x4x4-cell blocks that hold particles (rebuilt by every sort)
     size_t occBytes = 0;
     int *cellCount = nullptr;                 // [nC+1]

@@ -36,7 +36,6 @@ void particles_free(flip_ctx *c) {
     cudaFree(c->cellOfParticle); c->cellOfParticle = nullptr;
     cudaFree(c->sortIdx); c->sortIdx = nullptr;
     cudaFree(c->srcIdx); c->srcIdx = nullptr;
-    cudaFree(c->fastFlag); c->fastFlag = nullptr;
     cudaFree(c->pid[0]); cudaFree(c->pid[1]); c->pid[0] = c->pid[1] = nullptr;
     c->capacity = 0;
 }
@@ -71,7 +70,7 @@ void particles_alloc(flip_ctx *c, int capacity) {
     if (oldCap > 0) {
         soa_free(old[0]);
         soa_free(old[1]);
-        cudaFree(c->cellOfParticle); cudaFree(c->sortIdx); cudaFree(c->srcIdx); cudaFree(c->fastFlag);
+        cudaFree(c->cellOfParticle); cudaFree(c->sortIdx); cudaFree(c->srcIdx);
         cudaFree(c->pid[0]); cudaFree(c->pid[1]);
     }
     c->P[0] = nw[0];
@@ -81,7 +80,6 @@ void particles_alloc(flip_ctx *c, int capacity) {
     FLIP_CUDA_CHECK(cudaMalloc(&c->cellOfParticle, sizeof(int) * cap));
     FLIP_CUDA_CHECK(cudaMalloc(&c->sortIdx, sizeof(int) * cap));
     FLIP_CUDA_CHECK(cudaMalloc(&c->srcIdx, sizeof(int) * cap));
-    FLIP_CUDA_CHECK(cudaMalloc(&c->fastFlag, cap));
     c->capacity = cap;
 }
 
@@ -175,17 +173,25 @@ __global__ void k_speed_limit(int n, double speedLimitStep, int nbins, double ma
     for (int i = 0; i < 8; i++) S->speedHist[i] = 0;
 }
 
+// cellOf[t] = destination cell (or -1), with the extreme-velocity flag in bit 30; rankOf[t] = arrival number of
+// the particle in its cell (any order: k_cell_finalize orders the cell by previous index afterwards).  Particles
+// are cell-sorted from the previous step and move less than a cell per substep on average, so a warp holds few
+// distinct destination cells: one counter atomic per distinct cell of the warp instead of one per particle.
+static constexpr int FAST_BIT = 1 << 30;
 __global__ void k_classify(ParticleSoA p, SortParams sp, const float *__restrict__ phiS, int *__restrict__ cellOf,
-                           unsigned char *__restrict__ fast, int *__restrict__ cellCount, DeviceScalars *S) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= sp.n) return;
-    float x = p.px[t], y = p.py[t], z = p.pz[t];
+                           int *__restrict__ rankOf, int *__restrict__ cellCount, DeviceScalars *S) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = t < sp.n;
+    const int tt = live ? t : 0;
+    float x = p.px[tt], y = p.py[tt], z = p.pz[tt];
     int i = pos2idx(x, sp.invdx), j = pos2idx(y, sp.invdx), k = pos2idx(z, sp.invdx) - sp.kOff;
     int cell = -1;
     bool inRange = (i >= 0 && j >= 0 && k >= 0 && i < sp.I && j < sp.J && k < sp.K);
     bool gone = sp.ownedOnly && (k < sp.kOwn0 || k >= sp.kOwn1);   // now lives on a neighbouring slab
     unsigned char f = 0;
-    if (gone) {
+    if (!live) {
+        cell = -1;
+    } else if (gone) {
         cell = -1;
     } else if (inRange) {
         cell = i + sp.I * (j + sp.J * k);
@@ -201,7 +207,7 @@ __global__ void k_classify(ParticleSoA p, SortParams sp, const float *__restrict
                 cell = -1;
                 atomicAdd(&S->removedSolid, 1);
             } else {
-                float vx = p.vx[t], vy = p.vy[t], vz = p.vz[t];
+                float vx = p.vx[tt], vy = p.vy[tt], vz = p.vz[tt];
                 float ms = S->maxSpeedLimit;
                 double maxspeedsq = (double)fmul(ms, ms);   // float*float then widened (:4328)
                 if ((double)lengthsq3(vx, vy, vz) > maxspeedsq) f = 1;
@@ -211,26 +217,36 @@ __global__ void k_classify(ParticleSoA p, SortParams sp, const float *__restrict
         // cannot happen after _resolveCollision (positions are clamped into the boundary box); counted as solid
         atomicAdd(&S->removedSolid, 1);
     }
-    cellOf[t] = cell;
-    fast[t] = f;
-    if (cell >= 0) atomicAdd(&cellCount[cell], 1);
+    const unsigned int peers = __match_any_sync(0xffffffffu, cell);
+    int rank = 0;
+    if (cell >= 0) {
+        const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(&cellCount[cell], __popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        rank = base + __popc(peers & ((1u << lane) - 1u));
+    }
+    if (live) {
+        cellOf[t] = (cell >= 0 && f) ? (cell | FAST_BIT) : cell;
+        rankOf[t] = rank;
+    }
 }
 
-__global__ void k_scatter_idx(int n, const int *__restrict__ cellOf, const int *__restrict__ startA,
-                              int *__restrict__ cursor, int *__restrict__ sortIdx) {
+// sortIdx entry = previous index, with the extreme-velocity flag in bit 30
+__global__ void k_scatter_idx(int n, const int *__restrict__ cellOf, const int *__restrict__ rankOf,
+                              const int *__restrict__ startA, int *__restrict__ sortIdx) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
-    int cell = cellOf[t];
-    if (cell < 0) return;
-    int r = atomicAdd(&cursor[cell], 1);
-    sortIdx[startA[cell] + r] = t;
+    const int cf = cellOf[t];
+    if (cf < 0) return;
+    const int cell = cf & ~FAST_BIT;
+    sortIdx[startA[cell] + rankOf[t]] = t | (cf & FAST_BIT);
 }
 
 // One thread per cell: order the cell's candidates by previous index, apply the per-cell cap and
 // the speed rule, leave the kept ones at the front of the cell's range, publish the kept count.
 __global__ void k_cell_finalize(int nC, const int *__restrict__ startA, int *__restrict__ sortIdx,
-                                const unsigned char *__restrict__ fast, int *__restrict__ keptCount, int applyRules,
-                                int maxPerCell, DeviceScalars *S) {
+                                int *__restrict__ keptCount, int applyRules, int maxPerCell, DeviceScalars *S) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nC) return;
     int b = startA[c], e = startA[c + 1];
@@ -243,9 +259,11 @@ __global__ void k_cell_finalize(int nC, const int *__restrict__ startA, int *__r
         int v[SMALL];
         bool drop[SMALL];
 #pragma unroll
-        for (int a = 0; a < SMALL; a++) v[a] = (a < n) ? sortIdx[b + a] : 0x7fffffff;
-#pragma unroll
-        for (int a = 0; a < SMALL; a++) drop[a] = (a < n) ? (applyRules && fast[v[a]] != 0) : true;
+        for (int a = 0; a < SMALL; a++) {
+            const int w = (a < n) ? sortIdx[b + a] : 0x3fffffff;
+            v[a] = w & ~FAST_BIT;
+            drop[a] = (a < n) ? (applyRules && (w & FAST_BIT)) : true;
+        }
         int kept = 0;
 #pragma unroll
         for (int a = 0; a < SMALL; a++) {
@@ -261,27 +279,24 @@ __global__ void k_cell_finalize(int nC, const int *__restrict__ startA, int *__r
         keptCount[c] = kept;
         return;
     }
-    // insertion sort (the cap is 250)
+    // insertion sort by previous index (the cap is 250)
     for (int a = b + 1; a < e; a++) {
-        int v = sortIdx[a];
+        int w = sortIdx[a];
+        int v = w & ~FAST_BIT;
         int q = a - 1;
-        while (q >= b && sortIdx[q] > v) { sortIdx[q + 1] = sortIdx[q]; q--; }
-        sortIdx[q + 1] = v;
+        while (q >= b && (sortIdx[q] & ~FAST_BIT) > v) { sortIdx[q + 1] = sortIdx[q]; q--; }
+        sortIdx[q + 1] = w;
     }
-    int kept = n;
-    if (applyRules) {
-        kept = 0;
-        int crowded = 0, fastc = 0;
-        for (int a = b; a < e; a++) {
-            int v = sortIdx[a];
-            if (a - b >= maxPerCell) { crowded++; continue; }
-            if (fast[v]) { fastc++; continue; }
-            sortIdx[b + kept] = v;
-            kept++;
-        }
-        if (crowded) atomicAdd(&S->removedCrowded, crowded);
-        if (fastc) atomicAdd(&S->removedFast, fastc);
+    int kept = 0, crowded = 0, fastc = 0;
+    for (int a = b; a < e; a++) {
+        const int w = sortIdx[a];
+        if (applyRules && a - b >= maxPerCell) { crowded++; continue; }
+        if (applyRules && (w & FAST_BIT)) { fastc++; continue; }
+        sortIdx[b + kept] = w & ~FAST_BIT;
+        kept++;
     }
+    if (crowded) atomicAdd(&S->removedCrowded, crowded);
+    if (fastc) atomicAdd(&S->removedFast, fastc);
     keptCount[c] = kept;
 }
 
@@ -369,6 +384,7 @@ void particles_sort(flip_ctx *c, bool applyRules, double frameDt, int srcOffset,
     ParticleSoA src = soa_offset(c->P[c->cur_buf], srcOffset);
     ParticleSoA &dst = c->P[1 - c->cur_buf];
     int nC = d.nC;
+    if (nC >= FAST_BIT || n >= FAST_BIT) throw ApiError(FLIP_ERR_UNSUPPORTED, "more than 2^30 cells or particles per GPU");
     size_t ktSort = kt_begin(c);
     k_reset_sort_scalars<<<1, 1, 0, st>>>(c->dS); c->launches++;
     FLIP_CUDA_CHECK(cudaMemsetAsync(c->cellCount, 0, sizeof(int) * (nC + 1), st));
@@ -391,17 +407,18 @@ void particles_sort(flip_ctx *c, bool applyRules, double frameDt, int srcOffset,
                                        c->maxExtremeVelocityRemovalAbsolute, c->dS); c->launches++;
     }
     if (n > 0) {
-        k_classify<<<cdiv(n, TPB), TPB, 0, st>>>(src, sp, c->phiS, c->cellOfParticle, c->fastFlag, c->cellCount, c->dS);
+        // the arrival ranks live in srcIdx, which is only rebuilt (k_build_src) after the index scatter has used them
+        k_classify<<<cdiv(n, TPB), TPB, 0, st>>>(src, sp, c->phiS, c->cellOfParticle, c->srcIdx, c->cellCount, c->dS);
         c->launches++;
     }
     ensure_scan_temp(c, nC + 1);
     cub::DeviceScan::ExclusiveSum(c->scanTemp, c->scanTempBytes, c->cellCount, c->cellStartA, nC + 1, st); c->launches++;
-    FLIP_CUDA_CHECK(cudaMemsetAsync(c->cellCount, 0, sizeof(int) * (nC + 1), st));
     if (n > 0) {
-        k_scatter_idx<<<cdiv(n, TPB), TPB, 0, st>>>(n, c->cellOfParticle, c->cellStartA, c->cellCount, c->sortIdx);
+        k_scatter_idx<<<cdiv(n, TPB), TPB, 0, st>>>(n, c->cellOfParticle, c->srcIdx, c->cellStartA, c->sortIdx);
         c->launches++;
     }
-    k_cell_finalize<<<cdiv(nC, TPB), TPB, 0, st>>>(nC, c->cellStartA, c->sortIdx, c->fastFlag, c->cellCount,
+    // overwrites the candidate counts with the kept counts, cell by cell
+    k_cell_finalize<<<cdiv(nC, TPB), TPB, 0, st>>>(nC, c->cellStartA, c->sortIdx, c->cellCount,
                                                    applyRules ? 1 : 0, c->maxParticlesPerCell, c->dS);
     c->launches++;
     FLIP_CUDA_CHECK(cudaMemsetAsync(c->cellCount + nC, 0, sizeof(int), st));
@@ -526,6 +543,7 @@ struct GatherParams {
     float maxDist;        // 3dx  particlelevelset.cpp:295
     float hwS;            // cell-centre half width as added in double (GridIndexToCellCenter grid3d.h:101)
     float halfDxSolid;    // post-process thresholds
+    int packed;           // FLIP_SAMPLING_FAST: weights through the packed-f32x2 row; literal weights otherwise
 };
 
 __device__ __forceinline__ float kernel_weight(float d2, const GatherParams &g) {
@@ -645,6 +663,79 @@ __device__ __forceinline__ void gather_row(const ParticleSoA &p, const GatherPar
     }
 }
 
+// Packed single precision (sm_100a FADD2/FMUL2/FFMA2: two particles per instruction).  ptxas contracts packed
+// mul+add pairs into FFMA2 even with explicit .rn, so only quantities that tolerate it go through these.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void upk2(f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
+// Constants of one node for gather_row_pk (both halves hold the same number).
+struct PkNode {
+    f32x2 Xn, Yn, Zn, Xh, Yh, Zh;    // node coordinates and node + dx/2
+    f32x2 c1, c2, c3, one;           // Horner form of the weight: ((c1*d2 + c2)*d2 + c3)*d2 + 1
+};
+
+// The same row for power-of-two dx, two particles per instruction.  The kernel is bound by instruction issue
+// (ncu: issue slots 80 %, DRAM 6 %); here the coordinate differences, the three squared face distances and the
+// three weight polynomials of a particle PAIR are 23 packed instructions.  What must match the reference bit for
+// bit stays scalar and literal: the squared distance to the cell centre (SDF minimum).  The packed face distances
+// and the Horner weights differ from the literal ones by a few ulp: the support test can only differ where the
+// weight is ~1e-7, the weights by <1e-6, i.e. float summation noise for the face value (tolerance 1e-5) -- except
+// for the `valid = sum(w) > 1e-6` decision of a face whose total weight is that small, and the caller recomputes
+// those faces with gather_row.  Velocities are loaded under the support predicate.
+template <bool DOV, bool DOW>
+__device__ __forceinline__ void gather_row_pk(const ParticleSoA &p, const GatherParams &g, const PkNode &N, int qb, int qe,
+                                              float Xh, float Yh, float Zh, float &su, float &wu, float &sv, float &wv,
+                                              float &sw, float &ww, float &best2) {
+    const float rsq = g.rsq;
+    for (int q4 = qb & ~3; q4 < qe; q4 += 4) {
+        const float4 X4 = __ldg(reinterpret_cast<const float4 *>(p.px + q4));
+        const float4 Y4 = __ldg(reinterpret_cast<const float4 *>(p.py + q4));
+        const float4 Z4 = __ldg(reinterpret_cast<const float4 *>(p.pz + q4));
+        // a particle outside [qb,qe) is moved far away: no support hit, no effect on the minimum
+        const unsigned lo = (unsigned)max(qb - q4, 0), span = (unsigned)min(qe - q4, 4) - lo;
+        const float xs[4] = {(0u - lo) < span ? X4.x : 1.0e18f, (1u - lo) < span ? X4.y : 1.0e18f,
+                             (2u - lo) < span ? X4.z : 1.0e18f, (3u - lo) < span ? X4.w : 1.0e18f};
+        const float ys[4] = {Y4.x, Y4.y, Y4.z, Y4.w}, zs[4] = {Z4.x, Z4.y, Z4.z, Z4.w};
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const f32x2 x = pk2(xs[2 * h], xs[2 * h + 1]), y = pk2(ys[2 * h], ys[2 * h + 1]), z = pk2(zs[2 * h], zs[2 * h + 1]);
+            const f32x2 ax = sub2(N.Xn, x), bx = sub2(N.Xh, x), by = sub2(N.Yh, y), bz = sub2(N.Zh, z);
+            const f32x2 bz2 = mul2(bz, bz);
+            const f32x2 d2u = fma2(ax, ax, fma2(by, by, bz2));
+            const f32x2 wU = fma2(fma2(fma2(N.c1, d2u, N.c2), d2u, N.c3), d2u, N.one);
+            f32x2 d2v = 0, wV = 0, d2w = 0, wW = 0;
+            if (DOV) {
+                const f32x2 ay = sub2(N.Yn, y);
+                d2v = fma2(bx, bx, fma2(ay, ay, bz2));
+                wV = fma2(fma2(fma2(N.c1, d2v, N.c2), d2v, N.c3), d2v, N.one);
+            }
+            if (DOW) {
+                const f32x2 az = sub2(N.Zn, z);
+                d2w = fma2(bx, bx, fma2(by, by, mul2(az, az)));
+                wW = fma2(fma2(fma2(N.c1, d2w, N.c2), d2w, N.c3), d2w, N.one);
+            }
+            float du[2], wu2[2], dv[2], wv2[2], dw[2], ww2[2];
+            upk2(d2u, du[0], du[1]); upk2(wU, wu2[0], wu2[1]);
+            upk2(d2v, dv[0], dv[1]); upk2(wV, wv2[0], wv2[1]);
+            upk2(d2w, dw[0], dw[1]); upk2(wW, ww2[0], ww2[1]);
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const int m = 2 * h + e, q = q4 + m;
+                if (du[e] < rsq) { const float w = fmaxf(wu2[e], 1.0e-20f); su = fmaf(w, __ldg(p.vx + q), su); wu += w; }
+                if (DOV) { if (dv[e] < rsq) { const float w = fmaxf(wv2[e], 1.0e-20f); sv = fmaf(w, __ldg(p.vy + q), sv); wv += w; } }
+                if (DOW) { if (dw[e] < rsq) { const float w = fmaxf(ww2[e], 1.0e-20f); sw = fmaf(w, __ldg(p.vz + q), sw); ww += w; } }
+                // SDF: literal (x*x + y*y) + z*z of the exact differences
+                const float ex = fsub(Xh, xs[m]), ey = fsub(Yh, ys[m]), ez = fsub(Zh, zs[m]);
+                best2 = fminf(best2, fadd(fadd(fmul(ex, ex), fmul(ey, ey)), fmul(ez, ez)));
+            }
+        }
+    }
+}
+
 template <bool DYADIC>
 __global__ void __launch_bounds__(128) k_sdf_p2g(ParticleSoA p, const int *__restrict__ cellStart, GatherParams g,
                                                  float *__restrict__ U, float *__restrict__ V, float *__restrict__ W,
@@ -695,6 +786,9 @@ __global__ void __launch_bounds__(128) k_sdf_p2g(ParticleSoA p, const int *__res
     const float Xn = (float)dmul((double)(float)i, g.dx), Yn = (float)dmul((double)(float)j, g.dx),
                 Zn = (float)dmul((double)(float)kg, g.dx);
     const float Xh = fadd(Xn, g.hw), Yh = fadd(Yn, g.hw), Zh = fadd(Zn, g.hw);
+    PkNode N;
+    N.Xn = pk2(Xn, Xn); N.Yn = pk2(Yn, Yn); N.Zn = pk2(Zn, Zn); N.Xh = pk2(Xh, Xh); N.Yh = pk2(Yh, Yh); N.Zh = pk2(Zh, Zh);
+    N.c1 = pk2(-g.coef1, -g.coef1); N.c2 = pk2(g.coef2, g.coef2); N.c3 = pk2(-g.coef3, -g.coef3); N.one = pk2(1.0f, 1.0f);
     for (int ck = klo; ck <= khi; ck++) {
         for (int cj = jlo; cj <= jhi; cj++) {
             int rowBase = I * (cj + J * ck);
@@ -702,10 +796,39 @@ __global__ void __launch_bounds__(128) k_sdf_p2g(ParticleSoA p, const int *__res
             const int qe = __ldg(cellStart + rowBase + ihi + 1);
             if (qb == qe) continue;
             const bool doV = (cj <= j), doW = (ck <= k);     // uniform over the block
+            if (DYADIC && g.packed) {
+                if (doV && doW) gather_row_pk<true, true>(p, g, N, qb, qe, Xh, Yh, Zh, su, wu, sv, wv, sw, ww, best2);
+                else if (doV) gather_row_pk<true, false>(p, g, N, qb, qe, Xh, Yh, Zh, su, wu, sv, wv, sw, ww, best2);
+                else if (doW) gather_row_pk<false, true>(p, g, N, qb, qe, Xh, Yh, Zh, su, wu, sv, wv, sw, ww, best2);
+                else gather_row_pk<false, false>(p, g, N, qb, qe, Xh, Yh, Zh, su, wu, sv, wv, sw, ww, best2);
+                continue;
+            }
             if (doV && doW) gather_row<DYADIC, true, true>(p, g, f, qb, qe, Xn, Yn, Zn, Xh, Yh, Zh, su, wu, sv, wv, sw, ww, best2);
             else if (doV) gather_row<DYADIC, true, false>(p, g, f, qb, qe, Xn, Yn, Zn, Xh, Yh, Zh, su, wu, sv, wv, sw, ww, best2);
             else if (doW) gather_row<DYADIC, false, true>(p, g, f, qb, qe, Xn, Yn, Zn, Xh, Yh, Zh, su, wu, sv, wv, sw, ww, best2);
             else gather_row<DYADIC, false, false>(p, g, f, qb, qe, Xn, Yn, Zn, Xh, Yh, Zh, su, wu, sv, wv, sw, ww, best2);
+        }
+    }
+
+    if (DYADIC && g.packed) {
+        // faces whose total weight is within the rounding band of the validity threshold (there were hits, yet the
+        // sum is tiny): redo with the literal weights so that the valid mask is the reference's.  Practically never.
+        const float band = 6.0e-5f;
+        if ((wu > 0.0f && wu < band) || (wv > 0.0f && wv < band) || (ww > 0.0f && ww < band)) {
+            su = wu = sv = wv = sw = ww = 0.0f;
+            float b2 = 3.0e38f;
+            for (int ck = klo; ck <= khi; ck++) {
+                for (int cj = jlo; cj <= jhi; cj++) {
+                    int rowBase = I * (cj + J * ck);
+                    const int qb = __ldg(cellStart + rowBase + ilo);
+                    const int qe = __ldg(cellStart + rowBase + ihi + 1);
+                    if (qb == qe) continue;
+                    if (cj <= j && ck <= k) gather_row<true, true, true>(p, g, f, qb, qe, Xn, Yn, Zn, Xh, Yh, Zh, su, wu, sv, wv, sw, ww, b2);
+                    else if (cj <= j) gather_row<true, true, false>(p, g, f, qb, qe, Xn, Yn, Zn, Xh, Yh, Zh, su, wu, sv, wv, sw, ww, b2);
+                    else if (ck <= k) gather_row<true, false, true>(p, g, f, qb, qe, Xn, Yn, Zn, Xh, Yh, Zh, su, wu, sv, wv, sw, ww, b2);
+                    else gather_row<true, false, false>(p, g, f, qb, qe, Xn, Yn, Zn, Xh, Yh, Zh, su, wu, sv, wv, sw, ww, b2);
+                }
+            }
         }
     }
 
@@ -750,59 +873,59 @@ __global__ void __launch_bounds__(128) k_sdf_p2g(ParticleSoA p, const int *__res
 __global__ void k_sdf_far(ParticleSoA p, const int *__restrict__ cellStart, GatherParams g, float *__restrict__ phiL,
                           const float *__restrict__ phiS, const int *__restrict__ farCells,
                           const float *__restrict__ farBest, const int *__restrict__ farCount) {
-    // one WARP per queued cell: lane r < 25 scans row r of the 5x5 rows of the search box, then a warp minimum
     const int I = g.I, J = g.J, K = g.K;
     const int n = *farCount;
-    const int lane = threadIdx.x & 31;
-    const int nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < n; t += nwarps) {
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
         const int cell = farCells[t];
         float best2 = farBest[t];
         const int i = cell % I, j = (cell / I) % J, k = cell / (I * J);
-        const int cj = j + (lane % 5) - 2, ck = k + (lane / 5) - 2;
-        if (lane < 25 && cj >= 0 && cj < J && ck >= 0 && ck < K) {
-            const NodeFrame f = node_frame(g, i, j, k + g.kOff);
-            const float sr = g.srS;
-            const double invdx = g.invdx;
-            const float dxf = (float)g.dx, margin = 1.0e-3f * dxf;
-            const float Xn = (float)dmul((double)(float)i, g.dx), Yn = (float)dmul((double)(float)j, g.dx),
-                        Zn = (float)dmul((double)(float)(k + g.kOff), g.dx);
-            const float loIn = -sr + margin, hiIn = dxf + sr - margin, loOut = -sr - margin, hiOut = dxf + sr + margin;
-            const int ilo = max(i - 1, 0), ihi = min(i + 1, I - 1);
-            const int i2lo = max(i - 2, 0), i2hi = min(i + 2, I - 1);
-            const bool innerRow = (ck >= k - 1 && ck <= k + 1 && cj >= j - 1 && cj <= j + 1);
-            const int rowBase = I * (cj + J * ck);
-            const int qb = __ldg(cellStart + rowBase + i2lo);
-            const int qe = __ldg(cellStart + rowBase + i2hi + 1);
-            int sb = 0, se = 0;   // range already visited by k_sdf_p2g (skip)
-            if (innerRow) { sb = __ldg(cellStart + rowBase + ilo); se = __ldg(cellStart + rowBase + ihi + 1); }
-            for (int q = qb; q < qe; q++) {
-                if (innerRow && q >= sb && q < se) { q = se - 1; continue; }
-                float x = __ldg(p.px + q), y = __ldg(p.py + q), z = __ldg(p.pz + q);
-                // position relative to the cell's lower corner: inside the search box iff -sr <= u < dx + sr
-                float ux = fsub(x, Xn), uy = fsub(y, Yn), uz = fsub(z, Zn);
-                bool out = ux < loOut || ux >= hiOut || uy < loOut || uy >= hiOut || uz < loOut || uz >= hiOut;
-                if (out) continue;
-                bool in = ux >= loIn && ux < hiIn && uy >= loIn && uy < hiIn && uz >= loIn && uz < hiIn;
-                float xl = fsub(x, f.ox), yl = fsub(y, f.oy), zl = fsub(z, f.oz);
-                if (!in) {
-                    // borderline: the literal test.  Block membership of the particle: the blocks overlapped by
-                    // [p-sr, p+sr] in global coordinates; then the block-local search box.
-                    int bminx = pos2idx_d((double)fsub(x, sr), g.invBlockdxSDF), bmaxx = pos2idx_d((double)fadd(x, sr), g.invBlockdxSDF);
-                    int bminy = pos2idx_d((double)fsub(y, sr), g.invBlockdxSDF), bmaxy = pos2idx_d((double)fadd(y, sr), g.invBlockdxSDF);
-                    int bminz = pos2idx_d((double)fsub(z, sr), g.invBlockdxSDF), bmaxz = pos2idx_d((double)fadd(z, sr), g.invBlockdxSDF);
-                    if (f.bi < bminx || f.bi > bmaxx || f.bj < bminy || f.bj > bmaxy || f.bk < bminz || f.bk > bmaxz) continue;
-                    int gminx = pos2idx(fsub(xl, sr), invdx), gmaxx = pos2idx(fadd(xl, sr), invdx);
-                    int gminy = pos2idx(fsub(yl, sr), invdx), gmaxy = pos2idx(fadd(yl, sr), invdx);
-                    int gminz = pos2idx(fsub(zl, sr), invdx), gmaxz = pos2idx(fadd(zl, sr), invdx);
-                    if (f.li < gminx || f.li > gmaxx || f.lj < gminy || f.lj > gmaxy || f.lk < gminz || f.lk > gmaxz) continue;
+        const NodeFrame f = node_frame(g, i, j, k + g.kOff);
+        const float sr = g.srS;
+        const double invdx = g.invdx;
+        const float dxf = (float)g.dx, margin = 1.0e-3f * dxf;
+        const float Xn = (float)dmul((double)(float)i, g.dx), Yn = (float)dmul((double)(float)j, g.dx),
+                    Zn = (float)dmul((double)(float)(k + g.kOff), g.dx);
+        const float loIn = -sr + margin, hiIn = dxf + sr - margin, loOut = -sr - margin, hiOut = dxf + sr + margin;
+        const int jlo = max(j - 1, 0), jhi = min(j + 1, J - 1), klo = max(k - 1, 0), khi = min(k + 1, K - 1);
+        const int ilo = max(i - 1, 0), ihi = min(i + 1, I - 1);
+        const int j2lo = max(j - 2, 0), j2hi = min(j + 2, J - 1);
+        const int k2lo = max(k - 2, 0), k2hi = min(k + 2, K - 1);
+        const int i2lo = max(i - 2, 0), i2hi = min(i + 2, I - 1);
+        for (int ck = k2lo; ck <= k2hi; ck++) {
+            for (int cj = j2lo; cj <= j2hi; cj++) {
+                bool innerRow = (ck >= klo && ck <= khi && cj >= jlo && cj <= jhi);
+                int rowBase = I * (cj + J * ck);
+                int qb = __ldg(cellStart + rowBase + i2lo);
+                int qe = __ldg(cellStart + rowBase + i2hi + 1);
+                if (qb == qe) continue;
+                int sb = 0, se = 0;   // range already visited by k_sdf_p2g (skip)
+                if (innerRow) { sb = __ldg(cellStart + rowBase + ilo); se = __ldg(cellStart + rowBase + ihi + 1); }
+                for (int q = qb; q < qe; q++) {
+                    if (innerRow && q >= sb && q < se) { q = se - 1; continue; }
+                    float x = __ldg(p.px + q), y = __ldg(p.py + q), z = __ldg(p.pz + q);
+                    // position relative to the cell's lower corner: inside the search box iff -sr <= u < dx + sr
+                    float ux = fsub(x, Xn), uy = fsub(y, Yn), uz = fsub(z, Zn);
+                    bool out = ux < loOut || ux >= hiOut || uy < loOut || uy >= hiOut || uz < loOut || uz >= hiOut;
+                    if (out) continue;
+                    bool in = ux >= loIn && ux < hiIn && uy >= loIn && uy < hiIn && uz >= loIn && uz < hiIn;
+                    float xl = fsub(x, f.ox), yl = fsub(y, f.oy), zl = fsub(z, f.oz);
+                    if (!in) {
+                        // borderline: the literal test.  Block membership of the particle: the blocks overlapped by
+                        // [p-sr, p+sr] in global coordinates; then the block-local search box.
+                        int bminx = pos2idx_d((double)fsub(x, sr), g.invBlockdxSDF), bmaxx = pos2idx_d((double)fadd(x, sr), g.invBlockdxSDF);
+                        int bminy = pos2idx_d((double)fsub(y, sr), g.invBlockdxSDF), bmaxy = pos2idx_d((double)fadd(y, sr), g.invBlockdxSDF);
+                        int bminz = pos2idx_d((double)fsub(z, sr), g.invBlockdxSDF), bmaxz = pos2idx_d((double)fadd(z, sr), g.invBlockdxSDF);
+                        if (f.bi < bminx || f.bi > bmaxx || f.bj < bminy || f.bj > bmaxy || f.bk < bminz || f.bk > bmaxz) continue;
+                        int gminx = pos2idx(fsub(xl, sr), invdx), gmaxx = pos2idx(fadd(xl, sr), invdx);
+                        int gminy = pos2idx(fsub(yl, sr), invdx), gmaxy = pos2idx(fadd(yl, sr), invdx);
+                        int gminz = pos2idx(fsub(zl, sr), invdx), gmaxz = pos2idx(fadd(zl, sr), invdx);
+                        if (f.li < gminx || f.li > gmaxx || f.lj < gminy || f.lj > gmaxy || f.lk < gminz || f.lk > gmaxz) continue;
+                    }
+                    best2 = fminf(best2, lengthsq3(fsub(f.cx, xl), fsub(f.cy, yl), fsub(f.cz, zl)));
                 }
-                best2 = fminf(best2, lengthsq3(fsub(f.cx, xl), fsub(f.cy, yl), fsub(f.cz, zl)));
             }
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) best2 = fminf(best2, __shfl_xor_sync(0xffffffffu, best2, o));
-        if (lane == 0) phiL[cell] = finish_phi(g, phiS, best2, i, j, k);
+        phiL[cell] = finish_phi(g, phiS, best2, i, j, k);
     }
 }
 
@@ -827,6 +950,7 @@ static GatherParams make_gather_params(const flip_ctx *c) {
     g.maxDist = (float)(3.0 * d.dx);
     g.hwS = (float)(0.5 * d.dx);
     g.halfDxSolid = 0;
+    g.packed = c->samplingMode == FLIP_SAMPLING_FAST ? 1 : 0;
     return g;
 }
 
@@ -851,7 +975,7 @@ static void run_sdf_p2g(flip_ctx *c) {
     else
         k_sdf_p2g<false><<<grid, block, 0, c->stream>>>(c->P[c->cur_buf], c->cellStart, g, c->U, c->V, c->W, c->validU, c->validV,
                                                         c->validW, c->phiL, c->phiS, c->occ, farCells, farBest, farCount);
-    k_sdf_far<<<148 * 16, 128, 0, c->stream>>>(c->P[c->cur_buf], c->cellStart, g, c->phiL, c->phiS, farCells, farBest, farCount);
+    k_sdf_far<<<148 * 8, 128, 0, c->stream>>>(c->P[c->cur_buf], c->cellStart, g, c->phiL, c->phiS, farCells, farBest, farCount);
     c->launches++;
     kt_end(c, FLIP_KERNEL_SDF_P2G, kt);
     c->launches++;

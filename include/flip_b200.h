@@ -127,7 +127,12 @@ int flip_set_solver_mode(flip_ctx *ctx, int persistent);
  * identical inputs.  FLIP_SAMPLING_FAST (default) keeps the cell indices and interpolation weights exact
  * (they are exact in float when dx is a power of two) and evaluates only the 8-point blend in float: results
  * agree to a few ulp (rel-L2 ~1e-7, inside the 1e-4 contract) at a fraction of the instruction count.  Falls
- * back to EXACT per sample outside the interior of the grid and entirely when dx is not a power of two. */
+ * back to EXACT per sample outside the interior of the grid and entirely when dx is not a power of two.
+ * The same switch selects the P2G splat weights (VelocityAdvector, velocityadvector.cpp:437): EXACT evaluates
+ * the weight polynomial literally (left to right, scalar), so face values differ from the reference by float
+ * summation order only; FAST evaluates it in Horner form with packed FP32 pairs (weights agree to < 1e-6, face
+ * values to rel-L2 ~1e-7; faces whose total weight is near the 1e-6 validity threshold are recomputed
+ * literally, so the valid masks stay exact).  The liquid SDF is bit-exact in both modes. */
 enum { FLIP_SAMPLING_EXACT = 0, FLIP_SAMPLING_FAST = 1 };
 int flip_set_sampling_mode(flip_ctx *ctx, int mode);
 

@@ -78,10 +78,13 @@ def lockstep_substep(ref, gpu, dt, isolate=True, report=None):
             gpu.set_array(name, ref.array(name))
 
     def cmp_fields(tag, names=("U", "V", "W")):
+        scale = 0.0
         for name in names:
             a, b = gpu.array(name), ref.array(name)
             rep[f"{tag}.{name}.rel_l2"] = rel_l2(a, b)
             rep[f"{tag}.{name}.max_abs"] = max_abs(a, b)
+            scale = max(scale, float(np.max(np.abs(b))) if b.size else 0.0)
+        rep[f"{tag}.scale"] = scale     # largest |component| of the reference's MAC field at this stage
 
     def cmp_valid(tag):
         for name in ("validU", "validV", "validW"):
@@ -230,6 +233,14 @@ TOL_POS_MAX_ABS_DX = 1e-3  # particle positions: max-abs <= 1e-3 dx
 # sampled velocities per sample instead of bit-identity
 TOL_FAST_VEL_REL_L2 = 5e-6
 TOL_FAST_POS_REL_L2 = 1e-6
+# A component that is itself rounding noise (e.g. U and W of a column that only falls: |U| ~ 1e-7 next to
+# |V| ~ 1) has no meaningful relative error: it passes if its max-abs error is below the float-storage floor of
+# the velocities, 1e-5 * max|u| (SURVEY §8d parity report).
+TOL_FIELD_FLOOR = 1e-5
+
+
+def field_ok(rep, tag, comp, tol):
+    return rep[f"{tag}.{comp}.rel_l2"] <= tol or rep[f"{tag}.{comp}.max_abs"] <= TOL_FIELD_FLOOR * rep.get(f"{tag}.scale", 0.0)
 
 
 def check_report(rep, dx=0.125, isolate=True, exact_sampling=False):
@@ -261,8 +272,8 @@ def check_report(rep, dx=0.125, isolate=True, exact_sampling=False):
     # float fields
     for comp in "UVW":
         assert rep[f"p2g.{comp}.rel_l2"] <= TOL_P2G_REL_L2, rep
-        assert rep[f"pressure.{comp}.rel_l2"] <= TOL_REL_L2, rep
-        assert rep[f"extrapolate_b.{comp}.rel_l2"] <= TOL_REL_L2, rep
+        assert field_ok(rep, "pressure", comp, TOL_REL_L2), rep
+        assert field_ok(rep, "extrapolate_b", comp, TOL_REL_L2), rep
     assert rep["g2p.vel.rel_l2"] <= TOL_REL_L2, rep
     if "advance.pos.rel_l2" in rep:
         assert rep["advance.pos.rel_l2"] <= TOL_REL_L2, rep
