@@ -891,13 +891,27 @@ __global__ void k_sdf_far(ParticleSoA p, const int *__restrict__ cellStart, Gath
         const int j2lo = max(j - 2, 0), j2hi = min(j + 2, J - 1);
         const int k2lo = max(k - 2, 0), k2hi = min(k + 2, K - 1);
         const int i2lo = max(i - 2, 0), i2hi = min(i + 2, I - 1);
-        for (int ck = k2lo; ck <= k2hi; ck++) {
-            for (int cj = j2lo; cj <= j2hi; cj++) {
+        // which of the 5x5 rows hold particles at all: fifty independent loads in flight instead of one dependent
+        // pair per loop trip (this kernel is pure latency: most rows around a shell cell are empty)
+        unsigned int rows = 0u;
+#pragma unroll
+        for (int r = 0; r < 25; r++) {
+            const int cj = j + (r % 5) - 2, ck = k + (r / 5) - 2;
+            if (cj >= 0 && cj < J && ck >= 0 && ck < K) {
+                const int rowBase = I * (cj + J * ck);
+                if (__ldg(cellStart + rowBase + i2lo) != __ldg(cellStart + rowBase + i2hi + 1)) rows |= 1u << r;
+            }
+        }
+        (void)j2lo; (void)j2hi; (void)k2lo; (void)k2hi;
+        while (rows) {
+            {
+                const int r = __ffs(rows) - 1;
+                rows &= rows - 1u;
+                const int cj = j + (r % 5) - 2, ck = k + (r / 5) - 2;
                 bool innerRow = (ck >= klo && ck <= khi && cj >= jlo && cj <= jhi);
                 int rowBase = I * (cj + J * ck);
                 int qb = __ldg(cellStart + rowBase + i2lo);
                 int qe = __ldg(cellStart + rowBase + i2hi + 1);
-                if (qb == qe) continue;
                 int sb = 0, se = 0;   // range already visited by k_sdf_p2g (skip)
                 if (innerRow) { sb = __ldg(cellStart + rowBase + ilo); se = __ldg(cellStart + rowBase + ihi + 1); }
                 for (int q = qb; q < qe; q++) {

@@ -53,6 +53,33 @@ static SoAPtrs ptrs_of(flip_ctx *c, int buf) {
     return q;
 }
 
+// The cell index of the ghost-extended store, without sorting anything: cells are ordered plane by plane (k is
+// the slowest index), the neighbours' boundary layers arrive cell-sorted and lie entirely below / above the owned
+// planes, so the merged order is [ghosts from below][owned][ghosts from above] and the new cellStart is the
+// neighbours' slices and my own, rebased.  Also rebuilds the 4x4x4 occupancy blocks of the gather.
+__global__ void k_slab_merge_cellstart(int nC, int IJ, int kOwn0, int kOwn1, const int *__restrict__ oldStart,
+                                       const int *__restrict__ csLo, const int *__restrict__ csHi, int recvLo, int nOwned,
+                                       int total, int *__restrict__ newStart) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > nC) return;
+    const int lo0 = kOwn0 * IJ, hi0 = kOwn1 * IJ;
+    int v;
+    if (c == nC) v = total;
+    else if (c < lo0) v = csLo ? csLo[c] - csLo[0] : 0;
+    else if (c < hi0) v = recvLo + (oldStart[c] - oldStart[lo0]);
+    else v = recvLo + nOwned + (csHi ? csHi[c - hi0] - csHi[0] : 0);
+    newStart[c] = v;
+}
+__global__ void k_slab_mark_occ(int nC, const int *__restrict__ start, unsigned char *__restrict__ occ, int I, int J, int oI,
+                                int oJ) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nC) return;
+    if (start[c + 1] > start[c]) {
+        int i = c % I, j = (c / I) % J, k = c / (I * J);
+        occ[(i >> 2) + oI * ((j >> 2) + oJ * (k >> 2))] = 1;
+    }
+}
+
 void slab_exchange_ghosts(flip_ctx *c) {
     const Dims &d = c->d;
     cudaStream_t st = c->stream;
@@ -66,43 +93,64 @@ void slab_exchange_ghosts(flip_ctx *c) {
     const int recvLo = c->hS->recvCount[0], recvHi = c->hS->recvCount[1];
     const int n = c->np;
     const int total = n + recvLo + recvHi;
+    if (c->ownedBegin != 0) throw CudaError("z-slab ghost exchange expects the owned particles at the head of the store");
     c->npStore = n;
     particles_alloc(c, total);
-    SoAPtrs P = ptrs_of(c, c->cur_buf);
+    SoAPtrs S = ptrs_of(c, c->cur_buf), D = ptrs_of(c, 1 - c->cur_buf);
+    // the neighbours' cell-start slices of the exchanged planes land in the (idle) count array
+    const size_t sliceInts = (size_t)c->halo * IJ + 1;
+    int *csLo = hasLo ? c->cellCount : nullptr;
+    int *csHi = hasHi ? c->cellCount + (hasLo ? sliceInts : 0) : nullptr;
+    for (int a = 0; a < 6; a++)
+        FLIP_CUDA_CHECK(cudaMemcpyAsync(D.a[a] + recvLo, S.a[a], sizeof(float) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+    if (c->trackIds) FLIP_CUDA_CHECK(cudaMemcpyAsync(D.id + recvLo, S.id, sizeof(int) * (size_t)n, cudaMemcpyDeviceToDevice, st));
     comm_group_begin(c->comm);
     for (int a = 0; a < 6; a++) {
         if (hasLo) {
-            comm_send(c->comm, P.a[a], sizeof(float) * (size_t)sendLo, c->rank - 1, st);
-            comm_recv(c->comm, P.a[a] + n, sizeof(float) * (size_t)recvLo, c->rank - 1, st);
+            comm_send(c->comm, S.a[a], sizeof(float) * (size_t)sendLo, c->rank - 1, st);
+            comm_recv(c->comm, D.a[a], sizeof(float) * (size_t)recvLo, c->rank - 1, st);
         }
         if (hasHi) {
-            comm_send(c->comm, P.a[a] + (n - sendHi), sizeof(float) * (size_t)sendHi, c->rank + 1, st);
-            comm_recv(c->comm, P.a[a] + n + recvLo, sizeof(float) * (size_t)recvHi, c->rank + 1, st);
+            comm_send(c->comm, S.a[a] + (n - sendHi), sizeof(float) * (size_t)sendHi, c->rank + 1, st);
+            comm_recv(c->comm, D.a[a] + recvLo + n, sizeof(float) * (size_t)recvHi, c->rank + 1, st);
         }
     }
     if (c->trackIds) {
         if (hasLo) {
-            comm_send(c->comm, P.id, sizeof(int) * (size_t)sendLo, c->rank - 1, st);
-            comm_recv(c->comm, P.id + n, sizeof(int) * (size_t)recvLo, c->rank - 1, st);
+            comm_send(c->comm, S.id, sizeof(int) * (size_t)sendLo, c->rank - 1, st);
+            comm_recv(c->comm, D.id, sizeof(int) * (size_t)recvLo, c->rank - 1, st);
         }
         if (hasHi) {
-            comm_send(c->comm, P.id + (n - sendHi), sizeof(int) * (size_t)sendHi, c->rank + 1, st);
-            comm_recv(c->comm, P.id + n + recvLo, sizeof(int) * (size_t)recvHi, c->rank + 1, st);
+            comm_send(c->comm, S.id + (n - sendHi), sizeof(int) * (size_t)sendHi, c->rank + 1, st);
+            comm_recv(c->comm, D.id + recvLo + n, sizeof(int) * (size_t)recvHi, c->rank + 1, st);
         }
     }
+    if (hasLo) {
+        comm_send(c->comm, c->cellStart + (size_t)d.kOwn0 * IJ, sizeof(int) * sliceInts, c->rank - 1, st);
+        comm_recv(c->comm, csLo, sizeof(int) * sliceInts, c->rank - 1, st);
+    }
+    if (hasHi) {
+        comm_send(c->comm, c->cellStart + (size_t)(d.kOwn1 - c->halo) * IJ, sizeof(int) * sliceInts, c->rank + 1, st);
+        comm_recv(c->comm, csHi, sizeof(int) * sliceInts, c->rank + 1, st);
+    }
     comm_group_end(c->comm);
-    // sort owned + ghosts over the extended local grid
-    particles_sort(c, false, 0.0, 0, total, false);
-    int range[2] = {0, 0};
-    FLIP_CUDA_CHECK(cudaMemcpyAsync(&range[0], c->cellStart + (size_t)d.kOwn0 * IJ, sizeof(int), cudaMemcpyDeviceToHost, st));
-    FLIP_CUDA_CHECK(cudaMemcpyAsync(&range[1], c->cellStart + (size_t)d.kOwn1 * IJ, sizeof(int), cudaMemcpyDeviceToHost, st));
-    FLIP_CUDA_CHECK(cudaStreamSynchronize(st));
-    c->npStore = c->np;              // everything the sort kept (owned + ghosts)
-    c->ownedBegin = range[0];
-    c->ownedEnd = range[1];
-    c->np = range[1] - range[0];
+    k_slab_merge_cellstart<<<cdiv(d.nC + 1, TPB), TPB, 0, st>>>(d.nC, IJ, d.kOwn0, d.kOwn1, c->cellStart, csLo, csHi, recvLo, n,
+                                                               total, c->cellStartA);
+    c->launches++;
+    std::swap(c->cellStart, c->cellStartA);
+    {
+        const int oI = (d.I + 3) >> 2, oJ = (d.J + 3) >> 2, oK = (d.K + 3) >> 2;
+        FLIP_CUDA_CHECK(cudaMemsetAsync(c->occ, 0, (size_t)oI * oJ * oK, st));
+        k_slab_mark_occ<<<cdiv(d.nC, TPB), TPB, 0, st>>>(d.nC, c->cellStart, c->occ, d.I, d.J, oI, oJ);
+        c->launches++;
+    }
+    c->cur_buf = 1 - c->cur_buf;
+    c->npStore = total;              // owned + ghosts
+    c->ownedBegin = recvLo;
+    c->ownedEnd = recvLo + n;
+    c->np = n;
     c->ghostsPresent = true;
-    if (c->np != n) throw CudaError("z-slab ghost exchange lost owned particles (halo wider than a neighbouring slab?)");
+    FLIP_CUDA_CHECK(cudaGetLastError());
 }
 
 // Owned particles whose new plane belongs to a neighbour are appended (unordered) to the send buffers.
