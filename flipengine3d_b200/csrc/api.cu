@@ -512,6 +512,12 @@ int flip_update(flip_ctx *c, double dt) {
 }
 
 int flip_get_current_frame(const flip_ctx *c, int *f) { if (!c || !f) return FLIP_ERR_RUNTIME; *f = c->currentFrame; return FLIP_OK; }
+int flip_set_current_frame(flip_ctx *c, int f) {
+    return guarded(c, [&] {
+        if (f < 0) throw ApiError(FLIP_ERR_DOMAIN, "frame number must be >= 0");
+        c->currentFrame = f;
+    });
+}
 int flip_get_num_substeps(const flip_ctx *c, int *n) { if (!c || !n) return FLIP_ERR_RUNTIME; *n = (int)c->stats.size(); return FLIP_OK; }
 int flip_get_step_stats(const flip_ctx *c, int s, flip_step_stats *out) {
     if (!c || !out) return FLIP_ERR_RUNTIME;

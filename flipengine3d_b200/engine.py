@@ -83,6 +83,7 @@ def load_library():
     L.flip_initialize.argtypes = [vp]
     L.flip_update.argtypes = [vp, cd]
     L.flip_get_current_frame.argtypes = [vp, C.POINTER(ci)]
+    L.flip_set_current_frame.argtypes = [vp, ci]
     L.flip_get_num_substeps.argtypes = [vp, C.POINTER(ci)]
     L.flip_get_step_stats.argtypes = [vp, ci, C.POINTER(StepStats)]
     L.flip_get_num_particles.argtypes = [vp, C.POINTER(ci)]
@@ -276,6 +277,9 @@ class FluidSimulation:
         v = C.c_int()
         self._check(self.L.flip_get_current_frame(self.h, C.byref(v)))
         return v.value
+
+    def setCurrentFrame(self, frameno):
+        self._check(self.L.flip_set_current_frame(self.h, int(frameno)))
 
     def getNumMarkerParticles(self):
         v = C.c_int()

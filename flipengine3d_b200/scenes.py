@@ -78,8 +78,9 @@ def default_scene(n=30, seed=12344):
     return dict(name=f"default{n}", dims=(n, n, n), dx=DX, pos=pos, vel=vel)
 
 
-def dam_break(n=128, seed=12345, krange=None):
+def dam_break(n=128, seed=12345, krange=None, dx=DX):
     """Config 2 (n=128) / config 5 (n=512): column i∈[3s,35s) j∈[3s,67s) k∈[3s,n-3s), s=n/128.
+    dx: cell width (every BASELINE config uses 0.125; the tests also run a non-power-of-two width).
     krange=(k0,k1): only the particles seeded in cell planes [k0,k1) (identical to that part of the full
     scene), for z-slab ranks that must not materialise 128 M particles each."""
     s = max(n // 128, 1)
@@ -94,8 +95,8 @@ def dam_break(n=128, seed=12345, krange=None):
         skip = max(ka - k0, 0) * (i1 - i0) * (j1 - j0)
         k0, k1 = ka, max(kb, ka)
     cells = box_cells(i0, i1, j0, j1, k0, k1)
-    pos, vel = seed_cells(cells, DX, seed, skip_cells=skip)
-    return dict(name=f"dambreak{n}", dims=(n, n, n), dx=DX, pos=pos, vel=vel)
+    pos, vel = seed_cells(cells, dx, seed, skip_cells=skip)
+    return dict(name=f"dambreak{n}", dims=(n, n, n), dx=dx, pos=pos, vel=vel)
 
 
 def dam_break_z(n=64, seed=12347):

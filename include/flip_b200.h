@@ -159,6 +159,11 @@ int flip_initialize(flip_ctx *ctx);
 int flip_update(flip_ctx *ctx, double dt);
 /* FluidSimulation::getCurrentFrame :94 */
 int flip_get_current_frame(const flip_ctx *ctx, int *frame);
+/* FluidSimulation::setCurrentFrame  fluidsimulation.cpp:98 — with flip_get_particle_positions / _velocities and
+ * flip_load_particles this is the reference's snapshot / restore contract: a context
+ * restored from the two float-triplet blobs and the frame number continues the run (frame 0 alone uses the
+ * predicted first time step, :5595). */
+int flip_set_current_frame(flip_ctx *ctx, int frame);
 /* number of substeps the last flip_update took, and their stats (index 0..substeps-1) */
 int flip_get_num_substeps(const flip_ctx *ctx, int *substeps);
 int flip_get_step_stats(const flip_ctx *ctx, int substep, flip_step_stats *out);

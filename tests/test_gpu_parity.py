@@ -157,6 +157,17 @@ def test_lockstep_isolated(scene_name, n, frames, sampling):
         pc.check_report(rep, dx=sc["dx"], isolate=True, exact_sampling=(sampling == "exact"))
 
 
+@pytest.mark.parametrize("dx", [0.1, 0.3])
+def test_lockstep_isolated_non_dyadic_cell_width(dx):
+    """dx that is not a power of two: none of the exact-in-float shortcuts apply (packed P2G weights,
+    single-precision sampling, staggered-coordinate distances), every stage runs the literal restatement of
+    the reference's block-local double/float arithmetic and must match it bit for bit where the stage is
+    order-independent."""
+    sc = scenes.dam_break(32, dx=dx)
+    for rep in pc.lockstep_frames(sc, frames=4, isolate=True):
+        pc.check_report(rep, dx=sc["dx"], isolate=True, exact_sampling=True)
+
+
 @pytest.mark.parametrize("prec", ["jacobi", "multigrid"])
 def test_lockstep_chained(prec):
     """Whole substeps from identical particle state only (grids are NOT re-synchronised between
@@ -221,6 +232,45 @@ def test_particle_roundtrip_is_a_permutation():
     assert np.all(np.diff(flat) >= 0)
     assert np.array_equal(sim.getMarkerParticlePositionData(), p[:, :3])
     assert np.array_equal(sim.getMarkerParticleVelocityData(), p[:, 3:])
+
+
+def test_snapshot_restore_continues_the_run():
+    """the reference's snapshot is the two float-triplet blobs of
+    getMarkerParticlePositionData / VelocityData plus the frame number (fluidsimulation.cpp:2408-2420, :98);
+    loadMarkerParticleData + setCurrentFrame on a fresh simulation must continue the run.  The restored run
+    starts its PCG from zero instead of the previous pressure, so it agrees to the solver tolerance, not bit
+    for bit: same substep counts, same particle count, positions rel-L2 <= 1e-6."""
+    sc = scenes.dam_break(32)
+
+    def fresh():
+        s = fe.FluidSimulation(32, 32, 32, sc["dx"])
+        s.addBodyForce(0, -25, 0)
+        return s
+    a = fresh()
+    a.loadMarkerParticleData(fe.MarkerParticleData(sc["pos"], sc["vel"]))
+    a.initialize()
+    for _ in range(4):
+        a.update(1 / 30)
+    pos, vel, frame = a.getMarkerParticlePositionData(), a.getMarkerParticleVelocityData(), a.getCurrentFrame()
+    assert frame == 4 and pos.shape == vel.shape == (a.getNumMarkerParticles(), 3)
+    b = fresh()
+    b.loadMarkerParticleData(fe.MarkerParticleData(pos, vel))
+    b.setCurrentFrame(frame)
+    b.initialize()
+    assert b.getCurrentFrame() == 4 and b.getNumMarkerParticles() == a.getNumMarkerParticles()
+    # the restore is lossless: the store is cell-sorted and the blobs come out in that order
+    assert np.array_equal(b.getMarkerParticlePositionData(), pos) and np.array_equal(b.getMarkerParticleVelocityData(), vel)
+    for _ in range(3):
+        a.update(1 / 30)
+        b.update(1 / 30)
+        assert len(a.substep_stats()) == len(b.substep_stats())
+        assert a.getNumMarkerParticles() == b.getNumMarkerParticles()
+    pa, pb = a.getMarkerParticlePositionData(), b.getMarkerParticlePositionData()
+    assert pc.rel_l2(pb, pa) <= 1e-6
+    assert a.getCurrentFrame() == b.getCurrentFrame() == 7
+    with pytest.raises(ValueError):
+        b.setCurrentFrame(-1)
+    a.close(); b.close()
 
 
 def test_update_equals_stagewise():
