@@ -185,6 +185,16 @@ def test_pressure_tolerance_1e6_matches_reference_setting():
             assert rep["gpu.pcg_error"] <= 1e-6 * rep["gpu.rhs_max"]
 
 
+def test_pressure_stress_config_matches_reference():
+    """BASELINE config 4 at a size the oracle finishes in seconds: liquid in every interior cell, random particle
+    velocities, PCG to 1e-6 (the full 256^3 case is measured by scripts/pressure_stress.py)."""
+    sc = scenes.pressure_stress(40)
+    for rep in pc.lockstep_frames(sc, frames=1, isolate=True, tol=1e-6, sampling="exact"):
+        pc.check_report(rep, dx=sc["dx"], isolate=True, exact_sampling=True)
+        assert rep["gpu.pressure_rows"] == rep["ref.fluid_cells"] > 36 ** 3
+        assert rep["gpu.pcg_error"] <= 1e-6 * rep["gpu.rhs_max"]
+
+
 # ---------------------------------------------------------------- API behaviour (reference error semantics)
 def test_update_before_initialize_raises_runtime_error():
     sim = fe.FluidSimulation(8, 8, 8, 0.125)
