@@ -1601,6 +1601,7 @@ struct PressureScratch {
     int *flagAll = nullptr;
     int *posAll = nullptr;
     int nSegAll = 0;
+    int lastIterations = 0;            // PCG iterations of the previous solve (sizes the first poll-free batch)
     // multigrid hierarchy
     int numLevels = 0;                 // including level 0
     int firstSmall = 0;                // levels firstSmall..numLevels-1 run in one CTA (0: none)
@@ -2193,10 +2194,13 @@ void stage_pressure(flip_ctx *c, double dt) {
     if (slab) slab_allreduce_scalar(c, &c->dS->rho[0], COMM_SUM_F64);
 
     int it = 0;
-    const int batch = useMg ? 4 : 16;
+    // the host polls the convergence flag between batches of iterations (a stream sync each): the first batch
+    // runs up to just below the previous solve's count (consecutive substeps need nearly the same number)
+    const int batch = useMg ? 3 : 16;
+    const int firstBatch = (useMg && ps->lastIterations > batch + 2) ? ps->lastIterations - 2 : batch;
     bool done = false;
     while (!done && it < c->pressureMaxIter) {
-        int stop = it + batch;
+        int stop = it + (it == 0 ? firstBatch : batch);
         if (stop > c->pressureMaxIter) stop = c->pressureMaxIter;
         for (; it < stop; it++) {
             size_t ktIt = kt_begin(c);
@@ -2228,6 +2232,7 @@ void stage_pressure(flip_ctx *c, double dt) {
         for (int q = 1; q < 64 && h[q]; q++) fprintf(stderr, " %llu", h[q] - h[q - 1]);
         fprintf(stderr, "\n");
     }
+    ps->lastIterations = c->hS->pcgIterations;
     c->cur.pcg_iterations = c->hS->pcgIterations;
     c->cur.pcg_error = c->hS->pcgError;
     bool success = c->hS->pcgDone == 1;
