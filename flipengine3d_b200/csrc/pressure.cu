@@ -1611,6 +1611,10 @@ struct PressureScratch {
     int *segPool = nullptr;
     int *lvSeg[MG_MAX_LEVELS] = {nullptr};
     int *lvSegCount = nullptr;         // [MG_MAX_LEVELS]
+    // z-slabs: the same lists for the replicated (global) levels
+    int *gSegPool = nullptr;
+    int *gSeg[MG_MAX_LEVELS] = {nullptr};
+    int *gSegCount = nullptr;          // [MG_MAX_LEVELS]
     size_t coarseSmemBytes = 0;        // dynamic shared memory of k_mg_coarse (0: not usable, per-pass launches instead)
     int coarseBlocks = 0;              // its cooperative grid: one CTA per SM
     float *coarseBase = nullptr;       // levels >= 1 inside `pool` (L2 persistence window)
@@ -1779,6 +1783,13 @@ void pressure_alloc(flip_ctx *c) {
                 lv.oU = q; q += np; lv.oV = q; q += np; lv.oW = q; q += np; lv.b = q; q += np;
                 if (ps->gFirstSmall == 0 && lv.n <= MG_SMALL) ps->gFirstSmall = l;
             }
+            size_t ints = MG_MAX_LEVELS;
+            for (int l = Lc; l < L; l++) ints += (size_t)cdiv(ps->glv[l].n, 32) + 1;
+            FLIP_CUDA_CHECK(cudaMalloc(&ps->gSegPool, sizeof(int) * ints));
+            FLIP_CUDA_CHECK(cudaMemset(ps->gSegPool, 0, sizeof(int) * ints));
+            ps->gSegCount = ps->gSegPool;
+            int *qi = ps->gSegPool + MG_MAX_LEVELS;
+            for (int l = Lc; l < L; l++) { ps->gSeg[l] = qi; qi += cdiv(ps->glv[l].n, 32) + 1; }
         }
     }
 }
@@ -1790,7 +1801,7 @@ void pressure_free(flip_ctx *c) {
     if (c->mg) {
         PressureScratch *ps = (PressureScratch *)c->mg;
         cudaFree(ps->maskAll); cudaFree(ps->maskPrev); cudaFree(ps->flagAll); cudaFree(ps->posAll); cudaFree(ps->pool); cudaFree(ps->gpool);
-        cudaFree(ps->segPool); cudaFree(ps->trace);
+        cudaFree(ps->segPool); cudaFree(ps->gSegPool); cudaFree(ps->trace);
         delete ps;
         c->mg = nullptr;
     }
@@ -1944,6 +1955,16 @@ void stage_pressure(flip_ctx *c, double dt) {
             for (int l = Lc; l + 1 < ps->gLevels; l++) {
                 k_mg_coarsen<<<cdiv(ps->glv[l + 1].n, TPB), TPB, 0, st>>>(ps->glv[l], ps->glv[l + 1]); c->launches++;
             }
+            // active segments of the slab-local levels 1..Lc and of the replicated levels: the dam-break column
+            // fills an eighth of the box, a dense pass over a level spends most of its time on air
+            FLIP_CUDA_CHECK(cudaMemsetAsync(ps->lvSegCount, 0, sizeof(int) * MG_MAX_LEVELS, st));
+            FLIP_CUDA_CHECK(cudaMemsetAsync(ps->gSegCount, 0, sizeof(int) * MG_MAX_LEVELS, st));
+            for (int l = 1; l <= Lc; l++) {
+                k_mg_build_list<<<cdiv(ps->lv[l].n, TPB), TPB, 0, st>>>(ps->lv[l], ps->lvSeg[l], &ps->lvSegCount[l]); c->launches++;
+            }
+            for (int l = Lc; l < ps->gLevels; l++) {
+                k_mg_build_list<<<cdiv(ps->glv[l].n, TPB), TPB, 0, st>>>(ps->glv[l], ps->gSeg[l], &ps->gSegCount[l]); c->launches++;
+            }
         }
         kt_end(c, FLIP_KERNEL_PRESSURE_BUILD, ktB);
     }
@@ -1973,6 +1994,22 @@ void stage_pressure(flip_ctx *c, double dt) {
     auto xchg = [&](int l, float *x) {
         if (Lc && l < Lc) slab_exchange_cell_plane_f32(c, x, ps->lv[l].sk, d.kOwn0 >> l, d.kOwn1 >> l);
     };
+    // aligned z-slabs: every level >= 1 runs over its active-segment list (built in the set-up above)
+    const bool sl = Lc > 0 && ps->gSegPool != nullptr;
+    auto seg_of = [&](int l, bool localDesc) -> const int * { return (Lc && l >= Lc && !localDesc) ? ps->gSeg[l] : ps->lvSeg[l]; };
+    auto cnt_of = [&](int l, bool localDesc) -> const int * {
+        return (Lc && l >= Lc && !localDesc) ? &ps->gSegCount[l] : &ps->lvSegCount[l];
+    };
+    auto sl_blocks = [&](const MgLevel &lv) { return std::max(1, std::min(cdiv(cdiv(lv.n, 32), WPB), 148 * 8)); };
+    auto sl_rblocks = [&](const MgLevel &coarse) { return std::max(1, std::min(cdiv(coarse.n, 32), 148 * 8)); };
+    auto sweep_lvl = [&](int l, MgLevel &lv, MgLevel &C, const float *xin, const float *e, float *xout, float om, int mode) {
+        if (sl)
+            k_mg_sweep_list<<<sl_blocks(lv), TPB, 0, st>>>(lv, C, xin, e, xout, om, mp.scale, mode, seg_of(l, false), cnt_of(l, false),
+                                                          c->dS, 0.0f);
+        else
+            k_mg_sweep<<<cdiv(lv.n, TPB), TPB, 0, st>>>(lv, C, xin, e, xout, om, mp.scale, mode, c->dS);
+        c->launches++;
+    };
     // one V-cycle: z = M^-1 r, rho[rhoSlot] += z.r
     auto vcycle = [&](int rhoSlot) {
         const int nu = mp.nu;
@@ -1988,7 +2025,12 @@ void stage_pressure(flip_ctx *c, double dt) {
                 xchg(0, xa);
             }
             // xa holds the result
-            k_mg0_restrict<<<cdiv(up_desc(0).n, TPB), TPB, 0, st>>>(m0, up_desc(0), c->vr, xa, c->dS); c->launches++;
+            if (sl)     // the target is the local descriptor when level 1 is the first replicated one
+                k_mg0_restrict_list<<<sl_rblocks(up_desc(0)), 256, 0, st>>>(m0, up_desc(0), c->vr, xa, seg_of(1, Lc == 1),
+                                                                           cnt_of(1, Lc == 1), c->dS);
+            else
+                k_mg0_restrict<<<cdiv(up_desc(0).n, TPB), TPB, 0, st>>>(m0, up_desc(0), c->vr, xa, c->dS);
+            c->launches++;
             ps->lv[0].x = xa; ps->lv[0].x2 = xb;
             after_restrict(0);
         }
@@ -1996,13 +2038,17 @@ void stage_pressure(flip_ctx *c, double dt) {
             MgLevel &lv = *LV[l];
             float *xa = lv.x, *xb = lv.x2;
             for (int sw = 0; sw < nu; sw++) {
-                k_mg_sweep<<<cdiv(lv.n, TPB), TPB, 0, st>>>(lv, lv, xa, nullptr, xb, pre_om(sw), mp.scale, sw == 0 ? 0 : 1, c->dS);
-                c->launches++;
+                sweep_lvl(l, lv, lv, xa, nullptr, xb, pre_om(sw), sw == 0 ? 0 : 1);
                 std::swap(xa, xb);
                 xchg(l, xa);
             }
             lv.x = xa; lv.x2 = xb;
-            k_mg_restrict<<<cdiv(up_desc(l).n, TPB), TPB, 0, st>>>(lv, up_desc(l), lv.x, c->dS); c->launches++;
+            if (sl)
+                k_mg_restrict_list<<<sl_rblocks(up_desc(l)), 256, 0, st>>>(lv, up_desc(l), lv.x, seg_of(l + 1, l + 1 == Lc),
+                                                                          cnt_of(l + 1, l + 1 == Lc), c->dS);
+            else
+                k_mg_restrict<<<cdiv(up_desc(l).n, TPB), TPB, 0, st>>>(lv, up_desc(l), lv.x, c->dS);
+            c->launches++;
             after_restrict(l);
         }
         // ---- bottom: small levels in one CTA, or coarsest-level sweeps
@@ -2015,8 +2061,7 @@ void stage_pressure(flip_ctx *c, double dt) {
             MgLevel &lv = *LV[L - 1];
             float *xa = lv.x, *xb = lv.x2;
             for (int sw = 0; sw < mp.coarseSweeps; sw++) {
-                k_mg_sweep<<<cdiv(lv.n, TPB), TPB, 0, st>>>(lv, lv, xa, nullptr, xb, mp.omegaCoarse, mp.scale, sw == 0 ? 0 : 1, c->dS);
-                c->launches++;
+                sweep_lvl(L - 1, lv, lv, xa, nullptr, xb, mp.omegaCoarse, sw == 0 ? 0 : 1);
                 std::swap(xa, xb);
             }
             lv.x = xa; lv.x2 = xb;
@@ -2027,9 +2072,7 @@ void stage_pressure(flip_ctx *c, double dt) {
             MgLevel &lv = *LV[l];
             float *xa = lv.x, *xb = lv.x2;
             for (int sw = 0; sw < nu; sw++) {
-                k_mg_sweep<<<cdiv(lv.n, TPB), TPB, 0, st>>>(lv, up_desc(l), xa, up_x(l), xb, post_om(sw), mp.scale,
-                                                          sw == 0 ? 2 : 1, c->dS);
-                c->launches++;
+                sweep_lvl(l, lv, up_desc(l), xa, up_x(l), xb, post_om(sw), sw == 0 ? 2 : 1);
                 std::swap(xa, xb);
                 xchg(l, xa);      // the next sweep, and the finer level's prolongation, read the neighbours' planes
             }
