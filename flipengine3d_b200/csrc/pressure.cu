@@ -858,24 +858,51 @@ __global__ void __launch_bounds__(1024) k_mg_coarse(MgCoarseArgs A, const Device
         }
         for (int q = tid; q < A.smemFloats; q += nt) smf[q] = 0.0f;
         __syncthreads();
+    }
+    stamp();
+    // second half of the staging (the operator arrays): block 0 runs it during the restriction pass of level 1,
+    // in which it takes no part either
+    auto stage_operators = [&]() {
         for (int l = A.fs; l <= A.last; l++) {
             const MgLevel &G = A.lv[l];
             const SmLevel &L = sl[l];
-            for (int c = tid; c < G.n; c += nt) {
-                L.diag[c] = G.diag[c]; L.invD[c] = G.invD[c]; L.oU[c] = G.oU[c]; L.oV[c] = G.oV[c]; L.oW[c] = G.oW[c];
+            // all loads of four strides first (read-only path): through generic pointers the compiler must
+            // otherwise order every shared store before the next global load, ~20 dependent L2 latencies
+            for (int c0 = tid; c0 < G.n; c0 += 4 * nt) {
+                float v[4][5];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int c = c0 + u * nt;
+                    if (c < G.n) {
+                        v[u][0] = __ldg(G.diag + c); v[u][1] = __ldg(G.invD + c); v[u][2] = __ldg(G.oU + c);
+                        v[u][3] = __ldg(G.oV + c); v[u][4] = __ldg(G.oW + c);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int c = c0 + u * nt;
+                    if (c < G.n) { L.diag[c] = v[u][0]; L.invD[c] = v[u][1]; L.oU[c] = v[u][2]; L.oV[c] = v[u][3]; L.oW[c] = v[u][4]; }
+                }
             }
         }
         __syncthreads();
-    }
-    stamp();
+    };
+    bool staged = false;
 
     const float *lx[MG_MAX_LEVELS];
-    // ---- down through the list-driven levels
+    // ---- down through the list-driven levels.  Block 0 has just spent ~10 us staging: the other blocks share the
+    // down passes of level 1 among themselves (gw1 / nw1 / first block 1), so that the staging is off the critical path
+    const int wpb = nt >> 5;
     for (int l = 1; l < A.fs; l++) {
         const MgLevel &L = A.lv[l];
         const int *__restrict__ list = A.seg[l];
         const int nseg = A.segCount[l];
         float *xa = L.x, *xb = L.x2;
+        const bool skip0 = (l == 1) && gridDim.x > 1;
+        const int gw = skip0 ? (blockIdx.x == 0 ? 0x3fffffff : ((blockIdx.x - 1) * nt + tid) >> 5) : ((blockIdx.x * nt + tid) >> 5);
+        const int nw = skip0 ? (gridDim.x - 1) * wpb : gridDim.x * wpb;
+        const int rb = skip0 ? (blockIdx.x == 0 ? 0x3fffffff : (int)blockIdx.x - 1) : (int)blockIdx.x;   // restriction: block index
+        const int rnb = skip0 ? (int)gridDim.x - 1 : (int)gridDim.x;
         int sw = 0;
         if (nu >= 2) {
             for (int s = gw; s < nseg; s += nw) {
@@ -897,13 +924,15 @@ __global__ void __launch_bounds__(1024) k_mg_coarse(MgCoarseArgs A, const Device
             float *t = xa; xa = xb; xb = t;
         }
         lx[l] = xa;
+        if (blockIdx.x == 0 && !staged && (skip0 || l + 1 == A.fs)) { stage_operators(); staged = true; }
         // restriction into level l+1: eight threads per coarse cell, four coarse segments per CTA pass
         {
             const MgLevel &C = A.lv[l + 1];
             const int *__restrict__ listC = A.seg[l + 1];
             const int nsegC = A.segCount[l + 1];
             const int t = tid & 255, q = t & 7;
-            for (int s = blockIdx.x * (nt >> 8) + (tid >> 8); s < nsegC; s += gridDim.x * (nt >> 8)) {
+            for (long long s = (rb >= 0x3fffffff ? (long long)nsegC : (long long)rb * (nt >> 8) + (tid >> 8)); s < nsegC;
+                 s += (long long)rnb * (nt >> 8)) {
                 const int cc = listC[s] + (t >> 3);
                 float v = 0.0f;
                 const bool act = (cc < C.n) && C.invD[cc] != 0.0f;
@@ -923,6 +952,7 @@ __global__ void __launch_bounds__(1024) k_mg_coarse(MgCoarseArgs A, const Device
     }
     // ---- the single-CTA levels
     if (blockIdx.x == 0) {
+        if (!staged) { stage_operators(); staged = true; }
         const MgLevel &G = A.lv[A.fs];
         const SmLevel &L = sl[A.fs];
         for (int c = tid; c < G.n; c += nt) L.b[c] = G.b[c];
@@ -1738,7 +1768,11 @@ void pressure_alloc(flip_ctx *c) {
             if (coop && bytes + 4096 <= (size_t)maxOptin) {
                 FLIP_CUDA_CHECK(cudaFuncSetAttribute(k_mg_coarse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
                 FLIP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_mg_coarse, 1024, bytes));
-                if (perSm >= 1) { ps->coarseSmemBytes = bytes; ps->coarseBlocks = sms; }
+                if (perSm >= 1) {
+                    ps->coarseSmemBytes = bytes;
+                    ps->coarseBlocks = sms;
+                    if (const char *e = getenv("FLIP_MG_COARSE_BLOCKS")) ps->coarseBlocks = std::max(2, std::min(sms, atoi(e)));   // tuning knob
+                }
                 if (getenv("FLIP_MG_TRACE")) {
                     FLIP_CUDA_CHECK(cudaMalloc(&ps->trace, 64 * sizeof(unsigned long long)));
                     FLIP_CUDA_CHECK(cudaMemset(ps->trace, 0, 64 * sizeof(unsigned long long)));
