@@ -197,82 +197,8 @@ def test_pressure_stress_config_matches_reference():
 
 def test_cuda_path_against_the_numpy_restatement():
     """The CUDA stages against oracle/restatement.py on a seeded scene, from the CUDA path's own inputs: needs
-    neither oracle/_ref nor /root/reference.  Order-independent stages bit for bit, P2G and the projection to
-    their tolerances (literal P2G weights and double-precision sampling: FLIP_SAMPLING_EXACT)."""
-    from oracle import restatement as R
-    sc = scenes.dam_break(32)
-    dims, dx = sc["dims"], sc["dx"]
-    sim = fe.FluidSimulation(*dims, dx)
-    sim.addBodyForce(0, -25, 0)
-    sim.setSamplingMode("exact")
-    sim.enableParticleIds(True)
-    sim.loadMarkerParticleData(fe.MarkerParticleData(sc["pos"], sc["vel"]))
-    sim.initialize()
-    for _ in range(3):
-        sim.update(1 / 30)
-    sim.begin_frame(1 / 30)
-    dt = sim.begin_substep()
-    P = sim.getMarkerParticles().copy()
-    sim.stage("obstacles", dt)
-    solid = sim.array("solid_phi")
-    sim.stage("liquid_sdf", dt)
-    assert np.array_equal(sim.array("liquid_phi"), R.liquid_sdf(P[:, :3], dims, dx, solid))
-    sim.stage("p2g", dt)
-    ref = R.p2g(P[:, :3], P[:, 3:], dims, dx)
-    scale = max(float(np.abs(a).max()) for a in ref[:3])
-    for n, a, v in zip("UVW", ref[:3], ref[3:]):
-        assert np.array_equal(sim.array(f"valid{n}") != 0, v != 0), n
-        assert pc.rel_l2(sim.array(n), a) <= 1e-5 or pc.max_abs(sim.array(n), a) <= 1e-5 * scale, n
-    fields = {n: sim.array(n) for n in "UVW"}
-    valids = {n: sim.array(f"valid{n}") for n in "UVW"}
-    sim.stage("extrapolate_a", dt)
-    for n in "UVW":
-        assert np.array_equal(sim.array(n), R.extrapolate(fields[n], valids[n])), n
-    sim.stage("save", dt)
-    before = {n: sim.array(n) for n in "UVW"}
-    sim.stage("body_force", dt)
-    assert np.array_equal(sim.array("V"), R.body_force(before["V"], -25.0, dt))
-    pre = {n: sim.array(n) for n in "UVW"}
-    phi = sim.array("liquid_phi")
-    w = {n: sim.array(f"weight{n}") for n in "UVW"}
-    sim.stage("pressure", dt)
-    U, V, W, vU, vV, vW, rows, bmax = R.pressure_project(pre["U"], pre["V"], pre["W"], phi, w["U"], w["V"], w["W"], dims, dx, dt)
-    scale = max(float(np.abs(a).max()) for a in (U, V, W))
-    for n, a, v in (("U", U, vU), ("V", V, vV), ("W", W, vW)):
-        assert np.array_equal(sim.array(f"valid{n}") != 0, v != 0), n
-        assert pc.rel_l2(sim.array(n), a) <= 1e-4 or pc.max_abs(sim.array(n), a) <= 1e-5 * scale, n
-    fields = {n: sim.array(n) for n in "UVW"}
-    valids = {n: sim.array(f"valid{n}") for n in "UVW"}
-    sim.stage("extrapolate_b", dt)
-    for n in "UVW":
-        assert np.array_equal(sim.array(n), R.extrapolate(fields[n], valids[n])), n
-    fields = {n: sim.array(n) for n in "UVW"}
-    saved = {n: sim.array(f"saved{n}") for n in "UVW"}
-    sim.stage("constrain", dt)
-    for n in "UVW":
-        assert np.array_equal(sim.array(n), R.constrain(fields[n], w[n])), n
-        assert np.array_equal(sim.array(f"saved{n}"), R.constrain(saved[n], w[n])), n
-    new = tuple(sim.array(n) for n in "UVW")
-    old = tuple(sim.array(f"saved{n}") for n in "UVW")
-    ids0 = sim.getParticleIds().copy()
-    sim.stage("g2p", dt)
-    P1 = sim.getMarkerParticles().copy()
-    assert np.array_equal(sim.getParticleIds(), ids0)
-    assert np.array_equal(P1[:, 3:], R.g2p(P[:, :3], P[:, 3:], new, old, dims, dx))
-    sim.stage("advance", dt)
-    P2, ids2 = sim.getMarkerParticles(), sim.getParticleIds()
-    # the advance stage re-sorts the store: match by particle id; particles the collision march moved are excluded
-    # (the restatement has no _resolveCollision), they all lie within 3.5 cells of the walls
-    p1 = R.rk3(P[:, :3], new, dims, dx, dt)
-    lookup = np.full(int(ids0.max()) + 1, -1, dtype=np.int64)
-    lookup[ids0] = np.arange(ids0.size)
-    src = lookup[ids2]
-    same = (P2[:, :3] == p1[src]).all(axis=1)
-    lo, hi = 3.5 * dx, (dims[0] - 3.5) * dx
-    interior = ((P[src, :3] > lo) & (P[src, :3] < hi)).all(axis=1)
-    assert same[interior].all()
-    assert same.mean() > 0.8
-    sim.end_substep(); sim.end_frame(); sim.close()
+    neither oracle/_ref nor /root/reference (pc.restatement_check)."""
+    pc.restatement_check(scenes.dam_break(32))
 
 
 # ---------------------------------------------------------------- API behaviour (reference error semantics)
