@@ -29,6 +29,12 @@ def _gpu_from_golden(g, preconditioner=None, sampling=None):
     return sim
 
 
+# tests that step the unmodified reference engine next to the CUDA path need oracle/_ref (built by
+# __graft_entry__.build() where /root/reference exists; it travels to the GPU box with the snapshot).  Without it
+# they are skipped, not failed: the golden fixtures and the numpy restatement still pin the CUDA path.
+needs_ref = pytest.mark.skipif(not pc.refengine.available("golden"), reason="oracle/_ref/libflipref_golden.so not built")
+
+
 @pytest.fixture(scope="module")
 def dam24():
     return np.load(os.path.join(GOLD, "dam24_stages.npz"))
@@ -149,6 +155,7 @@ def test_default_scene_free_running_against_golden():
 
 
 # ---------------------------------------------------------------- lock-step against the live reference
+@needs_ref
 @pytest.mark.parametrize("sampling", ["exact", "fast"])
 @pytest.mark.parametrize("scene_name,n,frames", [("default", 30, 3), ("dambreak", 32, 6), ("spheredrop", 48, 4)])
 def test_lockstep_isolated(scene_name, n, frames, sampling):
@@ -157,6 +164,7 @@ def test_lockstep_isolated(scene_name, n, frames, sampling):
         pc.check_report(rep, dx=sc["dx"], isolate=True, exact_sampling=(sampling == "exact"))
 
 
+@needs_ref
 @pytest.mark.parametrize("dx", [0.1, 0.3])
 def test_lockstep_isolated_non_dyadic_cell_width(dx):
     """dx that is not a power of two: none of the exact-in-float shortcuts apply (packed P2G weights,
@@ -168,6 +176,7 @@ def test_lockstep_isolated_non_dyadic_cell_width(dx):
         pc.check_report(rep, dx=sc["dx"], isolate=True, exact_sampling=True)
 
 
+@needs_ref
 @pytest.mark.parametrize("prec", ["jacobi", "multigrid"])
 def test_lockstep_chained(prec):
     """Whole substeps from identical particle state only (grids are NOT re-synchronised between
@@ -177,6 +186,7 @@ def test_lockstep_chained(prec):
         pc.check_report(rep, dx=sc["dx"], isolate=False)
 
 
+@needs_ref
 def test_pressure_tolerance_1e6_matches_reference_setting():
     sc = scenes.dam_break(32)
     for rep in pc.lockstep_frames(sc, frames=3, isolate=True, tol=1e-6, sampling="exact"):
@@ -185,6 +195,7 @@ def test_pressure_tolerance_1e6_matches_reference_setting():
             assert rep["gpu.pcg_error"] <= 1e-6 * rep["gpu.rhs_max"]
 
 
+@needs_ref
 def test_pressure_stress_config_matches_reference():
     """BASELINE config 4 at a size the oracle finishes in seconds: liquid in every interior cell, random particle
     velocities, PCG to 1e-6 (the full 256^3 case is measured by scripts/pressure_stress.py)."""
@@ -195,10 +206,14 @@ def test_pressure_stress_config_matches_reference():
         assert rep["gpu.pcg_error"] <= 1e-6 * rep["gpu.rhs_max"]
 
 
-def test_cuda_path_against_the_numpy_restatement():
-    """The CUDA stages against oracle/restatement.py on a seeded scene, from the CUDA path's own inputs: needs
-    neither oracle/_ref nor /root/reference (pc.restatement_check)."""
-    pc.restatement_check(scenes.dam_break(32))
+@pytest.mark.parametrize("which", ["dam32", "dam32_dx0.1", "spheredrop48"])
+def test_cuda_path_against_the_numpy_restatement(which):
+    """The CUDA stages against oracle/restatement.py on seeded scenes, from the CUDA path's own inputs: needs
+    neither oracle/_ref nor /root/reference (pc.restatement_check).  The restatement itself is pinned to the
+    reference on the same scenes by tests/test_restatement_cpu.py."""
+    sc = {"dam32": lambda: scenes.dam_break(32), "dam32_dx0.1": lambda: scenes.dam_break(32, dx=0.1),
+          "spheredrop48": lambda: scenes.sphere_drop(48)}[which]()
+    pc.restatement_check(sc)
 
 
 # ---------------------------------------------------------------- API behaviour (reference error semantics)
