@@ -1,9 +1,2 @@
-mkdir -p gpurun_out
-timeout 900 python bench.py > gpurun_out/t_bench.json 2> gpurun_out/t_bench.err; echo "bench rc=$?"; tail -2 gpurun_out/t_bench.err
-python - <<'P'
-import json
-d=json.loads(open('gpurun_out/t_bench.json').read().strip().splitlines()[-1])
-print('ms/step', d['ms_per_step'], 'value', d['value'], 'e2e', d['e2e']['value'], d['e2e']['ms_per_step'], 'scaling_ref', d.get('scaling_ref',{}).get('ms_per_step'))
-print('roofline', d['roofline']['frac'], d['roofline']['traffic'], 'cpu', d['cpu_baseline']['value'])
-for k,v in d['kernels'].items(): print(k, round(v['avg_ms'],4), v['launches'], round(v.get('frac',0),3))
-P
+./build/fluidmanager_headless 100 30 | tail -4
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q --tb=short -k "fluidmanager or abi" 2>&1 | tail -6

@@ -73,3 +73,23 @@ def test_step_stats_struct_layout_matches_header(built):
     from flipengine3d_b200 import engine
     # 8 int32 + 3 double, naturally aligned
     assert C.sizeof(engine.StepStats) == 8 * 4 + 3 * 8
+
+
+def test_cpp_facade_example_links_and_refuses_to_run_without_a_device(built):
+    """include/fluidsimulation_b200.hpp (the FluidSimulation-named C++ façade) and examples/fluidmanager_headless.cpp
+    (the reference's FluidManager scene without DXViewer) compile against the C-ABI; without a GPU the program
+    exits with the no-CPU-fallback error instead of computing anything."""
+    import shutil
+    import subprocess
+    import torch
+    exe = os.path.join(ROOT, "build", "fluidmanager_headless")
+    if not os.path.exists(exe):
+        if shutil.which("g++") is None or shutil.which("make") is None:
+            pytest.skip("no C++ toolchain and no prebuilt example")
+        subprocess.run(["make", "-C", os.path.join(ROOT, "flipengine3d_b200", "csrc")], check=True, stdout=subprocess.DEVNULL)
+    assert os.path.exists(exe)
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: the run itself is covered by tests/test_gpu_parity.py")
+    r = subprocess.run([exe, "2"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
+    assert r.returncode == 2, (r.returncode, r.stdout, r.stderr)
+    assert "no CPU fallback" in r.stderr

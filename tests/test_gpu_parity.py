@@ -7,6 +7,8 @@ import os
 import numpy as np
 import pytest
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
 import parity_common as pc
 from flipengine3d_b200 import engine as fe
 from flipengine3d_b200 import scenes
@@ -217,6 +219,27 @@ def test_cuda_path_against_the_numpy_restatement(which):
 
 
 # ---------------------------------------------------------------- API behaviour (reference error semantics)
+def test_fluidmanager_scene_headless_through_the_cpp_facade():
+    """BASELINE config 1 as the reference runs it: FluidManager::initialize / iUpdate (src/FluidManager.cpp:47-83) in
+    C++ over include/fluidsimulation_b200.hpp, no DXViewer: the middle-third box seeds 10^3 cells x 8 particles,
+    falls, and stays inside the walls for 60 frames."""
+    import re
+    import subprocess
+    exe = os.path.join(ROOT, "build", "fluidmanager_headless")
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "flipengine3d_b200", "csrc")], check=True, stdout=subprocess.DEVNULL)
+    r = subprocess.run([exe, "60", "30"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-2000:])
+    assert "initialized: 30^3 cells, dx 0.125, 8000 marker particles" in r.stdout
+    m = re.search(r"done: 60 frames, ([0-9.]+) ms per frame .*?, (\d+) particles, y in \[([0-9.eE+-]+), ([0-9.eE+-]+)\]", r.stdout)
+    assert m, r.stdout[-2000:]
+    n, ymin, ymax = int(m.group(2)), float(m.group(3)), float(m.group(4))
+    assert 7900 <= n <= 8000          # only the extreme-velocity rule may remove a few
+    assert ymin >= 1.5 * 0.125 and ymax < 30 * 0.125 - 1.5 * 0.125      # inside the 1.5-cell walls
+    assert ymax < 1.6                 # the block (top at 2.5) has fallen into a pool
+    assert "frame   60" in r.stdout
+
+
 def test_update_before_initialize_raises_runtime_error():
     sim = fe.FluidSimulation(8, 8, 8, 0.125)
     with pytest.raises(RuntimeError):
