@@ -1,1 +1,2 @@
-timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q --tb=short -k "restatement" 2>&1 | tail -8
+timeout 1200 python -m pytest tests -m gpu -x -q --tb=short 2>&1 | tail -4
+python scripts/probe_vcycle.py 2>&1 | tail -1
