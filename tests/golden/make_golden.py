@@ -5,6 +5,7 @@ container:  python tests/golden/make_golden.py
 Fixtures (small, committed):
   default30_frames.npz   config 1 (FluidManager scene, 30^3, 8000 particles): per-frame particle
                          hashes/counts/PCG iterations over 6 frames + final particle state.
+  default30_static.npz   the static inputs of that scene (solid SDF, face weights, near-solid mask).
   dam24_stages.npz       a 24^3 dam break, third frame, every intermediate array of one substep
                          (inputs and outputs of each stage), for per-stage known-answer tests.
 The reference is bit-deterministic for injected particles with any thread count.
@@ -47,6 +48,21 @@ def default30():
     print("default30", hashes[-1], counts, iters, cells, substeps)
 
 
+def default30_static():
+    """Static inputs of the default scene (they come from the reference's mesh code, outside the hot path): nodal
+    solid SDF, face weights, near-solid mask -- what oracle/restatement.py's whole-step engine takes as given."""
+    sc = scenes.default_scene(30)
+    e = RefEngine(sc["dims"], sc["dx"], sc["pos"], sc["vel"], threads=2)
+    e.begin_frame(1.0 / 30.0)
+    dt = e.begin_substep()
+    e.stage("obstacles", dt)
+    e.update_weight_grid()
+    np.savez_compressed(os.path.join(HERE, "default30_static.npz"), solid_phi=e.array("solid_phi"), near_solid=e.array("near_solid"),
+                        weightU=e.array("weightU"), weightV=e.array("weightV"), weightW=e.array("weightW"))
+    e.close()
+    print("default30_static written")
+
+
 def dam24():
     sc = scenes.dam_break(24)
     e = RefEngine(sc["dims"], sc["dx"], sc["pos"], sc["vel"], threads=4)
@@ -86,4 +102,5 @@ def dam24():
 
 if __name__ == "__main__":
     default30()
+    default30_static()
     dam24()
