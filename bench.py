@@ -417,7 +417,7 @@ def main():
     ap.add_argument("--ref-steps", type=int, default=4, help="timed frames of that reference point")
     ap.add_argument("--ref-grid", type=int, default=128,
                     help="grid of the bounded CPU sample of the same workload (reference arm / cpu_baseline)")
-    ap.add_argument("--cpu-steps", type=int, default=3, help="frames of the cpu_baseline sample in our arm")
+    ap.add_argument("--cpu-steps", type=int, default=10, help="frames of the cpu_baseline sample in our arm (about 1 s each on 16 cores)")
     ap.add_argument("--preconditioner", default=None)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
