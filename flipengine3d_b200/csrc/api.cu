@@ -684,6 +684,39 @@ int flip_set_slab(flip_ctx *c, int rank, int nranks, const void *id, int idBytes
         peer_setup(c);
     });
 }
+int flip_static_inputs(int I, int J, int K, double dx, float *phi, int phiIsInput, float *wU, float *wV, float *wW,
+                       unsigned char *nearSolid, int nearDims[3]) {
+    if (I <= 0 || J <= 0 || K <= 0 || !(dx > 0.0)) return FLIP_ERR_DOMAIN;
+    try {
+        flip_ctx defaults;          // only its configuration defaults are read
+        Dims d;
+        d.I = I; d.J = J; d.K = K; d.dx = dx; d.kOff = 0; d.Kg = K; d.kOwn0 = 0; d.kOwn1 = K;
+        d.nU = (I + 1) * J * K; d.nV = I * (J + 1) * K; d.nW = I * J * (K + 1); d.nC = I * J * K;
+        d.nN = (I + 1) * (J + 1) * (K + 1);
+        std::vector<float> p, a, b, w, cc;
+        if (phiIsInput) {
+            if (!phi) return FLIP_ERR_RUNTIME;
+            p.assign(phi, phi + (size_t)d.nN);
+        } else {
+            build_box_solid_sdf(d, p);
+            if (phi) memcpy(phi, p.data(), sizeof(float) * p.size());
+        }
+        if (wU || wV || wW) {
+            build_weights(d, p, a, b, w, cc);
+            if (wU) memcpy(wU, a.data(), sizeof(float) * a.size());
+            if (wV) memcpy(wV, b.data(), sizeof(float) * b.size());
+            if (wW) memcpy(wW, w.data(), sizeof(float) * w.size());
+        }
+        if (nearSolid || nearDims) {
+            std::vector<unsigned char> ns;
+            int gi = 0, gj = 0, gk = 0;
+            build_near_solid(d, p, defaults.nearSolidFactor, defaults.solidExactBand, defaults.CFL, ns, gi, gj, gk);
+            if (nearSolid) memcpy(nearSolid, ns.data(), ns.size());
+            if (nearDims) { nearDims[0] = gi; nearDims[1] = gj; nearDims[2] = gk; }
+        }
+        return FLIP_OK;
+    } catch (const std::bad_alloc &) { g_createError = "host allocation failed"; return FLIP_ERR_RUNTIME; }
+}
 int flip_get_nccl_unique_id(void *out, int idBytes) {
     try {
         comm_unique_id(out, idBytes);

@@ -84,6 +84,7 @@ def load_library():
     L.flip_update.argtypes = [vp, cd]
     L.flip_get_current_frame.argtypes = [vp, C.POINTER(ci)]
     L.flip_set_current_frame.argtypes = [vp, ci]
+    L.flip_static_inputs.argtypes = [ci, ci, ci, C.c_double, vp, ci, vp, vp, vp, vp, C.POINTER(ci)]
     L.flip_get_num_substeps.argtypes = [vp, C.POINTER(ci)]
     L.flip_get_step_stats.argtypes = [vp, ci, C.POINTER(StepStats)]
     L.flip_get_num_particles.argtypes = [vp, C.POINTER(ci)]
@@ -116,6 +117,29 @@ def load_library():
     L.flip_set_halo.argtypes = [vp, ci]
     _lib = L
     return L
+
+
+def static_inputs(isize, jsize, ksize, dx, solid_phi=None):
+    """Host-side static inputs of a box domain (flip_static_inputs; no CUDA device needed):
+    dict(solid_phi (K+1,J+1,I+1), weightU, weightV, weightW, near_solid (nk,nj,ni)).  solid_phi given: the weights and
+    the mask are derived from it (as after flip_set_solid_sdf) instead of from the built-in box."""
+    L = load_library()
+    I, J, K = int(isize), int(jsize), int(ksize)
+    given = 0 if solid_phi is None else 1
+    phi = np.empty((K + 1, J + 1, I + 1), dtype=np.float32) if solid_phi is None else np.ascontiguousarray(solid_phi, dtype=np.float32).copy()
+    assert phi.shape == (K + 1, J + 1, I + 1)
+    wU = np.empty((K, J, I + 1), dtype=np.float32)
+    wV = np.empty((K, J + 1, I), dtype=np.float32)
+    wW = np.empty((K + 1, J, I), dtype=np.float32)
+    nd = (C.c_int * 3)()
+    rc = L.flip_static_inputs(I, J, K, float(dx), phi.ctypes.data if given else None, given, None, None, None, None, nd)
+    if rc != FLIP_OK:
+        raise _EXC.get(rc, RuntimeError)("flip_static_inputs failed")
+    ns = np.empty((nd[2], nd[1], nd[0]), dtype=np.uint8)
+    rc = L.flip_static_inputs(I, J, K, float(dx), phi.ctypes.data, given, wU.ctypes.data, wV.ctypes.data, wW.ctypes.data, ns.ctypes.data, nd)
+    if rc != FLIP_OK:
+        raise _EXC.get(rc, RuntimeError)("flip_static_inputs failed")
+    return dict(solid_phi=phi, weightU=wU, weightV=wV, weightW=wW, near_solid=ns)
 
 
 def nccl_unique_id():

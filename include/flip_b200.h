@@ -146,6 +146,16 @@ int flip_add_fluid_box(flip_ctx *ctx, const double lo[3], const double hi[3], co
 /* FluidSimulation::_addMarkerParticle  fluidsimulation.cpp:2637 (range-checked push). */
 int flip_add_marker_particle(flip_ctx *ctx, const float position[3], const float velocity[3]);
 
+/* The static inputs of a box domain, computed on the HOST exactly as flip_initialize computes them (no CUDA device
+ * needed; host code of csrc/static_host.cpp): the nodal solid SDF of the reference's domain box
+ * (_addStaticObjectsToSDF fluidsimulation.cpp:2927-2936, box of :2834-2839), the face weights
+ * (_updateWeightGridThread :3690-3730) and the coarse near-solid mask (:3083-3125).  Any output pointer may be NULL.
+ * phi: (I+1)(J+1)(K+1) floats; wU (I+1)JK, wV I(J+1)K, wW IJ(K+1) floats; near_solid: ceil(I/3)*ceil(J/3)*ceil(K/3)
+ * bytes, its dimensions returned in near_dims[3].  phi_is_input != 0: phi is READ (as flip_set_solid_sdf would supply it)
+ * and the weights / mask are derived from it instead of from the built-in box. */
+int flip_static_inputs(int isize, int jsize, int ksize, double dx, float *phi, int phi_is_input, float *wU, float *wV, float *wW,
+                       unsigned char *near_solid, int near_dims[3]);
+
 /* Override the static solid inputs.  By default the context builds the reference's
  * domain box (inset 1.5dx+5e-5, fluidsimulation.cpp:2834-2839) itself.  phi: (I+1)(J+1)(K+1) floats. */
 int flip_set_solid_sdf(flip_ctx *ctx, const float *phi_nodal);

@@ -93,3 +93,24 @@ def test_cpp_facade_example_links_and_refuses_to_run_without_a_device(built):
     r = subprocess.run([exe, "2"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
     assert r.returncode == 2, (r.returncode, r.stdout, r.stderr)
     assert "no CPU fallback" in r.stderr
+
+
+@pytest.mark.parametrize("fixture,n", [("dam24_stages.npz", 24), ("default30_static.npz", 30)])
+def test_host_static_inputs_match_the_reference(built, fixture, n):
+    """The host code that prepares the static inputs (csrc/static_host.cpp through flip_static_inputs, no device):
+    from the reference's solid SDF the face weights and the near-solid mask come out bit for bit; the built-in box
+    SDF has the reference's sign everywhere and its values in the 3dx band the step consumes."""
+    from flipengine3d_b200 import engine as fe
+    g = np.load(os.path.join(ROOT, "tests", "golden", fixture))
+    dx = 0.125
+    s = fe.static_inputs(n, n, n, dx, solid_phi=g["solid_phi"])
+    for c in "UVW":
+        assert np.array_equal(s["weight" + c], g["weight" + c]), c
+    assert np.array_equal(s["near_solid"].ravel(), g["near_solid"].ravel())
+    own = fe.static_inputs(n, n, n, dx)
+    assert np.array_equal(own["solid_phi"] < 0, g["solid_phi"] < 0)
+    band = np.abs(g["solid_phi"]) < 3 * dx
+    assert np.max(np.abs(own["solid_phi"][band] - g["solid_phi"][band])) < 1e-5
+    for c in "UVW":
+        assert np.max(np.abs(own["weight" + c] - g["weight" + c])) < 1e-4, c
+    assert np.array_equal(own["near_solid"].ravel(), g["near_solid"].ravel())
