@@ -161,7 +161,7 @@ def reference_arm(args, rank, world):
     v, ms, info = run_reference(args.ref_grid, args.steps, args.warmup, name=wl)
     grid_name = (f"{wl}256" if args.gpus == 1 else f"{wl}512") if args.workload is None else f"{args.workload}{args.grid}"
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32 fields / f64 PCG", "data": "synthetic",
             "config": {"workload": grid_name, "sample_grid": args.ref_grid, "dx": 0.125,
                        "frame_dt": FRAME_DT, "step": "one frame = FluidSimulation::update(1/30)"},
