@@ -5,17 +5,23 @@
 
 A "step" is one frame, FluidSimulation::update(1/30) (fluidsimulation.cpp:5755), i.e. all CFL
 substeps of the whole hot path (liquid SDF, P2G, extrapolation, body force, pressure projection,
-G2P, RK3 advection + collision + removal) over the synthetic sphere-drop scene of SURVEY §8d
-config 3 (256^3 grid, 16.1 M marker particles).  value = sum over timed substeps of live particles
-/ device time (CUDA events on the context's stream, max over ranks).
+G2P, RK3 advection + collision + removal).  Workload (pick_workload): on a 1-GPU box the synthetic
+sphere-drop scene of SURVEY §8d config 3 (256^3 grid, 16.1 M marker particles); for the scaling
+series -- N > 1 under torchrun, and N = 1 on a box that shows more than one GPU -- the dam break of
+config 5 (512^3, 127.9 M particles), the same fixed work at every N (strong scaling).  value = sum
+over timed substeps of live particles / device time (CUDA events on the context's stream, max over
+ranks).
 
 Our arm keeps the state resident in HBM for `value`; the `e2e` leg repeats the same frames through
 the C-ABI with HOST buffers: flip_set_particles (pinned host AoS -> device), flip_update,
-flip_get_particles (device -> pinned host AoS), every step, inside the timed region.
+flip_get_particles (device -> pinned host AoS), every step, inside the timed region.  With N > 1 the
+run starts with a slab-vs-single-GPU parity check of the same scene (`parity_ok` in the line).
 
 --impl reference times the UNMODIFIED reference engine (oracle/_ref/libflipref_fast.so, built by
-oracle/Makefile from /root/reference) on the host cores, all threads, on a bounded sample of the
-same workload.  This file and tests/ are the only places that may execute anything under oracle/.
+oracle/Makefile from /root/reference) on the host cores, all threads, on the SAME scene at full
+size; a 256^3 frame costs tens of CPU seconds, so the frame count is bounded by a wall-clock budget
+(the metric is per particle-substep).  This file and tests/ are the only places that may execute
+anything under oracle/.
 """
 import argparse
 import json
@@ -126,11 +132,35 @@ def workload(grid, name="spheredrop", krange=None):
     return scenes.sphere_drop(grid)
 
 
+def visible_gpus():
+    try:
+        import torch
+        return int(torch.cuda.device_count())
+    except Exception:
+        return 0
+
+
+def pick_workload(args, world):
+    """The workload of this run.  BENCH (a 1-GPU box): the single-GPU headline, spheredrop256.  The scaling series
+    (N = 1, 2, 4, 8 on ONE multi-GPU box) must be the same workload at every N, dambreak512 (BASELINE config 5),
+    so on a box that shows more than one GPU the N=1 run is that series' base point."""
+    if args.workload is not None:
+        return args.workload, args.grid, "given on the command line"
+    if world > 1:
+        return "dambreak", 512, "z-slab strong-scaling series"
+    if visible_gpus() > 1:
+        return "dambreak", 512, "N=1 point of the strong-scaling series (this box shows more than one GPU)"
+    return "spheredrop", 256, "single-GPU headline"
+
+
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the unmodified reference engine on the host cores
 # ------------------------------------------------------------------------------------------------
-def run_reference(grid, steps, warmup, threads=None, name="spheredrop"):
-    """Returns (particle_steps_per_s, ms_per_step, info). One step = one update(1/30)."""
+def run_reference(name, grid, steps, warmup, budget_s, threads=None):
+    """The reference engine's own update(1/30) on the SAME scene the GPU arm runs, all host threads.  A frame of the
+    256^3 scene costs tens of seconds of CPU, so the number of frames is bounded by `budget_s` of wall clock (at
+    least one warm-up and one timed frame); the metric is normalised per particle-substep, so it does not depend on
+    the frame count.  Returns (particle_steps_per_s, ms_per_frame, info)."""
     from oracle import refengine
     kind = "fast" if refengine.available("fast") else "golden"
     if not refengine.available(kind):
@@ -139,32 +169,46 @@ def run_reference(grid, steps, warmup, threads=None, name="spheredrop"):
     with quiet_stdout():
         ref = refengine.RefEngine(sc["dims"], sc["dx"], sc["pos"], sc["vel"], kind=kind, threads=threads)
         cores = ref.L.ref_get_threads()
-        for _ in range(warmup):
+        w_done, t_frame = 0, None
+        t_w0 = time.perf_counter()
+        while w_done < max(warmup, 0):
+            t0 = time.perf_counter()
             ref.update(FRAME_DT)
-        psteps, t0 = 0, time.perf_counter()
-        for _ in range(steps):
+            t_frame = time.perf_counter() - t0
+            w_done += 1
+            # warm-up may use up to 30 % of the budget
+            if time.perf_counter() - t_w0 + t_frame > 0.3 * budget_s:
+                break
+        psteps, frames, t0 = 0, 0, time.perf_counter()
+        while frames < max(steps, 1):
             n_before = ref.num_particles
+            t1 = time.perf_counter()
             ref.update(FRAME_DT)
+            t_frame = time.perf_counter() - t1
             psteps += n_before * max(ref.substeps, 1)
+            frames += 1
+            if time.perf_counter() - t0 + t_frame > 0.7 * budget_s:
+                break
         el = time.perf_counter() - t0
-    info = dict(kind="reference", cores=int(cores), build=kind,
-                substeps_per_frame=int(ref.substeps), sample=f"{name}{grid} ({sc['pos'].shape[0]} particles, same seeding rule as the GPU workload), "
-                       f"{steps} frame(s) of update(1/30) after {warmup} warm-up frame(s), surface reconstruction off")
+    info = dict(kind="reference", cores=int(cores), build=kind, frames_timed=frames, warmup_frames=w_done,
+                substeps_last_frame=int(ref.substeps),
+                sample=f"{name}{grid} ({sc['pos'].shape[0]} particles: the GPU arm's scene), {frames} frame(s) of update(1/30) "
+                       f"after {w_done} warm-up frame(s) (bounded by a {budget_s:.0f} s wall-clock budget), surface reconstruction off")
     ref.close()
-    return psteps / el, 1e3 * el / max(steps, 1), info
+    return psteps / el, 1e3 * el / frames, info
 
 
 def reference_arm(args, rank, world):
     if rank != 0:
         return
-    wl = args.workload or ("spheredrop" if args.gpus == 1 else "dambreak")
-    v, ms, info = run_reference(args.ref_grid, args.steps, args.warmup, name=wl)
-    grid_name = (f"{wl}256" if args.gpus == 1 else f"{wl}512") if args.workload is None else f"{args.workload}{args.grid}"
+    wl, grid, why = pick_workload(args, world)
+    v, ms, info = run_reference(wl, grid, args.steps, args.warmup, args.ref_budget)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32 fields / f64 PCG", "data": "synthetic",
-            "config": {"workload": grid_name, "sample_grid": args.ref_grid, "dx": 0.125,
-                       "frame_dt": FRAME_DT, "step": "one frame = FluidSimulation::update(1/30)"},
+            "config": {"workload": f"{wl}{grid}", "workload_choice": why, "same_config": True, "dx": 0.125, "frame_dt": FRAME_DT,
+                       "step": "one frame = FluidSimulation::update(1/30)", "frames_timed": info["frames_timed"],
+                       "warmup_frames": info["warmup_frames"]},
             "cpu_baseline": dict(info, value=v, unit=UNIT),
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -185,21 +229,24 @@ def liquid_face_count(phi):
 
 
 def algorithmic_bytes(Np, dims, n_rows, nf_liq):
-    """SURVEY §8d 'Algorithmic bytes' per launch of each kernel class."""
+    """SURVEY §8d 'Algorithmic bytes' per launch of each kernel class (DESIGN.md §4)."""
     I, J, K = dims
     Nc = I * J * K
     Nf = (I + 1) * J * K + I * (J + 1) * K + I * J * (K + 1)
+    P = 16 * n_rows                               # preconditioner data of level 0: 1/diag + three face weights, fp32
     return {
         "sdf_p2g": 24 * Np + 5 * Nf + 4 * Nc,     # fused liquid SDF + P2G: particles read once
         "g2p": 36 * Np + 8 * nf_liq,
         "advance": 24 * Np + 4 * nf_liq,
+        "g2p_advance": 48 * Np + 8 * nf_liq,      # fused G2P + RK3
         "extrapolate": 9 * Nf,                     # one extrapolateVelocityField call (3 components)
         "pcg_spmv": 36 * n_rows,
-        "pcg_iter": 124 * n_rows,                  # + P (preconditioner data) not credited
+        "precond": 16 * n_rows + P,                # V-cycle: r in, z out (fp64) + P; the coarse levels are not credited
+        "pcg_iter": 124 * n_rows + P,              # SpMV+dot 36n; x,r update 48n; precond 16n+P; direction 24n
     }
 
 
-def make_sim(args, wl_name, grid, rank, world, local_rank, dist):
+def make_sim(args, wl_name, grid, rank, world, local_rank, dist, ids=False):
     """One context per rank; with world > 1 the domain is split into z-slabs (flip_set_slab)."""
     from flipengine3d_b200 import engine as fe
     I = J = K = grid
@@ -207,6 +254,8 @@ def make_sim(args, wl_name, grid, rank, world, local_rank, dist):
     sim.addBodyForce(0.0, -25.0, 0.0)
     if args.preconditioner:
         sim.setPreconditioner(args.preconditioner)
+    if ids:
+        sim.enableParticleIds(True)
     krange = None
     if world > 1:
         ident = [fe.nccl_unique_id() if rank == 0 else None]
@@ -241,6 +290,70 @@ def timed_frames(sim, steps, stream, torch, barrier):
     return e0.elapsed_time(e1), psteps, substeps, pcg_iters, rows, stage_ms
 
 
+def slab_parity_check(args, wl_name, grid, rank, world, local_rank, dist, torch, frames=2):
+    """Before anything is timed on N > 1 GPUs: the z-slab run against the single-GPU run of the SAME scene (rank 0
+    runs the whole domain on its own GPU next to its slab).  Integer bookkeeping (substeps, particle count, pressure
+    rows, the set of particle ids) must be equal, per-particle positions rel-L2 <= 1e-4 (tests/parity_common.py).
+    Returns the report dict on rank 0, None elsewhere."""
+    dev = torch.device("cuda", local_rank)
+    sim, _ = make_sim(args, wl_name, grid, rank, world, local_rank, dist, ids=True)
+    single = None
+    if rank == 0:
+        single, _ = make_sim(args, wl_name, grid, 0, 1, local_rank, dist, ids=True)
+    rep = {"workload": f"{wl_name}{grid}", "frames": frames, "ok": True} if rank == 0 else None
+    for f in range(frames):
+        sim.update(FRAME_DT)
+        st = sim.substep_stats()
+        if rank == 0:
+            single.update(FRAME_DT)
+            rs = single.substep_stats()
+            same = (len(st) == len(rs) and [s["pressure_rows"] for s in st] == [s["pressure_rows"] for s in rs]
+                    and st[-1]["particles"] == rs[-1]["particles"])
+            rep["ok"] = bool(rep["ok"] and same)
+            rep[f"frame{f}"] = {"substeps": [len(st), len(rs)], "particles": [st[-1]["particles"], rs[-1]["particles"]],
+                                "rows": [[s["pressure_rows"] for s in st], [s["pressure_rows"] for s in rs]],
+                                "pcg_iterations": [[s["pcg_iterations"] for s in st], [s["pcg_iterations"] for s in rs]]}
+    # per-particle comparison after the last frame: every rank's (particles, ids) to rank 0 through NCCL
+    p = torch.from_numpy(sim.getMarkerParticles().copy()).to(dev)
+    ids = torch.from_numpy(sim.getParticleIds().astype(np.int64)).to(dev)
+    counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(counts, torch.tensor([p.shape[0]], dtype=torch.int64, device=dev))
+    if rank == 0:
+        P, IDS = [p], [ids]
+        for r in range(1, world):
+            n = int(counts[r].item())
+            bp = torch.empty((n, 6), dtype=torch.float32, device=dev)
+            bi = torch.empty((n,), dtype=torch.int64, device=dev)
+            dist.recv(bp, src=r)
+            dist.recv(bi, src=r)
+            P.append(bp); IDS.append(bi)
+        P, IDS = torch.cat(P), torch.cat(IDS)
+        R = torch.from_numpy(single.getMarkerParticles().copy()).to(dev)
+        RID = torch.from_numpy(single.getParticleIds().astype(np.int64)).to(dev)
+        same_ids = P.shape[0] == R.shape[0]
+        if same_ids:
+            o, ro = torch.argsort(IDS), torch.argsort(RID)
+            same_ids = bool(torch.equal(IDS[o], RID[ro]))
+        rep["same_ids"] = bool(same_ids)
+        rep["local_counts"] = [int(c.item()) for c in counts]
+        if same_ids:
+            a, b = P[o, :3].double(), R[ro, :3].double()
+            rep["pos_rel_l2"] = float(torch.linalg.norm(a - b) / torch.linalg.norm(b))
+            rep["pos_max_abs"] = float((a - b).abs().max())
+            rep["ok"] = bool(rep["ok"] and rep["pos_rel_l2"] <= 1e-4 and rep["pos_max_abs"] <= 1e-3 * 0.125)
+        else:
+            rep["ok"] = False
+        single.close()
+    else:
+        dist.send(p, dst=0)
+        dist.send(ids, dst=0)
+    sim.close()
+    del sim, p, ids
+    torch.cuda.empty_cache()
+    dist.barrier()
+    return rep
+
+
 def ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -250,9 +363,7 @@ def ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    wl_name, grid = args.workload, args.grid
-    if wl_name is None:
-        wl_name, grid = ("spheredrop", 256) if world == 1 else ("dambreak", 512)
+    wl_name, grid, why = pick_workload(args, world)
 
     def maxreduce(x):
         t = torch.tensor([x], dtype=torch.float64, device="cuda")
@@ -265,6 +376,10 @@ def ours(args, rank, world, local_rank):
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
+
+    parity = None
+    if world > 1 and args.parity_check:
+        parity = slab_parity_check(args, wl_name, grid, rank, world, local_rank, dist, torch, frames=args.parity_frames)
 
     sim, sc = make_sim(args, wl_name, grid, rank, world, local_rank, dist)
     I, J, K = sc["dims"]
@@ -320,6 +435,18 @@ def ours(args, rank, world, local_rank):
     h2d_all, d2h_all = sumreduce(float(h2d)), sumreduce(float(d2h))
     Np = int(sumreduce(float(Np_local)))
 
+    # ---- the same frames with the reference's literal arithmetic everywhere (FLIP_SAMPLING_EXACT: double-precision
+    # trilinear blend in G2P / RK3, literal P2G weights) for the number beside the default single-precision blend
+    exact = None
+    if args.exact_steps > 0:
+        sim.setSamplingMode("exact")
+        sim.update(FRAME_DT)
+        ms_x, ps_x, sub_x, _, _, _ = timed_frames(sim, args.exact_steps, stream, torch, barrier)
+        ms_x = maxreduce(ms_x)
+        exact = {"sampling_mode": "exact", "value": ps_x / (ms_x * 1e-3), "unit": UNIT, "ms_per_step": ms_x / args.exact_steps,
+                 "steps": args.exact_steps, "substeps_timed": sub_x}
+        sim.setSamplingMode("fast")
+
     line = None
     if rank == 0:
         peak, peak_kind = measured_hbm_peak()
@@ -337,17 +464,24 @@ def ours(args, rank, world, local_rank):
                     gbs = ab[name] / (avg_ms * 1e-3) / 1e9
                     ent.update(algorithmic_bytes=int(ab[name]), achieved_gbs=gbs, frac=gbs / peak)
                 kernels[name] = ent
-            # the dominant kernel: largest share of the step among single-kernel classes
-            singles = [k for k in ("sdf_p2g", "g2p", "advance", "pcg_spmv") if k in kernels]
-            dom = max(singles, key=lambda k: kernels[k]["total_ms"])
+            # the dominant kernel class: the largest share of the step over ALL classes that have an algorithmic-bytes
+            # figure (pcg_iter = one PCG iteration, i.e. SpMV + update + V-cycle + direction; it contains pcg_spmv and
+            # precond, which are also listed on their own)
+            cands = [k for k in kernels if "algorithmic_bytes" in kernels[k]]
+            dom = max(cands, key=lambda k: kernels[k]["total_ms"])
             roof = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["achieved_gbs"], "peak": peak,
                     "peak_kind": peak_kind, "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": None,
                     "algorithmic_bytes": kernels[dom]["algorithmic_bytes"], "avg_launch_ms": kernels[dom]["avg_ms"],
                     "share_of_step": kernels[dom]["share_of_step"]}
+            # DRAM bytes per launch come from an `ncu --set full` capture of THIS revision when one is committed
+            # (profiles/traffic.json names the capture); never from the run itself (ncu-timed runs are not bench values)
             tp_file = os.path.join(ROOT, "profiles", "traffic.json")
             if os.path.exists(tp_file):
                 try:
-                    roof["traffic"] = json.load(open(tp_file)).get(dom)
+                    tj = json.load(open(tp_file))
+                    if tj.get("workload") == f"{wl_name}{grid}" and dom in tj.get("per_launch_bytes", {}):
+                        roof["traffic"] = tj["per_launch_bytes"][dom]
+                        roof["traffic_source"] = tj.get("source")
                 except Exception:
                     pass
         else:
@@ -358,42 +492,31 @@ def ours(args, rank, world, local_rank):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32 fields / f64 PCG vectors", "data": "synthetic",
-                "config": {"workload": f"{wl_name}{grid}", "grid": [I, J, K], "dx": 0.125, "particles": Np,
+                "config": {"workload": f"{wl_name}{grid}", "workload_choice": why, "grid": [I, J, K], "dx": 0.125, "particles": Np,
                            "frame_dt": FRAME_DT, "step": "one frame = flip_update(1/30), all CFL substeps",
-                           "substeps_timed": substeps, "pcg_iterations_timed": pcg_iters, "pressure_rows": n_rows,
-                           "parallelism": "single GPU" if world == 1 else f"{world} z-slabs (one process per GPU, NCCL halo exchange, distributed PCG)",
-                           "l2": "inputs larger than L2 (particles and each MAC field exceed the 126 MB L2)",
-                           "note": "N=1 runs the single-GPU headline config (spheredrop256); N>1 runs dambreak512 split into "
-                                   "z-slabs (fixed total work); the N=1 point of that series is in scaling_ref"},
+                           "substeps_timed": substeps, "ms_per_substep": ms_max / max(substeps, 1),
+                           "pcg_iterations_timed": pcg_iters, "pressure_rows": n_rows,
+                           "sampling_mode": "fast (single-precision 8-point blend in G2P / RK3 and packed P2G weights; indices and "
+                                            "weights exact; the reference blends in double) -- see exact_mode for the literal arithmetic",
+                           "parallelism": "single GPU" if world == 1 else f"{world} z-slabs (one process per GPU, NVLink halo exchange, distributed PCG)",
+                           "l2": "inputs larger than L2 (particles and each MAC field exceed the 126 MB L2)"},
                 "roofline": roof, "kernels": kernels, "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_all) // args.steps,
                         "d2h_bytes_per_step": int(d2h_all) // args.steps, "ms_per_step": 1e3 * e2e_s / args.steps},
-                "gpu_launches": int(launches_all), "clocks": clocks}
+                "exact_mode": exact, "gpu_launches": int(launches_all), "clocks": clocks}
+        if parity is not None:
+            line["parity_ok"] = bool(parity["ok"])
+            line["parity"] = parity
     sim.close()
     del sim
 
-    # ---- N=1 only: the single-GPU point of the 512^3 strong-scaling series, and the CPU baseline
-    if world == 1 and rank == 0:
-        if args.scaling_ref and args.workload is None:
-            try:
-                sim2, sc2 = make_sim(args, "dambreak", 512, 0, 1, local_rank, dist)
-                stream2 = torch.cuda.ExternalStream(sim2.stream(), device=torch.device("cuda", local_rank))
-
-                def barrier2():
-                    sim2.synchronize()
-                    torch.cuda.synchronize()
-                for _ in range(3):
-                    sim2.update(FRAME_DT)
-                ms2, ps2, sub2, it2, rows2, _ = timed_frames(sim2, args.ref_steps, stream2, torch, barrier2)
-                line["scaling_ref"] = {"workload": "dambreak512", "n_gpus": 1, "value": ps2 / (ms2 * 1e-3), "unit": UNIT,
-                                       "ms_per_step": ms2 / args.ref_steps, "steps": args.ref_steps, "warmup": 3,
-                                       "particles": int(sim2.getNumMarkerParticles()), "pcg_iterations_timed": it2}
-                sim2.close()
-            except Exception as e:
-                line["scaling_ref"] = {"workload": "dambreak512", "error": str(e)[:200]}
+    # ---- N=1 only: the CPU baseline (the reference engine on this box's host cores), on the same scene where a frame
+    # of it fits the bounded sample, else on the same scene at half the resolution (said so in `sample`)
+    if world == 1 and rank == 0 and args.cpu_budget > 0:
         try:
-            v, cms, info = run_reference(args.ref_grid, args.cpu_steps, 1)
-            line["cpu_baseline"] = dict(info, value=v, unit=UNIT, ms_per_step=cms)
+            same = grid <= 256
+            v, cms, info = run_reference(wl_name, grid if same else 256, 1, 1 if grid <= 128 else 0, args.cpu_budget)
+            line["cpu_baseline"] = dict(info, value=v, unit=UNIT, ms_per_step=cms, same_config=same)
         except Exception as e:   # the oracle always exists on the GPU box; report loudly if not
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"FAILED: {e}"}
     if rank == 0:
@@ -410,14 +533,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, choices=[None, "spheredrop", "dambreak"],
-                    help="default: spheredrop256 on 1 GPU, dambreak512 in z-slabs on N > 1")
+                    help="default: spheredrop256 on a 1-GPU box; dambreak512 for the scaling series (N > 1, or N = 1 on a multi-GPU box)")
     ap.add_argument("--grid", type=int, default=256, help="grid size when --workload is given")
-    ap.add_argument("--no-scaling-ref", dest="scaling_ref", action="store_false",
-                    help="skip the single-GPU dambreak512 point of the strong-scaling series (N=1 runs only)")
-    ap.add_argument("--ref-steps", type=int, default=4, help="timed frames of that reference point")
-    ap.add_argument("--ref-grid", type=int, default=128,
-                    help="grid of the bounded CPU sample of the same workload (reference arm / cpu_baseline)")
-    ap.add_argument("--cpu-steps", type=int, default=10, help="frames of the cpu_baseline sample in our arm (about 1 s each on 16 cores)")
+    ap.add_argument("--ref-budget", type=float, default=240.0,
+                    help="wall-clock budget (s) of the reference arm's frames (the scene is the GPU arm's, at full size)")
+    ap.add_argument("--cpu-budget", type=float, default=30.0,
+                    help="wall-clock budget (s) of the cpu_baseline sample inside our arm (0: skip)")
+    ap.add_argument("--exact-steps", type=int, default=3, help="frames timed in FLIP_SAMPLING_EXACT beside the default mode (0: skip)")
+    ap.add_argument("--no-parity-check", dest="parity_check", action="store_false",
+                    help="N > 1: skip the slab-vs-single-GPU parity check that precedes the timing")
+    ap.add_argument("--parity-frames", type=int, default=2)
     ap.add_argument("--preconditioner", default=None)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

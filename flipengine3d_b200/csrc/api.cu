@@ -227,8 +227,15 @@ int flip_set_pic_flip_ratio(flip_ctx *c, double r) {
 int flip_set_cfl(flip_ctx *c, double cfl) {
     return guarded(c, [&] {
         if (cfl < 1.0) throw ApiError(FLIP_ERR_DOMAIN, "Error: CFL must be greater than or equal to 1.");
+        const double oldCfl = c->CFL;
+        const int oldLayers = c->extrapolationLayers;
         c->CFL = cfl;
         c->extrapolationLayers = (int)ceil(cfl) + 2;
+        if (slab_on(c) && c->halo < slab_required_halo(c)) {
+            c->CFL = oldCfl; c->extrapolationLayers = oldLayers;
+            throw ApiError(FLIP_ERR_DOMAIN, "Error: this CFL number needs more z-slab halo planes than flip_set_halo configured "
+                                            "(ceil(CFL) + 1 + extrapolation layers + 1).");
+        }
     });
 }
 int flip_set_substep_limits(flip_ctx *c, int mn, int mx) {
@@ -675,6 +682,9 @@ int flip_set_slab(flip_ctx *c, int rank, int nranks, const void *id, int idBytes
         int k0 = 0, k1 = 0;
         flip_slab_range(Kg, nranks, rank, &k0, &k1);
         if ((Kg / nranks) < H) throw ApiError(FLIP_ERR_DOMAIN, "z-slabs thinner than the halo width");
+        if (H < slab_required_halo(c))
+            throw ApiError(FLIP_ERR_DOMAIN, "z-slab halo narrower than the particle reach plus the extrapolation depth "
+                                            "(ceil(CFL) + 1 + extrapolation layers + 1 planes): call flip_set_halo first");
         const int lo = rank > 0 ? H : 0, hi = rank < nranks - 1 ? H : 0;
         c->comm = comm_create(rank, nranks, id, idBytes);
         c->rank = rank; c->nranks = nranks;
@@ -741,7 +751,10 @@ int flip_get_slab_info(const flip_ctx *c, int *kOff, int *Klocal, int *kOwn0, in
 }
 int flip_set_halo(flip_ctx *c, int planes) {
     return guarded(c, [&] {
-        if (planes < 16) throw ApiError(FLIP_ERR_DOMAIN, "the halo must cover the RK3 reach plus the extrapolation depth (>= 16 planes)");
+        if (c->nranks > 1) throw ApiError(FLIP_ERR_RUNTIME, "flip_set_halo must precede flip_set_slab");
+        if (planes < slab_required_halo(c))
+            throw ApiError(FLIP_ERR_DOMAIN, "the halo must cover the RK3 reach plus the extrapolation depth "
+                                            "(ceil(CFL) + 1 + extrapolation layers + 1 planes)");
         c->halo = planes;
     });
 }

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <cmath>
 #include <string>
 #include <vector>
 #include "../../include/flip_b200.h"
@@ -80,6 +81,9 @@ struct DeviceScalars {
     int globalRows;
     int extCount[6];           // extrapolation frontier sizes, [component][parity]
     int deferredCount;         // particles the single-precision G2P / RK3 kernels left to the literal ones
+    int slabError[3];          // z-slab exchange: [0] an emigrant jumped past the neighbouring slab, [1] a send buffer
+                               // overflowed, [2] an RK3 sample left the halo planes; summed over the ranks before
+                               // anybody acts on them
     // multigrid coarse solve etc.
     int pad[8];
 };
@@ -282,5 +286,9 @@ inline size_t ext_stride(const Dims &d) {
     return ((m + 63) / 64 + 1) * 64;
 }
 inline bool slab_on(const flip_ctx *c) { return c->nranks > 1; }
+// Halo planes a z-slab needs towards a neighbour: an owned particle travels up to ceil(CFL) cells in a substep and its
+// RK3 / G2P stencils reach one plane further; the redundantly extrapolated field of a slab is contaminated from its
+// local boundary plane inwards by one plane per extrapolation layer (the boundary counts as a border face there)
+inline int slab_required_halo(const flip_ctx *c) { return (int)ceil(c->CFL) + 1 + c->extrapolationLayers + 1; }
 
 }  // namespace flip

@@ -1169,20 +1169,30 @@ __device__ __forceinline__ void rk3_combine(const AdvectParams &a, float x, floa
     nx = fadd(x, fmul(sx, a.c3)); ny = fadd(y, fmul(sy, a.c3)); nz = fadd(z, fmul(sz, a.c3));
 }
 
+// z-slab: a sample position whose stencil would leave the local planes towards a neighbouring slab (not towards the
+// wall of the domain) reads zeros there; report it instead (DeviceScalars::slabError[2], acted on after the
+// migration exchange), the halo was sized for CFL-bounded substeps
+__device__ __forceinline__ bool leaves_halo(const AdvectParams &a, float z) {
+    const int kl = pos2idx(z, a.invdx) - a.G.kOff;
+    return (kl < 1 && a.G.kOff > 0) || (kl > a.G.K - 2 && a.G.kOff + a.G.K < a.G.Kg);
+}
+
 // literal sampling; list as in k_g2p
 __global__ void k_advance(ParticleSoA p, AdvectParams a, MacField f, const float *__restrict__ phiS,
                           const unsigned char *__restrict__ ns, const int *__restrict__ list,
-                          const int *__restrict__ listCount) {
+                          const int *__restrict__ listCount, DeviceScalars *S) {
     const int n = list ? *listCount : a.n;
+    const bool slab = a.G.K != a.G.Kg;
     for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
         const int t = list ? list[q] : q;
         float x = p.px[t], y = p.py[t], z = p.pz[t];
         float k1x, k1y, k1z, k2x, k2y, k2z, k3x, k3y, k3z;
         sample_velocity(f, a.G, a.dx, a.invdx, a.hdx, x, y, z, k1x, k1y, k1z);
-        sample_velocity(f, a.G, a.dx, a.invdx, a.hdx, fadd(x, fmul(k1x, a.c1)), fadd(y, fmul(k1y, a.c1)),
-                        fadd(z, fmul(k1z, a.c1)), k2x, k2y, k2z);
-        sample_velocity(f, a.G, a.dx, a.invdx, a.hdx, fadd(x, fmul(k2x, a.c2)), fadd(y, fmul(k2y, a.c2)),
-                        fadd(z, fmul(k2z, a.c2)), k3x, k3y, k3z);
+        const float z2 = fadd(z, fmul(k1z, a.c1));
+        sample_velocity(f, a.G, a.dx, a.invdx, a.hdx, fadd(x, fmul(k1x, a.c1)), fadd(y, fmul(k1y, a.c1)), z2, k2x, k2y, k2z);
+        const float z3 = fadd(z, fmul(k2z, a.c2));
+        sample_velocity(f, a.G, a.dx, a.invdx, a.hdx, fadd(x, fmul(k2x, a.c2)), fadd(y, fmul(k2y, a.c2)), z3, k3x, k3y, k3z);
+        if (slab && (leaves_halo(a, z) || leaves_halo(a, z2) || leaves_halo(a, z3))) S->slabError[2] = 1;
         float nx, ny, nz;
         rk3_combine(a, x, y, z, k1x, k1y, k1z, k2x, k2y, k2z, k3x, k3y, k3z, nx, ny, nz);
         resolve_collision(a, phiS, ns, x, y, z, nx, ny, nz);
@@ -1299,10 +1309,10 @@ void stage_advance(flip_ctx *c, double dt) {
             int *deferred = c->sortIdx, *cnt = &c->dS->deferredCount;
             FLIP_CUDA_CHECK(cudaMemsetAsync(cnt, 0, sizeof(int), c->stream));
             k_advance_fast<<<cdiv(c->np, TPB), TPB, 0, c->stream>>>(P, a, fn, c->phiS, c->nearSolid, deferred, cnt);
-            k_advance<<<148, TPB, 0, c->stream>>>(P, a, fn, c->phiS, c->nearSolid, deferred, cnt);
+            k_advance<<<148, TPB, 0, c->stream>>>(P, a, fn, c->phiS, c->nearSolid, deferred, cnt, c->dS);
             c->launches++;
         } else {
-            k_advance<<<cdiv(c->np, TPB), TPB, 0, c->stream>>>(P, a, fn, c->phiS, c->nearSolid, nullptr, nullptr);
+            k_advance<<<cdiv(c->np, TPB), TPB, 0, c->stream>>>(P, a, fn, c->phiS, c->nearSolid, nullptr, nullptr, c->dS);
         }
         kt_end(c, FLIP_KERNEL_ADVANCE, kt);
         c->launches++;

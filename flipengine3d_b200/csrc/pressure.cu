@@ -1832,6 +1832,10 @@ void pressure_free(flip_ctx *c) {
     cudaFree(c->segCell); cudaFree(c->segMask); cudaFree(c->Adiag);
     cudaFree(c->AoffU); cudaFree(c->AoffV); cudaFree(c->AoffW);
     cudaFree(c->vx_); cudaFree(c->vr); cudaFree(c->vs); cudaFree(c->vz); cudaFree(c->vb);
+    // (a failed re-allocation in flip_set_slab must not leave pointers that flip_destroy would free again)
+    c->segCell = nullptr; c->segMask = nullptr; c->Adiag = nullptr;
+    c->AoffU = c->AoffV = c->AoffW = nullptr;
+    c->vx_ = c->vr = c->vs = c->vz = c->vb = nullptr;
     if (c->mg) {
         PressureScratch *ps = (PressureScratch *)c->mg;
         cudaFree(ps->maskAll); cudaFree(ps->maskPrev); cudaFree(ps->flagAll); cudaFree(ps->posAll); cudaFree(ps->pool); cudaFree(ps->gpool);

@@ -23,6 +23,7 @@ __global__ void k_slab_ghost_counts(const int *__restrict__ cellStart, int IJ, i
     S->sendCount[1] = hasHi ? cellStart[kOwn1 * IJ] - cellStart[(kOwn1 - halo) * IJ] : 0;
     S->recvCount[0] = 0;
     S->recvCount[1] = 0;
+    S->slabError[0] = S->slabError[1] = S->slabError[2] = 0;
 }
 
 static void exchange_counts(flip_ctx *c) {
@@ -38,6 +39,9 @@ static void exchange_counts(flip_ctx *c) {
         comm_recv(c->comm, &c->dS->recvCount[1], sizeof(int), c->rank + 1, st);
     }
     comm_group_end(c->comm);
+    // an error seen by one rank (slabError != 0) must stop ALL ranks at the same point of the exchange sequence:
+    // a rank that threw on its own would leave its neighbours waiting in the next send/recv group for ever
+    comm_allreduce(c->comm, c->dS->slabError, 3, COMM_SUM_I32, st);
     scalars_to_host(c);
 }
 
@@ -154,15 +158,18 @@ void slab_exchange_ghosts(flip_ctx *c) {
 }
 
 // Owned particles whose new plane belongs to a neighbour are appended (unordered) to the send buffers.
+// reachLo / reachHi: thickness of the lower / upper neighbour's slab -- a particle that lands beyond it would have to
+// go to a rank this exchange does not talk to; that is reported (slabError[0]), never dropped silently.
 __global__ void k_slab_pack_emigrants(ParticleSoA p, const int *__restrict__ ids, int n, double invdx, int kOff, int kOwn0,
-                                      int kOwn1, float *lo, float *hi, int cap, DeviceScalars *S) {
+                                      int kOwn1, int reachLo, int reachHi, float *lo, float *hi, int cap, DeviceScalars *S) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     int kl = pos2idx(p.pz[t], invdx) - kOff;
     int side = (kl < kOwn0) ? 0 : (kl >= kOwn1 ? 1 : -1);
     if (side < 0) return;
+    if ((side == 0 && kl < kOwn0 - reachLo) || (side == 1 && kl >= kOwn1 + reachHi)) S->slabError[0] = 1;
     int slot = atomicAdd(&S->sendCount[side], 1);
-    if (slot >= cap) return;     // overflow is detected on the host from the count
+    if (slot >= cap) { S->slabError[1] = 1; return; }
     float *b = side ? hi : lo;
     b[slot] = p.px[t];
     b[(size_t)cap + slot] = p.py[t];
@@ -176,6 +183,7 @@ __global__ void k_slab_pack_emigrants(ParticleSoA p, const int *__restrict__ ids
 __global__ void k_slab_reset_counts(DeviceScalars *S) {
     S->sendCount[0] = S->sendCount[1] = 0;
     S->recvCount[0] = S->recvCount[1] = 0;
+    S->slabError[0] = S->slabError[1] = 0;      // [2] is set by the advance kernels that ran just before
 }
 
 void slab_drop_ghosts_and_migrate(flip_ctx *c) {
@@ -183,29 +191,47 @@ void slab_drop_ghosts_and_migrate(flip_ctx *c) {
     cudaStream_t st = c->stream;
     const bool hasLo = c->rank > 0, hasHi = c->rank < c->nranks - 1;
     const int n = c->np;      // owned, at [ownedBegin, ownedEnd)
-    int wantCap = std::max(1 << 16, c->capacity / 8);
-    if (wantCap > c->sendCap) {
-        for (int s = 0; s < 2; s++) {
-            cudaFree(c->sendBuf[s]);
-            c->sendBuf[s] = nullptr;
-            FLIP_CUDA_CHECK(cudaMalloc(&c->sendBuf[s], sizeof(float) * 7ull * wantCap));
+    int wantCap = std::max(std::max(1 << 16, c->capacity / 8), c->sendCap);
+    // thickness of the neighbouring slabs (global planes): how far an emigrant may land
+    int reachLo = 0, reachHi = 0;
+    {
+        int a = 0, b = 0;
+        if (hasLo) { flip_slab_range(d.Kg, c->nranks, c->rank - 1, &a, &b); reachLo = b - a; }
+        if (hasHi) { flip_slab_range(d.Kg, c->nranks, c->rank + 1, &a, &b); reachHi = b - a; }
+    }
+    int sendLo = 0, sendHi = 0, recvLo = 0, recvHi = 0;
+    for (int attempt = 0;; attempt++) {
+        if (wantCap > c->sendCap) {
+            for (int s = 0; s < 2; s++) {
+                cudaFree(c->sendBuf[s]);
+                c->sendBuf[s] = nullptr;
+                FLIP_CUDA_CHECK(cudaMalloc(&c->sendBuf[s], sizeof(float) * 7ull * wantCap));
+            }
+            c->sendCap = wantCap;
         }
-        c->sendCap = wantCap;
+        k_slab_reset_counts<<<1, 1, 0, st>>>(c->dS); c->launches++;
+        if (n > 0) {
+            ParticleSoA p = c->P[c->cur_buf];
+            p.px += c->ownedBegin; p.py += c->ownedBegin; p.pz += c->ownedBegin;
+            p.vx += c->ownedBegin; p.vy += c->ownedBegin; p.vz += c->ownedBegin;
+            k_slab_pack_emigrants<<<cdiv(n, TPB), TPB, 0, st>>>(p, c->trackIds ? c->pid[c->cur_buf] + c->ownedBegin : nullptr, n,
+                                                               1.0 / d.dx, d.kOff, d.kOwn0, d.kOwn1, reachLo, reachHi,
+                                                               c->sendBuf[0], c->sendBuf[1], c->sendCap, c->dS);
+            c->launches++;
+        }
+        exchange_counts(c);     // also sums slabError over the ranks: every rank takes the same branch below
+        sendLo = c->hS->sendCount[0]; sendHi = c->hS->sendCount[1];
+        recvLo = c->hS->recvCount[0]; recvHi = c->hS->recvCount[1];
+        if (c->hS->slabError[2])
+            throw ApiError(FLIP_ERR_DOMAIN, "z-slab advection: a particle's RK3 sample left the halo planes (substep longer than the "
+                                            "CFL bound the halo was sized for): raise flip_set_halo or lower the frame time");
+        const int jumped = c->hS->slabError[0], overflowed = c->hS->slabError[1];
+        if (!jumped && !overflowed) break;
+        // some rank's buffer overflowed (and nothing worse): every rank grows its buffers and packs again
+        if (!jumped && attempt < 8) { wantCap = c->sendCap * 2; continue; }
+        throw ApiError(FLIP_ERR_DOMAIN, "z-slab migration: a particle crossed more than one slab in a substep (slabs thinner than "
+                                        "the particle reach), or the migration buffers could not be grown");
     }
-    k_slab_reset_counts<<<1, 1, 0, st>>>(c->dS); c->launches++;
-    if (n > 0) {
-        ParticleSoA p = c->P[c->cur_buf];
-        p.px += c->ownedBegin; p.py += c->ownedBegin; p.pz += c->ownedBegin;
-        p.vx += c->ownedBegin; p.vy += c->ownedBegin; p.vz += c->ownedBegin;
-        k_slab_pack_emigrants<<<cdiv(n, TPB), TPB, 0, st>>>(p, c->trackIds ? c->pid[c->cur_buf] + c->ownedBegin : nullptr, n,
-                                                           1.0 / d.dx, d.kOff, d.kOwn0, d.kOwn1, c->sendBuf[0],
-                                                           c->sendBuf[1], c->sendCap, c->dS);
-        c->launches++;
-    }
-    exchange_counts(c);
-    const int sendLo = c->hS->sendCount[0], sendHi = c->hS->sendCount[1];
-    const int recvLo = c->hS->recvCount[0], recvHi = c->hS->recvCount[1];
-    if (sendLo > c->sendCap || sendHi > c->sendCap) throw CudaError("z-slab migration buffer overflow");
     const int total = n + recvLo + recvHi;
     particles_alloc(c, c->ownedBegin + total);
     SoAPtrs P = ptrs_of(c, c->cur_buf);

@@ -1,5 +1,7 @@
-"""N-GPU z-slab run vs the single-GPU run of the same scene (launch with torchrun, one rank per GPU).
-Rank 0 also runs the whole domain on its own GPU and compares counts (exact) and per-particle state."""
+"""N-GPU z-slab run vs the single-GPU run of the same scene AND vs the unmodified reference engine (launch with
+torchrun, one rank per GPU).  Rank 0 also runs the whole domain on its own GPU, and -- when oracle/_ref is built -- the
+reference engine on the host (free-running update(1/30), golden build), and compares counts (exact) and per-particle
+state (positions rel-L2 <= 1e-4) frame by frame.  Test infrastructure: the oracle is only the checker here."""
 import os
 import sys
 
@@ -8,6 +10,9 @@ import numpy as np
 import torch
 import torch.distributed as dist
 from flipengine3d_b200 import scenes, engine as fe
+from oracle import refengine
+
+ORACLE_FRAMES = 6     # free-running trajectories drift apart chaotically; the first frames are comparable per particle
 
 
 def main():
@@ -31,7 +36,10 @@ def main():
     sim.setSlab(rank, world, ident[0])
     sim.loadMarkerParticleData(fe.MarkerParticleData(sc["pos"], sc["vel"]))
     sim.initialize()
-    ref = None
+    ref, orc = None, None
+    if rank == 0 and refengine.available("golden") and os.environ.get("SLAB_CHECK_ORACLE", "1") != "0":
+        orc = refengine.RefEngine(sc["dims"], sc["dx"], sc["pos"], sc["vel"], kind="golden")
+    n0 = sc["pos"].shape[0]
     if rank == 0:
         ref = fe.FluidSimulation(I, J, K, sc["dx"], device=lr)
         ref.addBodyForce(0, -25, 0)
@@ -63,9 +71,21 @@ def main():
                 line["vel_max_abs"] = float(np.abs(a[:, 3:] - b[:, 3:]).max())
                 ok &= line["pos_rel_l2"] <= 1e-4
             ok &= same_ids and line["rows"][0] == line["rows"][1] and len(st) == len(rs)
+            if orc is not None and f < ORACLE_FRAMES:
+                orc.update(1 / 30)
+                o = {"substeps": orc.substeps, "particles": orc.num_particles, "fluid_cells": orc.num_fluid_cells}
+                ok &= o["substeps"] == len(st) and o["particles"] == st[-1]["particles"] and o["fluid_cells"] == st[-1]["pressure_rows"]
+                if o["particles"] == n0 and P.shape[0] == n0:
+                    # nothing was removed so far: the reference keeps its particles in input order (= id)
+                    op = orc.particles()
+                    a = P[order]
+                    o["pos_rel_l2"] = float(np.linalg.norm(a[:, :3] - op[:, :3]) / np.linalg.norm(op[:, :3]))
+                    o["pos_max_abs"] = float(np.abs(a[:, :3] - op[:, :3]).max())
+                    ok &= o["pos_rel_l2"] <= 1e-4
+                line["oracle"] = o
             print(line, flush=True)
     if rank == 0:
-        print("SLAB_CHECK", "OK" if ok else "FAILED", flush=True)
+        print("SLAB_CHECK", "OK" if ok else "FAILED", "(oracle compared)" if orc is not None else "(oracle/_ref not built: single-GPU only)", flush=True)
     dist.barrier()
     sim.close()
     dist.destroy_process_group()

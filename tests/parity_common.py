@@ -185,8 +185,27 @@ def lockstep_substep(ref, gpu, dt, isolate=True, report=None):
     return rep
 
 
+def developed_scene(scene, frames, preconditioner=None):
+    """The scene after `frames` free-running frames of the CUDA engine: a developed flow (splash, waves, particles
+    against the walls) as the starting state of a lock-step comparison, at sizes where stepping the CPU oracle
+    that far would take minutes."""
+    I, J, K = scene["dims"]
+    sim = fe.FluidSimulation(I, J, K, scene["dx"])
+    sim.addBodyForce(0.0, -25.0, 0.0)
+    if preconditioner is not None:
+        sim.setPreconditioner(preconditioner)
+    sim.loadMarkerParticleData(fe.MarkerParticleData(scene["pos"], scene["vel"]))
+    sim.initialize()
+    for _ in range(frames):
+        sim.update(1.0 / 30.0)
+    p = sim.getMarkerParticles().copy()
+    sim.close()
+    return dict(scene, name=f"{scene['name']}+{frames}f", pos=np.ascontiguousarray(p[:, :3]), vel=np.ascontiguousarray(p[:, 3:]))
+
+
 def lockstep_frames(scene, frames=1, isolate=True, tol=None, threads=None, preconditioner=None, verbose=False,
-                    sampling=None):
+                    sampling=None, max_substeps=None):
+    """max_substeps: stop after that many lock-step substeps in total (the large scenes cost tens of CPU seconds each)."""
     ref, gpu = make_pair(scene, tol=tol, threads=threads, preconditioner=preconditioner, sampling=sampling)
     reports = []
     for f in range(frames):
@@ -194,6 +213,8 @@ def lockstep_frames(scene, frames=1, isolate=True, tol=None, threads=None, preco
         gpu.begin_frame(1.0 / 30.0)
         more = True
         while more:
+            if max_substeps is not None and len(reports) >= max_substeps:
+                break
             dt = ref.begin_substep()
             gpu.begin_substep()   # bookkeeping only; the oracle's dt is used for both
             rep = {"frame": f, "dt": dt}

@@ -398,6 +398,37 @@ def test_run_to_run_determinism():
     assert pc.rel_l2(outs[0][0][:, :3], outs[1][0][:, :3]) <= 1e-6
 
 
+# ---------------------------------------------------------------- lock-step at the BASELINE sizes
+@needs_ref
+def test_lockstep_dambreak128_developed_flow():
+    """BASELINE config 2 (128^3, 1 998 848 particles) in the engine's default mode (single-precision sampling, multigrid
+    PCG) against the unmodified reference, stage by stage from identical state, starting from the flow after 10 frames
+    (the column has collapsed along the floor and hit the far wall).  ~2 M particles is ten times the 208 333 entries
+    after which FragmentedVector::operator[] aliases (fragmentedvector.h:141-153): the inputs are the oracle's logical
+    view, and the survivors' count / the per-cell cap run over the real particle density."""
+    sc = pc.developed_scene(scenes.dam_break(128), 10)
+    assert sc["pos"].shape[0] > 1990000
+    reps = pc.lockstep_frames(sc, frames=1, isolate=True, max_substeps=2)
+    assert reps
+    for rep in reps:
+        pc.check_report(rep, dx=sc["dx"], isolate=True, exact_sampling=False)
+        assert rep["gpu.pressure_rows"] == rep["ref.fluid_cells"] > 200000
+
+
+@needs_ref
+def test_lockstep_spheredrop256_headline_substep():
+    """The headline configuration (BASELINE config 3: 256^3, 16.1 M particles, what bench.py times): ONE substep
+    against the unmodified reference from the state after 4 frames (the sphere is entering the pool), stage by stage,
+    default mode.  About a minute of CPU for the oracle."""
+    sc = pc.developed_scene(scenes.sphere_drop(256), 4)
+    assert sc["pos"].shape[0] > 16000000
+    reps = pc.lockstep_frames(sc, frames=1, isolate=True, max_substeps=1)
+    assert len(reps) == 1
+    pc.check_report(reps[0], dx=sc["dx"], isolate=True, exact_sampling=False)
+    assert reps[0]["gpu.pressure_rows"] == reps[0]["ref.fluid_cells"] > 1900000
+    assert reps[0]["advance.gpu_particles"] == reps[0]["advance.ref_particles"] > 16000000
+
+
 # ---------------------------------------------------------------- properties at larger sizes
 def test_dambreak128_properties():
     """Config 2 (128^3, ~2M particles): size-independent properties of a free run."""

@@ -1,6 +1,8 @@
 """z-slab decomposition on real GPUs: a 2-rank torchrun of scripts/slab_check.py, which compares the
-slab run with the single-GPU run of the same scene (counts and pressure rows exact, per-particle
-positions rel-L2 <= 1e-4) while particles migrate across the slab cut.  Skipped with < 2 GPUs."""
+slab run with the single-GPU run of the same scene AND with the unmodified reference engine on the host
+(counts and pressure rows exact, per-particle positions rel-L2 <= 1e-4) while particles migrate across the slab
+cut.  Skipped with < 2 GPUs; bench.py --gpus N runs the same kind of check on the scaling workload before it times
+anything (`parity_ok` in its line), and profiles/ keeps the 2/4/8-rank logs of this script."""
 import os
 import subprocess
 import sys
@@ -23,3 +25,6 @@ def test_two_slabs_match_single_gpu(peer):
                        env=dict(os.environ, FLIP_PEER=peer))
     assert r.returncode == 0, r.stdout[-3000:]
     assert "SLAB_CHECK OK" in r.stdout, r.stdout[-3000:]
+    from oracle import refengine
+    if refengine.available("golden"):
+        assert "SLAB_CHECK OK (oracle compared)" in r.stdout, r.stdout[-3000:]
