@@ -32,6 +32,20 @@ def max_abs(a, b):
     return float(np.max(np.abs(np.asarray(a, dtype=np.float64) - np.asarray(b, dtype=np.float64))))
 
 
+FRAGMENT_ELEMENTS = int(5e6) // 24     # MarkerParticles per FragmentedVector node  fragmentedvector.h:296,321
+
+
+def aliased_slots(n):
+    """Logical particle indices that share storage in the reference (fragmentedvector.h:141-153):
+    operator[] picks the node with `int(i * (1.0 / elementsPerFragment))`, which for most exact multiples
+    i = k * 208333 rounds down to k - 1, so logical index i reads AND WRITES the slot of index i - 208333.
+    Returns (aliased i's, the indices i - 208333 they share a slot with)."""
+    inv = 1.0 / float(FRAGMENT_ELEMENTS)
+    hi = [i for i in range(FRAGMENT_ELEMENTS, n, FRAGMENT_ELEMENTS) if int(i * inv) != i // FRAGMENT_ELEMENTS]
+    hi = np.asarray(hi, dtype=np.int64)
+    return hi, hi - FRAGMENT_ELEMENTS
+
+
 def make_pair(scene, tol=None, threads=None, gravity=(0.0, -25.0, 0.0), preconditioner=None, sampling=None):
     """Returns (ref, gpu) engines initialised from the same scene; the GPU engine gets the oracle's
     own static solid SDF and the oracle's LOGICAL particle list."""
@@ -161,9 +175,28 @@ def lockstep_substep(ref, gpu, dt, isolate=True, report=None):
     gpu.stage("g2p", dt)
     pg, ids = particles_by_id(gpu)
     pr = ref.particles()
-    rep["g2p.vel.rel_l2"] = rel_l2(pg[:, 3:], pr[ids, 3:])
-    rep["g2p.vel.max_abs"] = max_abs(pg[:, 3:], pr[ids, 3:])
-    rep["g2p.vel.mismatch"] = int(np.count_nonzero(pg[:, 3:] != pr[ids, 3:]))
+    # Above 208 333 particles some logical indices share a slot in the reference (aliased_slots).  Its G2P loop updates
+    # particles IN PLACE by logical index (fluidsimulation.cpp:4082-4092), so a shared slot is updated twice -- or once,
+    # the two indices belong to different worker threads -- and both logical entries read the result.  Those few
+    # entries (2 per 208 333 particles) are compared against the two possible outcomes instead of the tolerance:
+    # the once-updated velocity v1 (what the CUDA path holds) or f(v1) = v1 + 0.95 (v1 - v0).
+    a_hi, a_lo = aliased_slots(n0)
+    shared = np.zeros(n0, dtype=bool)
+    shared[a_hi] = True
+    shared[a_lo] = True
+    keep = ~shared[ids]
+    rep["g2p.shared_slots"] = int(shared.sum())
+    if shared.any():
+        once = pg[~keep, 3:].astype(np.float64)
+        v0 = P0[ids[~keep], 3:].astype(np.float64)
+        got = pr[ids[~keep], 3:].astype(np.float64)
+        twice = once + 0.95 * (once - v0)
+        err = np.minimum(np.abs(got - once), np.abs(got - twice)).max(axis=1)
+        scale = max(float(np.abs(once).max()), 1.0)
+        rep["g2p.shared_slot_err"] = float(err.max() / scale)
+    rep["g2p.vel.rel_l2"] = rel_l2(pg[keep, 3:], pr[ids[keep], 3:])
+    rep["g2p.vel.max_abs"] = max_abs(pg[keep, 3:], pr[ids[keep], 3:])
+    rep["g2p.vel.mismatch"] = int(np.count_nonzero(pg[keep, 3:] != pr[ids[keep], 3:]))
     if isolate:
         # put the oracle's post-G2P velocities in (keeps ids = index in pr)
         gpu.setMarkerParticles(pr)
@@ -290,6 +323,10 @@ def check_report(rep, dx=0.125, isolate=True, exact_sampling=False):
             assert rep["g2p.vel.rel_l2"] <= TOL_FAST_VEL_REL_L2, rep
             if "advance.pos.rel_l2" in rep:
                 assert rep["advance.pos.rel_l2"] <= TOL_FAST_POS_REL_L2, rep
+    # entries that share a slot in the reference's particle container: once- or twice-updated, nothing else
+    if rep.get("g2p.shared_slots", 0):
+        assert rep["g2p.shared_slots"] <= 2 * (rep["n0"] // FRAGMENT_ELEMENTS), rep
+        assert rep["g2p.shared_slot_err"] <= 1e-5, rep
     # float fields
     for comp in "UVW":
         assert rep[f"p2g.{comp}.rel_l2"] <= TOL_P2G_REL_L2, rep

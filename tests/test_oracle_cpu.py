@@ -67,3 +67,32 @@ def test_dam_break_stage_arrays_reproduce_the_golden_substep():
             assert e.pcg_iterations == int(g["pressure.iterations"])
             assert e.num_fluid_cells == int(g["pressure.fluid_cells"])
     e.close()
+
+
+def test_particle_container_aliasing_matches_the_harness_model():
+    """SURVEY §0 fact 11: above 208 333 particles FragmentedVector::operator[] maps some logical indices
+    i = k * 208333 onto the slot of i - 208333 (fragmentedvector.h:141-153).  tests/parity_common.aliased_slots is the
+    model the GPU parity harness uses for it (the in-place G2P loop updates such a slot twice); here it is pinned to
+    the reference itself: the logical view after initialize() holds a duplicate exactly at the modelled indices."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import parity_common as pc
+    sc = scenes.dam_break(64)
+    n = 3 * pc.FRAGMENT_ELEMENTS + 1000
+    reps = -(-n // sc["pos"].shape[0])
+    # distinct in-domain positions: copies of the column shifted by a sub-cell amount
+    pos = np.concatenate([sc["pos"] + np.float32(1e-3 * r) for r in range(reps)])[:n]
+    vel = np.zeros_like(pos)
+    e = refengine.RefEngine(sc["dims"], sc["dx"], pos, vel, threads=2)
+    got = e.particles()
+    assert got.shape[0] == n
+    hi, lo = pc.aliased_slots(n)
+    assert len(hi) >= 1 and set(hi.tolist()) <= {pc.FRAGMENT_ELEMENTS * k for k in (1, 2, 3)}
+    differs = np.flatnonzero((got[:, :3] != pos).any(axis=1))
+    assert np.array_equal(differs, hi)                       # every other logical entry is the injected particle
+    # slot map s(i): i - 208333 for the modelled indices, i otherwise.  The load queue is a FragmentedVector too and is
+    # read by index (fluidsimulation.cpp:2773-2785), so storage slot j holds injected[s(j)], and the logical view reads
+    # storage[s(i)] = injected[s(s(i))]
+    slot = np.arange(n)
+    slot[hi] = lo
+    assert np.array_equal(got[:, :3], pos[slot[slot]])
+    e.close()
