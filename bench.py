@@ -241,6 +241,7 @@ def algorithmic_bytes(Np, dims, n_rows, nf_liq):
         "g2p_advance": 48 * Np + 8 * nf_liq,      # fused G2P + RK3
         "extrapolate": 9 * Nf,                     # one extrapolateVelocityField call (3 components)
         "pcg_spmv": 36 * n_rows,
+        "pcg_dir_spmv": 60 * n_rows,               # direction update (z, s in, s out: 24n) fused with the SpMV (36n)
         "precond": 16 * n_rows + P,                # V-cycle: r in, z out (fp64) + P; the coarse levels are not credited
         "pcg_iter": 124 * n_rows + P,              # SpMV+dot 36n; x,r update 48n; precond 16n+P; direction 24n
     }

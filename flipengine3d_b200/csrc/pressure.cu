@@ -682,87 +682,115 @@ __device__ __forceinline__ float sm_residual(const SmLevel &L, const float *x, i
     return (L.invD[c] == 0.0f) ? 0.0f : L.b[c] - (L.diag[c] * x[c] - sm_offsum(L, x, c));
 }
 
-// down, coarsest sweeps, up over the shared-memory levels first..last; leaves the result in sl[first].x
+// ---- the shared-memory levels.  The passes are written once for a generic thread group (tid, nt, sync): the whole
+// CTA with __syncthreads for the levels of more than SM_WARP_CELLS cells, ONE WARP with __syncwarp below that
+// (a 1024-thread barrier per pass costs more than the pass itself on a level of 8^3 cells or fewer).
+static constexpr int SM_WARP_CELLS = 512;
+
+// nu pre-sweeps from a zero guess (or `sweeps` of them on the coarsest level); leaves the result in L.x
+template <class Sync>
+__device__ __forceinline__ void sm_presweeps(const SmLevel &L, int sweeps, const MgParams &p, bool coarsest, int tid, int nt, Sync sync) {
+    float *xa = L.x, *xb = L.x2;
+    for (int s = 0; s < sweeps; s++) {
+        const float omega = coarsest ? p.omegaCoarse : p.om[s];
+        for (int c = tid; c < L.n; c += nt) {
+            const float inv = L.invD[c];
+            float v = 0.0f;
+            if (inv != 0.0f) {
+                if (s == 0) v = omega * inv * L.b[c];
+                else v = (1.0f - omega) * xa[c] + omega * inv * (L.b[c] + sm_offsum(L, xa, c));
+            }
+            xb[c] = v;
+        }
+        sync();
+        float *t = xa; xa = xb; xb = t;
+    }
+    if (sweeps & 1) {      // after an odd number of sweeps the result sits in x2: copy so that x always holds it
+        for (int c = tid; c < L.n; c += nt) L.x[c] = L.x2[c];
+        sync();
+    }
+}
+// b_C = P^T (b_L - A_L x_L)
+template <class Sync>
+__device__ __forceinline__ void sm_restrict(const SmLevel &L, const SmLevel &C, int tid, int nt, Sync sync) {
+    for (int cc = tid; cc < C.n; cc += nt) {
+        float acc = 0.0f;
+        if (C.invD[cc] != 0.0f) {
+            const int ci = cc % C.I, cj = (cc / C.I) % C.J, ck = cc / C.sk;
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const int i = 2 * ci + (q & 1), j = 2 * cj + ((q >> 1) & 1), k = 2 * ck + (q >> 2);
+                if (i < L.I && j < L.J && k < L.K) acc += sm_residual(L, L.x, i + L.sj * j + L.sk * k);
+            }
+        }
+        C.b[cc] = acc;
+    }
+    sync();
+}
+// nu post-sweeps on (x + scale * P e), e = the solution of the next coarser level; leaves the result in L.x
+template <class Sync>
+__device__ __forceinline__ void sm_postsweeps(const SmLevel &L, const SmLevel &C, const MgParams &p, int tid, int nt, Sync sync) {
+    const float scale = p.scale;
+    const float *e = C.x;
+    float *xa = L.x, *xb = L.x2;
+    for (int s = 0; s < p.nu; s++) {
+        const float omega = p.om[p.nu - 1 - s];
+        for (int c = tid; c < L.n; c += nt) {
+            const float inv = L.invD[c];
+            float v = 0.0f;
+            if (inv != 0.0f) {
+                if (s == 0) {
+                    // sweep on (x + scale * P e): parents of the cell and of its six neighbours
+                    const int i = c % L.I, j = (c / L.I) % L.J, k = c / L.sk;
+                    const int pi = i >> 1, pj = C.sj * (j >> 1), pk = C.sk * (k >> 1);
+                    const float xc = xa[c] + scale * e[pi + pj + pk];
+                    float ns = 0.0f;
+                    ns += L.oW[c - L.sk] * (xa[c - L.sk] + scale * e[pi + pj + C.sk * ((k - 1) >> 1)]);
+                    ns += L.oV[c - L.sj] * (xa[c - L.sj] + scale * e[pi + C.sj * ((j - 1) >> 1) + pk]);
+                    ns += L.oU[c - 1] * (xa[c - 1] + scale * e[((i - 1) >> 1) + pj + pk]);
+                    ns += L.oU[c] * (xa[c + 1] + scale * e[((i + 1) >> 1) + pj + pk]);
+                    ns += L.oV[c] * (xa[c + L.sj] + scale * e[pi + C.sj * ((j + 1) >> 1) + pk]);
+                    ns += L.oW[c] * (xa[c + L.sk] + scale * e[pi + pj + C.sk * ((k + 1) >> 1)]);
+                    v = (1.0f - omega) * xc + omega * inv * (L.b[c] + ns);
+                } else {
+                    v = (1.0f - omega) * xa[c] + omega * inv * (L.b[c] + sm_offsum(L, xa, c));
+                }
+            }
+            xb[c] = v;
+        }
+        sync();
+        float *t = xa; xa = xb; xb = t;
+    }
+    if (p.nu & 1) {
+        for (int c = tid; c < L.n; c += nt) L.x[c] = L.x2[c];
+        sync();
+    }
+}
+// down, coarsest sweeps, up over the levels first..last with one thread group; leaves the result in sl[first].x
+template <class Sync>
+__device__ __forceinline__ void sm_cycle(const SmLevel *sl, int first, int last, const MgParams &p, int tid, int nt, Sync sync) {
+    for (int l = first; l <= last; l++) {
+        sm_presweeps(sl[l], (l == last) ? p.coarseSweeps : p.nu, p, l == last, tid, nt, sync);
+        if (l < last) sm_restrict(sl[l], sl[l + 1], tid, nt, sync);
+    }
+    for (int l = last - 1; l >= first; l--) sm_postsweeps(sl[l], sl[l + 1], p, tid, nt, sync);
+}
+
+// the shared-memory levels first..last of the V-cycle, called by every thread of ONE CTA
 __device__ __forceinline__ void sm_small_body(const SmLevel *sl, int first, int last, const MgParams &p) {
     const int tid = threadIdx.x, nt = blockDim.x;
-    const float scale = p.scale;
-    for (int l = first; l <= last; l++) {
-        const SmLevel &L = sl[l];
-        const int sweeps = (l == last) ? p.coarseSweeps : p.nu;
-        float *xa = L.x, *xb = L.x2;
-        for (int s = 0; s < sweeps; s++) {
-            const float omega = (l == last) ? p.omegaCoarse : p.om[s];
-            for (int c = tid; c < L.n; c += nt) {
-                const float inv = L.invD[c];
-                float v = 0.0f;
-                if (inv != 0.0f) {
-                    if (s == 0) v = omega * inv * L.b[c];
-                    else v = (1.0f - omega) * xa[c] + omega * inv * (L.b[c] + sm_offsum(L, xa, c));
-                }
-                xb[c] = v;
-            }
-            __syncthreads();
-            float *t = xa; xa = xb; xb = t;
-        }
-        if (sweeps & 1) {
-            for (int c = tid; c < L.n; c += nt) L.x[c] = L.x2[c];
-            __syncthreads();
-        }
-        if (l < last) {
-            const SmLevel &C = sl[l + 1];
-            for (int cc = tid; cc < C.n; cc += nt) {
-                float acc = 0.0f;
-                if (C.invD[cc] != 0.0f) {
-                    const int ci = cc % C.I, cj = (cc / C.I) % C.J, ck = cc / C.sk;
-#pragma unroll
-                    for (int q = 0; q < 8; q++) {
-                        const int i = 2 * ci + (q & 1), j = 2 * cj + ((q >> 1) & 1), k = 2 * ck + (q >> 2);
-                        if (i < L.I && j < L.J && k < L.K) acc += sm_residual(L, L.x, i + L.sj * j + L.sk * k);
-                    }
-                }
-                C.b[cc] = acc;
-            }
-            __syncthreads();
-        }
+    auto bsync = [] { __syncthreads(); };
+    auto wsync = [] { __syncwarp(); };
+    int lw = first;     // first level small enough for one warp
+    while (lw <= last && sl[lw].n > SM_WARP_CELLS) lw++;
+    if (lw > last) { sm_cycle(sl, first, last, p, tid, nt, bsync); return; }
+    for (int l = first; l < lw; l++) {
+        sm_presweeps(sl[l], p.nu, p, false, tid, nt, bsync);
+        sm_restrict(sl[l], sl[l + 1], tid, nt, bsync);
     }
-    for (int l = last - 1; l >= first; l--) {
-        const SmLevel &L = sl[l];
-        const SmLevel &C = sl[l + 1];
-        const float *e = C.x;
-        float *xa = L.x, *xb = L.x2;
-        for (int s = 0; s < p.nu; s++) {
-            const float omega = p.om[p.nu - 1 - s];
-            for (int c = tid; c < L.n; c += nt) {
-                const float inv = L.invD[c];
-                float v = 0.0f;
-                if (inv != 0.0f) {
-                    if (s == 0) {
-                        // sweep on (x + scale * P e): parents of the cell and of its six neighbours
-                        const int i = c % L.I, j = (c / L.I) % L.J, k = c / L.sk;
-                        const int pi = i >> 1, pj = C.sj * (j >> 1), pk = C.sk * (k >> 1);
-                        const float xc = xa[c] + scale * e[pi + pj + pk];
-                        float ns = 0.0f;
-                        ns += L.oW[c - L.sk] * (xa[c - L.sk] + scale * e[pi + pj + C.sk * ((k - 1) >> 1)]);
-                        ns += L.oV[c - L.sj] * (xa[c - L.sj] + scale * e[pi + C.sj * ((j - 1) >> 1) + pk]);
-                        ns += L.oU[c - 1] * (xa[c - 1] + scale * e[((i - 1) >> 1) + pj + pk]);
-                        ns += L.oU[c] * (xa[c + 1] + scale * e[((i + 1) >> 1) + pj + pk]);
-                        ns += L.oV[c] * (xa[c + L.sj] + scale * e[pi + C.sj * ((j + 1) >> 1) + pk]);
-                        ns += L.oW[c] * (xa[c + L.sk] + scale * e[pi + pj + C.sk * ((k + 1) >> 1)]);
-                        v = (1.0f - omega) * xc + omega * inv * (L.b[c] + ns);
-                    } else {
-                        v = (1.0f - omega) * xa[c] + omega * inv * (L.b[c] + sm_offsum(L, xa, c));
-                    }
-                }
-                xb[c] = v;
-            }
-            __syncthreads();
-            float *t = xa; xa = xb; xb = t;
-        }
-        if (p.nu & 1) {
-            for (int c = tid; c < L.n; c += nt) L.x[c] = L.x2[c];
-            __syncthreads();
-        }
-    }
+    if (tid < 32) sm_cycle(sl, lw, last, p, tid, 32, wsync);
+    __syncthreads();
+    for (int l = lw - 1; l >= first; l--) sm_postsweeps(sl[l], sl[l + 1], p, tid, nt, bsync);
 }
 
 // ---- branch-free passes on the zero-padded global arrays of the levels >= 1 (same arithmetic as mg_sweep_cell /
@@ -819,18 +847,46 @@ struct MgCoarseArgs {
     int fs, last;                    // levels fs..last: block 0, shared memory
     MgParams p;
     int smemFloats;
+    int group;                       // CTAs that run the levels 2..fs-1 among themselves (group barrier)
+    unsigned int *groupBar;          // arrival counter of that barrier (zero between launches)
     unsigned long long *trace;       // developer probe (FLIP_MG_TRACE): globaltimer at every phase boundary, block 0
 };
 
+__device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Level 1 holds ~1/8 of the rows and keeps all 148 CTAs busy: its passes are separated by grid-wide barriers.
+// From level 2 on a pass is a few thousand cells: a grid-wide barrier (148 CTAs, ~3 us) costs far more than the
+// pass, so those levels are run by the first `group` CTAs only, separated by a barrier among just those CTAs (one
+// atomic arrival + an acquire spin per CTA, < 1 us); the other CTAs go straight to the grid barrier in front of the
+// up-sweeps of level 1.  Every CTA executes the same number of grid barriers.
 __global__ void __launch_bounds__(1024) k_mg_coarse(MgCoarseArgs A, const DeviceScalars *S) {
     cg::grid_group grid = cg::this_grid();
     extern __shared__ float smf[];
     __shared__ SmLevel sl[MG_MAX_LEVELS];
     if (S->pcgDone) return;      // grid-uniform: written by the previous launch only
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
-    const int gw = (blockIdx.x * nt + tid) >> 5, nw = (gridDim.x * nt) >> 5;
+    const int wpb = nt >> 5;
     const int nu = A.p.nu;
     const float scale = A.p.scale;
+    const int G = min(max(A.group, 1), (int)gridDim.x);
+    const bool inGroup = (int)blockIdx.x < G;
+    unsigned int gen = 0;        // group barriers passed so far (uniform over the group)
+    auto group_sync = [&]() {
+        gen++;
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            atomicAdd(A.groupBar, 1u);
+            const unsigned int target = gen * (unsigned int)G;
+            while (ld_acquire_gpu_u32(A.groupBar) < target) {}
+            __threadfence();
+        }
+        __syncthreads();
+    };
     int ntrace = 0;
     auto stamp = [&]() {
         if (A.trace && blockIdx.x == 0 && tid == 0) {
@@ -846,13 +902,13 @@ __global__ void __launch_bounds__(1024) k_mg_coarse(MgCoarseArgs A, const Device
         if (tid == 0) {
             float *q = smf;
             for (int l = A.fs; l <= A.last; l++) {
-                const MgLevel &G = A.lv[l];
+                const MgLevel &Gl = A.lv[l];
                 SmLevel L;
-                L.I = G.I; L.J = G.J; L.K = G.K; L.sj = G.sj; L.sk = G.sk; L.n = G.n;
-                const int pad = sm_pad(G.sk);
-                L.diag = q; q += G.n; L.invD = q; q += G.n; L.b = q; q += G.n;
-                L.oU = q + pad; q += G.n + 2 * pad; L.oV = q + pad; q += G.n + 2 * pad; L.oW = q + pad; q += G.n + 2 * pad;
-                L.x = q + pad; q += G.n + 2 * pad; L.x2 = q + pad; q += G.n + 2 * pad;
+                L.I = Gl.I; L.J = Gl.J; L.K = Gl.K; L.sj = Gl.sj; L.sk = Gl.sk; L.n = Gl.n;
+                const int pad = sm_pad(Gl.sk);
+                L.diag = q; q += Gl.n; L.invD = q; q += Gl.n; L.b = q; q += Gl.n;
+                L.oU = q + pad; q += Gl.n + 2 * pad; L.oV = q + pad; q += Gl.n + 2 * pad; L.oW = q + pad; q += Gl.n + 2 * pad;
+                L.x = q + pad; q += Gl.n + 2 * pad; L.x2 = q + pad; q += Gl.n + 2 * pad;
                 sl[l] = L;
             }
         }
@@ -860,28 +916,28 @@ __global__ void __launch_bounds__(1024) k_mg_coarse(MgCoarseArgs A, const Device
         __syncthreads();
     }
     stamp();
-    // second half of the staging (the operator arrays): block 0 runs it during the restriction pass of level 1,
-    // in which it takes no part either
+    // second half of the staging (the operator arrays): block 0 runs it during the down passes of level 1,
+    // in which it takes no part
     auto stage_operators = [&]() {
         for (int l = A.fs; l <= A.last; l++) {
-            const MgLevel &G = A.lv[l];
+            const MgLevel &Gl = A.lv[l];
             const SmLevel &L = sl[l];
             // all loads of four strides first (read-only path): through generic pointers the compiler must
             // otherwise order every shared store before the next global load, ~20 dependent L2 latencies
-            for (int c0 = tid; c0 < G.n; c0 += 4 * nt) {
+            for (int c0 = tid; c0 < Gl.n; c0 += 4 * nt) {
                 float v[4][5];
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
                     const int c = c0 + u * nt;
-                    if (c < G.n) {
-                        v[u][0] = __ldg(G.diag + c); v[u][1] = __ldg(G.invD + c); v[u][2] = __ldg(G.oU + c);
-                        v[u][3] = __ldg(G.oV + c); v[u][4] = __ldg(G.oW + c);
+                    if (c < Gl.n) {
+                        v[u][0] = __ldg(Gl.diag + c); v[u][1] = __ldg(Gl.invD + c); v[u][2] = __ldg(Gl.oU + c);
+                        v[u][3] = __ldg(Gl.oV + c); v[u][4] = __ldg(Gl.oW + c);
                     }
                 }
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
                     const int c = c0 + u * nt;
-                    if (c < G.n) { L.diag[c] = v[u][0]; L.invD[c] = v[u][1]; L.oU[c] = v[u][2]; L.oV[c] = v[u][3]; L.oW[c] = v[u][4]; }
+                    if (c < Gl.n) { L.diag[c] = v[u][0]; L.invD[c] = v[u][1]; L.oU[c] = v[u][2]; L.oV[c] = v[u][3]; L.oW[c] = v[u][4]; }
                 }
             }
         }
@@ -889,28 +945,21 @@ __global__ void __launch_bounds__(1024) k_mg_coarse(MgCoarseArgs A, const Device
     };
     bool staged = false;
 
+    // one pre-smoothing pass + the restriction of level l over the warps gw, gw + nw, ... / the CTAs rb, rb + rnb, ...
+    // (an index of 0x3fffffff: this CTA takes no part); `sync` separates the passes
     const float *lx[MG_MAX_LEVELS];
-    // ---- down through the list-driven levels.  Block 0 has just spent ~10 us staging: the other blocks share the
-    // down passes of level 1 among themselves (gw1 / nw1 / first block 1), so that the staging is off the critical path
-    const int wpb = nt >> 5;
-    for (int l = 1; l < A.fs; l++) {
+    auto down_level = [&](int l, int gw, int nw, int rb, int rnb, auto &&sync) {
         const MgLevel &L = A.lv[l];
         const int *__restrict__ list = A.seg[l];
         const int nseg = A.segCount[l];
         float *xa = L.x, *xb = L.x2;
-        const bool skip0 = (l == 1) && gridDim.x > 1;
-        const int gw = skip0 ? (blockIdx.x == 0 ? 0x3fffffff : ((blockIdx.x - 1) * nt + tid) >> 5) : ((blockIdx.x * nt + tid) >> 5);
-        const int nw = skip0 ? (gridDim.x - 1) * wpb : gridDim.x * wpb;
-        const int rb = skip0 ? (blockIdx.x == 0 ? 0x3fffffff : (int)blockIdx.x - 1) : (int)blockIdx.x;   // restriction: block index
-        const int rnb = skip0 ? (int)gridDim.x - 1 : (int)gridDim.x;
         int sw = 0;
         if (nu >= 2) {
             for (int s = gw; s < nseg; s += nw) {
                 const int c = list[s] + lane;
                 if (c < L.n) xb[c] = mgp_sweep(L, L, xa, nullptr, A.p.om[1], scale, 3, c, A.p.om[0]);
             }
-            grid.sync();
-            stamp();
+            sync();
             float *t = xa; xa = xb; xb = t;
             sw = 2;
         }
@@ -919,12 +968,11 @@ __global__ void __launch_bounds__(1024) k_mg_coarse(MgCoarseArgs A, const Device
                 const int c = list[s] + lane;
                 if (c < L.n) xb[c] = mgp_sweep(L, L, xa, nullptr, A.p.om[sw], scale, sw == 0 ? 0 : 1, c, 0.0f);
             }
-            grid.sync();
-            stamp();
+            sync();
             float *t = xa; xa = xb; xb = t;
         }
         lx[l] = xa;
-        if (blockIdx.x == 0 && !staged && (skip0 || l + 1 == A.fs)) { stage_operators(); staged = true; }
+        if (blockIdx.x == 0 && !staged && l == 1) { stage_operators(); staged = true; }
         // restriction into level l+1: eight threads per coarse cell, four coarse segments per CTA pass
         {
             const MgLevel &C = A.lv[l + 1];
@@ -947,26 +995,10 @@ __global__ void __launch_bounds__(1024) k_mg_coarse(MgCoarseArgs A, const Device
                 if (q == 0 && cc < C.n) C.b[cc] = act ? v : 0.0f;
             }
         }
-        grid.sync();
-        stamp();
-    }
-    // ---- the single-CTA levels
-    if (blockIdx.x == 0) {
-        if (!staged) { stage_operators(); staged = true; }
-        const MgLevel &G = A.lv[A.fs];
-        const SmLevel &L = sl[A.fs];
-        for (int c = tid; c < G.n; c += nt) L.b[c] = G.b[c];
-        __syncthreads();
-        stamp();
-        sm_small_body(sl, A.fs, A.last, A.p);
-        stamp();
-        for (int c = tid; c < G.n; c += nt) G.x[c] = L.x[c];
-    }
-    grid.sync();
-    stamp();
-    lx[A.fs] = A.lv[A.fs].x;
-    // ---- up
-    for (int l = A.fs - 1; l >= 1; l--) {
+        sync();
+    };
+    // the post-smoothing passes of level l (the first one on x + scale * P e); lastSync: also after the last pass
+    auto up_level = [&](int l, int gw, int nw, bool lastSync, auto &&sync) {
         const MgLevel &L = A.lv[l];
         const MgLevel &C = A.lv[l + 1];
         const int *__restrict__ list = A.seg[l];
@@ -980,11 +1012,55 @@ __global__ void __launch_bounds__(1024) k_mg_coarse(MgCoarseArgs A, const Device
                 const int c = list[s] + lane;
                 if (c < L.n) xb[c] = mgp_sweep(L, C, xa, e, omega, scale, sw == 0 ? 2 : 1, c, 0.0f);
             }
-            grid.sync();
-            stamp();
+            if (sw + 1 < nu || lastSync) sync();
             float *t = xa; xa = xb; xb = t;
         }
         lx[l] = xa;
+    };
+    auto gsync = [&]() { grid.sync(); stamp(); };
+    auto psync = [&]() { group_sync(); stamp(); };
+
+    // ---- level 1 down (all CTAs; block 0 has just spent ~10 us staging and stages the operators meanwhile: the
+    // other blocks share the passes among themselves, so that the staging is off the critical path)
+    if (A.fs > 1) {
+        const bool skip0 = gridDim.x > 1;
+        const int gw = skip0 ? (blockIdx.x == 0 ? 0x3fffffff : ((blockIdx.x - 1) * nt + tid) >> 5) : ((blockIdx.x * nt + tid) >> 5);
+        const int nw = skip0 ? (gridDim.x - 1) * wpb : gridDim.x * wpb;
+        const int rb = skip0 ? (blockIdx.x == 0 ? 0x3fffffff : (int)blockIdx.x - 1) : (int)blockIdx.x;
+        const int rnb = skip0 ? (int)gridDim.x - 1 : (int)gridDim.x;
+        down_level(1, gw, nw, rb, rnb, gsync);
+    }
+    // ---- levels 2 .. coarsest and back up to level 2: the group
+    if (inGroup) {
+        const int gwG = (blockIdx.x * nt + tid) >> 5, nwG = G * wpb;
+        for (int l = 2; l < A.fs; l++) down_level(l, gwG, nwG, (int)blockIdx.x, G, psync);
+        if (blockIdx.x == 0) {
+            if (!staged) { stage_operators(); staged = true; }
+            const MgLevel &Gl = A.lv[A.fs];
+            const SmLevel &L = sl[A.fs];
+            for (int c = tid; c < Gl.n; c += nt) L.b[c] = Gl.b[c];
+            __syncthreads();
+            stamp();
+            sm_small_body(sl, A.fs, A.last, A.p);
+            stamp();
+            for (int c = tid; c < Gl.n; c += nt) Gl.x[c] = L.x[c];
+        }
+        lx[A.fs] = A.lv[A.fs].x;
+        if (A.fs > 2) {
+            psync();      // the solution of level fs is visible to the group
+            for (int l = A.fs - 1; l >= 2; l--) up_level(l, gwG, nwG, l > 2, psync);
+        }
+    }
+    lx[A.fs] = A.lv[A.fs].x;
+    // where the group left the results of the levels it ran (parity of its ping-pong, the same on every CTA)
+    {
+        const int swaps = (nu >= 2 ? nu - 1 : nu) + nu;
+        for (int l = 2; l < A.fs; l++) lx[l] = (swaps & 1) ? A.lv[l].x2 : A.lv[l].x;
+    }
+    if (A.fs > 1) {
+        gsync();          // join: what level 1 prolongates from is complete
+        if (blockIdx.x == 0 && tid == 0) *A.groupBar = 0u;     // every group barrier of this launch has been passed
+        up_level(1, (blockIdx.x * nt + tid) >> 5, gridDim.x * wpb, false, gsync);
     }
 }
 
@@ -1098,6 +1174,124 @@ __global__ void __launch_bounds__(TPB, 6) k_mg0_sweep(const int *__restrict__ se
         }
     }
     if (last) block_add(part, &S->rho[rhoSlot]);
+}
+
+// ---- fused passes of the single-GPU multigrid PCG (two level-0 passes fewer per iteration) ----------------------
+// (1) k_pcg_update + the fused double pre-sweep (mode 3) in one pass.  The pre-sweep needs the NEW residual at the
+// six neighbours; it is recomputed there as r - alpha*q instead of being read back, and written to the other buffer
+// of a ping-pong pair (rOut) because neighbouring threads still read the old one.
+//     alpha = rho/(s.q);  x += alpha s;  r' = r - alpha q;  ||r'||_inf;  xout = two damped-Jacobi sweeps on r' from zero
+__global__ void __launch_bounds__(TPB, 5) k_pcg_update_presweep(const int *__restrict__ segCell, const unsigned int *__restrict__ segMask,
+                                                                Mg0 M, const double *__restrict__ s, const double *__restrict__ q,
+                                                                double *__restrict__ x, const double *__restrict__ r,
+                                                                double *__restrict__ rOut, float *__restrict__ xout, float omega,
+                                                                float omega0, DeviceScalars *S, int it) {
+    if (S->pcgDone) return;
+    const int lane = threadIdx.x & 31;
+    const int nseg = S->numSegments, nw = (gridDim.x * blockDim.x) >> 5;
+    const double alpha = S->rho[it % 3] / S->dotSZ[it % 3];
+    const int sj = M.g.sj, sk = M.g.sk;
+    double rabs = 0.0;
+    for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nseg; w += nw) {
+        const int c = segCell[w] + lane;
+        if (!((segMask[w] >> lane) & 1u)) continue;
+        // everything is loaded before anything is consumed (rows are interior cells: every index is in range)
+        const float a0 = M.oW[c - sk], a1 = M.oV[c - sj], a2 = M.oU[c - 1], a3 = M.oU[c], a4 = M.oV[c], a5 = M.oW[c];
+        const float d0 = M.invD[c - sk], d1 = M.invD[c - sj], d2 = M.invD[c - 1], d3 = M.invD[c + 1], d4 = M.invD[c + sj], d5 = M.invD[c + sk];
+        const double r0 = r[c - sk], r1 = r[c - sj], r2 = r[c - 1], r3 = r[c + 1], r4 = r[c + sj], r5 = r[c + sk];
+        const double q0 = q[c - sk], q1 = q[c - sj], q2 = q[c - 1], q3 = q[c + 1], q4 = q[c + sj], q5 = q[c + sk];
+        const double rc = r[c], qc = q[c], xc = x[c], sc = s[c];
+        const float inv = M.invD[c];
+        const double rv = rc - alpha * qc;
+        x[c] = xc + alpha * sc;
+        rOut[c] = rv;
+        rabs = fmax(rabs, fabs(rv));
+        const float b = (float)rv;
+        float ns = 0.0f;
+        // a neighbour that is not a row has a zero weight (and possibly stale vector entries): select, never multiply
+        ns += (a0 != 0.0f && d0 != 0.0f) ? a0 * (omega0 * d0 * (float)(r0 - alpha * q0)) : 0.0f;
+        ns += (a1 != 0.0f && d1 != 0.0f) ? a1 * (omega0 * d1 * (float)(r1 - alpha * q1)) : 0.0f;
+        ns += (a2 != 0.0f && d2 != 0.0f) ? a2 * (omega0 * d2 * (float)(r2 - alpha * q2)) : 0.0f;
+        ns += (a3 != 0.0f && d3 != 0.0f) ? a3 * (omega0 * d3 * (float)(r3 - alpha * q3)) : 0.0f;
+        ns += (a4 != 0.0f && d4 != 0.0f) ? a4 * (omega0 * d4 * (float)(r4 - alpha * q4)) : 0.0f;
+        ns += (a5 != 0.0f && d5 != 0.0f) ? a5 * (omega0 * d5 * (float)(r5 - alpha * q5)) : 0.0f;
+        xout[c] = (inv == 0.0f) ? 0.0f : (1.0f - omega) * (omega0 * inv * b) + omega * inv * (b + M.fac * ns);
+    }
+    block_max(rabs, &S->rMaxBits[it % 3]);
+}
+
+// (2) k_pcg_direction of iteration it-1 + k_pcg_spmv of iteration it in one pass: the new search vector is formed at
+// the row AND at its six neighbours (s' = z + beta s), written to the other buffer of a ping-pong pair, and q = A s'
+// follows at once.  it == 0: s' = z.  The convergence test of iteration it-1 (||r||_inf <= tol, pcgsolver.h:286-288)
+// is taken here by every block; the last block to finish publishes it.
+__global__ void __launch_bounds__(TPB, 5) k_pcg_dir_spmv(const int *__restrict__ segCell, const unsigned int *__restrict__ segMask,
+                                                         PcgParams pp, const double *__restrict__ Adiag,
+                                                         const float *__restrict__ AoffU, const float *__restrict__ AoffV,
+                                                         const float *__restrict__ AoffW, const double *__restrict__ z,
+                                                         const double *__restrict__ sOld, double *__restrict__ sNew,
+                                                         double *__restrict__ q, DeviceScalars *S, int it) {
+    if (S->pcgDone) return;
+    double beta = 0.0, rmax = 0.0;
+    bool converged = false, breakdown = false;
+    if (it > 0) {
+        rmax = __longlong_as_double((long long)S->rMaxBits[(it - 1) % 3]);
+        const double rho = S->rho[(it - 1) % 3], rhoNew = S->rho[it % 3];
+        converged = rmax <= S->pcgTol;
+        breakdown = !converged && (rhoNew == 0.0 || rhoNew != rhoNew);
+        beta = rhoNew / rho;
+    }
+    const int lane = threadIdx.x & 31;
+    double part = 0.0;
+    if (!converged && !breakdown) {
+        const PGrid &g = pp.g;
+        const int nseg = S->numSegments, nw = (gridDim.x * blockDim.x) >> 5;
+        for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nseg; w += nw) {
+            const int c = segCell[w] + lane;
+            if (!((segMask[w] >> lane) & 1u)) continue;
+            const float a0 = AoffW[c - g.sk], a1 = AoffV[c - g.sj], a2 = AoffU[c - 1], a3 = AoffU[c], a4 = AoffV[c], a5 = AoffW[c];
+            const double z0 = z[c - g.sk], z1 = z[c - g.sj], z2 = z[c - 1], z3 = z[c + 1], z4 = z[c + g.sj], z5 = z[c + g.sk];
+            double s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0, s5 = 0, sc = 0;
+            if (it > 0) {
+                s0 = sOld[c - g.sk]; s1 = sOld[c - g.sj]; s2 = sOld[c - 1]; s3 = sOld[c + 1]; s4 = sOld[c + g.sj]; s5 = sOld[c + g.sk];
+                sc = sOld[c];
+            }
+            const double zc = z[c], dg = Adiag[c];
+            const double vc = zc + beta * sc;
+            double off = 0.0;
+            off += (a0 != 0.0f) ? (double)a0 * (z0 + beta * s0) : 0.0;
+            off += (a1 != 0.0f) ? (double)a1 * (z1 + beta * s1) : 0.0;
+            off += (a2 != 0.0f) ? (double)a2 * (z2 + beta * s2) : 0.0;
+            off += (a3 != 0.0f) ? (double)a3 * (z3 + beta * s3) : 0.0;
+            off += (a4 != 0.0f) ? (double)a4 * (z4 + beta * s4) : 0.0;
+            off += (a5 != 0.0f) ? (double)a5 * (z5 + beta * s5) : 0.0;
+            const double qv = dg * vc - pp.factor * off;
+            sNew[c] = vc;
+            q[c] = qv;
+            part += vc * qv;
+        }
+    }
+    block_add(part, &S->dotSZ[it % 3]);
+    __shared__ bool last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        int ticket = atomicAdd(&S->pad[0], 1);
+        last = (ticket == (int)gridDim.x - 1);
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        S->pad[0] = 0;
+        if (it > 0) {
+            S->pcgIterations = it;
+            S->pcgError = rmax;
+            if (converged) S->pcgDone = 1;
+            else if (breakdown) S->pcgDone = 3;
+        }
+        // slots of the rotation that nobody reads or accumulates during this launch
+        S->dotSZ[(it + 1) % 3] = 0.0;
+        S->rMaxBits[it % 3] = 0ull;
+        S->rho[(it + 1) % 3] = 0.0;
+    }
 }
 
 // host-side dispatch on the sweep mode
@@ -1647,6 +1841,9 @@ struct PressureScratch {
     int *gSegCount = nullptr;          // [MG_MAX_LEVELS]
     size_t coarseSmemBytes = 0;        // dynamic shared memory of k_mg_coarse (0: not usable, per-pass launches instead)
     int coarseBlocks = 0;              // its cooperative grid: one CTA per SM
+    double *vq = nullptr, *vs2 = nullptr, *vr2 = nullptr;   // fused PCG passes: q = A s, ping-pong partners of s and r
+    int coarseGroup = 16;              // CTAs of that grid that run the levels >= 2 (k_mg_coarse)
+    unsigned int *groupBar = nullptr;  // their barrier counter
     float *coarseBase = nullptr;       // levels >= 1 inside `pool` (L2 persistence window)
     size_t coarseBytes = 0, l2SetAside = 0, l2Window = 0;
     unsigned long long *trace = nullptr;   // FLIP_MG_TRACE developer probe
@@ -1689,6 +1886,10 @@ void pressure_alloc(flip_ctx *c) {
     FLIP_CUDA_CHECK(cudaMalloc(&ps->maskPrev, sizeof(unsigned int) * nSeg));
     FLIP_CUDA_CHECK(cudaMemset(ps->maskAll, 0, sizeof(unsigned int) * nSeg));
     FLIP_CUDA_CHECK(cudaMemset(ps->maskPrev, 0, sizeof(unsigned int) * nSeg));
+    for (double **v : {&ps->vq, &ps->vs2, &ps->vr2}) {
+        FLIP_CUDA_CHECK(cudaMalloc(v, sizeof(double) * pad));
+        FLIP_CUDA_CHECK(cudaMemset(*v, 0, sizeof(double) * pad));
+    }
     FLIP_CUDA_CHECK(cudaMalloc(&ps->flagAll, sizeof(int) * (nSeg + 1)));
     FLIP_CUDA_CHECK(cudaMalloc(&ps->posAll, sizeof(int) * (nSeg + 1)));
     c->mg = ps;
@@ -1772,6 +1973,9 @@ void pressure_alloc(flip_ctx *c) {
                     ps->coarseSmemBytes = bytes;
                     ps->coarseBlocks = sms;
                     if (const char *e = getenv("FLIP_MG_COARSE_BLOCKS")) ps->coarseBlocks = std::max(2, std::min(sms, atoi(e)));   // tuning knob
+                    if (const char *e = getenv("FLIP_MG_GROUP")) ps->coarseGroup = std::max(1, std::min(sms, atoi(e)));            // tuning knob
+                    FLIP_CUDA_CHECK(cudaMalloc(&ps->groupBar, 64));
+                    FLIP_CUDA_CHECK(cudaMemset(ps->groupBar, 0, 64));
                 }
                 if (getenv("FLIP_MG_TRACE")) {
                     FLIP_CUDA_CHECK(cudaMalloc(&ps->trace, 64 * sizeof(unsigned long long)));
@@ -1839,7 +2043,8 @@ void pressure_free(flip_ctx *c) {
     if (c->mg) {
         PressureScratch *ps = (PressureScratch *)c->mg;
         cudaFree(ps->maskAll); cudaFree(ps->maskPrev); cudaFree(ps->flagAll); cudaFree(ps->posAll); cudaFree(ps->pool); cudaFree(ps->gpool);
-        cudaFree(ps->segPool); cudaFree(ps->gSegPool); cudaFree(ps->trace);
+        cudaFree(ps->segPool); cudaFree(ps->gSegPool); cudaFree(ps->trace); cudaFree(ps->groupBar);
+        cudaFree(ps->vq); cudaFree(ps->vs2); cudaFree(ps->vr2);
         delete ps;
         c->mg = nullptr;
     }
@@ -2136,14 +2341,23 @@ void stage_pressure(flip_ctx *c, double dt) {
     // in shared memory.  Same operator as `vcycle` up to float summation order in the restrictions.
     auto list_blocks = [&](const MgLevel &lv) { return std::max(1, std::min(cdiv(cdiv(lv.n, 32), WPB), 148 * 8)); };
     auto restrict_blocks = [&](const MgLevel &coarse) { return std::max(1, std::min(cdiv(coarse.n, 32), 148 * 8)); };
-    auto vcycle_list = [&](int rhoSlot) {
+    // fusedIt >= 0 (needs nu >= 2): the residual update of PCG iteration fusedIt is part of the first pass
+    // (k_pcg_update_presweep) and the new residual lands in the ping-pong partner of c->vr
+    auto vcycle_list = [&](int rhoSlot, int fusedIt) {
         const int nu = mp.nu;
         size_t ktV = kt_begin(c);
         // ---- down
         {
             float *xa = ps->lv[0].x, *xb = ps->lv[0].x2;
             int sw = 0;
-            if (nu >= 2) {
+            if (fusedIt >= 0) {
+                k_pcg_update_presweep<<<loopBlocks, TPB, 0, st>>>(c->segCell, c->segMask, m0, c->vs, ps->vq, c->vx_, c->vr, ps->vr2, xb,
+                                                                 pre_om(1), pre_om(0), c->dS, fusedIt);
+                c->launches++;
+                std::swap(c->vr, ps->vr2);
+                std::swap(xa, xb);
+                sw = 2;
+            } else if (nu >= 2) {
                 launch_mg0_sweep(loopBlocks, st, c->segCell, c->segMask, m0, ps->lv[1], c->vr, xa, nullptr, xb, pre_om(1),
                                                       mp.scale, 3, 0, nullptr, c->dS, 0, pre_om(0));
                 c->launches++;
@@ -2168,6 +2382,7 @@ void stage_pressure(flip_ctx *c, double dt) {
             A.segCount = ps->lvSegCount;
             A.fs = fs; A.last = L - 1; A.p = mp;
             A.smemFloats = (int)(ps->coarseSmemBytes / sizeof(float));
+            A.group = ps->coarseGroup; A.groupBar = ps->groupBar;
             A.trace = ps->trace;
             const DeviceScalars *Sdev = c->dS;
             void *args[] = {&A, &Sdev};
@@ -2237,7 +2452,9 @@ void stage_pressure(flip_ctx *c, double dt) {
     };
     // the list-driven cycle needs the single-CTA levels to start above level 0 and below the top
     const bool useLists = useMg && !slab && fs >= 1 && fs < L;
-    auto apply_precond = [&](int rhoSlot) { if (useLists) vcycle_list(rhoSlot); else vcycle(rhoSlot); };
+    auto apply_precond = [&](int rhoSlot) { if (useLists) vcycle_list(rhoSlot, -1); else vcycle(rhoSlot); };
+    // single GPU, multigrid with at least two pre-sweeps: the fused passes (two level-0 passes fewer per iteration)
+    const bool fused = useLists && mp.nu >= 2 && !getenv("FLIP_PCG_UNFUSED");
 
     k_pcg_scalars_init<<<1, 1, 0, st>>>(c->dS, pp.tolFactor); c->launches++;
     if (c->pcgPersistent && !slab) {
@@ -2270,7 +2487,7 @@ void stage_pressure(flip_ctx *c, double dt) {
     c->launches++;
     if (useMg) {
         apply_precond(0);
-        k_pcg_copy_zs<<<segBlocks, TPB, 0, st>>>(c->segCell, c->segMask, c->vz, c->vs, c->dS); c->launches++;
+        if (!fused) { k_pcg_copy_zs<<<segBlocks, TPB, 0, st>>>(c->segCell, c->segMask, c->vz, c->vs, c->dS); c->launches++; }
     }
     if (slab) slab_allreduce_scalar(c, &c->dS->rho[0], COMM_SUM_F64);
 
@@ -2280,6 +2497,31 @@ void stage_pressure(flip_ctx *c, double dt) {
     const int batch = useMg ? 3 : 16;
     const int firstBatch = (useMg && ps->lastIterations > batch + 2) ? ps->lastIterations - 2 : batch;
     bool done = false;
+    if (fused) {
+        // iteration it = [dir_spmv(it)] update+presweep(it), rest of the V-cycle, dir_spmv(it+1): the convergence test of
+        // iteration it is taken by dir_spmv(it+1), which returns at once when the residual is below the tolerance
+        auto dir_spmv = [&](int i) {
+            size_t ktSp = kt_begin(c);
+            k_pcg_dir_spmv<<<loopBlocks, TPB, 0, st>>>(c->segCell, c->segMask, pp, c->Adiag, c->AoffU, c->AoffV, c->AoffW, c->vz,
+                                                      c->vs, ps->vs2, ps->vq, c->dS, i);
+            kt_end(c, FLIP_KERNEL_PCG_DIR_SPMV, ktSp);
+            c->launches++;
+            std::swap(c->vs, ps->vs2);
+        };
+        dir_spmv(0);
+        while (!done && it < c->pressureMaxIter) {
+            int stop = it + (it == 0 ? firstBatch : batch);
+            if (stop > c->pressureMaxIter) stop = c->pressureMaxIter;
+            for (; it < stop; it++) {
+                size_t ktIt = kt_begin(c);
+                vcycle_list((it + 1) % 3, it);
+                dir_spmv(it + 1);
+                kt_end(c, FLIP_KERNEL_PCG_ITER, ktIt);
+            }
+            scalars_to_host(c);
+            done = c->hS->pcgDone != 0;
+        }
+    } else {
     while (!done && it < c->pressureMaxIter) {
         int stop = it + (it == 0 ? firstBatch : batch);
         if (stop > c->pressureMaxIter) stop = c->pressureMaxIter;
@@ -2303,6 +2545,7 @@ void stage_pressure(flip_ctx *c, double dt) {
         }
         scalars_to_host(c);
         done = c->hS->pcgDone != 0;
+    }
     }
     }   // multi-launch path
     FLIP_CUDA_CHECK(cudaGetLastError());

@@ -19,7 +19,7 @@ ARRAY_ID = dict(U=0, V=1, W=2, validU=3, validV=4, validW=5, liquid_phi=6, solid
                 near_solid=15, pressure=16)
 
 KERNEL_CLASSES = ("sdf_p2g", "g2p", "advance", "sort", "extrapolate", "pcg_spmv", "pcg_iter", "pressure_build",
-                  "pressure_apply", "precond", "pcg_solve")
+                  "pressure_apply", "precond", "pcg_solve", "pcg_dir_spmv", "g2p_advance")
 
 FLIP_OK, FLIP_ERR_RUNTIME, FLIP_ERR_DOMAIN, FLIP_ERR_OUT_OF_RANGE, FLIP_ERR_CUDA, FLIP_ERR_UNSUPPORTED = range(6)
 

@@ -230,7 +230,10 @@ enum {
     FLIP_KERNEL_PRESSURE_APPLY = 8, /* velocity update                                  */
     FLIP_KERNEL_PRECOND = 9,   /* one preconditioner application (multigrid V-cycle), multi-launch solver only */
     FLIP_KERNEL_PCG_SOLVE = 10, /* the whole PCG solve as one persistent cooperative kernel */
-    FLIP_NUM_KERNEL_CLASSES = 11
+    FLIP_KERNEL_PCG_DIR_SPMV = 11, /* search-direction update of iteration it-1 fused with the operator application of
+                                      iteration it (single-GPU multigrid PCG)                */
+    FLIP_KERNEL_G2P_ADVANCE = 12,  /* PIC/FLIP update fused with RK3 + collision              */
+    FLIP_NUM_KERNEL_CLASSES = 13
 };
 int flip_enable_kernel_timing(flip_ctx *ctx, int on);
 int flip_reset_kernel_timing(flip_ctx *ctx);
