@@ -106,6 +106,9 @@ static void free_grids(flip_ctx *c) {
     cudaFree(c->validU); cudaFree(c->validV); cudaFree(c->validW); cudaFree(c->status);
     cudaFree(c->frontier[0]); cudaFree(c->frontier[1]);
     cudaFree(c->phiL); cudaFree(c->phiS); cudaFree(c->wU); cudaFree(c->wV); cudaFree(c->wW);
+    for (auto &a : c->p2gAcc) { cudaFree(a); a = nullptr; }
+    cudaFree(c->occBits); c->occBits = nullptr;
+    cudaFree(c->p2gTiles); c->p2gTiles = nullptr;
     c->cellCount = c->cellStart = c->cellStartA = nullptr;
     c->U = c->V = c->W = c->sU = c->sV = c->sW = nullptr;
     c->validU = c->validV = c->validW = c->status = nullptr;
@@ -125,6 +128,9 @@ static void allocate_grids(flip_ctx *c) {
     dev_alloc(c->wU, d.nU); dev_alloc(c->wV, d.nV); dev_alloc(c->wW, d.nW);
     dev_alloc(c->cellCount, (size_t)d.nC + 1); dev_alloc(c->cellStart, (size_t)d.nC + 1);
     dev_alloc(c->cellStartA, (size_t)d.nC + 1);
+    // cell occupancy bitmaps (occupied / 3x3x3 / 5x5x5 neighbourhood / surface), one bit per cell, rows padded to whole words
+    dev_alloc(c->occBits, 4 * (size_t)((d.I + 31) / 32) * d.J * d.K);
+    c->occBitsValid = false;
     pressure_alloc(c);
     // phi_liquid starts at the "no particles" value 3dx (particlelevelset.cpp:295-301)
     std::vector<float> init((size_t)d.nC, (float)(3.0 * d.dx));

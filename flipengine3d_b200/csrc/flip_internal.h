@@ -171,6 +171,10 @@ struct flip_ctx {
     unsigned char *nearSolid = nullptr;
     int nsI = 0, nsJ = 0, nsK = 0;
     float *pressure = nullptr;                // (I,J,K) float, last solution
+    void *p2gAcc[4] = {nullptr, nullptr, nullptr, nullptr};   // fixed-point accumulators of the P2G scatter: U, V, W faces; cell minima
+    unsigned int *occBits = nullptr;          // cell occupancy bitmaps: occupied | 3x3x3 neighbourhood | 5x5x5 neighbourhood
+    int *p2gTiles = nullptr;                  // tile bookkeeping of the P2G scatter / SDF shell search (particles.cu)
+    bool occBitsValid = false;                // the sort has just written the first of them (rows of whole words)
 
     // pressure system, dense-indexed vectors over cells + active 32-cell segments
     int *segCell = nullptr;                   // [maxSegments] first cell of the segment

@@ -301,10 +301,15 @@ __global__ void k_cell_finalize(int nC, const int *__restrict__ startA, int *__r
 }
 
 // also marks the 4x4x4-cell blocks that hold particles (the gather kernel skips empty space with it)
+// and, when the rows are whole words long (bits != nullptr), the one-bit-per-cell occupancy map of k_occ_bits
 __global__ void k_build_src(int nC, const int *__restrict__ startA, const int *__restrict__ start,
                             const int *__restrict__ sortIdx, int *__restrict__ srcIdx, DeviceScalars *S,
-                            unsigned char *__restrict__ occ, int I, int J, int oI, int oJ) {
+                            unsigned char *__restrict__ occ, int I, int J, int oI, int oJ, unsigned int *__restrict__ bits) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (bits) {      // nC is a multiple of 32 here: whole warps pass or return together
+        const unsigned int m = __ballot_sync(0xffffffffu, c < nC && start[c + 1] > start[c]);
+        if ((threadIdx.x & 31) == 0 && c < nC) bits[c >> 5] = m;
+    }
     if (c >= nC) return;
     int b = start[c], e = start[c + 1];
     if (e > b) {
@@ -432,8 +437,9 @@ void particles_sort(flip_ctx *c, bool applyRules, double frameDt, int srcOffset,
             c->occBytes = need;
         }
         FLIP_CUDA_CHECK(cudaMemsetAsync(c->occ, 0, need, st));
+        c->occBitsValid = c->occBits && (d.I % 32 == 0);
         k_build_src<<<cdiv(nC, TPB), TPB, 0, st>>>(nC, c->cellStartA, c->cellStart, c->sortIdx, c->srcIdx, c->dS, c->occ, d.I,
-                                                   d.J, oI, oJ);
+                                                   d.J, oI, oJ, c->occBitsValid ? c->occBits : nullptr);
         c->launches++;
     }
     if (n > 0) {
@@ -866,80 +872,698 @@ __global__ void __launch_bounds__(128) k_sdf_p2g(ParticleSoA p, const int *__res
     phiL[cell] = finish_phi(g, phiS, best2, i, j, k);
 }
 
-// Liquid SDF of the queued cells: the rest of the 5x5x5 search box (particlelevelset.cpp:476-513, :596-621).
+// Liquid SDF of the queued cells: the whole 5x5x5 search box (particlelevelset.cpp:476-513, :596-621).
+// ONE WARP PER CELL.  (One thread per cell walks its rows through chains of dependent loads, ~0.4 us of L2 latency
+// per particle: measured 209 us for ~1e5 queued cells, nearly all of it the slowest thread's chain.)  Lane r < 25
+// fetches the particle range of row r of the 5x5 rows around the cell, all at once; the rows are then taken nearest
+// first -- a row whose nearest point is farther than the best particle so far ends the search -- with the lanes on
+// consecutive particles of the row (coalesced), and the lane minima are folded after every row.
 // A particle of a cell two away along some axis lies inside the reference's search box for roughly 3/4 of that
 // cell; the decision is taken in float with a margin far above the rounding of the reference's block-local
 // arithmetic, and only the borderline cases run the literal double-precision index computation.
-__global__ void k_sdf_far(ParticleSoA p, const int *__restrict__ cellStart, GatherParams g, float *__restrict__ phiL,
-                          const float *__restrict__ phiS, const int *__restrict__ farCells,
-                          const float *__restrict__ farBest, const int *__restrict__ farCount) {
+// the 25 (dj,dk) row offsets ordered by the distance of the row from the cell, packed as r = (dj+2) + 5 (dk+2)
+__constant__ unsigned char c_far_order[25] = {12, 7, 11, 13, 17, 6, 8, 16, 18, 2, 10, 14, 22, 1, 3, 5, 9, 15, 19, 21, 23, 0, 4, 20, 24};
+
+__global__ void __launch_bounds__(256) k_sdf_far(ParticleSoA p, const int *__restrict__ cellStart, GatherParams g,
+                                                 float *__restrict__ phiL, const float *__restrict__ phiS,
+                                                 const int *__restrict__ farCells, const float *__restrict__ farBest,
+                                                 const int *__restrict__ farCount) {
     const int I = g.I, J = g.J, K = g.K;
     const int n = *farCount;
-    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+    const int lane = threadIdx.x & 31;
+    const int nw = (gridDim.x * blockDim.x) >> 5;
+    const float sr = g.srS;
+    const double invdx = g.invdx;
+    const float dxf = (float)g.dx, margin = 1.0e-3f * dxf;
+    const float loIn = -sr + margin, hiIn = dxf + sr - margin, loOut = -sr - margin, hiOut = dxf + sr + margin;
+    // q2[d]: squared distance (in dx^2) from the centre to the nearest point of the cells at offset d along one axis,
+    // less a margin against the rounding of the computed distances
+    const float dx2 = fmul(dxf, dxf);
+    auto q2 = [&](int d) { return d == 0 ? 0.0f : (d == 1 || d == -1) ? 0.2499f * dx2 : 2.2499f * dx2; };
+    for (int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < n; t += nw) {
         const int cell = farCells[t];
         float best2 = farBest[t];
         const int i = cell % I, j = (cell / I) % J, k = cell / (I * J);
         const NodeFrame f = node_frame(g, i, j, k + g.kOff);
-        const float sr = g.srS;
-        const double invdx = g.invdx;
-        const float dxf = (float)g.dx, margin = 1.0e-3f * dxf;
         const float Xn = (float)dmul((double)(float)i, g.dx), Yn = (float)dmul((double)(float)j, g.dx),
                     Zn = (float)dmul((double)(float)(k + g.kOff), g.dx);
-        const float loIn = -sr + margin, hiIn = dxf + sr - margin, loOut = -sr - margin, hiOut = dxf + sr + margin;
-        const int jlo = max(j - 1, 0), jhi = min(j + 1, J - 1), klo = max(k - 1, 0), khi = min(k + 1, K - 1);
-        const int ilo = max(i - 1, 0), ihi = min(i + 1, I - 1);
-        const int j2lo = max(j - 2, 0), j2hi = min(j + 2, J - 1);
-        const int k2lo = max(k - 2, 0), k2hi = min(k + 2, K - 1);
         const int i2lo = max(i - 2, 0), i2hi = min(i + 2, I - 1);
-        // which of the 5x5 rows hold particles at all: fifty independent loads in flight instead of one dependent
-        // pair per loop trip (this kernel is pure latency: most rows around a shell cell are empty)
-        unsigned int rows = 0u;
-#pragma unroll
-        for (int r = 0; r < 25; r++) {
-            const int cj = j + (r % 5) - 2, ck = k + (r / 5) - 2;
+        int qb = 0, qe = 0;
+        if (lane < 25) {
+            const int cj = j + (lane % 5) - 2, ck = k + (lane / 5) - 2;
             if (cj >= 0 && cj < J && ck >= 0 && ck < K) {
                 const int rowBase = I * (cj + J * ck);
-                if (__ldg(cellStart + rowBase + i2lo) != __ldg(cellStart + rowBase + i2hi + 1)) rows |= 1u << r;
+                qb = __ldg(cellStart + rowBase + i2lo);
+                qe = __ldg(cellStart + rowBase + i2hi + 1);
             }
         }
-        (void)j2lo; (void)j2hi; (void)k2lo; (void)k2hi;
-        while (rows) {
-            {
-                const int r = __ffs(rows) - 1;
-                rows &= rows - 1u;
-                const int cj = j + (r % 5) - 2, ck = k + (r / 5) - 2;
-                bool innerRow = (ck >= klo && ck <= khi && cj >= jlo && cj <= jhi);
-                int rowBase = I * (cj + J * ck);
-                int qb = __ldg(cellStart + rowBase + i2lo);
-                int qe = __ldg(cellStart + rowBase + i2hi + 1);
-                int sb = 0, se = 0;   // range already visited by k_sdf_p2g (skip)
-                if (innerRow) { sb = __ldg(cellStart + rowBase + ilo); se = __ldg(cellStart + rowBase + ihi + 1); }
-                for (int q = qb; q < qe; q++) {
-                    if (innerRow && q >= sb && q < se) { q = se - 1; continue; }
-                    float x = __ldg(p.px + q), y = __ldg(p.py + q), z = __ldg(p.pz + q);
-                    // position relative to the cell's lower corner: inside the search box iff -sr <= u < dx + sr
-                    float ux = fsub(x, Xn), uy = fsub(y, Yn), uz = fsub(z, Zn);
-                    bool out = ux < loOut || ux >= hiOut || uy < loOut || uy >= hiOut || uz < loOut || uz >= hiOut;
-                    if (out) continue;
-                    bool in = ux >= loIn && ux < hiIn && uy >= loIn && uy < hiIn && uz >= loIn && uz < hiIn;
-                    float xl = fsub(x, f.ox), yl = fsub(y, f.oy), zl = fsub(z, f.oz);
-                    if (!in) {
-                        // borderline: the literal test.  Block membership of the particle: the blocks overlapped by
-                        // [p-sr, p+sr] in global coordinates; then the block-local search box.
-                        int bminx = pos2idx_d((double)fsub(x, sr), g.invBlockdxSDF), bmaxx = pos2idx_d((double)fadd(x, sr), g.invBlockdxSDF);
-                        int bminy = pos2idx_d((double)fsub(y, sr), g.invBlockdxSDF), bmaxy = pos2idx_d((double)fadd(y, sr), g.invBlockdxSDF);
-                        int bminz = pos2idx_d((double)fsub(z, sr), g.invBlockdxSDF), bmaxz = pos2idx_d((double)fadd(z, sr), g.invBlockdxSDF);
-                        if (f.bi < bminx || f.bi > bmaxx || f.bj < bminy || f.bj > bmaxy || f.bk < bminz || f.bk > bmaxz) continue;
-                        int gminx = pos2idx(fsub(xl, sr), invdx), gmaxx = pos2idx(fadd(xl, sr), invdx);
-                        int gminy = pos2idx(fsub(yl, sr), invdx), gmaxy = pos2idx(fadd(yl, sr), invdx);
-                        int gminz = pos2idx(fsub(zl, sr), invdx), gmaxz = pos2idx(fadd(zl, sr), invdx);
-                        if (f.li < gminx || f.li > gmaxx || f.lj < gminy || f.lj > gmaxy || f.lk < gminz || f.lk > gmaxz) continue;
-                    }
-                    best2 = fminf(best2, lengthsq3(fsub(f.cx, xl), fsub(f.cy, yl), fsub(f.cz, zl)));
+        const unsigned int rows = __ballot_sync(0xffffffffu, qe > qb);
+        for (int o = 0; o < 25; o++) {
+            const int r = c_far_order[o];
+            const int dj = (r % 5) - 2, dk = (r / 5) - 2;
+            if (!(q2(dj) + q2(dk) < best2)) break;       // the rows that follow are no nearer
+            if (!((rows >> r) & 1u)) continue;
+            const int rb = __shfl_sync(0xffffffffu, qb, r), re = __shfl_sync(0xffffffffu, qe, r);
+            float mine = best2;
+            for (int q = rb + lane; q < re; q += 32) {
+                const float x = __ldg(p.px + q), y = __ldg(p.py + q), z = __ldg(p.pz + q);
+                // position relative to the cell's lower corner: inside the search box iff -sr <= u < dx + sr
+                const float ux = fsub(x, Xn), uy = fsub(y, Yn), uz = fsub(z, Zn);
+                const bool out = ux < loOut || ux >= hiOut || uy < loOut || uy >= hiOut || uz < loOut || uz >= hiOut;
+                if (out) continue;
+                const bool in = ux >= loIn && ux < hiIn && uy >= loIn && uy < hiIn && uz >= loIn && uz < hiIn;
+                const float xl = fsub(x, f.ox), yl = fsub(y, f.oy), zl = fsub(z, f.oz);
+                if (!in) {
+                    // borderline: the literal test.  Block membership of the particle: the blocks overlapped by
+                    // [p-sr, p+sr] in global coordinates; then the block-local search box.
+                    int bminx = pos2idx_d((double)fsub(x, sr), g.invBlockdxSDF), bmaxx = pos2idx_d((double)fadd(x, sr), g.invBlockdxSDF);
+                    int bminy = pos2idx_d((double)fsub(y, sr), g.invBlockdxSDF), bmaxy = pos2idx_d((double)fadd(y, sr), g.invBlockdxSDF);
+                    int bminz = pos2idx_d((double)fsub(z, sr), g.invBlockdxSDF), bmaxz = pos2idx_d((double)fadd(z, sr), g.invBlockdxSDF);
+                    if (f.bi < bminx || f.bi > bmaxx || f.bj < bminy || f.bj > bmaxy || f.bk < bminz || f.bk > bmaxz) continue;
+                    int gminx = pos2idx(fsub(xl, sr), invdx), gmaxx = pos2idx(fadd(xl, sr), invdx);
+                    int gminy = pos2idx(fsub(yl, sr), invdx), gmaxy = pos2idx(fadd(yl, sr), invdx);
+                    int gminz = pos2idx(fsub(zl, sr), invdx), gmaxz = pos2idx(fadd(zl, sr), invdx);
+                    if (f.li < gminx || f.li > gmaxx || f.lj < gminy || f.lj > gmaxy || f.lk < gminz || f.lk > gmaxz) continue;
+                }
+                mine = fminf(mine, lengthsq3(fsub(f.cx, xl), fsub(f.cy, yl), fsub(f.cz, zl)));
+            }
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) mine = fminf(mine, __shfl_xor_sync(0xffffffffu, mine, s));
+            best2 = mine;
+        }
+        if (lane == 0) phiL[cell] = finish_phi(g, phiS, best2, i, j, k);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// P2G + liquid SDF as a shared-memory SCATTER (default for power-of-two dx in FLIP_SAMPLING_FAST; the gather above
+// stays the literal path of FLIP_SAMPLING_EXACT and of non-dyadic cell widths).
+//
+// A particle reaches, per component, at most the 2x2x2 faces around it (r = 0.866 dx < dx): 24 candidate faces,
+// ~8 hits, against ~650 (particle, face) evaluations per node of the 3x3x3-cell gather.  What a scatter needs is an
+// accumulation that many threads can add to; shared-memory float atomics are CAS loops on sm_100a and would make
+// the sums depend on the arrival order, so the sums are kept in FIXED POINT with native 32-bit integer atomics
+// (ATOMS.ADD; measured: 0.34 ms for the whole particle set against 0.81 ms with float CAS atomics and 1.5 ms with
+// global REDs, scripts/micro/atomics_bench.cu): integer addition is associative, hence the result is bit-reproducible
+// from run to run whatever the order, inside a tile and across tiles.  Per face and component TWO words:
+//     W = sum wq,  wq = round(w * 2^22)       u32: no overflow below sum(w) = 1024, i.e. 56 particles in each of the
+//                                             18 cells that can reach a face (denser cells: see below)
+//     S = sum round(wq v 2^(q-22))            i32: 2^q = the largest power of two with vmax 2^q <= 2^21, vmax = the
+//                                             maximum particle speed of the step (known from the sort)
+// in TWO TIERS: a contribution of weight below 1/16 goes to a second pair of words scaled 16 times finer (same bounds:
+// the terms are 16 times smaller).  S is formed from the ROUNDED weight, so u = S/W is a weighted mean with weights
+// wq/2^22 (2^26): the rounding of the weights only enters through the velocity differences of the contributors, and
+// the momentum terms are rounded at vmax 2^-22 -- vmax 2^-26 on the faces at the rim of the liquid, whose
+// contributions are all small: < 3e-6 vmax on a face of total weight 0.02, ~1e-7 of the face value in the bulk.
+// (Measured on the B200: the kernel is bound by the shared-memory atomic unit, ~4 cycles per warp-wide ATOMS; a third
+// word per component -- the same precision from one scale -- costs 682 us against 411 us for two.)
+// The liquid SDF rides along: a particle also takes the minimum of its squared distance to the 2x2x2 cell centres
+// around it (literal arithmetic: (x*x + y*y) + z*z of the exact differences; ATOMS.MAX on the inverted float bits),
+// where that distance is below dx -- every particle NOT among those a centre receives is at least dx away from it
+// along some axis, so a minimum below dx is final.  (That settles every liquid cell and most of the first air layer;
+// the other cells within reach of a particle are queued for k_sdf_far.)
+// One CTA owns the particles of a tile of 8x8x8 cells, spread evenly over its threads (thread t takes M consecutive
+// particles of the tile's 64 rows laid end to end: a thread per cell leaves 44 % of the lanes idle, E[max of 32
+// Poisson(8)] = 14; and neighbouring lanes M particles apart work on different cells, so their atomics rarely
+// collide), and accumulates into the (8+2)^3 slots around it; the tile's partial sums are then added to global
+// accumulators with one 64-bit RED per face (W in the low word, S in the high word: W cannot carry) where the
+// contributions of neighbouring tiles meet, and k_p2g_finish turns the sums into u = S/W and valid = W > 1e-6 (and
+// clears them).  Faces whose total weight is below P2G_LITERAL_BAND -- few particles near the rim of the support:
+// the fixed-point weight has too few significant digits there, and the valid-mask decision sum(w) > 1e-6 lies in
+// that range -- are queued and recomputed by k_p2g_literal with the literal weights in the fixed particle order of
+// the gather, so those values and the valid mask are what the gather produces.
+// ------------------------------------------------------------------------------------------------
+static constexpr int P2G_T = 8;                       // tile edge, cells
+static constexpr int P2G_F = P2G_T + 2;               // slots per axis
+static constexpr int P2G_SLOTS = P2G_F * P2G_F * P2G_F;
+static constexpr int P2G_WORDS = 13;                  // per slot: (W, S, W fine, S fine) of U, V, W; ~min squared distance
+static constexpr int P2G_THREADS = 512;
+static constexpr int P2G_ROWS = P2G_T * P2G_T;
+static constexpr float P2G_LITERAL_BAND = 0.02f;
+static constexpr float P2G_WSCALE = 4194304.0f;       // 2^22
+static constexpr int P2G_MAX_PER_CELL = 56;           // 18 cells x 56 particles x (w <= 1) < 1024: W and S cannot overflow;
+                                                      // the particles of a denser cell stay out of the sums and the 81 faces
+                                                      // around it are recomputed by k_p2g_literal
+
+// ---- occupancy bitmaps: one bit per cell, 32 cells of a row per word.  occ: the cell holds particles; near3 / near5:
+// some cell of the 3x3x3 / 5x5x5 neighbourhood does.  A face of node (i,j,k) can only receive weight from the 3x3x3
+// cells around cell (i,j,k), and a cell whose 5x5x5 neighbourhood is empty lies in no particle's SDF search box
+// (particlelevelset.cpp:476-513: a box reaches at most two cells from the particle's cell).
+__global__ void k_occ_bits(const int *__restrict__ cellStart, int I, int rows, int WR, unsigned int *__restrict__ bits) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= rows * WR) return;
+    const int row = w / WR, i = (w % WR) * 32 + lane;
+    bool on = false;
+    if (i < I) { const int c = row * I + i; on = __ldg(cellStart + c + 1) > __ldg(cellStart + c); }
+    const unsigned int m = __ballot_sync(0xffffffffu, on);
+    if (lane == 0) bits[w] = m;
+}
+// surf: the cell holds particles and some cell of its 5x5x5 neighbourhood (inside the grid) holds none
+__global__ void k_occ_dilate(const unsigned int *__restrict__ bits, int I, int J, int K, int WR, unsigned int *__restrict__ near3,
+                             unsigned int *__restrict__ near5, unsigned int *__restrict__ surf, int *__restrict__ tileFlags) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= J * K * WR) return;
+    const int wr = w % WR, j = (w / WR) % J, k = w / (WR * J);
+    // cells of the row that exist, per word
+    auto exist = [&](int q) { return (q < 0 || q >= WR) ? 0u : ((q + 1) * 32 <= I ? 0xffffffffu : ((1u << (I - q * 32)) - 1u)); };
+    const unsigned int xp = exist(wr - 1), xc = exist(wr), xn = exist(wr + 1);
+    unsigned int p3 = 0, c3 = 0, n3 = 0, p5 = 0, c5 = 0, n5 = 0, pe = 0, ce = 0, ne = 0;
+    for (int dk = -2; dk <= 2; dk++) {
+        const int kk = k + dk;
+        if (kk < 0 || kk >= K) continue;
+        for (int dj = -2; dj <= 2; dj++) {
+            const int jj = j + dj;
+            if (jj < 0 || jj >= J) continue;
+            const unsigned int *r = bits + (size_t)WR * (jj + (size_t)J * kk);
+            const unsigned int pv = wr > 0 ? __ldg(r + wr - 1) : 0u, cv = __ldg(r + wr), nv = wr + 1 < WR ? __ldg(r + wr + 1) : 0u;
+            p5 |= pv; c5 |= cv; n5 |= nv;
+            pe |= ~pv & xp; ce |= ~cv & xc; ne |= ~nv & xn;
+            if (dk >= -1 && dk <= 1 && dj >= -1 && dj <= 1) { p3 |= pv; c3 |= cv; n3 |= nv; }
+        }
+    }
+    // along the row: bit i of the result looks at bits i-d .. i+d across the word boundaries
+    const unsigned int d3 = c3 | (c3 << 1) | (p3 >> 31) | (c3 >> 1) | (n3 << 31);
+    const unsigned int d5 = c5 | (c5 << 1) | (p5 >> 31) | (c5 >> 1) | (n5 << 31) | (c5 << 2) | (p5 >> 30) | (c5 >> 2) | (n5 << 30);
+    const unsigned int e5 = ce | (ce << 1) | (pe >> 31) | (ce >> 1) | (ne << 31) | (ce << 2) | (pe >> 30) | (ce >> 2) | (ne << 30);
+    near3[w] = d3;
+    near5[w] = d5;
+    const unsigned int own = __ldg(bits + w);
+    surf[w] = own & e5;
+    // the 8x8x8-cell tiles this word touches: holds particles (P2G scatter) / holds empty cells within reach of a
+    // particle (SDF shell search).  Everybody stores the same 1.
+    const unsigned int shell = d5 & ~own & xc;
+    const int tX = (I + 7) >> 3, tY = (J + 7) >> 3;
+    const int tBase = tX * ((j >> 3) + tY * (k >> 3)) + wr * 4;
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+        if ((own >> (8 * b)) & 0xffu) tileFlags[2 * (tBase + b)] = 1;
+        if ((shell >> (8 * b)) & 0xffu) tileFlags[2 * (tBase + b) + 1] = 1;
+    }
+}
+
+// flags -> lists of tiles (and the flags are cleared for the next step); counts[0/1]: list lengths
+__global__ void k_tile_lists(int nTiles, int *__restrict__ tileFlags, int *__restrict__ listP, int *__restrict__ listS,
+                             int *__restrict__ counts) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nTiles) return;
+    const int2 f = reinterpret_cast<int2 *>(tileFlags)[t];
+    if (f.x | f.y) reinterpret_cast<int2 *>(tileFlags)[t] = make_int2(0, 0);
+    if (f.x) listP[warp_append_slot(&counts[0])] = t;
+    if (f.y) listS[warp_append_slot(&counts[1])] = t;
+}
+
+__device__ __forceinline__ unsigned int smem_addr(const void *p) { return (unsigned int)__cvta_generic_to_shared(p); }
+
+// round-to-nearest of |t| < 2^22 through the mantissa: t + 1.5*2^23 has the integer in its low bits (one FFMA
+// instead of a conversion)
+#define P2G_MAGIC 12582912.0f
+#define P2G_MAGIC_BITS 0x4B400000
+
+// One candidate face: weight (Horner form of velocityadvector.cpp:437; zero outside the support), the two
+// fixed-point words, two REDs.  The REDs are unconditional -- a miss adds zeros: ptxas turns a predicated ATOMS into a
+// branch around it with a convergence barrier (BSSY / BRA / BSYNC, three issue slots per atomic; some lane of a warp
+// hits nearly every candidate anyway).  vs = v * 2^(q-22).
+template <int OFF>
+__device__ __forceinline__ void p2g_candidate(float d2, float rsq, float c1, float c2, float c3, float vs, unsigned int addr) {
+    float w = fmaf(fmaf(fmaf(c1, d2, c2), d2, c3), d2, 1.0f);
+    w = d2 < rsq ? w : 0.0f;
+    const bool fine = w < 0.0625f;
+    const float t = fmaf(w, fine ? 16.0f * P2G_WSCALE : P2G_WSCALE, P2G_MAGIC);
+    const int iw = __float_as_int(t) - P2G_MAGIC_BITS;
+    const int is = __float_as_int(fmaf(t - P2G_MAGIC, vs, P2G_MAGIC)) - P2G_MAGIC_BITS;      // t - magic = (float)iw, exact
+    const unsigned int a = addr + (fine ? 8u : 0u);
+    asm volatile("red.shared.add.u32 [%0+%3], %1;\n\tred.shared.add.u32 [%0+%4], %2;"
+                 :: "r"(a), "r"(iw), "r"(is), "n"(OFF), "n"(OFF + 4) : "memory");
+}
+
+// the 2x2x2 faces of component COMP around a particle; s0/s1/s2: squared offsets to the two planes along x/y/z
+template <int COMP>
+__device__ __forceinline__ void p2g_component(unsigned int accAddr, int fi, int fj, int fk, const float *s0, const float *s1,
+                                              const float *s2, float vs, float rsq, float c1, float c2, float c3) {
+    const unsigned int a = accAddr + (unsigned int)((fi + P2G_F * (fj + P2G_F * fk)) * (P2G_WORDS * 4) + COMP * 16);
+#define P2G_CAND(DI, DJ, DK) \
+    p2g_candidate<((DI) + P2G_F * ((DJ) + P2G_F * (DK))) * (P2G_WORDS * 4)>(s0[DI] + (s1[DJ] + s2[DK]), rsq, c1, c2, c3, vs, a);
+    P2G_CAND(0, 0, 0) P2G_CAND(1, 0, 0) P2G_CAND(0, 1, 0) P2G_CAND(1, 1, 0)
+    P2G_CAND(0, 0, 1) P2G_CAND(1, 0, 1) P2G_CAND(0, 1, 1) P2G_CAND(1, 1, 1)
+#undef P2G_CAND
+}
+
+// squared distance to one of the 2x2x2 cell centres, literal ((x*x + y*y) + z*z); kept where below `thr`
+template <int OFF>
+__device__ __forceinline__ void sdf_candidate(float xy, float zz, float thr, unsigned int addr) {
+    const float d2 = fadd(xy, zz);
+    // non-negative floats order as integers: max of ~bits = min; 0 = nothing
+    const unsigned int inv = d2 < thr ? ~__float_as_uint(d2) : 0u;
+    asm volatile("red.shared.max.u32 [%0+%2], %1;" :: "r"(addr), "r"(inv), "n"(OFF) : "memory");
+}
+
+struct P2GGlobal {
+    ulonglong2 *accU, *accV, *accW;           // per face: x = S << 32 | W of the coarse tier, y = of the fine tier
+    unsigned int *minC;                       // per cell: ~bits of the minimum squared distance, 0 = none
+};
+struct SdfQueues {
+    int *farCells; float *farBest; int *farCount;   // (gather path only) no particle within 1.45 dx: the 5x5x5 box (k_sdf_far)
+    int *litFaces, *litCount; int litCap;           // faces below P2G_LITERAL_BAND or next to a dense cell (k_p2g_literal)
+};
+
+__global__ void __launch_bounds__(P2G_THREADS, 3) k_p2g_scatter(ParticleSoA p, const int *__restrict__ cellStart, GatherParams g,
+                                                               P2GGlobal G, int tilesX, int tilesY, float sScale, SdfQueues Q,
+                                                               const int *__restrict__ tileList, int *__restrict__ tileCounts) {
+    extern __shared__ int acc[];         // [slot][P2G_WORDS]
+    __shared__ int rowBeg[P2G_ROWS], rowPre[P2G_ROWS + 1];
+    __shared__ unsigned int rowDense[P2G_ROWS];    // bit i: cell i of the row is too dense for the fixed-point sums
+    __shared__ int nextTile;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int I = g.I, J = g.J, K = g.K;
+    const float dxf = (float)g.dx, invf = (float)g.invdx, hw = g.hw, rsq = g.rsq;
+    const float c1 = -g.coef1, c2 = g.coef2, c3 = -g.coef3;
+    const float thr = 0.999f * dxf * dxf;
+    const unsigned int accAddr = smem_addr(acc);
+    // persistent CTAs take the tiles that hold particles (most tiles of the box are air) from the list, one ticket each
+    const int nTiles = tileCounts[0];
+    for (;;) {
+    __syncthreads();                                   // the previous tile's flush has read acc / the row tables
+    if (tid == 0) nextTile = atomicAdd(&tileCounts[2], 1);
+    __syncthreads();
+    if (nextTile >= nTiles) break;
+    const int tile = tileList[nextTile];
+    const int tx = tile % tilesX, ty = (tile / tilesX) % tilesY, tz = tile / (tilesX * tilesY);
+    const int i0 = tx * P2G_T, j0 = ty * P2G_T, k0 = tz * P2G_T;     // first cell of the tile (local planes)
+    // the tile's 64 rows of 8 cells: particle ranges and their running total (two warps, shuffle scan)
+    if (tid < P2G_ROWS) {
+        const int j = j0 + (tid % P2G_T), k = k0 + tid / P2G_T;
+        int b = 0, n = 0;
+        unsigned int dense = 0u;
+        if (j < J && k < K) {
+            const int c = i0 + I * (j + J * k);
+            const int nc = min(P2G_T, I - i0);
+            int prev = __ldg(cellStart + c);
+            b = prev;
+#pragma unroll
+            for (int m = 1; m <= P2G_T; m++) {
+                if (m <= nc) {
+                    const int nx = __ldg(cellStart + c + m);
+                    if (nx - prev > P2G_MAX_PER_CELL) dense |= 1u << (m - 1);
+                    prev = nx;
                 }
             }
+            n = prev - b;
+            // the faces that a dense cell's particles can reach: the three faces of the 3x3x3 nodes from the cell's own
+            for (unsigned int dm = dense; dm; dm &= dm - 1u) {
+                const int ci = i0 + __ffs(dm) - 1;
+                const int slot = atomicAdd(Q.litCount, 81);
+                int w = 0;
+                for (int dk = 0; dk <= 2; dk++)
+                    for (int dj = 0; dj <= 2; dj++)
+                        for (int di = 0; di <= 2; di++) {
+                            const int ni = ci - 1 + di, nj = j - 1 + dj, nk = k - 1 + dk;
+                            // (nodes outside the grid: the cell's own node instead, a harmless duplicate)
+                            const bool in = ni >= 0 && nj >= 0 && nk >= 0 && ni <= I && nj <= J && nk <= K;
+                            const int node = in ? ni + (I + 1) * (nj + (J + 1) * nk) : ci + (I + 1) * (j + (J + 1) * k);
+                            for (int comp = 0; comp < 3; comp++, w++)
+                                if (slot + w < Q.litCap) Q.litFaces[slot + w] = (comp << 28) | node;
+                        }
+            }
         }
-        phiL[cell] = finish_phi(g, phiS, best2, i, j, k);
+        rowBeg[tid] = b;
+        rowDense[tid] = dense;
+        int v = n;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
+        rowPre[tid + 1] = v;     // inclusive within the warp
+    }
+    for (int q = tid; q < P2G_SLOTS * P2G_WORDS; q += P2G_THREADS) acc[q] = 0;
+    __syncthreads();
+    if (tid >= 32 && tid < P2G_ROWS) rowPre[tid + 1] += rowPre[32];
+    if (tid == 0) rowPre[0] = 0;
+    __syncthreads();
+    const int total = rowPre[P2G_ROWS];
+    const float org[3] = {(float)(i0 - 1), (float)(j0 - 1), (float)(k0 - 1) + (float)g.kOff};   // z-slab: local planes
+    // thread t: the M consecutive particles [t M, (t+1) M) of the rows laid end to end
+    const int M = (total + P2G_THREADS - 1) / P2G_THREADS;
+    int idx = tid * M;
+    const int idxEnd = min(idx + M, total);
+    int row = 0;
+    if (idx < total) {
+#pragma unroll
+        for (int s = P2G_ROWS / 2; s > 0; s >>= 1)
+            if (rowPre[row + s] <= idx) row += s;
+    }
+    for (; idx < idxEnd; idx++) {
+        while (idx >= rowPre[row + 1]) row++;
+        const int q = rowBeg[row] + (idx - rowPre[row]);
+        const float pos[3] = {__ldg(p.px + q), __ldg(p.py + q), __ldg(p.pz + q)};
+        // v 2^(q-22), at most 1/2 in magnitude; the clamp only guards the range of the mantissa trick against a speed
+        // above the recorded maximum
+        const float vsx = fminf(fmaxf(__ldg(p.vx + q) * sScale, -1.0f), 1.0f), vsy = fminf(fmaxf(__ldg(p.vy + q) * sScale, -1.0f), 1.0f),
+                    vsz = fminf(fmaxf(__ldg(p.vz + q) * sScale, -1.0f), 1.0f);
+        // per axis: the planes below / above the particle (a: through the nodes, b: through the cell centres), the
+        // offsets to them -- each ONE rounding of the exact difference, as the literal fsub(plane, p) -- and their
+        // squares.  dx is a power of two and the indices are far below 2^24: plane coordinates are exact.
+        int ia[3], ib[3];
+        float sqa[3][2], sqb[3][2];
+#pragma unroll
+        for (int ax = 0; ax < 3; ax++) {
+            const float u = pos[ax] * invf;
+            const float fa = floorf(u), fb = floorf(u - 0.5f);
+            const float ca = fa * dxf, cb = fb * dxf + hw;
+            const float da0 = fsub(pos[ax], ca), da1 = fsub(pos[ax], ca + dxf);
+            const float db0 = fsub(pos[ax], cb), db1 = fsub(pos[ax], cb + dxf);
+            sqa[ax][0] = fmul(da0, da0); sqa[ax][1] = fmul(da1, da1);
+            sqb[ax][0] = fmul(db0, db0); sqb[ax][1] = fmul(db1, db1);
+            ia[ax] = (int)(fa - org[ax]); ib[ax] = (int)(fb - org[ax]);    // slot coordinates inside the (8+2)^3 block
+        }
+        // component c is staggered on the two other axes
+        if (!((rowDense[row] >> (ia[0] - 1)) & 1u)) {
+            p2g_component<0>(accAddr, ia[0], ib[1], ib[2], sqa[0], sqb[1], sqb[2], vsx, rsq, c1, c2, c3);
+            p2g_component<1>(accAddr, ib[0], ia[1], ib[2], sqb[0], sqa[1], sqb[2], vsy, rsq, c1, c2, c3);
+            p2g_component<2>(accAddr, ib[0], ib[1], ia[2], sqb[0], sqb[1], sqa[2], vsz, rsq, c1, c2, c3);
+        }
+        // liquid SDF: the 2x2x2 cell centres
+        {
+            const unsigned int a = accAddr + (unsigned int)((ib[0] + P2G_F * (ib[1] + P2G_F * ib[2])) * (P2G_WORDS * 4) + 48);
+            const float xy00 = fadd(sqb[0][0], sqb[1][0]), xy10 = fadd(sqb[0][1], sqb[1][0]);
+            const float xy01 = fadd(sqb[0][0], sqb[1][1]), xy11 = fadd(sqb[0][1], sqb[1][1]);
+#define SDF_CAND(DI, DJ, DK, XY) sdf_candidate<((DI) + P2G_F * ((DJ) + P2G_F * (DK))) * (P2G_WORDS * 4)>(XY, sqb[2][DK], thr, a);
+            SDF_CAND(0, 0, 0, xy00) SDF_CAND(1, 0, 0, xy10) SDF_CAND(0, 1, 0, xy01) SDF_CAND(1, 1, 0, xy11)
+            SDF_CAND(0, 0, 1, xy00) SDF_CAND(1, 0, 1, xy10) SDF_CAND(0, 1, 1, xy01) SDF_CAND(1, 1, 1, xy11)
+#undef SDF_CAND
+        }
+    }
+    __syncthreads();
+    // the tile's partial sums -> global accumulators (faces outside the grid cannot exist in the reference's loops)
+    for (int s = tid; s < P2G_SLOTS; s += P2G_THREADS) {
+        const int *a = acc + s * P2G_WORDS;
+        const int fi = i0 - 1 + s % P2G_F, fj = j0 - 1 + (s / P2G_F) % P2G_F, fk = k0 - 1 + s / (P2G_F * P2G_F);
+        if (fi < 0 || fj < 0 || fk < 0) continue;
+        const unsigned int mn = a[12];
+        auto flush = [&](int comp, ulonglong2 *dst, size_t idx) {
+            const unsigned int wc = a[4 * comp], wf = a[4 * comp + 2];
+            const int sc = a[4 * comp + 1], sf = a[4 * comp + 3];
+            if (wc | (unsigned int)sc) atomicAdd(&dst[idx].x, ((unsigned long long)(unsigned int)sc << 32) + wc);
+            if (wf | (unsigned int)sf) atomicAdd(&dst[idx].y, ((unsigned long long)(unsigned int)sf << 32) + wf);
+        };
+        if (fi <= I && fj < J && fk < K) flush(0, G.accU, (size_t)fi + (size_t)(I + 1) * ((size_t)fj + (size_t)J * (size_t)fk));
+        if (fi < I && fj <= J && fk < K) flush(1, G.accV, (size_t)fi + (size_t)I * ((size_t)fj + (size_t)(J + 1) * (size_t)fk));
+        if (fi < I && fj < J && fk <= K) flush(2, G.accW, (size_t)fi + (size_t)I * ((size_t)fj + (size_t)J * (size_t)fk));
+        if (mn && fi < I && fj < J && fk < K) atomicMax(G.minC + ((size_t)fi + (size_t)I * ((size_t)fj + (size_t)J * (size_t)fk)), mn);
+    }
+    }   // tiles
+}
+
+// ---- liquid SDF of the cells the 2x2x2 scatter cannot settle (no particle within dx of the centre).  Such a cell is
+// EMPTY (a particle of the cell itself is within 0.87 dx of its centre), so the particles whose search box
+// (particlelevelset.cpp:476-513: at most two cells from the particle's cell) contains it lie in cells that have an
+// empty cell in their 5x5x5 neighbourhood: the SURFACE cells (bitmap from k_occ_dilate) -- a shell two cells thick
+// along the free surface and the walls.  One CTA per tile of 8x8x8 cells that holds unsettled cells: the particle
+// positions of the surface cells of the (8+4)^3 region go to shared memory once (a shell through the region: a few
+// thousand particles), then one thread per unsettled cell searches the 5x5x5 cells around it nearest first and stops
+// at the first cell that cannot hold anything nearer -- the dependent loads of the search cost a shared-memory
+// access instead of an L2 round trip (measured for ~4e5 such cells: 431 us with a warp per cell on global memory).
+// The box test is taken in float with a margin far above the rounding of the reference's block-local arithmetic;
+// only the borderline cases run the literal double-precision index computation.  A region with more surface
+// particles than the staging area holds sends its cells to k_sdf_far instead.
+static constexpr int SHELL_F = P2G_T + 4;
+static constexpr int SHELL_ROWS = SHELL_F * SHELL_F;
+static constexpr int SHELL_THREADS = 512;
+static constexpr int SHELL_CAP = 6144;      // particles staged per tile (72 KB)
+// the 125 cell offsets ordered by the distance of the cell from the centre of the middle one:
+// (di+2) | (dj+2) << 3 | (dk+2) << 6 | n1 << 9 | n2 << 11, n1 / n2 = number of axes with |d| = 1 / 2
+__constant__ unsigned short c_shell_order[125] = {
+    146, 657, 659, 650, 666, 594, 722, 1161, 1163, 1177, 1179, 1105, 1107, 1233, 1235, 1098, 1114, 1226, 1242, 1609, 1611, 1625,
+    1627, 1737, 1739, 1753, 1755, 2192, 2196, 2178, 2210, 2066, 2322, 2696, 2700, 2712, 2716, 2689, 2691, 2721, 2723, 2640, 2644,
+    2768, 2772, 2626, 2658, 2754, 2786, 2577, 2579, 2833, 2835, 2570, 2586, 2826, 2842, 3144, 3148, 3160, 3164, 3272, 3276, 3288,
+    3292, 3137, 3139, 3169, 3171, 3265, 3267, 3297, 3299, 3081, 3083, 3097, 3099, 3337, 3339, 3353, 3355, 4224, 4228, 4256, 4260,
+    4112, 4116, 4368, 4372, 4098, 4130, 4354, 4386, 4672, 4676, 4704, 4708, 4800, 4804, 4832, 4836, 4616, 4620, 4632, 4636, 4872,
+    4876, 4888, 4892, 4609, 4611, 4641, 4643, 4865, 4867, 4897, 4899, 6144, 6148, 6176, 6180, 6400, 6404, 6432, 6436};
+
+__device__ __noinline__ bool sdf_box_literal(const GatherParams &g, float x, float y, float z, int ci, int cj, int ckg) {
+    const float sr = g.srS;
+    const NodeFrame f = node_frame(g, ci, cj, ckg);
+    int bminx = pos2idx_d((double)fsub(x, sr), g.invBlockdxSDF), bmaxx = pos2idx_d((double)fadd(x, sr), g.invBlockdxSDF);
+    int bminy = pos2idx_d((double)fsub(y, sr), g.invBlockdxSDF), bmaxy = pos2idx_d((double)fadd(y, sr), g.invBlockdxSDF);
+    int bminz = pos2idx_d((double)fsub(z, sr), g.invBlockdxSDF), bmaxz = pos2idx_d((double)fadd(z, sr), g.invBlockdxSDF);
+    if (f.bi < bminx || f.bi > bmaxx || f.bj < bminy || f.bj > bmaxy || f.bk < bminz || f.bk > bmaxz) return false;
+    const float xl = fsub(x, f.ox), yl = fsub(y, f.oy), zl = fsub(z, f.oz);
+    int gminx = pos2idx(fsub(xl, sr), g.invdx), gmaxx = pos2idx(fadd(xl, sr), g.invdx);
+    int gminy = pos2idx(fsub(yl, sr), g.invdx), gmaxy = pos2idx(fadd(yl, sr), g.invdx);
+    int gminz = pos2idx(fsub(zl, sr), g.invdx), gmaxz = pos2idx(fadd(zl, sr), g.invdx);
+    return !(f.li < gminx || f.li > gmaxx || f.lj < gminy || f.lj > gmaxy || f.lk < gminz || f.lk > gmaxz);
+}
+
+__global__ void __launch_bounds__(SHELL_THREADS) k_sdf_shell(ParticleSoA p, const int *__restrict__ cellStart, GatherParams g,
+                                                            const unsigned int *__restrict__ occ, const unsigned int *__restrict__ near5,
+                                                            const unsigned int *__restrict__ surf, int WR, unsigned int *__restrict__ minC,
+                                                            int tilesX, int tilesY, SdfQueues Q, const int *__restrict__ tileList,
+                                                            int *__restrict__ tileCounts) {
+    extern __shared__ float stage[];              // [3][SHELL_CAP] particle positions
+    __shared__ int off[SHELL_ROWS * (SHELL_F + 1)];   // staged range of every cell of the region, row by row
+    __shared__ int rowG[SHELL_ROWS], rowS[SHELL_ROWS + 1];   // first particle of the row's span (global / staged)
+    __shared__ int warpSum[SHELL_THREADS / 32];
+    __shared__ int nextTile;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int I = g.I, J = g.J, K = g.K;
+    const float dxf = (float)g.dx, hw = g.hw, sr = g.srS, margin = 1.0e-3f * dxf, dx2 = dxf * dxf;
+    const float loIn = -sr + margin, hiIn = dxf + sr - margin, loOut = -sr - margin, hiOut = dxf + sr + margin;
+    float *sx = stage, *sy = stage + SHELL_CAP, *sz = stage + 2 * SHELL_CAP;
+    const int nTiles = tileCounts[1];
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) nextTile = atomicAdd(&tileCounts[3], 1);
+        __syncthreads();
+        if (nextTile >= nTiles) break;
+        const int tile = tileList[nextTile];
+        const int tx = tile % tilesX, ty = (tile / tilesX) % tilesY, tz = tile / (tilesX * tilesY);
+        const int i0 = tx * P2G_T, j0 = ty * P2G_T, k0 = tz * P2G_T;
+        const int i = i0 + (tid % P2G_T), j = j0 + (tid / P2G_T) % P2G_T, k = k0 + tid / (P2G_T * P2G_T);
+        // unsettled: an empty cell within reach of a particle that the 2x2x2 scatter left without a minimum
+        bool need = false;
+        int cell = 0;
+        if (i < I && j < J && k < K) {
+            const size_t word = (size_t)(i >> 5) + (size_t)WR * (j + (size_t)J * k);
+            cell = i + I * (j + J * k);
+            if (((__ldg(near5 + word) & ~__ldg(occ + word)) >> (i & 31)) & 1u) need = minC[cell] == 0u;
+        }
+        if (!__syncthreads_or(need)) continue;
+        // ---- stage, row by row of the (8+4)^2 rows of 12 cells: the span from the first to the last surface cell
+        int cnt = 0;
+        if (tid < SHELL_ROWS) {
+            const int cj = j0 - 2 + tid % SHELL_F, ck = k0 - 2 + tid / SHELL_F;
+            int first = -1, last = -1, b = 0;
+            if (cj >= 0 && ck >= 0 && cj < J && ck < K) {
+                const unsigned int *sw = surf + (size_t)WR * (cj + (size_t)J * ck);
+                for (int m = 0; m < SHELL_F; m++) {
+                    const int ci = i0 - 2 + m;
+                    if (ci >= 0 && ci < I && ((__ldg(sw + (ci >> 5)) >> (ci & 31)) & 1u)) { if (first < 0) first = m; last = m; }
+                }
+                if (first >= 0) {
+                    const int c = (i0 - 2) + I * (cj + J * ck);
+                    b = __ldg(cellStart + c + first);
+                    cnt = __ldg(cellStart + c + last + 1) - b;
+                    // where each cell of the row begins inside the span (cells outside it: empty ranges at its ends)
+                    for (int m = 0; m <= SHELL_F; m++) {
+                        const int ci = i0 - 2 + m;
+                        const int v = (m <= first) ? 0 : (m > last ? cnt : __ldg(cellStart + c + m) - b);
+                        (void)ci;
+                        off[tid * (SHELL_F + 1) + m] = v;
+                    }
+                }
+            }
+            if (first < 0)
+                for (int m = 0; m <= SHELL_F; m++) off[tid * (SHELL_F + 1) + m] = 0;
+            rowG[tid] = b;
+        }
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+        if (lane == 31) warpSum[wid] = incl;
+        __syncthreads();
+        int base = 0, total = 0;
+        for (int w = 0; w < SHELL_THREADS / 32; w++) { if (w < wid) base += warpSum[w]; total += warpSum[w]; }
+        if (total > SHELL_CAP) {       // (uniform) too crowded for the staging area
+            if (need) {
+                const int slot = warp_append_slot(Q.farCount);
+                Q.farCells[slot] = cell;
+                Q.farBest[slot] = 3.0e38f;
+            }
+            continue;
+        }
+        if (tid < SHELL_ROWS) rowS[tid] = base + incl - cnt;
+        if (tid == 0) rowS[SHELL_ROWS] = total;
+        __syncthreads();
+        for (int r = wid; r < SHELL_ROWS; r += SHELL_THREADS / 32) {
+            const int gb = rowG[r], sb = rowS[r], n = rowS[r + 1] - sb;
+            for (int q = lane; q < n; q += 32) {
+                sx[sb + q] = __ldg(p.px + gb + q); sy[sb + q] = __ldg(p.py + gb + q); sz[sb + q] = __ldg(p.pz + gb + q);
+            }
+        }
+        __syncthreads();
+        if (!need) continue;
+        // ---- the search
+        const int kg = k + g.kOff;
+        const float Xn = (float)i * dxf, Yn = (float)j * dxf, Zn = (float)kg * dxf;       // exact (power-of-two dx)
+        const float Xh = Xn + hw, Yh = Yn + hw, Zh = Zn + hw;
+        const int row0 = (j - j0 + 2) + SHELL_F * (k - k0 + 2), x0 = i - i0 + 2;
+        float best2 = 3.0e38f;
+        for (int o = 0; o < 125; o++) {
+            const unsigned int e = c_shell_order[o];
+            // squared distance to the nearest point of that cell, less a margin against the rounding of the computed ones
+            const float cellMin2 = ((float)((e >> 9) & 3u) * 0.2499f + (float)(e >> 11) * 2.2499f) * dx2;
+            if (!(cellMin2 < best2)) break;          // the cells that follow are no nearer
+            const int di = (int)(e & 7u) - 2, dj = (int)((e >> 3) & 7u) - 2, dk = (int)((e >> 6) & 7u) - 2;
+            const int row = row0 + dj + SHELL_F * dk;
+            const int sb = rowS[row];
+            const int qb = sb + off[row * (SHELL_F + 1) + x0 + di], qe = sb + off[row * (SHELL_F + 1) + x0 + di + 1];
+            for (int q = qb; q < qe; q++) {
+                const float x = sx[q], y = sy[q], z = sz[q];
+                // position relative to the cell's lower corner: inside the search box iff -sr <= u < dx + sr
+                const float ux = fsub(x, Xn), uy = fsub(y, Yn), uz = fsub(z, Zn);
+                if (ux < loOut || ux >= hiOut || uy < loOut || uy >= hiOut || uz < loOut || uz >= hiOut) continue;
+                const bool in = ux >= loIn && ux < hiIn && uy >= loIn && uy < hiIn && uz >= loIn && uz < hiIn;
+                if (!in && !sdf_box_literal(g, x, y, z, i, j, kg)) continue;
+                const float ex = fsub(Xh, x), ey = fsub(Yh, y), ez = fsub(Zh, z);
+                best2 = fminf(best2, fadd(fadd(fmul(ex, ex), fmul(ey, ey)), fmul(ez, ez)));
+            }
+        }
+        if (best2 < 1.0e38f) minC[cell] = ~__float_as_uint(best2);
+    }
+}
+
+// One thread per point (i,j,k) of the extended index space, as k_sdf_p2g: turns the accumulated sums of the three
+// faces of the node into velocities and valid flags and the accumulated minimum of the cell into the liquid SDF
+// (clearing the accumulators for the next step).  A cell that received no minimum lies in no particle's search box.
+__global__ void __launch_bounds__(128) k_p2g_finish(GatherParams g, P2GGlobal G, double invSScale,
+                                                    float *__restrict__ U, float *__restrict__ V, float *__restrict__ W,
+                                                    unsigned char *__restrict__ validU, unsigned char *__restrict__ validV,
+                                                    unsigned char *__restrict__ validW, float *__restrict__ phiL,
+                                                    const float *__restrict__ phiS, const unsigned int *__restrict__ near3,
+                                                    const unsigned int *__restrict__ near5, int WR, SdfQueues Q) {
+    const int I = g.I, J = g.J, K = g.K;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y, k = blockIdx.z;      // k: local plane
+    if (i > I) return;
+    const bool hasU = (j < J && k < K), hasV = (i < I && k < K), hasW = (i < I && j < J), hasC = (i < I && j < J && k < K);
+    const long long iu = (long long)i + (long long)(I + 1) * (j + (long long)J * k);
+    const long long iv = (long long)i + (long long)I * (j + (long long)(J + 1) * k);
+    const long long iw = (long long)i + (long long)I * (j + (long long)J * k);
+    // the neighbourhood bits of the cell the node belongs to (nodes past the last cell of an axis: the last cell)
+    const int ci = min(i, I - 1), cj = min(j, J - 1), ck = min(k, K - 1);
+    const size_t word = (size_t)(ci >> 5) + (size_t)WR * (cj + (size_t)J * ck);
+    const bool n3 = (__ldg(near3 + word) >> (ci & 31)) & 1u;
+    const bool n5 = n3 || ((__ldg(near5 + word) >> (ci & 31)) & 1u);
+    // (all loads first)
+    ulonglong2 aU = make_ulonglong2(0ull, 0ull), aV = aU, aW = aU;
+    if (n3) { if (hasU) aU = G.accU[iu]; if (hasV) aV = G.accV[iv]; if (hasW) aW = G.accW[iw]; }
+    const unsigned int mn = (n5 && hasC) ? G.minC[iw] : 0u;
+    // ---- faces (no particle can reach the faces of a node whose 3x3x3 cells are empty)
+    auto finish = [&](ulonglong2 a, ulonglong2 *acc, long long idx, float *field, unsigned char *valid, int comp) {
+        float val = 0.0f;
+        unsigned char ok = 0;
+        if ((a.x | a.y) != 0ull) {
+            acc[idx] = make_ulonglong2(0ull, 0ull);
+            // coarse + fine / 16, exact in double
+            const double wd = (double)(unsigned int)a.x + 0.0625 * (double)(unsigned int)a.y;
+            const double sd = (double)(int)(a.x >> 32) + 0.0625 * (double)(int)(a.y >> 32);
+            const float wsum = (float)(wd * (1.0 / (double)P2G_WSCALE));
+            const float ssum = (float)(sd * invSScale);
+            int slot = -1;
+            if (wsum < P2G_LITERAL_BAND) slot = warp_append_slot(Q.litCount);
+            if (slot >= 0 && slot < Q.litCap)
+                Q.litFaces[slot] = (comp << 28) | (int)((long long)i + (long long)(I + 1) * (j + (long long)(J + 1) * k));
+            else { ok = wsum > g.eps; val = ok ? __fdiv_rn(ssum, wsum) : ssum; }   // (a full queue costs digits, nothing else)
+        }
+        field[idx] = val;
+        valid[idx] = ok;
+    };
+    if (hasU) finish(aU, G.accU, iu, U, validU, 0);
+    if (hasV) finish(aV, G.accV, iv, V, validV, 1);
+    if (hasW) finish(aW, G.accW, iw, W, validW, 2);
+    if (!hasC) return;
+    // ---- liquid SDF of cell (i,j,k)
+    if (mn) {
+        G.minC[iw] = 0u;
+        phiL[iw] = finish_phi(g, phiS, __uint_as_float(~mn), i, j, k);
+    } else {
+        phiL[iw] = finish_phi(g, phiS, 3.0e38f, i, j, k);
+    }
+}
+
+// The queued faces (total weight below P2G_LITERAL_BAND, or next to a cell too dense for the scatter), ONE WARP PER
+// FACE: the literal weights of the reference (velocityadvector.cpp:436-441), the lanes on consecutive particles of a
+// cell row (coalesced; one thread per face walks ~150 particles through chains of dependent loads), the lane terms
+// folded by a fixed shuffle tree and the rows added in (k, j) order: a fixed summation order, hence deterministic.
+template <int COMP>
+__device__ __forceinline__ void literal_face(const ParticleSoA &p, const int *__restrict__ cellStart, const GatherParams &g, int i,
+                                             int j, int k, float &sum, float &wsum) {
+    const int I = g.I, J = g.J, K = g.K;
+    const int lane = threadIdx.x & 31;
+    const float Xn = (float)dmul((double)(float)i, g.dx), Yn = (float)dmul((double)(float)j, g.dx),
+                Zn = (float)dmul((double)(float)(k + g.kOff), g.dx);
+    // face position: the node, shifted by dx/2 on the two staggered axes
+    const float fx = COMP == 0 ? Xn : fadd(Xn, g.hw), fy = COMP == 1 ? Yn : fadd(Yn, g.hw), fz = COMP == 2 ? Zn : fadd(Zn, g.hw);
+    const float *vel = COMP == 0 ? p.vx : COMP == 1 ? p.vy : p.vz;
+    const int ilo = max(i - 1, 0), ihi = min(COMP == 0 ? i : i + 1, I - 1);
+    const int jlo = max(j - 1, 0), jhi = min(COMP == 1 ? j : j + 1, J - 1);
+    const int klo = max(k - 1, 0), khi = min(COMP == 2 ? k : k + 1, K - 1);
+    sum = 0.0f; wsum = 0.0f;
+    // the (at most nine) row ranges, fetched together by the first lanes
+    int qb = 0, qe = 0;
+    const int nj = jhi - jlo + 1, nk = khi - klo + 1;
+    if (lane < nj * nk) {
+        const int rowBase = I * ((jlo + lane % nj) + J * (klo + lane / nj));
+        qb = __ldg(cellStart + rowBase + ilo);
+        qe = __ldg(cellStart + rowBase + ihi + 1);
+    }
+    for (int r = 0; r < nj * nk; r++) {
+        const int rb = __shfl_sync(0xffffffffu, qb, r), re = __shfl_sync(0xffffffffu, qe, r);
+        for (int q0 = rb; q0 < re; q0 += 32) {
+            const int q = q0 + lane;
+            float ws = 0.0f, w = 0.0f;
+            if (q < re) {
+                const float ax = fsub(fx, __ldg(p.px + q)), ay = fsub(fy, __ldg(p.py + q)), az = fsub(fz, __ldg(p.pz + q));
+                const float d2 = fadd(fadd(fmul(ax, ax), fmul(ay, ay)), fmul(az, az));
+                if (d2 < g.rsq) {
+                    w = kernel_weight(d2, g);
+                    ws = fmul(w, __ldg(vel + q));
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                ws = fadd(ws, __shfl_xor_sync(0xffffffffu, ws, o));
+                w = fadd(w, __shfl_xor_sync(0xffffffffu, w, o));
+            }
+            sum = fadd(sum, ws);
+            wsum = fadd(wsum, w);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_p2g_literal(ParticleSoA p, const int *__restrict__ cellStart, GatherParams g,
+                                                     float *__restrict__ U, float *__restrict__ V, float *__restrict__ W,
+                                                     unsigned char *__restrict__ validU, unsigned char *__restrict__ validV,
+                                                     unsigned char *__restrict__ validW, const int *__restrict__ litFaces,
+                                                     const int *__restrict__ litCount, int litCap) {
+    const int I = g.I, J = g.J, K = g.K;
+    const int n = min(*litCount, litCap);
+    const int nw = (gridDim.x * blockDim.x) >> 5;
+    for (int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < n; t += nw) {
+        const int e = litFaces[t];
+        const int comp = (e >> 28) & 3, node = e & 0x0fffffff;
+        const int i = node % (I + 1), j = (node / (I + 1)) % (J + 1), k = node / ((I + 1) * (J + 1));
+        // (entries queued around a dense cell may name faces that do not exist on the upper borders)
+        if ((comp == 0 && (j >= J || k >= K)) || (comp == 1 && (i >= I || k >= K)) || (comp == 2 && (i >= I || j >= J))) continue;
+        float sum, wsum;
+        long long idx;
+        float *field;
+        unsigned char *valid;
+        if (comp == 0) { literal_face<0>(p, cellStart, g, i, j, k, sum, wsum); idx = (long long)i + (long long)(I + 1) * (j + (long long)J * k); field = U; valid = validU; }
+        else if (comp == 1) { literal_face<1>(p, cellStart, g, i, j, k, sum, wsum); idx = (long long)i + (long long)I * (j + (long long)(J + 1) * k); field = V; valid = validV; }
+        else { literal_face<2>(p, cellStart, g, i, j, k, sum, wsum); idx = (long long)i + (long long)I * (j + (long long)J * k); field = W; valid = validW; }
+        if ((threadIdx.x & 31) == 0) {
+            const bool ok = wsum > g.eps;
+            field[idx] = ok ? __fdiv_rn(sum, wsum) : sum;     // scalar /= weight only if weight > eps (:448-453)
+            valid[idx] = ok ? 1 : 0;
+        }
     }
 }
 
@@ -968,7 +1592,7 @@ static GatherParams make_gather_params(const flip_ctx *c) {
     return g;
 }
 
-// The SDF and the P2G are produced by the same gather; the stage that runs first computes both.
+// The SDF and the P2G are produced together; the stage that runs first computes both.
 static void run_sdf_p2g(flip_ctx *c) {
     const Dims &d = c->d;
     GatherParams g = make_gather_params(c);
@@ -982,14 +1606,89 @@ static void run_sdf_p2g(flip_ctx *c) {
     int *farCells = c->frontier[0];
     float *farBest = reinterpret_cast<float *>(c->frontier[1]);
     int *farCount = &c->dS->frontierCount[0];
-    FLIP_CUDA_CHECK(cudaMemsetAsync(farCount, 0, sizeof(int), c->stream));
-    if (dyadic)
+    FLIP_CUDA_CHECK(cudaMemsetAsync(c->dS->frontierCount, 0, 2 * sizeof(int), c->stream));
+    // the scatter: single-precision mode, power-of-two dx
+    const bool scatter = dyadic && g.packed && (long long)d.nN < (1ll << 28) && !getenv("FLIP_P2G_GATHER");
+    if (scatter) {
+        const int WR = cdiv(d.I, 32);
+        const size_t words = (size_t)WR * d.J * d.K;
+        if (!c->p2gAcc[0]) {
+            const size_t n[4] = {2 * (size_t)d.nU, 2 * (size_t)d.nV, 2 * (size_t)d.nW, ((size_t)d.nC + 1) / 2};
+            for (int m = 0; m < 4; m++) {
+                FLIP_CUDA_CHECK(cudaMalloc(&c->p2gAcc[m], sizeof(unsigned long long) * (n[m] + 16)));
+                FLIP_CUDA_CHECK(cudaMemsetAsync(c->p2gAcc[m], 0, sizeof(unsigned long long) * (n[m] + 16), c->stream));
+            }
+        }
+        P2GGlobal G;
+        G.accU = (ulonglong2 *)c->p2gAcc[0]; G.accV = (ulonglong2 *)c->p2gAcc[1];
+        G.accW = (ulonglong2 *)c->p2gAcc[2]; G.minC = (unsigned int *)c->p2gAcc[3];
+        unsigned int *bits = c->occBits, *near3 = bits + words, *near5 = bits + 2 * words;
+        const size_t stride = ext_stride(d);
+        SdfQueues Q;
+        Q.farCells = farCells; Q.farBest = farBest; Q.farCount = farCount;
+        Q.litFaces = c->frontier[1] + stride; Q.litCount = &c->dS->frontierCount[1]; Q.litCap = (int)std::min<size_t>(2 * stride, 1u << 30);
+        // momentum scale 2^q: the largest power of two with vmax 2^q <= 2^18 (vmax: the maximum particle speed, from the sort)
+        // momentum scale 2^q: the largest power of two with vmax 2^q <= 2^21 (vmax: the maximum particle speed, from the sort)
+        float vmax2;
+        { const unsigned int bitsv = c->hS->maxSpeedSqBits; memcpy(&vmax2, &bitsv, sizeof(float)); }
+        const double vmax = std::max(std::sqrt((double)vmax2) * 1.0000002, 1e-30);
+        int q = (int)std::floor(std::log2(2097152.0 / vmax));
+        q = std::max(-60, std::min(100, q));
+        const float sScale = (float)std::ldexp(1.0, q - 22);
+        const double invSScale = std::ldexp(1.0, -q);
+        unsigned int *surf = c->occBits + 3 * words;
+        const int tX = cdiv(d.I, P2G_T), tY = cdiv(d.J, P2G_T), tZ = cdiv(d.K, P2G_T);
+        // tile bookkeeping: [0,4) counts and tickets, then flags (two per tile; x tiles padded to whole words of the
+        // bitmaps), then the two lists
+        const int nTiles = tX * tY * tZ, nFlagTiles = nTiles + 8;
+        if (!c->p2gTiles) {
+            FLIP_CUDA_CHECK(cudaMalloc(&c->p2gTiles, sizeof(int) * (8 + 2 * (size_t)nFlagTiles + 2 * (size_t)nTiles)));
+            FLIP_CUDA_CHECK(cudaMemsetAsync(c->p2gTiles, 0, sizeof(int) * (8 + 2 * (size_t)nFlagTiles + 2 * (size_t)nTiles), c->stream));
+        }
+        int *tileCounts = c->p2gTiles, *tileFlags = c->p2gTiles + 8, *listP = tileFlags + 2 * nFlagTiles, *listS = listP + nTiles;
+        FLIP_CUDA_CHECK(cudaMemsetAsync(tileCounts, 0, 4 * sizeof(int), c->stream));
+        if (!c->occBitsValid) {
+            k_occ_bits<<<cdiv((long long)words * 32, TPB), TPB, 0, c->stream>>>(c->cellStart, d.I, d.J * d.K, WR, bits);
+            c->launches++;
+        }
+        k_occ_dilate<<<cdiv((long long)words, TPB), TPB, 0, c->stream>>>(bits, d.I, d.J, d.K, WR, near3, near5, surf, tileFlags);
+        k_tile_lists<<<cdiv(nTiles, TPB), TPB, 0, c->stream>>>(nTiles, tileFlags, listP, listS, tileCounts);
+        const size_t smem = (size_t)P2G_SLOTS * P2G_WORDS * sizeof(int);
+        {
+            static bool attrS = false;
+            if (!attrS) {
+                FLIP_CUDA_CHECK(cudaFuncSetAttribute(k_p2g_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                attrS = true;
+            }
+        }
+        k_p2g_scatter<<<148 * 3, P2G_THREADS, smem, c->stream>>>(c->P[c->cur_buf], c->cellStart, g, G, tX, tY, sScale, Q, listP, tileCounts);
+        {
+            static bool attr = false;
+            const size_t shellSmem = 3 * (size_t)SHELL_CAP * sizeof(float);
+            if (!attr) {
+                FLIP_CUDA_CHECK(cudaFuncSetAttribute(k_sdf_shell, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shellSmem));
+                attr = true;
+            }
+            k_sdf_shell<<<148 * 2, SHELL_THREADS, shellSmem, c->stream>>>(c->P[c->cur_buf], c->cellStart, g, bits, near5, surf, WR,
+                                                                         G.minC, tX, tY, Q, listS, tileCounts);
+        }
+        k_p2g_finish<<<grid, block, 0, c->stream>>>(g, G, invSScale, c->U, c->V, c->W, c->validU, c->validV, c->validW, c->phiL,
+                                                    c->phiS, near3, near5, WR, Q);
+        k_p2g_literal<<<148 * 8, 256, 0, c->stream>>>(c->P[c->cur_buf], c->cellStart, g, c->U, c->V, c->W, c->validU, c->validV,
+                                                      c->validW, Q.litFaces, Q.litCount, Q.litCap);
+        // (cells of a region too crowded for the shell kernel's staging area; it is after k_p2g_finish that their value stands)
+        k_sdf_far<<<148 * 8, 256, 0, c->stream>>>(c->P[c->cur_buf], c->cellStart, g, c->phiL, c->phiS, farCells, farBest, farCount);
+        c->launches += 7;
+        kt_end(c, FLIP_KERNEL_SDF_P2G, kt);
+        FLIP_CUDA_CHECK(cudaGetLastError());
+        return;
+    } else if (dyadic)
         k_sdf_p2g<true><<<grid, block, 0, c->stream>>>(c->P[c->cur_buf], c->cellStart, g, c->U, c->V, c->W, c->validU, c->validV,
                                                        c->validW, c->phiL, c->phiS, c->occ, farCells, farBest, farCount);
     else
         k_sdf_p2g<false><<<grid, block, 0, c->stream>>>(c->P[c->cur_buf], c->cellStart, g, c->U, c->V, c->W, c->validU, c->validV,
                                                         c->validW, c->phiL, c->phiS, c->occ, farCells, farBest, farCount);
-    k_sdf_far<<<148 * 8, 128, 0, c->stream>>>(c->P[c->cur_buf], c->cellStart, g, c->phiL, c->phiS, farCells, farBest, farCount);
+    k_sdf_far<<<148 * 8, 256, 0, c->stream>>>(c->P[c->cur_buf], c->cellStart, g, c->phiL, c->phiS, farCells, farBest, farCount);
     c->launches++;
     kt_end(c, FLIP_KERNEL_SDF_P2G, kt);
     c->launches++;

@@ -684,8 +684,10 @@ __device__ __forceinline__ float sm_residual(const SmLevel &L, const float *x, i
 
 // ---- the shared-memory levels.  The passes are written once for a generic thread group (tid, nt, sync): the whole
 // CTA with __syncthreads for the levels of more than SM_WARP_CELLS cells, ONE WARP with __syncwarp below that
-// (a 1024-thread barrier per pass costs more than the pass itself on a level of 8^3 cells or fewer).
-static constexpr int SM_WARP_CELLS = 512;
+// (a 1024-thread barrier per pass costs more than the pass itself on a level of 4^3 cells or fewer; measured on
+// the B200: with the 8^3 level in one warp as well the levels take 38 us instead of 19 -- a single warp has nothing
+// to hide the shared-memory latency of its sixteen cells per lane behind).
+static constexpr int SM_WARP_CELLS = 64;
 
 // nu pre-sweeps from a zero guess (or `sweeps` of them on the coarsest level); leaves the result in L.x
 template <class Sync>
@@ -777,9 +779,18 @@ __device__ __forceinline__ void sm_cycle(const SmLevel *sl, int first, int last,
 }
 
 // the shared-memory levels first..last of the V-cycle, called by every thread of ONE CTA
-__device__ __forceinline__ void sm_small_body(const SmLevel *sl, int first, int last, const MgParams &p) {
+// (tr: developer probe, a globaltimer stamp after every CTA-wide pass)
+__device__ __forceinline__ void sm_small_body(const SmLevel *sl, int first, int last, const MgParams &p,
+                                              unsigned long long *tr = nullptr, int *ntr = nullptr) {
     const int tid = threadIdx.x, nt = blockDim.x;
-    auto bsync = [] { __syncthreads(); };
+    auto bsync = [&] {
+        __syncthreads();
+        if (tr && tid == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+            tr[(*ntr)++] = t;
+        }
+    };
     auto wsync = [] { __syncwarp(); };
     int lw = first;     // first level small enough for one warp
     while (lw <= last && sl[lw].n > SM_WARP_CELLS) lw++;
@@ -1041,7 +1052,7 @@ __global__ void __launch_bounds__(1024) k_mg_coarse(MgCoarseArgs A, const Device
             for (int c = tid; c < Gl.n; c += nt) L.b[c] = Gl.b[c];
             __syncthreads();
             stamp();
-            sm_small_body(sl, A.fs, A.last, A.p);
+            sm_small_body(sl, A.fs, A.last, A.p, A.trace, &ntrace);
             stamp();
             for (int c = tid; c < Gl.n; c += nt) Gl.x[c] = L.x[c];
         }
@@ -1842,7 +1853,10 @@ struct PressureScratch {
     size_t coarseSmemBytes = 0;        // dynamic shared memory of k_mg_coarse (0: not usable, per-pass launches instead)
     int coarseBlocks = 0;              // its cooperative grid: one CTA per SM
     double *vq = nullptr, *vs2 = nullptr, *vr2 = nullptr;   // fused PCG passes: q = A s, ping-pong partners of s and r
-    int coarseGroup = 16;              // CTAs of that grid that run the levels >= 2 (k_mg_coarse)
+    int coarseGroup = 1 << 20;         // CTAs of that grid that run the levels >= 2 (k_mg_coarse); default: all of them
+                                       // (measured at 2 M rows: V-cycle 0.293 / 0.263 / 0.248 / 0.242 / 0.238 ms with
+                                       // 4 / 8 / 16 / 32 / 148 CTAs -- the passes are bound by their chains of dependent
+                                       // loads, which more CTAs walk in fewer rounds, not by the barrier)
     unsigned int *groupBar = nullptr;  // their barrier counter
     float *coarseBase = nullptr;       // levels >= 1 inside `pool` (L2 persistence window)
     size_t coarseBytes = 0, l2SetAside = 0, l2Window = 0;
@@ -2137,6 +2151,9 @@ void stage_pressure(flip_ctx *c, double dt) {
     }
     segBlocks = std::max(1, cdiv((long long)numSeg * 32, TPB));
     const int loopBlocks = std::min(segBlocks, 148 * 6);    // grid-stride passes: one resident wave
+    // the fused kernels hold five CTAs per SM (48 registers): a grid of 148 x 6 would leave a second, nearly empty wave
+    // that takes as long as the first (grid-stride loop: every CTA does the same share of the work)
+    const int fusedBlocks = std::min(segBlocks, 148 * 5);
     PcgParams pp;
     pp.g = g;
     pp.factor = bp.factor;
@@ -2351,7 +2368,7 @@ void stage_pressure(flip_ctx *c, double dt) {
             float *xa = ps->lv[0].x, *xb = ps->lv[0].x2;
             int sw = 0;
             if (fusedIt >= 0) {
-                k_pcg_update_presweep<<<loopBlocks, TPB, 0, st>>>(c->segCell, c->segMask, m0, c->vs, ps->vq, c->vx_, c->vr, ps->vr2, xb,
+                k_pcg_update_presweep<<<fusedBlocks, TPB, 0, st>>>(c->segCell, c->segMask, m0, c->vs, ps->vq, c->vx_, c->vr, ps->vr2, xb,
                                                                  pre_om(1), pre_om(0), c->dS, fusedIt);
                 c->launches++;
                 std::swap(c->vr, ps->vr2);
@@ -2502,7 +2519,7 @@ void stage_pressure(flip_ctx *c, double dt) {
         // iteration it is taken by dir_spmv(it+1), which returns at once when the residual is below the tolerance
         auto dir_spmv = [&](int i) {
             size_t ktSp = kt_begin(c);
-            k_pcg_dir_spmv<<<loopBlocks, TPB, 0, st>>>(c->segCell, c->segMask, pp, c->Adiag, c->AoffU, c->AoffV, c->AoffW, c->vz,
+            k_pcg_dir_spmv<<<fusedBlocks, TPB, 0, st>>>(c->segCell, c->segMask, pp, c->Adiag, c->AoffU, c->AoffV, c->AoffW, c->vz,
                                                       c->vs, ps->vs2, ps->vq, c->dS, i);
             kt_end(c, FLIP_KERNEL_PCG_DIR_SPMV, ktSp);
             c->launches++;

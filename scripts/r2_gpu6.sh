@@ -1,0 +1,4 @@
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -x -q --tb=short > gpurun_out/r2f_pytest.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/r2f_pytest.log
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/r2f_launches.csv python scripts/profile_step.py sphere256 3 1 > gpurun_out/r2f_prof.log 2>&1; echo "ncu rc=$?"
+python scripts/ncu_summary.py launches gpurun_out/r2f_launches.csv gpurun_out/r2f_launches.md; head -45 gpurun_out/r2f_launches.md

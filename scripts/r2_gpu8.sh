@@ -1,0 +1,11 @@
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -x -q --tb=short > gpurun_out/r2h_pytest.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/r2h_pytest.log
+timeout 600 python bench.py --steps 6 --warmup 3 --exact-steps 0 --cpu-budget 0 > gpurun_out/r2h_bench.json 2> gpurun_out/r2h_bench.err; echo "bench rc=$?"
+python - <<P
+import json
+d=json.loads(open('gpurun_out/r2h_bench.json').read().strip().splitlines()[-1])
+print('ms/step', round(d['ms_per_step'],3), 'ms/substep', round(d['config']['ms_per_substep'],3), 'its', d['config']['pcg_iterations_timed'])
+print('  ', {k: round(v['avg_ms'],4) for k,v in d['kernels'].items()})
+P
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/r2h_launches.csv python scripts/profile_step.py sphere256 3 1 > gpurun_out/r2h_prof.log 2>&1; echo "ncu rc=$?"
+python scripts/ncu_summary.py launches gpurun_out/r2h_launches.csv gpurun_out/r2h_launches.md; grep -E "p2g|sdf|occ" gpurun_out/r2h_launches.md

@@ -329,7 +329,7 @@ def check_report(rep, dx=0.125, isolate=True, exact_sampling=False):
         assert rep["g2p.shared_slot_err"] <= 1e-5, rep
     # float fields
     for comp in "UVW":
-        assert rep[f"p2g.{comp}.rel_l2"] <= TOL_P2G_REL_L2, rep
+        assert field_ok(rep, "p2g", comp, TOL_P2G_REL_L2), rep
         assert field_ok(rep, "pressure", comp, TOL_REL_L2), rep
         assert field_ok(rep, "extrapolate_b", comp, TOL_REL_L2), rep
     assert rep["g2p.vel.rel_l2"] <= TOL_REL_L2, rep

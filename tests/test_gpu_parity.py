@@ -84,9 +84,13 @@ def test_stages_against_golden(dam24, prec, sampling):
     sim.stage("liquid_sdf", dt)
     sim.stage("p2g", dt)
     assert np.array_equal(sim.array("liquid_phi"), g["liquid_phi"])
+    # (the column has only just started to fall: U and W are rounding noise, ~1e-7 next to |V| ~ 1, and have no meaningful
+    # relative error -- such a component passes on the float-storage floor of the field, see parity_common.field_ok)
+    scale = max(float(np.abs(g["p2g." + n]).max()) for n in "UVW")
     for n in "UVW":
         assert np.array_equal(sim.array("valid" + n), g["p2g.valid" + n])
-        assert pc.rel_l2(sim.array(n), g["p2g." + n]) <= pc.TOL_P2G_REL_L2
+        assert (pc.rel_l2(sim.array(n), g["p2g." + n]) <= pc.TOL_P2G_REL_L2
+                or pc.max_abs(sim.array(n), g["p2g." + n]) <= pc.TOL_FIELD_FLOOR * scale), n
     # extrapolation: bit exact from the golden input
     load("p2g")
     sim.stage("extrapolate_a", dt)
