@@ -969,7 +969,9 @@ __global__ void __launch_bounds__(256) k_sdf_far(ParticleSoA p, const int *__res
 //     W = sum wq,  wq = round(w * 2^22)       u32: no overflow below sum(w) = 1024, i.e. 56 particles in each of the
 //                                             18 cells that can reach a face (denser cells: see below)
 //     S = sum round(wq v 2^(q-22))            i32: 2^q = the largest power of two with vmax 2^q <= 2^21, vmax = the
-//                                             maximum particle speed of the step (known from the sort)
+//                                             largest magnitude of that velocity component among the TILE's particles
+//                                             (a pass over the tile's velocities first; a few fast particles elsewhere
+//                                             in the domain cost this tile no digits)
 // in TWO TIERS: a contribution of weight below 1/16 goes to a second pair of words scaled 16 times finer (same bounds:
 // the terms are 16 times smaller).  S is formed from the ROUNDED weight, so u = S/W is a weighted mean with weights
 // wq/2^22 (2^26): the rounding of the weights only enters through the velocity differences of the contributors, and
@@ -1086,7 +1088,8 @@ __device__ __forceinline__ unsigned int smem_addr(const void *p) { return (unsig
 template <int OFF>
 __device__ __forceinline__ void p2g_candidate(float d2, float rsq, float c1, float c2, float c3, float vs, unsigned int addr) {
     float w = fmaf(fmaf(fmaf(c1, d2, c2), d2, c3), d2, 1.0f);
-    w = d2 < rsq ? w : 0.0f;
+    // (the polynomial is a few 1e-8 below zero at the very rim of the support; the sums are unsigned)
+    w = d2 < rsq ? fmaxf(w, 0.0f) : 0.0f;
     const bool fine = w < 0.0625f;
     const float t = fmaf(w, fine ? 16.0f * P2G_WSCALE : P2G_WSCALE, P2G_MAGIC);
     const int iw = __float_as_int(t) - P2G_MAGIC_BITS;
@@ -1118,21 +1121,26 @@ __device__ __forceinline__ void sdf_candidate(float xy, float zz, float thr, uns
 }
 
 struct P2GGlobal {
-    ulonglong2 *accU, *accV, *accW;           // per face: x = S << 32 | W of the coarse tier, y = of the fine tier
+    ulonglong2 *accU, *accV, *accW;           // per face: see below
     unsigned int *minC;                       // per cell: ~bits of the minimum squared distance, 0 = none
 };
+// global accumulators of a face: x = sum of weights in units of 2^-26, y = sum of momenta in units of 2^-(qg+24), qg:
+// the scale exponent that the largest speed of the whole domain would get (every tile's own exponent lies in
+// [qg, qg+20])
 struct SdfQueues {
     int *farCells; float *farBest; int *farCount;   // (gather path only) no particle within 1.45 dx: the 5x5x5 box (k_sdf_far)
     int *litFaces, *litCount; int litCap;           // faces below P2G_LITERAL_BAND or next to a dense cell (k_p2g_literal)
 };
 
 __global__ void __launch_bounds__(P2G_THREADS, 3) k_p2g_scatter(ParticleSoA p, const int *__restrict__ cellStart, GatherParams g,
-                                                               P2GGlobal G, int tilesX, int tilesY, float sScale, SdfQueues Q,
+                                                               P2GGlobal G, int tilesX, int tilesY, int qg, SdfQueues Q,
                                                                const int *__restrict__ tileList, int *__restrict__ tileCounts) {
     extern __shared__ int acc[];         // [slot][P2G_WORDS]
     __shared__ int rowBeg[P2G_ROWS], rowPre[P2G_ROWS + 1];
     __shared__ unsigned int rowDense[P2G_ROWS];    // bit i: cell i of the row is too dense for the fixed-point sums
     __shared__ int nextTile;
+    __shared__ float vmaxWarp[P2G_THREADS / 32][3];
+    __shared__ int qTile[3];
     const int tid = threadIdx.x, lane = tid & 31;
     const int I = g.I, J = g.J, K = g.K;
     const float dxf = (float)g.dx, invf = (float)g.invdx, hw = g.hw, rsq = g.rsq;
@@ -1209,14 +1217,42 @@ __global__ void __launch_bounds__(P2G_THREADS, 3) k_p2g_scatter(ParticleSoA p, c
         for (int s = P2G_ROWS / 2; s > 0; s >>= 1)
             if (rowPre[row + s] <= idx) row += s;
     }
+    // ---- the momentum scales of this tile: largest |vx|, |vy|, |vz| of its particles
+    {
+        // (warp w reads the rows w, w + 16, ...: coalesced, and the lines are in L1 when the scatter below asks for them)
+        float mx = 0.0f, my = 0.0f, mz = 0.0f;
+        for (int r2 = tid >> 5; r2 < P2G_ROWS; r2 += P2G_THREADS / 32) {
+            const int qb = rowBeg[r2], qe = qb + (rowPre[r2 + 1] - rowPre[r2]);
+            for (int q = qb + lane; q < qe; q += 32) {
+                mx = fmaxf(mx, fabsf(__ldg(p.vx + q))); my = fmaxf(my, fabsf(__ldg(p.vy + q))); mz = fmaxf(mz, fabsf(__ldg(p.vz + q)));
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o)); my = fmaxf(my, __shfl_xor_sync(0xffffffffu, my, o));
+            mz = fmaxf(mz, __shfl_xor_sync(0xffffffffu, mz, o));
+        }
+        if (lane == 0) { vmaxWarp[tid >> 5][0] = mx; vmaxWarp[tid >> 5][1] = my; vmaxWarp[tid >> 5][2] = mz; }
+        __syncthreads();
+        if (tid < 3) {
+            float m = 0.0f;
+            for (int w = 0; w < P2G_THREADS / 32; w++) m = fmaxf(m, vmaxWarp[w][tid]);
+            // m < 2^e  =>  m 2^(21-e) < 2^21
+            const int e = (m > 0.0f && m < 3.0e38f) ? ilogbf(m) + 1 : -1000;
+            qTile[tid] = min(max(21 - e, qg), qg + 20);
+        }
+        __syncthreads();
+    }
+    const int qx = qTile[0], qy = qTile[1], qz = qTile[2];
+    const float sScaleX = __int_as_float((qx - 22 + 127) << 23), sScaleY = __int_as_float((qy - 22 + 127) << 23),
+                sScaleZ = __int_as_float((qz - 22 + 127) << 23);
     for (; idx < idxEnd; idx++) {
         while (idx >= rowPre[row + 1]) row++;
         const int q = rowBeg[row] + (idx - rowPre[row]);
         const float pos[3] = {__ldg(p.px + q), __ldg(p.py + q), __ldg(p.pz + q)};
-        // v 2^(q-22), at most 1/2 in magnitude; the clamp only guards the range of the mantissa trick against a speed
-        // above the recorded maximum
-        const float vsx = fminf(fmaxf(__ldg(p.vx + q) * sScale, -1.0f), 1.0f), vsy = fminf(fmaxf(__ldg(p.vy + q) * sScale, -1.0f), 1.0f),
-                    vsz = fminf(fmaxf(__ldg(p.vz + q) * sScale, -1.0f), 1.0f);
+        // v 2^(q-22), at most 1/2 in magnitude (the clamp only matters if qg was computed from too small a speed)
+        const float vsx = fminf(fmaxf(__ldg(p.vx + q) * sScaleX, -1.0f), 1.0f), vsy = fminf(fmaxf(__ldg(p.vy + q) * sScaleY, -1.0f), 1.0f),
+                    vsz = fminf(fmaxf(__ldg(p.vz + q) * sScaleZ, -1.0f), 1.0f);
         // per axis: the planes below / above the particle (a: through the nodes, b: through the cell centres), the
         // offsets to them -- each ONE rounding of the exact difference, as the literal fsub(plane, p) -- and their
         // squares.  dx is a power of two and the indices are far below 2^24: plane coordinates are exact.
@@ -1260,8 +1296,10 @@ __global__ void __launch_bounds__(P2G_THREADS, 3) k_p2g_scatter(ParticleSoA p, c
         auto flush = [&](int comp, ulonglong2 *dst, size_t idx) {
             const unsigned int wc = a[4 * comp], wf = a[4 * comp + 2];
             const int sc = a[4 * comp + 1], sf = a[4 * comp + 3];
-            if (wc | (unsigned int)sc) atomicAdd(&dst[idx].x, ((unsigned long long)(unsigned int)sc << 32) + wc);
-            if (wf | (unsigned int)sf) atomicAdd(&dst[idx].y, ((unsigned long long)(unsigned int)sf << 32) + wf);
+            if (!(wc | wf | (unsigned int)sc | (unsigned int)sf)) return;
+            const int qt = comp == 0 ? qx : comp == 1 ? qy : qz;
+            atomicAdd(&dst[idx].x, (unsigned long long)wc * 16ull + wf);
+            atomicAdd(&dst[idx].y, (unsigned long long)(((long long)sc * 16 + (long long)sf) * (1ll << (qg + 20 - qt))));
         };
         if (fi <= I && fj < J && fk < K) flush(0, G.accU, (size_t)fi + (size_t)(I + 1) * ((size_t)fj + (size_t)J * (size_t)fk));
         if (fi < I && fj <= J && fk < K) flush(1, G.accV, (size_t)fi + (size_t)I * ((size_t)fj + (size_t)(J + 1) * (size_t)fk));
@@ -1285,8 +1323,8 @@ __global__ void __launch_bounds__(P2G_THREADS, 3) k_p2g_scatter(ParticleSoA p, c
 // particles than the staging area holds sends its cells to k_sdf_far instead.
 static constexpr int SHELL_F = P2G_T + 4;
 static constexpr int SHELL_ROWS = SHELL_F * SHELL_F;
-static constexpr int SHELL_THREADS = 512;
-static constexpr int SHELL_CAP = 6144;      // particles staged per tile (72 KB)
+static constexpr int SHELL_THREADS = 256;
+static constexpr int SHELL_CAP = 4096;      // particles staged per tile (48 KB)
 // the 125 cell offsets ordered by the distance of the cell from the centre of the middle one:
 // (di+2) | (dj+2) << 3 | (dk+2) << 6 | n1 << 9 | n2 << 11, n1 / n2 = number of axes with |d| = 1 / 2
 __constant__ unsigned short c_shell_order[125] = {
@@ -1320,7 +1358,8 @@ __global__ void __launch_bounds__(SHELL_THREADS) k_sdf_shell(ParticleSoA p, cons
     __shared__ int off[SHELL_ROWS * (SHELL_F + 1)];   // staged range of every cell of the region, row by row
     __shared__ int rowG[SHELL_ROWS], rowS[SHELL_ROWS + 1];   // first particle of the row's span (global / staged)
     __shared__ int warpSum[SHELL_THREADS / 32];
-    __shared__ int nextTile;
+    __shared__ short needList[P2G_T * P2G_T * P2G_T];        // the unsettled cells of the tile, compacted
+    __shared__ int nextTile, needCount;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int I = g.I, J = g.J, K = g.K;
     const float dxf = (float)g.dx, hw = g.hw, sr = g.srS, margin = 1.0e-3f * dxf, dx2 = dxf * dxf;
@@ -1329,22 +1368,25 @@ __global__ void __launch_bounds__(SHELL_THREADS) k_sdf_shell(ParticleSoA p, cons
     const int nTiles = tileCounts[1];
     for (;;) {
         __syncthreads();
-        if (tid == 0) nextTile = atomicAdd(&tileCounts[3], 1);
+        if (tid == 0) { nextTile = atomicAdd(&tileCounts[3], 1); needCount = 0; }
         __syncthreads();
         if (nextTile >= nTiles) break;
         const int tile = tileList[nextTile];
         const int tx = tile % tilesX, ty = (tile / tilesX) % tilesY, tz = tile / (tilesX * tilesY);
         const int i0 = tx * P2G_T, j0 = ty * P2G_T, k0 = tz * P2G_T;
-        const int i = i0 + (tid % P2G_T), j = j0 + (tid / P2G_T) % P2G_T, k = k0 + tid / (P2G_T * P2G_T);
         // unsettled: an empty cell within reach of a particle that the 2x2x2 scatter left without a minimum
-        bool need = false;
-        int cell = 0;
-        if (i < I && j < J && k < K) {
-            const size_t word = (size_t)(i >> 5) + (size_t)WR * (j + (size_t)J * k);
-            cell = i + I * (j + J * k);
-            if (((__ldg(near5 + word) & ~__ldg(occ + word)) >> (i & 31)) & 1u) need = minC[cell] == 0u;
+        for (int t = tid; t < P2G_T * P2G_T * P2G_T; t += SHELL_THREADS) {
+            const int i = i0 + (t % P2G_T), j = j0 + (t / P2G_T) % P2G_T, k = k0 + t / (P2G_T * P2G_T);
+            bool need = false;
+            if (i < I && j < J && k < K) {
+                const size_t word = (size_t)(i >> 5) + (size_t)WR * (j + (size_t)J * k);
+                if (((__ldg(near5 + word) & ~__ldg(occ + word)) >> (i & 31)) & 1u) need = minC[i + I * (j + J * k)] == 0u;
+            }
+            if (need) needList[atomicAdd(&needCount, 1)] = (short)t;
         }
-        if (!__syncthreads_or(need)) continue;
+        __syncthreads();
+        const int nNeed = needCount;
+        if (nNeed == 0) continue;
         // ---- stage, row by row of the (8+4)^2 rows of 12 cells: the span from the first to the last surface cell
         int cnt = 0;
         if (tid < SHELL_ROWS) {
@@ -1352,25 +1394,33 @@ __global__ void __launch_bounds__(SHELL_THREADS) k_sdf_shell(ParticleSoA p, cons
             int first = -1, last = -1, b = 0;
             if (cj >= 0 && ck >= 0 && cj < J && ck < K) {
                 const unsigned int *sw = surf + (size_t)WR * (cj + (size_t)J * ck);
-                for (int m = 0; m < SHELL_F; m++) {
-                    const int ci = i0 - 2 + m;
-                    if (ci >= 0 && ci < I && ((__ldg(sw + (ci >> 5)) >> (ci & 31)) & 1u)) { if (first < 0) first = m; last = m; }
+                // the twelve surface bits of the row (cells i0-2 .. i0+9: at most two words)
+                unsigned int bits12 = 0u;
+                {
+                    const int lo = i0 - 2;
+                    const int w0 = lo >> 5;                      // (arithmetic shift: -1 for lo < 0)
+                    const unsigned long long two = ((w0 >= 0 && w0 < WR) ? (unsigned long long)__ldg(sw + w0) : 0ull) |
+                                                   ((w0 + 1 >= 0 && w0 + 1 < WR) ? (unsigned long long)__ldg(sw + w0 + 1) << 32 : 0ull);
+                    bits12 = (unsigned int)(two >> (lo - w0 * 32)) & 0xfffu;
                 }
-                if (first >= 0) {
+                if (bits12) {
+                    first = __ffs(bits12) - 1;
+                    last = 31 - __clz(bits12);
                     const int c = (i0 - 2) + I * (cj + J * ck);
+                    // where each cell of the row begins inside the span (cells outside it: empty ranges at its ends)
+                    int cs[SHELL_F + 1];
+#pragma unroll
+                    for (int m = 0; m <= SHELL_F; m++) cs[m] = (m >= first && m <= last + 1) ? __ldg(cellStart + c + m) : 0;
                     b = __ldg(cellStart + c + first);
                     cnt = __ldg(cellStart + c + last + 1) - b;
-                    // where each cell of the row begins inside the span (cells outside it: empty ranges at its ends)
-                    for (int m = 0; m <= SHELL_F; m++) {
-                        const int ci = i0 - 2 + m;
-                        const int v = (m <= first) ? 0 : (m > last ? cnt : __ldg(cellStart + c + m) - b);
-                        (void)ci;
-                        off[tid * (SHELL_F + 1) + m] = v;
-                    }
+#pragma unroll
+                    for (int m = 0; m <= SHELL_F; m++) off[tid * (SHELL_F + 1) + m] = (m <= first) ? 0 : (m > last ? cnt : cs[m] - b);
                 }
             }
-            if (first < 0)
+            if (first < 0) {
+#pragma unroll
                 for (int m = 0; m <= SHELL_F; m++) off[tid * (SHELL_F + 1) + m] = 0;
+            }
             rowG[tid] = b;
         }
         int incl = cnt;
@@ -1379,11 +1429,13 @@ __global__ void __launch_bounds__(SHELL_THREADS) k_sdf_shell(ParticleSoA p, cons
         if (lane == 31) warpSum[wid] = incl;
         __syncthreads();
         int base = 0, total = 0;
+#pragma unroll
         for (int w = 0; w < SHELL_THREADS / 32; w++) { if (w < wid) base += warpSum[w]; total += warpSum[w]; }
         if (total > SHELL_CAP) {       // (uniform) too crowded for the staging area
-            if (need) {
+            for (int t = tid; t < nNeed; t += SHELL_THREADS) {
+                const int q = needList[t];
                 const int slot = warp_append_slot(Q.farCount);
-                Q.farCells[slot] = cell;
+                Q.farCells[slot] = (i0 + (q % P2G_T)) + I * ((j0 + (q / P2G_T) % P2G_T) + J * (k0 + q / (P2G_T * P2G_T)));
                 Q.farBest[slot] = 3.0e38f;
             }
             continue;
@@ -1398,93 +1450,118 @@ __global__ void __launch_bounds__(SHELL_THREADS) k_sdf_shell(ParticleSoA p, cons
             }
         }
         __syncthreads();
-        if (!need) continue;
-        // ---- the search
-        const int kg = k + g.kOff;
-        const float Xn = (float)i * dxf, Yn = (float)j * dxf, Zn = (float)kg * dxf;       // exact (power-of-two dx)
-        const float Xh = Xn + hw, Yh = Yn + hw, Zh = Zn + hw;
-        const int row0 = (j - j0 + 2) + SHELL_F * (k - k0 + 2), x0 = i - i0 + 2;
-        float best2 = 3.0e38f;
-        for (int o = 0; o < 125; o++) {
-            const unsigned int e = c_shell_order[o];
-            // squared distance to the nearest point of that cell, less a margin against the rounding of the computed ones
-            const float cellMin2 = ((float)((e >> 9) & 3u) * 0.2499f + (float)(e >> 11) * 2.2499f) * dx2;
-            if (!(cellMin2 < best2)) break;          // the cells that follow are no nearer
-            const int di = (int)(e & 7u) - 2, dj = (int)((e >> 3) & 7u) - 2, dk = (int)((e >> 6) & 7u) - 2;
-            const int row = row0 + dj + SHELL_F * dk;
-            const int sb = rowS[row];
-            const int qb = sb + off[row * (SHELL_F + 1) + x0 + di], qe = sb + off[row * (SHELL_F + 1) + x0 + di + 1];
-            for (int q = qb; q < qe; q++) {
-                const float x = sx[q], y = sy[q], z = sz[q];
-                // position relative to the cell's lower corner: inside the search box iff -sr <= u < dx + sr
-                const float ux = fsub(x, Xn), uy = fsub(y, Yn), uz = fsub(z, Zn);
-                if (ux < loOut || ux >= hiOut || uy < loOut || uy >= hiOut || uz < loOut || uz >= hiOut) continue;
-                const bool in = ux >= loIn && ux < hiIn && uy >= loIn && uy < hiIn && uz >= loIn && uz < hiIn;
-                if (!in && !sdf_box_literal(g, x, y, z, i, j, kg)) continue;
-                const float ex = fsub(Xh, x), ey = fsub(Yh, y), ez = fsub(Zh, z);
-                best2 = fminf(best2, fadd(fadd(fmul(ex, ex), fmul(ey, ey)), fmul(ez, ez)));
+        // ---- the search, one thread per unsettled cell
+        for (int t = tid; t < nNeed; t += SHELL_THREADS) {
+            const int q0 = needList[t];
+            const int li = q0 % P2G_T, lj = (q0 / P2G_T) % P2G_T, lk = q0 / (P2G_T * P2G_T);
+            const int i = i0 + li, j = j0 + lj, k = k0 + lk, kg = k + g.kOff;
+            const float Xn = (float)i * dxf, Yn = (float)j * dxf, Zn = (float)kg * dxf;       // exact (power-of-two dx)
+            const float Xh = Xn + hw, Yh = Yn + hw, Zh = Zn + hw;
+            const int row0 = (lj + 2) + SHELL_F * (lk + 2), x0 = li + 2;
+            float best2 = 3.0e38f;
+            for (int o = 0; o < 125; o++) {
+                const unsigned int e = c_shell_order[o];
+                // squared distance to the nearest point of that cell, less a margin against the rounding of the computed ones
+                const float cellMin2 = ((float)((e >> 9) & 3u) * 0.2499f + (float)(e >> 11) * 2.2499f) * dx2;
+                if (!(cellMin2 < best2)) break;          // the cells that follow are no nearer
+                const int di = (int)(e & 7u) - 2, dj = (int)((e >> 3) & 7u) - 2, dk = (int)((e >> 6) & 7u) - 2;
+                const int row = row0 + dj + SHELL_F * dk;
+                const int sb = rowS[row];
+                const int qb = sb + off[row * (SHELL_F + 1) + x0 + di], qe = sb + off[row * (SHELL_F + 1) + x0 + di + 1];
+                for (int q = qb; q < qe; q++) {
+                    const float x = sx[q], y = sy[q], z = sz[q];
+                    // position relative to the cell's lower corner: inside the search box iff -sr <= u < dx + sr
+                    const float ux = fsub(x, Xn), uy = fsub(y, Yn), uz = fsub(z, Zn);
+                    if (ux < loOut || ux >= hiOut || uy < loOut || uy >= hiOut || uz < loOut || uz >= hiOut) continue;
+                    const bool in = ux >= loIn && ux < hiIn && uy >= loIn && uy < hiIn && uz >= loIn && uz < hiIn;
+                    if (!in && !sdf_box_literal(g, x, y, z, i, j, kg)) continue;
+                    const float ex = fsub(Xh, x), ey = fsub(Yh, y), ez = fsub(Zh, z);
+                    best2 = fminf(best2, fadd(fadd(fmul(ex, ex), fmul(ey, ey)), fmul(ez, ez)));
+                }
             }
+            if (best2 < 1.0e38f) minC[i + I * (j + J * k)] = ~__float_as_uint(best2);
         }
-        if (best2 < 1.0e38f) minC[cell] = ~__float_as_uint(best2);
     }
 }
 
-// One thread per point (i,j,k) of the extended index space, as k_sdf_p2g: turns the accumulated sums of the three
-// faces of the node into velocities and valid flags and the accumulated minimum of the cell into the liquid SDF
-// (clearing the accumulators for the next step).  A cell that received no minimum lies in no particle's search box.
-__global__ void __launch_bounds__(128) k_p2g_finish(GatherParams g, P2GGlobal G, double invSScale,
-                                                    float *__restrict__ U, float *__restrict__ V, float *__restrict__ W,
-                                                    unsigned char *__restrict__ validU, unsigned char *__restrict__ validV,
-                                                    unsigned char *__restrict__ validW, float *__restrict__ phiL,
-                                                    const float *__restrict__ phiS, const unsigned int *__restrict__ near3,
-                                                    const unsigned int *__restrict__ near5, int WR, SdfQueues Q) {
+// One thread per point (i,j,k) of the extended index space (FIN_NJ consecutive j per thread, every load issued before
+// the first use): turns the accumulated sums of the three faces of a node into velocities and valid flags and the
+// accumulated minimum of the cell into the liquid SDF (clearing the accumulators for the next step).  A cell that
+// received no minimum lies in no particle's search box.  (Measured: 222 us with one node per thread, 240 us with
+// two -- the kernel is not waiting on its loads.)
+static constexpr int FIN_NJ = 1;
+__global__ void k_p2g_finish(GatherParams g, P2GGlobal G, double invSScale,
+                             float *__restrict__ U, float *__restrict__ V, float *__restrict__ W,
+                             unsigned char *__restrict__ validU, unsigned char *__restrict__ validV,
+                             unsigned char *__restrict__ validW, float *__restrict__ phiL,
+                             const float *__restrict__ phiS, const unsigned int *__restrict__ near3,
+                             const unsigned int *__restrict__ near5, int WR, SdfQueues Q) {
     const int I = g.I, J = g.J, K = g.K;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int j = blockIdx.y, k = blockIdx.z;      // k: local plane
+    const int jb = blockIdx.y * FIN_NJ, k = blockIdx.z;      // k: local plane
     if (i > I) return;
-    const bool hasU = (j < J && k < K), hasV = (i < I && k < K), hasW = (i < I && j < J), hasC = (i < I && j < J && k < K);
-    const long long iu = (long long)i + (long long)(I + 1) * (j + (long long)J * k);
-    const long long iv = (long long)i + (long long)I * (j + (long long)(J + 1) * k);
-    const long long iw = (long long)i + (long long)I * (j + (long long)J * k);
-    // the neighbourhood bits of the cell the node belongs to (nodes past the last cell of an axis: the last cell)
-    const int ci = min(i, I - 1), cj = min(j, J - 1), ck = min(k, K - 1);
-    const size_t word = (size_t)(ci >> 5) + (size_t)WR * (cj + (size_t)J * ck);
-    const bool n3 = (__ldg(near3 + word) >> (ci & 31)) & 1u;
-    const bool n5 = n3 || ((__ldg(near5 + word) >> (ci & 31)) & 1u);
-    // (all loads first)
-    ulonglong2 aU = make_ulonglong2(0ull, 0ull), aV = aU, aW = aU;
-    if (n3) { if (hasU) aU = G.accU[iu]; if (hasV) aV = G.accV[iv]; if (hasW) aW = G.accW[iw]; }
-    const unsigned int mn = (n5 && hasC) ? G.minC[iw] : 0u;
-    // ---- faces (no particle can reach the faces of a node whose 3x3x3 cells are empty)
-    auto finish = [&](ulonglong2 a, ulonglong2 *acc, long long idx, float *field, unsigned char *valid, int comp) {
-        float val = 0.0f;
-        unsigned char ok = 0;
-        if ((a.x | a.y) != 0ull) {
-            acc[idx] = make_ulonglong2(0ull, 0ull);
-            // coarse + fine / 16, exact in double
-            const double wd = (double)(unsigned int)a.x + 0.0625 * (double)(unsigned int)a.y;
-            const double sd = (double)(int)(a.x >> 32) + 0.0625 * (double)(int)(a.y >> 32);
-            const float wsum = (float)(wd * (1.0 / (double)P2G_WSCALE));
-            const float ssum = (float)(sd * invSScale);
-            int slot = -1;
-            if (wsum < P2G_LITERAL_BAND) slot = warp_append_slot(Q.litCount);
-            if (slot >= 0 && slot < Q.litCap)
-                Q.litFaces[slot] = (comp << 28) | (int)((long long)i + (long long)(I + 1) * (j + (long long)(J + 1) * k));
-            else { ok = wsum > g.eps; val = ok ? __fdiv_rn(ssum, wsum) : ssum; }   // (a full queue costs digits, nothing else)
+    const int ci = min(i, I - 1), ck = min(k, K - 1);
+    bool n3[FIN_NJ], n5[FIN_NJ];
+    ulonglong2 aU[FIN_NJ], aV[FIN_NJ], aW[FIN_NJ];
+    unsigned int mn[FIN_NJ];
+#pragma unroll
+    for (int m = 0; m < FIN_NJ; m++) {
+        // the neighbourhood bits of the cell the node belongs to (nodes past the last cell of an axis: the last cell)
+        const int j = jb + m;
+        const int cj = min(j, J - 1);
+        const size_t word = (size_t)(ci >> 5) + (size_t)WR * (cj + (size_t)J * ck);
+        n3[m] = j <= J && ((__ldg(near3 + word) >> (ci & 31)) & 1u);
+        n5[m] = j <= J && (n3[m] || ((__ldg(near5 + word) >> (ci & 31)) & 1u));
+    }
+#pragma unroll
+    for (int m = 0; m < FIN_NJ; m++) {
+        const int j = jb + m;
+        const bool hasU = (j < J && k < K), hasV = (i < I && j <= J && k < K), hasW = (i < I && j < J), hasC = (i < I && j < J && k < K);
+        aU[m] = aV[m] = aW[m] = make_ulonglong2(0ull, 0ull);
+        mn[m] = 0u;
+        if (n3[m]) {
+            if (hasU) aU[m] = G.accU[(long long)i + (long long)(I + 1) * (j + (long long)J * k)];
+            if (hasV) aV[m] = G.accV[(long long)i + (long long)I * (j + (long long)(J + 1) * k)];
+            if (hasW) aW[m] = G.accW[(long long)i + (long long)I * (j + (long long)J * k)];
         }
-        field[idx] = val;
-        valid[idx] = ok;
-    };
-    if (hasU) finish(aU, G.accU, iu, U, validU, 0);
-    if (hasV) finish(aV, G.accV, iv, V, validV, 1);
-    if (hasW) finish(aW, G.accW, iw, W, validW, 2);
-    if (!hasC) return;
-    // ---- liquid SDF of cell (i,j,k)
-    if (mn) {
-        G.minC[iw] = 0u;
-        phiL[iw] = finish_phi(g, phiS, __uint_as_float(~mn), i, j, k);
-    } else {
-        phiL[iw] = finish_phi(g, phiS, 3.0e38f, i, j, k);
+        if (n5[m] && hasC) mn[m] = G.minC[(long long)i + (long long)I * (j + (long long)J * k)];
+    }
+#pragma unroll
+    for (int m = 0; m < FIN_NJ; m++) {
+        const int j = jb + m;
+        if (j > J) break;
+        const bool hasU = (j < J && k < K), hasV = (i < I && k < K), hasW = (i < I && j < J), hasC = (i < I && j < J && k < K);
+        const long long iu = (long long)i + (long long)(I + 1) * (j + (long long)J * k);
+        const long long iv = (long long)i + (long long)I * (j + (long long)(J + 1) * k);
+        const long long iw = (long long)i + (long long)I * (j + (long long)J * k);
+        // ---- faces (no particle can reach the faces of a node whose 3x3x3 cells are empty)
+        auto finish = [&](ulonglong2 a, ulonglong2 *acc, long long idx, float *field, unsigned char *valid, int comp) {
+            float val = 0.0f;
+            unsigned char ok = 0;
+            if ((a.x | a.y) != 0ull) {
+                acc[idx] = make_ulonglong2(0ull, 0ull);
+                const float wsum = (float)((double)a.x * (1.0 / (16.0 * (double)P2G_WSCALE)));
+                const float ssum = (float)((double)(long long)a.y * invSScale);
+                int slot = -1;
+                if (wsum < P2G_LITERAL_BAND) slot = warp_append_slot(Q.litCount);
+                if (slot >= 0 && slot < Q.litCap)
+                    Q.litFaces[slot] = (comp << 28) | (int)((long long)i + (long long)(I + 1) * (j + (long long)(J + 1) * k));
+                else { ok = wsum > g.eps; val = ok ? __fdiv_rn(ssum, wsum) : ssum; }   // (a full queue costs digits, nothing else)
+            }
+            field[idx] = val;
+            valid[idx] = ok;
+        };
+        if (hasU) finish(aU[m], G.accU, iu, U, validU, 0);
+        if (hasV) finish(aV[m], G.accV, iv, V, validV, 1);
+        if (hasW) finish(aW[m], G.accW, iw, W, validW, 2);
+        if (!hasC) continue;
+        // ---- liquid SDF of cell (i,j,k)
+        if (mn[m]) {
+            G.minC[iw] = 0u;
+            phiL[iw] = finish_phi(g, phiS, __uint_as_float(~mn[m]), i, j, k);
+        } else {
+            phiL[iw] = finish_phi(g, phiS, 3.0e38f, i, j, k);
+        }
     }
 }
 
@@ -1632,10 +1709,9 @@ static void run_sdf_p2g(flip_ctx *c) {
         float vmax2;
         { const unsigned int bitsv = c->hS->maxSpeedSqBits; memcpy(&vmax2, &bitsv, sizeof(float)); }
         const double vmax = std::max(std::sqrt((double)vmax2) * 1.0000002, 1e-30);
-        int q = (int)std::floor(std::log2(2097152.0 / vmax));
-        q = std::max(-60, std::min(100, q));
-        const float sScale = (float)std::ldexp(1.0, q - 22);
-        const double invSScale = std::ldexp(1.0, -q);
+        int qg = (int)std::floor(std::log2(2097152.0 / vmax));
+        qg = std::max(-60, std::min(60, qg));
+        const double invSScale = std::ldexp(1.0, -(qg + 24));
         unsigned int *surf = c->occBits + 3 * words;
         const int tX = cdiv(d.I, P2G_T), tY = cdiv(d.J, P2G_T), tZ = cdiv(d.K, P2G_T);
         // tile bookkeeping: [0,4) counts and tickets, then flags (two per tile; x tiles padded to whole words of the
@@ -1661,7 +1737,7 @@ static void run_sdf_p2g(flip_ctx *c) {
                 attrS = true;
             }
         }
-        k_p2g_scatter<<<148 * 3, P2G_THREADS, smem, c->stream>>>(c->P[c->cur_buf], c->cellStart, g, G, tX, tY, sScale, Q, listP, tileCounts);
+        k_p2g_scatter<<<148 * 3, P2G_THREADS, smem, c->stream>>>(c->P[c->cur_buf], c->cellStart, g, G, tX, tY, qg, Q, listP, tileCounts);
         {
             static bool attr = false;
             const size_t shellSmem = 3 * (size_t)SHELL_CAP * sizeof(float);
@@ -1669,10 +1745,12 @@ static void run_sdf_p2g(flip_ctx *c) {
                 FLIP_CUDA_CHECK(cudaFuncSetAttribute(k_sdf_shell, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shellSmem));
                 attr = true;
             }
-            k_sdf_shell<<<148 * 2, SHELL_THREADS, shellSmem, c->stream>>>(c->P[c->cur_buf], c->cellStart, g, bits, near5, surf, WR,
+            k_sdf_shell<<<148 * 3, SHELL_THREADS, shellSmem, c->stream>>>(c->P[c->cur_buf], c->cellStart, g, bits, near5, surf, WR,
                                                                          G.minC, tX, tY, Q, listS, tileCounts);
         }
-        k_p2g_finish<<<grid, block, 0, c->stream>>>(g, G, invSScale, c->U, c->V, c->W, c->validU, c->validV, c->validW, c->phiL,
+        // (one CTA per row of nodes where the row fits: I + 1 = 257 nodes would leave a third CTA of 128 with one thread)
+        const int fT = std::min(1024, ((d.I + 1 + 31) / 32) * 32);
+        k_p2g_finish<<<dim3(cdiv(d.I + 1, fT), cdiv(d.J + 1, FIN_NJ), d.K + 1), fT, 0, c->stream>>>(g, G, invSScale, c->U, c->V, c->W, c->validU, c->validV, c->validW, c->phiL,
                                                     c->phiS, near3, near5, WR, Q);
         k_p2g_literal<<<148 * 8, 256, 0, c->stream>>>(c->P[c->cur_buf], c->cellStart, g, c->U, c->V, c->W, c->validU, c->validV,
                                                       c->validW, Q.litFaces, Q.litCount, Q.litCap);
