@@ -75,6 +75,7 @@ static void free_all(flip_ctx *c) {
     cudaSetDevice(c->device);
     particles_free(c);
     free_grids(c);
+    mesher_free(c);
     cudaFree(c->scanTemp);
     cudaFree(c->nearSolid); cudaFree(c->pressure);
     cudaFree(c->dS);
@@ -311,9 +312,30 @@ int flip_load_particles(flip_ctx *c, int n, const float *pos, const float *vel) 
 
 int flip_add_fluid_box(flip_ctx *c, const double lo[3], const double hi[3], const double vel[3]) {
     return guarded(c, [&] {
-        flip_ctx::FluidBox b;
-        for (int a = 0; a < 3; a++) { b.lo[a] = lo[a]; b.hi[a] = hi[a]; b.vel[a] = vel ? vel[a] : 0.0; }
-        c->fluidBoxes.push_back(b);
+        flip_ctx::FluidObject o;
+        const int n[3] = {c->d.I, c->d.J, c->d.Kg};
+        for (int a = 0; a < 3; a++) {
+            o.boxLo[a] = lo[a]; o.boxHi[a] = hi[a]; o.vel[a] = vel ? vel[a] : 0.0;
+            // the cells that can have a corner node inside the box
+            o.lo[a] = std::max(0, (int)floor(lo[a] / c->d.dx) - 1);
+            o.hi[a] = std::min(n[a], (int)ceil(hi[a] / c->d.dx) + 1);
+        }
+        c->fluidObjects.push_back(std::move(o));
+    });
+}
+
+int flip_add_fluid_sdf(flip_ctx *c, const float *sdf, const int cellLo[3], const int cellHi[3], const double vel[3]) {
+    return guarded(c, [&] {
+        if (!sdf) throw ApiError(FLIP_ERR_RUNTIME, "null signed distance field");
+        flip_ctx::FluidObject o;
+        const int n[3] = {c->d.I, c->d.J, c->d.Kg};
+        for (int a = 0; a < 3; a++) {
+            o.boxLo[a] = o.boxHi[a] = 0.0; o.vel[a] = vel ? vel[a] : 0.0;
+            o.lo[a] = cellLo ? std::max(0, cellLo[a]) : 0;
+            o.hi[a] = cellHi ? std::min(n[a], cellHi[a]) : n[a];
+        }
+        o.sdf.assign(sdf, sdf + (size_t)(n[0] + 1) * (n[1] + 1) * (n[2] + 1));
+        c->fluidObjects.push_back(std::move(o));
     });
 }
 
@@ -344,34 +366,14 @@ int flip_set_solid_sdf(flip_ctx *c, const float *phi) {
     });
 }
 
-// Seeds the queued fluid boxes: 8 particles per cell whose centre lies in the box, at (+-dx/4)^3
-// around the cell centre (FluidSimulation::_addNewFluidCells, fluidsimulation.cpp:4528-4559, with
-// jitter factor 0 the jitter amplitude is 0.25*(0-1e-3)*dx: omitted).
-static void seed_boxes(flip_ctx *c, std::vector<float> &pos, std::vector<float> &vel) {
-    const Dims &d = c->d;
-    double q = 0.25 * d.dx;
-    for (auto &b : c->fluidBoxes) {
-        for (int k = d.kOff + d.kOwn0; k < d.kOff + d.kOwn1; k++) for (int j = 0; j < d.J; j++) for (int i = 0; i < d.I; i++) {
-            double cx = (i + 0.5) * d.dx, cy = (j + 0.5) * d.dx, cz = (k + 0.5) * d.dx;
-            if (cx < b.lo[0] || cx >= b.hi[0] || cy < b.lo[1] || cy >= b.hi[1] || cz < b.lo[2] || cz >= b.hi[2]) continue;
-            for (int s = 0; s < 8; s++) {
-                pos.push_back((float)(cx + ((s & 1) ? q : -q)));
-                pos.push_back((float)(cy + ((s & 2) ? q : -q)));
-                pos.push_back((float)(cz + ((s & 4) ? q : -q)));
-                vel.push_back((float)b.vel[0]); vel.push_back((float)b.vel[1]); vel.push_back((float)b.vel[2]);
-            }
-        }
-    }
-    c->fluidBoxes.clear();
-}
-
 int flip_initialize(flip_ctx *c) {
     return guarded(c, [&] {
         if (c->initialized) throw ApiError(FLIP_ERR_RUNTIME, "Error: FluidSimulation is already initialized.");
         upload_static_inputs(c);
-        // _loadParticles (fluidsimulation.cpp:2791) + queued fluid boxes
-        seed_boxes(c, c->loadQueuePos, c->loadQueueVel);
+        // _loadParticles (fluidsimulation.cpp:2791); queued fluid objects are seeded at the end of the first substep,
+        // as the reference's _updateFluidObjects does (:5504)
         int n = (int)(c->loadQueuePos.size() / 3);
+        c->nextParticleId = n;
         // (a z-slab keeps the particles of its own planes only; every rank may be handed the whole scene)
         particles_upload_split(c, c->loadQueuePos.data(), c->loadQueueVel.data(), n);
         c->loadQueuePos.clear(); c->loadQueuePos.shrink_to_fit();
@@ -395,11 +397,17 @@ static double next_time_step(flip_ctx *c, double dt) {
     // _calculateNextTimeStep (:5593-5613)
     double maxu;
     if (c->currentFrame == 0 && c->substepNumber == 0) {
-        // _predictMaximumMarkerParticleSpeed (:5529-5551): queued objects are already seeded here, so
-        // only the body-force term remains: |g| * dt, with |g| the float vec3 length
+        // _predictMaximumMarkerParticleSpeed (:5529-5551): the largest fluid velocity of the queued objects
+        // (_getMaximumMeshObjectFluidVelocity of a static object: |velocity| as a float vec3 length) plus the
+        // body-force term |g| * dt, with |g| the float vec3 length
+        maxu = 0.0;
+        for (auto &o : c->fluidObjects) {
+            float vx = (float)o.vel[0], vy = (float)o.vel[1], vz = (float)o.vel[2];
+            maxu = std::max(maxu, (double)sqrtf(vx * vx + vy * vy + vz * vz));
+        }
         float gx = (float)c->gravity[0], gy = (float)c->gravity[1], gz = (float)c->gravity[2];
         float len = sqrtf(gx * gx + gy * gy + gz * gz);
-        maxu = (double)len * dt;
+        maxu += (double)len * dt;
     } else {
         maxu = max_particle_speed(c);
     }
@@ -463,7 +471,7 @@ static void run_stage(flip_ctx *c, int stage, double dt) {
         case FLIP_STAGE_CONSTRAIN: stage_constrain(c); break;
         case FLIP_STAGE_G2P: stage_g2p(c); break;
         case FLIP_STAGE_ADVANCE: stage_advance(c, dt); break;
-        case FLIP_STAGE_TAIL: break;
+        case FLIP_STAGE_TAIL: stage_fluid_objects(c); break;       // _updateFluidObjects  :5504
         default: throw ApiError(FLIP_ERR_OUT_OF_RANGE, "bad stage id");
     }
     FLIP_CUDA_CHECK(cudaEventRecord(c->evStage[stage + 1], c->stream));
@@ -574,6 +582,40 @@ int flip_get_particle_ids(flip_ctx *c, int32_t *ids, int capacity) {
         if (!c->trackIds) throw ApiError(FLIP_ERR_RUNTIME, "particle ids are not enabled");
         if (capacity < c->np) throw ApiError(FLIP_ERR_OUT_OF_RANGE, "Error: particle buffer too small.");
         particles_download_ids(c, (int *)ids);
+    });
+}
+
+int flip_set_surface_subdivision_level(flip_ctx *c, int n) {
+    return guarded(c, [&] {
+        if (n < 1) throw ApiError(FLIP_ERR_DOMAIN, "Error: subdivision level must be greater than or equal to 1.");
+        if (n != c->surfaceSubdivision) c->stepCounter++;       // a cached mesh no longer applies
+        c->surfaceSubdivision = n;
+    });
+}
+int flip_set_surface_smoothing(flip_ctx *c, double value, int iterations) {
+    return guarded(c, [&] {
+        if (iterations < 0) throw ApiError(FLIP_ERR_DOMAIN, "Error: smoothing iterations must be greater than or equal to 0.");
+        c->surfaceSmoothingValue = value; c->surfaceSmoothingIterations = iterations;
+        c->stepCounter++;
+    });
+}
+int flip_get_isomesh_size(flip_ctx *c, int *numVertices, int *numTriangles) {
+    return guarded(c, [&] {
+        if (!c->initialized) throw ApiError(FLIP_ERR_RUNTIME, "Error: FluidSimulation must be initialized before its surface exists.");
+        mesher_get(c, numVertices, numTriangles, nullptr, nullptr);
+    });
+}
+int flip_get_isomesh(flip_ctx *c, float *verticesXyz, int *triangles) {
+    return guarded(c, [&] {
+        if (!c->initialized) throw ApiError(FLIP_ERR_RUNTIME, "Error: FluidSimulation must be initialized before its surface exists.");
+        mesher_get(c, nullptr, nullptr, verticesXyz, triangles);
+    });
+}
+
+int flip_get_isomesh_field(flip_ctx *c, float *values, unsigned char *inside, unsigned char *need) {
+    return guarded(c, [&] {
+        if (!c->initialized) throw ApiError(FLIP_ERR_RUNTIME, "Error: FluidSimulation must be initialized before its surface exists.");
+        mesher_debug_field(c, values, inside, need);
     });
 }
 

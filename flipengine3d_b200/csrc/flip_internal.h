@@ -135,8 +135,11 @@ struct flip_ctx {
 
     // ---- host staging
     std::vector<float> loadQueuePos, loadQueueVel;   // loadMarkerParticleData queue
-    struct FluidBox { double lo[3], hi[3], vel[3]; };
-    std::vector<FluidBox> fluidBoxes;
+    // addMeshFluid queue (_addedFluidMeshObjectQueue, fluidsimulation.h): cell range [lo,hi) of the object, its fluid
+    // velocity, and its signed distance field -- a nodal array of the global grid, or (sdf empty) an axis-aligned box
+    struct FluidObject { int lo[3], hi[3]; double boxLo[3], boxHi[3], vel[3]; std::vector<float> sdf; };
+    std::vector<FluidObject> fluidObjects;
+    int nextParticleId = 0;                   // ids of particles seeded after the load (enableParticleIds)
     std::vector<float> hostSolidPhi;          // nodal
     bool userSolidPhi = false;
     std::vector<float> hU, hV, hW;            // host mirror handed out by getVelocityField
@@ -173,6 +176,12 @@ struct flip_ctx {
     float *pressure = nullptr;                // (I,J,K) float, last solution
     void *p2gAcc[4] = {nullptr, nullptr, nullptr, nullptr};   // fixed-point accumulators of the P2G scatter: U, V, W faces; cell minima
     unsigned int *occBits = nullptr;          // cell occupancy bitmaps: occupied | 3x3x3 neighbourhood | 5x5x5 neighbourhood
+    // surface reconstruction (mesher.cu): getIsomesh() settings of the reference (fluidsimulation.h:1605-1608)
+    int surfaceSubdivision = 1;
+    double surfaceSmoothingValue = 0.5;
+    int surfaceSmoothingIterations = 2;
+    void *mesher = nullptr;
+    int64_t stepCounter = 0;                  // bumped whenever the particle store is re-sorted (cache stamp of the mesh)
     int *p2gTiles = nullptr;                  // tile bookkeeping of the P2G scatter / SDF shell search (particles.cu)
     bool occBitsValid = false;                // the sort has just written the first of them (rows of whole words)
 
@@ -236,6 +245,14 @@ void stage_liquid_sdf(flip_ctx *c);
 void stage_p2g(flip_ctx *c);
 void stage_g2p(flip_ctx *c);
 void stage_advance(flip_ctx *c, double dt);
+
+// seed.cu
+void stage_fluid_objects(flip_ctx *c);          // seeds the queued fluid objects on the device (end of a substep)
+
+// mesher.cu
+void mesher_get(flip_ctx *c, int *nv, int *nt, float *verts, int *tris);
+void mesher_free(flip_ctx *c);
+void mesher_debug_field(flip_ctx *c, float *values, unsigned char *inside, unsigned char *need);
 
 // grid.cu
 void stage_extrapolate(flip_ctx *c);

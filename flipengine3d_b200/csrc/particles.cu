@@ -460,6 +460,7 @@ void particles_sort(flip_ctx *c, bool applyRules, double frameDt, int srcOffset,
     if (!slab_on(c)) c->np_global = c->np;
     else if (ownedOnly) c->np_global = c->hS->globalParticles;
     c->cur_buf = 1 - c->cur_buf;
+    c->stepCounter++;
     c->ownedBegin = 0;
     c->ownedEnd = c->np;
     c->ghostsPresent = false;
@@ -1357,7 +1358,7 @@ __global__ void __launch_bounds__(SHELL_THREADS) k_sdf_shell(ParticleSoA p, cons
     extern __shared__ float stage[];              // [3][SHELL_CAP] particle positions
     __shared__ int off[SHELL_ROWS * (SHELL_F + 1)];   // staged range of every cell of the region, row by row
     __shared__ int rowG[SHELL_ROWS], rowS[SHELL_ROWS + 1];   // first particle of the row's span (global / staged)
-    __shared__ int warpSum[SHELL_THREADS / 32];
+    __shared__ __align__(16) int warpSum[SHELL_THREADS / 32];   // (aligned: the compiler reads it with 128-bit loads, which would otherwise take in the last word of rowS as well -- harmless, but compute-sanitizer racecheck reports it)
     __shared__ short needList[P2G_T * P2G_T * P2G_T];        // the unsettled cells of the tile, compacted
     __shared__ int nextTile, needCount;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;

@@ -690,8 +690,11 @@ __device__ __forceinline__ float sm_residual(const SmLevel &L, const float *x, i
 static constexpr int SM_WARP_CELLS = 64;
 
 // nu pre-sweeps from a zero guess (or `sweeps` of them on the coarsest level); leaves the result in L.x
+// (the descriptors live in shared memory: each pass copies what it uses into registers first -- through the reference
+// every array pointer would be re-read from shared memory after every store, a chain of two dependent loads per access)
 template <class Sync>
-__device__ __forceinline__ void sm_presweeps(const SmLevel &L, int sweeps, const MgParams &p, bool coarsest, int tid, int nt, Sync sync) {
+__device__ __forceinline__ void sm_presweeps(const SmLevel &Lref, int sweeps, const MgParams &p, bool coarsest, int tid, int nt, Sync sync) {
+    const SmLevel L = Lref;
     float *xa = L.x, *xb = L.x2;
     for (int s = 0; s < sweeps; s++) {
         const float omega = coarsest ? p.omegaCoarse : p.om[s];
@@ -714,7 +717,8 @@ __device__ __forceinline__ void sm_presweeps(const SmLevel &L, int sweeps, const
 }
 // b_C = P^T (b_L - A_L x_L)
 template <class Sync>
-__device__ __forceinline__ void sm_restrict(const SmLevel &L, const SmLevel &C, int tid, int nt, Sync sync) {
+__device__ __forceinline__ void sm_restrict(const SmLevel &Lref, const SmLevel &Cref, int tid, int nt, Sync sync) {
+    const SmLevel L = Lref, C = Cref;
     for (int cc = tid; cc < C.n; cc += nt) {
         float acc = 0.0f;
         if (C.invD[cc] != 0.0f) {
@@ -731,7 +735,8 @@ __device__ __forceinline__ void sm_restrict(const SmLevel &L, const SmLevel &C, 
 }
 // nu post-sweeps on (x + scale * P e), e = the solution of the next coarser level; leaves the result in L.x
 template <class Sync>
-__device__ __forceinline__ void sm_postsweeps(const SmLevel &L, const SmLevel &C, const MgParams &p, int tid, int nt, Sync sync) {
+__device__ __forceinline__ void sm_postsweeps(const SmLevel &Lref, const SmLevel &Cref, const MgParams &p, int tid, int nt, Sync sync) {
+    const SmLevel L = Lref, C = Cref;
     const float scale = p.scale;
     const float *e = C.x;
     float *xa = L.x, *xb = L.x2;

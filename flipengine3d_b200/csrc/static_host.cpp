@@ -4,6 +4,7 @@
 #include <cmath>
 #include <vector>
 #include "flip_internal.h"
+#include "mc_tables.h"
 
 namespace flip {
 
@@ -168,3 +169,13 @@ void build_near_solid(const Dims &d, const std::vector<float> &phi, int factor, 
 }
 
 }  // namespace flip
+
+// the generated marching-cubes case table of the surface reconstruction (mc_tables.h), for inspection and tests
+extern "C" int flip_mc_case_table(unsigned char counts[256], unsigned char edge_triples[256 * 24]) {
+    unsigned char tris[256][flip::MC_MAX_TRIS * 3];
+    unsigned char cnt[256];
+    flip::build_mc_tables(cnt, tris);
+    if (counts) memcpy(counts, cnt, 256);
+    if (edge_triples) memcpy(edge_triples, tris, sizeof(tris));
+    return FLIP_OK;
+}

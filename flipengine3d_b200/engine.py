@@ -78,6 +78,12 @@ def load_library():
     L.flip_set_sampling_mode.argtypes = [vp, ci]
     L.flip_load_particles.argtypes = [vp, ci, vp, vp]
     L.flip_add_fluid_box.argtypes = [vp, C.POINTER(cd), C.POINTER(cd), C.POINTER(cd)]
+    L.flip_add_fluid_sdf.argtypes = [vp, vp, C.POINTER(ci), C.POINTER(ci), C.POINTER(cd)]
+    L.flip_set_surface_subdivision_level.argtypes = [vp, ci]
+    L.flip_set_surface_smoothing.argtypes = [vp, cd, ci]
+    L.flip_get_isomesh_size.argtypes = [vp, C.POINTER(ci), C.POINTER(ci)]
+    L.flip_get_isomesh.argtypes = [vp, vp, vp]
+    L.flip_get_isomesh_field.argtypes = [vp, vp, vp, vp]
     L.flip_add_marker_particle.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.flip_set_solid_sdf.argtypes = [vp, vp]
     L.flip_initialize.argtypes = [vp]
@@ -273,6 +279,44 @@ class FluidSimulation:
         b = (C.c_double * 3)(*hi)
         v = (C.c_double * 3)(*velocity)
         self._check(self.L.flip_add_fluid_box(self.h, a, b, v))
+
+    def addMeshFluidSDF(self, nodal_sdf, velocity=(0.0, 0.0, 0.0), cell_lo=None, cell_hi=None):
+        """addMeshFluid(MeshObject, velocity) with the object given as the nodal signed distance field of the grid
+        (negative inside), shape (K+1, J+1, I+1): what MeshLevelSet::fastCalculateSignedDistanceField produces."""
+        I, J, K = self.dims
+        a = np.ascontiguousarray(nodal_sdf, dtype=np.float32)
+        if a.size != (I + 1) * (J + 1) * (K + 1):
+            raise ValueError("nodal_sdf must have (I+1)(J+1)(K+1) entries")
+        lo = (C.c_int * 3)(*cell_lo) if cell_lo is not None else None
+        hi = (C.c_int * 3)(*cell_hi) if cell_hi is not None else None
+        v = (C.c_double * 3)(*velocity)
+        self._check(self.L.flip_add_fluid_sdf(self.h, a.ctypes.data, lo, hi, v))
+
+    def setSurfaceSubdivisionLevel(self, n):
+        self._check(self.L.flip_set_surface_subdivision_level(self.h, int(n)))
+
+    def setSurfaceSmoothing(self, value, iterations):
+        self._check(self.L.flip_set_surface_smoothing(self.h, float(value), int(iterations)))
+
+    def getIsomesh(self):
+        """(vertices (nv,3) float32, triangles (nt,3) int32): FluidSimulation::getIsomesh, reconstructed on the device."""
+        nv, nt = C.c_int(), C.c_int()
+        self._check(self.L.flip_get_isomesh_size(self.h, C.byref(nv), C.byref(nt)))
+        v = np.empty((nv.value, 3), dtype=np.float32)
+        t = np.empty((nt.value, 3), dtype=np.int32)
+        if nv.value or nt.value:
+            self._check(self.L.flip_get_isomesh(self.h, v.ctypes.data, t.ctypes.data))
+        return v, t
+
+    def isomesh_field(self, subdivisions):
+        """Parity seam: (values, inside, need) of the mesher's scalar field, each of shape (K s+1, J s+1, I s+1)."""
+        I, J, K = self.dims
+        shp = (K * subdivisions + 1, J * subdivisions + 1, I * subdivisions + 1)
+        v = np.zeros(shp, dtype=np.float32)
+        a = np.zeros(shp, dtype=np.uint8)
+        b = np.zeros(shp, dtype=np.uint8)
+        self._check(self.L.flip_get_isomesh_field(self.h, v.ctypes.data, a.ctypes.data, b.ctypes.data))
+        return v, a, b
 
     def loadMarkerParticleData(self, data):
         if data.size == 0:

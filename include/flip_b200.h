@@ -139,9 +139,20 @@ int flip_set_sampling_mode(flip_ctx *ctx, int mode);
 /* FluidSimulation::loadMarkerParticleData  fluidsimulation.cpp:2488 — float xyz triplets; copied;
  * applied (with the in-domain filter of _loadMarkerParticles :2773) at flip_initialize(). */
 int flip_load_particles(flip_ctx *ctx, int n, const float *positions_xyz, const float *velocities_xyz);
-/* FluidSimulation::addMeshFluid(MeshObject) :1573 for the axis-aligned boxes FluidManager uses
- * (src/FluidManager.cpp:56-64): queues a box [lo,hi) of world coordinates seeded with 8 particles
- * per cell at flip_initialize() (reference: end of first step, _updateFluidObjects :4794). */
+/* FluidSimulation::addMeshFluid(MeshObject, velocity)  fluidsimulation.cpp:1573-1590: queues a fluid object.  Like the
+ * reference's queue (_addedFluidMeshObjectQueue) it is seeded at the END of the next substep (_updateFluidObjects :5504
+ * -> _updateAddedFluidMeshObjectQueue :4724-4759) -- on the device (csrc/seed.cu): eight points (+-dx/4)^3 per cell that
+ * has a corner node inside the object (MeshObject::getCells, meshobject.cpp:101-140), kept where the object's signed
+ * distance (trilinear sample of its nodal field) is <= 0, the solid SDF is > 0 and the sub-cell holds no particle yet
+ * (ParticleMaskGrid, particlemaskgrid.cpp:55-112).  Until it is seeded its |velocity| enters the predicted maximum
+ * speed of the first time step (_predictMaximumMarkerParticleSpeed :5529-5551).  Not reproduced: the reference's jitter
+ * of 2.5e-4 dx from the unseeded rand().
+ *   flip_add_fluid_sdf: the object as a NODAL signed distance field of the global grid, (I+1)(J+1)(K+1) floats, negative
+ *     inside -- what MeshLevelSet::fastCalculateSignedDistanceField leaves in _phi (copied); cell_lo / cell_hi: the cell
+ *     range [lo,hi) to scan (NULL: the whole grid).
+ *   flip_add_fluid_box: an axis-aligned box [lo,hi] of world coordinates (the object FluidManager builds,
+ *     src/FluidManager.cpp:56-64); its nodal distances are evaluated in place. */
+int flip_add_fluid_sdf(flip_ctx *ctx, const float *nodal_sdf, const int cell_lo[3], const int cell_hi[3], const double velocity[3]);
 int flip_add_fluid_box(flip_ctx *ctx, const double lo[3], const double hi[3], const double velocity[3]);
 /* FluidSimulation::_addMarkerParticle  fluidsimulation.cpp:2637 (range-checked push). */
 int flip_add_marker_particle(flip_ctx *ctx, const float position[3], const float velocity[3]);
@@ -195,6 +206,26 @@ int flip_get_particle_velocities(flip_ctx *ctx, float *xyz, int capacity);
  * keeps insertion order, fragmentedvector.h; here order is by cell).  Costs 8 B/particle/step. */
 int flip_enable_particle_ids(flip_ctx *ctx, int on);
 int flip_get_particle_ids(flip_ctx *ctx, int32_t *ids, int capacity);
+
+/* FluidSimulation::getIsomesh()  fluidsimulation.h:1126 -- the surface FluidManager draws (src/FluidManager.cpp:102-171):
+ * ParticleMesher::meshParticles (particlemesher.cpp:36: scalar field of the particles on the grid subdivided
+ * setSurfaceSubdivisionLevel times :228-231, marching cubes polygonizer3d.cpp:643-676) and TriangleMesh::smooth
+ * (trianglemesh.cpp:536-583; value 0.5, 2 iterations by default, fluidsimulation.h:1607-1608), at the engine's other
+ * defaults; reconstructed on the device (csrc/mesher.cu) from the particles as they stand at the call and cached until
+ * the next step.  flip_get_isomesh_size first, then flip_get_isomesh with room for 3 floats per vertex and 3 vertex
+ * indices per triangle.  Single GPU (a z-slab run gathers its particles on one rank first). */
+int flip_set_surface_subdivision_level(flip_ctx *ctx, int n);
+int flip_set_surface_smoothing(flip_ctx *ctx, double value, int iterations);
+int flip_get_isomesh_size(flip_ctx *ctx, int *num_vertices, int *num_triangles);
+int flip_get_isomesh(flip_ctx *ctx, float *vertices_xyz, int *triangles);
+/* parity seam: the mesher's scalar field on the (I s+1)(J s+1)(K s+1) nodes of the subdivided grid, i fastest: the
+ * inside flag of every node (value > 0 and not solid), whether the node belongs to a surface cell (`need`), and the
+ * exact value of those nodes (0 elsewhere).  Any pointer may be NULL. */
+int flip_get_isomesh_field(flip_ctx *ctx, float *values, unsigned char *inside, unsigned char *need);
+/* the marching-cubes case table the reconstruction uses (generated on the host, csrc/mc_tables.h; no CUDA device
+ * needed): per sign configuration (bit c = corner c inside; corner bits x | y << 1 | z << 2) the triangle count and up
+ * to 8 triples of crossed edges (edge = axis * 4 + the bits of its lower corner on the two other axes). */
+int flip_mc_case_table(unsigned char counts[256], unsigned char edge_triples[256 * 24]);
 
 /* FluidSimulation::getVelocityField :2242 + MACVelocityField::getRawArrayU/V/W macvelocityfield.cpp:100-110 */
 int flip_get_velocity_field(flip_ctx *ctx, float *U, float *V, float *W);

@@ -1,12 +1,20 @@
-// C++ façade over the C-ABI of flip_b200.h with the member names of the reference's FluidSimulation
-// (src/engine/fluidsimulation.h) for the calls on the hot path: the ones FluidManager makes
-// (src/FluidManager.cpp:12,51-67,76-79: constructor, setSurfaceSubdivisionLevel, getSimulationDimensions,
-// addMeshFluid, addBodyForce, initialize, getCurrentFrame, update) and the ones the north star adds
-// (getMarkerParticles, getNumMarkerParticles, loadMarkerParticleData, getVelocityField, snapshot blobs).
+// C++ façade over the C-ABI of flip_b200.h with the type and member names of the reference for the calls on the hot
+// path: everything FluidManager touches (src/FluidManager.cpp:12,47-83,102-171: FluidSimulation constructor,
+// setSurfaceSubdivisionLevel, getSimulationDimensions, AABB / TriangleMesh / MeshObject::updateMeshStatic,
+// addMeshFluid(MeshObject), addBodyForce, initialize, getCurrentFrame, update, getIsomesh) and what the north star
+// adds (addMarkerParticle, getMarkerParticles, getNumMarkerParticles, loadMarkerParticleData, getVelocityField with the
+// MACVelocityField raw arrays, snapshot blobs, the per-stage timing buckets).  The call sequence of
+// FluidManager::initialize / iUpdate compiles against this header unchanged (examples/fluidmanager_headless.cpp).
 // Header only; link with -lflip_b200.  Error behaviour: the exception types the reference throws for the same
 // misuse (std::runtime_error: update before initialize, fluidsimulation.cpp:5756; std::domain_error: dt < 0, :5761;
 // std::out_of_range: bad ranges, :2059).  There is no CPU fallback: without a CUDA device the constructor throws.
+//
+// The names live in namespace flipb200 and are also exported to the global namespace (vmath::vec3, AABB, Triangle,
+// TriangleMesh, MeshObject, MACVelocityField, MarkerParticle, FluidSimulation) unless FLIPB200_NO_GLOBAL_NAMES is
+// defined before the include.
 #pragma once
+#include <algorithm>
+#include <cmath>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -14,9 +22,26 @@
 
 namespace flipb200 {
 
+namespace vmath {      // vmath.h:33-120, the members FluidManager uses
+struct vec3 {
+    float x = 0.f, y = 0.f, z = 0.f;
+    vec3() = default;
+    template <class A, class B, class C>      // (float and double arguments mix freely, as with the reference's overloads)
+    vec3(A xx, B yy, C zz) : x((float)xx), y((float)yy), z((float)zz) {}
+    vec3 &operator+=(const vec3 &o) { x += o.x; y += o.y; z += o.z; return *this; }
+    float operator[](int i) const { return i == 0 ? x : (i == 1 ? y : z); }
+};
+inline vec3 operator+(const vec3 &a, const vec3 &b) { return vec3(a.x + b.x, a.y + b.y, a.z + b.z); }
+inline vec3 operator-(const vec3 &a, const vec3 &b) { return vec3(a.x - b.x, a.y - b.y, a.z - b.z); }
+inline vec3 operator*(float s, const vec3 &a) { return vec3(s * a.x, s * a.y, s * a.z); }
+inline float dot(const vec3 &a, const vec3 &b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+inline vec3 cross(const vec3 &a, const vec3 &b) { return vec3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+inline float length(const vec3 &a) { return std::sqrt(dot(a, a)); }
+inline vec3 normalize(const vec3 &a) { float l = length(a); return l > 0.f ? vec3(a.x / l, a.y / l, a.z / l) : a; }
+}  // namespace vmath
+
 // MarkerParticle (markerparticle.h:30-42): two vmath::vec3 of floats, 24 bytes -- the AoS wire format
-struct vec3 { float x = 0.f, y = 0.f, z = 0.f; };
-struct MarkerParticle { vec3 position, velocity; };
+struct MarkerParticle { vmath::vec3 position, velocity; };
 static_assert(sizeof(MarkerParticle) == 24, "MarkerParticle must be six packed floats");
 
 // FluidSimulationMarkerParticleData (fluidsimulation.h:102-106): float xyz triplets behind char pointers
@@ -24,6 +49,158 @@ struct FluidSimulationMarkerParticleData {
     int size = 0;
     char *positions = nullptr;
     char *velocities = nullptr;
+};
+
+// aabb.h:36-70
+struct AABB {
+    vmath::vec3 position;
+    double width = 0.0, height = 0.0, depth = 0.0;
+    AABB() = default;
+    AABB(vmath::vec3 p, double w, double h, double d) : position(p), width(w), height(h), depth(d) {}
+};
+
+// triangle.h:33-46, trianglemesh.h:50-130 (the two containers FluidManager reads and writes)
+struct Triangle {
+    int tri[3] = {0, 0, 0};
+    Triangle() = default;
+    Triangle(int a, int b, int c) { tri[0] = a; tri[1] = b; tri[2] = c; }
+};
+struct TriangleMesh {
+    std::vector<vmath::vec3> vertices;
+    std::vector<Triangle> triangles;
+};
+
+// MeshObject (meshobject.h:60-170) for static closed meshes: what addMeshFluid needs of it is the cell range
+// (getCells, meshobject.cpp:101-140) and the signed distance field that FluidSimulation computes from getMesh()
+// (MeshLevelSet::fastCalculateSignedDistanceField, fluidsimulation.cpp:4743-4744).  Here the nodal field is computed on
+// the host when the object is queued -- exact point-triangle distances within `band` cells of the mesh's bounding box,
+// the sign by crossing parity along +x -- and handed to the device seeding (flip_add_fluid_sdf).  An axis-aligned
+// box (the object FluidManager builds) is recognised and handed over analytically (flip_add_fluid_box).
+class MeshObject {
+public:
+    MeshObject() = default;
+    MeshObject(int isize, int jsize, int ksize, double dx) : _isize(isize), _jsize(jsize), _ksize(ksize), _dx(dx) {}
+    void getGridDimensions(int *i, int *j, int *k) const { *i = _isize; *j = _jsize; *k = _ksize; }
+    void updateMeshStatic(TriangleMesh meshCurrent) { _mesh = std::move(meshCurrent); }
+    TriangleMesh getMesh() const { return _mesh; }
+
+    void bounds(vmath::vec3 &lo, vmath::vec3 &hi) const {
+        lo = vmath::vec3(1e30f, 1e30f, 1e30f); hi = vmath::vec3(-1e30f, -1e30f, -1e30f);
+        for (const auto &v : _mesh.vertices) {
+            lo = vmath::vec3(std::min(lo.x, v.x), std::min(lo.y, v.y), std::min(lo.z, v.z));
+            hi = vmath::vec3(std::max(hi.x, v.x), std::max(hi.y, v.y), std::max(hi.z, v.z));
+        }
+    }
+    // eight vertices on the corners of their bounding box, twelve triangles: the mesh of getTriangleMeshFromAABB
+    bool isAxisAlignedBox() const {
+        if (_mesh.vertices.size() != 8 || _mesh.triangles.size() != 12) return false;
+        vmath::vec3 lo, hi;
+        bounds(lo, hi);
+        unsigned seen = 0;
+        for (const auto &v : _mesh.vertices) {
+            const bool x0 = v.x == lo.x, x1 = v.x == hi.x, y0 = v.y == lo.y, y1 = v.y == hi.y, z0 = v.z == lo.z, z1 = v.z == hi.z;
+            if (!((x0 || x1) && (y0 || y1) && (z0 || z1))) return false;
+            seen |= 1u << ((x1 ? 1 : 0) | (y1 ? 2 : 0) | (z1 ? 4 : 0));
+        }
+        return seen == 0xffu;
+    }
+    // nodal signed distance field of the grid, (I+1)(J+1)(K+1) floats, i fastest; cells [lo,hi) worth scanning
+    void signedDistanceField(std::vector<float> &phi, int lo[3], int hi[3], int band = 3) const {
+        const int ni = _isize + 1, nj = _jsize + 1, nk = _ksize + 1;
+        const float far = (float)((band + 1) * _dx);
+        phi.assign((size_t)ni * nj * nk, far);
+        vmath::vec3 blo, bhi;
+        bounds(blo, bhi);
+        const int n[3] = {_isize, _jsize, _ksize};
+        int nlo[3], nhi[3];
+        for (int a = 0; a < 3; a++) {
+            nlo[a] = std::max(0, (int)std::floor(blo[a] / _dx) - band);
+            nhi[a] = std::min(n[a], (int)std::ceil(bhi[a] / _dx) + band);
+            lo[a] = nlo[a]; hi[a] = nhi[a];
+        }
+        for (int k = nlo[2]; k <= nhi[2]; k++)
+            for (int j = nlo[1]; j <= nhi[1]; j++)
+                for (int i = nlo[0]; i <= nhi[0]; i++) {
+                    const vmath::vec3 p((float)(i * _dx), (float)(j * _dx), (float)(k * _dx));
+                    float d2 = 1e30f;
+                    int crossings = 0;
+                    // the parity ray leaves along +x from a point nudged off the lattice (mesh vertices on grid lines)
+                    const double ry = p.y + 1.2345e-4 * _dx, rz = p.z + 2.3456e-4 * _dx;
+                    for (const auto &t : _mesh.triangles) {
+                        const vmath::vec3 &a = _mesh.vertices[t.tri[0]], &b = _mesh.vertices[t.tri[1]], &c = _mesh.vertices[t.tri[2]];
+                        d2 = std::min(d2, pointTriangleDistanceSq(p, a, b, c));
+                        // intersection of the ray (x > p.x, y = ry, z = rz) with the triangle, in the yz projection
+                        const double ay = a.y - ry, az = a.z - rz, by = b.y - ry, bz = b.z - rz, cy = c.y - ry, cz = c.z - rz;
+                        const double w0 = by * cz - bz * cy, w1 = cy * az - cz * ay, w2 = ay * bz - az * by;
+                        if ((w0 > 0 && w1 > 0 && w2 > 0) || (w0 < 0 && w1 < 0 && w2 < 0)) {
+                            const double s = w0 + w1 + w2;
+                            const double x = (w0 * a.x + w1 * b.x + w2 * c.x) / s;
+                            if (x > p.x) crossings++;
+                        }
+                    }
+                    const float d = std::min(std::sqrt(d2), far);
+                    phi[(size_t)i + (size_t)ni * (j + (size_t)nj * k)] = (crossings & 1) ? -d : d;
+                }
+    }
+
+private:
+    static float pointTriangleDistanceSq(const vmath::vec3 &p, const vmath::vec3 &a, const vmath::vec3 &b, const vmath::vec3 &c) {
+        // closest point on a triangle (Ericson, Real-Time Collision Detection 5.1.5)
+        using namespace vmath;
+        const vec3 ab = b - a, ac = c - a, ap = p - a;
+        const float d1 = dot(ab, ap), d2 = dot(ac, ap);
+        if (d1 <= 0.f && d2 <= 0.f) return dot(ap, ap);
+        const vec3 bp = p - b;
+        const float d3 = dot(ab, bp), d4 = dot(ac, bp);
+        if (d3 >= 0.f && d4 <= d3) return dot(bp, bp);
+        const float vc = d1 * d4 - d3 * d2;
+        if (vc <= 0.f && d1 >= 0.f && d3 <= 0.f) { const vec3 q = p - (a + (d1 / (d1 - d3)) * ab); return dot(q, q); }
+        const vec3 cp = p - c;
+        const float d5 = dot(ab, cp), d6 = dot(ac, cp);
+        if (d6 >= 0.f && d5 <= d6) return dot(cp, cp);
+        const float vb = d5 * d2 - d1 * d6;
+        if (vb <= 0.f && d2 >= 0.f && d6 <= 0.f) { const vec3 q = p - (a + (d2 / (d2 - d6)) * ac); return dot(q, q); }
+        const float va = d3 * d6 - d5 * d4;
+        if (va <= 0.f && (d4 - d3) >= 0.f && (d5 - d6) >= 0.f) {
+            const vec3 q = p - (b + ((d4 - d3) / ((d4 - d3) + (d5 - d6))) * (c - b));
+            return dot(q, q);
+        }
+        const float den = 1.f / (va + vb + vc);
+        const vec3 q = p - (a + (vb * den) * ab + (vc * den) * ac);
+        return dot(q, q);
+    }
+    int _isize = 0, _jsize = 0, _ksize = 0;
+    double _dx = 0.0;
+    TriangleMesh _mesh;
+};
+
+// MACVelocityField (macvelocityfield.cpp:46-54,100-110): the three raw face arrays, U (i+1,j,k), V (i,j+1,k),
+// W (i,j,k+1), i fastest -- a host copy filled by FluidSimulation::getVelocityField()
+class MACVelocityField {
+public:
+    void getGridDimensions(int *i, int *j, int *k) const { *i = _isize; *j = _jsize; *k = _ksize; }
+    double getGridCellSize() const { return _dx; }
+    float *getRawArrayU() { return _u.data(); }
+    float *getRawArrayV() { return _v.data(); }
+    float *getRawArrayW() { return _w.data(); }
+    float U(int i, int j, int k) const { return _u[(size_t)i + (size_t)(_isize + 1) * (j + (size_t)_jsize * k)]; }
+    float V(int i, int j, int k) const { return _v[(size_t)i + (size_t)_isize * (j + (size_t)(_jsize + 1) * k)]; }
+    float W(int i, int j, int k) const { return _w[(size_t)i + (size_t)_isize * (j + (size_t)_jsize * k)]; }
+
+private:
+    friend class FluidSimulation;
+    int _isize = 0, _jsize = 0, _ksize = 0;
+    double _dx = 0.0;
+    std::vector<float> _u, _v, _w;
+};
+
+// the per-stage wall-clock buckets of the reference's log (fluidsimulation.h:1172-1190), in seconds, of the last frame
+struct TimingData {
+    double updateObstacleObjects = 0.0, updateLiquidLevelSet = 0.0, advectVelocityField = 0.0, saveVelocityField = 0.0,
+           calculateFluidCurvatureGrid = 0.0, applyBodyForcesToVelocityField = 0.0, applyViscosityToVelocityField = 0.0,
+           pressureSolve = 0.0, constrainVelocityFields = 0.0, updateDiffuseMaterial = 0.0, updateSheetSeeding = 0.0,
+           updateMarkerParticleVelocities = 0.0, deleteSavedVelocityField = 0.0, advanceMarkerParticles = 0.0,
+           updateFluidObjects = 0.0, outputNonMeshSimulationData = 0.0, outputMeshSimulationData = 0.0, frameTime = 0.0;
 };
 
 class FluidSimulation {
@@ -43,10 +220,38 @@ public:
     void getGridDimensions(int *i, int *j, int *k) const { *i = _isize; *j = _jsize; *k = _ksize; }
     double getCellSize() const { return _dx; }
     void getSimulationDimensions(double *w, double *h, double *d) const { *w = _isize * _dx; *h = _jsize * _dx; *d = _ksize * _dx; }
-    void setSurfaceSubdivisionLevel(int) {}          // surface reconstruction is outside the hot path
+    // surface reconstruction: the subdivision level of the mesher's scalar field (:1012-1023)
+    void setSurfaceSubdivisionLevel(int n) {
+        if (n < 1) throw std::domain_error("Error: subdivision level must be greater than or equal to 1.\n");
+        _subdivisionLevel = n;
+        flip_set_surface_subdivision_level(_c, n);
+    }
+    int getSurfaceSubdivisionLevel() const { return _subdivisionLevel; }
     void addBodyForce(double fx, double fy, double fz) { check(flip_add_body_force(_c, fx, fy, fz)); }
-    // addMeshFluid(MeshObject) for the axis-aligned box FluidManager builds (FluidManager.cpp:56-64)
+    // addMeshFluid (:1573-1590): queued, seeded on the device at the end of the next substep
+    void addMeshFluid(MeshObject fluid) { addMeshFluid(fluid, vmath::vec3(0.f, 0.f, 0.f)); }
+    void addMeshFluid(MeshObject fluid, vmath::vec3 velocity) {
+        int i, j, k;
+        fluid.getGridDimensions(&i, &j, &k);
+        if (i != _isize || j != _jsize || k != _ksize) throw std::domain_error("Error: mesh object dimensions must be equal to simulation dimensions.\n");
+        const double v[3] = {velocity.x, velocity.y, velocity.z};
+        if (fluid.isAxisAlignedBox()) {
+            vmath::vec3 lo, hi;
+            fluid.bounds(lo, hi);
+            const double l[3] = {lo.x, lo.y, lo.z}, h[3] = {hi.x, hi.y, hi.z};
+            check(flip_add_fluid_box(_c, l, h, v));
+            return;
+        }
+        std::vector<float> phi;
+        int clo[3], chi[3];
+        fluid.signedDistanceField(phi, clo, chi);
+        check(flip_add_fluid_sdf(_c, phi.data(), clo, chi, v));
+    }
     void addMeshFluidBox(const double lo[3], const double hi[3], const double velocity[3]) { check(flip_add_fluid_box(_c, lo, hi, velocity)); }
+    void addMarkerParticle(vmath::vec3 p, vmath::vec3 v = vmath::vec3()) {      // _addMarkerParticle :2637
+        const float pp[3] = {p.x, p.y, p.z}, vv[3] = {v.x, v.y, v.z};
+        check(flip_add_marker_particle(_c, pp, vv));
+    }
     void loadMarkerParticleData(FluidSimulationMarkerParticleData d) {
         check(flip_load_particles(_c, d.size, reinterpret_cast<const float *>(d.positions), reinterpret_cast<const float *>(d.velocities)));
     }
@@ -66,12 +271,47 @@ public:
     unsigned int getMarkerParticlePositionDataSize() { return getNumMarkerParticles() * 3u * (unsigned int)sizeof(float); }
     void getMarkerParticlePositionData(char *data) { check(flip_get_particle_positions(_c, reinterpret_cast<float *>(data), (int)getNumMarkerParticles())); }
     void getMarkerParticleVelocityData(char *data) { check(flip_get_particle_velocities(_c, reinterpret_cast<float *>(data), (int)getNumMarkerParticles())); }
-    // MACVelocityField raw arrays (macvelocityfield.cpp:100-110): U (i+1,j,k), V (i,j+1,k), W (i,j,k+1), i fastest
+    // getVelocityField (:2045-2047): the MAC field as it stands after the last step
+    MACVelocityField *getVelocityField() {
+        _mac._isize = _isize; _mac._jsize = _jsize; _mac._ksize = _ksize; _mac._dx = _dx;
+        _mac._u.resize((size_t)(_isize + 1) * _jsize * _ksize);
+        _mac._v.resize((size_t)_isize * (_jsize + 1) * _ksize);
+        _mac._w.resize((size_t)_isize * _jsize * (_ksize + 1));
+        check(flip_get_velocity_field(_c, _mac._u.data(), _mac._v.data(), _mac._w.data()));
+        return &_mac;
+    }
     void getVelocityField(std::vector<float> &U, std::vector<float> &V, std::vector<float> &W) {
-        U.resize((size_t)(_isize + 1) * _jsize * _ksize);
-        V.resize((size_t)_isize * (_jsize + 1) * _ksize);
-        W.resize((size_t)_isize * _jsize * (_ksize + 1));
-        check(flip_get_velocity_field(_c, U.data(), V.data(), W.data()));
+        MACVelocityField *m = getVelocityField();
+        U = m->_u; V = m->_v; W = m->_w;
+    }
+    // getIsomesh (fluidsimulation.h:1126): the surface of the liquid as of the last update(), reconstructed on the
+    // device from the marker particles (ParticleMesher::meshParticles, particlemesher.cpp:36)
+    TriangleMesh &getIsomesh() {
+        int nv = 0, nt = 0;
+        check(flip_get_isomesh_size(_c, &nv, &nt));
+        _isomesh.vertices.resize((size_t)nv);
+        _isomesh.triangles.resize((size_t)nt);
+        if (nv > 0 || nt > 0)
+            check(flip_get_isomesh(_c, reinterpret_cast<float *>(_isomesh.vertices.data()), reinterpret_cast<int *>(_isomesh.triangles.data())));
+        return _isomesh;
+    }
+    // the stage buckets of the last substep under the reference's names, seconds (CUDA events on the context's stream)
+    TimingData getTimingData() {
+        float ms[FLIP_NUM_STAGES];
+        check(flip_get_stage_times_ms(_c, ms));
+        TimingData t;
+        t.updateObstacleObjects = 1e-3 * ms[FLIP_STAGE_OBSTACLES];
+        t.updateLiquidLevelSet = 1e-3 * ms[FLIP_STAGE_LIQUID_SDF];
+        t.advectVelocityField = 1e-3 * (ms[FLIP_STAGE_P2G] + ms[FLIP_STAGE_EXTRAPOLATE_A]);
+        t.saveVelocityField = 1e-3 * ms[FLIP_STAGE_SAVE];
+        t.applyBodyForcesToVelocityField = 1e-3 * ms[FLIP_STAGE_BODY_FORCE];
+        t.pressureSolve = 1e-3 * ms[FLIP_STAGE_PRESSURE];
+        t.constrainVelocityFields = 1e-3 * (ms[FLIP_STAGE_EXTRAPOLATE_B] + ms[FLIP_STAGE_CONSTRAIN]);
+        t.updateMarkerParticleVelocities = 1e-3 * ms[FLIP_STAGE_G2P];
+        t.advanceMarkerParticles = 1e-3 * ms[FLIP_STAGE_ADVANCE];
+        t.updateFluidObjects = 1e-3 * ms[FLIP_STAGE_TAIL];
+        for (int s = 0; s < FLIP_NUM_STAGES; s++) t.frameTime += 1e-3 * ms[s];
+        return t;
     }
     // per-substep log integers of the last frame (_logStepInfo :5710-5745)
     int getNumSubsteps() { int n = 0; check(flip_get_num_substeps(_c, &n)); return n; }
@@ -89,6 +329,21 @@ private:
     flip_ctx *_c = nullptr;
     int _isize, _jsize, _ksize;
     double _dx;
+    int _subdivisionLevel = 1;
+    MACVelocityField _mac;
+    TriangleMesh _isomesh;
 };
 
 }  // namespace flipb200
+
+#ifndef FLIPB200_NO_GLOBAL_NAMES
+namespace vmath = flipb200::vmath;
+using flipb200::AABB;
+using flipb200::FluidSimulation;
+using flipb200::FluidSimulationMarkerParticleData;
+using flipb200::MACVelocityField;
+using flipb200::MarkerParticle;
+using flipb200::MeshObject;
+using flipb200::Triangle;
+using flipb200::TriangleMesh;
+#endif

@@ -48,6 +48,8 @@
 #include "engine/particlelevelset.h"
 #include "engine/meshlevelset.h"
 #include "engine/macvelocityfield.h"
+#include "engine/particlemesher.h"
+#include "engine/trianglemesh.h"
 #include "engine/threadutils.h"
 #include "engine/stopwatch.h"
 #undef private
@@ -60,6 +62,7 @@ struct RefSim {
     std::string lastError;
     // timing of the stage-wise step, seconds, indexed by stage id
     double stageTime[16] = {0};
+    TriangleMesh isomesh;      // ref_isomesh
 };
 
 template <class F>
@@ -415,6 +418,108 @@ void ref_sample_solid_phi(void *p, int n, const float *pos, float *out) {
     for (int i = 0; i < n; i++) {
         out[i] = s->_solidSDF.trilinearInterpolate(vmath::vec3(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]));
     }
+}
+
+/* FluidManager::initialize's fluid object (src/FluidManager.cpp:53-64): an axis-aligned box as a 12-triangle mesh in a
+ * MeshObject, queued with addMeshFluid (seeded by the reference at the end of the next step). */
+int ref_add_mesh_fluid_box(void *p, const double lo[3], const double hi[3], const double vel[3]) {
+    RefSim *h = (RefSim *)p;
+    return guarded(h, [&] {
+        FluidSimulation *s = h->sim;
+        vmath::vec3 q((float)lo[0], (float)lo[1], (float)lo[2]);
+        const double w = hi[0] - lo[0], ht = hi[1] - lo[1], d = hi[2] - lo[2];
+        TriangleMesh m;
+        m.vertices = {vmath::vec3(q.x, q.y, q.z), vmath::vec3(q.x + w, q.y, q.z), vmath::vec3(q.x + w, q.y, q.z + d),
+                      vmath::vec3(q.x, q.y, q.z + d), vmath::vec3(q.x, q.y + ht, q.z), vmath::vec3(q.x + w, q.y + ht, q.z),
+                      vmath::vec3(q.x + w, q.y + ht, q.z + d), vmath::vec3(q.x, q.y + ht, q.z + d)};
+        m.triangles = {Triangle(0, 1, 2), Triangle(0, 2, 3), Triangle(4, 7, 6), Triangle(4, 6, 5), Triangle(0, 3, 7), Triangle(0, 7, 4),
+                       Triangle(1, 5, 6), Triangle(1, 6, 2), Triangle(0, 4, 5), Triangle(0, 5, 1), Triangle(3, 2, 6), Triangle(3, 6, 7)};
+        MeshObject obj(s->_isize, s->_jsize, s->_ksize, s->_dx);
+        obj.updateMeshStatic(m);
+        s->addMeshFluid(obj, vmath::vec3((float)vel[0], (float)vel[1], (float)vel[2]));
+    });
+}
+
+/* The surface FluidSimulation::getIsomesh() would hold for the CURRENT particles: the body of _outputSurfaceMeshThread
+ * (fluidsimulation.cpp:5150-5218) run synchronously -- _polygonizeOutputSurface (ParticleMesher::meshParticles),
+ * removeMinimumTriangleCountPolyhedra, _removeMeshNearDomain, smooth, _invertContactNormals -- with the engine's
+ * settings except the subdivision level and the smoothing iterations given here (iterations < 0: the engine's). */
+int ref_isomesh(void *p, int subdivisions, int smoothIterations, int *nv, int *nt) {
+    RefSim *h = (RefSim *)p;
+    return guarded(h, [&] {
+        FluidSimulation *s = h->sim;
+        std::vector<vmath::vec3> particles;
+        particles.reserve(s->_markerParticles.size());
+        for (size_t i = 0; i < s->_markerParticles.size(); i++) particles.push_back(s->_markerParticles[i].position);
+        MeshLevelSet solid;
+        solid.constructMinimalSignedDistanceField(s->_solidSDF);
+        const int keepSub = s->_outputFluidSurfaceSubdivisionLevel, keepIt = s->_surfaceReconstructionSmoothingIterations;
+        s->_outputFluidSurfaceSubdivisionLevel = subdivisions;
+        if (smoothIterations >= 0) s->_surfaceReconstructionSmoothingIterations = smoothIterations;
+        TriangleMesh isomesh, preview;
+        s->_polygonizeOutputSurface(isomesh, preview, &particles, &solid);
+        isomesh.removeMinimumTriangleCountPolyhedra(s->_minimumSurfacePolyhedronTriangleCount);
+        s->_removeMeshNearDomain(isomesh);
+        s->_smoothSurfaceMesh(isomesh);
+        s->_invertContactNormals(isomesh);
+        s->_outputFluidSurfaceSubdivisionLevel = keepSub;
+        s->_surfaceReconstructionSmoothingIterations = keepIt;
+        h->isomesh = isomesh;
+        *nv = (int)isomesh.vertices.size();
+        *nt = (int)isomesh.triangles.size();
+    });
+}
+
+void ref_get_isomesh(void *p, float *verts, int *tris) {
+    RefSim *h = (RefSim *)p;
+    for (size_t i = 0; i < h->isomesh.vertices.size(); i++) {
+        verts[3 * i] = h->isomesh.vertices[i].x; verts[3 * i + 1] = h->isomesh.vertices[i].y; verts[3 * i + 2] = h->isomesh.vertices[i].z;
+    }
+    for (size_t i = 0; i < h->isomesh.triangles.size(); i++)
+        for (int q = 0; q < 3; q++) tris[3 * i + q] = h->isomesh.triangles[i].tri[q];
+}
+
+/* The mesher's scalar field of the current particles (ParticleMesher::_computeScalarField, one compute chunk), as the
+ * polygonizer reads it (ScalarField::getScalarFieldValue: solid nodes clamped to the threshold): (K s+1)(J s+1)(I s+1)
+ * floats, i fastest. */
+int ref_mesher_scalar_field(void *p, int subdivisions, float *out) {
+    RefSim *h = (RefSim *)p;
+    return guarded(h, [&] {
+        FluidSimulation *s = h->sim;
+        std::vector<vmath::vec3> particles;
+        for (size_t i = 0; i < s->_markerParticles.size(); i++) particles.push_back(s->_markerParticles[i].position);
+        MeshLevelSet solid;
+        solid.constructMinimalSignedDistanceField(s->_solidSDF);
+        ParticleMesherParameters params;
+        params.isize = s->_isize; params.jsize = s->_jsize; params.ksize = s->_ksize; params.dx = s->_dx;
+        params.subdivisions = subdivisions;
+        params.computechunks = 1;
+        params.radius = s->_markerParticleRadius * s->_markerParticleScale;
+        params.particles = &particles;
+        params.solidSDF = &solid;
+        params.isPreviewMesherEnabled = false;
+        ParticleMesher mesher;
+        mesher._initialize(params);
+        ParticleMesher::MesherComputeChunkData data;
+        mesher._generateComputeChunkData(data);
+        if (data.computeChunks.size() != 1) throw std::runtime_error("expected one compute chunk");
+        ParticleMesher::ScalarFieldData fieldData;
+        mesher._initializeScalarFieldData(data.computeChunks[0], data, fieldData);
+        const int ni = s->_isize * subdivisions + 1, nj = s->_jsize * subdivisions + 1, nk = s->_ksize * subdivisions + 1;
+        if (fieldData.particles.empty()) {
+            for (size_t q = 0; q < (size_t)ni * nj * nk; q++) out[q] = 0.0f;
+            return;
+        }
+        mesher._computeScalarField(fieldData);
+        // the chunk spans the bounding range of the blocks near particles; outside it the field keeps its fill value
+        for (size_t q = 0; q < (size_t)ni * nj * nk; q++) out[q] = -mesher._getMaxDistanceValue();
+        const ParticleMesher::MesherComputeChunk &c = data.computeChunks[0];
+        for (int k = 0; k < c.ksize; k++)
+            for (int j = 0; j < c.jsize; j++)
+                for (int i = 0; i < c.isize; i++)
+                    out[(size_t)(i + c.minGridIndex.i) + (size_t)ni * ((j + c.minGridIndex.j) + (size_t)nj * (k + c.minGridIndex.k))] =
+                        (float)fieldData.fieldValues.getScalarFieldValue(i, j, k);
+    });
 }
 
 }  // extern "C"

@@ -67,6 +67,10 @@ def _load(kind):
     L.ref_update_weight_grid.argtypes = [C.c_void_p]
     L.ref_sample_velocity.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.ref_sample_solid_phi.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.ref_add_mesh_fluid_box.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.ref_isomesh.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.ref_get_isomesh.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ref_mesher_scalar_field.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     _libs[kind] = L
     return L
 
@@ -201,6 +205,26 @@ class RefEngine:
         pos = np.ascontiguousarray(pos, dtype=np.float32)
         out = np.empty_like(pos)
         self.L.ref_sample_velocity(self.h, pos.shape[0], pos.ctypes.data, out.ctypes.data)
+        return out
+
+    def add_mesh_fluid_box(self, lo, hi, velocity=(0.0, 0.0, 0.0)):
+        """FluidSimulation::addMeshFluid(MeshObject) with the box mesh FluidManager builds."""
+        a, b, v = (C.c_double * 3)(*lo), (C.c_double * 3)(*hi), (C.c_double * 3)(*velocity)
+        self._check(self.L.ref_add_mesh_fluid_box(self.h, a, b, v))
+
+    def isomesh(self, subdivisions=1, smooth_iterations=-1):
+        """(vertices, triangles) of the surface getIsomesh() would return for the current particles."""
+        nv, nt = C.c_int(), C.c_int()
+        self._check(self.L.ref_isomesh(self.h, int(subdivisions), int(smooth_iterations), C.byref(nv), C.byref(nt)))
+        v = np.empty((nv.value, 3), dtype=np.float32)
+        t = np.empty((nt.value, 3), dtype=np.int32)
+        self.L.ref_get_isomesh(self.h, v.ctypes.data, t.ctypes.data)
+        return v, t
+
+    def mesher_scalar_field(self, subdivisions=1):
+        I, J, K = self.dims
+        out = np.empty((K * subdivisions + 1, J * subdivisions + 1, I * subdivisions + 1), dtype=np.float32)
+        self._check(self.L.ref_mesher_scalar_field(self.h, int(subdivisions), out.ctypes.data))
         return out
 
     def sample_solid_phi(self, pos):

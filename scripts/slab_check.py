@@ -40,6 +40,17 @@ def main():
     if rank == 0 and refengine.available("golden") and os.environ.get("SLAB_CHECK_ORACLE", "1") != "0":
         orc = refengine.RefEngine(sc["dims"], sc["dx"], sc["pos"], sc["vel"], kind="golden")
     n0 = sc["pos"].shape[0]
+    # Above 208 333 particles the reference aliases a few logical particle indices onto other particles' slots
+    # (FragmentedVector::operator[]; tests/parity_common.aliased_slots): the oracle then simulates the
+    # scene with those particles replaced by copies.  They are left out of the per-particle comparison, and the cell
+    # counts may differ by the cells those few particles tip over.
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+    from parity_common import aliased_slots
+    a_hi, a_lo = aliased_slots(n0)
+    unshared = np.ones(n0, dtype=bool)
+    unshared[a_hi] = False
+    unshared[a_lo] = False
+    count_slack = 2 * int(a_hi.size)
     if rank == 0:
         ref = fe.FluidSimulation(I, J, K, sc["dx"], device=lr)
         ref.addBodyForce(0, -25, 0)
@@ -74,11 +85,13 @@ def main():
             if orc is not None and f < ORACLE_FRAMES:
                 orc.update(1 / 30)
                 o = {"substeps": orc.substeps, "particles": orc.num_particles, "fluid_cells": orc.num_fluid_cells}
-                ok &= o["substeps"] == len(st) and o["particles"] == st[-1]["particles"] and o["fluid_cells"] == st[-1]["pressure_rows"]
+                ok &= o["substeps"] == len(st) and o["particles"] == st[-1]["particles"]
+                ok &= abs(o["fluid_cells"] - st[-1]["pressure_rows"]) <= count_slack
+                o["aliased_particles"] = int(a_hi.size)
                 if o["particles"] == n0 and P.shape[0] == n0:
                     # nothing was removed so far: the reference keeps its particles in input order (= id)
-                    op = orc.particles()
-                    a = P[order]
+                    op = orc.particles()[unshared]
+                    a = P[order][unshared]
                     o["pos_rel_l2"] = float(np.linalg.norm(a[:, :3] - op[:, :3]) / np.linalg.norm(op[:, :3]))
                     o["pos_max_abs"] = float(np.abs(a[:, :3] - op[:, :3]).max())
                     ok &= o["pos_rel_l2"] <= 1e-4
