@@ -255,8 +255,6 @@ def make_sim(args, wl_name, grid, rank, world, local_rank, dist, ids=False):
     sim.addBodyForce(0.0, -25.0, 0.0)
     if args.preconditioner:
         sim.setPreconditioner(args.preconditioner)
-    if ids:
-        sim.enableParticleIds(True)
     krange = None
     if world > 1:
         ident = [fe.nccl_unique_id() if rank == 0 else None]
@@ -264,6 +262,8 @@ def make_sim(args, wl_name, grid, rank, world, local_rank, dist, ids=False):
         sim.setSlab(rank, world, ident[0])
         krange = fe.slab_range(K, world, rank)
     sc = workload(grid, wl_name, krange=krange)
+    if ids:     # global ids: a rank that generates only its own planes counts from the particles that precede them
+        sim.enableParticleIds(True, base=sc.get("id_offset", 0))
     sim.loadMarkerParticleData(fe.MarkerParticleData(sc["pos"], sc["vel"]))
     sim.initialize()
     return sim, sc

@@ -373,7 +373,7 @@ int flip_initialize(flip_ctx *c) {
         // _loadParticles (fluidsimulation.cpp:2791); queued fluid objects are seeded at the end of the first substep,
         // as the reference's _updateFluidObjects does (:5504)
         int n = (int)(c->loadQueuePos.size() / 3);
-        c->nextParticleId = n;
+        c->nextParticleId = c->particleIdBase + n;
         // (a z-slab keeps the particles of its own planes only; every rank may be handed the whole scene)
         particles_upload_split(c, c->loadQueuePos.data(), c->loadQueueVel.data(), n);
         c->loadQueuePos.clear(); c->loadQueuePos.shrink_to_fit();
@@ -469,7 +469,10 @@ static void run_stage(flip_ctx *c, int stage, double dt) {
             break;
         case FLIP_STAGE_EXTRAPOLATE_B: stage_extrapolate(c); break;
         case FLIP_STAGE_CONSTRAIN: stage_constrain(c); break;
-        case FLIP_STAGE_G2P: stage_g2p(c); break;
+        case FLIP_STAGE_G2P:
+            if (c->fuseAdvance && stage_g2p_advance_fused(c, dt)) c->fusedAdvanceDone = true;
+            else stage_g2p(c);
+            break;
         case FLIP_STAGE_ADVANCE: stage_advance(c, dt); break;
         case FLIP_STAGE_TAIL: stage_fluid_objects(c); break;       // _updateFluidObjects  :5504
         default: throw ApiError(FLIP_ERR_OUT_OF_RANGE, "bad stage id");
@@ -517,7 +520,9 @@ int flip_update(flip_ctx *c, double dt) {
             if (r2) throw ApiError(r2, c->lastError);
             // all stages are enqueued back to back; the only host syncs are the scalar read-backs
             // inside the pressure stage and at the end of the advance stage
+            c->fuseAdvance = true;          // G2P and RK3 run as one pass where that applies (stage_g2p_advance_fused)
             for (int s = 0; s < FLIP_NUM_STAGES; s++) run_stage(c, s, step);
+            c->fuseAdvance = false;
             FLIP_CUDA_CHECK(cudaStreamSynchronize(c->stream));
             kt_collect(c);
             for (int s = 0; s < FLIP_NUM_STAGES; s++) {
@@ -576,6 +581,9 @@ int flip_get_particle_velocities(flip_ctx *c, float *xyz, int capacity) {
 
 int flip_enable_particle_ids(flip_ctx *c, int on) {
     return guarded(c, [&] { c->trackIds = on != 0; });
+}
+int flip_set_particle_id_base(flip_ctx *c, int base) {
+    return guarded(c, [&] { c->particleIdBase = base; });
 }
 int flip_get_particle_ids(flip_ctx *c, int32_t *ids, int capacity) {
     return guarded(c, [&] {

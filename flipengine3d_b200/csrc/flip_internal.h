@@ -155,6 +155,7 @@ struct flip_ctx {
     int *srcIdx = nullptr;                    // [capacity] final gather map
     int *pid[2] = {nullptr, nullptr};         // optional particle ids carried through the sorts
     bool trackIds = false;
+    int particleIdBase = 0;                   // id of the first loaded particle (a z-slab rank that is handed its own part of a scene)
     unsigned char *occ = nullptr;             // 4x4x4-cell blocks that hold particles (rebuilt by every sort)
     size_t occBytes = 0;
     int *cellCount = nullptr;                 // [nC+1]
@@ -181,6 +182,9 @@ struct flip_ctx {
     double surfaceSmoothingValue = 0.5;
     int surfaceSmoothingIterations = 2;
     void *mesher = nullptr;
+    bool fuseAdvance = false;                 // set by flip_update around its stage loop
+    bool fusedAdvanceDone = false;            // whole-step path: the advection kernels already ran with the G2P stage
+    bool speedHistReady = false;              // ... and left the speed histogram of the removal rules in the device scalars
     int64_t stepCounter = 0;                  // bumped whenever the particle store is re-sorted (cache stamp of the mesh)
     int *p2gTiles = nullptr;                  // tile bookkeeping of the P2G scatter / SDF shell search (particles.cu)
     bool occBitsValid = false;                // the sort has just written the first of them (rows of whole words)
@@ -245,6 +249,7 @@ void stage_liquid_sdf(flip_ctx *c);
 void stage_p2g(flip_ctx *c);
 void stage_g2p(flip_ctx *c);
 void stage_advance(flip_ctx *c, double dt);
+bool stage_g2p_advance_fused(flip_ctx *c, double dt);   // whole-step path: G2P + RK3 in one pass (false: not applicable)
 
 // seed.cu
 void stage_fluid_objects(flip_ctx *c);          // seeds the queued fluid objects on the device (end of a substep)

@@ -321,9 +321,9 @@ __global__ void k_build_src(int nC, const int *__restrict__ startA, const int *_
     if (c == nC - 1) S->numParticles = e;
 }
 
-__global__ void k_iota(int *p, int n) {
+__global__ void k_iota(int *p, int n, int base) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < n) p[t] = t;
+    if (t < n) p[t] = base + t;
 }
 
 __global__ void k_gather(ParticleSoA src, ParticleSoA dst, const int *__restrict__ srcIdx, int nmax, DeviceScalars *S,
@@ -402,7 +402,8 @@ void particles_sort(flip_ctx *c, bool applyRules, double frameDt, int srcOffset,
         // _removeMarkerParticles(_currentFrameDeltaTime): bins are CFL*dx/dt_FRAME wide
         double speedLimitStep = c->CFL * d.dx / frameDt;
         int nGlobal = n;
-        if (n > 0) { k_speed_hist<<<cdiv(n, TPB), TPB, 0, st>>>(src, sp, speedLimitStep, c->maxSubsteps, c->dS); c->launches++; }
+        if (n > 0 && !c->speedHistReady) { k_speed_hist<<<cdiv(n, TPB), TPB, 0, st>>>(src, sp, speedLimitStep, c->maxSubsteps, c->dS); c->launches++; }
+        c->speedHistReady = false;
         if (slab_on(c)) {
             // the rule is global: histogram and particle count summed over the slabs
             comm_allreduce(c->comm, c->dS->speedHist, 8, COMM_SUM_I32, st);
@@ -474,7 +475,7 @@ void particles_upload_aos(flip_ctx *c, const float *aos6, int n) {
         float *tmp = c->P[1 - c->cur_buf].px;
         FLIP_CUDA_CHECK(cudaMemcpyAsync(tmp, aos6, sizeof(float) * 6ll * n, cudaMemcpyHostToDevice, c->stream));
         k_aos_to_soa<<<cdiv(n, TPB), TPB, 0, c->stream>>>(tmp, n, c->P[c->cur_buf]); c->launches++;
-        if (c->trackIds) { k_iota<<<cdiv(n, TPB), TPB, 0, c->stream>>>(c->pid[c->cur_buf], n); c->launches++; }
+        if (c->trackIds) { k_iota<<<cdiv(n, TPB), TPB, 0, c->stream>>>(c->pid[c->cur_buf], n, c->particleIdBase); c->launches++; }
     }
     particles_sort(c, false, 0.0, 0, n, slab_on(c));
 }
@@ -488,7 +489,7 @@ void particles_upload_split(flip_ctx *c, const float *pos, const float *vel, int
         FLIP_CUDA_CHECK(cudaMemcpyAsync(tp, pos, sizeof(float) * 3ll * n, cudaMemcpyHostToDevice, c->stream));
         FLIP_CUDA_CHECK(cudaMemcpyAsync(tv, vel, sizeof(float) * 3ll * n, cudaMemcpyHostToDevice, c->stream));
         k_split_to_soa<<<cdiv(n, TPB), TPB, 0, c->stream>>>(tp, tv, n, c->P[c->cur_buf]); c->launches++;
-        if (c->trackIds) { k_iota<<<cdiv(n, TPB), TPB, 0, c->stream>>>(c->pid[c->cur_buf], n); c->launches++; }
+        if (c->trackIds) { k_iota<<<cdiv(n, TPB), TPB, 0, c->stream>>>(c->pid[c->cur_buf], n, c->particleIdBase); c->launches++; }
     }
     particles_sort(c, false, 0.0, 0, n, slab_on(c));
 }
@@ -2009,6 +2010,70 @@ __global__ void k_advance_fast(ParticleSoA p, AdvectParams a, MacField f, const 
     p.px[t] = nx; p.py[t] = ny; p.pz[t] = nz;
 }
 
+// G2P and the RK3 advection in ONE pass over the particles (whole-step path, single precision, single GPU): the grid
+// sample of the PIC/FLIP update at the particle's position IS the first Ralston stage (the same field at the same
+// point, fluidsimulation.cpp:4084 and :4192), so the fused kernel reads the position once, samples the new field
+// three times instead of four and the saved field once, and writes velocity and position; the speed histogram of
+// _getMarkerParticleSpeedLimit (:4300-4305), which the sort that follows needs, is taken from the updated velocity
+// while it is in registers.  Arithmetic per particle is that of k_g2p_fast followed by k_advance_fast (same device
+// functions): results are bit-identical to the two-kernel path.  Particles that leave the interior box at any
+// sample go to the literal kernels (k_g2p then k_advance), untouched here.
+__global__ void __launch_bounds__(256) k_g2p_advance_fused(ParticleSoA p, AdvectParams a, MacField fnew, MacField fold,
+                                                          const float *__restrict__ phiS, const unsigned char *__restrict__ ns,
+                                                          int *__restrict__ deferred, int *__restrict__ deferredCount,
+                                                          double speedLimitStep, int nbins, DeviceScalars *S) {
+    __shared__ int sh[8];
+    if (threadIdx.x < 8) sh[threadIdx.x] = 0;
+    __syncthreads();
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < a.n) {
+        const float x = p.px[t], y = p.py[t], z = p.pz[t];
+        float k1x, k1y, k1z, k2x, k2y, k2z, k3x, k3y, k3z, ox = 0.f, oy = 0.f, oz = 0.f;
+        bool ok = fast_interior(a.F, x, y, z);
+        if (ok) {
+            const FastStencil s = fast_stencil(a.F, x, y, z);
+            fast_sample(fnew, a.F, s, k1x, k1y, k1z);
+            fast_sample(fold, a.F, s, ox, oy, oz);
+            const float x2 = fadd(x, fmul(k1x, a.c1)), y2 = fadd(y, fmul(k1y, a.c1)), z2 = fadd(z, fmul(k1z, a.c1));
+            ok = fast_interior(a.F, x2, y2, z2);
+            if (ok) {
+                fast_sample(fnew, a.F, fast_stencil(a.F, x2, y2, z2), k2x, k2y, k2z);
+                const float x3 = fadd(x, fmul(k2x, a.c2)), y3 = fadd(y, fmul(k2y, a.c2)), z3 = fadd(z, fmul(k2z, a.c2));
+                ok = fast_interior(a.F, x3, y3, z3);
+                if (ok) fast_sample(fnew, a.F, fast_stencil(a.F, x3, y3, z3), k3x, k3y, k3z);
+            }
+        }
+        float vx, vy, vz;
+        if (!ok) {
+            deferred[warp_append_slot(deferredCount)] = t;
+            // (its histogram entry is added by k_speed_hist_list once the literal kernels have updated it)
+        } else {
+            picflip_update(p, a, t, k1x, k1y, k1z, ox, oy, oz);
+            vx = p.vx[t]; vy = p.vy[t]; vz = p.vz[t];
+            const double b = fmin(floor((double)length3(vx, vy, vz) / speedLimitStep), (double)(nbins - 1));
+            const int bi = (int)b;
+            if (bi > 0) atomicAdd(&sh[bi], 1);
+            float nx, ny, nz;
+            rk3_combine(a, x, y, z, k1x, k1y, k1z, k2x, k2y, k2z, k3x, k3y, k3z, nx, ny, nz);
+            resolve_collision(a, phiS, ns, x, y, z, nx, ny, nz);
+            p.px[t] = nx; p.py[t] = ny; p.pz[t] = nz;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x > 0 && threadIdx.x < 8 && sh[threadIdx.x]) atomicAdd(&S->speedHist[threadIdx.x], sh[threadIdx.x]);
+}
+// the histogram entries of the deferred particles (after the literal G2P)
+__global__ void k_speed_hist_list(ParticleSoA p, const int *__restrict__ list, const int *__restrict__ listCount, double speedLimitStep,
+                                  int nbins, DeviceScalars *S) {
+    const int n = *listCount;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+        const int t = list[q];
+        const double b = fmin(floor((double)length3(p.vx[t], p.vy[t], p.vz[t]) / speedLimitStep), (double)(nbins - 1));
+        const int bi = (int)b;
+        if (bi > 0) atomicAdd(&S->speedHist[bi], 1);
+    }
+}
+
 // single-precision sampling needs a power-of-two dx (exact index / weight arithmetic in float) and extents
 // whose coordinates stay far below 2^24 ulps
 static bool sampling_fast(const flip_ctx *c) {
@@ -2077,7 +2142,37 @@ void stage_g2p(flip_ctx *c) {
     FLIP_CUDA_CHECK(cudaGetLastError());
 }
 
+// whole-step path: stage_g2p + the kernels of stage_advance as one pass (see k_g2p_advance_fused); the sort that ends
+// stage_advance follows as usual and finds its speed histogram ready
+bool stage_g2p_advance_fused(flip_ctx *c, double dt) {
+    if (c->np == 0 || slab_on(c) || !sampling_fast(c) || getenv("FLIP_NO_FUSED_ADVANCE")) return false;
+    AdvectParams a = make_advect_params(c, dt);
+    MacField fn{c->U, c->V, c->W}, fo{c->sU, c->sV, c->sW};
+    const ParticleSoA P = soa_offset(c->P[c->cur_buf], c->ownedBegin);
+    int *deferred = c->sortIdx, *cnt = &c->dS->deferredCount;
+    const double speedLimitStep = c->CFL * c->d.dx / c->frameDt;
+    size_t kt = kt_begin(c);
+    FLIP_CUDA_CHECK(cudaMemsetAsync(cnt, 0, sizeof(int), c->stream));
+    k_g2p_advance_fused<<<cdiv(c->np, 256), 256, 0, c->stream>>>(P, a, fn, fo, c->phiS, c->nearSolid, deferred, cnt, speedLimitStep,
+                                                                 c->maxSubsteps, c->dS);
+    // the few particles outside the interior box: the literal kernels, in stage order
+    k_g2p<<<148, TPB, 0, c->stream>>>(P, a, fn, fo, deferred, cnt);
+    k_speed_hist_list<<<148, TPB, 0, c->stream>>>(P, deferred, cnt, speedLimitStep, c->maxSubsteps, c->dS);
+    k_advance<<<148, TPB, 0, c->stream>>>(P, a, fn, c->phiS, c->nearSolid, deferred, cnt, c->dS);
+    kt_end(c, FLIP_KERNEL_G2P_ADVANCE, kt);
+    c->launches += 4;
+    FLIP_CUDA_CHECK(cudaGetLastError());
+    c->speedHistReady = true;
+    return true;
+}
+
 void stage_advance(flip_ctx *c, double dt) {
+    if (c->fusedAdvanceDone) {
+        // (the kernels ran with the G2P stage; only the removal rules and the sort are left)
+        c->fusedAdvanceDone = false;
+        particles_sort(c, true, c->frameDt, 0, c->np, false);
+        return;
+    }
     if (c->np > 0) {
         AdvectParams a = make_advect_params(c, dt);
         MacField fn{c->U, c->V, c->W};

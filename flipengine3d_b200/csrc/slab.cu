@@ -148,6 +148,8 @@ void slab_exchange_ghosts(flip_ctx *c) {
         k_slab_mark_occ<<<cdiv(d.nC, TPB), TPB, 0, st>>>(d.nC, c->cellStart, c->occ, d.I, d.J, oI, oJ);
         c->launches++;
     }
+    c->occBitsValid = false;         // the one-bit occupancy map of the last sort does not know the ghosts
+    c->stepCounter++;
     c->cur_buf = 1 - c->cur_buf;
     c->npStore = total;              // owned + ghosts
     c->ownedBegin = recvLo;

@@ -100,6 +100,7 @@ def load_library():
     L.flip_get_particle_velocities.argtypes = [vp, vp, ci]
     L.flip_get_velocity_field.argtypes = [vp, vp, vp, vp]
     L.flip_enable_particle_ids.argtypes = [vp, ci]
+    L.flip_set_particle_id_base.argtypes = [vp, ci]
     L.flip_get_particle_ids.argtypes = [vp, vp, ci]
     L.flip_begin_frame.argtypes = [vp, cd]
     L.flip_begin_substep.argtypes = [vp, C.POINTER(cd)]
@@ -365,8 +366,9 @@ class FluidSimulation:
         aos = np.ascontiguousarray(aos, dtype=np.float32).reshape(-1, 6)
         self._check(self.L.flip_set_particles(self.h, aos.shape[0], aos.ctypes.data))
 
-    def enableParticleIds(self, on=True):
+    def enableParticleIds(self, on=True, base=0):
         self._check(self.L.flip_enable_particle_ids(self.h, 1 if on else 0))
+        self._check(self.L.flip_set_particle_id_base(self.h, int(base)))
 
     def getParticleIds(self):
         n = self.getNumMarkerParticles()

@@ -96,7 +96,7 @@ def dam_break(n=128, seed=12345, krange=None, dx=DX):
         k0, k1 = ka, max(kb, ka)
     cells = box_cells(i0, i1, j0, j1, k0, k1)
     pos, vel = seed_cells(cells, dx, seed, skip_cells=skip)
-    return dict(name=f"dambreak{n}", dims=(n, n, n), dx=dx, pos=pos, vel=vel)
+    return dict(name=f"dambreak{n}", dims=(n, n, n), dx=dx, pos=pos, vel=vel, id_offset=8 * skip)
 
 
 def dam_break_z(n=64, seed=12347):

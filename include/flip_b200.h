@@ -206,6 +206,9 @@ int flip_get_particle_velocities(flip_ctx *ctx, float *xyz, int capacity);
  * keeps insertion order, fragmentedvector.h; here order is by cell).  Costs 8 B/particle/step. */
 int flip_enable_particle_ids(flip_ctx *ctx, int on);
 int flip_get_particle_ids(flip_ctx *ctx, int32_t *ids, int capacity);
+/* ids count from `base` instead of 0 (before flip_initialize): a z-slab rank that loads only its own part of a scene
+ * passes the number of particles that precede it, so that ids are global. */
+int flip_set_particle_id_base(flip_ctx *ctx, int base);
 
 /* FluidSimulation::getIsomesh()  fluidsimulation.h:1126 -- the surface FluidManager draws (src/FluidManager.cpp:102-171):
  * ParticleMesher::meshParticles (particlemesher.cpp:36: scalar field of the particles on the grid subdivided
