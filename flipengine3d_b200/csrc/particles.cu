@@ -1486,12 +1486,13 @@ __global__ void __launch_bounds__(SHELL_THREADS) k_sdf_shell(ParticleSoA p, cons
     }
 }
 
-// One thread per point (i,j,k) of the extended index space (FIN_NJ consecutive j per thread, every load issued before
-// the first use): turns the accumulated sums of the three faces of a node into velocities and valid flags and the
-// accumulated minimum of the cell into the liquid SDF (clearing the accumulators for the next step).  A cell that
-// received no minimum lies in no particle's search box.  (Measured: 222 us with one node per thread, 240 us with
-// two -- the kernel is not waiting on its loads.)
-static constexpr int FIN_NJ = 1;
+// One thread per point (i,j,k) of the extended index space: turns the accumulated sums of the three faces of a node
+// into velocities and valid flags and the accumulated minimum of the cell into the liquid SDF (clearing the
+// accumulators for the next step).  A cell that received no minimum lies in no particle's search box.  Five nodes in
+// six are far from any particle and take the short path: zeros and the "no particles" SDF value (finish_phi of an
+// infinite distance: 3 dx, particlelevelset.cpp:295), in 32-bit index arithmetic (the scatter path is limited to
+// 2^28 nodes).  (ncu on the first version: 210 instructions per node, issue-bound at 225 us; the loads were not the
+// limit -- two nodes per thread with all loads hoisted took 240 us.)
 __global__ void k_p2g_finish(GatherParams g, P2GGlobal G, double invSScale,
                              float *__restrict__ U, float *__restrict__ V, float *__restrict__ W,
                              unsigned char *__restrict__ validU, unsigned char *__restrict__ validV,
@@ -1500,70 +1501,61 @@ __global__ void k_p2g_finish(GatherParams g, P2GGlobal G, double invSScale,
                              const unsigned int *__restrict__ near5, int WR, SdfQueues Q) {
     const int I = g.I, J = g.J, K = g.K;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int jb = blockIdx.y * FIN_NJ, k = blockIdx.z;      // k: local plane
+    const int j = blockIdx.y, k = blockIdx.z;      // k: local plane
     if (i > I) return;
-    const int ci = min(i, I - 1), ck = min(k, K - 1);
-    bool n3[FIN_NJ], n5[FIN_NJ];
-    ulonglong2 aU[FIN_NJ], aV[FIN_NJ], aW[FIN_NJ];
-    unsigned int mn[FIN_NJ];
-#pragma unroll
-    for (int m = 0; m < FIN_NJ; m++) {
-        // the neighbourhood bits of the cell the node belongs to (nodes past the last cell of an axis: the last cell)
-        const int j = jb + m;
-        const int cj = min(j, J - 1);
-        const size_t word = (size_t)(ci >> 5) + (size_t)WR * (cj + (size_t)J * ck);
-        n3[m] = j <= J && ((__ldg(near3 + word) >> (ci & 31)) & 1u);
-        n5[m] = j <= J && (n3[m] || ((__ldg(near5 + word) >> (ci & 31)) & 1u));
-    }
-#pragma unroll
-    for (int m = 0; m < FIN_NJ; m++) {
-        const int j = jb + m;
-        const bool hasU = (j < J && k < K), hasV = (i < I && j <= J && k < K), hasW = (i < I && j < J), hasC = (i < I && j < J && k < K);
-        aU[m] = aV[m] = aW[m] = make_ulonglong2(0ull, 0ull);
-        mn[m] = 0u;
-        if (n3[m]) {
-            if (hasU) aU[m] = G.accU[(long long)i + (long long)(I + 1) * (j + (long long)J * k)];
-            if (hasV) aV[m] = G.accV[(long long)i + (long long)I * (j + (long long)(J + 1) * k)];
-            if (hasW) aW[m] = G.accW[(long long)i + (long long)I * (j + (long long)J * k)];
-        }
-        if (n5[m] && hasC) mn[m] = G.minC[(long long)i + (long long)I * (j + (long long)J * k)];
-    }
-#pragma unroll
-    for (int m = 0; m < FIN_NJ; m++) {
-        const int j = jb + m;
-        if (j > J) break;
-        const bool hasU = (j < J && k < K), hasV = (i < I && k < K), hasW = (i < I && j < J), hasC = (i < I && j < J && k < K);
-        const long long iu = (long long)i + (long long)(I + 1) * (j + (long long)J * k);
-        const long long iv = (long long)i + (long long)I * (j + (long long)(J + 1) * k);
-        const long long iw = (long long)i + (long long)I * (j + (long long)J * k);
-        // ---- faces (no particle can reach the faces of a node whose 3x3x3 cells are empty)
-        auto finish = [&](ulonglong2 a, ulonglong2 *acc, long long idx, float *field, unsigned char *valid, int comp) {
-            float val = 0.0f;
-            unsigned char ok = 0;
-            if ((a.x | a.y) != 0ull) {
-                acc[idx] = make_ulonglong2(0ull, 0ull);
-                const float wsum = (float)((double)a.x * (1.0 / (16.0 * (double)P2G_WSCALE)));
-                const float ssum = (float)((double)(long long)a.y * invSScale);
-                int slot = -1;
-                if (wsum < P2G_LITERAL_BAND) slot = warp_append_slot(Q.litCount);
-                if (slot >= 0 && slot < Q.litCap)
-                    Q.litFaces[slot] = (comp << 28) | (int)((long long)i + (long long)(I + 1) * (j + (long long)(J + 1) * k));
-                else { ok = wsum > g.eps; val = ok ? __fdiv_rn(ssum, wsum) : ssum; }   // (a full queue costs digits, nothing else)
+    const bool hasU = (j < J && k < K), hasV = (i < I && k < K), hasW = (i < I && j < J), hasC = (i < I && j < J && k < K);
+    const int iu = i + (I + 1) * (j + J * k), iv = i + I * (j + (J + 1) * k), iw = i + I * (j + J * k);
+    // the neighbourhood bits of the cell the node belongs to (nodes past the last cell of an axis: the last cell)
+    const int ci = min(i, I - 1);
+    const int word = (ci >> 5) + WR * (min(j, J - 1) + J * min(k, K - 1));
+    const unsigned int bit = 1u << (ci & 31);
+    const bool n3 = __ldg(near3 + word) & bit;
+    if (!n3) {
+        // no particle can reach the faces of this node, nor lies in the 3x3x3 cells around the cell
+        if (hasU) { U[iu] = 0.0f; validU[iu] = 0; }
+        if (hasV) { V[iv] = 0.0f; validV[iv] = 0; }
+        if (hasW) { W[iw] = 0.0f; validW[iw] = 0; }
+        if (hasC) {
+            float phi = g.maxDist;
+            if (__ldg(near5 + word) & bit) {           // within reach of a particle two cells away (k_sdf_shell)
+                const unsigned int mn = G.minC[iw];
+                if (mn) { G.minC[iw] = 0u; phi = finish_phi(g, phiS, __uint_as_float(~mn), i, j, k); }
             }
-            field[idx] = val;
-            valid[idx] = ok;
-        };
-        if (hasU) finish(aU[m], G.accU, iu, U, validU, 0);
-        if (hasV) finish(aV[m], G.accV, iv, V, validV, 1);
-        if (hasW) finish(aW[m], G.accW, iw, W, validW, 2);
-        if (!hasC) continue;
-        // ---- liquid SDF of cell (i,j,k)
-        if (mn[m]) {
-            G.minC[iw] = 0u;
-            phiL[iw] = finish_phi(g, phiS, __uint_as_float(~mn[m]), i, j, k);
-        } else {
-            phiL[iw] = finish_phi(g, phiS, 3.0e38f, i, j, k);
+            phiL[iw] = phi;
         }
+        return;
+    }
+    // (all loads first)
+    ulonglong2 aU = make_ulonglong2(0ull, 0ull), aV = aU, aW = aU;
+    if (hasU) aU = G.accU[iu];
+    if (hasV) aV = G.accV[iv];
+    if (hasW) aW = G.accW[iw];
+    const unsigned int mn = hasC ? G.minC[iw] : 0u;
+    auto finish = [&](ulonglong2 a, ulonglong2 *acc, int idx, float *field, unsigned char *valid, int comp) {
+        float val = 0.0f;
+        unsigned char ok = 0;
+        if ((a.x | a.y) != 0ull) {
+            acc[idx] = make_ulonglong2(0ull, 0ull);
+            const float wsum = (float)((double)a.x * (1.0 / (16.0 * (double)P2G_WSCALE)));
+            const float ssum = (float)((double)(long long)a.y * invSScale);
+            int slot = -1;
+            if (wsum < P2G_LITERAL_BAND) slot = warp_append_slot(Q.litCount);
+            if (slot >= 0 && slot < Q.litCap) Q.litFaces[slot] = (comp << 28) | (i + (I + 1) * (j + (J + 1) * k));
+            else { ok = wsum > g.eps; val = ok ? __fdiv_rn(ssum, wsum) : ssum; }   // (a full queue costs digits, nothing else)
+        }
+        field[idx] = val;
+        valid[idx] = ok;
+    };
+    if (hasU) finish(aU, G.accU, iu, U, validU, 0);
+    if (hasV) finish(aV, G.accV, iv, V, validV, 1);
+    if (hasW) finish(aW, G.accW, iw, W, validW, 2);
+    if (!hasC) return;
+    // ---- liquid SDF of cell (i,j,k)
+    if (mn) {
+        G.minC[iw] = 0u;
+        phiL[iw] = finish_phi(g, phiS, __uint_as_float(~mn), i, j, k);
+    } else {
+        phiL[iw] = g.maxDist;
     }
 }
 
@@ -1752,7 +1744,7 @@ static void run_sdf_p2g(flip_ctx *c) {
         }
         // (one CTA per row of nodes where the row fits: I + 1 = 257 nodes would leave a third CTA of 128 with one thread)
         const int fT = std::min(1024, ((d.I + 1 + 31) / 32) * 32);
-        k_p2g_finish<<<dim3(cdiv(d.I + 1, fT), cdiv(d.J + 1, FIN_NJ), d.K + 1), fT, 0, c->stream>>>(g, G, invSScale, c->U, c->V, c->W, c->validU, c->validV, c->validW, c->phiL,
+        k_p2g_finish<<<dim3(cdiv(d.I + 1, fT), d.J + 1, d.K + 1), fT, 0, c->stream>>>(g, G, invSScale, c->U, c->V, c->W, c->validU, c->validV, c->validW, c->phiL,
                                                     c->phiS, near3, near5, WR, Q);
         k_p2g_literal<<<148 * 8, 256, 0, c->stream>>>(c->P[c->cur_buf], c->cellStart, g, c->U, c->V, c->W, c->validU, c->validV,
                                                       c->validW, Q.litFaces, Q.litCount, Q.litCap);

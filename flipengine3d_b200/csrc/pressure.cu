@@ -783,10 +783,87 @@ __device__ __forceinline__ void sm_cycle(const SmLevel *sl, int first, int last,
     for (int l = last - 1; l >= first; l--) sm_postsweeps(sl[l], sl[l + 1], p, tid, nt, sync);
 }
 
+// ---- the levels of at most SM_WARP_CELLS (64) cells: a direct solve.  Walking them with sweeps in one warp costs
+// ~12 us per V-cycle (thirteen dependent passes over <= 64 cells, measured with FLIP_MG_TRACE); their operator is fixed
+// for the whole solve, so its dense inverse is computed once per solve (Gauss-Jordan in shared memory, no pivoting: the
+// Galerkin operators are symmetric positive definite M-matrices unless the liquid has no free surface at all, in
+// which case the flag stays 0 and the sweeps are used) and a V-cycle applies it as a 64 x 64 product.  An exact
+// coarse solve keeps the preconditioner symmetric positive definite.
+__global__ void __launch_bounds__(1024) k_mg_invert_small(MgLevel L, float *__restrict__ inv, int *__restrict__ ok) {
+    constexpr int N = SM_WARP_CELLS;              // the system is padded to N unknowns (identity rows): shifts, no divisions
+    __shared__ float A[N][2 * N + 1];
+    __shared__ float col[N];
+    __shared__ float piv;
+    __shared__ int bad;
+    const int n = L.n, tid = threadIdx.x, nt = blockDim.x;
+    if (n > N) { if (tid == 0) *ok = 0; return; }
+    for (int q = tid; q < N * 2 * N; q += nt) { const int r = q >> 7, c = q & (2 * N - 1); A[r][c] = (c == r + N || c == r) ? 1.0f : 0.0f; }
+    if (tid == 0) bad = 0;
+    __syncthreads();
+    float dloc = 0.0f;
+    for (int c = tid; c < n; c += nt) {
+        const int i = c % L.I, j = (c / L.I) % L.J, k = c / L.sk;
+        if (L.invD[c] == 0.0f) continue;          // an inactive cell keeps x = 0 (its right-hand side is 0)
+        A[c][c] = L.diag[c];
+        // couplings are stored with the lower cell of the pair; a coupling to an inactive cell is 0 by construction
+        if (i + 1 < L.I) { const float o = L.oU[c]; A[c][c + 1] = -o; A[c + 1][c] = -o; }
+        if (j + 1 < L.J) { const float o = L.oV[c]; A[c][c + L.sj] = -o; A[c + L.sj][c] = -o; }
+        if (k + 1 < L.K) { const float o = L.oW[c]; A[c][c + L.sk] = -o; A[c + L.sk][c] = -o; }
+        dloc = fmaxf(dloc, fabsf(L.diag[c]));
+    }
+    __syncthreads();
+    float dmax = 1.0f;
+    for (int c = 0; c < n; c++) dmax = fmaxf(dmax, fabsf(A[c][c]));
+    (void)dloc;
+    for (int p = 0; p < N; p++) {
+        if (tid == 0) { piv = A[p][p]; if (!(piv > 1.0e-6f * dmax)) bad = 1; }
+        if (tid < N) col[tid] = A[tid][p];          // column p before this step touches it
+        __syncthreads();
+        if (bad) break;
+        const float ip = 1.0f / piv;
+        // rows r != p: A[r] -= col[r] * (A[p] / piv); row p: A[p] /= piv   (row p is read unscaled, every element once)
+        for (int q = tid; q < N * 2 * N; q += nt) {
+            const int r = q >> 7, c = q & (2 * N - 1);
+            const float ap = A[p][c] * ip;
+            if (r != p) A[r][c] -= col[r] * ap;
+        }
+        __syncthreads();
+        for (int c = tid; c < 2 * N; c += nt) A[p][c] *= ip;
+        __syncthreads();
+    }
+    __syncthreads();
+    if (bad) { if (tid == 0) *ok = 0; return; }
+    for (int q = tid; q < N * N; q += nt) {
+        const int r = q >> 6, c = q & (N - 1);
+        const bool act = r < n && c < n && L.invD[r] != 0.0f && L.invD[c] != 0.0f;
+        inv[r * N + c] = act ? A[r][N + c] : 0.0f;
+    }
+    if (tid == 0) *ok = 1;
+}
+
+// x = inv * b on the level, by the whole CTA (sixteen threads per row, four columns each; rows >= n idle)
+__device__ __forceinline__ void sm_direct_solve(const SmLevel &Lref, const float *__restrict__ inv, int tid) {
+    const SmLevel L = Lref;
+    const int row = tid >> 4, part = tid & 15;
+    float acc = 0.0f;
+    if (row < L.n) {
+        const float4 a = __ldg(reinterpret_cast<const float4 *>(inv + row * SM_WARP_CELLS + part * 4));
+        const int c = part * 4;
+        acc = a.x * (c < L.n ? L.b[c] : 0.0f) + a.y * (c + 1 < L.n ? L.b[c + 1] : 0.0f) + a.z * (c + 2 < L.n ? L.b[c + 2] : 0.0f) +
+              a.w * (c + 3 < L.n ? L.b[c + 3] : 0.0f);
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    if (row < L.n && part == 0) L.x[row] = acc;
+}
+
 // the shared-memory levels first..last of the V-cycle, called by every thread of ONE CTA
 // (tr: developer probe, a globaltimer stamp after every CTA-wide pass)
 __device__ __forceinline__ void sm_small_body(const SmLevel *sl, int first, int last, const MgParams &p,
-                                              unsigned long long *tr = nullptr, int *ntr = nullptr) {
+                                              unsigned long long *tr = nullptr, int *ntr = nullptr,
+                                              const float *smallInv = nullptr) {
     const int tid = threadIdx.x, nt = blockDim.x;
     auto bsync = [&] {
         __syncthreads();
@@ -804,7 +881,8 @@ __device__ __forceinline__ void sm_small_body(const SmLevel *sl, int first, int 
         sm_presweeps(sl[l], p.nu, p, false, tid, nt, bsync);
         sm_restrict(sl[l], sl[l + 1], tid, nt, bsync);
     }
-    if (tid < 32) sm_cycle(sl, lw, last, p, tid, 32, wsync);
+    if (smallInv) sm_direct_solve(sl[lw], smallInv, tid);       // (block-uniform)
+    else if (tid < 32) sm_cycle(sl, lw, last, p, tid, 32, wsync);
     __syncthreads();
     for (int l = lw - 1; l >= first; l--) sm_postsweeps(sl[l], sl[l + 1], p, tid, nt, bsync);
 }
@@ -866,6 +944,8 @@ struct MgCoarseArgs {
     int group;                       // CTAs that run the levels 2..fs-1 among themselves (group barrier)
     unsigned int *groupBar;          // arrival counter of that barrier (zero between launches)
     unsigned long long *trace;       // developer probe (FLIP_MG_TRACE): globaltimer at every phase boundary, block 0
+    const float *smallInv;           // dense inverse of the first level of at most SM_WARP_CELLS cells (k_mg_invert_small)
+    const int *smallInvOk;           // ... usable (the level's operator was not singular)
 };
 
 __device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int *p) {
@@ -1057,7 +1137,7 @@ __global__ void __launch_bounds__(1024) k_mg_coarse(MgCoarseArgs A, const Device
             for (int c = tid; c < Gl.n; c += nt) L.b[c] = Gl.b[c];
             __syncthreads();
             stamp();
-            sm_small_body(sl, A.fs, A.last, A.p, A.trace, &ntrace);
+            sm_small_body(sl, A.fs, A.last, A.p, A.trace, &ntrace, (A.smallInv && *A.smallInvOk) ? A.smallInv : nullptr);
             stamp();
             for (int c = tid; c < Gl.n; c += nt) Gl.x[c] = L.x[c];
         }
@@ -1866,6 +1946,9 @@ struct PressureScratch {
     float *coarseBase = nullptr;       // levels >= 1 inside `pool` (L2 persistence window)
     size_t coarseBytes = 0, l2SetAside = 0, l2Window = 0;
     unsigned long long *trace = nullptr;   // FLIP_MG_TRACE developer probe
+    float *smallInv = nullptr;             // dense inverse of the first level of <= SM_WARP_CELLS cells, and its validity flag
+    int *smallInvOk = nullptr;
+    int smallLevel = 0;
     int coopBlocks = 0;                // grid of the persistent solver (SMs x resident CTAs)
     // z-slabs: levels >= Lc span the WHOLE domain and are held (redundantly) by every rank; the
     // restricted residual of level Lc is all-gathered once per V-cycle.  Lc == 0: every level is local.
@@ -1995,6 +2078,14 @@ void pressure_alloc(flip_ctx *c) {
                     if (const char *e = getenv("FLIP_MG_GROUP")) ps->coarseGroup = std::max(1, std::min(sms, atoi(e)));            // tuning knob
                     FLIP_CUDA_CHECK(cudaMalloc(&ps->groupBar, 64));
                     FLIP_CUDA_CHECK(cudaMemset(ps->groupBar, 0, 64));
+                    for (int l = ps->firstSmall; l < ps->numLevels; l++)
+                        if (ps->lv[l].n <= SM_WARP_CELLS) { ps->smallLevel = l; break; }
+                    if (ps->smallLevel && !getenv("FLIP_MG_NO_DIRECT")) {
+                        FLIP_CUDA_CHECK(cudaMalloc(&ps->smallInv, sizeof(float) * SM_WARP_CELLS * SM_WARP_CELLS));
+                        FLIP_CUDA_CHECK(cudaMemset(ps->smallInv, 0, sizeof(float) * SM_WARP_CELLS * SM_WARP_CELLS));
+                        FLIP_CUDA_CHECK(cudaMalloc(&ps->smallInvOk, sizeof(int)));
+                        FLIP_CUDA_CHECK(cudaMemset(ps->smallInvOk, 0, sizeof(int)));
+                    }
                 }
                 if (getenv("FLIP_MG_TRACE")) {
                     FLIP_CUDA_CHECK(cudaMalloc(&ps->trace, 64 * sizeof(unsigned long long)));
@@ -2063,6 +2154,7 @@ void pressure_free(flip_ctx *c) {
         PressureScratch *ps = (PressureScratch *)c->mg;
         cudaFree(ps->maskAll); cudaFree(ps->maskPrev); cudaFree(ps->flagAll); cudaFree(ps->posAll); cudaFree(ps->pool); cudaFree(ps->gpool);
         cudaFree(ps->segPool); cudaFree(ps->gSegPool); cudaFree(ps->trace); cudaFree(ps->groupBar);
+        cudaFree(ps->smallInv); cudaFree(ps->smallInvOk);
         cudaFree(ps->vq); cudaFree(ps->vs2); cudaFree(ps->vr2);
         delete ps;
         c->mg = nullptr;
@@ -2190,6 +2282,10 @@ void stage_pressure(flip_ctx *c, double dt) {
         if (Lc == 0) {
             for (int l = 1; l + 1 < ps->numLevels; l++) {
                 k_mg_coarsen<<<cdiv(ps->lv[l + 1].n, TPB), TPB, 0, st>>>(ps->lv[l], ps->lv[l + 1]); c->launches++;
+            }
+            if (!slab && ps->smallInv) {
+                k_mg_invert_small<<<1, 1024, 0, st>>>(ps->lv[ps->smallLevel], ps->smallInv, ps->smallInvOk);
+                c->launches++;
             }
             if (!slab) {
                 // active segments of the coarse levels; cells outside them keep a zero iterate for the whole solve
@@ -2406,6 +2502,7 @@ void stage_pressure(flip_ctx *c, double dt) {
             A.smemFloats = (int)(ps->coarseSmemBytes / sizeof(float));
             A.group = ps->coarseGroup; A.groupBar = ps->groupBar;
             A.trace = ps->trace;
+            A.smallInv = ps->smallInv; A.smallInvOk = ps->smallInvOk;
             const DeviceScalars *Sdev = c->dS;
             void *args[] = {&A, &Sdev};
             FLIP_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)k_mg_coarse, dim3(ps->coarseBlocks), dim3(1024), args,
