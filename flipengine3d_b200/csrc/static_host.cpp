@@ -47,65 +47,84 @@ void build_box_solid_sdf(const Dims &d, std::vector<float> &phi) {
     }
 }
 
-// LevelsetUtils::fractionInside(float,float)  levelsetutils.cpp:39-51
-static float fractionInside2(float phiLeft, float phiRight) {
-    if (phiLeft < 0 && phiRight < 0) return 1;
-    if (phiLeft < 0 && phiRight >= 0) return phiLeft / (phiLeft - phiRight);
-    if (phiLeft >= 0 && phiRight < 0) return phiRight / (phiRight - phiLeft);
+// Fraction of a segment on which a linear function with end values a, b is negative
+// (LevelsetUtils::fractionInside(float,float), levelsetutils.cpp:39-51).
+static float negative_fraction(float a, float b) {
+    const bool na = a < 0, nb = b < 0;
+    if (na && nb) return 1;
+    if (na) return a / (a - b);
+    if (nb) return b / (b - a);
     return 0;
 }
 
-static void cycle4(float *a) {
-    float t = a[0];
-    a[0] = a[1]; a[1] = a[2]; a[2] = a[3]; a[3] = t;
+// Area fraction of a unit square on which the bilinear patch through its corner values is negative, by the sixteen
+// marching-squares cases (LevelsetUtils::fractionInside(bl, br, tl, tr), levelsetutils.cpp:62-142; the reference rotates
+// the corner list in a loop until it reaches the canonical orientation of the case -- here the rotation of every
+// sign mask is tabulated).  Corners in cyclic order q[0..3] = bl, br, tr, tl; bit c of the mask: corner c negative.
+// The float operations and their order are the reference's: the weights derived from this are bit-identical.
+namespace {
+struct SquareCase {
+    signed char kind;      // -1: none negative, 0: one, 1: two adjacent, 2: two opposite, 3: three, 4: all
+    signed char first;     // index of the corner that comes first in the canonical orientation
+};
+SquareCase square_case(unsigned mask) {
+    const int count = __builtin_popcount(mask);
+    auto neg = [&](int c) { return (mask >> (c & 3)) & 1u; };
+    if (count == 0) return {-1, 0};
+    if (count == 4) return {4, 0};
+    for (int s = 0; s < 4; s++) {
+        if (count == 1 && neg(s)) return {0, (signed char)s};                       // the negative corner first
+        if (count == 3 && !neg(s)) return {3, (signed char)s};                      // the positive corner first
+        if (count == 2 && neg(s) && neg(s + 1)) return {1, (signed char)s};         // the negative edge first
+    }
+    for (int s = 0; s < 4; s++)
+        if (neg(s) && neg(s + 2)) return {2, (signed char)s};                       // the diagonal, lowest index first
+    return {-1, 0};
 }
+const struct SquareTable {
+    SquareCase c[16];
+    SquareTable() { for (unsigned m = 0; m < 16; m++) c[m] = square_case(m); }
+} kSquare;
+}  // namespace
 
-// LevelsetUtils::fractionInside(float bl, br, tl, tr)  levelsetutils.cpp:62-142 (marching-squares
-// area of the negative region of a bilinear patch).
-static float fractionInside4(float phibl, float phibr, float phitl, float phitr) {
-    int insideCount = (phibl < 0 ? 1 : 0) + (phitl < 0 ? 1 : 0) + (phibr < 0 ? 1 : 0) + (phitr < 0 ? 1 : 0);
-    float list[4] = {phibl, phibr, phitr, phitl};
-    if (insideCount == 4) return 1;
-    if (insideCount == 3) {
-        while (list[0] < 0) cycle4(list);
-        float side0 = 1 - fractionInside2(list[0], list[3]);
-        float side1 = 1 - fractionInside2(list[0], list[1]);
-        return 1.0f - 0.5f * side0 * side1;
-    }
-    if (insideCount == 2) {
-        while (list[0] >= 0 || !(list[1] < 0 || list[2] < 0)) cycle4(list);
-        if (list[1] < 0) {
-            float sideLeft = fractionInside2(list[0], list[3]);
-            float sideRight = fractionInside2(list[1], list[2]);
-            return 0.5f * (sideLeft + sideRight);
+static float negative_area(float bl, float br, float tl, float tr) {
+    const float q[4] = {bl, br, tr, tl};
+    const unsigned mask = (bl < 0 ? 1u : 0u) | (br < 0 ? 2u : 0u) | (tr < 0 ? 4u : 0u) | (tl < 0 ? 8u : 0u);
+    const SquareCase sc = kSquare.c[mask];
+    const float v0 = q[sc.first & 3], v1 = q[(sc.first + 1) & 3], v2 = q[(sc.first + 2) & 3], v3 = q[(sc.first + 3) & 3];
+    switch (sc.kind) {
+        case 4: return 1;
+        case 3: {       // a positive corner (v0) cut off by its two edges
+            const float cutA = 1 - negative_fraction(v0, v3), cutB = 1 - negative_fraction(v0, v1);
+            return 1.0f - 0.5f * cutA * cutB;
         }
-        float middlePoint = 0.25f * (list[0] + list[1] + list[2] + list[3]);
-        if (middlePoint < 0) {
-            float area = 0;
-            float side1 = 1 - fractionInside2(list[0], list[3]);
-            float side3 = 1 - fractionInside2(list[2], list[3]);
-            area += 0.5f * side1 * side3;
-            float side2 = 1 - fractionInside2(list[2], list[1]);
-            float side0 = 1 - fractionInside2(list[0], list[1]);
-            area += 0.5f * side0 * side2;
-            return 1.0f - area;
+        case 1: {       // the edge v0-v1 is negative: a trapezoid
+            const float along03 = negative_fraction(v0, v3), along12 = negative_fraction(v1, v2);
+            return 0.5f * (along03 + along12);
         }
-        float area = 0;
-        float side0 = fractionInside2(list[0], list[1]);
-        float side1 = fractionInside2(list[0], list[3]);
-        area += 0.5f * side0 * side1;
-        float side2 = fractionInside2(list[2], list[1]);
-        float side3 = fractionInside2(list[2], list[3]);
-        area += 0.5f * side2 * side3;
-        return area;
+        case 2: {       // v0 and v2 negative: the sign of the centre decides whether they are joined
+            const float centre = 0.25f * (v0 + v1 + v2 + v3);
+            if (centre < 0) {
+                float positive = 0;
+                const float a3 = 1 - negative_fraction(v0, v3), c3 = 1 - negative_fraction(v2, v3);
+                positive += 0.5f * a3 * c3;
+                const float c1 = 1 - negative_fraction(v2, v1), a1 = 1 - negative_fraction(v0, v1);
+                positive += 0.5f * a1 * c1;
+                return 1.0f - positive;
+            }
+            float negative = 0;
+            const float a1 = negative_fraction(v0, v1), a3 = negative_fraction(v0, v3);
+            negative += 0.5f * a1 * a3;
+            const float c1 = negative_fraction(v2, v1), c3 = negative_fraction(v2, v3);
+            negative += 0.5f * c1 * c3;
+            return negative;
+        }
+        case 0: {       // a negative corner (v0) cut off by its two edges
+            const float cutA = negative_fraction(v0, v3), cutB = negative_fraction(v0, v1);
+            return 0.5f * cutA * cutB;
+        }
+        default: return 0;
     }
-    if (insideCount == 1) {
-        while (list[0] >= 0) cycle4(list);
-        float side0 = fractionInside2(list[0], list[3]);
-        float side1 = fractionInside2(list[0], list[1]);
-        return 0.5f * side0 * side1;
-    }
-    return 0;
 }
 
 static inline float clamp01(float w) { return std::max(0.0f, std::min(w, 1.0f)); }
@@ -122,17 +141,17 @@ void build_weights(const Dims &d, const std::vector<float> &phi, std::vector<flo
     for (int k = 0; k < d.K; k++)
         for (int j = 0; j < d.J; j++)
             for (int i = 0; i <= d.I; i++, idx++)
-                wU[idx] = clamp01(1.0f - fractionInside4(P(i, j, k), P(i, j + 1, k), P(i, j, k + 1), P(i, j + 1, k + 1)));
+                wU[idx] = clamp01(1.0f - negative_area(P(i, j, k), P(i, j + 1, k), P(i, j, k + 1), P(i, j + 1, k + 1)));
     idx = 0;
     for (int k = 0; k < d.K; k++)
         for (int j = 0; j <= d.J; j++)
             for (int i = 0; i < d.I; i++, idx++)
-                wV[idx] = clamp01(1.0f - fractionInside4(P(i, j, k), P(i, j, k + 1), P(i + 1, j, k), P(i + 1, j, k + 1)));
+                wV[idx] = clamp01(1.0f - negative_area(P(i, j, k), P(i, j, k + 1), P(i + 1, j, k), P(i + 1, j, k + 1)));
     idx = 0;
     for (int k = 0; k <= d.K; k++)
         for (int j = 0; j < d.J; j++)
             for (int i = 0; i < d.I; i++, idx++)
-                wW[idx] = clamp01(1.0f - fractionInside4(P(i, j, k), P(i, j + 1, k), P(i + 1, j, k), P(i + 1, j + 1, k)));
+                wW[idx] = clamp01(1.0f - negative_area(P(i, j, k), P(i, j + 1, k), P(i + 1, j, k), P(i + 1, j + 1, k)));
 }
 
 // FluidSimulation::_updateNearSolidGrid (fluidsimulation.cpp:3083-3127): coarse cells (3dx) holding a
