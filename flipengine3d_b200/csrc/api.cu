@@ -76,6 +76,7 @@ static void free_all(flip_ctx *c) {
     particles_free(c);
     free_grids(c);
     mesher_free(c);
+    for (auto &o : c->fluidObjects) cudaFree(o.dsdf);
     cudaFree(c->scanTemp);
     cudaFree(c->nearSolid); cudaFree(c->pressure);
     cudaFree(c->dS);
@@ -310,32 +311,122 @@ int flip_load_particles(flip_ctx *c, int n, const float *pos, const float *vel) 
     });
 }
 
-int flip_add_fluid_box(flip_ctx *c, const double lo[3], const double hi[3], const double vel[3]) {
-    return guarded(c, [&] {
-        flip_ctx::FluidObject o;
-        const int n[3] = {c->d.I, c->d.J, c->d.Kg};
-        for (int a = 0; a < 3; a++) {
-            o.boxLo[a] = lo[a]; o.boxHi[a] = hi[a]; o.vel[a] = vel ? vel[a] : 0.0;
+static flip_ctx::FluidObject make_fluid_object(flip_ctx *c, const float *sdf, const int cellLo[3], const int cellHi[3], const double lo[3],
+                                              const double hi[3], const double vel[3]) {
+    flip_ctx::FluidObject o;
+    const int n[3] = {c->d.I, c->d.J, c->d.Kg};
+    for (int a = 0; a < 3; a++) {
+        o.vel[a] = vel ? vel[a] : 0.0;
+        if (sdf) {
+            o.boxLo[a] = o.boxHi[a] = 0.0;
+            o.lo[a] = cellLo ? std::max(0, cellLo[a]) : 0;
+            o.hi[a] = cellHi ? std::min(n[a], cellHi[a]) : n[a];
+        } else {
+            o.boxLo[a] = lo[a]; o.boxHi[a] = hi[a];
             // the cells that can have a corner node inside the box
             o.lo[a] = std::max(0, (int)floor(lo[a] / c->d.dx) - 1);
             o.hi[a] = std::min(n[a], (int)ceil(hi[a] / c->d.dx) + 1);
         }
-        c->fluidObjects.push_back(std::move(o));
-    });
+    }
+    if (sdf) o.sdf.assign(sdf, sdf + (size_t)(n[0] + 1) * (n[1] + 1) * (n[2] + 1));
+    return o;
+}
+
+// The level-set grid a MeshFluidSource keeps for itself (MeshFluidSource::update, meshfluidsource.cpp:178-198): the
+// bounding box of the mesh grown by _gridpad = 4 cell widths in total (AABB::expand, aabb.cpp:122-128: half on either
+// side), in cells [gmin, gmax] clamped to the domain, with gmax - gmin + 2 nodes per axis.  The velocity constraint of
+// an inflow reads this grid at the WORLD position (no offset subtracted, fluidsimulation.cpp:3401,4138 -- seeding does
+// subtract it, :4549), and nodes outside the grid read as 0: stage_inflow_* reproduce exactly that.
+static void source_level_set_grid(flip_ctx *c, flip_ctx::FluidObject &o, const double meshLo[3], const double meshHi[3]) {
+    const int n[3] = {c->d.I, c->d.J, c->d.Kg};
+    const double dx = c->d.dx, invdx = 1.0 / dx;
+    const double pad = 4.0 * dx;
+    for (int a = 0; a < 3; a++) {
+        const float vmin = (float)meshLo[a], vmax = (float)meshHi[a];                   // mesh vertices are floats
+        double width = (double)vmax - (double)vmin + 1e-9;                              // AABB(points), aabb.cpp:54-82
+        const float pmin = vmin - (float)(0.5 * pad);                                   // position -= vec3(h, h, h)
+        width += pad;
+        const float pmax = pmin + (float)width;                                         // getMaxPoint
+        int gmin = (int)floor((double)pmin * invdx), gmax = (int)floor((double)pmax * invdx);
+        gmin = std::max(gmin, 0); gmax = std::min(gmax, n[a] - 1);
+        o.sdfOrigin[a] = gmin;
+        o.sdfNodes[a] = std::max(gmax - gmin + 1, 1) + 1;
+    }
+}
+
+int flip_add_fluid_box(flip_ctx *c, const double lo[3], const double hi[3], const double vel[3]) {
+    return guarded(c, [&] { c->fluidObjects.push_back(make_fluid_object(c, nullptr, nullptr, nullptr, lo, hi, vel)); });
 }
 
 int flip_add_fluid_sdf(flip_ctx *c, const float *sdf, const int cellLo[3], const int cellHi[3], const double vel[3]) {
     return guarded(c, [&] {
         if (!sdf) throw ApiError(FLIP_ERR_RUNTIME, "null signed distance field");
-        flip_ctx::FluidObject o;
-        const int n[3] = {c->d.I, c->d.J, c->d.Kg};
-        for (int a = 0; a < 3; a++) {
-            o.boxLo[a] = o.boxHi[a] = 0.0; o.vel[a] = vel ? vel[a] : 0.0;
-            o.lo[a] = cellLo ? std::max(0, cellLo[a]) : 0;
-            o.hi[a] = cellHi ? std::min(n[a], cellHi[a]) : n[a];
-        }
-        o.sdf.assign(sdf, sdf + (size_t)(n[0] + 1) * (n[1] + 1) * (n[2] + 1));
+        c->fluidObjects.push_back(make_fluid_object(c, sdf, cellLo, cellHi, nullptr, nullptr, vel));
+    });
+}
+
+int flip_add_fluid_source_box(flip_ctx *c, int outflow, const double lo[3], const double hi[3], const double vel[3], int *id) {
+    return guarded(c, [&] {
+        flip_ctx::FluidObject o = make_fluid_object(c, nullptr, nullptr, nullptr, lo, hi, vel);
+        source_level_set_grid(c, o, lo, hi);
+        o.kind = outflow ? 2 : 1; o.id = c->nextSourceId++;
+        if (id) *id = o.id;
         c->fluidObjects.push_back(std::move(o));
+    });
+}
+
+int flip_add_fluid_source_sdf(flip_ctx *c, int outflow, const float *sdf, const int cellLo[3], const int cellHi[3],
+                              const double meshLo[3], const double meshHi[3], const double vel[3], int *id) {
+    return guarded(c, [&] {
+        if (!sdf) throw ApiError(FLIP_ERR_RUNTIME, "null signed distance field");
+        flip_ctx::FluidObject o = make_fluid_object(c, sdf, cellLo, cellHi, nullptr, nullptr, vel);
+        if (meshLo && meshHi) source_level_set_grid(c, o, meshLo, meshHi);
+        else {
+            // no mesh bounds given: the box of the nodes inside the object
+            const int ni = c->d.I + 1, nj = c->d.J + 1, nk = c->d.Kg + 1;
+            double blo[3] = {1e300, 1e300, 1e300}, bhi[3] = {-1e300, -1e300, -1e300};
+            for (int k = 0; k < nk; k++)
+                for (int j = 0; j < nj; j++)
+                    for (int i = 0; i < ni; i++)
+                        if (sdf[(size_t)i + (size_t)ni * (j + (size_t)nj * k)] <= 0.0f) {
+                            const int q[3] = {i, j, k};
+                            for (int a = 0; a < 3; a++) { blo[a] = std::min(blo[a], q[a] * c->d.dx); bhi[a] = std::max(bhi[a], q[a] * c->d.dx); }
+                        }
+            if (blo[0] > bhi[0]) for (int a = 0; a < 3; a++) blo[a] = bhi[a] = 0.0;
+            source_level_set_grid(c, o, blo, bhi);
+        }
+        o.kind = outflow ? 2 : 1; o.id = c->nextSourceId++;
+        if (id) *id = o.id;
+        c->fluidObjects.push_back(std::move(o));
+    });
+}
+
+int flip_enable_fluid_source(flip_ctx *c, int id, int on) {
+    return guarded(c, [&] {
+        for (auto &o : c->fluidObjects)
+            if (o.kind != 0 && o.id == id) { o.enabled = on != 0; return; }
+        throw ApiError(FLIP_ERR_RUNTIME, "Error: could not find mesh fluid source to remove.");
+    });
+}
+
+int flip_constrain_fluid_source_velocity(flip_ctx *c, int id, int on) {
+    return guarded(c, [&] {
+        for (auto &o : c->fluidObjects)
+            if (o.kind != 0 && o.id == id) { o.constrained = on != 0; return; }
+        throw ApiError(FLIP_ERR_RUNTIME, "Error: could not find mesh fluid source.");
+    });
+}
+
+int flip_remove_fluid_source(flip_ctx *c, int id) {
+    return guarded(c, [&] {
+        for (size_t q = 0; q < c->fluidObjects.size(); q++)
+            if (c->fluidObjects[q].kind != 0 && c->fluidObjects[q].id == id) {
+                FLIP_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+                cudaFree(c->fluidObjects[q].dsdf);
+                c->fluidObjects.erase(c->fluidObjects.begin() + q);
+                return;
+            }
+        throw ApiError(FLIP_ERR_RUNTIME, "Error: could not find mesh fluid source to remove.");      // :1979-1982
     });
 }
 
@@ -402,6 +493,7 @@ static double next_time_step(flip_ctx *c, double dt) {
         // body-force term |g| * dt, with |g| the float vec3 length
         maxu = 0.0;
         for (auto &o : c->fluidObjects) {
+            if (o.kind == 2 || !o.enabled) continue;       // queued objects and enabled inflow sources (:5536-5545)
             float vx = (float)o.vel[0], vy = (float)o.vel[1], vz = (float)o.vel[2];
             maxu = std::max(maxu, (double)sqrtf(vx * vx + vy * vy + vz * vz));
         }
@@ -453,7 +545,7 @@ static void run_stage(flip_ctx *c, int stage, double dt) {
         case FLIP_STAGE_P2G: stage_p2g(c); break;
         case FLIP_STAGE_EXTRAPOLATE_A: if (c->np_global > 0 || c->npStore > 0) stage_extrapolate(c); break;   // :3262 guards on !empty()
         case FLIP_STAGE_SAVE: stage_save(c); break;
-        case FLIP_STAGE_BODY_FORCE: stage_body_force(c, dt); break;
+        case FLIP_STAGE_BODY_FORCE: stage_body_force(c, dt); stage_inflow_body_force_exclusion(c); break;
         case FLIP_STAGE_PRESSURE:
             stage_pressure(c, dt);
             if (slab_on(c)) {
@@ -470,8 +562,8 @@ static void run_stage(flip_ctx *c, int stage, double dt) {
         case FLIP_STAGE_EXTRAPOLATE_B: stage_extrapolate(c); break;
         case FLIP_STAGE_CONSTRAIN: stage_constrain(c); break;
         case FLIP_STAGE_G2P:
-            if (c->fuseAdvance && stage_g2p_advance_fused(c, dt)) c->fusedAdvanceDone = true;
-            else stage_g2p(c);
+            if (c->fuseAdvance && !has_constrained_inflow(c) && stage_g2p_advance_fused(c, dt)) c->fusedAdvanceDone = true;
+            else { stage_g2p(c); stage_inflow_constrain_particles(c); }
             break;
         case FLIP_STAGE_ADVANCE: stage_advance(c, dt); break;
         case FLIP_STAGE_TAIL: stage_fluid_objects(c); break;       // _updateFluidObjects  :5504

@@ -137,8 +137,15 @@ struct flip_ctx {
     std::vector<float> loadQueuePos, loadQueueVel;   // loadMarkerParticleData queue
     // addMeshFluid queue (_addedFluidMeshObjectQueue, fluidsimulation.h): cell range [lo,hi) of the object, its fluid
     // velocity, and its signed distance field -- a nodal array of the global grid, or (sdf empty) an axis-aligned box
-    struct FluidObject { int lo[3], hi[3]; double boxLo[3], boxHi[3], vel[3]; std::vector<float> sdf; };
+    // kind 0: queued object, seeded once; 1: inflow source (emits at the end of every substep); 2: outflow source
+    // (MeshFluidSource, meshfluidsource.h; _updateMeshFluidSources fluidsimulation.cpp:4700-4722)
+    struct FluidObject {
+        int lo[3], hi[3]; double boxLo[3], boxHi[3], vel[3]; std::vector<float> sdf;
+        int kind = 0, id = 0; bool enabled = true, constrained = true; float *dsdf = nullptr;
+        int sdfOrigin[3] = {0, 0, 0}, sdfNodes[3] = {0, 0, 0};   // the source's own level-set grid (meshfluidsource.cpp:178-198)
+    };
     std::vector<FluidObject> fluidObjects;
+    int nextSourceId = 1;
     int nextParticleId = 0;                   // ids of particles seeded after the load (enableParticleIds)
     std::vector<float> hostSolidPhi;          // nodal
     bool userSolidPhi = false;
@@ -252,7 +259,10 @@ void stage_advance(flip_ctx *c, double dt);
 bool stage_g2p_advance_fused(flip_ctx *c, double dt);   // whole-step path: G2P + RK3 in one pass (false: not applicable)
 
 // seed.cu
-void stage_fluid_objects(flip_ctx *c);          // seeds the queued fluid objects on the device (end of a substep)
+void stage_fluid_objects(flip_ctx *c);          // seeds the queued fluid objects / runs the sources (end of a substep)
+bool has_constrained_inflow(const flip_ctx *c);          // an enabled inflow source that pins the velocity inside it
+void stage_inflow_body_force_exclusion(flip_ctx *c);     // _getInflowConstrainedVelocityComponents :3372
+void stage_inflow_constrain_particles(flip_ctx *c);      // _constrainMarkerParticleVelocities :4161
 
 // mesher.cu
 void mesher_get(flip_ctx *c, int *nv, int *nt, float *verts, int *tris);

@@ -79,6 +79,11 @@ def load_library():
     L.flip_load_particles.argtypes = [vp, ci, vp, vp]
     L.flip_add_fluid_box.argtypes = [vp, C.POINTER(cd), C.POINTER(cd), C.POINTER(cd)]
     L.flip_add_fluid_sdf.argtypes = [vp, vp, C.POINTER(ci), C.POINTER(ci), C.POINTER(cd)]
+    L.flip_add_fluid_source_box.argtypes = [vp, ci, C.POINTER(cd), C.POINTER(cd), C.POINTER(cd), C.POINTER(ci)]
+    L.flip_add_fluid_source_sdf.argtypes = [vp, ci, vp, C.POINTER(ci), C.POINTER(ci), C.POINTER(cd), C.POINTER(ci)]
+    L.flip_enable_fluid_source.argtypes = [vp, ci, ci]
+    L.flip_remove_fluid_source.argtypes = [vp, ci]
+    L.flip_constrain_fluid_source_velocity.argtypes = [vp, ci, ci]
     L.flip_set_surface_subdivision_level.argtypes = [vp, ci]
     L.flip_set_surface_smoothing.argtypes = [vp, cd, ci]
     L.flip_get_isomesh_size.argtypes = [vp, C.POINTER(ci), C.POINTER(ci)]
@@ -263,8 +268,22 @@ class FluidSimulation:
     def setSolverMode(self, persistent=True):
         self._check(self.L.flip_set_solver_mode(self.h, 1 if persistent else 0))
 
-    def setSurfaceSubdivisionLevel(self, n):
-        """Accepted and ignored: surface reconstruction is outside the hot path."""
+    def addMeshFluidSourceBox(self, lo, hi, velocity=(0.0, 0.0, 0.0), outflow=False):
+        """addMeshFluidSource with a static box MeshFluidSource (inflow, or outflow=True); returns the source id."""
+        a, b, v = (C.c_double * 3)(*lo), (C.c_double * 3)(*hi), (C.c_double * 3)(*velocity)
+        sid = C.c_int()
+        self._check(self.L.flip_add_fluid_source_box(self.h, 1 if outflow else 0, a, b, v, C.byref(sid)))
+        return sid.value
+
+    def enableMeshFluidSource(self, sid, on=True):
+        self._check(self.L.flip_enable_fluid_source(self.h, int(sid), 1 if on else 0))
+
+    def constrainMeshFluidSourceVelocity(self, sid, on=True):
+        """MeshFluidSource::enable/disableConstrainedFluidVelocity (on by default)."""
+        self._check(self.L.flip_constrain_fluid_source_velocity(self.h, int(sid), 1 if on else 0))
+
+    def removeMeshFluidSource(self, sid):
+        self._check(self.L.flip_remove_fluid_source(self.h, int(sid)))
 
     def getSimulationDimensions(self):
         return tuple(d * self.dx for d in self.dims)

@@ -154,6 +154,27 @@ int flip_load_particles(flip_ctx *ctx, int n, const float *positions_xyz, const 
  *     src/FluidManager.cpp:56-64); its nodal distances are evaluated in place. */
 int flip_add_fluid_sdf(flip_ctx *ctx, const float *nodal_sdf, const int cell_lo[3], const int cell_hi[3], const double velocity[3]);
 int flip_add_fluid_box(flip_ctx *ctx, const double lo[3], const double hi[3], const double velocity[3]);
+/* FluidSimulation::addMeshFluidSource / removeMeshFluidSource  fluidsimulation.cpp:1953-1985 with a MeshFluidSource
+ * (meshfluidsource.h) that is an inflow (setInflow: emits at the end of EVERY substep where sub-cells are free,
+ * _updateInflowMeshFluidSource :4561-4604 with the default substep emissions of 1) or an outflow (setOutflow + fluid
+ * outflow: removes the particles inside it, _updateOutflowMeshFluidSource :4607-4668, not inversed).  Static sources,
+ * given as a box or as a nodal signed distance field like the queued objects above; *id identifies the source for
+ * flip_enable_fluid_source (MeshFluidSource::enable / disable) and flip_remove_fluid_source.  Same device kernels as
+ * the queue (csrc/seed.cu). */
+int flip_add_fluid_source_box(flip_ctx *ctx, int outflow, const double lo[3], const double hi[3], const double velocity[3], int *id);
+int flip_add_fluid_source_sdf(flip_ctx *ctx, int outflow, const float *nodal_sdf, const int cell_lo[3], const int cell_hi[3],
+                              const double mesh_lo[3], const double mesh_hi[3], const double velocity[3], int *id);
+/* mesh_lo / mesh_hi: the bounding box of the source's mesh (may be NULL: the box of the nodes with sdf <= 0).  It fixes
+ * the extent of the level-set grid the reference keeps per source (MeshFluidSource::update, meshfluidsource.cpp:178-198),
+ * which the inflow velocity constraint reads at un-offset world positions (fluidsimulation.cpp:3401, :4138) -- a quirk
+ * of the reference that decides where the constraint acts and that is reproduced as it is. */
+int flip_enable_fluid_source(flip_ctx *ctx, int id, int on);
+int flip_remove_fluid_source(flip_ctx *ctx, int id);
+/* MeshFluidSource::enableConstrainedFluidVelocity / disableConstrainedFluidVelocity (meshfluidsource.cpp:146-152; on by
+ * default): while on, the faces inside an inflow get no body force (_getInflowConstrainedVelocityComponents
+ * fluidsimulation.cpp:3372) and the particles inside it carry the source's velocity after the PIC/FLIP update
+ * (_constrainMarkerParticleVelocities :4113). */
+int flip_constrain_fluid_source_velocity(flip_ctx *ctx, int id, int on);
 /* FluidSimulation::_addMarkerParticle  fluidsimulation.cpp:2637 (range-checked push). */
 int flip_add_marker_particle(flip_ctx *ctx, const float position[3], const float velocity[3]);
 

@@ -174,6 +174,43 @@ private:
     TriangleMesh _mesh;
 };
 
+// MeshFluidSource (meshfluidsource.h:40-117) for static closed meshes: an inflow that emits at the end of every substep
+// or an outflow that removes the particles inside it.  enable() / disable() and removeMeshFluidSource act on the device
+// object once the source has been added to a simulation.
+class FluidSimulation;
+class MeshFluidSource {
+public:
+    MeshFluidSource() = default;
+    MeshFluidSource(int i, int j, int k, double dx) : _object(i, j, k, dx) {}
+    void updateMeshStatic(TriangleMesh meshCurrent) { _object.updateMeshStatic(std::move(meshCurrent)); }
+    void enable() { _enabled = true; push(); }
+    void disable() { _enabled = false; push(); }
+    bool isEnabled() const { return _enabled; }
+    void setInflow() { _inflow = true; }
+    bool isInflow() const { return _inflow; }
+    void setOutflow() { _inflow = false; }
+    bool isOutflow() const { return !_inflow; }
+    void setVelocity(vmath::vec3 v) { _velocity = v; }
+    vmath::vec3 getVelocity() const { return _velocity; }
+    void enableConstrainedFluidVelocity() { _constrained = true; push(); }
+    void disableConstrainedFluidVelocity() { _constrained = false; push(); }
+    bool isConstrainedFluidVelocityEnabled() const { return _constrained; }
+    MeshObject *getMeshObject() { return &_object; }
+
+private:
+    friend class FluidSimulation;
+    void push() {
+        if (!_ctx) return;
+        flip_enable_fluid_source(_ctx, _id, _enabled ? 1 : 0);
+        flip_constrain_fluid_source_velocity(_ctx, _id, _constrained ? 1 : 0);
+    }
+    MeshObject _object;
+    bool _enabled = true, _inflow = true, _constrained = true;
+    vmath::vec3 _velocity;
+    flip_ctx *_ctx = nullptr;
+    int _id = 0;
+};
+
 // MACVelocityField (macvelocityfield.cpp:46-54,100-110): the three raw face arrays, U (i+1,j,k), V (i,j+1,k),
 // W (i,j,k+1), i fastest -- a host copy filled by FluidSimulation::getVelocityField()
 class MACVelocityField {
@@ -248,6 +285,34 @@ public:
         check(flip_add_fluid_sdf(_c, phi.data(), clo, chi, v));
     }
     void addMeshFluidBox(const double lo[3], const double hi[3], const double velocity[3]) { check(flip_add_fluid_box(_c, lo, hi, velocity)); }
+    // addMeshFluidSource / removeMeshFluidSource (:1953-1985)
+    void addMeshFluidSource(MeshFluidSource *source) {
+        if (source->_ctx == _c) throw std::runtime_error("Error: Mesh fluid source has already been added.\n");
+        const vmath::vec3 vv = source->getVelocity();
+        const double v[3] = {vv.x, vv.y, vv.z};
+        int id = 0;
+        if (source->_object.isAxisAlignedBox()) {
+            vmath::vec3 lo, hi;
+            source->_object.bounds(lo, hi);
+            const double l[3] = {lo.x, lo.y, lo.z}, h[3] = {hi.x, hi.y, hi.z};
+            check(flip_add_fluid_source_box(_c, source->isOutflow() ? 1 : 0, l, h, v, &id));
+        } else {
+            std::vector<float> phi;
+            int clo[3], chi[3];
+            source->_object.signedDistanceField(phi, clo, chi);
+            vmath::vec3 lo, hi;
+            source->_object.bounds(lo, hi);
+            const double l[3] = {lo.x, lo.y, lo.z}, h[3] = {hi.x, hi.y, hi.z};
+            check(flip_add_fluid_source_sdf(_c, source->isOutflow() ? 1 : 0, phi.data(), clo, chi, l, h, v, &id));
+        }
+        source->_ctx = _c; source->_id = id;
+        source->push();
+    }
+    void removeMeshFluidSource(MeshFluidSource *source) {
+        if (source->_ctx != _c) throw std::runtime_error("Error: could not find mesh fluid source to remove.\n");
+        check(flip_remove_fluid_source(_c, source->_id));
+        source->_ctx = nullptr;
+    }
     void addMarkerParticle(vmath::vec3 p, vmath::vec3 v = vmath::vec3()) {      // _addMarkerParticle :2637
         const float pp[3] = {p.x, p.y, p.z}, vv[3] = {v.x, v.y, v.z};
         check(flip_add_marker_particle(_c, pp, vv));
@@ -343,6 +408,7 @@ using flipb200::FluidSimulation;
 using flipb200::FluidSimulationMarkerParticleData;
 using flipb200::MACVelocityField;
 using flipb200::MarkerParticle;
+using flipb200::MeshFluidSource;
 using flipb200::MeshObject;
 using flipb200::Triangle;
 using flipb200::TriangleMesh;

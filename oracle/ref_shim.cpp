@@ -49,6 +49,7 @@
 #include "engine/meshlevelset.h"
 #include "engine/macvelocityfield.h"
 #include "engine/particlemesher.h"
+#include "engine/meshfluidsource.h"
 #include "engine/trianglemesh.h"
 #include "engine/threadutils.h"
 #include "engine/stopwatch.h"
@@ -63,6 +64,7 @@ struct RefSim {
     // timing of the stage-wise step, seconds, indexed by stage id
     double stageTime[16] = {0};
     TriangleMesh isomesh;      // ref_isomesh
+    std::vector<MeshFluidSource *> sources;   // kept alive for the simulation (it stores the pointers)
 };
 
 template <class F>
@@ -438,6 +440,42 @@ int ref_add_mesh_fluid_box(void *p, const double lo[3], const double hi[3], cons
         obj.updateMeshStatic(m);
         s->addMeshFluid(obj, vmath::vec3((float)vel[0], (float)vel[1], (float)vel[2]));
     });
+}
+
+/* FluidSimulation::addMeshFluidSource with a static box MeshFluidSource: inflow (setInflow + setVelocity) or outflow
+ * (setOutflow; fluid outflow is on by default).  Returns the index of the source in this shim's list. */
+int ref_add_fluid_source_box(void *p, int outflow, const double lo[3], const double hi[3], const double vel[3]) {
+    RefSim *h = (RefSim *)p;
+    int idx = -1;
+    guarded(h, [&] {
+        FluidSimulation *s = h->sim;
+        vmath::vec3 q((float)lo[0], (float)lo[1], (float)lo[2]);
+        const double w = hi[0] - lo[0], ht = hi[1] - lo[1], d = hi[2] - lo[2];
+        TriangleMesh m;
+        m.vertices = {vmath::vec3(q.x, q.y, q.z), vmath::vec3(q.x + w, q.y, q.z), vmath::vec3(q.x + w, q.y, q.z + d),
+                      vmath::vec3(q.x, q.y, q.z + d), vmath::vec3(q.x, q.y + ht, q.z), vmath::vec3(q.x + w, q.y + ht, q.z),
+                      vmath::vec3(q.x + w, q.y + ht, q.z + d), vmath::vec3(q.x, q.y + ht, q.z + d)};
+        m.triangles = {Triangle(0, 1, 2), Triangle(0, 2, 3), Triangle(4, 7, 6), Triangle(4, 6, 5), Triangle(0, 3, 7), Triangle(0, 7, 4),
+                       Triangle(1, 5, 6), Triangle(1, 6, 2), Triangle(0, 4, 5), Triangle(0, 5, 1), Triangle(3, 2, 6), Triangle(3, 6, 7)};
+        MeshFluidSource *src = new MeshFluidSource(s->_isize, s->_jsize, s->_ksize, s->_dx);
+        src->updateMeshStatic(m);
+        if (outflow) src->setOutflow(); else src->setInflow();
+        src->setVelocity(vmath::vec3((float)vel[0], (float)vel[1], (float)vel[2]));
+        s->addMeshFluidSource(src);
+        h->sources.push_back(src);
+        idx = (int)h->sources.size() - 1;
+    });
+    return idx;
+}
+void ref_constrain_fluid_source_velocity(void *p, int idx, int on) {
+    RefSim *h = (RefSim *)p;
+    if (idx >= 0 && idx < (int)h->sources.size()) {
+        if (on) h->sources[idx]->enableConstrainedFluidVelocity(); else h->sources[idx]->disableConstrainedFluidVelocity();
+    }
+}
+void ref_enable_fluid_source(void *p, int idx, int on) {
+    RefSim *h = (RefSim *)p;
+    if (idx >= 0 && idx < (int)h->sources.size()) { if (on) h->sources[idx]->enable(); else h->sources[idx]->disable(); }
 }
 
 /* The surface FluidSimulation::getIsomesh() would hold for the CURRENT particles: the body of _outputSurfaceMeshThread

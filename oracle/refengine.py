@@ -68,6 +68,9 @@ def _load(kind):
     L.ref_sample_velocity.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.ref_sample_solid_phi.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.ref_add_mesh_fluid_box.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.ref_add_fluid_source_box.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.ref_enable_fluid_source.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.ref_constrain_fluid_source_velocity.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.ref_isomesh.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.ref_get_isomesh.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.ref_mesher_scalar_field.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
@@ -211,6 +214,19 @@ class RefEngine:
         """FluidSimulation::addMeshFluid(MeshObject) with the box mesh FluidManager builds."""
         a, b, v = (C.c_double * 3)(*lo), (C.c_double * 3)(*hi), (C.c_double * 3)(*velocity)
         self._check(self.L.ref_add_mesh_fluid_box(self.h, a, b, v))
+
+    def add_fluid_source_box(self, lo, hi, velocity=(0.0, 0.0, 0.0), outflow=False):
+        """FluidSimulation::addMeshFluidSource with a static box inflow / outflow MeshFluidSource; returns its handle."""
+        a, b, v = (C.c_double * 3)(*lo), (C.c_double * 3)(*hi), (C.c_double * 3)(*velocity)
+        idx = self.L.ref_add_fluid_source_box(self.h, 1 if outflow else 0, a, b, v)
+        assert idx >= 0, self.L.ref_last_error(self.h)
+        return idx
+
+    def constrain_fluid_source_velocity(self, idx, on=True):
+        self.L.ref_constrain_fluid_source_velocity(self.h, int(idx), 1 if on else 0)
+
+    def enable_fluid_source(self, idx, on=True):
+        self.L.ref_enable_fluid_source(self.h, int(idx), 1 if on else 0)
 
     def isomesh(self, subdivisions=1, smooth_iterations=-1):
         """(vertices, triangles) of the surface getIsomesh() would return for the current particles."""
