@@ -241,6 +241,34 @@ __device__ __forceinline__ int warp_append_slot(int *counter) {
     return base + __popc(m & ((1u << lane) - 1u));
 }
 
+// Block-aggregated append: EVERY thread of the block calls it together with the number of items it holds; the return
+// value is the slot of the thread's first item.  One global atomic per block -- appends of a few lanes at a time from
+// a whole grid (warp_append_slot in divergent code) serialise on the counter's address in L2.
+template <int THREADS>
+__device__ __forceinline__ int block_append_slots(int *counter, int mine) {
+    __shared__ int warpTot[THREADS / 32];
+    __shared__ int base;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) warpTot[wid] = incl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+#pragma unroll
+        for (int w = 0; w < THREADS / 32; w++) { const int v = warpTot[w]; warpTot[w] = tot; tot += v; }
+        base = tot ? atomicAdd(counter, tot) : 0;
+    }
+    __syncthreads();
+    const int slot = base + warpTot[wid] + incl - mine;
+    __syncthreads();        // the shared words are free for the next call
+    return slot;
+}
+
 // warp reductions
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
