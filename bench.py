@@ -418,18 +418,22 @@ def ours(args, rank, world, local_rank):
     barrier()
     e2e_psteps, h2d, d2h = 0, 0, 0
     t0 = time.perf_counter()
+    e2e_per_step, e2e_substeps = [], 0
     for _ in range(args.steps):
+        t_it = time.perf_counter()
         n = sim.getNumMarkerParticles()
         sim.setMarkerParticles(host[:n])             # host -> device (pinned)
         h2d += n * 24
         sim.update(FRAME_DT)
         for st in sim.substep_stats():
             e2e_psteps += st["particles"] + st["removed_solid"] + st["removed_crowded"] + st["removed_fast"]
+            e2e_substeps += 1
         n = sim.getNumMarkerParticles()
         if n > host.shape[0]:
             host = torch.empty((n + n // 4, 6), dtype=torch.float32).pin_memory().numpy()
         sim.getMarkerParticles(out=host)             # device -> host (pinned)
         d2h += n * 24
+        e2e_per_step.append(round(1e3 * (time.perf_counter() - t_it), 3))
     sim.synchronize()
     e2e_s = maxreduce(time.perf_counter() - t0)
     e2e_value = e2e_psteps / e2e_s
@@ -503,7 +507,8 @@ def ours(args, rank, world, local_rank):
                            "l2": "inputs larger than L2 (particles and each MAC field exceed the 126 MB L2)"},
                 "roofline": roof, "kernels": kernels, "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_all) // args.steps,
-                        "d2h_bytes_per_step": int(d2h_all) // args.steps, "ms_per_step": 1e3 * e2e_s / args.steps},
+                        "d2h_bytes_per_step": int(d2h_all) // args.steps, "ms_per_step": 1e3 * e2e_s / args.steps,
+                        "per_step_ms_rank0": e2e_per_step, "substeps_timed": e2e_substeps},
                 "exact_mode": exact, "gpu_launches": int(launches_all), "clocks": clocks}
         if parity is not None:
             line["parity_ok"] = bool(parity["ok"])

@@ -1846,50 +1846,58 @@ __device__ __forceinline__ float row_pressure(const float *__restrict__ phi, con
     return is_row(phi, g, c) ? (float)x[c] : 0.0f;
 }
 
+// One CTA row per (j, k) line of faces, threads along i (no index divisions; the row test takes the coordinates).
 template <int DIR>
 __global__ void k_apply_pressure(ApplyParams ap, const float *__restrict__ phi, const double *__restrict__ x,
                                  const float *__restrict__ wgt, float *__restrict__ vel,
                                  unsigned char *__restrict__ valid) {
     const PGrid &g = ap.g;
-    int gi = g.I + (DIR == 0), gj = g.J + (DIR == 1), gk = g.K + (DIR == 2);
-    long long n = (long long)gi * gj * gk;
-    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (t >= n) return;
-    int i = (int)(t % gi), j = (int)((t / gi) % gj), k = (int)(t / ((long long)gi * gj));
-    int a = (DIR == 0) ? i : (DIR == 1 ? j : k + g.kOff);          // global index along DIR
-    int amax = (DIR == 0) ? g.I : (DIR == 1 ? g.J : g.Kg);
+    const int gi = g.I + (DIR == 0), gj = g.J + (DIR == 1);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y, k = blockIdx.z;     // k: local plane
+    if (i >= gi) return;
+    const size_t t = (size_t)i + (size_t)gi * ((size_t)j + (size_t)gj * k);
+    const int a = (DIR == 0) ? i : (DIR == 1 ? j : k + g.kOff);          // global index along DIR
+    const int amax = (DIR == 0) ? g.I : (DIR == 1 ? g.J : g.Kg);
     unsigned char vflag = 0;
     // z-slab: the lowest local face plane has no cell below it in local storage (halo, re-imported later)
     const bool noLowerCell = (DIR == 2) && (k == 0);
     if (noLowerCell && a != 0) { valid[t] = 0; return; }
     if (!(a == 0 || a == amax - 1)) {
         const int stride = (DIR == 0) ? 1 : (DIR == 1 ? g.sj : g.sk);
-        // cell "2" is (i,j,k), cell "1" is one step back along DIR (pi,pj,pk)
-        int c2 = i + g.I * (j + g.J * k);
-        int c1 = c2 - stride;
-        bool in2 = (DIR == 2) ? (k < g.K) : (a < amax);       // the face past the last (local) cell
+        // cell "2" is (i,j,k), cell "1" is one step back along DIR
+        const int c2 = i + g.I * (j + g.J * k);
+        const int c1 = c2 - stride;
+        const bool in2 = (DIR == 2) ? (k < g.K) : (a < amax);       // the face past the last (local) cell
+        // a pressure row of the global system (is_row): liquid cell in [1, N-2]^3
+        const int kg = k + g.kOff;
+        auto interior = [&](int ci, int cj, int ckg) {
+            return ci >= 1 && cj >= 1 && ckg >= 1 && ci < g.I - 1 && cj < g.J - 1 && ckg < g.Kg - 1;
+        };
+        const bool int2 = interior(i, j, kg);
+        const bool int1 = interior(i - (DIR == 0), j - (DIR == 1), kg - (DIR == 2));
         // FluidMaterialGrid::isFaceBorderingMaterial{U,V,W}  fluidmaterialgrid.cpp:126-150
-        bool f1 = phi[c1] < 0.0f;
-        bool f2 = in2 ? (phi[c2] < 0.0f) : false;
-        float w = wgt[t];
+        const float phi1 = __ldg(phi + c1);
+        const float phi2 = in2 ? __ldg(phi + c2) : 0.0f;   // (w>0 never occurs on the outermost face of a walled domain)
+        const bool f1 = phi1 < 0.0f;
+        const bool f2 = in2 ? (phi2 < 0.0f) : false;
+        const float w = wgt[t];
         if (w > 0.0f && (f1 || f2)) {
+            // pressureGrid is 0 except at pressure cells, where it is (float)soln  (:843-847)
             float p1 = 0.0f, p2 = 0.0f;
             if (f1 && f2) {
-                p1 = row_pressure(phi, x, g, c1);
-                p2 = row_pressure(phi, x, g, c2);
+                p1 = int1 ? (float)x[c1] : 0.0f;
+                p2 = int2 ? (float)x[c2] : 0.0f;
             } else {
                 const float eps = 1e-6f;
-                float phi1 = phi[c1];
-                float phi2 = in2 ? phi[c2] : 0.0f;   // (w>0 never occurs on the outermost face of a walled domain)
                 if (f1) {
                     float theta = __fdiv_rn(phi2, fadd(phi1, eps));
                     theta = (float)fmax(-25.0, fmin((double)theta, 25.0));
-                    p1 = row_pressure(phi, x, g, c1);
+                    p1 = int1 ? (float)x[c1] : 0.0f;
                     p2 = fmul(theta, p1);
                 } else {
                     float theta = __fdiv_rn(phi1, fadd(phi2, eps));
                     theta = (float)fmax(-25.0, fmin((double)theta, 25.0));
-                    p2 = row_pressure(phi, x, g, c2);
+                    p2 = int2 ? (float)x[c2] : 0.0f;
                     p1 = fmul(theta, p2);
                 }
             }
@@ -2694,9 +2702,13 @@ void stage_pressure(flip_ctx *c, double dt) {
     ap.g = g;
     ap.factor = (float)(dt / d.dx);
     size_t ktAp = kt_begin(c);
-    k_apply_pressure<0><<<cdiv(d.nU, TPB), TPB, 0, st>>>(ap, c->phiL, c->vx_, c->wU, c->U, c->validU);
-    k_apply_pressure<1><<<cdiv(d.nV, TPB), TPB, 0, st>>>(ap, c->phiL, c->vx_, c->wV, c->V, c->validV);
-    k_apply_pressure<2><<<cdiv(d.nW, TPB), TPB, 0, st>>>(ap, c->phiL, c->vx_, c->wW, c->W, c->validW);
+    {
+        // (one CTA per row of faces where the row fits: I + 1 = 257 faces would leave a second CTA of 256 with one thread)
+        const int aT = std::min(1024, ((d.I + 1 + 31) / 32) * 32);
+        k_apply_pressure<0><<<dim3(cdiv(d.I + 1, aT), d.J, d.K), aT, 0, st>>>(ap, c->phiL, c->vx_, c->wU, c->U, c->validU);
+        k_apply_pressure<1><<<dim3(cdiv(d.I, aT), d.J + 1, d.K), aT, 0, st>>>(ap, c->phiL, c->vx_, c->wV, c->V, c->validV);
+        k_apply_pressure<2><<<dim3(cdiv(d.I, aT), d.J, d.K + 1), aT, 0, st>>>(ap, c->phiL, c->vx_, c->wW, c->W, c->validW);
+    }
     kt_end(c, FLIP_KERNEL_PRESSURE_APPLY, ktAp);
     c->launches += 3;
     FLIP_CUDA_CHECK(cudaGetLastError());

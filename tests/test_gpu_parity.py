@@ -183,6 +183,22 @@ def test_lockstep_isolated_non_dyadic_cell_width(dx):
 
 
 @needs_ref
+@pytest.mark.parametrize("dims", [(12, 20, 14), (19, 13, 37), (45, 18, 23)])
+def test_lockstep_isolated_odd_grids(dims):
+    """Non-cubic grids whose rows are shorter than, or no multiple of, the vector widths of the streaming kernels
+    (the extrapolation start pass settles sixteen faces per thread with byte masks and switches to one face per thread
+    below 17 cells; occupancy bitmaps are padded to whole words; P2G tiles are cut at the domain edge): every stage
+    against the reference from identical inputs."""
+    I, J, K = dims
+    cells = scenes.box_cells(3, max(I // 2, 5), 3, J - 4, 3, K - 3)
+    pos, vel = scenes.seed_cells(cells, scenes.DX, 4242)
+    sc = dict(name="odd%dx%dx%d" % dims, dims=dims, dx=scenes.DX, pos=pos, vel=vel)
+    for sampling in ("exact", "fast"):
+        for rep in pc.lockstep_frames(sc, frames=4, isolate=True, sampling=sampling):
+            pc.check_report(rep, dx=sc["dx"], isolate=True, exact_sampling=(sampling == "exact"))
+
+
+@needs_ref
 @pytest.mark.parametrize("prec", ["jacobi", "multigrid"])
 def test_lockstep_chained(prec):
     """Whole substeps from identical particle state only (grids are NOT re-synchronised between
