@@ -17,12 +17,11 @@ static constexpr int TPB = 256;
 // level grid (1 byte per face): 0 = KNOWN from the start (valid and not on the border),
 // 1..L = filled in layer l, 0xFE = border (the reference's DONE-from-the-start: never written, never
 // a source of propagation, but counted as a DONE neighbour), 0xFF = UNKNOWN.
-// Layer l: every face of the previous frontier (level l-1) claims its UNKNOWN 6-neighbours by
-// setting their level to l (byte-wide atomicCAS, so each face is listed once); each claimed face then
-// takes the mean of its neighbours that were DONE before this layer (level < l, or border) -- faces
-// claimed in the same layer carry level l and are therefore not counted, which is the reference's
-// WAITING state -- summed in the order +i,-i,+j,-j,+k,-k (gridutils.cpp:190-224).  Claiming and filling
-// are separate launches, as in the reference, so the result does not depend on thread order:
+// Layer l: every face of the previous frontier (level l-1) looks at its UNKNOWN 6-neighbours; each such face is taken
+// by exactly one of the frontier faces around it (the first in its own summation order, see k_ext_layer) and set to
+// the mean of its neighbours that were DONE before this layer (level < l, or border) -- faces taken in the same
+// layer carry level l or still 0xFF and are therefore not counted, which is the reference's WAITING state -- summed
+// in the order +i,-i,+j,-j,+k,-k (gridutils.cpp:190-224).  The result does not depend on thread order:
 // bit-reproducible and equal to the reference's.
 // ------------------------------------------------------------------------------------------------
 static constexpr int EXT_MAX_LAYERS = 15;      // counters per component: the start frontier and one per layer
