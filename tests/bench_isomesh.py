@@ -11,7 +11,7 @@ specs = sys.argv[1:] or ["dam64:2", "dam128:2", "spheredrop256:1"]
 for spec in specs:
     name, sub = spec.split(":"); sub = int(sub)
     n = int("".join(ch for ch in name if ch.isdigit()))
-    sc = scenes.dam_break(n) if name.startswith("dam") else scenes.sphere_drop(n)
+    sc = scenes.dam_break(n) if name.startswith("dam") else (scenes.default_scene(n) if name.startswith("default") else scenes.sphere_drop(n))
     I, J, K = sc["dims"]
     sim = fe.FluidSimulation(I, J, K, sc["dx"])
     sim.addBodyForce(0, -25, 0)
