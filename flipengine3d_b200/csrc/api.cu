@@ -1,6 +1,7 @@
 // C-ABI of libflip_b200.so (include/flip_b200.h): context lifetime, configuration, the frame /
 // substep loop of FluidSimulation::update and the stage dispatcher.
 #include <algorithm>
+#include <limits>
 #include <cmath>
 #include <cstring>
 #include <new>
@@ -146,11 +147,21 @@ static void upload_static_inputs(flip_ctx *c) {
     gd.K = d.Kg; gd.kOff = 0;
     gd.nN = (d.I + 1) * (d.J + 1) * (d.Kg + 1);
     gd.nC = d.I * d.J * d.Kg;
+    FLIP_CUDA_CHECK(cudaStreamSynchronize(c->stream));      // (the copies below run on the legacy stream)
     if (!c->userSolidPhi) build_box_solid_sdf(gd, c->hostSolidPhi);
+    // the domain with the enabled obstacles merged in (_addStaticObjectsToSDF, fluidsimulation.cpp:2927-2975)
+    const std::vector<float> *solid = &c->hostSolidPhi;
+    std::vector<float> merged;
+    for (auto &o : c->obstacles) {
+        if (!o.enabled) continue;
+        if (merged.empty()) { merged = c->hostSolidPhi; solid = &merged; }
+        for (size_t q = 0; q < merged.size(); q++) merged[q] = std::min(merged[q], o.sdf[q]);
+    }
+    c->solidDirty = false;
     std::vector<unsigned char> ns;
-    build_near_solid(gd, c->hostSolidPhi, c->nearSolidFactor, c->solidExactBand, c->CFL, ns, c->nsI, c->nsJ, c->nsK);
+    build_near_solid(gd, *solid, c->nearSolidFactor, c->solidExactBand, c->CFL, ns, c->nsI, c->nsJ, c->nsK);
     const size_t nodePlane = (size_t)(d.I + 1) * (d.J + 1);
-    std::vector<float> local(c->hostSolidPhi.begin() + nodePlane * d.kOff, c->hostSolidPhi.begin() + nodePlane * (d.kOff + d.K + 1));
+    std::vector<float> local(solid->begin() + nodePlane * d.kOff, solid->begin() + nodePlane * (d.kOff + d.K + 1));
     std::vector<float> wU, wV, wW, wC;
     build_weights(d, local, wU, wV, wW, wC);
     FLIP_CUDA_CHECK(cudaMemcpy(c->phiS, local.data(), sizeof(float) * d.nN, cudaMemcpyHostToDevice));
@@ -457,6 +468,82 @@ int flip_set_solid_sdf(flip_ctx *c, const float *phi) {
     });
 }
 
+// ---- static obstacles ---------------------------------------------------------------------------
+static void obstacles_changed(flip_ctx *c) {
+    if (c->initialized) c->solidDirty = true;      // picked up by the next substep's obstacle stage (_isSolidLevelSetUpToDate = false)
+    c->stepCounter++;                              // a cached surface mesh was clamped against the old solid
+}
+
+int flip_add_obstacle_sdf(flip_ctx *c, const float *sdf, int *id) {
+    return guarded(c, [&] {
+        if (!sdf) throw ApiError(FLIP_ERR_RUNTIME, "null signed distance field");
+        flip_ctx::Obstacle o;
+        o.id = c->nextObstacleId++;
+        o.sdf.assign(sdf, sdf + (size_t)(c->d.I + 1) * (c->d.J + 1) * (c->d.Kg + 1));
+        if (id) *id = o.id;
+        c->obstacles.push_back(std::move(o));
+        obstacles_changed(c);
+    });
+}
+
+int flip_add_obstacle_box(flip_ctx *c, const double lo[3], const double hi[3], int *id) {
+    return guarded(c, [&] {
+        // the distances MeshLevelSet computes for a box mesh: exact within the band of solidExactBand cells around the
+        // mesh's index box (meshlevelset.cpp:572-601), untouched (here: +inf) elsewhere
+        const int n[3] = {c->d.I + 1, c->d.J + 1, c->d.Kg + 1};
+        const double dx = c->d.dx;
+        flip_ctx::Obstacle o;
+        o.id = c->nextObstacleId++;
+        o.sdf.assign((size_t)n[0] * n[1] * n[2], std::numeric_limits<float>::max());
+        int a0[3], a1[3];
+        for (int a = 0; a < 3; a++) {
+            a0[a] = std::max(0, (int)floor(lo[a] / dx) - c->solidExactBand);
+            a1[a] = std::min(n[a] - 1, (int)ceil(hi[a] / dx) + c->solidExactBand);
+        }
+        const float cx[3] = {(float)(0.5 * (lo[0] + hi[0])), (float)(0.5 * (lo[1] + hi[1])), (float)(0.5 * (lo[2] + hi[2]))};
+        const float hx[3] = {(float)(0.5 * (hi[0] - lo[0])), (float)(0.5 * (hi[1] - lo[1])), (float)(0.5 * (hi[2] - lo[2]))};
+        for (int k = a0[2]; k <= a1[2]; k++)
+            for (int j = a0[1]; j <= a1[1]; j++)
+                for (int i = a0[0]; i <= a1[0]; i++) {
+                    const float p[3] = {(float)(i * dx), (float)(j * dx), (float)(k * dx)};
+                    float q[3], out2 = 0.0f, in = -std::numeric_limits<float>::max();
+                    for (int a = 0; a < 3; a++) {
+                        q[a] = std::fabs(p[a] - cx[a]) - hx[a];
+                        const float e = std::max(q[a], 0.0f);
+                        out2 += e * e;
+                        in = std::max(in, q[a]);
+                    }
+                    o.sdf[(size_t)i + (size_t)n[0] * (j + (size_t)n[1] * k)] = std::sqrt(out2) + std::min(in, 0.0f);
+                }
+        if (id) *id = o.id;
+        c->obstacles.push_back(std::move(o));
+        obstacles_changed(c);
+    });
+}
+
+int flip_enable_obstacle(flip_ctx *c, int id, int on) {
+    return guarded(c, [&] {
+        for (auto &o : c->obstacles)
+            if (o.id == id) {
+                if (o.enabled != (on != 0)) { o.enabled = on != 0; obstacles_changed(c); }
+                return;
+            }
+        throw ApiError(FLIP_ERR_RUNTIME, "Error: could not find mesh obstacle.");
+    });
+}
+
+int flip_remove_obstacle(flip_ctx *c, int id) {
+    return guarded(c, [&] {
+        for (size_t q = 0; q < c->obstacles.size(); q++)
+            if (c->obstacles[q].id == id) {
+                c->obstacles.erase(c->obstacles.begin() + q);
+                obstacles_changed(c);
+                return;
+            }
+        throw ApiError(FLIP_ERR_DOMAIN, "Error: could not find mesh obstacle to remove.");      // std::invalid_argument, :2020-2024
+    });
+}
+
 int flip_initialize(flip_ctx *c) {
     return guarded(c, [&] {
         if (c->initialized) throw ApiError(FLIP_ERR_RUNTIME, "Error: FluidSimulation is already initialized.");
@@ -540,7 +627,7 @@ int flip_begin_substep(flip_ctx *c, double *out) {
 static void run_stage(flip_ctx *c, int stage, double dt) {
     FLIP_CUDA_CHECK(cudaEventRecord(c->evStage[stage], c->stream));
     switch (stage) {
-        case FLIP_STAGE_OBSTACLES: break;                    // static scene
+        case FLIP_STAGE_OBSTACLES: if (c->solidDirty) upload_static_inputs(c); break;     // static solids: only after a change (:2007)
         case FLIP_STAGE_LIQUID_SDF: stage_liquid_sdf(c); break;
         case FLIP_STAGE_P2G: stage_p2g(c); break;
         case FLIP_STAGE_EXTRAPOLATE_A: if (c->np_global > 0 || c->npStore > 0) stage_extrapolate(c); break;   // :3262 guards on !empty()

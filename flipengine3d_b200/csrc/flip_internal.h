@@ -147,7 +147,13 @@ struct flip_ctx {
     std::vector<FluidObject> fluidObjects;
     int nextSourceId = 1;
     int nextParticleId = 0;                   // ids of particles seeded after the load (enableParticleIds)
-    std::vector<float> hostSolidPhi;          // nodal
+    std::vector<float> hostSolidPhi;          // nodal: the domain (built-in box or flip_set_solid_sdf), WITHOUT the obstacles
+    // static obstacles (addMeshObstacle, fluidsimulation.cpp:1994): nodal SDFs merged into the solid SDF by minimum
+    // (MeshLevelSet::calculateUnion, meshlevelset.cpp:1758-1795)
+    struct Obstacle { int id = 0; bool enabled = true; std::vector<float> sdf; };
+    std::vector<Obstacle> obstacles;
+    int nextObstacleId = 1;
+    bool solidDirty = false;                  // obstacles changed after initialize: re-derived at the next substep (:2007)
     bool userSolidPhi = false;
     std::vector<float> hU, hV, hW;            // host mirror handed out by getVelocityField
 

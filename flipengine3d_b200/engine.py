@@ -84,6 +84,10 @@ def load_library():
     L.flip_enable_fluid_source.argtypes = [vp, ci, ci]
     L.flip_remove_fluid_source.argtypes = [vp, ci]
     L.flip_constrain_fluid_source_velocity.argtypes = [vp, ci, ci]
+    L.flip_add_obstacle_box.argtypes = [vp, C.POINTER(cd), C.POINTER(cd), C.POINTER(ci)]
+    L.flip_add_obstacle_sdf.argtypes = [vp, vp, C.POINTER(ci)]
+    L.flip_enable_obstacle.argtypes = [vp, ci, ci]
+    L.flip_remove_obstacle.argtypes = [vp, ci]
     L.flip_set_surface_subdivision_level.argtypes = [vp, ci]
     L.flip_set_surface_smoothing.argtypes = [vp, cd, ci]
     L.flip_get_isomesh_size.argtypes = [vp, C.POINTER(ci), C.POINTER(ci)]
@@ -277,6 +281,27 @@ class FluidSimulation:
 
     def enableMeshFluidSource(self, sid, on=True):
         self._check(self.L.flip_enable_fluid_source(self.h, int(sid), 1 if on else 0))
+
+    def addMeshObstacleBox(self, lo, hi):
+        """FluidSimulation::addMeshObstacle with a static box MeshObject; returns the obstacle's handle."""
+        oid = C.c_int()
+        self._check(self.L.flip_add_obstacle_box(self.h, (C.c_double * 3)(*lo), (C.c_double * 3)(*hi), C.byref(oid)))
+        return oid.value
+
+    def addMeshObstacleSDF(self, nodal_sdf):
+        """... with the nodal signed distance field of the obstacle, shape (K+1, J+1, I+1), negative inside."""
+        a = np.ascontiguousarray(nodal_sdf, dtype=np.float32)
+        I, J, K = self.dims
+        assert a.size == (I + 1) * (J + 1) * (K + 1)
+        oid = C.c_int()
+        self._check(self.L.flip_add_obstacle_sdf(self.h, a.ctypes.data, C.byref(oid)))
+        return oid.value
+
+    def enableMeshObstacle(self, oid, on=True):
+        self._check(self.L.flip_enable_obstacle(self.h, int(oid), 1 if on else 0))
+
+    def removeMeshObstacle(self, oid):
+        self._check(self.L.flip_remove_obstacle(self.h, int(oid)))
 
     def constrainMeshFluidSourceVelocity(self, sid, on=True):
         """MeshFluidSource::enable/disableConstrainedFluidVelocity (on by default)."""

@@ -175,6 +175,19 @@ int flip_remove_fluid_source(flip_ctx *ctx, int id);
  * fluidsimulation.cpp:3372) and the particles inside it carry the source's velocity after the PIC/FLIP update
  * (_constrainMarkerParticleVelocities :4113). */
 int flip_constrain_fluid_source_velocity(flip_ctx *ctx, int id, int on);
+/* Static obstacles: FluidSimulation::addMeshObstacle / removeMeshObstacle (fluidsimulation.cpp:1994-2031) and
+ * MeshObject::enable / disable for meshes that do not move.  The obstacle comes as an axis-aligned box or as the nodal
+ * signed distance field a MeshLevelSet holds for it ((I+1)(J+1)(K+1) floats, negative inside, a large positive value
+ * where the field was not computed); it is merged into the solid SDF by minimum, as MeshLevelSet::calculateUnion does
+ * (meshlevelset.cpp:1758-1795), and the face weights, the near-solid mask and everything that reads the solid SDF
+ * (collision, removal, seeding, the surface clamp) follow.  Before flip_initialize the merge happens there; afterwards at
+ * the start of the next substep (the reference's _isSolidLevelSetUpToDate = false, :2007).  Obstacles have zero velocity
+ * and zero friction (MeshObject defaults); animated / rigid-body obstacles are not supported.
+ * flip_remove_obstacle of an unknown id: FLIP_ERR_DOMAIN (the reference throws std::invalid_argument). */
+int flip_add_obstacle_box(flip_ctx *ctx, const double lo[3], const double hi[3], int *id);
+int flip_add_obstacle_sdf(flip_ctx *ctx, const float *nodal_sdf, int *id);
+int flip_enable_obstacle(flip_ctx *ctx, int id, int on);
+int flip_remove_obstacle(flip_ctx *ctx, int id);
 /* FluidSimulation::_addMarkerParticle  fluidsimulation.cpp:2637 (range-checked push). */
 int flip_add_marker_particle(flip_ctx *ctx, const float position[3], const float velocity[3]);
 

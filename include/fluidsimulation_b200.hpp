@@ -83,6 +83,11 @@ public:
     void getGridDimensions(int *i, int *j, int *k) const { *i = _isize; *j = _jsize; *k = _ksize; }
     void updateMeshStatic(TriangleMesh meshCurrent) { _mesh = std::move(meshCurrent); }
     TriangleMesh getMesh() const { return _mesh; }
+    // MeshObject::enable / disable / isEnabled (meshobject.cpp:267-283): acts on the device once the object is an obstacle
+    void enable() { _enabled = true; if (_ctx) flip_enable_obstacle(_ctx, _obstacleId, 1); }
+    void disable() { _enabled = false; if (_ctx) flip_enable_obstacle(_ctx, _obstacleId, 0); }
+    bool isEnabled() const { return _enabled; }
+    bool isAnimated() const { return false; }       // static meshes only (updateMeshStatic)
 
     void bounds(vmath::vec3 &lo, vmath::vec3 &hi) const {
         lo = vmath::vec3(1e30f, 1e30f, 1e30f); hi = vmath::vec3(-1e30f, -1e30f, -1e30f);
@@ -105,9 +110,9 @@ public:
         return seen == 0xffu;
     }
     // nodal signed distance field of the grid, (I+1)(J+1)(K+1) floats, i fastest; cells [lo,hi) worth scanning
-    void signedDistanceField(std::vector<float> &phi, int lo[3], int hi[3], int band = 3) const {
+    void signedDistanceField(std::vector<float> &phi, int lo[3], int hi[3], int band = 3, float farValue = 0.0f) const {
         const int ni = _isize + 1, nj = _jsize + 1, nk = _ksize + 1;
-        const float far = (float)((band + 1) * _dx);
+        const float far = farValue > 0.0f ? farValue : (float)((band + 1) * _dx);      // nodes outside the band
         phi.assign((size_t)ni * nj * nk, far);
         vmath::vec3 blo, bhi;
         bounds(blo, bhi);
@@ -169,9 +174,13 @@ private:
         const vec3 q = p - (a + (vb * den) * ab + (vc * den) * ac);
         return dot(q, q);
     }
+    friend class FluidSimulation;
     int _isize = 0, _jsize = 0, _ksize = 0;
     double _dx = 0.0;
     TriangleMesh _mesh;
+    bool _enabled = true;
+    flip_ctx *_ctx = nullptr;     // the simulation this object is an obstacle of
+    int _obstacleId = 0;
 };
 
 // MeshFluidSource (meshfluidsource.h:40-117) for static closed meshes: an inflow that emits at the end of every substep
@@ -312,6 +321,29 @@ public:
         if (source->_ctx != _c) throw std::runtime_error("Error: could not find mesh fluid source to remove.\n");
         check(flip_remove_fluid_source(_c, source->_id));
         source->_ctx = nullptr;
+    }
+    // addMeshObstacle / removeMeshObstacle (:1994-2031), static meshes: merged into the solid SDF on the device side
+    void addMeshObstacle(MeshObject *obstacle) {
+        if (obstacle->_ctx == _c) throw std::runtime_error("Error: mesh obstacle has already been added.\n");
+        int id = 0;
+        if (obstacle->isAxisAlignedBox()) {
+            vmath::vec3 lo, hi;
+            obstacle->bounds(lo, hi);
+            const double l[3] = {lo.x, lo.y, lo.z}, h[3] = {hi.x, hi.y, hi.z};
+            check(flip_add_obstacle_box(_c, l, h, &id));
+        } else {
+            std::vector<float> phi;
+            int clo[3], chi[3];
+            obstacle->signedDistanceField(phi, clo, chi, 3, 3.0e38f);       // _solidLevelSetExactBand = 3; untouched elsewhere
+            check(flip_add_obstacle_sdf(_c, phi.data(), &id));
+        }
+        obstacle->_ctx = _c; obstacle->_obstacleId = id;
+        if (!obstacle->isEnabled()) check(flip_enable_obstacle(_c, id, 0));
+    }
+    void removeMeshObstacle(MeshObject *obstacle) {
+        if (obstacle->_ctx != _c) throw std::invalid_argument("Error: could not find mesh obstacle to remove.\n");
+        check(flip_remove_obstacle(_c, obstacle->_obstacleId));
+        obstacle->_ctx = nullptr;
     }
     void addMarkerParticle(vmath::vec3 p, vmath::vec3 v = vmath::vec3()) {      // _addMarkerParticle :2637
         const float pp[3] = {p.x, p.y, p.z}, vv[3] = {v.x, v.y, v.z};

@@ -65,6 +65,7 @@ struct RefSim {
     double stageTime[16] = {0};
     TriangleMesh isomesh;      // ref_isomesh
     std::vector<MeshFluidSource *> sources;   // kept alive for the simulation (it stores the pointers)
+    std::vector<MeshObject *> obstacles;      // likewise (addMeshObstacle keeps the pointer)
 };
 
 template <class F>
@@ -439,6 +440,38 @@ int ref_add_mesh_fluid_box(void *p, const double lo[3], const double hi[3], cons
         MeshObject obj(s->_isize, s->_jsize, s->_ksize, s->_dx);
         obj.updateMeshStatic(m);
         s->addMeshFluid(obj, vmath::vec3((float)vel[0], (float)vel[1], (float)vel[2]));
+    });
+}
+
+/* FluidSimulation::addMeshObstacle (fluidsimulation.cpp:1994-2008) with a static box MeshObject; returns its index in this
+ * shim's list.  ref_remove_obstacle: removeMeshObstacle (:2010-2031). */
+int ref_add_obstacle_box(void *p, const double lo[3], const double hi[3]) {
+    RefSim *h = (RefSim *)p;
+    int idx = -1;
+    guarded(h, [&] {
+        FluidSimulation *s = h->sim;
+        vmath::vec3 q((float)lo[0], (float)lo[1], (float)lo[2]);
+        const double w = hi[0] - lo[0], ht = hi[1] - lo[1], d = hi[2] - lo[2];
+        TriangleMesh m;
+        m.vertices = {vmath::vec3(q.x, q.y, q.z), vmath::vec3(q.x + w, q.y, q.z), vmath::vec3(q.x + w, q.y, q.z + d),
+                      vmath::vec3(q.x, q.y, q.z + d), vmath::vec3(q.x, q.y + ht, q.z), vmath::vec3(q.x + w, q.y + ht, q.z),
+                      vmath::vec3(q.x + w, q.y + ht, q.z + d), vmath::vec3(q.x, q.y + ht, q.z + d)};
+        m.triangles = {Triangle(0, 1, 2), Triangle(0, 2, 3), Triangle(4, 7, 6), Triangle(4, 6, 5), Triangle(0, 3, 7), Triangle(0, 7, 4),
+                       Triangle(1, 5, 6), Triangle(1, 6, 2), Triangle(0, 4, 5), Triangle(0, 5, 1), Triangle(3, 2, 6), Triangle(3, 6, 7)};
+        MeshObject *obj = new MeshObject(s->_isize, s->_jsize, s->_ksize, s->_dx);
+        obj->updateMeshStatic(m);
+        s->addMeshObstacle(obj);
+        h->obstacles.push_back(obj);
+        idx = (int)h->obstacles.size() - 1;
+    });
+    return idx;
+}
+int ref_remove_obstacle(void *p, int idx) {
+    RefSim *h = (RefSim *)p;
+    return guarded(h, [&] {
+        if (idx < 0 || idx >= (int)h->obstacles.size() || !h->obstacles[idx]) throw std::runtime_error("no such obstacle");
+        h->sim->removeMeshObstacle(h->obstacles[idx]);
+        h->obstacles[idx] = nullptr;
     });
 }
 

@@ -70,6 +70,8 @@ def _load(kind):
     L.ref_add_mesh_fluid_box.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.ref_add_fluid_source_box.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.ref_enable_fluid_source.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.ref_add_obstacle_box.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.ref_remove_obstacle.argtypes = [C.c_void_p, C.c_int]
     L.ref_constrain_fluid_source_velocity.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.ref_isomesh.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.ref_get_isomesh.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -221,6 +223,16 @@ class RefEngine:
         idx = self.L.ref_add_fluid_source_box(self.h, 1 if outflow else 0, a, b, v)
         assert idx >= 0, self.L.ref_last_error(self.h)
         return idx
+
+    def add_obstacle_box(self, lo, hi):
+        """FluidSimulation::addMeshObstacle with a static box MeshObject; returns its handle."""
+        a, b = (C.c_double * 3)(*lo), (C.c_double * 3)(*hi)
+        idx = self.L.ref_add_obstacle_box(self.h, a, b)
+        assert idx >= 0, self.L.ref_last_error(self.h)
+        return idx
+
+    def remove_obstacle(self, idx):
+        self._check(self.L.ref_remove_obstacle(self.h, int(idx)))
 
     def constrain_fluid_source_velocity(self, idx, on=True):
         self.L.ref_constrain_fluid_source_velocity(self.h, int(idx), 1 if on else 0)

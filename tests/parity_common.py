@@ -46,10 +46,15 @@ def aliased_slots(n):
     return hi, hi - FRAGMENT_ELEMENTS
 
 
-def make_pair(scene, tol=None, threads=None, gravity=(0.0, -25.0, 0.0), preconditioner=None, sampling=None):
+def make_pair(scene, tol=None, threads=None, gravity=(0.0, -25.0, 0.0), preconditioner=None, sampling=None, obstacles=(),
+              own_solid=False):
     """Returns (ref, gpu) engines initialised from the same scene; the GPU engine gets the oracle's
-    own static solid SDF and the oracle's LOGICAL particle list."""
+    own static solid SDF and the oracle's LOGICAL particle list.  obstacles: (lo, hi) boxes added to
+    the reference with addMeshObstacle (their distances arrive with the oracle's solid SDF); own_solid: the GPU engine builds
+    its solid SDF itself instead (its domain box, and the obstacles through flip_add_obstacle_box)."""
     ref = refengine.RefEngine(scene["dims"], scene["dx"], scene["pos"], scene["vel"], gravity=gravity, threads=threads, tol=tol)
+    for lo, hi in obstacles:
+        ref.add_obstacle_box(lo, hi)
     ref.stage("obstacles", 1.0 / 30.0)   # builds the solid SDF / near-solid grid exactly as the first step would
     I, J, K = scene["dims"]
     gpu = fe.FluidSimulation(I, J, K, scene["dx"])
@@ -61,7 +66,11 @@ def make_pair(scene, tol=None, threads=None, gravity=(0.0, -25.0, 0.0), precondi
     if sampling is not None:
         gpu.setSamplingMode(sampling)
     gpu.enableParticleIds(True)
-    gpu.setSolidSDF(ref.array("solid_phi"))
+    if own_solid:
+        for lo, hi in obstacles:
+            gpu.addMeshObstacleBox(lo, hi)
+    else:
+        gpu.setSolidSDF(ref.array("solid_phi"))
     gpu.initialize()
     gpu.setMarkerParticles(ref.particles())
     return ref, gpu
@@ -237,9 +246,10 @@ def developed_scene(scene, frames, preconditioner=None):
 
 
 def lockstep_frames(scene, frames=1, isolate=True, tol=None, threads=None, preconditioner=None, verbose=False,
-                    sampling=None, max_substeps=None):
+                    sampling=None, max_substeps=None, obstacles=(), own_solid=False):
     """max_substeps: stop after that many lock-step substeps in total (the large scenes cost tens of CPU seconds each)."""
-    ref, gpu = make_pair(scene, tol=tol, threads=threads, preconditioner=preconditioner, sampling=sampling)
+    ref, gpu = make_pair(scene, tol=tol, threads=threads, preconditioner=preconditioner, sampling=sampling, obstacles=obstacles,
+                         own_solid=own_solid)
     reports = []
     for f in range(frames):
         ref.begin_frame(1.0 / 30.0)

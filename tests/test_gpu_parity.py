@@ -264,6 +264,30 @@ def test_fluidmanager_scene_headless_through_the_cpp_facade():
     assert mm and int(mm.group(1)) > 1000 and int(mm.group(2)) > 2000, r.stdout[-500:]
 
 
+def test_obstacles_and_sources_through_the_cpp_facade():
+    """examples/obstacles_and_sources.cpp: a wedge (general closed mesh -> host signed distance field) and a box as
+    static obstacles, an inflow and an outflow MeshFluidSource, MeshObject::disable and removeMeshObstacle at run time,
+    all through include/fluidsimulation_b200.hpp.  The inflow keeps emitting, nothing ends up deep inside an enabled
+    obstacle, the outflow keeps the count bounded."""
+    import re
+    import subprocess
+    exe = os.path.join(ROOT, "build", "obstacles_and_sources")
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "flipengine3d_b200", "csrc")], check=True, stdout=subprocess.DEVNULL)
+    r = subprocess.run([exe, "40", "40"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-2000:])
+    rows = re.findall(r"frame\s+(\d+)\s+particles (\d+)\s+inside ramp (\d+)\s+inside block (\d+)", r.stdout)
+    assert len(rows) >= 4, r.stdout[-2000:]
+    counts = [int(x[1]) for x in rows]
+    assert counts[0] > 1000 and counts[1] > counts[0]                       # the inflow keeps pouring
+    for f, n, in_ramp, in_block in rows:
+        assert int(in_ramp) == 0, rows                                       # the wedge holds all the way
+        if int(f) < 20:
+            assert int(in_block) == 0, rows                                  # the block, while it is enabled
+    m = re.search(r"done: 40 frames, peak (\d+) particles, final (\d+)", r.stdout)
+    assert m and int(m.group(2)) > 0, r.stdout[-500:]
+
+
 def test_update_before_initialize_raises_runtime_error():
     sim = fe.FluidSimulation(8, 8, 8, 0.125)
     with pytest.raises(RuntimeError):
@@ -574,6 +598,85 @@ def test_inflow_and_outflow_sources_match_the_reference(constrained, low):
     before = gpu.getNumMarkerParticles()
     gpu.update(1.0 / 30.0)
     assert gpu.getNumMarkerParticles() <= before
+
+
+_OBSTACLES = [((12.3 * 0.125, 0.0, 6.2 * 0.125), (16.7 * 0.125, 9.4 * 0.125, 25.9 * 0.125)),        # a wall across the flow
+              ((20.2 * 0.125, 5.5 * 0.125, 12.1 * 0.125), (24.9 * 0.125, 11.6 * 0.125, 19.8 * 0.125))]    # a block above the floor
+
+
+@needs_ref
+@pytest.mark.parametrize("sampling", ["exact", "fast"])
+def test_lockstep_with_static_obstacles(sampling):
+    """SURVEY §8f rank 4, static half: mesh obstacles inside the domain (addMeshObstacle, fluidsimulation.cpp:1994).  The
+    dam break runs into a wall and a block; every stage against the reference from identical inputs (the obstacles'
+    distances arrive with the oracle's solid SDF: weights, near-solid mask, collision, removal are derived from it here)."""
+    sc = scenes.dam_break(32)
+    for rep in pc.lockstep_frames(sc, frames=8, isolate=True, sampling=sampling, obstacles=_OBSTACLES):
+        pc.check_report(rep, dx=sc["dx"], isolate=True, exact_sampling=(sampling == "exact"))
+
+
+@needs_ref
+def test_static_obstacles_through_the_obstacle_api():
+    """The same scene with the obstacles added through flip_add_obstacle_box (the façade's addMeshObstacle for a box mesh):
+    the merged solid SDF has the reference's sign at every node and its value wherever the reference computed one (the
+    band of three cells around the obstacle, meshlevelset.cpp:572-601), the face weights are the reference's, and the
+    free-running simulations stay together (same substeps, particle counts and pressure rows; positions to 1e-4 rel-L2
+    over the first frames).  Removing an obstacle after initialize restores the plain domain at the next substep."""
+    sc = scenes.dam_break(32)
+    dx = sc["dx"]
+    ref, gpu = pc.make_pair(sc, obstacles=_OBSTACLES, own_solid=True)
+    R, G = ref.array("solid_phi"), gpu.array("solid_phi")
+    assert np.array_equal(R < 0, G < 0), int(np.count_nonzero((R < 0) != (G < 0)))
+    plain = pc.refengine.RefEngine(sc["dims"], dx, sc["pos"][:1], sc["vel"][:1])
+    plain.stage("obstacles", 1.0 / 30.0)
+    B = plain.array("solid_phi")
+    touched = R != B                                     # where the reference computed an obstacle distance
+    assert touched.sum() > 1000
+    # (where the obstacle's band meets nodes more than three cells from the domain walls the reference's domain value is an
+    # upper bound, the built-in box SDF the true distance: the minimum can then pick different sources -- far from any surface)
+    own = touched & (G == np.minimum(G, R))
+    assert np.abs(R[own] - G[own]).max() <= 0.5 * dx
+    near = np.abs(R) < 2.5 * dx                          # everything the step reads quantitatively lies here
+    worst = np.unravel_index(np.argmax(np.abs(R - G) * near), R.shape)
+    assert np.abs(R[near] - G[near]).max() <= 2e-4 * dx, (worst, R[worst], G[worst], B[worst])
+    ref.update_weight_grid()
+    for name in ("weightU", "weightV", "weightW"):
+        assert np.abs(ref.array(name) - gpu.array(name)).max() <= 1e-4, name
+    assert np.array_equal(ref.array("near_solid").ravel(), gpu.array("near_solid").ravel())
+    ids0 = None
+    for f in range(6):
+        ref.update(1.0 / 30.0)
+        gpu.update(1.0 / 30.0)
+        st = gpu.substep_stats()
+        assert ref.substeps == len(st) and ref.num_particles == st[-1]["particles"], (f, ref.substeps, len(st), ref.num_particles, st[-1]["particles"])
+        assert abs(ref.num_fluid_cells - st[-1]["pressure_rows"]) <= 2, (f, ref.num_fluid_cells, st[-1]["pressure_rows"])
+        if f < 4:
+            p, ids = pc.particles_by_id(gpu)
+            a = ref.particles()
+            assert pc.rel_l2(p[np.argsort(ids), :3], a[:, :3]) <= 1e-4, (f, pc.rel_l2(p[np.argsort(ids), :3], a[:, :3]))
+    P, Q = gpu.getMarkerParticles(), ref.particles()
+    for lo, hi in _OBSTACLES:
+        # nothing deep inside an obstacle (the collision rule of the reference, _resolveCollision :4214-4262, leaves a
+        # particle that ends a step just under a surface where it is: as many of those here as there)
+        def inside(A, margin):
+            return np.all((A[:, :3] > np.array(lo) + margin * dx) & (A[:, :3] < np.array(hi) - margin * dx), axis=1)
+        assert not inside(P, 0.5).any(), int(inside(P, 0.5).sum())
+        assert abs(int(inside(P, 0.05).sum()) - int(inside(Q, 0.05).sum())) <= 4, (int(inside(P, 0.05).sum()), int(inside(Q, 0.05).sum()))
+    # removal after initialize: picked up by the next substep
+    gpu2 = fe.FluidSimulation(32, 32, 32, dx)
+    gpu2.addBodyForce(0, -25, 0)
+    oid = gpu2.addMeshObstacleBox(*_OBSTACLES[0])
+    gpu2.loadMarkerParticleData(fe.MarkerParticleData(sc["pos"], sc["vel"]))
+    gpu2.initialize()
+    with_obstacle = gpu2.array("solid_phi").copy()
+    gpu2.removeMeshObstacle(oid)
+    gpu2.update(1.0 / 30.0)
+    without = gpu2.array("solid_phi")
+    assert (with_obstacle < without).sum() > 1000
+    band = np.abs(B) < 3 * dx
+    assert np.array_equal(without < 0, B < 0) and np.abs(without[band] - B[band]).max() <= 2e-4 * dx
+    with pytest.raises(Exception):
+        gpu2.removeMeshObstacle(oid)
 
 
 def _mesh_edges_manifold(t):
