@@ -228,6 +228,19 @@ void flip_destroy(flip_ctx *c) {
 
 const char *flip_last_error(const flip_ctx *c) { return c ? c->lastError.c_str() : "null context"; }
 
+int flip_reset_body_force(flip_ctx *c) {       // resetBodyForce  fluidsimulation.cpp:1598
+    return guarded(c, [&] { c->gravity[0] = c->gravity[1] = c->gravity[2] = 0.0; });
+}
+int flip_set_extreme_velocity_removal(flip_ctx *c, int on) {      // enable / disableExtremeVelocityRemoval  :1869-1881
+    return guarded(c, [&] { c->extremeVelocityRemoval = on != 0; });
+}
+int flip_set_marker_particle_scale(flip_ctx *c, double s) {       // setMarkerParticleScale  :168-179
+    return guarded(c, [&] {
+        if (s < 0.0) throw ApiError(FLIP_ERR_DOMAIN, "Error: marker particle scale must be greater than or equal to 0.");
+        if (s != c->markerParticleScale) c->stepCounter++;          // a cached mesh no longer applies
+        c->markerParticleScale = s;
+    });
+}
 int flip_add_body_force(flip_ctx *c, double fx, double fy, double fz) {
     // _constantBodyForces is summed by _getConstantBodyForce (fluidsimulation.cpp:3436-3444), in vec3 floats
     return guarded(c, [&] {

@@ -118,6 +118,8 @@ struct flip_ctx {
     double solidBufferWidth = 0.1f;          // float in the reference (fluidsimulation.h:1685)
     double maxExtremeVelocityRemovalPercent = 0.0005;
     int maxExtremeVelocityRemovalAbsolute = 35;
+    bool extremeVelocityRemoval = true;      // _isExtremeVelocityRemovalEnabled (fluidsimulation.h; :4345)
+    double markerParticleScale = 3.0;        // _markerParticleScale: the mesher's particle radius factor (:5083)
     float markerParticleStepDistanceFactor = 0.5f;
     int nearSolidFactor = 3;
     int solidExactBand = 3;

@@ -340,7 +340,7 @@ static void mesher_build(flip_ctx *c, float *hostValues = nullptr, unsigned char
     P.invBlockdx = 1.0 / (double)(float)(10 * P.subdx);
     // _initializeParticleRadii (:2644-2648) and params.radius = _markerParticleRadius * _markerParticleScale (:5083)
     const double volume = d.dx * d.dx * d.dx / 8.0, pi = 3.141592653;
-    const double radius = pow(3 * volume / (4 * pi), 1.0 / 3.0) * 3.0;
+    const double radius = pow(3 * volume / (4 * pi), 1.0 / 3.0) * c->markerParticleScale;     // default scale 3.0
     P.r = (float)radius; P.sr = 1.5f * P.r; P.maxd = (float)(3.0 * (double)P.r);
     P.oI = (d.I + 3) >> 2; P.oJ = (d.J + 3) >> 2; P.oK = (d.K + 3) >> 2;
     const long long nNodes = (long long)P.ni * P.nj * P.nk, nCells = (long long)(P.ni - 1) * (P.nj - 1) * (P.nk - 1);

@@ -160,7 +160,7 @@ __global__ void k_speed_hist(ParticleSoA p, SortParams sp, double speedLimitStep
 }
 
 // _getMarkerParticleSpeedLimit, second loop (:4307-4320)
-__global__ void k_speed_limit(int n, double speedLimitStep, int nbins, double maxpct, int maxabs, DeviceScalars *S) {
+__global__ void k_speed_limit(int n, double speedLimitStep, int nbins, double maxpct, int maxabs, int enabled, DeviceScalars *S) {
     int maxRemovalCount = (int)fmin((double)(int)((double)n * maxpct), (double)maxabs);
     double maxspeed = nbins * speedLimitStep;
     int cur = 0;
@@ -169,7 +169,8 @@ __global__ void k_speed_limit(int n, double speedLimitStep, int nbins, double ma
         cur += S->speedHist[i];
         maxspeed = i * speedLimitStep;
     }
-    S->maxSpeedLimit = (float)maxspeed;
+    // disabled (disableExtremeVelocityRemoval): no speed exceeds the limit (its square is +inf in k_classify)
+    S->maxSpeedLimit = enabled ? (float)maxspeed : 3.0e38f;
     for (int i = 0; i < 8; i++) S->speedHist[i] = 0;
 }
 
@@ -410,7 +411,7 @@ void particles_sort(flip_ctx *c, bool applyRules, double frameDt, int srcOffset,
             nGlobal = c->np_global;
         }
         k_speed_limit<<<1, 1, 0, st>>>(nGlobal, speedLimitStep, c->maxSubsteps, c->maxExtremeVelocityRemovalPercent,
-                                       c->maxExtremeVelocityRemovalAbsolute, c->dS); c->launches++;
+                                       c->maxExtremeVelocityRemovalAbsolute, c->extremeVelocityRemoval ? 1 : 0, c->dS); c->launches++;
     }
     if (n > 0) {
         // the arrival ranks live in srcIdx, which is only rebuilt (k_build_src) after the index scatter has used them

@@ -84,6 +84,9 @@ def load_library():
     L.flip_enable_fluid_source.argtypes = [vp, ci, ci]
     L.flip_remove_fluid_source.argtypes = [vp, ci]
     L.flip_constrain_fluid_source_velocity.argtypes = [vp, ci, ci]
+    L.flip_reset_body_force.argtypes = [vp]
+    L.flip_set_extreme_velocity_removal.argtypes = [vp, ci]
+    L.flip_set_marker_particle_scale.argtypes = [vp, cd]
     L.flip_add_obstacle_box.argtypes = [vp, C.POINTER(cd), C.POINTER(cd), C.POINTER(ci)]
     L.flip_add_obstacle_sdf.argtypes = [vp, vp, C.POINTER(ci)]
     L.flip_enable_obstacle.argtypes = [vp, ci, ci]
@@ -281,6 +284,15 @@ class FluidSimulation:
 
     def enableMeshFluidSource(self, sid, on=True):
         self._check(self.L.flip_enable_fluid_source(self.h, int(sid), 1 if on else 0))
+
+    def resetBodyForce(self):
+        self._check(self.L.flip_reset_body_force(self.h))
+
+    def enableExtremeVelocityRemoval(self, on=True):
+        self._check(self.L.flip_set_extreme_velocity_removal(self.h, 1 if on else 0))
+
+    def setMarkerParticleScale(self, s):
+        self._check(self.L.flip_set_marker_particle_scale(self.h, float(s)))
 
     def addMeshObstacleBox(self, lo, hi):
         """FluidSimulation::addMeshObstacle with a static box MeshObject; returns the obstacle's handle."""

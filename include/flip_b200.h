@@ -95,6 +95,12 @@ const char *flip_create_error(void);
 
 /* FluidSimulation::addBodyForce(double,double,double)  fluidsimulation.cpp:1563 */
 int flip_add_body_force(flip_ctx *ctx, double fx, double fy, double fz);
+/* resetBodyForce :1598; enableExtremeVelocityRemoval / disableExtremeVelocityRemoval :1869-1881 (the speed rule of
+ * _removeMarkerParticles :4345, on by default); setMarkerParticleScale :168-179 (the particle radius factor of the
+ * surface reconstruction, 3.0 by default, :5083). */
+int flip_reset_body_force(flip_ctx *ctx);
+int flip_set_extreme_velocity_removal(flip_ctx *ctx, int on);
+int flip_set_marker_particle_scale(flip_ctx *ctx, double scale);
 /* FluidSimulation::setPICFLIPRatio :1440, setCFLConditionNumber :1100,
  * setMin/MaxTimeStepsPerFrame :1086-1098, pressure-solver members fluidsimulation.h:1657-1659 */
 int flip_set_pic_flip_ratio(flip_ctx *ctx, double ratio);

@@ -352,9 +352,44 @@ public:
     void loadMarkerParticleData(FluidSimulationMarkerParticleData d) {
         check(flip_load_particles(_c, d.size, reinterpret_cast<const float *>(d.positions), reinterpret_cast<const float *>(d.velocities)));
     }
-    void setPICFLIPRatio(double r) { check(flip_set_pic_flip_ratio(_c, r)); }
-    void setCFLConditionNumber(double n) { check(flip_set_cfl(_c, n)); }
-    void initialize() { check(flip_initialize(_c)); }
+    void setPICFLIPRatio(double r) { check(flip_set_pic_flip_ratio(_c, r)); _picflip = r; }
+    double getPICFLIPRatio() const { return _picflip; }
+    void setCFLConditionNumber(double n) { check(flip_set_cfl(_c, n)); _cfl = n; }
+    double getCFLConditionNumber() const { return _cfl; }
+    // setMin / MaxTimeStepsPerFrame (:1801-1831)
+    void setMinTimeStepsPerFrame(int n) {
+        if (n < 1) throw std::domain_error("Error: min step count must be greater than or equal to 1.\n");
+        check(flip_set_substep_limits(_c, n, _maxSteps)); _minSteps = n;
+    }
+    void setMaxTimeStepsPerFrame(int n) {
+        if (n < 1) throw std::domain_error("Error: max step count must be greater than or equal to 1.\n");
+        check(flip_set_substep_limits(_c, _minSteps, n)); _maxSteps = n;
+    }
+    int getMinTimeStepsPerFrame() const { return _minSteps; }
+    int getMaxTimeStepsPerFrame() const { return _maxSteps; }
+    void resetBodyForce() { check(flip_reset_body_force(_c)); }
+    void enableExtremeVelocityRemoval() { check(flip_set_extreme_velocity_removal(_c, 1)); _extreme = true; }
+    void disableExtremeVelocityRemoval() { check(flip_set_extreme_velocity_removal(_c, 0)); _extreme = false; }
+    bool isExtremeVelocityRemovalEnabled() const { return _extreme; }
+    void setMarkerParticleScale(double s) { check(flip_set_marker_particle_scale(_c, s)); _particleScale = s; }
+    double getMarkerParticleScale() const { return _particleScale; }
+    // setSurfaceSmoothingValue / Iterations (fluidsimulation.h:1607-1608 defaults: 0.5, 2)
+    void setSurfaceSmoothingValue(double v) { _smoothValue = v; check(flip_set_surface_smoothing(_c, _smoothValue, _smoothIterations)); }
+    void setSurfaceSmoothingIterations(int n) { _smoothIterations = n; check(flip_set_surface_smoothing(_c, _smoothValue, _smoothIterations)); }
+    double getSurfaceSmoothingValue() const { return _smoothValue; }
+    int getSurfaceSmoothingIterations() const { return _smoothIterations; }
+    // thread-count knobs of the host engine: accepted, without effect on the device path
+    void setMaxThreadCount(int) {}
+    int getGridWidth() const { return _isize; }
+    int getGridHeight() const { return _jsize; }
+    int getGridDepth() const { return _ksize; }
+    double getSimulationWidth() const { return _isize * _dx; }
+    double getSimulationHeight() const { return _jsize * _dx; }
+    double getSimulationDepth() const { return _ksize * _dx; }
+    void getVersion(int *major, int *minor, int *revision) const { *major = 1; *minor = 0; *revision = 9; }     // the restated engine
+    bool isInitialized() const { return _initialized; }
+    bool isCurrentFrameFinished() const { return true; }        // update() returns when the frame is done
+    void initialize() { check(flip_initialize(_c)); _initialized = true; }
     void update(double dt) { check(flip_update(_c, dt)); }
     int getCurrentFrame() { int f = 0; check(flip_get_current_frame(_c, &f)); return f; }
     void setCurrentFrame(int f) { check(flip_set_current_frame(_c, f)); }
@@ -427,6 +462,9 @@ private:
     int _isize, _jsize, _ksize;
     double _dx;
     int _subdivisionLevel = 1;
+    double _picflip = 0.05, _cfl = 5.0, _particleScale = 3.0, _smoothValue = 0.5;      // the engine's defaults (fluidsimulation.h)
+    int _minSteps = 1, _maxSteps = 6, _smoothIterations = 2;
+    bool _extreme = true, _initialized = false;
     MACVelocityField _mac;
     TriangleMesh _isomesh;
 };

@@ -443,6 +443,16 @@ int ref_add_mesh_fluid_box(void *p, const double lo[3], const double hi[3], cons
     });
 }
 
+/* enable / disableExtremeVelocityRemoval (:1869-1881), setMarkerParticleScale (:168-179) */
+void ref_set_extreme_velocity_removal(void *p, int on) {
+    FluidSimulation *s = ((RefSim *)p)->sim;
+    if (on) s->enableExtremeVelocityRemoval(); else s->disableExtremeVelocityRemoval();
+}
+int ref_set_marker_particle_scale(void *p, double scale) {
+    RefSim *h = (RefSim *)p;
+    return guarded(h, [&] { h->sim->setMarkerParticleScale(scale); });
+}
+
 /* FluidSimulation::addMeshObstacle (fluidsimulation.cpp:1994-2008) with a static box MeshObject; returns its index in this
  * shim's list.  ref_remove_obstacle: removeMeshObstacle (:2010-2031). */
 int ref_add_obstacle_box(void *p, const double lo[3], const double hi[3]) {

@@ -70,6 +70,8 @@ def _load(kind):
     L.ref_add_mesh_fluid_box.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.ref_add_fluid_source_box.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.ref_enable_fluid_source.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.ref_set_extreme_velocity_removal.argtypes = [C.c_void_p, C.c_int]
+    L.ref_set_marker_particle_scale.argtypes = [C.c_void_p, C.c_double]
     L.ref_add_obstacle_box.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.ref_remove_obstacle.argtypes = [C.c_void_p, C.c_int]
     L.ref_constrain_fluid_source_velocity.argtypes = [C.c_void_p, C.c_int, C.c_int]
@@ -223,6 +225,12 @@ class RefEngine:
         idx = self.L.ref_add_fluid_source_box(self.h, 1 if outflow else 0, a, b, v)
         assert idx >= 0, self.L.ref_last_error(self.h)
         return idx
+
+    def set_extreme_velocity_removal(self, on=True):
+        self.L.ref_set_extreme_velocity_removal(self.h, 1 if on else 0)
+
+    def set_marker_particle_scale(self, scale):
+        self._check(self.L.ref_set_marker_particle_scale(self.h, float(scale)))
 
     def add_obstacle_box(self, lo, hi):
         """FluidSimulation::addMeshObstacle with a static box MeshObject; returns its handle."""

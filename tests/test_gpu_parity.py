@@ -679,6 +679,49 @@ def test_static_obstacles_through_the_obstacle_api():
         gpu2.removeMeshObstacle(oid)
 
 
+@needs_ref
+@pytest.mark.parametrize("enabled", [True, False])
+def test_extreme_velocity_removal_switch(enabled):
+    """enable / disableExtremeVelocityRemoval (fluidsimulation.cpp:1869-1881): a handful of particles far faster than the
+    rest are removed by the speed rule of _removeMarkerParticles (:4345) when it is on and kept when it is off -- the same
+    count as the reference either way."""
+    sc = scenes.dam_break(32)
+    vel = sc["vel"].copy()
+    vel[::3000] = (60.0, 40.0, -50.0)                      # 9 particles; the limit of the first frame is CFL dx / dt = 18.75 per bin
+    sc = dict(sc, vel=vel)
+    ref, gpu = pc.make_pair(sc)
+    ref.set_extreme_velocity_removal(enabled)
+    gpu.enableExtremeVelocityRemoval(enabled)
+    n0 = ref.num_particles
+    for _ in range(2):
+        ref.update(1.0 / 30.0)
+        gpu.update(1.0 / 30.0)
+        assert ref.num_particles == gpu.getNumMarkerParticles(), (enabled, ref.num_particles, gpu.getNumMarkerParticles())
+    assert (ref.num_particles < n0) == enabled, (enabled, n0, ref.num_particles)
+
+
+@needs_ref
+def test_surface_particle_scale_follows_the_reference():
+    """setMarkerParticleScale (:168-179): the radius factor of the mesher's scalar field (:5083); the reconstructed surface
+    keeps the reference's vertex count and vertices at another scale than the default 3.0."""
+    sc = scenes.dam_break(32)
+    ref, gpu = pc.make_pair(sc)
+    for _ in range(2):
+        ref.update(1.0 / 30.0)
+    gpu.setMarkerParticles(ref.particles())
+    for scale in (2.4, 3.0):
+        ref.set_marker_particle_scale(scale)
+        gpu.setMarkerParticleScale(scale)
+        gpu.setSurfaceSubdivisionLevel(2)
+        gpu.setSurfaceSmoothing(0.5, 0)
+        v, t = gpu.getIsomesh()
+        rv, rt = ref.isomesh(2, 0)
+        assert v.shape[0] == rv.shape[0] > 1000, (scale, v.shape, rv.shape)
+        from scipy.spatial import cKDTree
+        dist, _ = cKDTree(rv.astype(np.float64)).query(v.astype(np.float64))
+        assert dist.max() <= 1e-5 * sc["dx"], (scale, dist.max())
+
+
 def _mesh_edges_manifold(t):
     e = np.concatenate([t[:, [0, 1]], t[:, [1, 2]], t[:, [2, 0]]], axis=0)
     key = np.sort(e, axis=1)
