@@ -15,6 +15,7 @@
 #pragma once
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -315,12 +316,18 @@ public:
             check(flip_add_fluid_source_sdf(_c, source->isOutflow() ? 1 : 0, phi.data(), clo, chi, l, h, v, &id));
         }
         source->_ctx = _c; source->_id = id;
+        _sources.push_back(source);
         source->push();
     }
     void removeMeshFluidSource(MeshFluidSource *source) {
         if (source->_ctx != _c) throw std::runtime_error("Error: could not find mesh fluid source to remove.\n");
         check(flip_remove_fluid_source(_c, source->_id));
         source->_ctx = nullptr;
+        for (size_t q = 0; q < _sources.size(); q++)
+            if (_sources[q] == source) { _sources.erase(_sources.begin() + q); break; }
+    }
+    void removeMeshFluidSources() {                                // :1987-1992
+        while (!_sources.empty()) removeMeshFluidSource(_sources.back());
     }
     // addMeshObstacle / removeMeshObstacle (:1994-2031), static meshes: merged into the solid SDF on the device side
     void addMeshObstacle(MeshObject *obstacle) {
@@ -338,12 +345,18 @@ public:
             check(flip_add_obstacle_sdf(_c, phi.data(), &id));
         }
         obstacle->_ctx = _c; obstacle->_obstacleId = id;
+        _obstacles.push_back(obstacle);
         if (!obstacle->isEnabled()) check(flip_enable_obstacle(_c, id, 0));
     }
     void removeMeshObstacle(MeshObject *obstacle) {
         if (obstacle->_ctx != _c) throw std::invalid_argument("Error: could not find mesh obstacle to remove.\n");
         check(flip_remove_obstacle(_c, obstacle->_obstacleId));
         obstacle->_ctx = nullptr;
+        for (size_t q = 0; q < _obstacles.size(); q++)
+            if (_obstacles[q] == obstacle) { _obstacles.erase(_obstacles.begin() + q); break; }
+    }
+    void removeMeshObstacles() {                                   // :2032-2036
+        while (!_obstacles.empty()) removeMeshObstacle(_obstacles.back());
     }
     void addMarkerParticle(vmath::vec3 p, vmath::vec3 v = vmath::vec3()) {      // _addMarkerParticle :2637
         const float pp[3] = {p.x, p.y, p.z}, vv[3] = {v.x, v.y, v.z};
@@ -403,6 +416,10 @@ public:
     unsigned int getMarkerParticlePositionDataSize() { return getNumMarkerParticles() * 3u * (unsigned int)sizeof(float); }
     void getMarkerParticlePositionData(char *data) { check(flip_get_particle_positions(_c, reinterpret_cast<float *>(data), (int)getNumMarkerParticles())); }
     void getMarkerParticleVelocityData(char *data) { check(flip_get_particle_velocities(_c, reinterpret_cast<float *>(data), (int)getNumMarkerParticles())); }
+    unsigned int getMarkerParticleVelocityDataSize() { return getMarkerParticlePositionDataSize(); }
+    // ...DataRange (:2314-2338): particles [start, end) of the current order
+    void getMarkerParticlePositionDataRange(int start_idx, int end_idx, char *data) { dataRange(start_idx, end_idx, data, true); }
+    void getMarkerParticleVelocityDataRange(int start_idx, int end_idx, char *data) { dataRange(start_idx, end_idx, data, false); }
     // getVelocityField (:2045-2047): the MAC field as it stands after the last step
     MACVelocityField *getVelocityField() {
         _mac._isize = _isize; _mac._jsize = _jsize; _mac._ksize = _ksize; _mac._dx = _dx;
@@ -451,6 +468,13 @@ public:
     flip_ctx *handle() { return _c; }
 
 private:
+    void dataRange(int start_idx, int end_idx, char *data, bool positions) {
+        const int n = (int)getNumMarkerParticles();
+        if (start_idx < 0 || end_idx > n || start_idx > end_idx) throw std::domain_error("Error: invalid range.\n");
+        std::vector<float> all((size_t)3 * n);
+        if (n > 0) check(positions ? flip_get_particle_positions(_c, all.data(), n) : flip_get_particle_velocities(_c, all.data(), n));
+        std::memcpy(data, all.data() + (size_t)3 * start_idx, sizeof(float) * 3 * (size_t)(end_idx - start_idx));
+    }
     void check(int rc) {
         if (rc == FLIP_OK) return;
         std::string m = flip_last_error(_c);
@@ -465,6 +489,8 @@ private:
     double _picflip = 0.05, _cfl = 5.0, _particleScale = 3.0, _smoothValue = 0.5;      // the engine's defaults (fluidsimulation.h)
     int _minSteps = 1, _maxSteps = 6, _smoothIterations = 2;
     bool _extreme = true, _initialized = false;
+    std::vector<MeshObject *> _obstacles;
+    std::vector<MeshFluidSource *> _sources;
     MACVelocityField _mac;
     TriangleMesh _isomesh;
 };
