@@ -79,7 +79,7 @@ struct DeviceScalars {
     int sendCount[2], recvCount[2];
     int globalParticles;       // sum over ranks of the sort input (speed-limit rule)
     int globalRows;
-    int extCount[48];          // extrapolation frontier sizes, [component][layer] (grid.cu: EXT_MAX_LAYERS + 1 per component)
+    int extCount[96];          // extrapolation frontier sizes, [component][layer] (grid.cu: EXT_MAX_LAYERS + 1 per component)
     int deferredCount;         // particles the single-precision G2P / RK3 kernels left to the literal ones
     int slabError[3];          // z-slab exchange: [0] an emigrant jumped past the neighbouring slab, [1] a send buffer
                                // overflowed, [2] an RK3 sample left the halo planes; summed over the ranks before

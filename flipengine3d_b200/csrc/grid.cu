@@ -24,7 +24,7 @@ static constexpr int TPB = 256;
 // in the order +i,-i,+j,-j,+k,-k (gridutils.cpp:190-224).  The result does not depend on thread order:
 // bit-reproducible and equal to the reference's.
 // ------------------------------------------------------------------------------------------------
-static constexpr int EXT_MAX_LAYERS = 15;      // counters per component: the start frontier and one per layer
+static constexpr int EXT_MAX_LAYERS = 31;      // counters per component: the start frontier and one per layer
 struct ExtComp {
     float *grid;
     const unsigned char *valid;
@@ -246,7 +246,7 @@ void stage_extrapolate(flip_ctx *c) {
             fprintf(stderr, "\n");
         }
     }
-    if (c->extrapolationLayers > EXT_MAX_LAYERS) throw ApiError(FLIP_ERR_UNSUPPORTED, "more than 15 extrapolation layers (CFL > 13)");
+    if (c->extrapolationLayers > EXT_MAX_LAYERS) throw ApiError(FLIP_ERR_UNSUPPORTED, "more than 31 extrapolation layers (CFL > 29)");
     FLIP_CUDA_CHECK(cudaMemsetAsync(c->dS->extCount, 0, sizeof(c->dS->extCount), st));
     if (d.I >= 17) k_ext_init<<<dim3(cdiv(cdiv(nbig, 16), TPB), 3), TPB, 0, st>>>(A);
     else k_ext_init_small<<<dim3(cdiv(nbig, TPB), 3), TPB, 0, st>>>(A);

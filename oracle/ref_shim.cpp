@@ -443,6 +443,18 @@ int ref_add_mesh_fluid_box(void *p, const double lo[3], const double hi[3], cons
     });
 }
 
+/* setCFLConditionNumber (:1765), setPICFLIPRatio, setMin / MaxTimeStepsPerFrame (:1801-1831) */
+int ref_set_step_settings(void *p, int cfl, double picflip, int min_steps, int max_steps) {
+    RefSim *h = (RefSim *)p;
+    return guarded(h, [&] {
+        FluidSimulation *s = h->sim;
+        if (cfl > 0) s->setCFLConditionNumber(cfl);
+        if (picflip >= 0.0) s->setPICFLIPRatio(picflip);
+        if (min_steps > 0) s->setMinTimeStepsPerFrame(min_steps);
+        if (max_steps > 0) s->setMaxTimeStepsPerFrame(max_steps);
+    });
+}
+
 /* enable / disableExtremeVelocityRemoval (:1869-1881), setMarkerParticleScale (:168-179) */
 void ref_set_extreme_velocity_removal(void *p, int on) {
     FluidSimulation *s = ((RefSim *)p)->sim;

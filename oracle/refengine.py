@@ -70,6 +70,7 @@ def _load(kind):
     L.ref_add_mesh_fluid_box.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.ref_add_fluid_source_box.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.ref_enable_fluid_source.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.ref_set_step_settings.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_int]
     L.ref_set_extreme_velocity_removal.argtypes = [C.c_void_p, C.c_int]
     L.ref_set_marker_particle_scale.argtypes = [C.c_void_p, C.c_double]
     L.ref_add_obstacle_box.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
@@ -225,6 +226,10 @@ class RefEngine:
         idx = self.L.ref_add_fluid_source_box(self.h, 1 if outflow else 0, a, b, v)
         assert idx >= 0, self.L.ref_last_error(self.h)
         return idx
+
+    def set_step_settings(self, cfl=0, picflip=-1.0, min_steps=0, max_steps=0):
+        """setCFLConditionNumber / setPICFLIPRatio / setMin-, setMaxTimeStepsPerFrame (0 / negative: left alone)."""
+        self._check(self.L.ref_set_step_settings(self.h, int(cfl), float(picflip), int(min_steps), int(max_steps)))
 
     def set_extreme_velocity_removal(self, on=True):
         self.L.ref_set_extreme_velocity_removal(self.h, 1 if on else 0)

@@ -47,7 +47,7 @@ def aliased_slots(n):
 
 
 def make_pair(scene, tol=None, threads=None, gravity=(0.0, -25.0, 0.0), preconditioner=None, sampling=None, obstacles=(),
-              own_solid=False):
+              own_solid=False, settings=None):
     """Returns (ref, gpu) engines initialised from the same scene; the GPU engine gets the oracle's
     own static solid SDF and the oracle's LOGICAL particle list.  obstacles: (lo, hi) boxes added to
     the reference with addMeshObstacle (their distances arrive with the oracle's solid SDF); own_solid: the GPU engine builds
@@ -55,6 +55,8 @@ def make_pair(scene, tol=None, threads=None, gravity=(0.0, -25.0, 0.0), precondi
     ref = refengine.RefEngine(scene["dims"], scene["dx"], scene["pos"], scene["vel"], gravity=gravity, threads=threads, tol=tol)
     for lo, hi in obstacles:
         ref.add_obstacle_box(lo, hi)
+    if settings:      # dict(cfl=, picflip=, min_steps=, max_steps=): the step's settings on both engines
+        ref.set_step_settings(**settings)
     ref.stage("obstacles", 1.0 / 30.0)   # builds the solid SDF / near-solid grid exactly as the first step would
     I, J, K = scene["dims"]
     gpu = fe.FluidSimulation(I, J, K, scene["dx"])
@@ -66,6 +68,13 @@ def make_pair(scene, tol=None, threads=None, gravity=(0.0, -25.0, 0.0), precondi
     if sampling is not None:
         gpu.setSamplingMode(sampling)
     gpu.enableParticleIds(True)
+    if settings:
+        if settings.get("cfl"):
+            gpu.setCFLConditionNumber(settings["cfl"])
+        if settings.get("picflip", -1.0) >= 0.0:
+            gpu.setPICFLIPRatio(settings["picflip"])
+        if settings.get("min_steps") or settings.get("max_steps"):
+            gpu.setTimeStepsPerFrame(settings.get("min_steps") or 1, settings.get("max_steps") or 6)
     if own_solid:
         for lo, hi in obstacles:
             gpu.addMeshObstacleBox(lo, hi)
@@ -246,10 +255,10 @@ def developed_scene(scene, frames, preconditioner=None):
 
 
 def lockstep_frames(scene, frames=1, isolate=True, tol=None, threads=None, preconditioner=None, verbose=False,
-                    sampling=None, max_substeps=None, obstacles=(), own_solid=False):
+                    sampling=None, max_substeps=None, obstacles=(), own_solid=False, settings=None):
     """max_substeps: stop after that many lock-step substeps in total (the large scenes cost tens of CPU seconds each)."""
     ref, gpu = make_pair(scene, tol=tol, threads=threads, preconditioner=preconditioner, sampling=sampling, obstacles=obstacles,
-                         own_solid=own_solid)
+                         own_solid=own_solid, settings=settings)
     reports = []
     for f in range(frames):
         ref.begin_frame(1.0 / 30.0)

@@ -680,6 +680,23 @@ def test_static_obstacles_through_the_obstacle_api():
 
 
 @needs_ref
+@pytest.mark.parametrize("settings", [dict(cfl=9, picflip=0.3), dict(cfl=2, min_steps=2, max_steps=4, picflip=0.0)])
+def test_lockstep_with_other_step_settings(settings):
+    """setCFLConditionNumber / setPICFLIPRatio / setMin-, setMaxTimeStepsPerFrame away from the defaults (CFL 9: eleven
+    extrapolation layers and a wider near-solid mask; CFL 2 with 2..4 substeps per frame): every stage against the reference
+    from identical inputs, the same substep sequence."""
+    sc = scenes.dam_break(32)
+    for rep in pc.lockstep_frames(sc, frames=5, isolate=True, sampling="exact", settings=settings):
+        pc.check_report(rep, dx=sc["dx"], isolate=True, exact_sampling=True)
+    ref, gpu = pc.make_pair(sc, settings=settings)
+    for _ in range(4):
+        ref.update(1.0 / 30.0)
+        gpu.update(1.0 / 30.0)
+        assert ref.substeps == len(gpu.substep_stats()), (settings, ref.substeps, len(gpu.substep_stats()))
+        assert ref.num_particles == gpu.getNumMarkerParticles()
+
+
+@needs_ref
 @pytest.mark.parametrize("enabled", [True, False])
 def test_extreme_velocity_removal_switch(enabled):
     """enable / disableExtremeVelocityRemoval (fluidsimulation.cpp:1869-1881): a handful of particles far faster than the
