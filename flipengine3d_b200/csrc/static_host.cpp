@@ -2,6 +2,7 @@
 // the domain box, the variational face weights derived from it, and the coarse near-solid mask.
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <vector>
 #include "flip_internal.h"
 #include "mc_tables.h"
@@ -188,6 +189,97 @@ void build_near_solid(const Dims &d, const std::vector<float> &phi, int factor, 
 }
 
 }  // namespace flip
+
+// ------------------------------------------------------------------------------------------------
+// Nodal signed distance field of a closed triangle mesh on the simulation grid (what a MeshLevelSet holds after
+// fastCalculateSignedDistanceField, meshlevelset.cpp:773-828): the exact point-to-triangle distance at the nodes of the
+// mesh's index box grown by `band` cells (the reference computes exact distances in the band of every triangle's box,
+// :572-601, and leaves an upper bound elsewhere), negative inside (parity of the crossings of a ray; the reference
+// counts intersections along grid lines, :603-700 -- the same set for a closed mesh), `far` at all other nodes.
+// Used by the façade for fluid objects, sources and obstacles that are not axis-aligned boxes.
+namespace {
+struct V3 { float x, y, z; };
+inline V3 operator-(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline V3 operator+(V3 a, V3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+inline V3 operator*(float s, V3 a) { return {s * a.x, s * a.y, s * a.z}; }
+inline float dot3(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+// closest point on a triangle (Ericson, Real-Time Collision Detection 5.1.5), squared distance
+float point_triangle_dist2(V3 p, V3 a, V3 b, V3 c) {
+    const V3 ab = b - a, ac = c - a, ap = p - a;
+    const float d1 = dot3(ab, ap), d2 = dot3(ac, ap);
+    if (d1 <= 0.f && d2 <= 0.f) return dot3(ap, ap);
+    const V3 bp = p - b;
+    const float d3 = dot3(ab, bp), d4 = dot3(ac, bp);
+    if (d3 >= 0.f && d4 <= d3) return dot3(bp, bp);
+    const float vc = d1 * d4 - d3 * d2;
+    if (vc <= 0.f && d1 >= 0.f && d3 <= 0.f) { const V3 q = p - (a + (d1 / (d1 - d3)) * ab); return dot3(q, q); }
+    const V3 cp = p - c;
+    const float d5 = dot3(ab, cp), d6 = dot3(ac, cp);
+    if (d6 >= 0.f && d5 <= d6) return dot3(cp, cp);
+    const float vb = d5 * d2 - d1 * d6;
+    if (vb <= 0.f && d2 >= 0.f && d6 <= 0.f) { const V3 q = p - (a + (d2 / (d2 - d6)) * ac); return dot3(q, q); }
+    const float va = d3 * d6 - d5 * d4;
+    if (va <= 0.f && (d4 - d3) >= 0.f && (d5 - d6) >= 0.f) {
+        const V3 q = p - (b + ((d4 - d3) / ((d4 - d3) + (d5 - d6))) * (c - b));
+        return dot3(q, q);
+    }
+    const float denom = 1.0f / (va + vb + vc);
+    const V3 q = p - (a + (vb * denom) * ab + (vc * denom) * ac);
+    return dot3(q, q);
+}
+}  // namespace
+
+extern "C" int flip_mesh_sdf(int isize, int jsize, int ksize, double dx, const float *vertices_xyz, int num_vertices,
+                             const int *triangles, int num_triangles, int band, float far_value, float *phi, int cell_lo[3],
+                             int cell_hi[3]) {
+    if (isize <= 0 || jsize <= 0 || ksize <= 0 || !(dx > 0.0) || !phi || band < 0) return FLIP_ERR_DOMAIN;
+    for (int t = 0; t < 3 * num_triangles; t++)
+        if (triangles[t] < 0 || triangles[t] >= num_vertices) return FLIP_ERR_OUT_OF_RANGE;
+    const int ni = isize + 1, nj = jsize + 1, nk = ksize + 1;
+    const float far = far_value > 0.0f ? far_value : (float)((band + 1) * dx);
+    std::fill(phi, phi + (size_t)ni * nj * nk, far);
+    const V3 *vert = reinterpret_cast<const V3 *>(vertices_xyz);
+    float blo[3] = {1e30f, 1e30f, 1e30f}, bhi[3] = {-1e30f, -1e30f, -1e30f};
+    for (int v = 0; v < num_vertices; v++) {
+        const float q[3] = {vert[v].x, vert[v].y, vert[v].z};
+        for (int a = 0; a < 3; a++) { blo[a] = std::min(blo[a], q[a]); bhi[a] = std::max(bhi[a], q[a]); }
+    }
+    const int n[3] = {isize, jsize, ksize};
+    int nlo[3] = {0, 0, 0}, nhi[3] = {-1, -1, -1};
+    if (num_vertices > 0 && num_triangles > 0)
+        for (int a = 0; a < 3; a++) {
+            nlo[a] = std::max(0, (int)std::floor(blo[a] / dx) - band);
+            nhi[a] = std::min(n[a], (int)std::ceil(bhi[a] / dx) + band);
+        }
+    for (int a = 0; a < 3; a++) {
+        if (cell_lo) cell_lo[a] = nlo[a];
+        if (cell_hi) cell_hi[a] = std::max(nhi[a], nlo[a]);
+    }
+    for (int k = nlo[2]; k <= nhi[2]; k++)
+        for (int j = nlo[1]; j <= nhi[1]; j++)
+            for (int i = nlo[0]; i <= nhi[0]; i++) {
+                const V3 p = {(float)(i * dx), (float)(j * dx), (float)(k * dx)};
+                float d2 = 1e30f;
+                int crossings = 0;
+                // the parity ray leaves along +x from a point nudged off the lattice (mesh vertices on grid lines)
+                const double ry = p.y + 1.2345e-4 * dx, rz = p.z + 2.3456e-4 * dx;
+                for (int t = 0; t < num_triangles; t++) {
+                    const V3 &a = vert[triangles[3 * t]], &b = vert[triangles[3 * t + 1]], &c = vert[triangles[3 * t + 2]];
+                    d2 = std::min(d2, point_triangle_dist2(p, a, b, c));
+                    // intersection of the ray (x > p.x, y = ry, z = rz) with the triangle, in the yz projection
+                    const double ay = a.y - ry, az = a.z - rz, by = b.y - ry, bz = b.z - rz, cy = c.y - ry, cz = c.z - rz;
+                    const double w0 = by * cz - bz * cy, w1 = cy * az - cz * ay, w2 = ay * bz - az * by;
+                    if ((w0 > 0 && w1 > 0 && w2 > 0) || (w0 < 0 && w1 < 0 && w2 < 0)) {
+                        const double s = w0 + w1 + w2;
+                        const double x = (w0 * a.x + w1 * b.x + w2 * c.x) / s;
+                        if (x > p.x) crossings++;
+                    }
+                }
+                const float d = std::min(std::sqrt(d2), far);
+                phi[(size_t)i + (size_t)ni * (j + (size_t)nj * k)] = (crossings & 1) ? -d : d;
+            }
+    return FLIP_OK;
+}
 
 // the generated marching-cubes case table of the surface reconstruction (mc_tables.h), for inspection and tests
 extern "C" int flip_mc_case_table(unsigned char counts[256], unsigned char edge_triples[256 * 24]) {

@@ -84,6 +84,7 @@ def load_library():
     L.flip_enable_fluid_source.argtypes = [vp, ci, ci]
     L.flip_remove_fluid_source.argtypes = [vp, ci]
     L.flip_constrain_fluid_source_velocity.argtypes = [vp, ci, ci]
+    L.flip_mesh_sdf.argtypes = [ci, ci, ci, cd, vp, ci, vp, ci, ci, C.c_float, vp, C.POINTER(ci), C.POINTER(ci)]
     L.flip_reset_body_force.argtypes = [vp]
     L.flip_set_extreme_velocity_removal.argtypes = [vp, ci]
     L.flip_set_marker_particle_scale.argtypes = [vp, cd]
@@ -159,6 +160,21 @@ def static_inputs(isize, jsize, ksize, dx, solid_phi=None):
     if rc != FLIP_OK:
         raise _EXC.get(rc, RuntimeError)("flip_static_inputs failed")
     return dict(solid_phi=phi, weightU=wU, weightV=wV, weightW=wW, near_solid=ns)
+
+
+def mesh_sdf(dims, dx, vertices, triangles, band=3, far=0.0):
+    """flip_mesh_sdf (host code, no CUDA device needed): the nodal signed distance field of a closed triangle mesh on the
+    grid -- (phi of shape (K+1, J+1, I+1), cell_lo, cell_hi)."""
+    L = load_library()
+    I, J, K = (int(d) for d in dims)
+    v = np.ascontiguousarray(vertices, dtype=np.float32)
+    t = np.ascontiguousarray(triangles, dtype=np.int32)
+    phi = np.empty((K + 1, J + 1, I + 1), dtype=np.float32)
+    lo, hi = (C.c_int * 3)(), (C.c_int * 3)()
+    rc = L.flip_mesh_sdf(I, J, K, float(dx), v.ctypes.data, v.shape[0], t.ctypes.data, t.shape[0], int(band), float(far), phi.ctypes.data, lo, hi)
+    if rc != FLIP_OK:
+        raise _EXC.get(rc, RuntimeError)("flip_mesh_sdf failed")
+    return phi, tuple(lo), tuple(hi)
 
 
 def nccl_unique_id():
@@ -284,6 +300,19 @@ class FluidSimulation:
 
     def enableMeshFluidSource(self, sid, on=True):
         self._check(self.L.flip_enable_fluid_source(self.h, int(sid), 1 if on else 0))
+
+    def meshSDF(self, vertices, triangles, band=3, far=0.0):
+        """flip_mesh_sdf (host code): (phi of shape (K+1, J+1, I+1), cell_lo, cell_hi) of a closed triangle mesh."""
+        return mesh_sdf(self.dims, self.dx, vertices, triangles, band, far)
+
+    def addMeshFluidMesh(self, vertices, triangles, velocity=(0.0, 0.0, 0.0)):
+        """addMeshFluid(MeshObject) for a mesh that is not a box: host signed distance field -> flip_add_fluid_sdf."""
+        phi, lo, hi = self.meshSDF(vertices, triangles)
+        self.addMeshFluidSDF(phi, velocity, lo, hi)
+
+    def addMeshObstacleMesh(self, vertices, triangles):
+        phi, _, _ = self.meshSDF(vertices, triangles, band=3, far=3.0e38)
+        return self.addMeshObstacleSDF(phi)
 
     def resetBodyForce(self):
         self._check(self.L.flip_reset_body_force(self.h))

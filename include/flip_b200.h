@@ -210,6 +210,14 @@ int flip_static_inputs(int isize, int jsize, int ksize, double dx, float *phi, i
 /* Override the static solid inputs.  By default the context builds the reference's
  * domain box (inset 1.5dx+5e-5, fluidsimulation.cpp:2834-2839) itself.  phi: (I+1)(J+1)(K+1) floats. */
 int flip_set_solid_sdf(flip_ctx *ctx, const float *phi_nodal);
+/* The nodal signed distance field of a closed triangle mesh on the grid, as a MeshLevelSet holds it after
+ * fastCalculateSignedDistanceField(mesh, band) (meshlevelset.cpp:773-828; MeshObject::getMeshLevelSet meshobject.cpp:239):
+ * exact distances at the nodes within `band` cells of the mesh's index box, negative inside, far_value (or (band+1) dx when
+ * far_value <= 0) elsewhere.  HOST code, no device needed; the input of flip_add_fluid_sdf / flip_add_fluid_source_sdf /
+ * flip_add_obstacle_sdf for meshes that are not axis-aligned boxes.  phi: (I+1)(J+1)(K+1) floats; cell_lo / cell_hi
+ * (may be NULL): the cell range worth scanning. */
+int flip_mesh_sdf(int isize, int jsize, int ksize, double dx, const float *vertices_xyz, int num_vertices, const int *triangles,
+                  int num_triangles, int band, float far_value, float *phi, int cell_lo[3], int cell_hi[3]);
 
 /* FluidSimulation::initialize  fluidsimulation.cpp:82 */
 int flip_initialize(flip_ctx *ctx);

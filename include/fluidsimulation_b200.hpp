@@ -111,70 +111,17 @@ public:
         return seen == 0xffu;
     }
     // nodal signed distance field of the grid, (I+1)(J+1)(K+1) floats, i fastest; cells [lo,hi) worth scanning
+    // (flip_mesh_sdf: what MeshObject::getMeshLevelSet hands the engine, meshobject.cpp:239)
     void signedDistanceField(std::vector<float> &phi, int lo[3], int hi[3], int band = 3, float farValue = 0.0f) const {
-        const int ni = _isize + 1, nj = _jsize + 1, nk = _ksize + 1;
-        const float far = farValue > 0.0f ? farValue : (float)((band + 1) * _dx);      // nodes outside the band
-        phi.assign((size_t)ni * nj * nk, far);
-        vmath::vec3 blo, bhi;
-        bounds(blo, bhi);
-        const int n[3] = {_isize, _jsize, _ksize};
-        int nlo[3], nhi[3];
-        for (int a = 0; a < 3; a++) {
-            nlo[a] = std::max(0, (int)std::floor(blo[a] / _dx) - band);
-            nhi[a] = std::min(n[a], (int)std::ceil(bhi[a] / _dx) + band);
-            lo[a] = nlo[a]; hi[a] = nhi[a];
-        }
-        for (int k = nlo[2]; k <= nhi[2]; k++)
-            for (int j = nlo[1]; j <= nhi[1]; j++)
-                for (int i = nlo[0]; i <= nhi[0]; i++) {
-                    const vmath::vec3 p((float)(i * _dx), (float)(j * _dx), (float)(k * _dx));
-                    float d2 = 1e30f;
-                    int crossings = 0;
-                    // the parity ray leaves along +x from a point nudged off the lattice (mesh vertices on grid lines)
-                    const double ry = p.y + 1.2345e-4 * _dx, rz = p.z + 2.3456e-4 * _dx;
-                    for (const auto &t : _mesh.triangles) {
-                        const vmath::vec3 &a = _mesh.vertices[t.tri[0]], &b = _mesh.vertices[t.tri[1]], &c = _mesh.vertices[t.tri[2]];
-                        d2 = std::min(d2, pointTriangleDistanceSq(p, a, b, c));
-                        // intersection of the ray (x > p.x, y = ry, z = rz) with the triangle, in the yz projection
-                        const double ay = a.y - ry, az = a.z - rz, by = b.y - ry, bz = b.z - rz, cy = c.y - ry, cz = c.z - rz;
-                        const double w0 = by * cz - bz * cy, w1 = cy * az - cz * ay, w2 = ay * bz - az * by;
-                        if ((w0 > 0 && w1 > 0 && w2 > 0) || (w0 < 0 && w1 < 0 && w2 < 0)) {
-                            const double s = w0 + w1 + w2;
-                            const double x = (w0 * a.x + w1 * b.x + w2 * c.x) / s;
-                            if (x > p.x) crossings++;
-                        }
-                    }
-                    const float d = std::min(std::sqrt(d2), far);
-                    phi[(size_t)i + (size_t)ni * (j + (size_t)nj * k)] = (crossings & 1) ? -d : d;
-                }
+        phi.resize((size_t)(_isize + 1) * (_jsize + 1) * (_ksize + 1));
+        static_assert(sizeof(vmath::vec3) == 12 && sizeof(Triangle) == 12, "packed float / int triplets");
+        const int rc = flip_mesh_sdf(_isize, _jsize, _ksize, _dx, reinterpret_cast<const float *>(_mesh.vertices.data()),
+                                     (int)_mesh.vertices.size(), reinterpret_cast<const int *>(_mesh.triangles.data()),
+                                     (int)_mesh.triangles.size(), band, farValue, phi.data(), lo, hi);
+        if (rc != FLIP_OK) throw std::domain_error("Error: bad triangle mesh for a signed distance field.\n");
     }
 
 private:
-    static float pointTriangleDistanceSq(const vmath::vec3 &p, const vmath::vec3 &a, const vmath::vec3 &b, const vmath::vec3 &c) {
-        // closest point on a triangle (Ericson, Real-Time Collision Detection 5.1.5)
-        using namespace vmath;
-        const vec3 ab = b - a, ac = c - a, ap = p - a;
-        const float d1 = dot(ab, ap), d2 = dot(ac, ap);
-        if (d1 <= 0.f && d2 <= 0.f) return dot(ap, ap);
-        const vec3 bp = p - b;
-        const float d3 = dot(ab, bp), d4 = dot(ac, bp);
-        if (d3 >= 0.f && d4 <= d3) return dot(bp, bp);
-        const float vc = d1 * d4 - d3 * d2;
-        if (vc <= 0.f && d1 >= 0.f && d3 <= 0.f) { const vec3 q = p - (a + (d1 / (d1 - d3)) * ab); return dot(q, q); }
-        const vec3 cp = p - c;
-        const float d5 = dot(ab, cp), d6 = dot(ac, cp);
-        if (d6 >= 0.f && d5 <= d6) return dot(cp, cp);
-        const float vb = d5 * d2 - d1 * d6;
-        if (vb <= 0.f && d2 >= 0.f && d6 <= 0.f) { const vec3 q = p - (a + (d2 / (d2 - d6)) * ac); return dot(q, q); }
-        const float va = d3 * d6 - d5 * d4;
-        if (va <= 0.f && (d4 - d3) >= 0.f && (d5 - d6) >= 0.f) {
-            const vec3 q = p - (b + ((d4 - d3) / ((d4 - d3) + (d5 - d6))) * (c - b));
-            return dot(q, q);
-        }
-        const float den = 1.f / (va + vb + vc);
-        const vec3 q = p - (a + (vb * den) * ab + (vc * den) * ac);
-        return dot(q, q);
-    }
     friend class FluidSimulation;
     int _isize = 0, _jsize = 0, _ksize = 0;
     double _dx = 0.0;

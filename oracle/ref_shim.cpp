@@ -443,6 +443,41 @@ int ref_add_mesh_fluid_box(void *p, const double lo[3], const double hi[3], cons
     });
 }
 
+/* MeshLevelSet::fastCalculateSignedDistanceField(mesh, band) (meshlevelset.cpp:773-828) of an arbitrary triangle mesh on a
+ * grid of its own: the nodal phi, (I+1)(J+1)(K+1) floats. */
+int ref_mesh_level_set(int isize, int jsize, int ksize, double dx, const float *verts, int nv, const int *tris, int nt, int band,
+                       float *out) {
+    try {
+        TriangleMesh m;
+        for (int v = 0; v < nv; v++) m.vertices.push_back(vmath::vec3(verts[3 * v], verts[3 * v + 1], verts[3 * v + 2]));
+        for (int t = 0; t < nt; t++) m.triangles.push_back(Triangle(tris[3 * t], tris[3 * t + 1], tris[3 * t + 2]));
+        MeshLevelSet sdf(isize, jsize, ksize, dx);
+        sdf.disableVelocityData();
+        sdf.fastCalculateSignedDistanceField(m, band);
+        size_t q = 0;
+        for (int k = 0; k <= ksize; k++)
+            for (int j = 0; j <= jsize; j++)
+                for (int i = 0; i <= isize; i++) out[q++] = sdf(i, j, k);
+        return 0;
+    } catch (std::exception &) {
+        return 1;
+    }
+}
+
+/* addMeshFluid with an arbitrary static closed mesh (queued, seeded at the end of the next step) */
+int ref_add_mesh_fluid_mesh(void *p, const float *verts, int nv, const int *tris, int nt, const double vel[3]) {
+    RefSim *h = (RefSim *)p;
+    return guarded(h, [&] {
+        FluidSimulation *s = h->sim;
+        TriangleMesh m;
+        for (int v = 0; v < nv; v++) m.vertices.push_back(vmath::vec3(verts[3 * v], verts[3 * v + 1], verts[3 * v + 2]));
+        for (int t = 0; t < nt; t++) m.triangles.push_back(Triangle(tris[3 * t], tris[3 * t + 1], tris[3 * t + 2]));
+        MeshObject obj(s->_isize, s->_jsize, s->_ksize, s->_dx);
+        obj.updateMeshStatic(m);
+        s->addMeshFluid(obj, vmath::vec3((float)vel[0], (float)vel[1], (float)vel[2]));
+    });
+}
+
 /* setCFLConditionNumber (:1765), setPICFLIPRatio, setMin / MaxTimeStepsPerFrame (:1801-1831) */
 int ref_set_step_settings(void *p, int cfl, double picflip, int min_steps, int max_steps) {
     RefSim *h = (RefSim *)p;

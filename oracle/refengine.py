@@ -70,6 +70,8 @@ def _load(kind):
     L.ref_add_mesh_fluid_box.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.ref_add_fluid_source_box.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.ref_enable_fluid_source.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.ref_mesh_level_set.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    L.ref_add_mesh_fluid_mesh.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_double)]
     L.ref_set_step_settings.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_int]
     L.ref_set_extreme_velocity_removal.argtypes = [C.c_void_p, C.c_int]
     L.ref_set_marker_particle_scale.argtypes = [C.c_void_p, C.c_double]
@@ -227,6 +229,12 @@ class RefEngine:
         assert idx >= 0, self.L.ref_last_error(self.h)
         return idx
 
+    def add_mesh_fluid_mesh(self, vertices, triangles, velocity=(0.0, 0.0, 0.0)):
+        """FluidSimulation::addMeshFluid with a static closed triangle mesh."""
+        v = np.ascontiguousarray(vertices, dtype=np.float32)
+        t = np.ascontiguousarray(triangles, dtype=np.int32)
+        self._check(self.L.ref_add_mesh_fluid_mesh(self.h, v.ctypes.data, v.shape[0], t.ctypes.data, t.shape[0], (C.c_double * 3)(*velocity)))
+
     def set_step_settings(self, cfl=0, picflip=-1.0, min_steps=0, max_steps=0):
         """setCFLConditionNumber / setPICFLIPRatio / setMin-, setMaxTimeStepsPerFrame (0 / negative: left alone)."""
         self._check(self.L.ref_set_step_settings(self.h, int(cfl), float(picflip), int(min_steps), int(max_steps)))
@@ -291,3 +299,15 @@ class RefEngine:
             more = self.end_substep()
         self.end_frame()
         return dts
+
+
+def mesh_level_set(dims, dx, vertices, triangles, band=3, kind="golden"):
+    """MeshLevelSet::fastCalculateSignedDistanceField of a triangle mesh: nodal phi, shape (K+1, J+1, I+1)."""
+    L = _load(kind)
+    v = np.ascontiguousarray(vertices, dtype=np.float32)
+    t = np.ascontiguousarray(triangles, dtype=np.int32)
+    I, J, K = (int(d) for d in dims)
+    out = np.empty((K + 1, J + 1, I + 1), dtype=np.float32)
+    rc = L.ref_mesh_level_set(I, J, K, float(dx), v.ctypes.data, v.shape[0], t.ctypes.data, t.shape[0], int(band), out.ctypes.data)
+    assert rc == 0
+    return out

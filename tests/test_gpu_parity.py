@@ -538,6 +538,31 @@ def test_device_seeding_matches_addMeshFluid_of_the_reference():
 
 
 @needs_ref
+def test_device_seeding_of_a_general_mesh_matches_the_reference():
+    """addMeshFluid with a closed mesh that is not a box (an octahedron): host signed distance field (flip_mesh_sdf) ->
+    flip_add_fluid_sdf -> the seeding kernels, against the reference's addMeshFluid(MeshObject) of the same mesh: the same
+    particle count and sub-cell positions (up to the reference's jitter)."""
+    n, dx = 30, 0.125
+    c, r = np.array((1.77, 1.83, 1.71), np.float32), 0.93
+    v = np.array([c + (r, 0, 0), c - (r, 0, 0), c + (0, 0.8 * r, 0), c - (0, 0.8 * r, 0), c + (0, 0, 1.2 * r), c - (0, 0, 1.2 * r)], np.float32)
+    t = np.array([(0, 2, 4), (2, 1, 4), (1, 3, 4), (3, 0, 4), (2, 0, 5), (1, 2, 5), (3, 1, 5), (0, 3, 5)], np.int32)
+    ref = pc.refengine.RefEngine((n, n, n), dx, np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32), threads=1)
+    ref.add_mesh_fluid_mesh(v, t, velocity=(0.5, 0.0, -0.25))
+    gpu = fe.FluidSimulation(n, n, n, dx)
+    gpu.addBodyForce(0, -25, 0)
+    gpu.addMeshFluidMesh(v, t, velocity=(0.5, 0.0, -0.25))
+    gpu.initialize()
+    ref.update(1.0 / 30.0)
+    gpu.update(1.0 / 30.0)
+    a, b = ref.particles(), gpu.getMarkerParticles()
+    assert a.shape[0] == b.shape[0] > 1000, (a.shape, b.shape)
+    key = lambda p: np.lexsort((np.floor(p[:, 0] / (dx / 2)), np.floor(p[:, 1] / (dx / 2)), np.floor(p[:, 2] / (dx / 2))))
+    a, b = a[key(a)], b[key(b)]
+    assert np.abs(a[:, :3] - b[:, :3]).max() <= 3e-4 * dx
+    assert np.array_equal(a[:, 3:], b[:, 3:])
+
+
+@needs_ref
 @pytest.mark.parametrize("constrained,low", [(True, False), (False, False), (True, True)])
 def test_inflow_and_outflow_sources_match_the_reference(constrained, low):
     """SURVEY §8f rank 2, second half: MeshFluidSource inflow (emits at the end of every substep where sub-cells are

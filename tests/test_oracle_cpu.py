@@ -96,3 +96,37 @@ def test_particle_container_aliasing_matches_the_harness_model():
     slot[hi] = lo
     assert np.array_equal(got[:, :3], pos[slot[slot]])
     e.close()
+
+
+def _wedge(p, w, h, d):
+    x, y, z = p
+    v = np.array([(x, y, z), (x + w, y, z), (x, y + h, z), (x, y, z + d), (x + w, y, z + d), (x, y + h, z + d)], np.float32)
+    t = np.array([(0, 2, 1), (3, 4, 5), (0, 1, 4), (0, 4, 3), (0, 3, 5), (0, 5, 2), (1, 2, 5), (1, 5, 4)], np.int32)
+    return v, t
+
+
+def _octahedron(c, r):
+    c = np.array(c, np.float32)
+    v = np.array([c + (r, 0, 0), c - (r, 0, 0), c + (0, 0.8 * r, 0), c - (0, 0.8 * r, 0), c + (0, 0, 1.2 * r), c - (0, 0, 1.2 * r)], np.float32)
+    t = np.array([(0, 2, 4), (2, 1, 4), (1, 3, 4), (3, 0, 4), (2, 0, 5), (1, 2, 5), (3, 1, 5), (0, 3, 5)], np.int32)
+    return v, t
+
+
+@pytest.mark.parametrize("mesh", ["wedge", "octahedron"])
+def test_mesh_signed_distance_field_matches_the_reference_level_set(mesh):
+    """flip_mesh_sdf (host code of the library: what the façade hands over for fluid objects, sources and obstacles that
+    are not boxes) against MeshLevelSet::fastCalculateSignedDistanceField of the unmodified reference on the same mesh:
+    the same sign at every node that is not ON the surface, the same distance within the band the engine reads."""
+    from flipengine3d_b200 import engine as fe
+    n, dx = 28, 0.125
+    v, t = _wedge((0.83, 0.41, 0.67), 1.31, 0.9, 1.7) if mesh == "wedge" else _octahedron((1.77, 1.63, 1.71), 0.93)
+    ref = refengine.mesh_level_set((n, n, n), dx, v, t, band=3)
+    mine, lo, hi = fe.mesh_sdf((n, n, n), dx, v, t, band=3)
+    off = np.abs(ref) > 1e-6
+    assert (ref < 0).sum() > 300
+    assert np.array_equal((ref < 0)[off], (mine < 0)[off])
+    near = np.abs(ref) < 2.5 * dx
+    assert near.sum() > 1500 and np.abs(ref - mine)[near].max() <= 1e-6
+    # the cell range handed to the seeding kernel covers every node inside the mesh
+    kk, jj, ii = np.nonzero(ref < 0)
+    assert lo[0] <= ii.min() and ii.max() <= hi[0] and lo[1] <= jj.min() and jj.max() <= hi[1] and lo[2] <= kk.min() and kk.max() <= hi[2]
