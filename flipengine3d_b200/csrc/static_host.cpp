@@ -255,29 +255,55 @@ extern "C" int flip_mesh_sdf(int isize, int jsize, int ksize, double dx, const f
         if (cell_lo) cell_lo[a] = nlo[a];
         if (cell_hi) cell_hi[a] = std::max(nhi[a], nlo[a]);
     }
-    for (int k = nlo[2]; k <= nhi[2]; k++)
-        for (int j = nlo[1]; j <= nhi[1]; j++)
-            for (int i = nlo[0]; i <= nhi[0]; i++) {
-                const V3 p = {(float)(i * dx), (float)(j * dx), (float)(k * dx)};
-                float d2 = 1e30f;
-                int crossings = 0;
-                // the parity ray leaves along +x from a point nudged off the lattice (mesh vertices on grid lines)
-                const double ry = p.y + 1.2345e-4 * dx, rz = p.z + 2.3456e-4 * dx;
-                for (int t = 0; t < num_triangles; t++) {
-                    const V3 &a = vert[triangles[3 * t]], &b = vert[triangles[3 * t + 1]], &c = vert[triangles[3 * t + 2]];
+    if (nhi[0] < nlo[0] || nhi[1] < nlo[1] || nhi[2] < nlo[2]) return FLIP_OK;
+    // the region of interest: the mesh's index box grown by the band
+    const int ri = nhi[0] - nlo[0] + 1, rj = nhi[1] - nlo[1] + 1, rk = nhi[2] - nlo[2] + 1;
+    std::vector<float> best((size_t)ri * rj * rk, 1e30f);          // squared distance to the nearest triangle seen
+    std::vector<std::vector<float>> hits((size_t)rj * rk);          // x of the crossings of the +x ray of every (j, k) line
+    for (int t = 0; t < num_triangles; t++) {
+        const V3 &a = vert[triangles[3 * t]], &b = vert[triangles[3 * t + 1]], &c = vert[triangles[3 * t + 2]];
+        const float tlo[3] = {std::min(a.x, std::min(b.x, c.x)), std::min(a.y, std::min(b.y, c.y)), std::min(a.z, std::min(b.z, c.z))};
+        const float thi[3] = {std::max(a.x, std::max(b.x, c.x)), std::max(a.y, std::max(b.y, c.y)), std::max(a.z, std::max(b.z, c.z))};
+        int q0[3], q1[3];
+        for (int ax = 0; ax < 3; ax++) {
+            q0[ax] = std::max(nlo[ax], (int)std::floor(tlo[ax] / dx) - band);
+            q1[ax] = std::min(nhi[ax], (int)std::ceil(thi[ax] / dx) + band);
+        }
+        // exact distances in the band of the triangle's index box (meshlevelset.cpp:572-601)
+        for (int k = q0[2]; k <= q1[2]; k++)
+            for (int j = q0[1]; j <= q1[1]; j++)
+                for (int i = q0[0]; i <= q1[0]; i++) {
+                    const V3 p = {(float)(i * dx), (float)(j * dx), (float)(k * dx)};
+                    float &d2 = best[(size_t)(i - nlo[0]) + (size_t)ri * ((j - nlo[1]) + (size_t)rj * (k - nlo[2]))];
                     d2 = std::min(d2, point_triangle_dist2(p, a, b, c));
-                    // intersection of the ray (x > p.x, y = ry, z = rz) with the triangle, in the yz projection
-                    const double ay = a.y - ry, az = a.z - rz, by = b.y - ry, bz = b.z - rz, cy = c.y - ry, cz = c.z - rz;
-                    const double w0 = by * cz - bz * cy, w1 = cy * az - cz * ay, w2 = ay * bz - az * by;
-                    if ((w0 > 0 && w1 > 0 && w2 > 0) || (w0 < 0 && w1 < 0 && w2 < 0)) {
-                        const double s = w0 + w1 + w2;
-                        const double x = (w0 * a.x + w1 * b.x + w2 * c.x) / s;
-                        if (x > p.x) crossings++;
-                    }
                 }
-                const float d = std::min(std::sqrt(d2), far);
+        // crossings of the +x rays through the (j, k) lines the triangle's yz projection can cover; every ray starts from a
+        // point nudged off the lattice (mesh vertices on grid lines)
+        const int j0 = std::max(nlo[1], (int)std::floor(tlo[1] / dx) - 1), j1 = std::min(nhi[1], (int)std::ceil(thi[1] / dx));
+        const int k0 = std::max(nlo[2], (int)std::floor(tlo[2] / dx) - 1), k1 = std::min(nhi[2], (int)std::ceil(thi[2] / dx));
+        for (int k = k0; k <= k1; k++)
+            for (int j = j0; j <= j1; j++) {
+                const double ry = (double)(float)(j * dx) + 1.2345e-4 * dx, rz = (double)(float)(k * dx) + 2.3456e-4 * dx;
+                const double ay = a.y - ry, az = a.z - rz, by = b.y - ry, bz = b.z - rz, cy = c.y - ry, cz = c.z - rz;
+                const double w0 = by * cz - bz * cy, w1 = cy * az - cz * ay, w2 = ay * bz - az * by;
+                if ((w0 > 0 && w1 > 0 && w2 > 0) || (w0 < 0 && w1 < 0 && w2 < 0)) {
+                    const double s = w0 + w1 + w2;
+                    hits[(size_t)(j - nlo[1]) + (size_t)rj * (k - nlo[2])].push_back((float)((w0 * a.x + w1 * b.x + w2 * c.x) / s));
+                }
+            }
+    }
+    for (int k = nlo[2]; k <= nhi[2]; k++)
+        for (int j = nlo[1]; j <= nhi[1]; j++) {
+            const std::vector<float> &xs = hits[(size_t)(j - nlo[1]) + (size_t)rj * (k - nlo[2])];
+            for (int i = nlo[0]; i <= nhi[0]; i++) {
+                const float px = (float)(i * dx);
+                int crossings = 0;
+                for (float x : xs) crossings += x > px ? 1 : 0;
+                const float d2 = best[(size_t)(i - nlo[0]) + (size_t)ri * ((j - nlo[1]) + (size_t)rj * (k - nlo[2]))];
+                const float d = d2 < 1e29f ? std::min(std::sqrt(d2), far) : far;       // no triangle within the band: the bound
                 phi[(size_t)i + (size_t)ni * (j + (size_t)nj * k)] = (crossings & 1) ? -d : d;
             }
+        }
     return FLIP_OK;
 }
 
