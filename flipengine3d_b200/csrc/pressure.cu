@@ -1160,6 +1160,24 @@ __global__ void __launch_bounds__(1024) k_mg_coarse(MgCoarseArgs A, const Device
     }
 }
 
+// (Tried: a contiguous chunk of segments per block for L1 reuse of the j neighbours -- no faster, less balanced.)
+// Walk of a warp over the active segments w0, w0 + nw, w0 + 2 nw, ... with the descriptors (first cell, row mask) of
+// the next 32 trips fetched at once, one per lane, and handed out by shuffle.  Body variables: segc, segm.
+// (`continue` inside the body goes on to the next trip; every lane reaches the shuffles of every trip.)
+#define SEG_WALK_BEGIN(segCell, segMask, nseg, nw, lane)                                                     \
+    for (int segBase_ = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; segBase_ < (nseg); segBase_ += 32 * (nw)) { \
+        const long long segMine_ = (long long)segBase_ + (long long)(lane) * (nw);                            \
+        int segCellMine_ = 0;                                                                                 \
+        unsigned int segMaskMine_ = 0u;                                                                       \
+        if (segMine_ < (nseg)) { segCellMine_ = (segCell)[segMine_]; segMaskMine_ = (segMask)[segMine_]; }    \
+        const int segTrips_ = min(32, ((nseg) - segBase_ + (nw) - 1) / (nw));                                 \
+        for (int segTrip_ = 0; segTrip_ < segTrips_; segTrip_++) {                                            \
+            const int segc = __shfl_sync(0xffffffffu, segCellMine_, segTrip_);                                \
+            const unsigned int segm = __shfl_sync(0xffffffffu, segMaskMine_, segTrip_);
+#define SEG_WALK_END \
+        }            \
+    }
+
 // ---- level 0: segment-driven, right-hand side = the fp64 PCG residual
 struct Mg0 {
     PGrid g;
@@ -1288,9 +1306,9 @@ __global__ void __launch_bounds__(TPB, 5) k_pcg_update_presweep(const int *__res
     const double alpha = S->rho[it % 3] / S->dotSZ[it % 3];
     const int sj = M.g.sj, sk = M.g.sk;
     double rabs = 0.0;
-    for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nseg; w += nw) {
-        const int c = segCell[w] + lane;
-        if (!((segMask[w] >> lane) & 1u)) continue;
+    SEG_WALK_BEGIN(segCell, segMask, nseg, nw, lane)
+        const int c = segc + lane;
+        if (!((segm >> lane) & 1u)) continue;
         // everything is loaded before anything is consumed (rows are interior cells: every index is in range)
         const float a0 = M.oW[c - sk], a1 = M.oV[c - sj], a2 = M.oU[c - 1], a3 = M.oU[c], a4 = M.oV[c], a5 = M.oW[c];
         const float d0 = M.invD[c - sk], d1 = M.invD[c - sj], d2 = M.invD[c - 1], d3 = M.invD[c + 1], d4 = M.invD[c + sj], d5 = M.invD[c + sk];
@@ -1312,7 +1330,7 @@ __global__ void __launch_bounds__(TPB, 5) k_pcg_update_presweep(const int *__res
         ns += (a4 != 0.0f && d4 != 0.0f) ? a4 * (omega0 * d4 * (float)(r4 - alpha * q4)) : 0.0f;
         ns += (a5 != 0.0f && d5 != 0.0f) ? a5 * (omega0 * d5 * (float)(r5 - alpha * q5)) : 0.0f;
         xout[c] = (inv == 0.0f) ? 0.0f : (1.0f - omega) * (omega0 * inv * b) + omega * inv * (b + M.fac * ns);
-    }
+    SEG_WALK_END
     block_max(rabs, &S->rMaxBits[it % 3]);
 }
 
@@ -1341,9 +1359,13 @@ __global__ void __launch_bounds__(TPB, 5) k_pcg_dir_spmv(const int *__restrict__
     if (!converged && !breakdown) {
         const PGrid &g = pp.g;
         const int nseg = S->numSegments, nw = (gridDim.x * blockDim.x) >> 5;
-        for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nseg; w += nw) {
-            const int c = segCell[w] + lane;
-            if (!((segMask[w] >> lane) & 1u)) continue;
+        // A warp walks the segments w0, w0 + nw, ...: lane l fetches the descriptor of the l-th of the next 32 trips in
+        // ONE coalesced-by-stride load, and every trip takes its descriptor by shuffle -- otherwise each trip is two
+        // dependent round trips (descriptor, then rows), and with ~15 trips per warp that chain, not bandwidth, is
+        // the kernel's time.
+        SEG_WALK_BEGIN(segCell, segMask, nseg, nw, lane)
+            const int c = segc + lane;
+            if (!((segm >> lane) & 1u)) continue;
             const float a0 = AoffW[c - g.sk], a1 = AoffV[c - g.sj], a2 = AoffU[c - 1], a3 = AoffU[c], a4 = AoffV[c], a5 = AoffW[c];
             const double z0 = z[c - g.sk], z1 = z[c - g.sj], z2 = z[c - 1], z3 = z[c + 1], z4 = z[c + g.sj], z5 = z[c + g.sk];
             double s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0, s5 = 0, sc = 0;
@@ -1364,7 +1386,7 @@ __global__ void __launch_bounds__(TPB, 5) k_pcg_dir_spmv(const int *__restrict__
             sNew[c] = vc;
             q[c] = qv;
             part += vc * qv;
-        }
+        SEG_WALK_END
     }
     block_add(part, &S->dotSZ[it % 3]);
     __shared__ bool last;
