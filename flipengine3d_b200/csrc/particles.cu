@@ -1192,7 +1192,7 @@ __global__ void __launch_bounds__(P2G_THREADS, 3) k_p2g_scatter(ParticleSoA p, c
                             const bool in = ni >= 0 && nj >= 0 && nk >= 0 && ni <= I && nj <= J && nk <= K;
                             const int node = in ? ni + (I + 1) * (nj + (J + 1) * nk) : ci + (I + 1) * (j + (J + 1) * k);
                             for (int comp = 0; comp < 3; comp++, w++)
-                                if (slot + w < Q.litCap) Q.litFaces[slot + w] = (comp << 28) | node;
+                                if (slot + w < Q.litCap) Q.litFaces[slot + w] = (int)(((unsigned int)comp << 30) | (unsigned int)node);
                         }
             }
         }
@@ -1492,7 +1492,7 @@ __global__ void __launch_bounds__(SHELL_THREADS) k_sdf_shell(ParticleSoA p, cons
 // accumulators for the next step).  A cell that received no minimum lies in no particle's search box.  Five nodes in
 // six are far from any particle and take the short path: zeros and the "no particles" SDF value (finish_phi of an
 // infinite distance: 3 dx, particlelevelset.cpp:295), in 32-bit index arithmetic (the scatter path is limited to
-// 2^28 nodes).  (ncu on the first version: 210 instructions per node, issue-bound at 225 us; the loads were not the
+// 2^30 nodes).  (ncu on the first version: 210 instructions per node, issue-bound at 225 us; the loads were not the
 // limit -- two nodes per thread with all loads hoisted took 240 us.)
 __global__ void k_p2g_finish(GatherParams g, P2GGlobal G, double invSScale,
                              float *__restrict__ U, float *__restrict__ V, float *__restrict__ W,
@@ -1541,7 +1541,7 @@ __global__ void k_p2g_finish(GatherParams g, P2GGlobal G, double invSScale,
             const float ssum = (float)((double)(long long)a.y * invSScale);
             int slot = -1;
             if (wsum < P2G_LITERAL_BAND) slot = warp_append_slot(Q.litCount);
-            if (slot >= 0 && slot < Q.litCap) Q.litFaces[slot] = (comp << 28) | (i + (I + 1) * (j + (J + 1) * k));
+            if (slot >= 0 && slot < Q.litCap) Q.litFaces[slot] = (int)(((unsigned int)comp << 30) | (unsigned int)(i + (I + 1) * (j + (J + 1) * k)));
             else { ok = wsum > g.eps; val = ok ? __fdiv_rn(ssum, wsum) : ssum; }   // (a full queue costs digits, nothing else)
         }
         field[idx] = val;
@@ -1620,7 +1620,7 @@ __global__ void __launch_bounds__(256) k_p2g_literal(ParticleSoA p, const int *_
     const int nw = (gridDim.x * blockDim.x) >> 5;
     for (int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < n; t += nw) {
         const int e = litFaces[t];
-        const int comp = (e >> 28) & 3, node = e & 0x0fffffff;
+        const int comp = (int)((unsigned int)e >> 30), node = e & 0x3fffffff;
         const int i = node % (I + 1), j = (node / (I + 1)) % (J + 1), k = node / ((I + 1) * (J + 1));
         // (entries queued around a dense cell may name faces that do not exist on the upper borders)
         if ((comp == 0 && (j >= J || k >= K)) || (comp == 1 && (i >= I || k >= K)) || (comp == 2 && (i >= I || j >= J))) continue;
@@ -1680,7 +1680,7 @@ static void run_sdf_p2g(flip_ctx *c) {
     int *farCount = &c->dS->frontierCount[0];
     FLIP_CUDA_CHECK(cudaMemsetAsync(c->dS->frontierCount, 0, 2 * sizeof(int), c->stream));
     // the scatter: single-precision mode, power-of-two dx
-    const bool scatter = dyadic && g.packed && (long long)d.nN < (1ll << 28) && !getenv("FLIP_P2G_GATHER");
+    const bool scatter = dyadic && g.packed && (long long)d.nN < (1ll << 30) && !getenv("FLIP_P2G_GATHER");
     if (scatter) {
         const int WR = cdiv(d.I, 32);
         const size_t words = (size_t)WR * d.J * d.K;
