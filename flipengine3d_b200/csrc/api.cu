@@ -109,6 +109,9 @@ static void free_grids(flip_ctx *c) {
     cudaFree(c->validU); cudaFree(c->validV); cudaFree(c->validW); cudaFree(c->status);
     cudaFree(c->frontier[0]); cudaFree(c->frontier[1]);
     cudaFree(c->phiL); cudaFree(c->phiS); cudaFree(c->wU); cudaFree(c->wV); cudaFree(c->wW);
+    cudaFree(c->wC); cudaFree(c->solU); cudaFree(c->solV); cudaFree(c->solW); cudaFree(c->pocketFlag);
+    c->wC = c->solU = c->solV = c->solW = nullptr;
+    c->pocketFlag = nullptr;
     for (auto &a : c->p2gAcc) { cudaFree(a); a = nullptr; }
     cudaFree(c->occBits); c->occBits = nullptr;
     cudaFree(c->p2gTiles); c->p2gTiles = nullptr;
@@ -168,6 +171,11 @@ static void upload_static_inputs(flip_ctx *c) {
     FLIP_CUDA_CHECK(cudaMemcpy(c->wU, wU.data(), sizeof(float) * d.nU, cudaMemcpyHostToDevice));
     FLIP_CUDA_CHECK(cudaMemcpy(c->wV, wV.data(), sizeof(float) * d.nV, cudaMemcpyHostToDevice));
     FLIP_CUDA_CHECK(cudaMemcpy(c->wW, wW.data(), sizeof(float) * d.nW, cudaMemcpyHostToDevice));
+    if (c->solU) {      // moving solids: the centre weights multiply their velocities in the divergence
+        build_center_weights(d, local, wC);
+        if (!c->wC) dev_alloc(c->wC, d.nC);
+        FLIP_CUDA_CHECK(cudaMemcpy(c->wC, wC.data(), sizeof(float) * d.nC, cudaMemcpyHostToDevice));
+    }
     cudaFree(c->nearSolid); c->nearSolid = nullptr;
     dev_alloc(c->nearSolid, ns.size());
     FLIP_CUDA_CHECK(cudaMemcpy(c->nearSolid, ns.data(), ns.size(), cudaMemcpyHostToDevice));
@@ -557,6 +565,37 @@ int flip_remove_obstacle(flip_ctx *c, int id) {
     });
 }
 
+// Face velocities of the solids.  The reference keeps them with the solid SDF (VelocityDataGrid, meshlevelset.h:69-87) and
+// fills them from the vertex velocities of animated meshes; here the caller hands in the three face arrays.
+int flip_set_solid_velocity(flip_ctx *c, const float *U, const float *V, const float *W) {
+    return guarded(c, [&] {
+        const Dims &d = c->d;
+        FLIP_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        if (!U && !V && !W) {       // every solid at rest again
+            cudaFree(c->solU); cudaFree(c->solV); cudaFree(c->solW);
+            c->solU = c->solV = c->solW = nullptr;
+            return;
+        }
+        if (!U || !V || !W) throw ApiError(FLIP_ERR_RUNTIME, "flip_set_solid_velocity: three arrays or three null pointers");
+        if (slab_on(c)) throw ApiError(FLIP_ERR_UNSUPPORTED, "solid velocities are not supported in a z-slab run");
+        if (!c->solU) {
+            dev_alloc(c->solU, d.nU); dev_alloc(c->solV, d.nV); dev_alloc(c->solW, d.nW);
+            dev_alloc(c->pocketFlag, d.nC);
+        }
+        FLIP_CUDA_CHECK(cudaMemcpy(c->solU, U, sizeof(float) * d.nU, cudaMemcpyHostToDevice));
+        FLIP_CUDA_CHECK(cudaMemcpy(c->solV, V, sizeof(float) * d.nV, cudaMemcpyHostToDevice));
+        FLIP_CUDA_CHECK(cudaMemcpy(c->solW, W, sizeof(float) * d.nW, cudaMemcpyHostToDevice));
+        if (c->initialized && !c->wC) {
+            // the centre weights of the solid SDF as it stands on the device
+            std::vector<float> phi((size_t)d.nN), wC;
+            FLIP_CUDA_CHECK(cudaMemcpy(phi.data(), c->phiS, sizeof(float) * d.nN, cudaMemcpyDeviceToHost));
+            build_center_weights(d, phi, wC);
+            dev_alloc(c->wC, d.nC);
+            FLIP_CUDA_CHECK(cudaMemcpy(c->wC, wC.data(), sizeof(float) * d.nC, cudaMemcpyHostToDevice));
+        }
+    });
+}
+
 int flip_initialize(flip_ctx *c) {
     return guarded(c, [&] {
         if (c->initialized) throw ApiError(FLIP_ERR_RUNTIME, "Error: FluidSimulation is already initialized.");
@@ -843,6 +882,10 @@ static void *array_ptr(const flip_ctx *c, int which, int64_t *bytes) {
         case FLIP_ARRAY_WEIGHT_U: *bytes = 4ll * d.nU; return c->wU;
         case FLIP_ARRAY_WEIGHT_V: *bytes = 4ll * d.nV; return c->wV;
         case FLIP_ARRAY_WEIGHT_W: *bytes = 4ll * d.nW; return c->wW;
+        case FLIP_ARRAY_WEIGHT_C: if (!c->wC) break; *bytes = 4ll * d.nC; return c->wC;
+        case FLIP_ARRAY_SOLID_VEL_U: *bytes = 4ll * d.nU; return c->solU;
+        case FLIP_ARRAY_SOLID_VEL_V: *bytes = 4ll * d.nV; return c->solV;
+        case FLIP_ARRAY_SOLID_VEL_W: *bytes = 4ll * d.nW; return c->solW;
         case FLIP_ARRAY_SAVED_U: *bytes = 4ll * d.nU; return c->sU;
         case FLIP_ARRAY_SAVED_V: *bytes = 4ll * d.nV; return c->sV;
         case FLIP_ARRAY_SAVED_W: *bytes = 4ll * d.nW; return c->sW;
@@ -866,7 +909,7 @@ int flip_get_array(flip_ctx *c, int which, void *out) {
         void *p = array_ptr(c, which, &bytes);
         if (bytes < 0) {
             if (which == FLIP_ARRAY_WEIGHT_C)
-                throw ApiError(FLIP_ERR_UNSUPPORTED, "the cell-centre weight only multiplies solid velocities, which are zero for static solids; it is not built");
+                throw ApiError(FLIP_ERR_UNSUPPORTED, "the cell-centre weight only multiplies solid velocities; it is built once flip_set_solid_velocity has been called");
             throw ApiError(FLIP_ERR_OUT_OF_RANGE, "bad array id");
         }
         FLIP_CUDA_CHECK(cudaStreamSynchronize(c->stream));
@@ -972,6 +1015,20 @@ int flip_static_inputs(int I, int J, int K, double dx, float *phi, int phiIsInpu
             if (nearSolid) memcpy(nearSolid, ns.data(), ns.size());
             if (nearDims) { nearDims[0] = gi; nearDims[1] = gj; nearDims[2] = gk; }
         }
+        return FLIP_OK;
+    } catch (const std::bad_alloc &) { g_createError = "host allocation failed"; return FLIP_ERR_RUNTIME; }
+}
+int flip_center_weights(int I, int J, int K, double dx, const float *phi, float *wC) {
+    if (I <= 0 || J <= 0 || K <= 0 || !(dx > 0.0)) return FLIP_ERR_DOMAIN;
+    if (!phi || !wC) return FLIP_ERR_RUNTIME;
+    try {
+        Dims d;
+        d.I = I; d.J = J; d.K = K; d.dx = dx; d.kOff = 0; d.Kg = K; d.kOwn0 = 0; d.kOwn1 = K;
+        d.nC = I * J * K;
+        d.nN = (I + 1) * (J + 1) * (K + 1);
+        std::vector<float> p(phi, phi + (size_t)d.nN), cc;
+        build_center_weights(d, p, cc);
+        memcpy(wC, cc.data(), sizeof(float) * cc.size());
         return FLIP_OK;
     } catch (const std::bad_alloc &) { g_createError = "host allocation failed"; return FLIP_ERR_RUNTIME; }
 }

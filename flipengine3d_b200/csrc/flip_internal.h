@@ -84,8 +84,9 @@ struct DeviceScalars {
     int slabError[3];          // z-slab exchange: [0] an emigrant jumped past the neighbouring slab, [1] a send buffer
                                // overflowed, [2] an RK3 sample left the halo planes; summed over the ranks before
                                // anybody acts on them
+    int pocketChanged;         // enclosed-pocket search of the moving-solid path: a pass changed a flag
     // multigrid coarse solve etc.
-    int pad[8];
+    int pad[7];
 };
 
 }  // namespace flip
@@ -187,6 +188,10 @@ struct flip_ctx {
     float *phiL = nullptr;                    // liquid SDF
     float *phiS = nullptr;                    // solid SDF, nodal
     float *wU = nullptr, *wV = nullptr, *wW = nullptr, *wC = nullptr;
+    // face velocities of the solids (MeshLevelSet::getFaceVelocityU/V/W, meshlevelset.cpp:207-231): null while every
+    // solid is at rest.  They enter the divergence (pressuresolver.cpp:608-613) and the solid constraint (:3884-3933).
+    float *solU = nullptr, *solV = nullptr, *solW = nullptr;
+    unsigned char *pocketFlag = nullptr;      // [nC] scratch of the enclosed-pocket search (pressuresolver.cpp:124-244)
     unsigned char *nearSolid = nullptr;
     int nsI = 0, nsJ = 0, nsK = 0;
     float *pressure = nullptr;                // (I,J,K) float, last solution
@@ -248,6 +253,7 @@ namespace flip {
 void build_box_solid_sdf(const Dims &d, std::vector<float> &phi);
 void build_weights(const Dims &d, const std::vector<float> &phi, std::vector<float> &wU, std::vector<float> &wV,
                    std::vector<float> &wW, std::vector<float> &wC);
+void build_center_weights(const Dims &d, const std::vector<float> &phi, std::vector<float> &wC);
 void build_near_solid(const Dims &d, const std::vector<float> &phi, int factor, int band, double cfl,
                       std::vector<unsigned char> &grid, int &gi, int &gj, int &gk);
 

@@ -320,8 +320,24 @@ __global__ void k_constrain(float *__restrict__ a, float *__restrict__ b, const 
     }
 }
 
+// ... with moving solids: such a face takes the solid's face velocity (fluidsimulation.cpp:3893-3894); the friction of
+// partly open faces is 0 as before.
+__global__ void k_constrain_moving(float *__restrict__ a, float *__restrict__ b, const float *__restrict__ w,
+                                   const float *__restrict__ solid, int n) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n && w[t] == 0.0f) { const float v = solid[t]; a[t] = v; b[t] = v; }
+}
+
 void stage_constrain(flip_ctx *c) {
     const Dims &d = c->d;
+    if (c->solU) {
+        k_constrain_moving<<<cdiv(d.nU, TPB), TPB, 0, c->stream>>>(c->sU, c->U, c->wU, c->solU, d.nU);
+        k_constrain_moving<<<cdiv(d.nV, TPB), TPB, 0, c->stream>>>(c->sV, c->V, c->wV, c->solV, d.nV);
+        k_constrain_moving<<<cdiv(d.nW, TPB), TPB, 0, c->stream>>>(c->sW, c->W, c->wW, c->solW, d.nW);
+        c->launches += 3;
+        FLIP_CUDA_CHECK(cudaGetLastError());
+        return;
+    }
     k_constrain<<<cdiv(cdiv(d.nU, 4), TPB), TPB, 0, c->stream>>>(c->sU, c->U, c->wU, d.nU);
     k_constrain<<<cdiv(cdiv(d.nV, 4), TPB), TPB, 0, c->stream>>>(c->sV, c->V, c->wV, d.nV);
     k_constrain<<<cdiv(cdiv(d.nW, 4), TPB), TPB, 0, c->stream>>>(c->sW, c->W, c->wW, d.nW);

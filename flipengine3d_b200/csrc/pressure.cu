@@ -83,6 +83,83 @@ __global__ void k_seg_compact(int nSeg, const unsigned int *__restrict__ mask, c
 }
 
 // ---- 2. right-hand side and matrix
+// ---- moving solids: _conditionSolidVelocityField (pressuresolver.cpp:124-244).  Liquid cells of [1,N-2]^3 are joined
+// through faces of weight >= 1e-6; a joined region of more than one cell none of whose cells has an air neighbour
+// across such a face (_computeBordersAirGridThread :246-268) is an enclosed pocket, and the solid velocities on the six
+// faces of each of its cells are set to zero (in the stored arrays, as there).  The reference flood-fills region by
+// region on one thread; here "reaches air" spreads from the air-bordering cells, one cell per pass and direction, until
+// a pass changes nothing, and the cells it never reached are the pockets.
+// flag: 0 not a liquid interior cell, 1 liquid and not (yet) reached, 2 reached.
+#define POCKET_EPS 1e-6f
+__device__ __forceinline__ bool pocket_interior(const PGrid &g, int i, int j, int k) {
+    return i >= 1 && j >= 1 && k >= 1 && i < g.I - 1 && j < g.J - 1 && k < g.K - 1;
+}
+__global__ void k_pocket_init(PGrid g, int nC, const float *__restrict__ phi, const float *__restrict__ wU,
+                              const float *__restrict__ wV, const float *__restrict__ wW, unsigned char *__restrict__ flag) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nC) return;
+    const int i = c % g.I, j = (c / g.I) % g.J, k = c / g.sk;
+    unsigned char f = 0;
+    if (pocket_interior(g, i, j, k) && phi[c] < 0.0f) {
+        const int fu = i + (g.I + 1) * (j + g.J * k), fv = i + g.I * (j + (g.J + 1) * k);
+        const bool air = (wU[fu] >= POCKET_EPS && phi[c - 1] >= 0.0f) || (wU[fu + 1] >= POCKET_EPS && phi[c + 1] >= 0.0f) ||
+                         (wV[fv] >= POCKET_EPS && phi[c - g.sj] >= 0.0f) || (wV[fv + g.I] >= POCKET_EPS && phi[c + g.sj] >= 0.0f) ||
+                         (wW[c] >= POCKET_EPS && phi[c - g.sk] >= 0.0f) || (wW[c + g.sk] >= POCKET_EPS && phi[c + g.sk] >= 0.0f);
+        f = air ? 2 : 1;
+    }
+    flag[c] = f;
+}
+__global__ void k_pocket_spread(PGrid g, int nC, const float *__restrict__ wU, const float *__restrict__ wV,
+                                const float *__restrict__ wW, volatile unsigned char *flag, int *changed) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nC || flag[c] != 1) return;
+    const int i = c % g.I, j = (c / g.I) % g.J, k = c / g.sk;
+    const int fu = i + (g.I + 1) * (j + g.J * k), fv = i + g.I * (j + (g.J + 1) * k);
+    // (a neighbour with flag 2 is a liquid interior cell)
+    const bool reached = (flag[c - 1] == 2 && wU[fu] >= POCKET_EPS) || (flag[c + 1] == 2 && wU[fu + 1] >= POCKET_EPS) ||
+                         (flag[c - g.sj] == 2 && wV[fv] >= POCKET_EPS) || (flag[c + g.sj] == 2 && wV[fv + g.I] >= POCKET_EPS) ||
+                         (flag[c - g.sk] == 2 && wW[c] >= POCKET_EPS) || (flag[c + g.sk] == 2 && wW[c + g.sk] >= POCKET_EPS);
+    if (reached) { flag[c] = 2; *changed = 1; }
+}
+__global__ void k_pocket_zero(PGrid g, int nC, const float *__restrict__ wU, const float *__restrict__ wV,
+                              const float *__restrict__ wW, const unsigned char *__restrict__ flag,
+                              float *__restrict__ solU, float *__restrict__ solV, float *__restrict__ solW) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nC || flag[c] != 1) return;
+    const int i = c % g.I, j = (c / g.I) % g.J, k = c / g.sk;
+    const int fu = i + (g.I + 1) * (j + g.J * k), fv = i + g.I * (j + (g.J + 1) * k);
+    // joined to another cell of the pocket?  (a neighbour with a nonzero flag is a liquid interior cell; next to an
+    // unreached cell it is unreached too)
+    const bool joined = (flag[c - 1] && wU[fu] >= POCKET_EPS) || (flag[c + 1] && wU[fu + 1] >= POCKET_EPS) ||
+                        (flag[c - g.sj] && wV[fv] >= POCKET_EPS) || (flag[c + g.sj] && wV[fv + g.I] >= POCKET_EPS) ||
+                        (flag[c - g.sk] && wW[c] >= POCKET_EPS) || (flag[c + g.sk] && wW[c + g.sk] >= POCKET_EPS);
+    if (!joined) return;        // a region of one cell is left alone (:219)
+    solU[fu] = 0.0f; solU[fu + 1] = 0.0f;
+    solV[fv] = 0.0f; solV[fv + g.I] = 0.0f;
+    solW[c] = 0.0f; solW[c + g.sk] = 0.0f;
+}
+
+static void condition_solid_velocities(flip_ctx *c, const PGrid &g) {
+    const Dims &d = c->d;
+    cudaStream_t st = c->stream;
+    const int blocks = cdiv(d.nC, TPB);
+    int *changed = &c->dS->pocketChanged;
+    k_pocket_init<<<blocks, TPB, 0, st>>>(g, d.nC, c->phiL, c->wU, c->wV, c->wW, c->pocketFlag);
+    c->launches++;
+    for (;;) {
+        FLIP_CUDA_CHECK(cudaMemsetAsync(changed, 0, sizeof(int), st));
+        for (int pass = 0; pass < 16; pass++) k_pocket_spread<<<blocks, TPB, 0, st>>>(g, d.nC, c->wU, c->wV, c->wW, c->pocketFlag, changed);
+        c->launches += 16;
+        int h = 0;
+        FLIP_CUDA_CHECK(cudaMemcpyAsync(&h, changed, sizeof(int), cudaMemcpyDeviceToHost, st));
+        FLIP_CUDA_CHECK(cudaStreamSynchronize(st));
+        if (!h) break;
+    }
+    k_pocket_zero<<<blocks, TPB, 0, st>>>(g, d.nC, c->wU, c->wV, c->wW, c->pocketFlag, c->solU, c->solV, c->solW);
+    c->launches++;
+    FLIP_CUDA_CHECK(cudaGetLastError());
+}
+
 struct BuildParams {
     PGrid g;
     double invdx;     // 1.0/_dx                    pressuresolver.cpp:582
@@ -95,7 +172,9 @@ __global__ void k_build_system(const int *__restrict__ segCell, const unsigned i
                                const float *__restrict__ wU, const float *__restrict__ wV, const float *__restrict__ wW,
                                double *__restrict__ Adiag, float *__restrict__ AoffU, float *__restrict__ AoffV,
                                float *__restrict__ AoffW, double *__restrict__ b, double *__restrict__ x,
-                               DeviceScalars *S, const unsigned int *__restrict__ prevRowBits) {
+                               DeviceScalars *S, const unsigned int *__restrict__ prevRowBits,
+                               const float *__restrict__ solU, const float *__restrict__ solV,
+                               const float *__restrict__ solW, const float *__restrict__ wC) {
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     if (warp >= S->numSegments) return;
@@ -111,8 +190,8 @@ __global__ void k_build_system(const int *__restrict__ segCell, const unsigned i
         double volRight = wU[fu + 1], volLeft = wU[fu];
         double volTop = wV[fv + g.I], volBottom = wV[fv];
         double volFront = wW[fw + g.sk], volBack = wW[fw];
-        // _calculateNegativeDivergenceVectorThread  pressuresolver.cpp:580-613 (static solids: the
-        // solid-velocity terms are +-0)
+        // _calculateNegativeDivergenceVectorThread  pressuresolver.cpp:580-613 (solids at rest: the
+        // solid-velocity terms are +-0 and are skipped)
         double f = bp.invdx;
         double div = 0.0;
         div = dadd(div, dmul(dmul(-f, volRight), (double)U[fu + 1]));
@@ -121,6 +200,16 @@ __global__ void k_build_system(const int *__restrict__ segCell, const unsigned i
         div = dadd(div, dmul(dmul(f, volBottom), (double)V[fv]));
         div = dadd(div, dmul(dmul(-f, volFront), (double)W[fw + g.sk]));
         div = dadd(div, dmul(dmul(f, volBack), (double)W[fw]));
+        if (solU) {
+            // moving solids (pressuresolver.cpp:595, :608-613): +-factor * (w_face - w_centre) * u_solid, in this order
+            const double volCenter = wC[c];
+            div = dadd(div, dmul(dmul(f, dsub(volRight, volCenter)), (double)solU[fu + 1]));
+            div = dadd(div, dmul(dmul(-f, dsub(volLeft, volCenter)), (double)solU[fu]));
+            div = dadd(div, dmul(dmul(f, dsub(volTop, volCenter)), (double)solV[fv + g.I]));
+            div = dadd(div, dmul(dmul(-f, dsub(volBottom, volCenter)), (double)solV[fv]));
+            div = dadd(div, dmul(dmul(f, dsub(volFront, volCenter)), (double)solW[fw + g.sk]));
+            div = dadd(div, dmul(dmul(-f, dsub(volBack, volCenter)), (double)solW[fw]));
+        }
         b[c] = div;
         // initial guess: 0 as in the reference (pcgsolver.h:258), or -- warm start -- the pressure this cell had in
         // the previous solve if it was a row then (segments are aligned: bit `lane` of word c/32)
@@ -2198,6 +2287,11 @@ void stage_pressure(flip_ctx *c, double dt) {
     PGrid g{d.I, d.J, d.K, d.I, d.I * d.J, d.kOff, d.Kg, d.kOwn0, d.kOwn1, 0};
     int nSeg = ps->nSegAll;
 
+    // moving solids: enclosed pockets first (PressureSolver::solve, pressuresolver.cpp:46)
+    if (c->solU) {
+        if (!c->wC) throw ApiError(FLIP_ERR_RUNTIME, "solid velocities without centre weights");
+        condition_solid_velocities(c, g);
+    }
     // warm start: the row bits of the previous solve say where vx_ holds a pressure worth starting from
     const bool warm = c->pressureWarmStart != 0;
     std::swap(ps->maskAll, ps->maskPrev);
@@ -2232,7 +2326,7 @@ void stage_pressure(flip_ctx *c, double dt) {
     bp.factor = dt / (d.dx * d.dx);
     k_build_system<<<segBlocks, TPB, 0, st>>>(c->segCell, c->segMask, bp, c->phiL, c->U, c->V, c->W, c->wU, c->wV,
                                              c->wW, c->Adiag, c->AoffU, c->AoffV, c->AoffW, c->vb, c->vx_, c->dS,
-                                             warm ? ps->maskPrev : nullptr);
+                                             warm ? ps->maskPrev : nullptr, c->solU, c->solV, c->solW, c->wC);
     c->launches++;
     kt_end(c, FLIP_KERNEL_PRESSURE_BUILD, ktBuild);
     const bool slab = slab_on(c);

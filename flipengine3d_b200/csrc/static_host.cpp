@@ -130,6 +130,67 @@ static float negative_area(float bl, float br, float tl, float tr) {
 
 static inline float clamp01(float w) { return std::max(0.0f, std::min(w, 1.0f)); }
 
+// Volume fraction of a tetrahedron on which the linear function through its corner values is negative
+// (LevelsetUtils::volumeFraction(float, float, float, float), levelsetutils.cpp:213-226, over the sorted-tetrahedron
+// and sorted-prism formulas of levelsetutils.h:72-85).  Only the sorted values enter; they are put in order by the
+// reference's five-comparator network, so that equal values (and signed zeros) end up where they do there.
+static float negative_tet_volume(float a, float b, float c, float d) {
+    float v[4] = {a, b, c, d};
+    static const unsigned char net[5][2] = {{0, 1}, {2, 3}, {0, 2}, {1, 3}, {1, 2}};
+    for (auto &cmp : net)
+        if (v[cmp[0]] > v[cmp[1]]) std::swap(v[cmp[0]], v[cmp[1]]);
+    auto corner = [](float p, float q, float r, float s) { return p * p * p / ((p - q) * (p - r) * (p - s)); };
+    if (v[3] <= 0) return 1;
+    if (v[2] <= 0) return 1 - corner(v[3], v[2], v[1], v[0]);      // one positive corner cut off
+    if (v[1] <= 0) {                                               // two and two: a prism
+        const float e02 = v[0] / (v[0] - v[2]), e03 = v[0] / (v[0] - v[3]);
+        const float e13 = v[1] / (v[1] - v[3]), e12 = v[1] / (v[1] - v[2]);
+        return e02 * e03 * (1 - e12) + e03 * (1 - e13) * e12 + e13 * e12;
+    }
+    if (v[0] <= 0) return corner(v[0], v[1], v[2], v[3]);          // one negative corner cut off
+    return 0;
+}
+
+// Solid fraction of a cell from the eight nodal values of the solid SDF (MeshLevelSet::_getCellWeight,
+// meshlevelset.cpp:1490-1513): the mean of the two decompositions of the cube into five tetrahedra
+// (LevelsetUtils::volumeFraction of eight values, levelsetutils.cpp:243-259), summed in the reference's order; the
+// central tetrahedron of each decomposition counts twice.  q[x + 2 y + 4 z] = phi(i + x, j + y, k + z).
+static float negative_cell_volume(const float q[8]) {
+    int negatives = 0;
+    for (int n = 0; n < 8; n++) negatives += q[n] < 0 ? 1 : 0;
+    if (negatives == 8) return 1.0f;
+    if (negatives == 0) return 0.0f;
+    static const unsigned char tets[10][5] = {       // four corners and the multiplicity
+        {0, 4, 5, 6, 1}, {0, 5, 1, 3, 1}, {0, 2, 6, 3, 1}, {5, 6, 7, 3, 1}, {0, 6, 5, 3, 2},
+        {1, 5, 4, 7, 1}, {1, 4, 0, 2, 1}, {1, 3, 7, 2, 1}, {4, 7, 6, 2, 1}, {1, 7, 4, 2, 2}};
+    float sum = 0.0f;
+    bool first = true;
+    for (auto &t : tets) {
+        float part = negative_tet_volume(q[t[0]], q[t[1]], q[t[2]], q[t[3]]);
+        if (t[4] == 2) part = 2 * part;
+        sum = first ? part : sum + part;
+        first = false;
+    }
+    return sum / 12.0f;
+}
+
+// The cell-centre entry of the weight grid (_updateWeightGridThread, CENTER branch, fluidsimulation.cpp:3720-3727): it
+// multiplies the solid face velocities in the divergence (pressuresolver.cpp:595-613), so it is only built when solid
+// velocities are in use.
+void build_center_weights(const Dims &d, const std::vector<float> &phi, std::vector<float> &wC) {
+    const int ni = d.I + 1, nj = d.J + 1;
+    wC.resize(d.nC);
+    size_t idx = 0;
+    for (int k = 0; k < d.K; k++)
+        for (int j = 0; j < d.J; j++)
+            for (int i = 0; i < d.I; i++, idx++) {
+                float q[8];
+                for (int n = 0; n < 8; n++)
+                    q[n] = phi[(size_t)(i + (n & 1)) + (size_t)ni * ((size_t)(j + ((n >> 1) & 1)) + (size_t)nj * (k + (n >> 2)))];
+                wC[idx] = clamp01(1.0f - negative_cell_volume(q));
+            }
+}
+
 // FluidSimulation::_updateWeightGridThread (fluidsimulation.cpp:3690-3730) over
 // MeshLevelSet::getFaceWeightU/V/W (meshlevelset.cpp:357-387).  The cell-centre weight multiplies
 // the (zero) velocities of static solids only (pressuresolver.cpp:595-600) and is not built.

@@ -16,7 +16,7 @@ STAGES = ("obstacles", "liquid_sdf", "p2g", "extrapolate_a", "save", "body_force
 STAGE_ID = {n: i for i, n in enumerate(STAGES)}
 ARRAY_ID = dict(U=0, V=1, W=2, validU=3, validV=4, validW=5, liquid_phi=6, solid_phi=7,
                 weightU=8, weightV=9, weightW=10, weightC=11, savedU=12, savedV=13, savedW=14,
-                near_solid=15, pressure=16)
+                near_solid=15, pressure=16, solidU=17, solidV=18, solidW=19)
 
 KERNEL_CLASSES = ("sdf_p2g", "g2p", "advance", "sort", "extrapolate", "pcg_spmv", "pcg_iter", "pressure_build",
                   "pressure_apply", "precond", "pcg_solve", "pcg_dir_spmv", "g2p_advance")
@@ -104,6 +104,8 @@ def load_library():
     L.flip_get_current_frame.argtypes = [vp, C.POINTER(ci)]
     L.flip_set_current_frame.argtypes = [vp, ci]
     L.flip_static_inputs.argtypes = [ci, ci, ci, C.c_double, vp, ci, vp, vp, vp, vp, C.POINTER(ci)]
+    L.flip_center_weights.argtypes = [ci, ci, ci, C.c_double, vp, vp]
+    L.flip_set_solid_velocity.argtypes = [vp, vp, vp, vp]
     L.flip_get_num_substeps.argtypes = [vp, C.POINTER(ci)]
     L.flip_get_step_stats.argtypes = [vp, ci, C.POINTER(StepStats)]
     L.flip_get_num_particles.argtypes = [vp, C.POINTER(ci)]
@@ -160,6 +162,19 @@ def static_inputs(isize, jsize, ksize, dx, solid_phi=None):
     if rc != FLIP_OK:
         raise _EXC.get(rc, RuntimeError)("flip_static_inputs failed")
     return dict(solid_phi=phi, weightU=wU, weightV=wV, weightW=wW, near_solid=ns)
+
+
+def center_weights(dims, dx, solid_phi):
+    """flip_center_weights (host code, no CUDA device needed): the cell-centre weights (K, J, I) of a nodal solid SDF."""
+    L = load_library()
+    I, J, K = (int(d) for d in dims)
+    phi = np.ascontiguousarray(solid_phi, dtype=np.float32)
+    assert phi.shape == (K + 1, J + 1, I + 1)
+    wC = np.empty((K, J, I), dtype=np.float32)
+    rc = L.flip_center_weights(I, J, K, float(dx), phi.ctypes.data, wC.ctypes.data)
+    if rc != FLIP_OK:
+        raise _EXC.get(rc, RuntimeError)("flip_center_weights failed")
+    return wC
 
 
 def mesh_sdf(dims, dx, vertices, triangles, band=3, far=0.0):
@@ -337,6 +352,22 @@ class FluidSimulation:
         oid = C.c_int()
         self._check(self.L.flip_add_obstacle_sdf(self.h, a.ctypes.data, C.byref(oid)))
         return oid.value
+
+    def setSolidVelocity(self, U=None, V=None, W=None):
+        """flip_set_solid_velocity: the face velocities of the solids (MeshLevelSet::getFaceVelocityU/V/W), shapes
+        (K, J, I+1), (K, J+1, I), (K+1, J, I); no arguments: every solid at rest again."""
+        if U is None and V is None and W is None:
+            self._check(self.L.flip_set_solid_velocity(self.h, None, None, None))
+            self._solid_velocity = False
+            return
+        a = [np.ascontiguousarray(x, dtype=np.float32) for x in (U, V, W)]
+        for x, name in zip(a, ("solidU", "solidV", "solidW")):
+            assert x.shape == self.shape_of(name), (name, x.shape)
+        self._check(self.L.flip_set_solid_velocity(self.h, a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data))
+        self._solid_velocity = True
+
+    def hasSolidVelocity(self):
+        return bool(getattr(self, "_solid_velocity", False))
 
     def enableMeshObstacle(self, oid, on=True):
         self._check(self.L.flip_enable_obstacle(self.h, int(oid), 1 if on else 0))
@@ -547,13 +578,13 @@ class FluidSimulation:
         I, J, K = self.dims
         if name != "solid_phi_global":
             K = self.local_K
-        if name in ("U", "validU", "weightU", "savedU"):
+        if name in ("U", "validU", "weightU", "savedU", "solidU"):
             return (K, J, I + 1)
-        if name in ("V", "validV", "weightV", "savedV"):
+        if name in ("V", "validV", "weightV", "savedV", "solidV"):
             return (K, J + 1, I)
-        if name in ("W", "validW", "weightW", "savedW"):
+        if name in ("W", "validW", "weightW", "savedW", "solidW"):
             return (K + 1, J, I)
-        if name in ("liquid_phi", "pressure"):
+        if name in ("liquid_phi", "pressure", "weightC"):
             return (K, J, I)
         if name == "solid_phi":
             return (K + 1, J + 1, I + 1)

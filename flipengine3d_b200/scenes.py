@@ -99,6 +99,34 @@ def dam_break(n=128, seed=12345, krange=None, dx=DX):
     return dict(name=f"dambreak{n}", dims=(n, n, n), dx=dx, pos=pos, vel=vel, id_offset=8 * skip)
 
 
+def dam_break_with_chamber(n=32, seed=12349):
+    """The small dam break plus a closed chamber high above the floor, built from six wall boxes (none aligned with the
+    grid) and filled to the brim: a liquid region enclosed by solids that touches no air -- what
+    PressureSolver::_conditionSolidVelocityField (pressuresolver.cpp:124-244) looks for.  Returns the scene with the
+    wall boxes under "obstacles" ((lo, hi) world coordinates) and the chamber's cells under "chamber_cells"."""
+    sc = dam_break(n, seed=seed)
+    dx = sc["dx"]
+    o0, o1 = np.array([18.3, 15.3, 8.3]), np.array([27.7, 24.7, 20.7])      # outer box, in cells
+    t = 2.4                                                                  # wall thickness
+    walls = []
+    for a in range(3):
+        lo, hi = o0.copy(), o1.copy()
+        hi[a] = o0[a] + t
+        walls.append((tuple(lo * dx), tuple(hi * dx)))
+        lo, hi = o0.copy(), o1.copy()
+        lo[a] = o1[a] - t
+        walls.append((tuple(lo * dx), tuple(hi * dx)))
+    cells = box_cells(21, 25, 18, 22, 11, 18)          # the cells wholly inside the cavity
+    pos, vel = seed_cells(cells, dx, seed + 1)
+    sc = dict(sc)
+    sc["name"] = f"dambreakchamber{n}"
+    sc["pos"] = np.concatenate([sc["pos"], pos], axis=0)
+    sc["vel"] = np.concatenate([sc["vel"], vel], axis=0)
+    sc["obstacles"] = walls
+    sc["chamber_cells"] = cells
+    return sc
+
+
 def dam_break_z(n=64, seed=12347):
     """A column against the low-z wall that collapses along +z: particles cross z-slab boundaries
     (migration test of the multi-GPU decomposition)."""

@@ -62,7 +62,10 @@ enum {
     FLIP_ARRAY_SAVED_U = 12, FLIP_ARRAY_SAVED_V = 13, FLIP_ARRAY_SAVED_W = 14,
     FLIP_ARRAY_NEAR_SOLID = 15, /* uint8 coarse grid, cell = 3dx  fluidsimulation.cpp:3094 */
     FLIP_ARRAY_PRESSURE = 16,   /* float (I,J,K) pressure of the last solve (pressuresolver.cpp:843-847) */
-    FLIP_NUM_ARRAYS = 17
+    FLIP_ARRAY_SOLID_VEL_U = 17, FLIP_ARRAY_SOLID_VEL_V = 18, FLIP_ARRAY_SOLID_VEL_W = 19, /* float, MAC layout: the solids'
+                                   face velocities (VelocityDataGrid::field, meshlevelset.h:69-87); exist after
+                                   flip_set_solid_velocity, and so does FLIP_ARRAY_WEIGHT_C */
+    FLIP_NUM_ARRAYS = 20
 };
 
 /* Per-substep bookkeeping: the integers the reference logs in _logStepInfo (fluidsimulation.cpp:5710-5745). */
@@ -188,12 +191,32 @@ int flip_constrain_fluid_source_velocity(flip_ctx *ctx, int id, int on);
  * (meshlevelset.cpp:1758-1795), and the face weights, the near-solid mask and everything that reads the solid SDF
  * (collision, removal, seeding, the surface clamp) follow.  Before flip_initialize the merge happens there; afterwards at
  * the start of the next substep (the reference's _isSolidLevelSetUpToDate = false, :2007).  Obstacles have zero velocity
- * and zero friction (MeshObject defaults); animated / rigid-body obstacles are not supported.
+ * and zero friction (MeshObject defaults) unless flip_set_solid_velocity supplies face velocities; the per-substep SDF of an
+ * animated / rigid-body obstacle is not built by the library.
  * flip_remove_obstacle of an unknown id: FLIP_ERR_DOMAIN (the reference throws std::invalid_argument). */
 int flip_add_obstacle_box(flip_ctx *ctx, const double lo[3], const double hi[3], int *id);
 int flip_add_obstacle_sdf(flip_ctx *ctx, const float *nodal_sdf, int *id);
 int flip_enable_obstacle(flip_ctx *ctx, int id, int on);
 int flip_remove_obstacle(flip_ctx *ctx, int id);
+/* Moving solids, the hot-path half: the face velocities of the solids, as MeshLevelSet keeps them
+ * beside the solid SDF (getFaceVelocityU/V/W, meshlevelset.cpp:207-231; the reference fills them from the vertex
+ * velocities of animated meshes and normalises them, :640-702, :1319-1372).  Three HOST arrays in the MAC layout
+ * (U (I+1)JK, V I(J+1)K, W IJ(K+1)), copied; three NULLs: every solid at rest again (the default).  While set,
+ *   - the right-hand side of the pressure system carries the solid terms +-(w_face - w_centre) u_solid / dx of
+ *     _calculateNegativeDivergenceVectorThread (pressuresolver.cpp:595-613), w_centre being the cell-centre entry of the
+ *     weight grid (_updateWeightGridThread CENTER :3720-3727 over MeshLevelSet::_getCellWeight, meshlevelset.cpp:1490-1513),
+ *     which is built from the solid SDF from then on (FLIP_ARRAY_WEIGHT_C);
+ *   - before every solve the velocities around liquid regions that are enclosed by solids and touch no air are set to
+ *     zero IN the stored arrays, as _conditionSolidVelocityField does (pressuresolver.cpp:124-244; regions of one cell
+ *     are left alone, :219), on the device;
+ *   - faces of zero weight take the solid's face velocity in the solid constraint (_constrainVelocityFieldThread
+ *     fluidsimulation.cpp:3884-3933; friction is 0, the MeshObject default, so partly open faces keep their value).
+ * The SDF of a moving solid itself is the caller's (flip_add_obstacle_sdf / flip_enable_obstacle / flip_remove_obstacle per
+ * substep, or flip_set_solid_sdf before flip_initialize).  Not available in a z-slab run (FLIP_ERR_UNSUPPORTED). */
+int flip_set_solid_velocity(flip_ctx *ctx, const float *U, const float *V, const float *W);
+/* The cell-centre weights of a nodal solid SDF, computed on the HOST exactly as the library computes them (no CUDA device
+ * needed): phi (I+1)(J+1)(K+1) floats in, wC IJK floats out. */
+int flip_center_weights(int isize, int jsize, int ksize, double dx, const float *phi_nodal, float *wC);
 /* FluidSimulation::_addMarkerParticle  fluidsimulation.cpp:2637 (range-checked push). */
 int flip_add_marker_particle(flip_ctx *ctx, const float position[3], const float velocity[3]);
 

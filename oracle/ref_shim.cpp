@@ -346,7 +346,9 @@ enum {
     AR_SOLID_PHI = 7,                             /* float (I+1,J+1,K+1) nodal */
     AR_WEIGHT_U = 8, AR_WEIGHT_V = 9, AR_WEIGHT_W = 10, AR_WEIGHT_C = 11, /* float */
     AR_SAVED_U = 12, AR_SAVED_V = 13, AR_SAVED_W = 14,
-    AR_NEAR_SOLID = 15                            /* uint8, coarse grid */
+    AR_NEAR_SOLID = 15,                           /* uint8, coarse grid */
+    AR_SOLID_VEL_U = 16, AR_SOLID_VEL_V = 17, AR_SOLID_VEL_W = 18  /* float, MAC layout: the face velocities kept with the
+                                                     solid SDF (VelocityDataGrid::field, meshlevelset.h:69-87) */
 };
 
 static void *arrayPtr(FluidSimulation *s, int which, size_t *bytes) {
@@ -369,6 +371,9 @@ static void *arrayPtr(FluidSimulation *s, int which, size_t *bytes) {
         case AR_SAVED_V: return f(s->_savedVelocityField.getArray3dV());
         case AR_SAVED_W: return f(s->_savedVelocityField.getArray3dW());
         case AR_NEAR_SOLID: return b(&s->_nearSolidGrid);
+        case AR_SOLID_VEL_U: return f(s->_solidSDF._velocityData.field.getArray3dU());
+        case AR_SOLID_VEL_V: return f(s->_solidSDF._velocityData.field.getArray3dV());
+        case AR_SOLID_VEL_W: return f(s->_solidSDF._velocityData.field.getArray3dW());
     }
     *bytes = 0;
     return nullptr;
@@ -405,6 +410,8 @@ void ref_near_solid_dims(void *p, int *gi, int *gj, int *gk) {
 
 /* Forces the weight grid to exist (it is otherwise built lazily inside the first pressure solve). */
 void ref_update_weight_grid(void *p) { ((RefSim *)p)->sim->_updateWeightGrid(); }
+/* ... again, after the solid SDF was overwritten through ref_set_array (the flag _updateSolidLevelSet would clear, :3070) */
+void ref_invalidate_weight_grid(void *p) { ((RefSim *)p)->sim->_isWeightGridUpToDate = false; }
 
 /* Single-point samplers used by the unit tests of the restated interpolation code. */
 void ref_sample_velocity(void *p, int n, const float *pos, float *out) {

@@ -11,7 +11,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 STAGES = dict(obstacles=0, liquid_sdf=1, p2g=2, extrapolate_a=3, save=4, body_force=5, pressure=6,
               extrapolate_b=7, constrain=8, g2p=9, advance=10, tail=11)
 ARRAYS = dict(U=0, V=1, W=2, validU=3, validV=4, validW=5, liquid_phi=6, solid_phi=7,
-              weightU=8, weightV=9, weightW=10, weightC=11, savedU=12, savedV=13, savedW=14, near_solid=15)
+              weightU=8, weightV=9, weightW=10, weightC=11, savedU=12, savedV=13, savedW=14, near_solid=15,
+              solidU=16, solidV=17, solidW=18)
 
 
 def lib_path(kind="golden"):
@@ -65,6 +66,7 @@ def _load(kind):
     L.ref_set_array.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     L.ref_near_solid_dims.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 3
     L.ref_update_weight_grid.argtypes = [C.c_void_p]
+    L.ref_invalidate_weight_grid.argtypes = [C.c_void_p]
     L.ref_sample_velocity.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.ref_sample_solid_phi.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.ref_add_mesh_fluid_box.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
@@ -175,11 +177,11 @@ class RefEngine:
 
     def shape_of(self, name):
         I, J, K = self.dims
-        if name in ("U", "validU", "weightU", "savedU"):
+        if name in ("U", "validU", "weightU", "savedU", "solidU"):
             return (K, J, I + 1)
-        if name in ("V", "validV", "weightV", "savedV"):
+        if name in ("V", "validV", "weightV", "savedV", "solidV"):
             return (K, J + 1, I)
-        if name in ("W", "validW", "weightW", "savedW"):
+        if name in ("W", "validW", "weightW", "savedW", "solidW"):
             return (K + 1, J, I)
         if name in ("liquid_phi", "weightC"):
             return (K, J, I)
@@ -208,7 +210,9 @@ class RefEngine:
         assert self.L.ref_array_bytes(self.h, which) == a.nbytes
         assert self.L.ref_set_array(self.h, which, a.ctypes.data) == 0
 
-    def update_weight_grid(self):
+    def update_weight_grid(self, force=False):
+        if force:       # the solid SDF was overwritten with set_array
+            self.L.ref_invalidate_weight_grid(self.h)
         self.L.ref_update_weight_grid(self.h)
 
     def sample_velocity(self, pos):

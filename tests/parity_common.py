@@ -46,18 +46,35 @@ def aliased_slots(n):
     return hi, hi - FRAGMENT_ELEMENTS
 
 
+def solid_velocity_field(shapes):
+    """A smooth, nowhere-constant face velocity field for the moving-solid tests: dict(U, V, W) of float32 arrays of the given
+    MAC shapes (k, j, i); every face differs from its neighbours, so an index slip shows."""
+    out = {}
+    for name, (a, b, c, amp) in zip("UVW", ((0.31, 0.17, 0.11, 0.8), (0.13, 0.29, 0.19, 0.6), (0.23, 0.07, 0.37, 0.7))):
+        k, j, i = np.meshgrid(*[np.arange(n) for n in shapes[name]], indexing="ij")
+        out[name] = (amp * np.sin(a * i + b * j + c * k + 0.3)).astype(np.float32)
+    return out
+
+
 def make_pair(scene, tol=None, threads=None, gravity=(0.0, -25.0, 0.0), preconditioner=None, sampling=None, obstacles=(),
-              own_solid=False, settings=None):
+              own_solid=False, settings=None, solid_velocity=False, solid_velocity_early=False):
     """Returns (ref, gpu) engines initialised from the same scene; the GPU engine gets the oracle's
     own static solid SDF and the oracle's LOGICAL particle list.  obstacles: (lo, hi) boxes added to
     the reference with addMeshObstacle (their distances arrive with the oracle's solid SDF); own_solid: the GPU engine builds
-    its solid SDF itself instead (its domain box, and the obstacles through flip_add_obstacle_box)."""
+    its solid SDF itself instead (its domain box, and the obstacles through flip_add_obstacle_box).  solid_velocity: both
+    engines get the face velocities of solid_velocity_field for their solids (the reference in the VelocityDataGrid of its
+    solid SDF, the GPU engine through flip_set_solid_velocity -- before flip_initialize with solid_velocity_early)."""
     ref = refengine.RefEngine(scene["dims"], scene["dx"], scene["pos"], scene["vel"], gravity=gravity, threads=threads, tol=tol)
     for lo, hi in obstacles:
         ref.add_obstacle_box(lo, hi)
     if settings:      # dict(cfl=, picflip=, min_steps=, max_steps=): the step's settings on both engines
         ref.set_step_settings(**settings)
     ref.stage("obstacles", 1.0 / 30.0)   # builds the solid SDF / near-solid grid exactly as the first step would
+    vel = None
+    if solid_velocity:
+        vel = solid_velocity_field({n: ref.shape_of("solid" + n) for n in "UVW"})
+        for n in "UVW":
+            ref.set_array("solid" + n, vel[n])
     I, J, K = scene["dims"]
     gpu = fe.FluidSimulation(I, J, K, scene["dx"])
     gpu.addBodyForce(*gravity)
@@ -80,7 +97,11 @@ def make_pair(scene, tol=None, threads=None, gravity=(0.0, -25.0, 0.0), precondi
             gpu.addMeshObstacleBox(lo, hi)
     else:
         gpu.setSolidSDF(ref.array("solid_phi"))
+    if vel is not None and solid_velocity_early:
+        gpu.setSolidVelocity(vel["U"], vel["V"], vel["W"])
     gpu.initialize()
+    if vel is not None and not solid_velocity_early:
+        gpu.setSolidVelocity(vel["U"], vel["V"], vel["W"])
     gpu.setMarkerParticles(ref.particles())
     return ref, gpu
 
@@ -168,6 +189,14 @@ def lockstep_substep(ref, gpu, dt, isolate=True, report=None):
     cmp_valid("pressure")
     rep["pressure.ref_iterations"] = ref.pcg_iterations
     rep["pressure.ref_error"] = ref.pcg_error
+    if gpu.hasSolidVelocity():
+        # moving solids: the velocities as the enclosed-pocket conditioning left them (pressuresolver.cpp:124-244, in place
+        # in both engines), and the cell-centre weights that multiply them in the divergence
+        for name in "UVW":
+            a, b = gpu.array("solid" + name), ref.array("solid" + name)
+            rep[f"solid.{name}.mismatch"] = int(np.count_nonzero(a != b))
+            rep[f"solid.{name}.zero_faces"] = int(np.count_nonzero(b == 0))
+        rep["solid.weightC.mismatch"] = int(np.count_nonzero(gpu.array("weightC") != ref.array("weightC")))
     if isolate:
         sync_grids()
 
@@ -255,10 +284,10 @@ def developed_scene(scene, frames, preconditioner=None):
 
 
 def lockstep_frames(scene, frames=1, isolate=True, tol=None, threads=None, preconditioner=None, verbose=False,
-                    sampling=None, max_substeps=None, obstacles=(), own_solid=False, settings=None):
+                    sampling=None, max_substeps=None, obstacles=(), own_solid=False, settings=None, solid_velocity=False):
     """max_substeps: stop after that many lock-step substeps in total (the large scenes cost tens of CPU seconds each)."""
     ref, gpu = make_pair(scene, tol=tol, threads=threads, preconditioner=preconditioner, sampling=sampling, obstacles=obstacles,
-                         own_solid=own_solid, settings=settings)
+                         own_solid=own_solid, settings=settings, solid_velocity=solid_velocity)
     reports = []
     for f in range(frames):
         ref.begin_frame(1.0 / 30.0)
@@ -328,6 +357,10 @@ def check_report(rep, dx=0.125, isolate=True, exact_sampling=False):
         assert rep[f"pressure.valid{comp}.hamming"] == 0, rep
     # order-independent stages: bit-exact from identical inputs
     assert rep["sdf.mismatch_cells"] == 0, rep
+    if "solid.weightC.mismatch" in rep:
+        assert rep["solid.weightC.mismatch"] == 0, rep
+        for comp in "UVW":
+            assert rep[f"solid.{comp}.mismatch"] == 0, rep
     if isolate:
         for comp in "UVW":
             assert rep[f"extrapolate_a.{comp}.mismatch"] == 0, rep
