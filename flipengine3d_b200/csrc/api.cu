@@ -110,6 +110,10 @@ static void free_grids(flip_ctx *c) {
     cudaFree(c->frontier[0]); cudaFree(c->frontier[1]);
     cudaFree(c->phiL); cudaFree(c->phiS); cudaFree(c->wU); cudaFree(c->wV); cudaFree(c->wW);
     cudaFree(c->wC); cudaFree(c->solU); cudaFree(c->solV); cudaFree(c->solW); cudaFree(c->pocketFlag);
+    for (int m = 0; m < 3; m++) {
+        cudaFree(c->solidWeightSum[m]); cudaFree(c->solidValid[m]);
+        c->solidWeightSum[m] = nullptr; c->solidValid[m] = nullptr;
+    }
     c->wC = c->solU = c->solV = c->solW = nullptr;
     c->pocketFlag = nullptr;
     for (auto &a : c->p2gAcc) { cudaFree(a); a = nullptr; }
@@ -507,39 +511,131 @@ int flip_add_obstacle_sdf(flip_ctx *c, const float *sdf, int *id) {
     });
 }
 
+// the distances MeshLevelSet computes for a box mesh: exact within the band of solidExactBand cells around the mesh's
+// index box (meshlevelset.cpp:572-601), untouched (here: the largest float) elsewhere
+static void box_obstacle_sdf(const flip_ctx *c, const double lo[3], const double hi[3], std::vector<float> &sdf) {
+    const int n[3] = {c->d.I + 1, c->d.J + 1, c->d.Kg + 1};
+    const double dx = c->d.dx;
+    sdf.assign((size_t)n[0] * n[1] * n[2], std::numeric_limits<float>::max());
+    int a0[3], a1[3];
+    for (int a = 0; a < 3; a++) {
+        a0[a] = std::max(0, (int)floor(lo[a] / dx) - c->solidExactBand);
+        a1[a] = std::min(n[a] - 1, (int)ceil(hi[a] / dx) + c->solidExactBand);
+    }
+    const float cx[3] = {(float)(0.5 * (lo[0] + hi[0])), (float)(0.5 * (lo[1] + hi[1])), (float)(0.5 * (lo[2] + hi[2]))};
+    const float hx[3] = {(float)(0.5 * (hi[0] - lo[0])), (float)(0.5 * (hi[1] - lo[1])), (float)(0.5 * (hi[2] - lo[2]))};
+    for (int k = a0[2]; k <= a1[2]; k++)
+        for (int j = a0[1]; j <= a1[1]; j++)
+            for (int i = a0[0]; i <= a1[0]; i++) {
+                const float p[3] = {(float)(i * dx), (float)(j * dx), (float)(k * dx)};
+                float q[3], out2 = 0.0f, in = -std::numeric_limits<float>::max();
+                for (int a = 0; a < 3; a++) {
+                    q[a] = std::fabs(p[a] - cx[a]) - hx[a];
+                    const float e = std::max(q[a], 0.0f);
+                    out2 += e * e;
+                    in = std::max(in, q[a]);
+                }
+                sdf[(size_t)i + (size_t)n[0] * (j + (size_t)n[1] * k)] = std::sqrt(out2) + std::min(in, 0.0f);
+            }
+}
+
 int flip_add_obstacle_box(flip_ctx *c, const double lo[3], const double hi[3], int *id) {
     return guarded(c, [&] {
-        // the distances MeshLevelSet computes for a box mesh: exact within the band of solidExactBand cells around the
-        // mesh's index box (meshlevelset.cpp:572-601), untouched (here: +inf) elsewhere
-        const int n[3] = {c->d.I + 1, c->d.J + 1, c->d.Kg + 1};
-        const double dx = c->d.dx;
         flip_ctx::Obstacle o;
         o.id = c->nextObstacleId++;
-        o.sdf.assign((size_t)n[0] * n[1] * n[2], std::numeric_limits<float>::max());
-        int a0[3], a1[3];
-        for (int a = 0; a < 3; a++) {
-            a0[a] = std::max(0, (int)floor(lo[a] / dx) - c->solidExactBand);
-            a1[a] = std::min(n[a] - 1, (int)ceil(hi[a] / dx) + c->solidExactBand);
-        }
-        const float cx[3] = {(float)(0.5 * (lo[0] + hi[0])), (float)(0.5 * (lo[1] + hi[1])), (float)(0.5 * (lo[2] + hi[2]))};
-        const float hx[3] = {(float)(0.5 * (hi[0] - lo[0])), (float)(0.5 * (hi[1] - lo[1])), (float)(0.5 * (hi[2] - lo[2]))};
-        for (int k = a0[2]; k <= a1[2]; k++)
-            for (int j = a0[1]; j <= a1[1]; j++)
-                for (int i = a0[0]; i <= a1[0]; i++) {
-                    const float p[3] = {(float)(i * dx), (float)(j * dx), (float)(k * dx)};
-                    float q[3], out2 = 0.0f, in = -std::numeric_limits<float>::max();
-                    for (int a = 0; a < 3; a++) {
-                        q[a] = std::fabs(p[a] - cx[a]) - hx[a];
-                        const float e = std::max(q[a], 0.0f);
-                        out2 += e * e;
-                        in = std::max(in, q[a]);
-                    }
-                    o.sdf[(size_t)i + (size_t)n[0] * (j + (size_t)n[1] * k)] = std::sqrt(out2) + std::min(in, 0.0f);
-                }
+        o.isBox = true;
+        for (int a = 0; a < 3; a++) { o.lo[a] = lo[a]; o.hi[a] = hi[a]; }
+        box_obstacle_sdf(c, lo, hi, o.sdf);
         if (id) *id = o.id;
         c->obstacles.push_back(std::move(o));
         obstacles_changed(c);
     });
+}
+
+// MeshObject::updateMeshAnimated(previous, current, next) (meshobject.cpp:61-95) for a box that translates rigidly: the
+// three meshes are the box of flip_add_obstacle_box moved by the three offsets.  From then on the obstacle stage of every
+// substep (_updateSolidLevelSet, fluidsimulation.cpp:3028-3071, which rebuilds the solid SDF while an animated mesh
+// changes, :3002) places the box at current + t (next - current), t = the part of the frame completed when the substep
+// starts (:2892-2893, MeshObject::getMesh(t) meshobject.cpp:158-177), gives it the velocity
+// ((current - previous) + t ((next - current) - (current - previous))) / frame dt (getVertexVelocities :199-215), and
+// re-derives solid SDF, weights, near-solid mask and the solids' face velocities.
+int flip_set_obstacle_box_motion(flip_ctx *c, int id, const double offPrev[3], const double offCur[3], const double offNext[3]) {
+    return guarded(c, [&] {
+        if (!offPrev || !offCur || !offNext) throw ApiError(FLIP_ERR_RUNTIME, "null offset");
+        if (slab_on(c)) throw ApiError(FLIP_ERR_UNSUPPORTED, "animated obstacles are not supported in a z-slab run");
+        for (auto &o : c->obstacles)
+            if (o.id == id) {
+                if (!o.isBox) throw ApiError(FLIP_ERR_UNSUPPORTED, "only obstacles added with flip_add_obstacle_box can be animated");
+                o.animated = true;
+                for (int a = 0; a < 3; a++) { o.offPrev[a] = offPrev[a]; o.offCur[a] = offCur[a]; o.offNext[a] = offNext[a]; }
+                return;
+            }
+        throw ApiError(FLIP_ERR_RUNTIME, "Error: could not find mesh obstacle.");
+    });
+}
+
+// The obstacle stage with animated obstacles (see flip_set_obstacle_box_motion).  Host work per substep: the SDF of every
+// moving box and the solid fractions of all solids; the device normalises and extrapolates the face velocities.
+static void update_animated_obstacles(flip_ctx *c) {
+    bool any = false;
+    for (auto &o : c->obstacles) any = any || (o.enabled && o.animated);
+    if (!any) {
+        if (c->solidVelFromAnimation) {         // the last animated obstacle was disabled or removed: solids at rest again
+            FLIP_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+            cudaFree(c->solU); cudaFree(c->solV); cudaFree(c->solW);
+            c->solU = c->solV = c->solW = nullptr;
+            c->solidVelFromAnimation = false;
+        }
+        return;
+    }
+    c->solidVelFromAnimation = true;
+    const Dims &d = c->d;
+    // fluidsimulation.cpp:2892-2893 (floats)
+    const float frameTime = (float)(c->frameRemaining + c->substepDt);
+    float t = 1.0f - frameTime / (float)c->frameDt;
+    t = std::fmin(1.0f, std::fmax(0.0f, t));
+    const double invdt = c->frameDt < 1e-10 ? 0.0 : 1.0 / c->frameDt;
+    for (auto &o : c->obstacles) {
+        if (!o.enabled || !o.animated) continue;
+        double lo[3], hi[3];
+        for (int a = 0; a < 3; a++) {
+            // the lower corner vertex of the three meshes as floats, then the reference's float interpolation
+            const float p0 = (float)(o.lo[a] + o.offPrev[a]), p1 = (float)(o.lo[a] + o.offCur[a]), p2 = (float)(o.lo[a] + o.offNext[a]);
+            const float pt = p1 + t * (p2 - p1);
+            const float m1 = p1 - p0, m2 = p2 - p1;
+            o.velocity[a] = (float)((double)(m1 + t * (m2 - m1)) * invdt);
+            lo[a] = pt;
+            hi[a] = (double)pt + (o.hi[a] - o.lo[a]);
+        }
+        box_obstacle_sdf(c, lo, hi, o.sdf);
+    }
+    upload_static_inputs(c);        // merged solid SDF, face weights, near-solid mask (and the centre weights below)
+    // the velocity data of the merged solid SDF: weights of all solids, values of the moving ones
+    std::vector<float> weightSum[3], fieldSum[3];
+    const int n[3] = {d.nU, d.nV, d.nW};
+    for (int m = 0; m < 3; m++) { weightSum[m].assign(n[m], 0.0f); fieldSum[m].assign(n[m], 0.0f); }
+    add_solid_fractions(d, c->hostSolidPhi, nullptr, weightSum, fieldSum);
+    for (auto &o : c->obstacles)
+        if (o.enabled) add_solid_fractions(d, o.sdf, o.animated ? o.velocity : nullptr, weightSum, fieldSum);
+    if (!c->solU) {
+        dev_alloc(c->solU, d.nU); dev_alloc(c->solV, d.nV); dev_alloc(c->solW, d.nW);
+        dev_alloc(c->pocketFlag, d.nC);
+    }
+    float *sol[3] = {c->solU, c->solV, c->solW};
+    for (int m = 0; m < 3; m++) {
+        if (!c->solidWeightSum[m]) { dev_alloc(c->solidWeightSum[m], n[m]); dev_alloc(c->solidValid[m], n[m]); }
+        FLIP_CUDA_CHECK(cudaMemcpy(sol[m], fieldSum[m].data(), sizeof(float) * n[m], cudaMemcpyHostToDevice));
+        FLIP_CUDA_CHECK(cudaMemcpy(c->solidWeightSum[m], weightSum[m].data(), sizeof(float) * n[m], cudaMemcpyHostToDevice));
+    }
+    if (!c->wC) {
+        std::vector<float> phi((size_t)d.nN), wC;
+        FLIP_CUDA_CHECK(cudaMemcpy(phi.data(), c->phiS, sizeof(float) * d.nN, cudaMemcpyDeviceToHost));
+        build_center_weights(d, phi, wC);
+        dev_alloc(c->wC, d.nC);
+        FLIP_CUDA_CHECK(cudaMemcpy(c->wC, wC.data(), sizeof(float) * d.nC, cudaMemcpyHostToDevice));
+    }
+    solid_velocity_normalize_extrapolate(c, 5);      // _numVelocityExtrapolationLayers, meshlevelset.h:364
+    c->stepCounter++;
 }
 
 int flip_enable_obstacle(flip_ctx *c, int id, int on) {
@@ -679,7 +775,10 @@ int flip_begin_substep(flip_ctx *c, double *out) {
 static void run_stage(flip_ctx *c, int stage, double dt) {
     FLIP_CUDA_CHECK(cudaEventRecord(c->evStage[stage], c->stream));
     switch (stage) {
-        case FLIP_STAGE_OBSTACLES: if (c->solidDirty) upload_static_inputs(c); break;     // static solids: only after a change (:2007)
+        case FLIP_STAGE_OBSTACLES:
+            update_animated_obstacles(c);                       // every substep while an animated obstacle is enabled (:3002)
+            if (c->solidDirty) upload_static_inputs(c);         // static solids: only after a change (:2007)
+            break;
         case FLIP_STAGE_LIQUID_SDF: stage_liquid_sdf(c); break;
         case FLIP_STAGE_P2G: stage_p2g(c); break;
         case FLIP_STAGE_EXTRAPOLATE_A: if (c->np_global > 0 || c->npStore > 0) stage_extrapolate(c); break;   // :3262 guards on !empty()

@@ -153,7 +153,20 @@ struct flip_ctx {
     std::vector<float> hostSolidPhi;          // nodal: the domain (built-in box or flip_set_solid_sdf), WITHOUT the obstacles
     // static obstacles (addMeshObstacle, fluidsimulation.cpp:1994): nodal SDFs merged into the solid SDF by minimum
     // (MeshLevelSet::calculateUnion, meshlevelset.cpp:1758-1795)
-    struct Obstacle { int id = 0; bool enabled = true; std::vector<float> sdf; };
+    struct Obstacle {
+        int id = 0;
+        bool enabled = true;
+        std::vector<float> sdf;
+        // a box that moves rigidly (MeshObject::updateMeshAnimated, meshobject.cpp:61-95): the box it was added as and the
+        // translations of the previous, the current and the next frame's mesh against it
+        bool isBox = false, animated = false;
+        double lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+        double offPrev[3] = {0, 0, 0}, offCur[3] = {0, 0, 0}, offNext[3] = {0, 0, 0};
+        float velocity[3] = {0, 0, 0};            // of the substep under way
+    };
+    bool solidVelFromAnimation = false;       // solU/V/W are rebuilt every substep from the animated obstacles
+    float *solidWeightSum[3] = {nullptr, nullptr, nullptr};    // device: summed solid fractions of the faces (U, V, W)
+    unsigned char *solidValid[3] = {nullptr, nullptr, nullptr}; // device: faces whose solid velocity is defined
     std::vector<Obstacle> obstacles;
     int nextObstacleId = 1;
     bool solidDirty = false;                  // obstacles changed after initialize: re-derived at the next substep (:2007)
@@ -254,6 +267,8 @@ void build_box_solid_sdf(const Dims &d, std::vector<float> &phi);
 void build_weights(const Dims &d, const std::vector<float> &phi, std::vector<float> &wU, std::vector<float> &wV,
                    std::vector<float> &wW, std::vector<float> &wC);
 void build_center_weights(const Dims &d, const std::vector<float> &phi, std::vector<float> &wC);
+void add_solid_fractions(const Dims &d, const std::vector<float> &phi, const float velocity[3], std::vector<float> weightSum[3],
+                         std::vector<float> fieldSum[3]);
 void build_near_solid(const Dims &d, const std::vector<float> &phi, int factor, int band, double cfl,
                       std::vector<unsigned char> &grid, int &gi, int &gj, int &gk);
 
@@ -288,6 +303,7 @@ void stage_extrapolate(flip_ctx *c);
 void stage_save(flip_ctx *c);
 void stage_body_force(flip_ctx *c, double dt);
 void stage_constrain(flip_ctx *c);
+void solid_velocity_normalize_extrapolate(flip_ctx *c, int layers);
 
 // pressure.cu
 void pressure_alloc(flip_ctx *c);

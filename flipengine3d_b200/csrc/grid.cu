@@ -219,14 +219,42 @@ __global__ void __launch_bounds__(TPB) k_ext_layer(ExtArgs A, int layer) {
 }
 
 // MACVelocityField::extrapolateVelocityField  macvelocityfield.cpp:671-677
+static void extrapolate_fields(flip_ctx *c, float *const grids[3], const unsigned char *const valids[3], int layers, bool timed);
 void stage_extrapolate(flip_ctx *c) {
-    const Dims &d = c->d;
-    cudaStream_t st = c->stream;
-    size_t kt = kt_begin(c);
-    const size_t nmax = ext_stride(d);   // per-component stride of the scratch arrays
-    ExtArgs A;
     float *grids[3] = {c->U, c->V, c->W};
     const unsigned char *valids[3] = {c->validU, c->validV, c->validW};
+    extrapolate_fields(c, grids, valids, c->extrapolationLayers, true);
+}
+
+// The velocity data of the solid SDF after all solids were merged (MeshLevelSet::normalizeVelocityGrid, meshlevelset.cpp:
+// 640-702, _normalizeVelocityGridThread :1738-1756): value / weight where the summed weight exceeds 1e-6 (those faces are
+// valid), 0 elsewhere, then extrapolated over `layers` (5, meshlevelset.h:364) layers with the same routine as the fluid.
+__global__ void k_solid_normalize(float *__restrict__ field, const float *__restrict__ weight, unsigned char *__restrict__ valid, int n) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const float w = weight[t];
+    const bool ok = w > 1e-6f;
+    field[t] = ok ? __fdiv_rn(field[t], w) : 0.0f;
+    valid[t] = ok ? 1 : 0;
+}
+void solid_velocity_normalize_extrapolate(flip_ctx *c, int layers) {
+    const Dims &d = c->d;
+    float *grids[3] = {c->solU, c->solV, c->solW};
+    const int n[3] = {d.nU, d.nV, d.nW};
+    for (int m = 0; m < 3; m++) {
+        k_solid_normalize<<<cdiv(n[m], TPB), TPB, 0, c->stream>>>(grids[m], c->solidWeightSum[m], c->solidValid[m], n[m]);
+        c->launches++;
+    }
+    const unsigned char *valids[3] = {c->solidValid[0], c->solidValid[1], c->solidValid[2]};
+    extrapolate_fields(c, grids, valids, layers, false);
+}
+
+static void extrapolate_fields(flip_ctx *c, float *const grids[3], const unsigned char *const valids[3], int layers, bool timed) {
+    const Dims &d = c->d;
+    cudaStream_t st = c->stream;
+    size_t kt = timed ? kt_begin(c) : 0;
+    const size_t nmax = ext_stride(d);   // per-component stride of the scratch arrays
+    ExtArgs A;
     const int gi[3] = {d.I + 1, d.I, d.I}, gj[3] = {d.J, d.J + 1, d.J}, gk[3] = {d.K, d.K, d.K + 1};
     long long nbig = 0;
     for (int m = 0; m < 3; m++) {
@@ -242,23 +270,23 @@ void stage_extrapolate(flip_ctx *c) {
     if (trace) {
         for (int m = 0; m < 3; m++) {
             fprintf(stderr, "ext comp %d:", m);
-            for (int l = 0; l <= c->extrapolationLayers; l++) fprintf(stderr, " %d", c->hS->extCount[(EXT_MAX_LAYERS + 1) * m + l]);
+            for (int l = 0; l <= layers; l++) fprintf(stderr, " %d", c->hS->extCount[(EXT_MAX_LAYERS + 1) * m + l]);
             fprintf(stderr, "\n");
         }
     }
-    if (c->extrapolationLayers > EXT_MAX_LAYERS) throw ApiError(FLIP_ERR_UNSUPPORTED, "more than 31 extrapolation layers (CFL > 29)");
+    if (layers > EXT_MAX_LAYERS) throw ApiError(FLIP_ERR_UNSUPPORTED, "more than 31 extrapolation layers (CFL > 29)");
     FLIP_CUDA_CHECK(cudaMemsetAsync(c->dS->extCount, 0, sizeof(c->dS->extCount), st));
     if (d.I >= 17) k_ext_init<<<dim3(cdiv(cdiv(nbig, 16), TPB), 3), TPB, 0, st>>>(A);
     else k_ext_init_small<<<dim3(cdiv(nbig, TPB), 3), TPB, 0, st>>>(A);
     c->launches++;
     // frontier sizes live on the device; launches use a fixed grid with a grid-stride loop
     const dim3 blocks(148 * 8, 3);
-    for (int layer = 1; layer <= c->extrapolationLayers; layer++) {
+    for (int layer = 1; layer <= layers; layer++) {
         k_ext_layer<<<blocks, TPB, 0, st>>>(A, layer);
         c->launches++;
     }
     FLIP_CUDA_CHECK(cudaGetLastError());
-    kt_end(c, FLIP_KERNEL_EXTRAPOLATE, kt);
+    if (timed) kt_end(c, FLIP_KERNEL_EXTRAPOLATE, kt);
 }
 
 // ------------------------------------------------------------------------------------------------

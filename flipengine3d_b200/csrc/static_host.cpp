@@ -216,6 +216,34 @@ void build_weights(const Dims &d, const std::vector<float> &phi, std::vector<flo
                 wW[idx] = clamp01(1.0f - negative_area(P(i, j, k), P(i, j + 1, k), P(i + 1, j, k), P(i + 1, j + 1, k)));
 }
 
+// What one solid adds to the velocity data of the solid SDF (MeshLevelSet::_computeVelocityGridThread, meshlevelset.cpp:
+// 1319-1372, summed by calculateUnion :1797-1828): on every face its solid fraction (getFaceWeightU/V/W of ITS OWN signed
+// distance field, :357-387) as weight and fraction x velocity as value.  phi: the solid's nodal field on this grid;
+// velocity: the velocity of a rigidly translating solid (null: at rest -- the domain walls and static obstacles add
+// weight only).
+void add_solid_fractions(const Dims &d, const std::vector<float> &phi, const float velocity[3], std::vector<float> weightSum[3],
+                         std::vector<float> fieldSum[3]) {
+    const int ni = d.I + 1, nj = d.J + 1;
+    auto P = [&](int i, int j, int k) { return phi[(size_t)i + (size_t)ni * ((size_t)j + (size_t)nj * k)]; };
+    auto add = [&](int comp, size_t idx, float fraction) {
+        if (!(fraction > 0.0f)) return;
+        weightSum[comp][idx] += fraction;
+        if (velocity) fieldSum[comp][idx] += fraction * velocity[comp];
+    };
+    size_t idx = 0;
+    for (int k = 0; k < d.K; k++)
+        for (int j = 0; j < d.J; j++)
+            for (int i = 0; i <= d.I; i++, idx++) add(0, idx, negative_area(P(i, j, k), P(i, j + 1, k), P(i, j, k + 1), P(i, j + 1, k + 1)));
+    idx = 0;
+    for (int k = 0; k < d.K; k++)
+        for (int j = 0; j <= d.J; j++)
+            for (int i = 0; i < d.I; i++, idx++) add(1, idx, negative_area(P(i, j, k), P(i, j, k + 1), P(i + 1, j, k), P(i + 1, j, k + 1)));
+    idx = 0;
+    for (int k = 0; k <= d.K; k++)
+        for (int j = 0; j < d.J; j++)
+            for (int i = 0; i < d.I; i++, idx++) add(2, idx, negative_area(P(i, j, k), P(i, j + 1, k), P(i + 1, j, k), P(i + 1, j + 1, k)));
+}
+
 // FluidSimulation::_updateNearSolidGrid (fluidsimulation.cpp:3083-3127): coarse cells (3dx) holding a
 // node with |phi_solid| < 3dx, dilated ceil(CFL/3) times with the 6-neighbourhood (GridUtils::featherGrid6).
 void build_near_solid(const Dims &d, const std::vector<float> &phi, int factor, int band, double cfl,

@@ -106,6 +106,7 @@ def load_library():
     L.flip_static_inputs.argtypes = [ci, ci, ci, C.c_double, vp, ci, vp, vp, vp, vp, C.POINTER(ci)]
     L.flip_center_weights.argtypes = [ci, ci, ci, C.c_double, vp, vp]
     L.flip_set_solid_velocity.argtypes = [vp, vp, vp, vp]
+    L.flip_set_obstacle_box_motion.argtypes = [vp, ci, C.POINTER(cd), C.POINTER(cd), C.POINTER(cd)]
     L.flip_get_num_substeps.argtypes = [vp, C.POINTER(ci)]
     L.flip_get_step_stats.argtypes = [vp, ci, C.POINTER(StepStats)]
     L.flip_get_num_particles.argtypes = [vp, C.POINTER(ci)]
@@ -364,6 +365,13 @@ class FluidSimulation:
         for x, name in zip(a, ("solidU", "solidV", "solidW")):
             assert x.shape == self.shape_of(name), (name, x.shape)
         self._check(self.L.flip_set_solid_velocity(self.h, a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data))
+        self._solid_velocity = True
+
+    def setMeshObstacleBoxMotion(self, oid, off_prev, off_cur, off_next):
+        """MeshObject::updateMeshAnimated for a box obstacle that translates: the offsets of the previous, the current and
+        the next frame's mesh against the box it was added as (call once per frame, before update)."""
+        d3 = C.c_double * 3
+        self._check(self.L.flip_set_obstacle_box_motion(self.h, int(oid), d3(*off_prev), d3(*off_cur), d3(*off_next)))
         self._solid_velocity = True
 
     def hasSolidVelocity(self):

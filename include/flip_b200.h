@@ -214,6 +214,23 @@ int flip_remove_obstacle(flip_ctx *ctx, int id);
  * The SDF of a moving solid itself is the caller's (flip_add_obstacle_sdf / flip_enable_obstacle / flip_remove_obstacle per
  * substep, or flip_set_solid_sdf before flip_initialize).  Not available in a z-slab run (FLIP_ERR_UNSUPPORTED). */
 int flip_set_solid_velocity(flip_ctx *ctx, const float *U, const float *V, const float *W);
+/* Animated obstacles, rigid translation of a box: MeshObject::updateMeshAnimated(previous, current, next)
+ * (meshobject.cpp:61-95) for an obstacle added with flip_add_obstacle_box -- the three meshes are that box moved by the
+ * three offsets; call it once per frame before flip_update, as the reference's callers do.  While such an obstacle is
+ * enabled, the obstacle stage of EVERY substep (_updateSolidLevelSet fluidsimulation.cpp:3028-3071 rebuilds the solid SDF
+ * while an animated mesh changes, :3002) places the box at current + t (next - current) with t the part of the frame
+ * completed at the start of the substep (:2892-2893; MeshObject::getMesh(t) meshobject.cpp:158-177), gives it the
+ * velocity ((current - previous) + t ((next - current) - (current - previous))) / frame dt (getVertexVelocities
+ * :199-215), re-derives solid SDF, face / centre weights and near-solid mask, and builds the solids' face velocities the
+ * way the merged MeshLevelSet does: per face the sum over solids of solid fraction x velocity divided by the summed
+ * solid fractions where that exceeds 1e-6 (_computeVelocityGridThread meshlevelset.cpp:1319-1372, calculateUnion
+ * :1797-1828, _normalizeVelocityGridThread :1738-1756), then 5 layers of extrapolation (:697, the fluid's routine, on
+ * the device).  The per-substep SDF and the solid fractions are HOST work (as in the reference); divergence,
+ * conditioning, constraint and extrapolation run on the device (flip_set_solid_velocity describes them; the arrays it
+ * would set are overwritten every substep while an animated obstacle is enabled).  General animated meshes: rebuild their
+ * SDF with flip_mesh_sdf and hand over SDF and velocities yourself.  Not available in a z-slab run. */
+int flip_set_obstacle_box_motion(flip_ctx *ctx, int id, const double offset_prev[3], const double offset_cur[3],
+                                 const double offset_next[3]);
 /* The cell-centre weights of a nodal solid SDF, computed on the HOST exactly as the library computes them (no CUDA device
  * needed): phi (I+1)(J+1)(K+1) floats in, wC IJK floats out. */
 int flip_center_weights(int isize, int jsize, int ksize, double dx, const float *phi_nodal, float *wC);

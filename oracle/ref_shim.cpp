@@ -530,6 +530,27 @@ int ref_add_obstacle_box(void *p, const double lo[3], const double hi[3]) {
     });
     return idx;
 }
+/* MeshObject::updateMeshAnimated (meshobject.cpp:61-95) for obstacle `idx`: the box [lo,hi] moved by the three offsets as
+ * the previous, current and next frame's mesh (call once per frame, before update / the stage-wise step). */
+static TriangleMesh boxMesh(const double lo[3], const double hi[3], const double off[3]) {
+    vmath::vec3 q((float)(lo[0] + off[0]), (float)(lo[1] + off[1]), (float)(lo[2] + off[2]));
+    const double w = hi[0] - lo[0], ht = hi[1] - lo[1], d = hi[2] - lo[2];
+    TriangleMesh m;
+    m.vertices = {vmath::vec3(q.x, q.y, q.z), vmath::vec3(q.x + w, q.y, q.z), vmath::vec3(q.x + w, q.y, q.z + d),
+                  vmath::vec3(q.x, q.y, q.z + d), vmath::vec3(q.x, q.y + ht, q.z), vmath::vec3(q.x + w, q.y + ht, q.z),
+                  vmath::vec3(q.x + w, q.y + ht, q.z + d), vmath::vec3(q.x, q.y + ht, q.z + d)};
+    m.triangles = {Triangle(0, 1, 2), Triangle(0, 2, 3), Triangle(4, 7, 6), Triangle(4, 6, 5), Triangle(0, 3, 7), Triangle(0, 7, 4),
+                   Triangle(1, 5, 6), Triangle(1, 6, 2), Triangle(0, 4, 5), Triangle(0, 5, 1), Triangle(3, 2, 6), Triangle(3, 6, 7)};
+    return m;
+}
+int ref_animate_obstacle_box(void *p, int idx, const double lo[3], const double hi[3], const double offPrev[3],
+                             const double offCur[3], const double offNext[3]) {
+    RefSim *h = (RefSim *)p;
+    return guarded(h, [&] {
+        if (idx < 0 || idx >= (int)h->obstacles.size() || !h->obstacles[idx]) throw std::runtime_error("no such obstacle");
+        h->obstacles[idx]->updateMeshAnimated(boxMesh(lo, hi, offPrev), boxMesh(lo, hi, offCur), boxMesh(lo, hi, offNext));
+    });
+}
 int ref_remove_obstacle(void *p, int idx) {
     RefSim *h = (RefSim *)p;
     return guarded(h, [&] {

@@ -79,6 +79,7 @@ def _load(kind):
     L.ref_set_marker_particle_scale.argtypes = [C.c_void_p, C.c_double]
     L.ref_add_obstacle_box.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.ref_remove_obstacle.argtypes = [C.c_void_p, C.c_int]
+    L.ref_animate_obstacle_box.argtypes = [C.c_void_p, C.c_int] + [C.POINTER(C.c_double)] * 5
     L.ref_constrain_fluid_source_velocity.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.ref_isomesh.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.ref_get_isomesh.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -255,6 +256,11 @@ class RefEngine:
         idx = self.L.ref_add_obstacle_box(self.h, a, b)
         assert idx >= 0, self.L.ref_last_error(self.h)
         return idx
+
+    def animate_obstacle_box(self, idx, lo, hi, off_prev, off_cur, off_next):
+        """MeshObject::updateMeshAnimated with the box [lo,hi] moved by the three offsets (previous / current / next frame)."""
+        d3 = C.c_double * 3
+        self._check(self.L.ref_animate_obstacle_box(self.h, int(idx), d3(*lo), d3(*hi), d3(*off_prev), d3(*off_cur), d3(*off_next)))
 
     def remove_obstacle(self, idx):
         self._check(self.L.ref_remove_obstacle(self.h, int(idx)))
