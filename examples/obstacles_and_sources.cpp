@@ -80,6 +80,24 @@ int main(int argc, char **argv) {
         sim.removeMeshObstacle(&ramp);
         sim.update(1.0 / 30.0);
         printf("done: %d frames, peak %d particles, final %d\n", frames, peak, sim.getNumMarkerParticles());
+        // an animated obstacle (MeshObject::updateMeshAnimated once per frame): a plate that sweeps along the floor
+        MeshObject plate(n, n, n, dx);
+        const vmath::vec3 p0(0.12f * L, 0.04f * L, 0.2f * L);
+        const float stepx = 0.012f * L;
+        auto plateAt = [&](int f) { return boxMesh(vmath::vec3(p0.x + stepx * f, p0.y, p0.z), 0.06f * L, 0.25f * L, 0.6f * L); };
+        plate.updateMeshAnimated(plateAt(-1), plateAt(0), plateAt(1));
+        sim.addMeshObstacle(&plate);
+        for (int f = 0; f < 12; f++) {
+            plate.updateMeshAnimated(plateAt(f - 1), plateAt(f), plateAt(f + 1));
+            sim.update(1.0 / 30.0);
+        }
+        int inPlate = 0;
+        for (const auto &mp : sim.getMarkerParticles()) {
+            const vmath::vec3 p = mp.position;
+            if (p.x > p0.x + stepx * 12 + 0.5f * dx && p.x < p0.x + stepx * 12 + 0.06f * L - 0.5f * dx && p.y > p0.y + 0.5f * dx &&
+                p.y < p0.y + 0.25f * L - 0.5f * dx && p.z > p0.z + 0.5f * dx && p.z < p0.z + 0.6f * L - 0.5f * dx) inPlate++;
+        }
+        printf("animated plate: 12 frames, particles %d, inside plate %d\n", sim.getNumMarkerParticles(), inPlate);
     } catch (const std::exception &e) {
         fprintf(stderr, "error: %s\n", e.what());
         return strstr(e.what(), "no CUDA device") ? 2 : 1;

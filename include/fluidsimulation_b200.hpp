@@ -82,13 +82,29 @@ public:
     MeshObject() = default;
     MeshObject(int isize, int jsize, int ksize, double dx) : _isize(isize), _jsize(jsize), _ksize(ksize), _dx(dx) {}
     void getGridDimensions(int *i, int *j, int *k) const { *i = _isize; *j = _jsize; *k = _ksize; }
-    void updateMeshStatic(TriangleMesh meshCurrent) { _mesh = std::move(meshCurrent); }
+    void updateMeshStatic(TriangleMesh meshCurrent) { _mesh = std::move(meshCurrent); _animated = false; }
+    // MeshObject::updateMeshAnimated (meshobject.cpp:61-95), once per frame before update(): the previous, the current and
+    // the next frame's mesh.  Supported: an axis-aligned box that translates rigidly (flip_set_obstacle_box_motion);
+    // anything else throws.  May be called before or after addMeshObstacle.
+    void updateMeshAnimated(TriangleMesh meshPrevious, TriangleMesh meshCurrent, TriangleMesh meshNext) {
+        MeshObject prev(_isize, _jsize, _ksize, _dx), next(_isize, _jsize, _ksize, _dx);
+        prev._mesh = std::move(meshPrevious);
+        next._mesh = std::move(meshNext);
+        _mesh = std::move(meshCurrent);
+        if (!isAxisAlignedBox() || !prev.isAxisAlignedBox() || !next.isAxisAlignedBox())
+            throw std::runtime_error("Error: animated mesh objects are supported for rigidly translating axis-aligned boxes only.\n");
+        vmath::vec3 lo, hi, plo, phi, nlo, nhi;
+        bounds(lo, hi); prev.bounds(plo, phi); next.bounds(nlo, nhi);
+        for (int a = 0; a < 3; a++) { _curLo[a] = (&lo.x)[a]; _prevLo[a] = (&plo.x)[a]; _nextLo[a] = (&nlo.x)[a]; }
+        _animated = true;
+        pushMotion();
+    }
     TriangleMesh getMesh() const { return _mesh; }
     // MeshObject::enable / disable / isEnabled (meshobject.cpp:267-283): acts on the device once the object is an obstacle
     void enable() { _enabled = true; if (_ctx) flip_enable_obstacle(_ctx, _obstacleId, 1); }
     void disable() { _enabled = false; if (_ctx) flip_enable_obstacle(_ctx, _obstacleId, 0); }
     bool isEnabled() const { return _enabled; }
-    bool isAnimated() const { return false; }       // static meshes only (updateMeshStatic)
+    bool isAnimated() const { return _animated; }
 
     void bounds(vmath::vec3 &lo, vmath::vec3 &hi) const {
         lo = vmath::vec3(1e30f, 1e30f, 1e30f); hi = vmath::vec3(-1e30f, -1e30f, -1e30f);
@@ -129,6 +145,15 @@ private:
     bool _enabled = true;
     flip_ctx *_ctx = nullptr;     // the simulation this object is an obstacle of
     int _obstacleId = 0;
+    bool _animated = false;
+    double _baseLo[3] = {0, 0, 0};                     // lower corner of the box the obstacle was added as
+    double _prevLo[3] = {0, 0, 0}, _curLo[3] = {0, 0, 0}, _nextLo[3] = {0, 0, 0};
+    void pushMotion() {
+        if (!_ctx || !_animated) return;
+        double a[3], b[3], c[3];
+        for (int q = 0; q < 3; q++) { a[q] = _prevLo[q] - _baseLo[q]; b[q] = _curLo[q] - _baseLo[q]; c[q] = _nextLo[q] - _baseLo[q]; }
+        if (flip_set_obstacle_box_motion(_ctx, _obstacleId, a, b, c) != FLIP_OK) throw std::runtime_error(flip_last_error(_ctx));
+    }
 };
 
 // MeshFluidSource (meshfluidsource.h:40-117) for static closed meshes: an inflow that emits at the end of every substep
@@ -285,6 +310,7 @@ public:
             obstacle->bounds(lo, hi);
             const double l[3] = {lo.x, lo.y, lo.z}, h[3] = {hi.x, hi.y, hi.z};
             check(flip_add_obstacle_box(_c, l, h, &id));
+            for (int a = 0; a < 3; a++) obstacle->_baseLo[a] = l[a];
         } else {
             std::vector<float> phi;
             int clo[3], chi[3];
@@ -292,6 +318,7 @@ public:
             check(flip_add_obstacle_sdf(_c, phi.data(), &id));
         }
         obstacle->_ctx = _c; obstacle->_obstacleId = id;
+        obstacle->pushMotion();                                    // an animation set before the object was added
         _obstacles.push_back(obstacle);
         if (!obstacle->isEnabled()) check(flip_enable_obstacle(_c, id, 0));
     }

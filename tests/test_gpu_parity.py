@@ -266,8 +266,8 @@ def test_fluidmanager_scene_headless_through_the_cpp_facade():
 
 def test_obstacles_and_sources_through_the_cpp_facade():
     """examples/obstacles_and_sources.cpp: a wedge (general closed mesh -> host signed distance field) and a box as
-    static obstacles, an inflow and an outflow MeshFluidSource, MeshObject::disable and removeMeshObstacle at run time,
-    all through include/fluidsimulation_b200.hpp.  The inflow keeps emitting, nothing ends up deep inside an enabled
+    static obstacles, an inflow and an outflow MeshFluidSource, MeshObject::disable and removeMeshObstacle at run time, then
+    an animated plate (MeshObject::updateMeshAnimated every frame), all through include/fluidsimulation_b200.hpp.  The inflow keeps emitting, nothing ends up deep inside an enabled
     obstacle, the outflow keeps the count bounded."""
     import re
     import subprocess
@@ -286,6 +286,9 @@ def test_obstacles_and_sources_through_the_cpp_facade():
             assert int(in_block) == 0, rows                                  # the block, while it is enabled
     m = re.search(r"done: 40 frames, peak (\d+) particles, final (\d+)", r.stdout)
     assert m and int(m.group(2)) > 0, r.stdout[-500:]
+    # the epilogue: a plate animated with MeshObject::updateMeshAnimated sweeps along the floor; nothing stays inside it
+    m = re.search(r"animated plate: 12 frames, particles (\d+), inside plate (\d+)", r.stdout)
+    assert m and int(m.group(1)) > 0 and int(m.group(2)) <= 5, r.stdout[-500:]
 
 
 def test_update_before_initialize_raises_runtime_error():
