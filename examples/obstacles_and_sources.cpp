@@ -87,8 +87,14 @@ int main(int argc, char **argv) {
         auto plateAt = [&](int f) { return boxMesh(vmath::vec3(p0.x + stepx * f, p0.y, p0.z), 0.06f * L, 0.25f * L, 0.6f * L); };
         plate.updateMeshAnimated(plateAt(-1), plateAt(0), plateAt(1));
         sim.addMeshObstacle(&plate);
+        // ... and a general animated mesh: a wedge that rises out of the floor (per-vertex velocities)
+        MeshObject lift(n, n, n, dx);
+        auto liftAt = [&](int f) { return wedgeMesh(vmath::vec3(0.55f * L, 0.02f * L + 0.006f * L * f, 0.25f * L), 0.2f * L, 0.12f * L, 0.5f * L); };
+        lift.updateMeshAnimated(liftAt(-1), liftAt(0), liftAt(1));
+        sim.addMeshObstacle(&lift);
         for (int f = 0; f < 12; f++) {
             plate.updateMeshAnimated(plateAt(f - 1), plateAt(f), plateAt(f + 1));
+            lift.updateMeshAnimated(liftAt(f - 1), liftAt(f), liftAt(f + 1));
             sim.update(1.0 / 30.0);
         }
         int inPlate = 0;

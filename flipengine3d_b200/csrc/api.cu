@@ -574,6 +574,50 @@ int flip_set_obstacle_box_motion(flip_ctx *c, int id, const double offPrev[3], c
     });
 }
 
+// FluidSimulation::addMeshObstacle with a closed triangle mesh the library keeps (so that it can be animated):
+// vertices as xyz triplets, triangles as vertex index triplets.  Static until flip_set_obstacle_mesh_motion is called.
+int flip_add_obstacle_mesh(flip_ctx *c, const float *vertices, int numVertices, const int *triangles, int numTriangles, int *id) {
+    return guarded(c, [&] {
+        if (!vertices || !triangles || numVertices <= 0 || numTriangles <= 0) throw ApiError(FLIP_ERR_RUNTIME, "empty mesh");
+        flip_ctx::Obstacle o;
+        o.id = c->nextObstacleId++;
+        o.isMesh = true;
+        o.vertsCur.assign(vertices, vertices + 3 * (size_t)numVertices);
+        o.vertsPrev = o.vertsCur;
+        o.vertsNext = o.vertsCur;
+        o.triangles.assign(triangles, triangles + 3 * (size_t)numTriangles);
+        o.sdf.resize((size_t)(c->d.I + 1) * (c->d.J + 1) * (c->d.Kg + 1));
+        const int rc = flip_mesh_sdf(c->d.I, c->d.J, c->d.Kg, c->d.dx, vertices, numVertices, triangles, numTriangles, c->solidExactBand,
+                                     std::numeric_limits<float>::max(), o.sdf.data(), nullptr, nullptr);
+        if (rc != FLIP_OK) throw ApiError(rc, "bad triangle mesh");
+        if (id) *id = o.id;
+        c->obstacles.push_back(std::move(o));
+        obstacles_changed(c);
+    });
+}
+
+// MeshObject::updateMeshAnimated(previous, current, next) (meshobject.cpp:61-95) for an obstacle added with
+// flip_add_obstacle_mesh: the vertices of the three frames (same count and order: fixed topology).  Per substep the mesh
+// stands at current + t (next - current) and vertex v moves with ((cur - prev)_v + t ((next - cur)_v - (cur - prev)_v)) /
+// frame dt; the solids' face velocities take the velocity of the nearest surface point (flip::mesh_velocity_data).
+int flip_set_obstacle_mesh_motion(flip_ctx *c, int id, const float *prev, const float *cur, const float *next) {
+    return guarded(c, [&] {
+        if (!prev || !cur || !next) throw ApiError(FLIP_ERR_RUNTIME, "null vertex array");
+        if (slab_on(c)) throw ApiError(FLIP_ERR_UNSUPPORTED, "animated obstacles are not supported in a z-slab run");
+        for (auto &o : c->obstacles)
+            if (o.id == id) {
+                if (!o.isMesh) throw ApiError(FLIP_ERR_UNSUPPORTED, "only obstacles added with flip_add_obstacle_mesh take vertex animations");
+                const size_t n = o.vertsCur.size();
+                o.vertsPrev.assign(prev, prev + n);
+                o.vertsCur.assign(cur, cur + n);
+                o.vertsNext.assign(next, next + n);
+                o.animated = true;
+                return;
+            }
+        throw ApiError(FLIP_ERR_RUNTIME, "Error: could not find mesh obstacle.");
+    });
+}
+
 // The obstacle stage with animated obstacles (see flip_set_obstacle_box_motion).  Host work per substep: the SDF of every
 // moving box and the solid fractions of all solids; the device normalises and extrapolates the face velocities.
 static void update_animated_obstacles(flip_ctx *c) {
@@ -595,8 +639,28 @@ static void update_animated_obstacles(flip_ctx *c) {
     float t = 1.0f - frameTime / (float)c->frameDt;
     t = std::fmin(1.0f, std::fmax(0.0f, t));
     const double invdt = c->frameDt < 1e-10 ? 0.0 : 1.0 / c->frameDt;
+    // per moving mesh: its solid fractions and fraction x nearest-surface velocity on every face
+    struct MeshData { const flip_ctx::Obstacle *o; std::vector<float> fraction[3], field[3]; };
+    std::vector<MeshData> meshData;
     for (auto &o : c->obstacles) {
-        if (!o.enabled || !o.animated) continue;
+        if (!o.enabled || !o.animated || !o.isMesh) continue;
+        const size_t n3 = o.vertsCur.size();
+        std::vector<float> vt(n3), vel(n3);
+        for (size_t q = 0; q < n3; q++) {
+            const float p0 = o.vertsPrev[q], p1 = o.vertsCur[q], p2 = o.vertsNext[q];
+            vt[q] = p1 + t * (p2 - p1);
+            const float m1 = p1 - p0, m2 = p2 - p1;
+            vel[q] = (float)((double)(m1 + t * (m2 - m1)) * invdt);
+        }
+        meshData.emplace_back();
+        meshData.back().o = &o;
+        const int rc = mesh_velocity_data(d, vt.data(), (int)(n3 / 3), o.triangles.data(), (int)(o.triangles.size() / 3), vel.data(),
+                                          c->solidExactBand, std::numeric_limits<float>::max(), o.sdf, meshData.back().fraction,
+                                          meshData.back().field);
+        if (rc != FLIP_OK) throw ApiError(rc, "bad animated triangle mesh");
+    }
+    for (auto &o : c->obstacles) {
+        if (!o.enabled || !o.animated || o.isMesh) continue;
         double lo[3], hi[3];
         for (int a = 0; a < 3; a++) {
             // the lower corner vertex of the three meshes as floats, then the reference's float interpolation
@@ -616,7 +680,10 @@ static void update_animated_obstacles(flip_ctx *c) {
     for (int m = 0; m < 3; m++) { weightSum[m].assign(n[m], 0.0f); fieldSum[m].assign(n[m], 0.0f); }
     add_solid_fractions(d, c->hostSolidPhi, nullptr, weightSum, fieldSum);
     for (auto &o : c->obstacles)
-        if (o.enabled) add_solid_fractions(d, o.sdf, o.animated ? o.velocity : nullptr, weightSum, fieldSum);
+        if (o.enabled && !(o.animated && o.isMesh)) add_solid_fractions(d, o.sdf, o.animated ? o.velocity : nullptr, weightSum, fieldSum);
+    for (auto &md : meshData)
+        for (int m = 0; m < 3; m++)
+            for (int q = 0; q < n[m]; q++) { weightSum[m][q] += md.fraction[m][q]; fieldSum[m][q] += md.field[m][q]; }
     if (!c->solU) {
         dev_alloc(c->solU, d.nU); dev_alloc(c->solV, d.nV); dev_alloc(c->solW, d.nW);
         dev_alloc(c->pocketFlag, d.nC);

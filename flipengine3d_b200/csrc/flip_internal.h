@@ -163,6 +163,10 @@ struct flip_ctx {
         double lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
         double offPrev[3] = {0, 0, 0}, offCur[3] = {0, 0, 0}, offNext[3] = {0, 0, 0};
         float velocity[3] = {0, 0, 0};            // of the substep under way
+        // a closed triangle mesh that moves (rigidly or deforming, fixed topology): the three frames' vertices
+        bool isMesh = false;
+        std::vector<int> triangles;
+        std::vector<float> vertsPrev, vertsCur, vertsNext;        // xyz triplets
     };
     bool solidVelFromAnimation = false;       // solU/V/W are rebuilt every substep from the animated obstacles
     float *solidWeightSum[3] = {nullptr, nullptr, nullptr};    // device: summed solid fractions of the faces (U, V, W)
@@ -267,6 +271,9 @@ void build_box_solid_sdf(const Dims &d, std::vector<float> &phi);
 void build_weights(const Dims &d, const std::vector<float> &phi, std::vector<float> &wU, std::vector<float> &wV,
                    std::vector<float> &wW, std::vector<float> &wC);
 void build_center_weights(const Dims &d, const std::vector<float> &phi, std::vector<float> &wC);
+int mesh_velocity_data(const Dims &d, const float *vertices_xyz, int num_vertices, const int *triangles, int num_triangles,
+                       const float *vertex_velocities_xyz, int band, float far_value, std::vector<float> &phi,
+                       std::vector<float> fraction[3], std::vector<float> field[3]);
 void add_solid_fractions(const Dims &d, const std::vector<float> &phi, const float velocity[3], std::vector<float> weightSum[3],
                          std::vector<float> fieldSum[3]);
 void build_near_solid(const Dims &d, const std::vector<float> &phi, int factor, int band, double cfl,

@@ -318,15 +318,18 @@ float point_triangle_dist2(V3 p, V3 a, V3 b, V3 c) {
 }
 }  // namespace
 
-extern "C" int flip_mesh_sdf(int isize, int jsize, int ksize, double dx, const float *vertices_xyz, int num_vertices,
-                             const int *triangles, int num_triangles, int band, float far_value, float *phi, int cell_lo[3],
-                             int cell_hi[3]) {
+// closest: (may be null) per node the triangle that gave the distance, -1 where none lies within the band -- what
+// MeshLevelSet::_closestTriangles holds after the exact-band pass.
+static int mesh_sdf_impl(int isize, int jsize, int ksize, double dx, const float *vertices_xyz, int num_vertices,
+                         const int *triangles, int num_triangles, int band, float far_value, float *phi, int cell_lo[3],
+                         int cell_hi[3], int *closest) {
     if (isize <= 0 || jsize <= 0 || ksize <= 0 || !(dx > 0.0) || !phi || band < 0) return FLIP_ERR_DOMAIN;
     for (int t = 0; t < 3 * num_triangles; t++)
         if (triangles[t] < 0 || triangles[t] >= num_vertices) return FLIP_ERR_OUT_OF_RANGE;
     const int ni = isize + 1, nj = jsize + 1, nk = ksize + 1;
     const float far = far_value > 0.0f ? far_value : (float)((band + 1) * dx);
     std::fill(phi, phi + (size_t)ni * nj * nk, far);
+    if (closest) std::fill(closest, closest + (size_t)ni * nj * nk, -1);
     const V3 *vert = reinterpret_cast<const V3 *>(vertices_xyz);
     float blo[3] = {1e30f, 1e30f, 1e30f}, bhi[3] = {-1e30f, -1e30f, -1e30f};
     for (int v = 0; v < num_vertices; v++) {
@@ -348,6 +351,8 @@ extern "C" int flip_mesh_sdf(int isize, int jsize, int ksize, double dx, const f
     // the region of interest: the mesh's index box grown by the band
     const int ri = nhi[0] - nlo[0] + 1, rj = nhi[1] - nlo[1] + 1, rk = nhi[2] - nlo[2] + 1;
     std::vector<float> best((size_t)ri * rj * rk, 1e30f);          // squared distance to the nearest triangle seen
+    std::vector<int> bestTri;
+    if (closest) bestTri.assign((size_t)ri * rj * rk, -1);
     std::vector<std::vector<float>> hits((size_t)rj * rk);          // x of the crossings of the +x ray of every (j, k) line
     for (int t = 0; t < num_triangles; t++) {
         const V3 &a = vert[triangles[3 * t]], &b = vert[triangles[3 * t + 1]], &c = vert[triangles[3 * t + 2]];
@@ -363,8 +368,12 @@ extern "C" int flip_mesh_sdf(int isize, int jsize, int ksize, double dx, const f
             for (int j = q0[1]; j <= q1[1]; j++)
                 for (int i = q0[0]; i <= q1[0]; i++) {
                     const V3 p = {(float)(i * dx), (float)(j * dx), (float)(k * dx)};
-                    float &d2 = best[(size_t)(i - nlo[0]) + (size_t)ri * ((j - nlo[1]) + (size_t)rj * (k - nlo[2]))];
-                    d2 = std::min(d2, point_triangle_dist2(p, a, b, c));
+                    const size_t q = (size_t)(i - nlo[0]) + (size_t)ri * ((j - nlo[1]) + (size_t)rj * (k - nlo[2]));
+                    const float cand = point_triangle_dist2(p, a, b, c);
+                    if (cand < best[q]) {           // the first of equally near triangles stays (meshlevelset.cpp:596)
+                        best[q] = cand;
+                        if (closest) bestTri[q] = t;
+                    }
                 }
         // crossings of the +x rays through the (j, k) lines the triangle's yz projection can cover; every ray starts from a
         // point nudged off the lattice (mesh vertices on grid lines)
@@ -391,9 +400,147 @@ extern "C" int flip_mesh_sdf(int isize, int jsize, int ksize, double dx, const f
                 const float d2 = best[(size_t)(i - nlo[0]) + (size_t)ri * ((j - nlo[1]) + (size_t)rj * (k - nlo[2]))];
                 const float d = d2 < 1e29f ? std::min(std::sqrt(d2), far) : far;       // no triangle within the band: the bound
                 phi[(size_t)i + (size_t)ni * (j + (size_t)nj * k)] = (crossings & 1) ? -d : d;
+                if (closest) closest[(size_t)i + (size_t)ni * (j + (size_t)nj * k)] = bestTri[(size_t)(i - nlo[0]) + (size_t)ri * ((j - nlo[1]) + (size_t)rj * (k - nlo[2]))];
             }
         }
     return FLIP_OK;
+}
+
+extern "C" int flip_mesh_sdf(int isize, int jsize, int ksize, double dx, const float *vertices_xyz, int num_vertices,
+                             const int *triangles, int num_triangles, int band, float far_value, float *phi, int cell_lo[3],
+                             int cell_hi[3]) {
+    return mesh_sdf_impl(isize, jsize, ksize, dx, vertices_xyz, num_vertices, triangles, num_triangles, band, far_value, phi,
+                         cell_lo, cell_hi, nullptr);
+}
+
+// ------------------------------------------------------------------------------------------------
+// The velocity data of a moving mesh (MeshLevelSet::_computeVelocityGridThread, meshlevelset.cpp:1319-1372): on every face
+// whose solid fraction (of the mesh's own signed distance field) is positive, fraction x the velocity of the mesh surface
+// nearest to the face centre.  Nearest surface point as the reference finds it (getNearestVelocity :168-205): among the
+// closest triangles of the eight nodes of the cell that holds the face centre, the one nearest to the centre; its
+// velocity there (_pointToTriangleVelocity :1567-1640): the barycentric blend of the vertex velocities where the
+// projection falls inside the triangle, else the blend along the nearer of the two candidate edges
+// (_pointToSegmentVelocity :1696-1714).
+namespace {
+inline float length3(V3 a) { return std::sqrt(dot3(a, a)); }
+V3 segment_velocity(V3 x0, V3 x1, V3 x2, V3 v1, V3 v2, float *distance) {
+    const V3 dxs = x2 - x1;
+    const double m2 = dot3(dxs, dxs);
+    float s12 = (float)(dot3(x2 - x0, dxs) / m2);
+    s12 = s12 < 0 ? 0 : (s12 > 1 ? 1 : s12);
+    *distance = length3(x0 - (s12 * x1 + (1 - s12) * x2));
+    return s12 * v1 + (1 - s12) * v2;
+}
+V3 triangle_velocity(V3 x0, V3 x1, V3 x2, V3 x3, V3 v1, V3 v2, V3 v3) {
+    const float eps = 1e-6f;
+    auto still = [&](V3 v) { return std::fabs(v.x) < eps && std::fabs(v.y) < eps && std::fabs(v.z) < eps; };
+    if (still(v1) && still(v2) && still(v3)) return {0, 0, 0};
+    const V3 x13 = x1 - x3, x23 = x2 - x3, x03 = x0 - x3;
+    const float m13 = dot3(x13, x13), m23 = dot3(x23, x23), d = dot3(x13, x23);
+    const float invdet = 1.0f / std::fmax(m13 * m23 - d * d, 1e-30f);
+    const float a = dot3(x13, x03), b = dot3(x23, x03);
+    const float w23 = invdet * (m23 * a - d * b), w31 = invdet * (m13 * b - d * a), w12 = 1 - w23 - w31;
+    if (w23 >= 0 && w31 >= 0 && w12 >= 0) return w23 * v1 + w31 * v2 + w12 * v3;
+    float d1, d2;
+    V3 e1, e2;
+    if (w23 > 0) { e1 = segment_velocity(x0, x1, x2, v1, v2, &d1); e2 = segment_velocity(x0, x1, x3, v1, v3, &d2); }
+    else if (w31 > 0) { e1 = segment_velocity(x0, x1, x2, v1, v2, &d1); e2 = segment_velocity(x0, x2, x3, v2, v3, &d2); }
+    else { e1 = segment_velocity(x0, x1, x3, v1, v3, &d1); e2 = segment_velocity(x0, x2, x3, v2, v3, &d2); }
+    return d1 < d2 ? e1 : e2;
+}
+}  // namespace
+
+namespace flip {
+// phi: the mesh's nodal field (out); fraction[3] / field[3]: per face of U, V, W the solid fraction and fraction x
+// velocity component (out, resized).
+int mesh_velocity_data(const Dims &d, const float *vertices_xyz, int num_vertices, const int *triangles, int num_triangles,
+                       const float *vertex_velocities_xyz, int band, float far_value, std::vector<float> &phi,
+                       std::vector<float> fraction[3], std::vector<float> field[3]) {
+    const int ni = d.I + 1, nj = d.J + 1, nk = d.K + 1;
+    phi.resize((size_t)ni * nj * nk);
+    std::vector<int> closest((size_t)ni * nj * nk);
+    int clo[3], chi[3];
+    const int rc = mesh_sdf_impl(d.I, d.J, d.K, d.dx, vertices_xyz, num_vertices, triangles, num_triangles, band, far_value,
+                                 phi.data(), clo, chi, closest.data());
+    if (rc != FLIP_OK) return rc;
+    const V3 *vert = reinterpret_cast<const V3 *>(vertices_xyz), *vel = reinterpret_cast<const V3 *>(vertex_velocities_xyz);
+    const int n[3] = {d.nU, d.nV, d.nW};
+    for (int m = 0; m < 3; m++) { fraction[m].assign(n[m], 0.0f); field[m].assign(n[m], 0.0f); }
+    auto P = [&](int i, int j, int k) { return phi[(size_t)i + (size_t)ni * ((size_t)j + (size_t)nj * k)]; };
+    const double invdx = 1.0 / d.dx;
+    auto nearest_velocity = [&](V3 p) -> V3 {
+        const int gi = (int)std::floor(p.x * invdx), gj = (int)std::floor(p.y * invdx), gk = (int)std::floor(p.z * invdx);
+        int tri = -1;
+        float nearest = 1e30f;
+        static const int order[8][3] = {{0, 0, 0}, {1, 0, 0}, {1, 0, 1}, {0, 0, 1}, {0, 1, 0}, {1, 1, 0}, {1, 1, 1}, {0, 1, 1}};
+        for (auto &o : order) {
+            const int a = gi + o[0], b = gj + o[1], c = gk + o[2];
+            if (a < 0 || b < 0 || c < 0 || a >= ni || b >= nj || c >= nk) continue;
+            const int t = closest[(size_t)a + (size_t)ni * ((size_t)b + (size_t)nj * c)];
+            if (t < 0) continue;
+            const float dist = std::sqrt(point_triangle_dist2(p, vert[triangles[3 * t]], vert[triangles[3 * t + 1]], vert[triangles[3 * t + 2]]));
+            if (dist < nearest) { nearest = dist; tri = t; }
+        }
+        if (tri < 0) return {0, 0, 0};
+        const int *q = triangles + 3 * tri;
+        return triangle_velocity(p, vert[q[0]], vert[q[1]], vert[q[2]], vel[q[0]], vel[q[1]], vel[q[2]]);
+    };
+    // only the faces of the mesh's index box grown by the band can have a positive fraction
+    const int i0 = clo[0], i1 = std::min(chi[0], d.I), j0 = clo[1], j1 = std::min(chi[1], d.J), k0 = clo[2], k1 = std::min(chi[2], d.K);
+    for (int k = k0; k <= k1; k++)
+        for (int j = j0; j <= j1; j++)
+            for (int i = i0; i <= i1; i++) {
+                if (j < d.J && k < d.K) {
+                    const float f = negative_area(P(i, j, k), P(i, j + 1, k), P(i, j, k + 1), P(i, j + 1, k + 1));
+                    if (f > 0.0f) {
+                        const size_t idx = (size_t)i + (size_t)(d.I + 1) * ((size_t)j + (size_t)d.J * k);
+                        const V3 v = nearest_velocity({(float)(i * d.dx), (float)((j + 0.5) * d.dx), (float)((k + 0.5) * d.dx)});
+                        fraction[0][idx] = f; field[0][idx] = f * v.x;
+                    }
+                }
+                if (i < d.I && k < d.K) {
+                    const float f = negative_area(P(i, j, k), P(i, j, k + 1), P(i + 1, j, k), P(i + 1, j, k + 1));
+                    if (f > 0.0f) {
+                        const size_t idx = (size_t)i + (size_t)d.I * ((size_t)j + (size_t)(d.J + 1) * k);
+                        const V3 v = nearest_velocity({(float)((i + 0.5) * d.dx), (float)(j * d.dx), (float)((k + 0.5) * d.dx)});
+                        fraction[1][idx] = f; field[1][idx] = f * v.y;
+                    }
+                }
+                if (i < d.I && j < d.J) {
+                    const float f = negative_area(P(i, j, k), P(i, j + 1, k), P(i + 1, j, k), P(i + 1, j + 1, k));
+                    if (f > 0.0f) {
+                        const size_t idx = (size_t)i + (size_t)d.I * ((size_t)j + (size_t)d.J * k);
+                        const V3 v = nearest_velocity({(float)((i + 0.5) * d.dx), (float)((j + 0.5) * d.dx), (float)(k * d.dx)});
+                        fraction[2][idx] = f; field[2][idx] = f * v.z;
+                    }
+                }
+            }
+    return FLIP_OK;
+}
+}  // namespace flip
+
+extern "C" int flip_mesh_velocity_data(int isize, int jsize, int ksize, double dx, const float *vertices_xyz, int num_vertices,
+                                       const int *triangles, int num_triangles, const float *vertex_velocities_xyz, int band,
+                                       float far_value, float *phi, float *fractionU, float *fractionV, float *fractionW,
+                                       float *fieldU, float *fieldV, float *fieldW) {
+    if (isize <= 0 || jsize <= 0 || ksize <= 0 || !(dx > 0.0) || !phi || !vertex_velocities_xyz) return FLIP_ERR_DOMAIN;
+    try {
+        flip::Dims d;
+        d.I = isize; d.J = jsize; d.K = ksize; d.dx = dx; d.kOff = 0; d.Kg = ksize; d.kOwn0 = 0; d.kOwn1 = ksize;
+        d.nU = (isize + 1) * jsize * ksize; d.nV = isize * (jsize + 1) * ksize; d.nW = isize * jsize * (ksize + 1);
+        d.nC = isize * jsize * ksize; d.nN = (isize + 1) * (jsize + 1) * (ksize + 1);
+        std::vector<float> p, fr[3], fl[3];
+        const int rc = flip::mesh_velocity_data(d, vertices_xyz, num_vertices, triangles, num_triangles, vertex_velocities_xyz, band,
+                                                far_value, p, fr, fl);
+        if (rc != FLIP_OK) return rc;
+        memcpy(phi, p.data(), sizeof(float) * p.size());
+        float *outs[6] = {fractionU, fractionV, fractionW, fieldU, fieldV, fieldW};
+        for (int m = 0; m < 3; m++) {
+            if (outs[m]) memcpy(outs[m], fr[m].data(), sizeof(float) * fr[m].size());
+            if (outs[3 + m]) memcpy(outs[3 + m], fl[m].data(), sizeof(float) * fl[m].size());
+        }
+        return FLIP_OK;
+    } catch (const std::bad_alloc &) { return FLIP_ERR_RUNTIME; }
 }
 
 // the generated marching-cubes case table of the surface reconstruction (mc_tables.h), for inspection and tests

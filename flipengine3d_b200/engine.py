@@ -106,6 +106,9 @@ def load_library():
     L.flip_static_inputs.argtypes = [ci, ci, ci, C.c_double, vp, ci, vp, vp, vp, vp, C.POINTER(ci)]
     L.flip_center_weights.argtypes = [ci, ci, ci, C.c_double, vp, vp]
     L.flip_set_solid_velocity.argtypes = [vp, vp, vp, vp]
+    L.flip_add_obstacle_mesh.argtypes = [vp, vp, ci, vp, ci, C.POINTER(ci)]
+    L.flip_set_obstacle_mesh_motion.argtypes = [vp, ci, vp, vp, vp]
+    L.flip_mesh_velocity_data.argtypes = [ci, ci, ci, cd, vp, ci, vp, ci, vp, ci, C.c_float, vp, vp, vp, vp, vp, vp, vp]
     L.flip_set_obstacle_box_motion.argtypes = [vp, ci, C.POINTER(cd), C.POINTER(cd), C.POINTER(cd)]
     L.flip_get_num_substeps.argtypes = [vp, C.POINTER(ci)]
     L.flip_get_step_stats.argtypes = [vp, ci, C.POINTER(StepStats)]
@@ -176,6 +179,27 @@ def center_weights(dims, dx, solid_phi):
     if rc != FLIP_OK:
         raise _EXC.get(rc, RuntimeError)("flip_center_weights failed")
     return wC
+
+
+def mesh_velocity_data(dims, dx, vertices, triangles, vertex_velocities, band=3, far=0.0):
+    """flip_mesh_velocity_data (host code, no CUDA device needed): dict(phi (K+1,J+1,I+1), fractionU/V/W, fieldU/V/W in the MAC
+    shapes) of a closed mesh whose vertices move with vertex_velocities."""
+    L = load_library()
+    I, J, K = (int(d) for d in dims)
+    v = np.ascontiguousarray(vertices, dtype=np.float32)
+    t = np.ascontiguousarray(triangles, dtype=np.int32)
+    w = np.ascontiguousarray(vertex_velocities, dtype=np.float32)
+    assert w.shape == v.shape
+    out = dict(phi=np.empty((K + 1, J + 1, I + 1), dtype=np.float32))
+    shapes = dict(U=(K, J, I + 1), V=(K, J + 1, I), W=(K + 1, J, I))
+    for kind in ("fraction", "field"):
+        for n in "UVW":
+            out[kind + n] = np.empty(shapes[n], dtype=np.float32)
+    rc = L.flip_mesh_velocity_data(I, J, K, float(dx), v.ctypes.data, v.shape[0], t.ctypes.data, t.shape[0], w.ctypes.data, int(band),
+                                   float(far), out["phi"].ctypes.data, *[out[k + n].ctypes.data for k in ("fraction", "field") for n in "UVW"])
+    if rc != FLIP_OK:
+        raise _EXC.get(rc, RuntimeError)("flip_mesh_velocity_data failed")
+    return out
 
 
 def mesh_sdf(dims, dx, vertices, triangles, band=3, far=0.0):
@@ -365,6 +389,20 @@ class FluidSimulation:
         for x, name in zip(a, ("solidU", "solidV", "solidW")):
             assert x.shape == self.shape_of(name), (name, x.shape)
         self._check(self.L.flip_set_solid_velocity(self.h, a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data))
+        self._solid_velocity = True
+
+    def addMeshObstacleMesh(self, vertices, triangles):
+        """FluidSimulation::addMeshObstacle with a closed triangle mesh the library keeps (it can be animated)."""
+        v = np.ascontiguousarray(vertices, dtype=np.float32)
+        t = np.ascontiguousarray(triangles, dtype=np.int32)
+        oid = C.c_int()
+        self._check(self.L.flip_add_obstacle_mesh(self.h, v.ctypes.data, v.shape[0], t.ctypes.data, t.shape[0], C.byref(oid)))
+        return oid.value
+
+    def setMeshObstacleMeshMotion(self, oid, prev, cur, nxt):
+        """MeshObject::updateMeshAnimated for a mesh obstacle: the vertices of the previous / current / next frame."""
+        a = [np.ascontiguousarray(x, dtype=np.float32) for x in (prev, cur, nxt)]
+        self._check(self.L.flip_set_obstacle_mesh_motion(self.h, int(oid), a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data))
         self._solid_velocity = True
 
     def setMeshObstacleBoxMotion(self, oid, off_prev, off_cur, off_next):

@@ -127,6 +127,18 @@ def dam_break_with_chamber(n=32, seed=12349):
     return sc
 
 
+WEDGE_TRIANGLES = np.array([[0, 2, 1], [3, 4, 5], [0, 1, 4], [0, 4, 3], [1, 2, 5], [1, 5, 4], [2, 0, 3], [2, 3, 5]], dtype=np.int32)
+
+
+def wedge_vertices(centre, angle, scale=1.0):
+    """A triangular prism (closed mesh of 6 vertices, WEDGE_TRIANGLES) turned by `angle` about its z axis: the animated
+    mesh obstacle of the moving-solid tests (every vertex has its own velocity when it turns)."""
+    base = scale * np.array([[-0.45, -0.5, -0.9], [0.45, -0.5, -0.9], [0.0, 0.55, -0.9], [-0.45, -0.5, 0.9], [0.45, -0.5, 0.9], [0.0, 0.55, 0.9]])
+    c, s = np.cos(angle), np.sin(angle)
+    R = np.array([[c, -s, 0.0], [s, c, 0.0], [0.0, 0.0, 1.0]])
+    return (base @ R.T + np.asarray(centre, dtype=np.float64)).astype(np.float32)
+
+
 def dam_break_z(n=64, seed=12347):
     """A column against the low-z wall that collapses along +z: particles cross z-slab boundaries
     (migration test of the multi-GPU decomposition)."""

@@ -227,10 +227,24 @@ int flip_set_solid_velocity(flip_ctx *ctx, const float *U, const float *V, const
  * :1797-1828, _normalizeVelocityGridThread :1738-1756), then 5 layers of extrapolation (:697, the fluid's routine, on
  * the device).  The per-substep SDF and the solid fractions are HOST work (as in the reference); divergence,
  * conditioning, constraint and extrapolation run on the device (flip_set_solid_velocity describes them; the arrays it
- * would set are overwritten every substep while an animated obstacle is enabled).  General animated meshes: rebuild their
- * SDF with flip_mesh_sdf and hand over SDF and velocities yourself.  Not available in a z-slab run. */
+ * would set are overwritten every substep while an animated obstacle is enabled).  General animated meshes:
+ * flip_add_obstacle_mesh / flip_set_obstacle_mesh_motion below.  Not available in a z-slab run. */
 int flip_set_obstacle_box_motion(flip_ctx *ctx, int id, const double offset_prev[3], const double offset_cur[3],
                                  const double offset_next[3]);
+/* Animated obstacles, general closed meshes of fixed topology (rigid or deforming): flip_add_obstacle_mesh hands the library
+ * the mesh itself (addMeshObstacle with a MeshObject; static until animated: its signed distance field is flip_mesh_sdf's),
+ * flip_set_obstacle_mesh_motion the vertices of the previous, the current and the next frame (updateMeshAnimated; same
+ * count and order as the mesh was added with), once per frame.  Per substep as above, with per-vertex velocities; the
+ * face velocity is that of the mesh surface nearest to the face centre, found and interpolated as the reference does
+ * (MeshLevelSet::getNearestVelocity meshlevelset.cpp:168-205 over the closest triangles of the surrounding nodes,
+ * _pointToTriangleVelocity :1567-1640).  flip_mesh_velocity_data is that computation on its own (HOST code, no device
+ * needed; the CPU tests pin it to the reference): phi as flip_mesh_sdf, per face of U / V / W the mesh's solid fraction
+ * and fraction x velocity component (any output but phi may be NULL). */
+int flip_add_obstacle_mesh(flip_ctx *ctx, const float *vertices_xyz, int num_vertices, const int *triangles, int num_triangles, int *id);
+int flip_set_obstacle_mesh_motion(flip_ctx *ctx, int id, const float *vertices_prev, const float *vertices_cur, const float *vertices_next);
+int flip_mesh_velocity_data(int isize, int jsize, int ksize, double dx, const float *vertices_xyz, int num_vertices, const int *triangles,
+                            int num_triangles, const float *vertex_velocities_xyz, int band, float far_value, float *phi,
+                            float *fractionU, float *fractionV, float *fractionW, float *fieldU, float *fieldV, float *fieldW);
 /* The cell-centre weights of a nodal solid SDF, computed on the HOST exactly as the library computes them (no CUDA device
  * needed): phi (I+1)(J+1)(K+1) floats in, wC IJK floats out. */
 int flip_center_weights(int isize, int jsize, int ksize, double dx, const float *phi_nodal, float *wC);

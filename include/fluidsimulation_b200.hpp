@@ -84,18 +84,28 @@ public:
     void getGridDimensions(int *i, int *j, int *k) const { *i = _isize; *j = _jsize; *k = _ksize; }
     void updateMeshStatic(TriangleMesh meshCurrent) { _mesh = std::move(meshCurrent); _animated = false; }
     // MeshObject::updateMeshAnimated (meshobject.cpp:61-95), once per frame before update(): the previous, the current and
-    // the next frame's mesh.  Supported: an axis-aligned box that translates rigidly (flip_set_obstacle_box_motion);
-    // anything else throws.  May be called before or after addMeshObstacle.
+    // the next frame's mesh (fixed topology).  An axis-aligned box that translates rigidly goes through
+    // flip_set_obstacle_box_motion, any other closed mesh (turning, deforming) through flip_set_obstacle_mesh_motion with
+    // per-vertex velocities.  May be called before or after addMeshObstacle (an object added as a static box has to keep
+    // translating as a box).
     void updateMeshAnimated(TriangleMesh meshPrevious, TriangleMesh meshCurrent, TriangleMesh meshNext) {
-        MeshObject prev(_isize, _jsize, _ksize, _dx), next(_isize, _jsize, _ksize, _dx);
-        prev._mesh = std::move(meshPrevious);
-        next._mesh = std::move(meshNext);
+        if (meshPrevious.vertices.size() != meshCurrent.vertices.size() || meshNext.vertices.size() != meshCurrent.vertices.size())
+            throw std::runtime_error("Error: animated mesh objects must keep their topology.\n");
+        _meshPrev = std::move(meshPrevious);
+        _meshNext = std::move(meshNext);
         _mesh = std::move(meshCurrent);
-        if (!isAxisAlignedBox() || !prev.isAxisAlignedBox() || !next.isAxisAlignedBox())
-            throw std::runtime_error("Error: animated mesh objects are supported for rigidly translating axis-aligned boxes only.\n");
-        vmath::vec3 lo, hi, plo, phi, nlo, nhi;
-        bounds(lo, hi); prev.bounds(plo, phi); next.bounds(nlo, nhi);
-        for (int a = 0; a < 3; a++) { _curLo[a] = (&lo.x)[a]; _prevLo[a] = (&plo.x)[a]; _nextLo[a] = (&nlo.x)[a]; }
+        MeshObject prev(_isize, _jsize, _ksize, _dx), next(_isize, _jsize, _ksize, _dx);
+        prev._mesh = _meshPrev;
+        next._mesh = _meshNext;
+        _boxMotion = isAxisAlignedBox() && prev.isAxisAlignedBox() && next.isAxisAlignedBox();
+        if (_ctx && _addedAsBox && !_boxMotion)
+            throw std::runtime_error("Error: an obstacle added as a box can only translate; add it with its animation set.\n");
+        if (_ctx && !_addedAsBox) _boxMotion = false;
+        if (_boxMotion) {
+            vmath::vec3 lo, hi, plo, phi, nlo, nhi;
+            bounds(lo, hi); prev.bounds(plo, phi); next.bounds(nlo, nhi);
+            for (int a = 0; a < 3; a++) { _curLo[a] = (&lo.x)[a]; _prevLo[a] = (&plo.x)[a]; _nextLo[a] = (&nlo.x)[a]; }
+        }
         _animated = true;
         pushMotion();
     }
@@ -145,11 +155,20 @@ private:
     bool _enabled = true;
     flip_ctx *_ctx = nullptr;     // the simulation this object is an obstacle of
     int _obstacleId = 0;
-    bool _animated = false;
+    bool _animated = false, _boxMotion = false, _addedAsBox = false;
+    TriangleMesh _meshPrev, _meshNext;
     double _baseLo[3] = {0, 0, 0};                     // lower corner of the box the obstacle was added as
     double _prevLo[3] = {0, 0, 0}, _curLo[3] = {0, 0, 0}, _nextLo[3] = {0, 0, 0};
     void pushMotion() {
         if (!_ctx || !_animated) return;
+        if (!_boxMotion) {
+            static_assert(sizeof(vmath::vec3) == 12, "packed float triplets");
+            if (flip_set_obstacle_mesh_motion(_ctx, _obstacleId, reinterpret_cast<const float *>(_meshPrev.vertices.data()),
+                                              reinterpret_cast<const float *>(_mesh.vertices.data()),
+                                              reinterpret_cast<const float *>(_meshNext.vertices.data())) != FLIP_OK)
+                throw std::runtime_error(flip_last_error(_ctx));
+            return;
+        }
         double a[3], b[3], c[3];
         for (int q = 0; q < 3; q++) { a[q] = _prevLo[q] - _baseLo[q]; b[q] = _curLo[q] - _baseLo[q]; c[q] = _nextLo[q] - _baseLo[q]; }
         if (flip_set_obstacle_box_motion(_ctx, _obstacleId, a, b, c) != FLIP_OK) throw std::runtime_error(flip_last_error(_ctx));
@@ -305,17 +324,22 @@ public:
     void addMeshObstacle(MeshObject *obstacle) {
         if (obstacle->_ctx == _c) throw std::runtime_error("Error: mesh obstacle has already been added.\n");
         int id = 0;
-        if (obstacle->isAxisAlignedBox()) {
+        if (obstacle->isAxisAlignedBox() && (!obstacle->_animated || obstacle->_boxMotion)) {
             vmath::vec3 lo, hi;
             obstacle->bounds(lo, hi);
             const double l[3] = {lo.x, lo.y, lo.z}, h[3] = {hi.x, hi.y, hi.z};
             check(flip_add_obstacle_box(_c, l, h, &id));
             for (int a = 0; a < 3; a++) obstacle->_baseLo[a] = l[a];
+            obstacle->_addedAsBox = true;
         } else {
-            std::vector<float> phi;
-            int clo[3], chi[3];
-            obstacle->signedDistanceField(phi, clo, chi, 3, 3.0e38f);       // _solidLevelSetExactBand = 3; untouched elsewhere
-            check(flip_add_obstacle_sdf(_c, phi.data(), &id));
+            // the library keeps the mesh (its signed distance field in the band of three cells, _solidLevelSetExactBand, is
+            // flip_mesh_sdf's) so that it can be animated later
+            static_assert(sizeof(vmath::vec3) == 12 && sizeof(Triangle) == 12, "packed float / int triplets");
+            const TriangleMesh &m = obstacle->_mesh;
+            check(flip_add_obstacle_mesh(_c, reinterpret_cast<const float *>(m.vertices.data()), (int)m.vertices.size(),
+                                         reinterpret_cast<const int *>(m.triangles.data()), (int)m.triangles.size(), &id));
+            obstacle->_addedAsBox = false;
+            obstacle->_boxMotion = false;
         }
         obstacle->_ctx = _c; obstacle->_obstacleId = id;
         obstacle->pushMotion();                                    // an animation set before the object was added

@@ -551,6 +551,34 @@ int ref_animate_obstacle_box(void *p, int idx, const double lo[3], const double 
         h->obstacles[idx]->updateMeshAnimated(boxMesh(lo, hi, offPrev), boxMesh(lo, hi, offCur), boxMesh(lo, hi, offNext));
     });
 }
+/* addMeshObstacle with an arbitrary closed mesh (static until ref_animate_obstacle_mesh), and updateMeshAnimated with the
+ * vertices of the previous / current / next frame (same triangles). */
+static TriangleMesh meshOf(const float *verts, int nv, const int *tris, int nt) {
+    TriangleMesh m;
+    for (int v = 0; v < nv; v++) m.vertices.push_back(vmath::vec3(verts[3 * v], verts[3 * v + 1], verts[3 * v + 2]));
+    for (int t = 0; t < nt; t++) m.triangles.push_back(Triangle(tris[3 * t], tris[3 * t + 1], tris[3 * t + 2]));
+    return m;
+}
+int ref_add_obstacle_mesh(void *p, const float *verts, int nv, const int *tris, int nt) {
+    RefSim *h = (RefSim *)p;
+    int idx = -1;
+    guarded(h, [&] {
+        FluidSimulation *s = h->sim;
+        MeshObject *obj = new MeshObject(s->_isize, s->_jsize, s->_ksize, s->_dx);
+        obj->updateMeshStatic(meshOf(verts, nv, tris, nt));
+        s->addMeshObstacle(obj);
+        h->obstacles.push_back(obj);
+        idx = (int)h->obstacles.size() - 1;
+    });
+    return idx;
+}
+int ref_animate_obstacle_mesh(void *p, int idx, const float *prev, const float *cur, const float *next, int nv, const int *tris, int nt) {
+    RefSim *h = (RefSim *)p;
+    return guarded(h, [&] {
+        if (idx < 0 || idx >= (int)h->obstacles.size() || !h->obstacles[idx]) throw std::runtime_error("no such obstacle");
+        h->obstacles[idx]->updateMeshAnimated(meshOf(prev, nv, tris, nt), meshOf(cur, nv, tris, nt), meshOf(next, nv, tris, nt));
+    });
+}
 int ref_remove_obstacle(void *p, int idx) {
     RefSim *h = (RefSim *)p;
     return guarded(h, [&] {

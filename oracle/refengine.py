@@ -79,6 +79,8 @@ def _load(kind):
     L.ref_set_marker_particle_scale.argtypes = [C.c_void_p, C.c_double]
     L.ref_add_obstacle_box.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.ref_remove_obstacle.argtypes = [C.c_void_p, C.c_int]
+    L.ref_add_obstacle_mesh.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    L.ref_animate_obstacle_mesh.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
     L.ref_animate_obstacle_box.argtypes = [C.c_void_p, C.c_int] + [C.POINTER(C.c_double)] * 5
     L.ref_constrain_fluid_source_velocity.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.ref_isomesh.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
@@ -261,6 +263,22 @@ class RefEngine:
         """MeshObject::updateMeshAnimated with the box [lo,hi] moved by the three offsets (previous / current / next frame)."""
         d3 = C.c_double * 3
         self._check(self.L.ref_animate_obstacle_box(self.h, int(idx), d3(*lo), d3(*hi), d3(*off_prev), d3(*off_cur), d3(*off_next)))
+
+    def add_obstacle_mesh(self, vertices, triangles):
+        """FluidSimulation::addMeshObstacle with a closed triangle mesh; returns its index in the shim's list."""
+        v = np.ascontiguousarray(vertices, dtype=np.float32)
+        t = np.ascontiguousarray(triangles, dtype=np.int32)
+        idx = self.L.ref_add_obstacle_mesh(self.h, v.ctypes.data, v.shape[0], t.ctypes.data, t.shape[0])
+        if idx < 0:
+            raise RuntimeError(self.L.ref_last_error(self.h).decode())
+        return idx
+
+    def animate_obstacle_mesh(self, idx, prev, cur, nxt, triangles):
+        """MeshObject::updateMeshAnimated with the vertices of the previous / current / next frame."""
+        a = [np.ascontiguousarray(x, dtype=np.float32) for x in (prev, cur, nxt)]
+        t = np.ascontiguousarray(triangles, dtype=np.int32)
+        self._check(self.L.ref_animate_obstacle_mesh(self.h, int(idx), a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data,
+                                                     a[0].shape[0], t.ctypes.data, t.shape[0]))
 
     def remove_obstacle(self, idx):
         self._check(self.L.ref_remove_obstacle(self.h, int(idx)))

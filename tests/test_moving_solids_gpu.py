@@ -151,3 +151,51 @@ def test_animated_box_obstacle_against_reference():
         gpu.array("solidU")
     ref.close()
     gpu.close()
+
+
+@needs_ref
+def test_animated_mesh_obstacle_against_reference():
+    """A general animated mesh: a wedge that turns and translates into the dam-break column, animated every frame with
+    updateMeshAnimated in the reference and flip_set_obstacle_mesh_motion here (per-vertex velocities, nearest-surface
+    velocity on the faces).  Same checks as for the plate."""
+    sc = scenes.dam_break(32)
+    dx = sc["dx"]
+    tris = scenes.WEDGE_TRIANGLES
+
+    def frame(f):
+        return scenes.wedge_vertices((2.05 - 0.045 * f, 0.95 + 0.005 * f, 2.0), 0.04 * f)
+    ref, gpu = pc.make_pair(sc, own_solid=True)
+    ridx = ref.add_obstacle_mesh(frame(0), tris)
+    gid = gpu.addMeshObstacleMesh(frame(0), tris)
+    for f in range(8):
+        ref.animate_obstacle_mesh(ridx, frame(f - 1), frame(f), frame(f + 1), tris)
+        gpu.setMeshObstacleMeshMotion(gid, frame(f - 1), frame(f), frame(f + 1))
+        ref.update(1.0 / 30.0)
+        gpu.update(1.0 / 30.0)
+        st = gpu.substep_stats()
+        assert ref.substeps == len(st), (f, ref.substeps, len(st))
+        assert abs(ref.num_particles - st[-1]["particles"]) <= 4, (f, ref.num_particles, st[-1]["particles"])
+        assert abs(ref.num_fluid_cells - st[-1]["pressure_rows"]) <= 2, (f, ref.num_fluid_cells, st[-1]["pressure_rows"])
+        assert all(s["pcg_converged"] == 1 for s in st), st
+        p, ids = pc.particles_by_id(gpu)
+        a = ref.particles()
+        if p.shape[0] == a.shape[0]:
+            err = pc.rel_l2(p[np.argsort(ids), :3], a[:, :3])
+            assert err <= 5e-3, (f, err)
+        com = float(np.abs(p[:, :3].mean(0) - a[:, :3].mean(0)).max())
+        mv = float(np.abs(p[:, 3:].mean(0) - a[:, 3:].mean(0)).max())
+        assert com <= 2e-4 and mv <= 5e-3, (f, com, mv)
+    R, G = ref.array("solid_phi"), gpu.array("solid_phi")
+    assert np.array_equal(R < 0, G < 0), int(np.count_nonzero((R < 0) != (G < 0)))
+    near = np.abs(R) < 2.5 * dx
+    assert np.abs(R[near] - G[near]).max() <= 2e-4 * dx, np.abs(R[near] - G[near]).max() / dx
+    for name in ("weightU", "weightV", "weightW", "weightC"):
+        assert np.abs(ref.array(name) - gpu.array(name)).max() <= 1e-4, name
+    vmax = 0.0
+    for name in "UVW":
+        a, b = gpu.array("solid" + name), ref.array("solid" + name)
+        vmax = max(vmax, float(np.abs(b).max()))
+        assert np.abs(a - b).max() <= 2e-5, (name, float(np.abs(a - b).max()))
+    assert vmax > 1.3
+    ref.close()
+    gpu.close()
