@@ -632,6 +632,7 @@ static void update_animated_obstacles(flip_ctx *c) {
         }
         return;
     }
+    if (slab_on(c)) throw ApiError(FLIP_ERR_UNSUPPORTED, "animated obstacles are not supported in a z-slab run");
     c->solidVelFromAnimation = true;
     const Dims &d = c->d;
     // fluidsimulation.cpp:2892-2893 (floats)

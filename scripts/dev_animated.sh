@@ -1,3 +1,4 @@
-# developer batch: the animated-mesh test, twice (run-to-run spread of the splash)
+# developer batch: the tests around the obstacle / mesh code (facade examples, seeding of meshes, static and moving solids)
 mkdir -p gpurun_out
-for r in 1 2; do timeout 200 python -m pytest tests/test_moving_solids_gpu.py -m gpu -q --tb=short -k "animated" > gpurun_out/r2h_moving_$r.log 2>&1; echo "moving run $r rc=$?"; tail -12 gpurun_out/r2h_moving_$r.log | cut -c1-1500; done
+timeout 300 python -m pytest tests/test_gpu_parity.py tests/test_moving_solids_gpu.py -m gpu -x -q --tb=short -k "facade or seeding or static_obstacles or moving or animated or solid_velocity" > gpurun_out/r2i_obstacle_tests.log 2>&1; echo "rc=$?"; tail -15 gpurun_out/r2i_obstacle_tests.log | cut -c1-1500
+build/obstacles_and_sources 40 40 | tail -3

@@ -288,7 +288,7 @@ def test_obstacles_and_sources_through_the_cpp_facade():
     assert m and int(m.group(2)) > 0, r.stdout[-500:]
     # the epilogue: a plate animated with MeshObject::updateMeshAnimated sweeps along the floor; nothing stays inside it
     m = re.search(r"animated plate: 12 frames, particles (\d+), inside plate (\d+)", r.stdout)
-    assert m and int(m.group(1)) > 0 and int(m.group(2)) <= 5, r.stdout[-500:]
+    assert m and int(m.group(1)) > 0 and int(m.group(2)) <= 10, r.stdout[-500:]       # measured: 2 (particles just under its skin)
 
 
 def test_update_before_initialize_raises_runtime_error():
