@@ -53,6 +53,8 @@ int main(int argc, char **argv) {
         sim.addMeshFluidSource(&inflow);
         sim.addMeshFluidSource(&drain);
 
+        sim.setBoundaryFriction(0.2);       // the floor and the walls drag the flow (setBoundaryFriction / MeshObject::setFriction)
+        block.setFriction(0.5f);
         sim.addBodyForce(0.0, -25.0, 0.0);
         sim.initialize();
         printf("initialized: %d^3 cells, 2 obstacles, 1 inflow, 1 outflow\n", n);

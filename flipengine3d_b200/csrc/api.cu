@@ -110,6 +110,8 @@ static void free_grids(flip_ctx *c) {
     cudaFree(c->frontier[0]); cudaFree(c->frontier[1]);
     cudaFree(c->phiL); cudaFree(c->phiS); cudaFree(c->wU); cudaFree(c->wV); cudaFree(c->wW);
     cudaFree(c->wC); cudaFree(c->solU); cudaFree(c->solV); cudaFree(c->solW); cudaFree(c->pocketFlag);
+    cudaFree(c->fricU); cudaFree(c->fricV); cudaFree(c->fricW);
+    c->fricU = c->fricV = c->fricW = nullptr;
     for (int m = 0; m < 3; m++) {
         cudaFree(c->solidWeightSum[m]); cudaFree(c->solidValid[m]);
         c->solidWeightSum[m] = nullptr; c->solidValid[m] = nullptr;
@@ -179,6 +181,27 @@ static void upload_static_inputs(flip_ctx *c) {
         build_center_weights(d, local, wC);
         if (!c->wC) dev_alloc(c->wC, d.nC);
         FLIP_CUDA_CHECK(cudaMemcpy(c->wC, wC.data(), sizeof(float) * d.nC, cudaMemcpyHostToDevice));
+    }
+    if (!c->userFaceFriction) {
+        // face friction of the merged solids (0 everywhere, the default: no arrays, the constraint takes its short path)
+        bool any = c->boundaryFriction != 0.0f;
+        for (auto &o : c->obstacles) any = any || (o.enabled && o.friction != 0.0f);
+        if (any && !slab_on(c)) {
+            std::vector<FrictionSolid> solids;
+            solids.push_back({&c->hostSolidPhi, c->boundaryFriction});
+            for (int pass = 0; pass < 2; pass++)            // static obstacles first, then the animated ones (:3062-3063)
+                for (auto &o : c->obstacles)
+                    if (o.enabled && o.animated == (pass == 1)) solids.push_back({&o.sdf, o.friction});
+            std::vector<float> fU, fV, fW;
+            build_face_friction(d, c->solidExactBand, solids, fU, fV, fW);
+            if (!c->fricU) { dev_alloc(c->fricU, d.nU); dev_alloc(c->fricV, d.nV); dev_alloc(c->fricW, d.nW); }
+            FLIP_CUDA_CHECK(cudaMemcpy(c->fricU, fU.data(), sizeof(float) * d.nU, cudaMemcpyHostToDevice));
+            FLIP_CUDA_CHECK(cudaMemcpy(c->fricV, fV.data(), sizeof(float) * d.nV, cudaMemcpyHostToDevice));
+            FLIP_CUDA_CHECK(cudaMemcpy(c->fricW, fW.data(), sizeof(float) * d.nW, cudaMemcpyHostToDevice));
+        } else if (c->fricU) {
+            cudaFree(c->fricU); cudaFree(c->fricV); cudaFree(c->fricW);
+            c->fricU = c->fricV = c->fricW = nullptr;
+        }
     }
     cudaFree(c->nearSolid); c->nearSolid = nullptr;
     dev_alloc(c->nearSolid, ns.size());
@@ -571,6 +594,65 @@ int flip_set_obstacle_box_motion(flip_ctx *c, int id, const double offPrev[3], c
                 return;
             }
         throw ApiError(FLIP_ERR_RUNTIME, "Error: could not find mesh obstacle.");
+    });
+}
+
+// Friction: setBoundaryFriction (fluidsimulation.cpp:1747-1759) and MeshObject::setFriction (meshobject.cpp:300-304) of an
+// obstacle, both in [0, 1]; the face friction of the constraint is re-derived with the static inputs.
+int flip_set_boundary_friction(flip_ctx *c, double f) {
+    return guarded(c, [&] {
+        if (!(f >= 0.0 && f <= 1.0)) throw ApiError(FLIP_ERR_DOMAIN, "Error: boundary friction must be in range [0.0, 1.0].");
+        if (slab_on(c) && f != 0.0) throw ApiError(FLIP_ERR_UNSUPPORTED, "friction is not supported in a z-slab run");
+        c->boundaryFriction = (float)f;
+        obstacles_changed(c);
+    });
+}
+int flip_set_obstacle_friction(flip_ctx *c, int id, double f) {
+    return guarded(c, [&] {
+        if (slab_on(c) && f != 0.0) throw ApiError(FLIP_ERR_UNSUPPORTED, "friction is not supported in a z-slab run");
+        for (auto &o : c->obstacles)
+            if (o.id == id) {
+                o.friction = (float)std::fmax(std::fmin(f, 1.0), 0.0);        // clamped, as setFriction does
+                obstacles_changed(c);
+                return;
+            }
+        throw ApiError(FLIP_ERR_RUNTIME, "Error: could not find mesh obstacle.");
+    });
+}
+// The face friction itself (parity seam, and for callers that keep their own solids): three HOST arrays in the MAC layout,
+// copied; three NULLs: back to the friction derived from the boundary and the obstacles.
+int flip_set_face_friction(flip_ctx *c, const float *U, const float *V, const float *W) {
+    return guarded(c, [&] {
+        const Dims &d = c->d;
+        FLIP_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        if (!U && !V && !W) {
+            c->userFaceFriction = false;
+            cudaFree(c->fricU); cudaFree(c->fricV); cudaFree(c->fricW);
+            c->fricU = c->fricV = c->fricW = nullptr;
+            obstacles_changed(c);
+            return;
+        }
+        if (!U || !V || !W) throw ApiError(FLIP_ERR_RUNTIME, "flip_set_face_friction: three arrays or three null pointers");
+        if (slab_on(c)) throw ApiError(FLIP_ERR_UNSUPPORTED, "friction is not supported in a z-slab run");
+        if (!c->fricU) { dev_alloc(c->fricU, d.nU); dev_alloc(c->fricV, d.nV); dev_alloc(c->fricW, d.nW); }
+        FLIP_CUDA_CHECK(cudaMemcpy(c->fricU, U, sizeof(float) * d.nU, cudaMemcpyHostToDevice));
+        FLIP_CUDA_CHECK(cudaMemcpy(c->fricV, V, sizeof(float) * d.nV, cudaMemcpyHostToDevice));
+        FLIP_CUDA_CHECK(cudaMemcpy(c->fricW, W, sizeof(float) * d.nW, cudaMemcpyHostToDevice));
+        c->userFaceFriction = true;
+    });
+}
+int flip_get_face_friction(flip_ctx *c, float *U, float *V, float *W) {
+    return guarded(c, [&] {
+        const Dims &d = c->d;
+        FLIP_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        float *out[3] = {U, V, W};
+        const float *src[3] = {c->fricU, c->fricV, c->fricW};
+        const int n[3] = {d.nU, d.nV, d.nW};
+        for (int m = 0; m < 3; m++) {
+            if (!out[m]) continue;
+            if (src[m]) FLIP_CUDA_CHECK(cudaMemcpy(out[m], src[m], sizeof(float) * n[m], cudaMemcpyDeviceToHost));
+            else memset(out[m], 0, sizeof(float) * n[m]);
+        }
     });
 }
 
@@ -1182,6 +1264,44 @@ int flip_static_inputs(int I, int J, int K, double dx, float *phi, int phiIsInpu
             if (nearSolid) memcpy(nearSolid, ns.data(), ns.size());
             if (nearDims) { nearDims[0] = gi; nearDims[1] = gj; nearDims[2] = gk; }
         }
+        return FLIP_OK;
+    } catch (const std::bad_alloc &) { g_createError = "host allocation failed"; return FLIP_ERR_RUNTIME; }
+}
+// The face friction of a set of solids, on the HOST (no device needed): solids[0] is the domain (nodal field everywhere),
+// the others obstacle fields carrying the largest float outside their band, in merge order.
+int flip_face_friction(int I, int J, int K, double dx, int band, int numSolids, const float *const *phis, const float *frictions,
+                       float *fU, float *fV, float *fW) {
+    if (I <= 0 || J <= 0 || K <= 0 || !(dx > 0.0) || numSolids <= 0 || !phis || !frictions) return FLIP_ERR_DOMAIN;
+    try {
+        Dims d;
+        d.I = I; d.J = J; d.K = K; d.dx = dx; d.kOff = 0; d.Kg = K; d.kOwn0 = 0; d.kOwn1 = K;
+        d.nU = (I + 1) * J * K; d.nV = I * (J + 1) * K; d.nW = I * J * (K + 1); d.nC = I * J * K;
+        d.nN = (I + 1) * (J + 1) * (K + 1);
+        std::vector<std::vector<float>> fields(numSolids);
+        std::vector<FrictionSolid> solids;
+        for (int q = 0; q < numSolids; q++) {
+            fields[q].assign(phis[q], phis[q] + (size_t)d.nN);
+            solids.push_back({&fields[q], frictions[q]});
+        }
+        std::vector<float> a, b, w;
+        build_face_friction(d, band, solids, a, b, w);
+        if (fU) memcpy(fU, a.data(), sizeof(float) * a.size());
+        if (fV) memcpy(fV, b.data(), sizeof(float) * b.size());
+        if (fW) memcpy(fW, w.data(), sizeof(float) * w.size());
+        return FLIP_OK;
+    } catch (const std::bad_alloc &) { g_createError = "host allocation failed"; return FLIP_ERR_RUNTIME; }
+}
+// The nodal field the library gives a box obstacle (flip_add_obstacle_box), on the HOST: exact box distances within `band`
+// cells of the box's index range, the largest float elsewhere.
+int flip_box_obstacle_sdf(int I, int J, int K, double dx, int band, const double lo[3], const double hi[3], float *phi) {
+    if (I <= 0 || J <= 0 || K <= 0 || !(dx > 0.0) || !lo || !hi || !phi) return FLIP_ERR_DOMAIN;
+    try {
+        flip_ctx tmp;       // geometry and band only
+        tmp.d.I = I; tmp.d.J = J; tmp.d.K = K; tmp.d.Kg = K; tmp.d.dx = dx;
+        tmp.solidExactBand = band;
+        std::vector<float> sdf;
+        box_obstacle_sdf(&tmp, lo, hi, sdf);
+        memcpy(phi, sdf.data(), sizeof(float) * sdf.size());
         return FLIP_OK;
     } catch (const std::bad_alloc &) { g_createError = "host allocation failed"; return FLIP_ERR_RUNTIME; }
 }

@@ -163,11 +163,17 @@ struct flip_ctx {
         double lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
         double offPrev[3] = {0, 0, 0}, offCur[3] = {0, 0, 0}, offNext[3] = {0, 0, 0};
         float velocity[3] = {0, 0, 0};            // of the substep under way
+        float friction = 0.0f;                    // MeshObject::setFriction (meshobject.cpp:300-304)
         // a closed triangle mesh that moves (rigidly or deforming, fixed topology): the three frames' vertices
         bool isMesh = false;
         std::vector<int> triangles;
         std::vector<float> vertsPrev, vertsCur, vertsNext;        // xyz triplets
     };
+    // friction of the solids on the partly open faces (_getFaceFrictionU/V/W, fluidsimulation.cpp:3785-3853): null while
+    // every friction is 0 (the default).  userFaceFriction: handed in with flip_set_face_friction, not derived here.
+    float *fricU = nullptr, *fricV = nullptr, *fricW = nullptr;
+    float boundaryFriction = 0.0f;            // setBoundaryFriction (:1747-1759)
+    bool userFaceFriction = false;
     bool solidVelFromAnimation = false;       // solU/V/W are rebuilt every substep from the animated obstacles
     float *solidWeightSum[3] = {nullptr, nullptr, nullptr};    // device: summed solid fractions of the faces (U, V, W)
     unsigned char *solidValid[3] = {nullptr, nullptr, nullptr}; // device: faces whose solid velocity is defined
@@ -271,6 +277,9 @@ void build_box_solid_sdf(const Dims &d, std::vector<float> &phi);
 void build_weights(const Dims &d, const std::vector<float> &phi, std::vector<float> &wU, std::vector<float> &wV,
                    std::vector<float> &wW, std::vector<float> &wC);
 void build_center_weights(const Dims &d, const std::vector<float> &phi, std::vector<float> &wC);
+struct FrictionSolid { const std::vector<float> *phi; float friction; };
+void build_face_friction(const Dims &d, int band, const std::vector<FrictionSolid> &solids, std::vector<float> &fU,
+                         std::vector<float> &fV, std::vector<float> &fW);
 int mesh_velocity_data(const Dims &d, const float *vertices_xyz, int num_vertices, const int *triangles, int num_triangles,
                        const float *vertex_velocities_xyz, int band, float far_value, std::vector<float> &phi,
                        std::vector<float> fraction[3], std::vector<float> field[3]);

@@ -356,8 +356,32 @@ __global__ void k_constrain_moving(float *__restrict__ a, float *__restrict__ b,
     if (t < n && w[t] == 0.0f) { const float v = solid[t]; a[t] = v; b[t] = v; }
 }
 
+// ... with friction: a partly open face is pulled towards the solid's velocity, f u_solid + (1 - f) u (:3895-3900), f the
+// face friction of build_face_friction; solid: null while every solid is at rest.
+__global__ void k_constrain_friction(float *__restrict__ a, float *__restrict__ b, const float *__restrict__ w,
+                                     const float *__restrict__ solid, const float *__restrict__ friction, int n) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const float wt = w[t];
+    const float us = solid ? solid[t] : 0.0f;
+    if (wt == 0.0f) { a[t] = us; b[t] = us; }
+    else if (wt < 1.0f) {
+        const float f = friction[t], g = fsub(1.0f, f);
+        a[t] = fadd(fmul(f, us), fmul(g, a[t]));
+        b[t] = fadd(fmul(f, us), fmul(g, b[t]));
+    }
+}
+
 void stage_constrain(flip_ctx *c) {
     const Dims &d = c->d;
+    if (c->fricU) {
+        k_constrain_friction<<<cdiv(d.nU, TPB), TPB, 0, c->stream>>>(c->sU, c->U, c->wU, c->solU, c->fricU, d.nU);
+        k_constrain_friction<<<cdiv(d.nV, TPB), TPB, 0, c->stream>>>(c->sV, c->V, c->wV, c->solV, c->fricV, d.nV);
+        k_constrain_friction<<<cdiv(d.nW, TPB), TPB, 0, c->stream>>>(c->sW, c->W, c->wW, c->solW, c->fricW, d.nW);
+        c->launches += 3;
+        FLIP_CUDA_CHECK(cudaGetLastError());
+        return;
+    }
     if (c->solU) {
         k_constrain_moving<<<cdiv(d.nU, TPB), TPB, 0, c->stream>>>(c->sU, c->U, c->wU, c->solU, d.nU);
         k_constrain_moving<<<cdiv(d.nV, TPB), TPB, 0, c->stream>>>(c->sV, c->V, c->wV, c->solV, d.nV);

@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <limits>
 #include <vector>
 #include "flip_internal.h"
 #include "mc_tables.h"
@@ -242,6 +243,47 @@ void add_solid_fractions(const Dims &d, const std::vector<float> &phi, const flo
     for (int k = 0; k <= d.K; k++)
         for (int j = 0; j < d.J; j++)
             for (int i = 0; i < d.I; i++, idx++) add(2, idx, negative_area(P(i, j, k), P(i, j + 1, k), P(i + 1, j, k), P(i + 1, j + 1, k)));
+}
+
+// Friction of the solids on the faces (_getFaceFrictionU/V/W, fluidsimulation.cpp:3785-3853): a quarter of the sum, over the
+// four nodes of the face, of the friction of the mesh object the solid SDF names as closest at that node
+// (MeshLevelSet::getClosestMeshObject, meshlevelset.cpp:140-150; none: 0).  The closest object of a node is settled by the
+// order in which the solids are merged (_addStaticObjectsToSDF / _addAnimatedObjectsToSolidSDF, :2877-2975, over
+// calculateUnion, meshlevelset.cpp:1782-1796): the domain first, wherever its boundary mesh lies within the exact band;
+// a later solid takes a node over where its distance is below the merged one AND nearer to zero, if the node lies in that
+// solid's band.  solids[0] is the domain (its field everywhere; in band where |phi| < (band + 1/2) dx), the others carry the
+// largest float outside their band.
+void build_face_friction(const Dims &d, int band, const std::vector<FrictionSolid> &solids, std::vector<float> &fU,
+                         std::vector<float> &fV, std::vector<float> &fW) {
+    const int ni = d.I + 1, nj = d.J + 1, nk = d.K + 1;
+    const size_t nN = (size_t)ni * nj * nk;
+    std::vector<float> merged(nN, std::numeric_limits<float>::max()), nodeFriction(nN, 0.0f);
+    const float far = std::numeric_limits<float>::max();
+    for (size_t s = 0; s < solids.size(); s++) {
+        const std::vector<float> &phi = *solids[s].phi;
+        const float domainBand = (float)((band + 0.5) * d.dx);
+        for (size_t q = 0; q < nN; q++) {
+            const float v = phi[q];
+            if (!(v < merged[q])) continue;
+            const bool inBand = s == 0 ? std::fabs(v) < domainBand : v != far;
+            if (inBand && std::fabs(v) < std::fabs(merged[q])) nodeFriction[q] = solids[s].friction;
+            merged[q] = v;
+        }
+    }
+    auto F = [&](int i, int j, int k) { return nodeFriction[(size_t)i + (size_t)ni * ((size_t)j + (size_t)nj * k)]; };
+    fU.resize(d.nU); fV.resize(d.nV); fW.resize(d.nW);
+    size_t idx = 0;
+    for (int k = 0; k < d.K; k++)
+        for (int j = 0; j < d.J; j++)
+            for (int i = 0; i <= d.I; i++, idx++) fU[idx] = 0.25f * (((F(i, j, k) + F(i, j + 1, k)) + F(i, j, k + 1)) + F(i, j + 1, k + 1));
+    idx = 0;
+    for (int k = 0; k < d.K; k++)
+        for (int j = 0; j <= d.J; j++)
+            for (int i = 0; i < d.I; i++, idx++) fV[idx] = 0.25f * (((F(i, j, k) + F(i + 1, j, k)) + F(i, j, k + 1)) + F(i + 1, j, k + 1));
+    idx = 0;
+    for (int k = 0; k <= d.K; k++)
+        for (int j = 0; j < d.J; j++)
+            for (int i = 0; i < d.I; i++, idx++) fW[idx] = 0.25f * (((F(i, j, k) + F(i + 1, j, k)) + F(i, j + 1, k)) + F(i + 1, j + 1, k));
 }
 
 // FluidSimulation::_updateNearSolidGrid (fluidsimulation.cpp:3083-3127): coarse cells (3dx) holding a

@@ -105,10 +105,16 @@ def load_library():
     L.flip_set_current_frame.argtypes = [vp, ci]
     L.flip_static_inputs.argtypes = [ci, ci, ci, C.c_double, vp, ci, vp, vp, vp, vp, C.POINTER(ci)]
     L.flip_center_weights.argtypes = [ci, ci, ci, C.c_double, vp, vp]
+    L.flip_face_friction.argtypes = [ci, ci, ci, C.c_double, ci, ci, vp, vp, vp, vp, vp]
+    L.flip_box_obstacle_sdf.argtypes = [ci, ci, ci, C.c_double, ci, C.POINTER(C.c_double), C.POINTER(C.c_double), vp]
     L.flip_set_solid_velocity.argtypes = [vp, vp, vp, vp]
     L.flip_add_obstacle_mesh.argtypes = [vp, vp, ci, vp, ci, C.POINTER(ci)]
     L.flip_set_obstacle_mesh_motion.argtypes = [vp, ci, vp, vp, vp]
     L.flip_mesh_velocity_data.argtypes = [ci, ci, ci, cd, vp, ci, vp, ci, vp, ci, C.c_float, vp, vp, vp, vp, vp, vp, vp]
+    L.flip_set_boundary_friction.argtypes = [vp, cd]
+    L.flip_set_obstacle_friction.argtypes = [vp, ci, cd]
+    L.flip_set_face_friction.argtypes = [vp, vp, vp, vp]
+    L.flip_get_face_friction.argtypes = [vp, vp, vp, vp]
     L.flip_set_obstacle_box_motion.argtypes = [vp, ci, C.POINTER(cd), C.POINTER(cd), C.POINTER(cd)]
     L.flip_get_num_substeps.argtypes = [vp, C.POINTER(ci)]
     L.flip_get_step_stats.argtypes = [vp, ci, C.POINTER(StepStats)]
@@ -166,6 +172,34 @@ def static_inputs(isize, jsize, ksize, dx, solid_phi=None):
     if rc != FLIP_OK:
         raise _EXC.get(rc, RuntimeError)("flip_static_inputs failed")
     return dict(solid_phi=phi, weightU=wU, weightV=wV, weightW=wW, near_solid=ns)
+
+
+def box_obstacle_sdf(dims, dx, lo, hi, band=3):
+    """flip_box_obstacle_sdf (host code): the nodal field (K+1, J+1, I+1) of a box obstacle, FLT_MAX outside its band."""
+    L = load_library()
+    I, J, K = (int(d) for d in dims)
+    phi = np.empty((K + 1, J + 1, I + 1), dtype=np.float32)
+    d3 = C.c_double * 3
+    rc = L.flip_box_obstacle_sdf(I, J, K, float(dx), int(band), d3(*lo), d3(*hi), phi.ctypes.data)
+    if rc != FLIP_OK:
+        raise _EXC.get(rc, RuntimeError)("flip_box_obstacle_sdf failed")
+    return phi
+
+
+def face_friction(dims, dx, phis, frictions, band=3):
+    """flip_face_friction (host code): dict(U, V, W) of the face friction of solids given as nodal fields in merge order
+    (phis[0]: the domain) with their frictions."""
+    L = load_library()
+    I, J, K = (int(d) for d in dims)
+    arrs = [np.ascontiguousarray(p, dtype=np.float32) for p in phis]
+    ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+    fr = np.ascontiguousarray(frictions, dtype=np.float32)
+    out = dict(U=np.empty((K, J, I + 1), np.float32), V=np.empty((K, J + 1, I), np.float32), W=np.empty((K + 1, J, I), np.float32))
+    rc = L.flip_face_friction(I, J, K, float(dx), int(band), len(arrs), ptrs, fr.ctypes.data, out["U"].ctypes.data, out["V"].ctypes.data,
+                              out["W"].ctypes.data)
+    if rc != FLIP_OK:
+        raise _EXC.get(rc, RuntimeError)("flip_face_friction failed")
+    return out
 
 
 def center_weights(dims, dx, solid_phi):
@@ -349,6 +383,29 @@ class FluidSimulation:
         """addMeshFluid(MeshObject) for a mesh that is not a box: host signed distance field -> flip_add_fluid_sdf."""
         phi, lo, hi = self.meshSDF(vertices, triangles)
         self.addMeshFluidSDF(phi, velocity, lo, hi)
+
+    def setBoundaryFriction(self, f):
+        """FluidSimulation::setBoundaryFriction (ValueError outside [0, 1])."""
+        self._check(self.L.flip_set_boundary_friction(self.h, float(f)))
+
+    def setMeshObstacleFriction(self, oid, f):
+        """MeshObject::setFriction of an obstacle."""
+        self._check(self.L.flip_set_obstacle_friction(self.h, int(oid), float(f)))
+
+    def setFaceFriction(self, U=None, V=None, W=None):
+        """flip_set_face_friction: the face friction of the constraint handed in directly; no arguments: derived again."""
+        if U is None and V is None and W is None:
+            self._check(self.L.flip_set_face_friction(self.h, None, None, None))
+            return
+        a = [np.ascontiguousarray(x, dtype=np.float32) for x in (U, V, W)]
+        for x, name in zip(a, ("solidU", "solidV", "solidW")):
+            assert x.shape == self.shape_of(name), (name, x.shape)
+        self._check(self.L.flip_set_face_friction(self.h, a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data))
+
+    def getFaceFriction(self):
+        out = {n: np.empty(self.shape_of("solid" + n), dtype=np.float32) for n in "UVW"}
+        self._check(self.L.flip_get_face_friction(self.h, out["U"].ctypes.data, out["V"].ctypes.data, out["W"].ctypes.data))
+        return out
 
     def addMeshObstacleMesh(self, vertices, triangles):
         phi, _, _ = self.meshSDF(vertices, triangles, band=3, far=3.0e38)

@@ -210,7 +210,7 @@ int flip_remove_obstacle(flip_ctx *ctx, int id);
  *     zero IN the stored arrays, as _conditionSolidVelocityField does (pressuresolver.cpp:124-244; regions of one cell
  *     are left alone, :219), on the device;
  *   - faces of zero weight take the solid's face velocity in the solid constraint (_constrainVelocityFieldThread
- *     fluidsimulation.cpp:3884-3933; friction is 0, the MeshObject default, so partly open faces keep their value).
+ *     fluidsimulation.cpp:3884-3933; partly open faces follow the friction, see flip_set_boundary_friction).
  * The SDF of a moving solid itself is the caller's (flip_add_obstacle_sdf / flip_enable_obstacle / flip_remove_obstacle per
  * substep, or flip_set_solid_sdf before flip_initialize).  Not available in a z-slab run (FLIP_ERR_UNSUPPORTED). */
 int flip_set_solid_velocity(flip_ctx *ctx, const float *U, const float *V, const float *W);
@@ -245,6 +245,26 @@ int flip_set_obstacle_mesh_motion(flip_ctx *ctx, int id, const float *vertices_p
 int flip_mesh_velocity_data(int isize, int jsize, int ksize, double dx, const float *vertices_xyz, int num_vertices, const int *triangles,
                             int num_triangles, const float *vertex_velocities_xyz, int band, float far_value, float *phi,
                             float *fractionU, float *fractionV, float *fractionW, float *fieldU, float *fieldV, float *fieldW);
+/* Friction of the solids: FluidSimulation::setBoundaryFriction (fluidsimulation.cpp:1747-1759; std::domain_error outside
+ * [0,1]) and MeshObject::setFriction of an obstacle (meshobject.cpp:300-304; clamped to [0,1]); both 0 by default.  In the
+ * solid constraint a partly open face (0 < weight < 1) becomes f u_solid + (1 - f) u (_constrainVelocityFieldThread
+ * :3895-3900) with the face friction f of _getFaceFrictionU/V/W (:3785-3853): a quarter of the sum over the face's four
+ * nodes of the friction of the solid the merged level set names as closest there (MeshLevelSet::getClosestMeshObject; the
+ * merge order and take-over rule of calculateUnion, meshlevelset.cpp:1782-1796, are restated on the host).  Re-derived
+ * with the static inputs (at flip_initialize, after a change at the next substep, every substep with animated obstacles).
+ * flip_set_face_friction hands the three face arrays in directly (MAC layout, copied; NULLs: derived again) and
+ * flip_get_face_friction reads back what the constraint uses (zeros while every friction is 0).  Not in z-slab runs. */
+int flip_set_boundary_friction(flip_ctx *ctx, double friction);
+int flip_set_obstacle_friction(flip_ctx *ctx, int id, double friction);
+int flip_set_face_friction(flip_ctx *ctx, const float *U, const float *V, const float *W);
+int flip_get_face_friction(flip_ctx *ctx, float *U, float *V, float *W);
+/* HOST utilities behind the above (no CUDA device needed; the CPU tests pin them to the reference): the face friction of
+ * num_solids solids given as nodal fields in merge order -- phis[0] the domain (defined everywhere), the others obstacle
+ * fields carrying the largest float outside their band, as flip_box_obstacle_sdf / flip_mesh_sdf(far = FLT_MAX) produce
+ * them -- with their frictions; and the nodal field of a box obstacle. */
+int flip_face_friction(int isize, int jsize, int ksize, double dx, int band, int num_solids, const float *const *phis,
+                       const float *frictions, float *fU, float *fV, float *fW);
+int flip_box_obstacle_sdf(int isize, int jsize, int ksize, double dx, int band, const double lo[3], const double hi[3], float *phi);
 /* The cell-centre weights of a nodal solid SDF, computed on the HOST exactly as the library computes them (no CUDA device
  * needed): phi (I+1)(J+1)(K+1) floats in, wC IJK floats out. */
 int flip_center_weights(int isize, int jsize, int ksize, double dx, const float *phi_nodal, float *wC);

@@ -115,6 +115,12 @@ public:
     void disable() { _enabled = false; if (_ctx) flip_enable_obstacle(_ctx, _obstacleId, 0); }
     bool isEnabled() const { return _enabled; }
     bool isAnimated() const { return _animated; }
+    // MeshObject::setFriction / getFriction (meshobject.cpp:300-308), clamped to [0, 1]
+    void setFriction(float f) {
+        _friction = std::max(0.0f, std::min(f, 1.0f));
+        if (_ctx && flip_set_obstacle_friction(_ctx, _obstacleId, _friction) != FLIP_OK) throw std::runtime_error(flip_last_error(_ctx));
+    }
+    float getFriction() const { return _friction; }
 
     void bounds(vmath::vec3 &lo, vmath::vec3 &hi) const {
         lo = vmath::vec3(1e30f, 1e30f, 1e30f); hi = vmath::vec3(-1e30f, -1e30f, -1e30f);
@@ -156,6 +162,7 @@ private:
     flip_ctx *_ctx = nullptr;     // the simulation this object is an obstacle of
     int _obstacleId = 0;
     bool _animated = false, _boxMotion = false, _addedAsBox = false;
+    float _friction = 0.0f;
     TriangleMesh _meshPrev, _meshNext;
     double _baseLo[3] = {0, 0, 0};                     // lower corner of the box the obstacle was added as
     double _prevLo[3] = {0, 0, 0}, _curLo[3] = {0, 0, 0}, _nextLo[3] = {0, 0, 0};
@@ -320,7 +327,10 @@ public:
     void removeMeshFluidSources() {                                // :1987-1992
         while (!_sources.empty()) removeMeshFluidSource(_sources.back());
     }
-    // addMeshObstacle / removeMeshObstacle (:1994-2031), static meshes: merged into the solid SDF on the device side
+    // setBoundaryFriction / getBoundaryFriction (:1743-1759): std::domain_error outside [0, 1]
+    void setBoundaryFriction(double f) { check(flip_set_boundary_friction(_c, f)); _boundaryFriction = f; }
+    double getBoundaryFriction() const { return _boundaryFriction; }
+    // addMeshObstacle / removeMeshObstacle (:1994-2031): merged into the solid SDF on the device side
     void addMeshObstacle(MeshObject *obstacle) {
         if (obstacle->_ctx == _c) throw std::runtime_error("Error: mesh obstacle has already been added.\n");
         int id = 0;
@@ -342,6 +352,7 @@ public:
             obstacle->_boxMotion = false;
         }
         obstacle->_ctx = _c; obstacle->_obstacleId = id;
+        if (obstacle->_friction != 0.0f) check(flip_set_obstacle_friction(_c, id, obstacle->_friction));
         obstacle->pushMotion();                                    // an animation set before the object was added
         _obstacles.push_back(obstacle);
         if (!obstacle->isEnabled()) check(flip_enable_obstacle(_c, id, 0));
@@ -488,6 +499,7 @@ private:
     int _minSteps = 1, _maxSteps = 6, _smoothIterations = 2;
     bool _extreme = true, _initialized = false;
     std::vector<MeshObject *> _obstacles;
+    double _boundaryFriction = 0.0;
     std::vector<MeshFluidSource *> _sources;
     MACVelocityField _mac;
     TriangleMesh _isomesh;

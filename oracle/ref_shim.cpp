@@ -579,6 +579,34 @@ int ref_animate_obstacle_mesh(void *p, int idx, const float *prev, const float *
         h->obstacles[idx]->updateMeshAnimated(meshOf(prev, nv, tris, nt), meshOf(cur, nv, tris, nt), meshOf(next, nv, tris, nt));
     });
 }
+/* setBoundaryFriction (:1747-1759), MeshObject::setFriction of obstacle `idx`, and the face friction the constraint reads
+ * (_getFaceFrictionU/V/W :3785-3853) for every face of component comp (0 U, 1 V, 2 W), in the MAC layout. */
+int ref_set_boundary_friction(void *p, double f) {
+    RefSim *h = (RefSim *)p;
+    return guarded(h, [&] { h->sim->setBoundaryFriction(f); });
+}
+int ref_set_obstacle_friction(void *p, int idx, double f) {
+    RefSim *h = (RefSim *)p;
+    return guarded(h, [&] {
+        if (idx < 0 || idx >= (int)h->obstacles.size() || !h->obstacles[idx]) throw std::runtime_error("no such obstacle");
+        h->obstacles[idx]->setFriction((float)f);
+    });
+}
+int ref_face_friction(void *p, int comp, float *out) {
+    RefSim *h = (RefSim *)p;
+    return guarded(h, [&] {
+        FluidSimulation *s = h->sim;
+        const int I = s->_isize, J = s->_jsize, K = s->_ksize;
+        const int ni = comp == 0 ? I + 1 : I, nj = comp == 1 ? J + 1 : J, nk = comp == 2 ? K + 1 : K;
+        size_t q = 0;
+        for (int k = 0; k < nk; k++)
+            for (int j = 0; j < nj; j++)
+                for (int i = 0; i < ni; i++, q++) {
+                    GridIndex g(i, j, k);
+                    out[q] = comp == 0 ? s->_getFaceFrictionU(g) : (comp == 1 ? s->_getFaceFrictionV(g) : s->_getFaceFrictionW(g));
+                }
+    });
+}
 int ref_remove_obstacle(void *p, int idx) {
     RefSim *h = (RefSim *)p;
     return guarded(h, [&] {

@@ -81,6 +81,9 @@ def _load(kind):
     L.ref_remove_obstacle.argtypes = [C.c_void_p, C.c_int]
     L.ref_add_obstacle_mesh.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
     L.ref_animate_obstacle_mesh.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    L.ref_set_boundary_friction.argtypes = [C.c_void_p, C.c_double]
+    L.ref_set_obstacle_friction.argtypes = [C.c_void_p, C.c_int, C.c_double]
+    L.ref_face_friction.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     L.ref_animate_obstacle_box.argtypes = [C.c_void_p, C.c_int] + [C.POINTER(C.c_double)] * 5
     L.ref_constrain_fluid_source_velocity.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.ref_isomesh.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
@@ -279,6 +282,21 @@ class RefEngine:
         t = np.ascontiguousarray(triangles, dtype=np.int32)
         self._check(self.L.ref_animate_obstacle_mesh(self.h, int(idx), a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data,
                                                      a[0].shape[0], t.ctypes.data, t.shape[0]))
+
+    def set_boundary_friction(self, f):
+        self._check(self.L.ref_set_boundary_friction(self.h, float(f)))
+
+    def set_obstacle_friction(self, idx, f):
+        self._check(self.L.ref_set_obstacle_friction(self.h, int(idx), float(f)))
+
+    def face_friction(self):
+        """dict(U, V, W): _getFaceFrictionU/V/W of every face (after the solid SDF has been built)."""
+        out = {}
+        for comp, n in enumerate("UVW"):
+            a = np.empty(self.shape_of("solid" + n), dtype=np.float32)
+            self._check(self.L.ref_face_friction(self.h, comp, a.ctypes.data))
+            out[n] = a
+        return out
 
     def remove_obstacle(self, idx):
         self._check(self.L.ref_remove_obstacle(self.h, int(idx)))

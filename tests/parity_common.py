@@ -57,16 +57,22 @@ def solid_velocity_field(shapes):
 
 
 def make_pair(scene, tol=None, threads=None, gravity=(0.0, -25.0, 0.0), preconditioner=None, sampling=None, obstacles=(),
-              own_solid=False, settings=None, solid_velocity=False, solid_velocity_early=False):
+              own_solid=False, settings=None, solid_velocity=False, solid_velocity_early=False, friction=None):
     """Returns (ref, gpu) engines initialised from the same scene; the GPU engine gets the oracle's
     own static solid SDF and the oracle's LOGICAL particle list.  obstacles: (lo, hi) boxes added to
     the reference with addMeshObstacle (their distances arrive with the oracle's solid SDF); own_solid: the GPU engine builds
     its solid SDF itself instead (its domain box, and the obstacles through flip_add_obstacle_box).  solid_velocity: both
     engines get the face velocities of solid_velocity_field for their solids (the reference in the VelocityDataGrid of its
-    solid SDF, the GPU engine through flip_set_solid_velocity -- before flip_initialize with solid_velocity_early)."""
+    solid SDF, the GPU engine through flip_set_solid_velocity -- before flip_initialize with solid_velocity_early).
+    friction = (boundary, [per obstacle]): setBoundaryFriction / MeshObject::setFriction on the reference; the GPU engine gets
+    the same settings with own_solid, else the reference's face friction itself (flip_set_face_friction)."""
     ref = refengine.RefEngine(scene["dims"], scene["dx"], scene["pos"], scene["vel"], gravity=gravity, threads=threads, tol=tol)
-    for lo, hi in obstacles:
-        ref.add_obstacle_box(lo, hi)
+    if friction:
+        ref.set_boundary_friction(friction[0])
+    for q, (lo, hi) in enumerate(obstacles):
+        idx = ref.add_obstacle_box(lo, hi)
+        if friction:
+            ref.set_obstacle_friction(idx, friction[1][q])
     if settings:      # dict(cfl=, picflip=, min_steps=, max_steps=): the step's settings on both engines
         ref.set_step_settings(**settings)
     ref.stage("obstacles", 1.0 / 30.0)   # builds the solid SDF / near-solid grid exactly as the first step would
@@ -93,10 +99,17 @@ def make_pair(scene, tol=None, threads=None, gravity=(0.0, -25.0, 0.0), precondi
         if settings.get("min_steps") or settings.get("max_steps"):
             gpu.setTimeStepsPerFrame(settings.get("min_steps") or 1, settings.get("max_steps") or 6)
     if own_solid:
-        for lo, hi in obstacles:
-            gpu.addMeshObstacleBox(lo, hi)
+        if friction:
+            gpu.setBoundaryFriction(friction[0])
+        for q, (lo, hi) in enumerate(obstacles):
+            oid = gpu.addMeshObstacleBox(lo, hi)
+            if friction:
+                gpu.setMeshObstacleFriction(oid, friction[1][q])
     else:
         gpu.setSolidSDF(ref.array("solid_phi"))
+        if friction:
+            F = ref.face_friction()
+            gpu.setFaceFriction(F["U"], F["V"], F["W"])
     if vel is not None and solid_velocity_early:
         gpu.setSolidVelocity(vel["U"], vel["V"], vel["W"])
     gpu.initialize()
@@ -284,10 +297,11 @@ def developed_scene(scene, frames, preconditioner=None):
 
 
 def lockstep_frames(scene, frames=1, isolate=True, tol=None, threads=None, preconditioner=None, verbose=False,
-                    sampling=None, max_substeps=None, obstacles=(), own_solid=False, settings=None, solid_velocity=False):
+                    sampling=None, max_substeps=None, obstacles=(), own_solid=False, settings=None, solid_velocity=False,
+                    friction=None):
     """max_substeps: stop after that many lock-step substeps in total (the large scenes cost tens of CPU seconds each)."""
     ref, gpu = make_pair(scene, tol=tol, threads=threads, preconditioner=preconditioner, sampling=sampling, obstacles=obstacles,
-                         own_solid=own_solid, settings=settings, solid_velocity=solid_velocity)
+                         own_solid=own_solid, settings=settings, solid_velocity=solid_velocity, friction=friction)
     reports = []
     for f in range(frames):
         ref.begin_frame(1.0 / 30.0)

@@ -133,3 +133,37 @@ def test_mesh_velocity_data_equals_the_reference():
         assert np.abs(u - want).max() <= 5e-6, (n, float(np.abs(u - want).max()))         # measured: 2.4e-7
     assert seen > 1.5           # the turning wedge's surface moves at up to 1.9 units/s
     ref.close()
+
+
+_FRICTION_BOXES = [((12.3 * 0.125, 0.0, 6.2 * 0.125), (16.7 * 0.125, 9.4 * 0.125, 25.9 * 0.125)),                    # a wall across the flow
+                   ((20.27 * 0.125, 5.52 * 0.125, 12.13 * 0.125), (24.91 * 0.125, 11.64 * 0.125, 19.86 * 0.125)),    # a block above the floor
+                   ((14.93 * 0.125, 6.31 * 0.125, 9.44 * 0.125), (19.58 * 0.125, 12.17 * 0.125, 15.62 * 0.125)),     # ... one that overlaps the wall
+                   ((22.41 * 0.125, 0.0, 3.37 * 0.125), (29.83 * 0.125, 4.56 * 0.125, 9.12 * 0.125))]                # a step into the domain walls
+_FRICTIONS = (0.35, [0.7, 0.2, 0.45, 0.9])
+
+
+@needs_ref
+def test_face_friction_equals_the_reference_where_the_constraint_reads_it():
+    """flip_face_friction (host code; the merge order and take-over rule of MeshLevelSet::calculateUnion restated) against
+    _getFaceFrictionU/V/W of the reference for a domain with boundary friction and four boxes of different friction, two
+    of them overlapping and one reaching into the domain walls: equal on every partly open face (the only faces whose
+    friction the constraint reads, fluidsimulation.cpp:3895)."""
+    sc = scenes.dam_break(32)
+    dx = sc["dx"]
+    I, J, K = sc["dims"]
+    ref = refengine.RefEngine(sc["dims"], dx, sc["pos"][:8], sc["vel"][:8])
+    ref.set_boundary_friction(_FRICTIONS[0])
+    for (lo, hi), f in zip(_FRICTION_BOXES, _FRICTIONS[1]):
+        ref.set_obstacle_friction(ref.add_obstacle_box(lo, hi), f)
+    ref.stage("obstacles", 1.0 / 30.0)
+    ref.update_weight_grid()
+    want = ref.face_friction()
+    phis = [fe.static_inputs(I, J, K, dx)["solid_phi"]] + [fe.box_obstacle_sdf(sc["dims"], dx, lo, hi) for lo, hi in _FRICTION_BOXES]
+    mine = fe.face_friction(sc["dims"], dx, phis, [_FRICTIONS[0]] + list(_FRICTIONS[1]))
+    for n in "UVW":
+        w = ref.array("weight" + n)
+        partial = (w > 0) & (w < 1)
+        assert partial.sum() > 3000
+        assert len(np.unique(want[n][partial])) >= 10           # blends of the five frictions around edges and overlaps
+        assert np.array_equal(mine[n][partial], want[n][partial]), (n, int(np.count_nonzero(mine[n][partial] != want[n][partial])))
+    ref.close()

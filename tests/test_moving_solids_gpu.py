@@ -200,3 +200,61 @@ def test_animated_mesh_obstacle_against_reference():
     assert vmax > 1.3
     ref.close()
     gpu.close()
+
+
+_FRICTION_BOXES = [((12.3 * 0.125, 0.0, 6.2 * 0.125), (16.7 * 0.125, 9.4 * 0.125, 25.9 * 0.125)),
+                   ((20.27 * 0.125, 5.52 * 0.125, 12.13 * 0.125), (24.91 * 0.125, 11.64 * 0.125, 19.86 * 0.125)),
+                   ((14.93 * 0.125, 6.31 * 0.125, 9.44 * 0.125), (19.58 * 0.125, 12.17 * 0.125, 15.62 * 0.125)),
+                   ((22.41 * 0.125, 0.0, 3.37 * 0.125), (29.83 * 0.125, 4.56 * 0.125, 9.12 * 0.125))]
+_FRICTIONS = (0.35, [0.7, 0.2, 0.45, 0.9])
+
+
+@needs_ref
+def test_lockstep_with_friction():
+    """Boundary and obstacle friction (setBoundaryFriction, MeshObject::setFriction): every stage from identical inputs over
+    eight frames of the dam break running into the obstacles; the constrained field -- partly open faces blended towards
+    the solid with the face friction, fluidsimulation.cpp:3895-3900 -- bit for bit (check_report), here with the reference's
+    own face friction handed over through flip_set_face_friction."""
+    sc = scenes.dam_break(32)
+    reps = pc.lockstep_frames(sc, frames=8, isolate=True, obstacles=_FRICTION_BOXES, friction=_FRICTIONS)
+    assert len(reps) >= 8
+    for rep in reps:
+        pc.check_report(rep, dx=sc["dx"], isolate=True)
+
+
+@needs_ref
+def test_friction_through_the_api_against_reference():
+    """flip_set_boundary_friction / flip_set_obstacle_friction with the library's own solids: the derived face friction equals
+    the reference's on every partly open face, and the free-running simulations stay together (friction slows the flow
+    along the floor and the obstacles: without it the positions differ by orders of magnitude more)."""
+    sc = scenes.dam_break(32)
+    ref, gpu = pc.make_pair(sc, obstacles=_FRICTION_BOXES, own_solid=True, friction=_FRICTIONS)
+    ref.update_weight_grid()
+    want, mine = ref.face_friction(), gpu.getFaceFriction()
+    for n in "UVW":
+        w = ref.array("weight" + n)
+        partial = (w > 0) & (w < 1)
+        assert np.array_equal(mine[n][partial], want[n][partial]), (n, int(np.count_nonzero(mine[n][partial] != want[n][partial])))
+    plain_ref, plain_gpu = pc.make_pair(sc, obstacles=_FRICTION_BOXES, own_solid=True)
+    for f in range(6):
+        ref.update(1.0 / 30.0)
+        gpu.update(1.0 / 30.0)
+        plain_gpu.update(1.0 / 30.0)
+        st = gpu.substep_stats()
+        assert ref.substeps == len(st), (f, ref.substeps, len(st))
+        assert abs(ref.num_particles - st[-1]["particles"]) <= 4, (f, ref.num_particles, st[-1]["particles"])
+        assert all(s["pcg_converged"] == 1 for s in st), st
+        p, ids = pc.particles_by_id(gpu)
+        a = ref.particles()
+        if p.shape[0] == a.shape[0]:
+            err = pc.rel_l2(p[np.argsort(ids), :3], a[:, :3])
+            assert err <= 2e-3, (f, err)
+    # friction matters in this scene: the frictionless run has drifted much further from the reference than the run with it
+    q, qids = pc.particles_by_id(plain_gpu)
+    a = ref.particles()
+    if q.shape[0] == a.shape[0] and p.shape[0] == a.shape[0]:
+        with_f = pc.rel_l2(p[np.argsort(ids), :3], a[:, :3])
+        without = pc.rel_l2(q[np.argsort(qids), :3], a[:, :3])
+        assert without > 3.0 * with_f, (with_f, without)
+    for e in (ref, gpu, plain_ref, plain_gpu):
+        e.close()
