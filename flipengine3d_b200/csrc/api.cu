@@ -769,7 +769,7 @@ static void update_animated_obstacles(flip_ctx *c) {
             for (int q = 0; q < n[m]; q++) { weightSum[m][q] += md.fraction[m][q]; fieldSum[m][q] += md.field[m][q]; }
     if (!c->solU) {
         dev_alloc(c->solU, d.nU); dev_alloc(c->solV, d.nV); dev_alloc(c->solW, d.nW);
-        dev_alloc(c->pocketFlag, d.nC);
+        if (!c->pocketFlag) dev_alloc(c->pocketFlag, d.nC);     // (kept when the velocities are withdrawn)
     }
     float *sol[3] = {c->solU, c->solV, c->solW};
     for (int m = 0; m < 3; m++) {
@@ -826,7 +826,7 @@ int flip_set_solid_velocity(flip_ctx *c, const float *U, const float *V, const f
         if (slab_on(c)) throw ApiError(FLIP_ERR_UNSUPPORTED, "solid velocities are not supported in a z-slab run");
         if (!c->solU) {
             dev_alloc(c->solU, d.nU); dev_alloc(c->solV, d.nV); dev_alloc(c->solW, d.nW);
-            dev_alloc(c->pocketFlag, d.nC);
+            if (!c->pocketFlag) dev_alloc(c->pocketFlag, d.nC);     // (kept when the velocities are withdrawn)
         }
         FLIP_CUDA_CHECK(cudaMemcpy(c->solU, U, sizeof(float) * d.nU, cudaMemcpyHostToDevice));
         FLIP_CUDA_CHECK(cudaMemcpy(c->solV, V, sizeof(float) * d.nV, cudaMemcpyHostToDevice));
