@@ -167,3 +167,54 @@ def test_face_friction_equals_the_reference_where_the_constraint_reads_it():
         assert len(np.unique(want[n][partial])) >= 10           # blends of the five frictions around edges and overlaps
         assert np.array_equal(mine[n][partial], want[n][partial]), (n, int(np.count_nonzero(mine[n][partial] != want[n][partial])))
     ref.close()
+
+
+_BOX_TRIANGLES = np.array([[0, 1, 2], [0, 2, 3], [4, 7, 6], [4, 6, 5], [0, 3, 7], [0, 7, 4], [1, 5, 6], [1, 6, 2], [0, 4, 5], [0, 5, 1],
+                           [3, 2, 6], [3, 6, 7]], dtype=np.int32)
+
+
+def _box_vertices(lo, hi):
+    (x0, y0, z0), (x1, y1, z1) = lo, hi
+    return np.array([[x0, y0, z0], [x1, y0, z0], [x1, y0, z1], [x0, y0, z1], [x0, y1, z0], [x1, y1, z0], [x1, y1, z1], [x0, y1, z1]],
+                    dtype=np.float32)
+
+
+@needs_ref
+def test_box_obstacle_field_equals_the_reference_level_set_of_the_box_mesh():
+    """flip_box_obstacle_sdf (the analytic box distances the library gives a box obstacle, and every substep an animated
+    one) against MeshLevelSet::fastCalculateSignedDistanceField of the twelve-triangle box mesh: the same sign wherever both
+    computed a distance, the same value within 2e-4 dx near the surface -- for a box inside the domain and one cut by it."""
+    dims, dx = (32, 32, 32), 0.125
+    for lo, hi in (((1.56, 0.22, 0.81), (1.96, 1.63, 3.17)), ((2.81, -0.4, 1.13), (4.3, 0.97, 2.26))):
+        mine = fe.box_obstacle_sdf(dims, dx, lo, hi, band=3)
+        want = refengine.mesh_level_set(dims, dx, _box_vertices(lo, hi), _BOX_TRIANGLES, band=3)
+        both = (mine < 1e30) & (np.abs(want) < 3.0 * dx)
+        assert both.sum() > 1500
+        assert np.array_equal(mine[both] < 0, want[both] < 0)
+        near = both & (np.abs(want) < 2.5 * dx)
+        assert np.abs(mine[near] - want[near]).max() <= 2e-4 * dx, np.abs(mine[near] - want[near]).max() / dx
+
+
+def test_mesh_velocity_data_of_a_mesh_at_rest_and_bad_input():
+    """Host code, no oracle: a mesh whose vertices do not move adds solid fractions and no velocity (the reference's
+    isStatic branch, meshlevelset.cpp:1410-1417); its fractions are 1 - the face weights flip_static_inputs derives from the
+    same field; a triangle that names a vertex out of range is refused."""
+    dims, dx = (24, 24, 24), 0.125
+    v = scenes.wedge_vertices((1.5, 1.4, 1.5), 0.3)
+    md = fe.mesh_velocity_data(dims, dx, v, scenes.WEDGE_TRIANGLES, np.zeros_like(v), band=3, far=3.0e38)
+    for n in "UVW":
+        assert not md["field" + n].any()
+        assert md["fraction" + n].max() == 1.0 and md["fraction" + n].min() == 0.0
+    w = fe.static_inputs(*dims, dx, solid_phi=md["phi"])
+    for n in "UVW":
+        assert np.abs((1.0 - w["weight" + n]) - md["fraction" + n]).max() <= 1e-6, n
+    bad = scenes.WEDGE_TRIANGLES.copy()
+    bad[3, 1] = 17
+    with pytest.raises(IndexError):
+        fe.mesh_velocity_data(dims, dx, v, bad, np.zeros_like(v))
+    # a uniform translation: every face with a positive fraction carries fraction x that velocity
+    vel = np.tile(np.array([[0.4, -0.7, 0.25]], dtype=np.float32), (v.shape[0], 1))
+    md = fe.mesh_velocity_data(dims, dx, v, scenes.WEDGE_TRIANGLES, vel, band=3, far=3.0e38)
+    for c, n in enumerate("UVW"):
+        fr, fl = md["fraction" + n], md["field" + n]
+        assert np.abs(fl - fr * vel[0, c]).max() <= 2e-6, n
