@@ -465,30 +465,43 @@ extern "C" int flip_mesh_sdf(int isize, int jsize, int ksize, double dx, const f
 // (_pointToSegmentVelocity :1696-1714).
 namespace {
 inline float length3(V3 a) { return std::sqrt(dot3(a, a)); }
-V3 segment_velocity(V3 x0, V3 x1, V3 x2, V3 v1, V3 v2, float *distance) {
-    const V3 dxs = x2 - x1;
-    const double m2 = dot3(dxs, dxs);
-    float s12 = (float)(dot3(x2 - x0, dxs) / m2);
-    s12 = s12 < 0 ? 0 : (s12 > 1 ? 1 : s12);
-    *distance = length3(x0 - (s12 * x1 + (1 - s12) * x2));
-    return s12 * v1 + (1 - s12) * v2;
+// velocity at the point of the segment pa-pb nearest to p, blended from the end velocities; *distance: how far that is
+V3 segment_velocity(V3 p, V3 pa, V3 pb, V3 va, V3 vb, float *distance) {
+    const V3 along = pb - pa;
+    const double len2 = dot3(along, along);
+    float towardsA = (float)(dot3(pb - p, along) / len2);      // 1 at pa, 0 at pb
+    towardsA = towardsA < 0 ? 0 : (towardsA > 1 ? 1 : towardsA);
+    *distance = length3(p - (towardsA * pa + (1 - towardsA) * pb));
+    return towardsA * va + (1 - towardsA) * vb;
 }
-V3 triangle_velocity(V3 x0, V3 x1, V3 x2, V3 x3, V3 v1, V3 v2, V3 v3) {
-    const float eps = 1e-6f;
-    auto still = [&](V3 v) { return std::fabs(v.x) < eps && std::fabs(v.y) < eps && std::fabs(v.z) < eps; };
-    if (still(v1) && still(v2) && still(v3)) return {0, 0, 0};
-    const V3 x13 = x1 - x3, x23 = x2 - x3, x03 = x0 - x3;
-    const float m13 = dot3(x13, x13), m23 = dot3(x23, x23), d = dot3(x13, x23);
-    const float invdet = 1.0f / std::fmax(m13 * m23 - d * d, 1e-30f);
-    const float a = dot3(x13, x03), b = dot3(x23, x03);
-    const float w23 = invdet * (m23 * a - d * b), w31 = invdet * (m13 * b - d * a), w12 = 1 - w23 - w31;
-    if (w23 >= 0 && w31 >= 0 && w12 >= 0) return w23 * v1 + w31 * v2 + w12 * v3;
-    float d1, d2;
-    V3 e1, e2;
-    if (w23 > 0) { e1 = segment_velocity(x0, x1, x2, v1, v2, &d1); e2 = segment_velocity(x0, x1, x3, v1, v3, &d2); }
-    else if (w31 > 0) { e1 = segment_velocity(x0, x1, x2, v1, v2, &d1); e2 = segment_velocity(x0, x2, x3, v2, v3, &d2); }
-    else { e1 = segment_velocity(x0, x1, x3, v1, v3, &d1); e2 = segment_velocity(x0, x2, x3, v2, v3, &d2); }
-    return d1 < d2 ? e1 : e2;
+// corner[3], cornerVel[3]: a triangle and the velocities of its corners
+V3 triangle_velocity(V3 p, const V3 corner[3], const V3 cornerVel[3]) {
+    const float tiny = 1e-6f;
+    bool atRest = true;
+    for (int c = 0; c < 3; c++)
+        atRest = atRest && std::fabs(cornerVel[c].x) < tiny && std::fabs(cornerVel[c].y) < tiny && std::fabs(cornerVel[c].z) < tiny;
+    if (atRest) return {0, 0, 0};
+    // barycentric weights of the projection of p onto the triangle's plane, with corner 2 as the origin
+    const V3 e0 = corner[0] - corner[2], e1 = corner[1] - corner[2], rel = p - corner[2];
+    const float g00 = dot3(e0, e0), g11 = dot3(e1, e1), g01 = dot3(e0, e1);
+    const float scale = 1.0f / std::fmax(g00 * g11 - g01 * g01, 1e-30f);
+    const float r0 = dot3(e0, rel), r1 = dot3(e1, rel);
+    float bary[3];
+    bary[0] = scale * (g11 * r0 - g01 * r1);
+    bary[1] = scale * (g00 * r1 - g01 * r0);
+    bary[2] = 1 - bary[0] - bary[1];
+    if (bary[0] >= 0 && bary[1] >= 0 && bary[2] >= 0) return bary[0] * cornerVel[0] + bary[1] * cornerVel[1] + bary[2] * cornerVel[2];
+    // outside: the nearer of the two edges at the first corner with a positive weight (its opposite edge is ruled out);
+    // with neither of the first two positive, the two edges at corner 2
+    static const int edges[3][2][2] = {{{0, 1}, {0, 2}}, {{0, 1}, {1, 2}}, {{0, 2}, {1, 2}}};
+    const int which = bary[0] > 0 ? 0 : (bary[1] > 0 ? 1 : 2);
+    float dist[2];
+    V3 cand[2];
+    for (int e = 0; e < 2; e++) {
+        const int a = edges[which][e][0], b = edges[which][e][1];
+        cand[e] = segment_velocity(p, corner[a], corner[b], cornerVel[a], cornerVel[b], &dist[e]);
+    }
+    return dist[0] < dist[1] ? cand[0] : cand[1];
 }
 }  // namespace
 
@@ -525,7 +538,8 @@ int mesh_velocity_data(const Dims &d, const float *vertices_xyz, int num_vertice
         }
         if (tri < 0) return {0, 0, 0};
         const int *q = triangles + 3 * tri;
-        return triangle_velocity(p, vert[q[0]], vert[q[1]], vert[q[2]], vel[q[0]], vel[q[1]], vel[q[2]]);
+        const V3 corner[3] = {vert[q[0]], vert[q[1]], vert[q[2]]}, cornerVel[3] = {vel[q[0]], vel[q[1]], vel[q[2]]};
+        return triangle_velocity(p, corner, cornerVel);
     };
     // only the faces of the mesh's index box grown by the band can have a positive fraction
     const int i0 = clo[0], i1 = std::min(chi[0], d.I), j0 = clo[1], j1 = std::min(chi[1], d.J), k0 = clo[2], k1 = std::min(chi[2], d.K);
