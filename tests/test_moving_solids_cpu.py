@@ -218,3 +218,37 @@ def test_mesh_velocity_data_of_a_mesh_at_rest_and_bad_input():
     for c, n in enumerate("UVW"):
         fr, fl = md["fraction" + n], md["field" + n]
         assert np.abs(fl - fr * vel[0, c]).max() <= 2e-6, n
+
+
+@needs_ref
+def test_restated_constraint_with_solid_velocities_and_friction_equals_the_reference():
+    """oracle/restatement.constrain with solid velocities and friction against the reference's _constrainVelocityFields on a
+    developed flow (boundary friction, four boxes of different friction, a smooth solid velocity field): bit for bit."""
+    sc = scenes.dam_break(32)
+    ref = refengine.RefEngine(sc["dims"], sc["dx"], sc["pos"], sc["vel"])
+    ref.set_boundary_friction(_FRICTIONS[0])
+    for (lo, hi), f in zip(_FRICTION_BOXES, _FRICTIONS[1]):
+        ref.set_obstacle_friction(ref.add_obstacle_box(lo, hi), f)
+    ref.stage("obstacles", 1.0 / 30.0)
+    vel = pc.solid_velocity_field({n: ref.shape_of("solid" + n) for n in "UVW"})
+    for n in "UVW":
+        ref.set_array("solid" + n, vel[n])
+    for _ in range(4):
+        ref.update(1.0 / 30.0)
+    ref.begin_frame(1.0 / 30.0)
+    dt = ref.begin_substep()
+    for st in ("obstacles", "liquid_sdf", "p2g", "extrapolate_a", "save", "body_force", "pressure", "extrapolate_b"):
+        ref.stage(st, dt)
+    before = {n: ref.array(n) for n in "UVW"}
+    saved = {n: ref.array("saved" + n) for n in "UVW"}
+    solid = {n: ref.array("solid" + n) for n in "UVW"}          # as the pocket conditioning of this substep left them
+    fric = ref.face_friction()
+    ref.stage("constrain", dt)
+    changed = 0
+    for n in "UVW":
+        w = ref.array("weight" + n)
+        assert np.array_equal(rs.constrain(before[n], w, solid[n], fric[n]), ref.array(n)), n
+        assert np.array_equal(rs.constrain(saved[n], w, solid[n], fric[n]), ref.array("saved" + n)), n
+        changed += int(np.count_nonzero((ref.array(n) != before[n]) & (w > 0) & (w < 1)))
+    assert changed > 500            # the friction blend acted on the partly open faces
+    ref.close()
